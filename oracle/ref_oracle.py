@@ -1,0 +1,256 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_ref/libfpohm_ref.so — the reference's own
+sources (octree.cpp, voxelization.cpp, global_functions.cpp, metro_hausdorff.cpp + vendored geogram /
+libigl / VCG) compiled in place by oracle/ref/Makefile, behind the extern "C" driver oracle/ref/ref_driver.cpp.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "_ref" / "libfpohm_ref.so"
+
+_lib = None
+
+
+def available() -> bool:
+    return LIB_PATH.exists()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} missing: run `make -C oracle/ref` where /root/reference exists")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.ref_octree_build.restype = C.c_void_p
+        _lib.ref_octree_random.restype = C.c_void_p
+        _lib.ref_octree_from_marks.restype = C.c_void_p
+        _lib.ref_compute_octree.restype = C.c_void_p
+        _lib.ref_dexel_sign.restype = C.c_void_p
+        _lib.ref_tree_build.restype = C.c_void_p
+        _lib.ref_hex_connectivity.restype = C.c_void_p
+        _lib.ref_tree_num_edges.restype = C.c_int64
+        _lib.ref_tree_num_nodes.restype = C.c_int64
+        _lib.ref_conn_csr.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def num_cores() -> int:
+    return lib().ref_num_cores()
+
+
+def octree_grid_setup(V, F, num_voxels: int):
+    V, F = _f64(V), _i32(F)
+    gs = np.zeros(3, np.int32); o = np.zeros(3); mt = np.zeros(3); vs = C.c_double()
+    lib().ref_octree_grid_setup(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.c_int(num_voxels),
+                                _p(gs), _p(o), _p(mt), C.byref(vs))
+    return gs, o, mt, vs.value
+
+
+class RefOctree:
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+
+    @classmethod
+    def build(cls, V, F, grid_size, origin, mesh_transform, voxel_size, stop_extent, graded=True, paired=True):
+        V, F = _f64(V), _i32(F)
+        gs, o, mt = _i32(grid_size), _f64(origin), _f64(mesh_transform)
+        h = lib().ref_octree_build(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(gs), _p(o), _p(mt),
+                                   C.c_double(voxel_size), C.c_int(stop_extent), C.c_int(graded), C.c_int(paired))
+        return cls(h)
+
+    @classmethod
+    def random(cls, grid_size, graded=True, paired=True):
+        gs = _i32(grid_size)
+        return cls(lib().ref_octree_random(_p(gs), C.c_int(graded), C.c_int(paired)))
+
+    @classmethod
+    def from_marks(cls, grid_size, marks, graded=True, paired=True):
+        gs, m = _i32(grid_size), _i32(marks).reshape(-1, 4)
+        return cls(lib().ref_octree_from_marks(_p(gs), _p(m), C.c_int64(len(m)), C.c_int(graded), C.c_int(paired)))
+
+    def refine(self, cells, stop_extent):
+        c = _i32(cells)
+        lib().ref_octree_refine(self.h, _p(c), C.c_int64(len(c)), C.c_int(stop_extent))
+
+    def sizes(self):
+        nn, nc, nl = C.c_int64(), C.c_int64(), C.c_int64(); nr, md = C.c_int32(), C.c_int32()
+        lib().ref_octree_sizes(self.h, C.byref(nn), C.byref(nc), C.byref(nl), C.byref(nr), C.byref(md))
+        return dict(nodes=nn.value, cells=nc.value, leaves=nl.value, roots=nr.value, max_depth=md.value)
+
+    def export(self):
+        s = self.sizes()
+        node_pos = np.zeros((s["nodes"], 3), np.int32); node_neigh = np.zeros((s["nodes"], 6), np.int32)
+        first_child = np.zeros(s["cells"], np.int32); corner = np.zeros((s["cells"], 8), np.int32)
+        neigh = np.zeros((s["cells"], 6), np.int32)
+        lib().ref_octree_export(self.h, _p(node_pos), _p(node_neigh), _p(first_child), _p(corner), _p(neigh))
+        return dict(node_pos=node_pos, node_neigh=node_neigh, first_child=first_child, corner=corner, neigh=neigh, **s)
+
+    def flags(self):
+        f = lib().ref_octree_flags(self.h)
+        return bool(f & 1), bool(f & 2)
+
+    def cell_sign(self, origin, spacing):
+        s = self.sizes(); o = _f64(origin)
+        inside = np.zeros(s["cells"], np.float32)
+        lib().ref_octree_cell_sign(self.h, _p(o), C.c_double(spacing), _p(inside))
+        return inside
+
+    def hexes(self):
+        s = self.sizes()
+        Vp = np.zeros((s["nodes"], 3)); hexa = np.zeros((s["leaves"], 8), np.uint32); h2c = np.zeros(s["leaves"], np.int32)
+        lib().ref_octree_hexes(self.h, _p(Vp), _p(hexa), _p(h2c))
+        return Vp, hexa, h2c
+
+    def __del__(self):
+        if self.h and _lib is not None:
+            _lib.ref_octree_free(self.h)
+            self.h = None
+
+
+def compute_octree(V, F, min_corner, extent, spacing, padding=0, graded=True, paired=True):
+    V, F = _f64(V), _i32(F); mc, ex = _f64(min_corner), _f64(extent)
+    nv, nh = C.c_int64(), C.c_int64()
+    h = C.c_void_p(lib().ref_compute_octree(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(mc), _p(ex),
+                                            C.c_double(spacing), C.c_int(padding), C.c_int(graded), C.c_int(paired),
+                                            C.byref(nv), C.byref(nh)))
+    Vp = np.zeros((nv.value, 3)); hexa = np.zeros((nh.value, 8), np.uint32); inside = np.zeros(nh.value, np.float32)
+    lib().ref_compute_octree_export(h, _p(Vp), _p(hexa), _p(inside))
+    lib().ref_compute_octree_free(h)
+    return Vp, hexa, inside
+
+
+def voxel_sign(V, F, origin, extent, spacing, padding=0):
+    V, F = _f64(V), _i32(F); o, ex = _f64(origin), _f64(extent)
+    dims = np.zeros(3, np.int32)
+    lib().ref_voxel_dims(_p(ex), C.c_double(spacing), C.c_int(padding), _p(dims))
+    out = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.uint8)
+    lib().ref_voxel_sign(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(o), _p(ex), C.c_double(spacing),
+                         C.c_int(padding), _p(out))
+    return out.reshape(dims[2], dims[1], dims[0]), dims
+
+
+def dexel_sign(V, F, origin, extent, spacing, padding=0):
+    V, F = _f64(V), _i32(F); o, ex = _f64(origin), _f64(extent)
+    dims = np.zeros(2, np.int32); tot = C.c_int64()
+    h = C.c_void_p(lib().ref_dexel_sign(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(o), _p(ex),
+                                        C.c_double(spacing), C.c_int(padding), _p(dims), C.byref(tot)))
+    off = np.zeros(int(dims[0]) * int(dims[1]) + 1, np.int64); val = np.zeros(tot.value)
+    lib().ref_dexel_export(h, _p(off), _p(val))
+    lib().ref_dexel_free(h)
+    return off, val, dims
+
+
+class RefTree:
+    def __init__(self, V, F):
+        self.V, self.F = _f64(V), _i32(F)
+        self.h = C.c_void_p(lib().ref_tree_build(_p(self.V), C.c_int64(len(self.V)), _p(self.F), C.c_int64(len(self.F))))
+
+    def normals(self):
+        nE = lib().ref_tree_num_edges(self.h)
+        FN = np.zeros((len(self.F), 3)); VN = np.zeros((len(self.V), 3)); EN = np.zeros((nE, 3))
+        E = np.zeros((nE, 2), np.int32); EMAP = np.zeros(3 * len(self.F), np.int32)
+        lib().ref_tree_normals(self.h, _p(FN), _p(VN), _p(EN), _p(E), _p(EMAP))
+        return FN, VN, EN, E, EMAP
+
+    def flatten(self):
+        n = lib().ref_tree_num_nodes(self.h)
+        box = np.zeros((n, 6)); prim = np.zeros(n, np.int32); lr = np.zeros((n, 2), np.int32)
+        lib().ref_tree_flatten(self.h, _p(box), _p(prim), _p(lr))
+        return box, prim, lr
+
+    def signed_distance(self, P):
+        P = _f64(P); n = len(P)
+        S = np.zeros(n); I = np.zeros(n, np.int32); Cc = np.zeros((n, 3)); N = np.zeros((n, 3))
+        lib().ref_signed_distance(self.h, _p(P), C.c_int64(n), _p(S), _p(I), _p(Cc), _p(N))
+        return S, I, Cc, N
+
+    def __del__(self):
+        if self.h and _lib is not None:
+            _lib.ref_tree_free(self.h)
+            self.h = None
+
+
+def point_mesh_sqdist(V, F, P):
+    V, F, P = _f64(V), _i32(F), _f64(P); n = len(P)
+    D = np.zeros(n); I = np.zeros(n, np.int32); Cc = np.zeros((n, 3))
+    lib().ref_point_mesh_sqdist(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(P), C.c_int64(n), _p(D), _p(I), _p(Cc))
+    return D, I, Cc
+
+
+def points_inside_mesh(V, F, P):
+    V, F, P = _f64(V), _i32(F), _f64(P); n = len(P)
+    S = np.zeros(n)
+    lib().ref_points_inside_mesh(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), _p(P), C.c_int64(n), _p(S))
+    return S
+
+
+def polyline_project(V, curve_off, curve_vs, circle, P, curve_id):
+    V, P = _f64(V), _f64(P)
+    co = np.ascontiguousarray(curve_off, np.int64); cv = _i32(curve_vs); ci = np.ascontiguousarray(circle, np.uint8)
+    cid = _i32(curve_id); n = len(P)
+    oL = np.zeros((n, 3)); aL = np.zeros((n, 3))
+    lib().ref_polyline_project(_p(V), C.c_int64(len(V)), _p(co), _p(cv), _p(ci), _p(P), _p(cid), C.c_int64(n), _p(oL), _p(aL))
+    return oL, aL
+
+
+def scaled_jacobian(V, hexa):
+    V = _f64(V); hexa = np.ascontiguousarray(hexa, np.uint32); H = len(hexa)
+    VJ = np.zeros(8 * H); HJ = np.zeros(H); mad = np.zeros(3); fl = C.c_int64()
+    lib().ref_scaled_jacobian(_p(V), C.c_int64(len(V)), _p(hexa), C.c_int64(H), _p(VJ), _p(HJ), _p(mad), C.byref(fl))
+    return VJ, HJ, mad, fl.value
+
+
+def hex_connectivity(hexa, nV):
+    hexa = np.ascontiguousarray(hexa, np.uint32); H = len(hexa)
+    nF, nE = C.c_int64(), C.c_int64()
+    h = C.c_void_p(lib().ref_hex_connectivity(_p(hexa), C.c_int64(H), C.c_int64(nV), C.byref(nF), C.byref(nE)))
+    nF, nE = nF.value, nE.value
+    out = dict(F_vs=np.zeros((nF, 4), np.uint32), F_es=np.zeros((nF, 4), np.uint32), F_boundary=np.zeros(nF, np.uint8),
+               E_vs=np.zeros((nE, 2), np.uint32), E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8),
+               H_fs=np.zeros((H, 6), np.uint32))
+    lib().ref_conn_fixed(h, _p(out["F_vs"]), _p(out["F_es"]), _p(out["F_boundary"]), _p(out["E_vs"]), _p(out["E_boundary"]),
+                         _p(out["V_boundary"]), _p(out["H_fs"]))
+    names = ["F_nhs", "E_nfs", "E_nhs", "V_nvs", "V_nes", "V_nfs", "V_nhs"]
+    sizes = [nF, nE, nE, nV, nV, nV, nV]
+    for which, (nm, n) in enumerate(zip(names, sizes)):
+        tot = lib().ref_conn_csr(h, C.c_int(which), None, None)
+        off = np.zeros(n + 1, np.int64); val = np.zeros(tot, np.uint32)
+        lib().ref_conn_csr(h, C.c_int(which), _p(off), _p(val))
+        out[nm] = (off, val)
+    lib().ref_conn_free(h)
+    return out
+
+
+def hausdorff(VA, FA, VB, FB):
+    VA, FA, VB, FB = _f64(VA), _i32(FA), _f64(VB), _i32(FB)
+    out = np.zeros(3)
+    lib().ref_hausdorff(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)), _p(FB),
+                        C.c_int64(len(FB)), _p(out))
+    return dict(diag=out[0], max=out[1], mean=out[2])
+
+
+def hausdorff_ratio(VA, FA, VB, FB, thr):
+    VA, FA, VB, FB = _f64(VA), _i32(FA), _f64(VB), _i32(FB)
+    r = C.c_double()
+    ok = lib().ref_hausdorff_ratio(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)),
+                                   _p(FB), C.c_int64(len(FB)), C.c_double(thr), C.byref(r))
+    return bool(ok), r.value
