@@ -1,0 +1,331 @@
+"""ctypes binding of libfpohm.so + thin host classes that mirror the reference's interface names.
+
+Nothing here computes: every function marshals numpy arrays (or raw device pointers for the `_dev`
+variants) into the extern "C" entry points of include/fpohm.h.  If the shared library is missing the
+import of this module raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+__all__ = [
+    "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice",
+]
+
+LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
+_lib = None
+
+
+class FpohmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fpohm error {code}: {msg}")
+        self.code = code
+
+
+class _OctreeParams(C.Structure):
+    _fields_ = [("grid_size", C.c_int32 * 3), ("origin", C.c_double * 3), ("mesh_transform", C.c_double * 3),
+                ("voxel_size", C.c_double), ("stop_extent", C.c_int32), ("graded", C.c_int32), ("paired", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                              "there is no CPU fallback")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.fpohm_last_error.restype = C.c_char_p
+        _lib.fpohm_version.restype = C.c_char_p
+    return _lib
+
+
+def _chk(rc: int):
+    if rc != 0:
+        raise FpohmError(rc, lib().fpohm_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def device_count() -> int:
+    return lib().fpohm_device_count()
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = C.c_void_p()
+        _chk(lib().fpohm_ctx_create(C.c_int(device), C.byref(self.h)))
+        self.device = device
+
+    def sync(self):
+        _chk(lib().fpohm_ctx_sync(self.h))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_double()
+        _chk(lib().fpohm_ctx_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _chk(lib().fpohm_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().fpohm_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TriMesh:
+    """Device-resident triangle mesh (the reference's M_i / mf.tri) with lazily built trees."""
+
+    def __init__(self, ctx: Context, V, F):
+        self.ctx = ctx
+        self.V, self.F = _f64(V), _i32(F)
+        self.h = C.c_void_p()
+        _chk(lib().fpohm_mesh_upload(ctx.h, _p(self.V), C.c_int64(len(self.V)), _p(self.F), C.c_int64(len(self.F)), C.byref(self.h)))
+
+    # build_aabb_tree, ghm.cpp:4231-4248
+    def build_aabb_tree(self):
+        _chk(lib().fpohm_mesh_build_query_tree(self.ctx.h, self.h))
+        return self
+
+    def normals(self):
+        self.build_aabb_tree()
+        nE = C.c_int64()
+        _chk(lib().fpohm_mesh_num_edges(self.h, C.byref(nE)))
+        FN = np.zeros((len(self.F), 3)); VN = np.zeros((len(self.V), 3)); EN = np.zeros((nE.value, 3))
+        E = np.zeros((nE.value, 2), np.int32); EMAP = np.zeros(3 * len(self.F), np.int32)
+        _chk(lib().fpohm_mesh_normals(self.h, _p(FN), _p(VN), _p(EN), _p(E), _p(EMAP)))
+        return FN, VN, EN, E, EMAP
+
+    def tree(self):
+        self.build_aabb_tree()
+        n = C.c_int64()
+        _chk(lib().fpohm_mesh_tree_nodes(self.h, C.byref(n)))
+        box = np.zeros((n.value, 6)); prim = np.zeros(n.value, np.int32); lr = np.zeros((n.value, 2), np.int32)
+        _chk(lib().fpohm_mesh_tree_export(self.h, _p(box), _p(prim), _p(lr)))
+        return box, prim, lr
+
+    # igl::signed_distance_pseudonormal, igl/signed_distance.cpp:186-218
+    def signed_distance_pseudonormal(self, P, want=("S", "I", "C", "N")):
+        P = _f64(P).reshape(-1, 3); n = len(P)
+        S = np.zeros(n) if "S" in want else None
+        I = np.zeros(n, np.int32) if "I" in want else None
+        Cc = np.zeros((n, 3)) if "C" in want else None
+        N = np.zeros((n, 3)) if "N" in want else None
+        _chk(lib().fpohm_signed_distance(self.ctx.h, self.h, _p(P), C.c_int64(n), _p(S), _p(I), _p(Cc), _p(N)))
+        return S, I, Cc, N
+
+    def signed_distance_dev(self, P_ptr: int, n: int, S_ptr=0, I_ptr=0, C_ptr=0, N_ptr=0, stream: int = 0):
+        _chk(lib().fpohm_signed_distance_dev(self.ctx.h, self.h, C.c_void_p(P_ptr), C.c_int64(n), C.c_void_p(S_ptr),
+                                             C.c_void_p(I_ptr), C.c_void_p(C_ptr), C.c_void_p(N_ptr), C.c_void_p(stream)))
+
+    # igl::point_mesh_squared_distance
+    def point_mesh_squared_distance(self, P):
+        P = _f64(P).reshape(-1, 3); n = len(P)
+        D = np.zeros(n); I = np.zeros(n, np.int32); Cc = np.zeros((n, 3))
+        _chk(lib().fpohm_point_mesh_sqdist(self.ctx.h, self.h, _p(P), C.c_int64(n), _p(D), _p(I), _p(Cc)))
+        return D, I, Cc
+
+    def close(self):
+        if self.h:
+            lib().fpohm_mesh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_igl_tree(V, F):
+    """igl::AABB::init restatement, host only (no GPU): pre-order (box, primitive, left/right)."""
+    V, F = _f64(V), _i32(F)
+    n = C.c_int64(0)
+    _chk(lib().fpohm_host_igl_tree(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.byref(n), None, None, None))
+    box = np.zeros((n.value, 6)); prim = np.zeros(n.value, np.int32); lr = np.zeros((n.value, 2), np.int32)
+    _chk(lib().fpohm_host_igl_tree(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.byref(n), _p(box), _p(prim), _p(lr)))
+    return box, prim, lr
+
+
+def host_igl_normals(V, F):
+    V, F = _f64(V), _i32(F)
+    n = C.c_int64(0)
+    _chk(lib().fpohm_host_igl_normals(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.byref(n), None, None, None, None, None))
+    FN = np.zeros((len(F), 3)); VN = np.zeros((len(V), 3)); EN = np.zeros((n.value, 3))
+    E = np.zeros((n.value, 2), np.int32); EMAP = np.zeros(3 * len(F), np.int32)
+    _chk(lib().fpohm_host_igl_normals(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.byref(n), _p(FN), _p(VN), _p(EN), _p(E), _p(EMAP)))
+    return FN, VN, EN, E, EMAP
+
+
+# points_inside_mesh, gf.cpp:4024-4048
+def points_inside_mesh(ctx: Context, Ps, V, F):
+    m = TriMesh(ctx, V, F)
+    try:
+        return m.signed_distance_pseudonormal(Ps, want=("S",))[0]
+    finally:
+        m.close()
+
+
+class OctreeParams:
+    def __init__(self, grid_size, origin, mesh_transform, voxel_size, stop_extent, graded=True, paired=True):
+        self.c = _OctreeParams()
+        for d in range(3):
+            self.c.grid_size[d] = int(grid_size[d]); self.c.origin[d] = float(origin[d]); self.c.mesh_transform[d] = float(mesh_transform[d])
+        self.c.voxel_size = float(voxel_size); self.c.stop_extent = int(stop_extent)
+        self.c.graded = int(bool(graded)); self.c.paired = int(bool(paired))
+
+    grid_size = property(lambda s: np.array(s.c.grid_size[:], np.int32))
+    origin = property(lambda s: np.array(s.c.origin[:]))
+    mesh_transform = property(lambda s: np.array(s.c.mesh_transform[:]))
+    voxel_size = property(lambda s: s.c.voxel_size)
+
+
+# ghm.cpp:463-493
+def octree_grid_setup(V, num_voxels: int = 1 << 20) -> OctreeParams:
+    V = _f64(V)
+    p = OctreeParams([1, 1, 1], [0, 0, 0], [0, 0, 0], 1.0, 1)
+    _chk(lib().fpohm_octree_grid_setup(_p(V), C.c_int64(len(V)), C.c_int32(num_voxels), C.byref(p.c)))
+    return p
+
+
+class Octree:
+    """Mirror of OctreeGrid (octree.h:62-270) over a device-resident level-synchronous octree."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    @classmethod
+    def build(cls, ctx: Context, mesh: TriMesh, params: OctreeParams):
+        h = C.c_void_p()
+        _chk(lib().fpohm_octree_build(ctx.h, mesh.h, C.byref(params.c), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_marks(cls, ctx: Context, grid_size, marks, graded=True, paired=True):
+        gs = _i32(grid_size); m = _i32(marks).reshape(-1, 4)
+        h = C.c_void_p()
+        _chk(lib().fpohm_octree_build_from_marks(ctx.h, _p(gs), _p(m), C.c_int64(len(m)), C.c_int32(graded), C.c_int32(paired), C.byref(h)))
+        return cls(ctx, h)
+
+    def subdivide(self, mesh: TriMesh, stop_extent: int):
+        _chk(lib().fpohm_octree_subdivide(self.h, mesh.h, C.c_int32(stop_extent)))
+
+    def refine(self, mesh: TriMesh, cell_ids, stop_extent: int):
+        c = _i32(cell_ids)
+        _chk(lib().fpohm_octree_refine(self.h, mesh.h, _p(c), C.c_int64(len(c)), C.c_int32(stop_extent)))
+
+    def sizes(self):
+        nn, nc, nl = C.c_int64(), C.c_int64(), C.c_int64(); nr, md = C.c_int32(), C.c_int32()
+        _chk(lib().fpohm_octree_sizes(self.h, C.byref(nn), C.byref(nc), C.byref(nl), C.byref(nr), C.byref(md)))
+        return dict(nodes=nn.value, cells=nc.value, leaves=nl.value, roots=nr.value, max_depth=md.value)
+
+    def export(self):
+        s = self.sizes()
+        node_pos = np.zeros((s["nodes"], 3), np.int32); node_neigh = np.zeros((s["nodes"], 6), np.int32)
+        first_child = np.zeros(s["cells"], np.int32); corner = np.zeros((s["cells"], 8), np.int32)
+        neigh = np.zeros((s["cells"], 6), np.int32)
+        _chk(lib().fpohm_octree_export(self.h, _p(node_pos), _p(node_neigh), _p(first_child), _p(corner), _p(neigh)))
+        return dict(node_pos=node_pos, node_neigh=node_neigh, first_child=first_child, corner=corner, neigh=neigh, **s)
+
+    def hexes(self):
+        s = self.sizes()
+        Vp = np.zeros((s["nodes"], 3)); hexa = np.zeros((s["leaves"], 8), np.uint32); h2c = np.zeros(s["leaves"], np.int32)
+        _chk(lib().fpohm_octree_hexes(self.h, _p(Vp), _p(hexa), _p(h2c)))
+        return Vp, hexa, h2c
+
+    def flags(self):
+        f = C.c_int32()
+        _chk(lib().fpohm_octree_check(self.h, C.byref(f)))
+        return bool(f.value & 1), bool(f.value & 2)
+
+    def cell_sign(self, mesh: TriMesh, origin, spacing: float):
+        s = self.sizes(); o = _f64(origin)
+        inside = np.zeros(s["cells"], np.float32)
+        _chk(lib().fpohm_octree_cell_sign(self.h, mesh.h, _p(o), C.c_double(spacing), _p(inside)))
+        return inside
+
+    def close(self):
+        if self.h:
+            lib().fpohm_octree_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# scaled_jacobian, gf.cpp:2309-2358 — returns (V_Js, H_Js, (min, ave, deviation), flipped) like Mesh_Quality
+def scaled_jacobian(ctx: Context, V, hexa):
+    V = _f64(V); hexa = np.ascontiguousarray(hexa, np.uint32); H = len(hexa)
+    VJ = np.zeros(8 * H); HJ = np.zeros(H); mad = np.zeros(3); fl = C.c_int64()
+    _chk(lib().fpohm_scaled_jacobian(ctx.h, _p(V), C.c_int64(len(V)), _p(hexa), C.c_int64(H), _p(VJ), _p(HJ), _p(mad), C.byref(fl)))
+    return VJ, HJ, mad, fl.value
+
+
+def scaled_jacobian_dev(ctx: Context, V_ptr, nV, hex_ptr, H, VJ_ptr, HJ_ptr, stats_ptr, flipped_ptr, stream=0):
+    _chk(lib().fpohm_scaled_jacobian_dev(ctx.h, C.c_void_p(V_ptr), C.c_int64(nV), C.c_void_p(hex_ptr), C.c_int64(H),
+                                         C.c_void_p(VJ_ptr), C.c_void_p(HJ_ptr), C.c_void_p(stats_ptr), C.c_void_p(flipped_ptr),
+                                         C.c_void_p(stream)))
+
+
+class HexConnectivity:
+    """build_connectivity, Hex branch (gf.cpp:121-186,226-264)."""
+    NAMES = ["F_nhs", "E_nfs", "E_nhs", "V_nvs", "V_nes", "V_nfs", "V_nhs"]
+
+    def __init__(self, ctx: Context, hexa, nV: int):
+        hexa = np.ascontiguousarray(hexa, np.uint32); H = len(hexa)
+        h = C.c_void_p()
+        _chk(lib().fpohm_hex_connectivity(ctx.h, _p(hexa), C.c_int64(H), C.c_int64(nV), C.byref(h)))
+        try:
+            nF, nE = C.c_int64(), C.c_int64()
+            _chk(lib().fpohm_conn_sizes(h, C.byref(nF), C.byref(nE)))
+            nF, nE = nF.value, nE.value
+            self.F_vs = np.zeros((nF, 4), np.uint32); self.F_es = np.zeros((nF, 4), np.uint32); self.F_boundary = np.zeros(nF, np.uint8)
+            self.E_vs = np.zeros((nE, 2), np.uint32); self.E_boundary = np.zeros(nE, np.uint8); self.V_boundary = np.zeros(nV, np.uint8)
+            self.H_fs = np.zeros((H, 6), np.uint32)
+            _chk(lib().fpohm_conn_fixed(h, _p(self.F_vs), _p(self.F_es), _p(self.F_boundary), _p(self.E_vs), _p(self.E_boundary),
+                                        _p(self.V_boundary), _p(self.H_fs)))
+            sizes = [nF, nE, nE, nV, nV, nV, nV]
+            for which, (nm, n) in enumerate(zip(self.NAMES, sizes)):
+                tot = C.c_int64()
+                _chk(lib().fpohm_conn_csr(h, C.c_int32(which), None, None, C.byref(tot)))
+                off = np.zeros(n + 1, np.int64); val = np.zeros(tot.value, np.uint32)
+                _chk(lib().fpohm_conn_csr(h, C.c_int32(which), _p(off), _p(val), C.byref(tot)))
+                setattr(self, nm, (off, val))
+        finally:
+            lib().fpohm_conn_free(h)
+
+
+def voxel_lattice(ctx: Context, bb_min, bb_max, num_voxels: int):
+    mn, mx = _f64(bb_min), _f64(bb_max)
+    dim = np.zeros(3, np.int32)
+    _chk(lib().fpohm_voxel_lattice_dims(_p(mn), _p(mx), C.c_int32(num_voxels), _p(dim)))
+    nv = int(dim[0]) * int(dim[1]) * int(dim[2]); nh = int(dim[0] - 1) * int(dim[1] - 1) * int(dim[2] - 1)
+    Vp = np.zeros((nv, 3)); hexa = np.zeros((nh, 8), np.uint32)
+    _chk(lib().fpohm_voxel_lattice(ctx.h, _p(mn), _p(mx), C.c_int32(num_voxels), _p(Vp), _p(hexa)))
+    return Vp, hexa, dim

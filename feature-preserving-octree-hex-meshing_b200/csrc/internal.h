@@ -1,0 +1,119 @@
+// Internal plumbing of libfpohm.so: error reporting, device buffers, context.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/fpohm.h"
+
+namespace fpohm {
+
+void set_error(const char *fmt, ...);
+
+struct Failure { int code; };
+
+#define FPOHM_CUDA(expr)                                                                     \
+	do {                                                                                     \
+		cudaError_t e__ = (expr);                                                            \
+		if (e__ != cudaSuccess) {                                                            \
+			::fpohm::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+			throw ::fpohm::Failure{e__ == cudaErrorMemoryAllocation ? FPOHM_ENOMEM : FPOHM_ECUDA};   \
+		}                                                                                    \
+	} while (0)
+
+#define FPOHM_REQUIRE(cond, code, ...)            \
+	do {                                          \
+		if (!(cond)) {                            \
+			::fpohm::set_error(__VA_ARGS__);      \
+			throw ::fpohm::Failure{code};         \
+		}                                         \
+	} while (0)
+
+// every extern "C" body is wrapped so no exception crosses the C-ABI
+#define FPOHM_API_BEGIN try {
+#define FPOHM_API_END                                                        \
+	return FPOHM_OK;                                                         \
+	} catch (const ::fpohm::Failure &f) { return f.code; }                   \
+	catch (const std::bad_alloc &) { ::fpohm::set_error("host out of memory"); return FPOHM_ENOMEM; } \
+	catch (...) { ::fpohm::set_error("unexpected exception"); return FPOHM_ECUDA; }
+
+// Plain device buffer (stream-ordered allocation keeps repeated calls cheap).
+template <class T>
+struct DevBuf {
+	T *p = nullptr;
+	int64_t n = 0;
+	cudaStream_t s = nullptr;
+	DevBuf() = default;
+	DevBuf(int64_t count, cudaStream_t stream) { alloc(count, stream); }
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+	DevBuf &operator=(DevBuf &&o) noexcept {
+		if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+		return *this;
+	}
+	~DevBuf() { release(); }
+	void alloc(int64_t count, cudaStream_t stream) {
+		release();
+		n = count; s = stream;
+		if (count > 0) FPOHM_CUDA(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)count, stream));
+	}
+	void release() {
+		if (p) cudaFreeAsync(p, s);
+		p = nullptr; n = 0;
+	}
+	void zero() { if (n) FPOHM_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * (size_t)n, s)); }
+	void upload(const T *h, int64_t count) {
+		if (count) FPOHM_CUDA(cudaMemcpyAsync(p, h, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, s));
+	}
+	void download(T *h, int64_t count) const {
+		if (count) FPOHM_CUDA(cudaMemcpyAsync(h, p, sizeof(T) * (size_t)count, cudaMemcpyDeviceToHost, s));
+	}
+};
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+} // namespace fpohm
+
+struct fpohm_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double last_ms = 0;
+	int64_t launches = 0;
+};
+
+namespace fpohm {
+// grid for a grid-stride kernel: a multiple of the SM count (148 on B200), capped by the work
+inline int grid_for(const fpohm_ctx *ctx, int64_t work_items, int block, int ctas_per_sm = 8) {
+	int64_t need = (work_items + block - 1) / block;
+	int64_t cap = (int64_t)ctx->sm_count * ctas_per_sm;
+	if (need < 1) need = 1;
+	return (int)(need < cap ? need : cap);
+}
+struct DeviceGuard {
+	int prev = 0;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+struct KernelTimer {
+	fpohm_ctx *c; cudaStream_t s;
+	KernelTimer(fpohm_ctx *ctx, cudaStream_t st) : c(ctx), s(st) { cudaEventRecord(c->ev0, s); }
+	void stop() {
+		cudaEventRecord(c->ev1, s);
+		cudaEventSynchronize(c->ev1);
+		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+		c->last_ms = ms;
+	}
+};
+#define FPOHM_LAUNCH_CHECK(ctx)                      \
+	do {                                             \
+		(ctx)->launches++;                           \
+		FPOHM_CUDA(cudaGetLastError());              \
+	} while (0)
+} // namespace fpohm

@@ -1,0 +1,63 @@
+// fpohm_mesh: device-resident triangle soup, facet-bbox tree (subdivision predicate) and the
+// igl-identical closest-point tree with its normals (query layer).
+#pragma once
+#include "internal.h"
+
+namespace fpohm {
+
+// One internal node of the flattened closest-point tree.  Both child boxes live in the parent so a
+// node visit is ONE 128-byte line.  child >= 0: internal node index; child < 0: leaf, primitive = ~child.
+struct alignas(128) QNode {
+	double lmin[3], lmax[3];
+	double rmin[3], rmax[3];
+	int32_t left, right;
+	int32_t pad[4];
+};
+static_assert(sizeof(QNode) == 128, "QNode must be one cache line");
+
+// host-side result of the igl::AABB::init restatement, in DFS pre-order (node 0 = root)
+struct HostTree {
+	std::vector<double> box;    // 6 per node: min xyz, max xyz
+	std::vector<int32_t> prim;  // -1 for internal nodes
+	std::vector<int32_t> lr;    // 2 per node, -1 for leaves
+};
+
+void build_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, HostTree &out);
+void build_igl_normals(const double *V, int64_t nV, const int32_t *F, int64_t nF,
+                       std::vector<double> &FN, std::vector<double> &VN, std::vector<double> &EN,
+                       std::vector<int32_t> &E, std::vector<int32_t> &EMAP);
+
+} // namespace fpohm
+
+struct fpohm_mesh {
+	fpohm_ctx *ctx = nullptr;
+	int64_t nV = 0, nF = 0;
+	std::vector<double> hV;
+	std::vector<int32_t> hF;
+	fpohm::DevBuf<double> V;       // 3 per vertex
+	fpohm::DevBuf<int32_t> F;      // 3 per facet
+	fpohm::DevBuf<double> tri;     // 9 per facet: A, B, C
+	double bbox[6] = {0, 0, 0, 0, 0, 0};
+
+	// subdivision-predicate structure: implicit balanced tree over Morton-sorted facet boxes
+	// (heap layout, node 1 = root, children 2n / 2n+1, leaves = single facet boxes), 6 doubles per node
+	bool has_pred = false;
+	int64_t pred_nodes = 0;
+	fpohm::DevBuf<double> pred_box;
+
+	// query structure
+	bool has_tree = false;
+	fpohm::HostTree htree;
+	int64_t n_qnodes = 0;
+	fpohm::DevBuf<fpohm::QNode> qnodes;
+	int32_t qroot = 0;             // >= 0 internal node, < 0 leaf (~prim) when nF == 1
+	std::vector<double> hFN, hVN, hEN;
+	std::vector<int32_t> hE, hEMAP;
+	fpohm::DevBuf<double> FN, VN, EN;
+	fpohm::DevBuf<int32_t> EMAP;
+};
+
+namespace fpohm {
+void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
+void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
+} // namespace fpohm

@@ -1,0 +1,852 @@
+// Level-synchronous construction of the graded (2:1 over faces AND edges) and paired octree.
+//
+// Replaces OctreeGrid (grid_meshing/octree.cpp) as driven by octree_mesh (ghm.cpp:460-567):
+//   createRootCells            octree.cpp:64-117
+//   subdivide(pred, ...)       octree.cpp:648-690   BFS: a cell is TESTED iff it is a root or its parent's
+//                                                   predicate was true (children pushed only then, :676-678)
+//   splitCell                  octree.cpp:501-593
+//   makeCellGraded             octree.cpp:598-627   internal cell => its 6 face + 12 edge neighbours of the same
+//                                                   size exist (their parents are internal)
+//   makeCellPaired + siblings  octree.cpp:574-590,632-643   internal cell => all 7 siblings internal
+//                                                   (root cell => all roots internal)
+//   should_subdivide           ghm.cpp:502-517 -> geo/mesh/mesh_AABB.h:214-239 -> geo/basic/geometry.h:612-622
+//
+// The sequential code only ever splits a cell when one of these rules forces it, and enforces every rule
+// after every split, so its result is the LEAST fix-point of the rules over the predicate-true set P and is
+// independent of split order (DESIGN.md §octree proves the two directions).  Rules only push constraints
+// from level l+1 to level l (grading, tree) or sideways inside one sibling family (pairing), hence:
+//   phase 1 (top-down)   T_0 = roots, P_l = {c in T_l : pred(c)}, T_{l+1} = children(P_l)
+//   phase 2 (bottom-up)  I_l = family_close(P_l ∪ parents(I_{l+1}) ∪ parents(N18(I_{l+1})))
+// with every set a sorted array of per-level Morton codes; union = radix sort + unique, family_close = unique on
+// code>>3 then x8 expansion.  Phase 3 numbers cells/nodes canonically and derives every link table with
+// binary searches instead of the reference's linked-list walks.
+#include "octree.h"
+
+#include <algorithm>
+#include <map>
+#include <set>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
+
+using namespace fpohm;
+
+namespace {
+
+constexpr uint64_t INVALID = ~0ull;
+
+// Cube::delta / invDelta, common.h:147-158
+__host__ __device__ __forceinline__ int corner_to_morton(int k) { return ((k & 1) ^ ((k >> 1) & 1)) | (k & 2) | (k & 4); }
+__host__ __device__ __forceinline__ int morton_to_corner(int m) { const int dx = m & 1, dy = (m >> 1) & 1, dz = (m >> 2) & 1; return dy ? 4 * dz + 3 - dx : 4 * dz + dx; }
+
+__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t *a, int64_t lo, int64_t hi, uint64_t key) {
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (a[mid] < key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+// rank of `code` among internal cells of `level` (global rank, i.e. including lower levels), or -1
+__device__ __forceinline__ int64_t internal_rank(const LevelTable &t, int level, uint64_t code) {
+	if (level < 0 || level >= t.n_levels) return -1;
+	const int64_t lo = t.off[level], hi = t.off[level + 1];
+	const int64_t i = lower_bound_u64(t.code, lo, hi, code);
+	return (i < hi && t.code[i] == code) ? i : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase 1
+__global__ void roots_kernel(uint64_t *__restrict__ code, int rx, int ry, int rz) {
+	// roots are listed in MORTON order here (sets are sorted arrays); their cell ids are Layout3D ids (phase 3)
+	const int n = rx * ry * rz;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const int x = i % rx, y = (i / rx) % ry, z = (i / rx) / ry;
+		code[i] = morton3(x, y, z);
+	}
+}
+
+// should_subdivide (ghm.cpp:502-517) for every cell of T_l.  One thread per cell; stack descent of the complete
+// binary facet-box tree with early exit on the first overlapping facet (the reference visits every overlapping
+// leaf, mesh_AABB.h:214-239, but only ORs a flag — same result).
+__global__ void __launch_bounds__(256)
+predicate_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift /*depth - level*/, double bx, double by, double bz,
+                 double vs, const double *__restrict__ box, int64_t P, uint8_t *__restrict__ flag)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint64_t c = cells[i];
+		const int x = (int)(compact1by2(c) << shift), y = (int)(compact1by2(c >> 1) << shift), z = (int)(compact1by2(c >> 2) << shift);
+		const int extent = 1 << shift;
+		// box.xyz_min = (mesh_transform + origin) + voxel_size * x ; box.xyz_max = box.xyz_min + voxel_size * extent
+		const double mn0 = bx + vs * x, mn1 = by + vs * y, mn2 = bz + vs * z;
+		const double mx0 = mn0 + vs * extent, mx1 = mn1 + vs * extent, mx2 = mn2 + vs * extent;
+		int64_t stack[40];
+		int sp = 0;
+		stack[sp++] = 1;
+		bool hit = false;
+		while (sp > 0 && !hit) {
+			const int64_t nd = stack[--sp];
+			const double *b = box + 6 * nd;
+			// bboxes_overlap, geo/basic/geometry.h:612-622 (closed intervals)
+			if (mx0 < b[0] || mn0 > b[3] || mx1 < b[1] || mn1 > b[4] || mx2 < b[2] || mn2 > b[5]) continue;
+			if (nd >= P) { hit = true; break; }
+			stack[sp++] = 2 * nd + 1;
+			stack[sp++] = 2 * nd;
+		}
+		flag[i] = hit;
+	}
+}
+
+__global__ void children_kernel(const uint64_t *__restrict__ parents, int64_t n, uint64_t *__restrict__ out) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 8 * n; i += (int64_t)gridDim.x * blockDim.x)
+		out[i] = (parents[i >> 3] << 3) | (uint64_t)(i & 7);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase 2: cells forced at level l by the internal cells of level l+1.
+// For a cell c with parent p and octant o, parents(c ∪ N18(c)) = { p + (a_x s_x, a_y s_y, a_z s_z) : a in {0,1}^3,
+// |a| <= 2 } with s = -1/+1 for o = 0/1: 7 candidates, a = 0 is the tree rule.
+__global__ void forced_kernel(const uint64_t *__restrict__ cells, int64_t n, int graded, int lx, int ly, int lz /*level-l bounds*/,
+                              uint64_t *__restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint64_t c = cells[i];
+		const uint64_t p = c >> 3;
+		const int px = (int)compact1by2(p), py = (int)compact1by2(p >> 1), pz = (int)compact1by2(p >> 2);
+		const int sx = (c & 1) ? 1 : -1, sy = (c & 2) ? 1 : -1, sz = (c & 4) ? 1 : -1;
+		uint64_t *o = out + 7 * i;
+		o[0] = p;
+#pragma unroll
+		for (int a = 1; a < 7; ++a) { // a = bit mask over axes, 7 (=vertex neighbour) excluded
+			uint64_t v = INVALID;
+			if (graded) {
+				const int qx = px + ((a & 1) ? sx : 0), qy = py + ((a & 2) ? sy : 0), qz = pz + ((a & 4) ? sz : 0);
+				if (qx >= 0 && qy >= 0 && qz >= 0 && qx < lx && qy < ly && qz < lz) v = morton3(qx, qy, qz);
+			}
+			o[a] = v;
+		}
+	}
+}
+
+__global__ void family_kernel(const uint64_t *__restrict__ in, int64_t n, uint64_t *__restrict__ out) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] >> 3;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase 3
+__global__ void root_cells_kernel(uint8_t *__restrict__ lvl, uint64_t *__restrict__ code, int rx, int ry, int rz) {
+	const int n = rx * ry * rz;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const int x = i % rx, y = (i / rx) % ry, z = (i / rx) / ry; // Layout3D::toGrid, common.h:76-82
+		lvl[i] = 0; code[i] = morton3(x, y, z);
+	}
+}
+
+// children of the g-th internal cell (global rank over levels) get ids n_roots + 8 g + corner
+__global__ void child_cells_kernel(LevelTable t, int64_t n_internal, uint8_t *__restrict__ lvl, uint64_t *__restrict__ code) {
+	for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_internal; g += (int64_t)gridDim.x * blockDim.x) {
+		int l = 0;
+		while (g >= t.off[l + 1]) ++l;
+		const uint64_t pc = t.code[g];
+		const int64_t base = t.n_roots + 8 * g;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			lvl[base + k] = (uint8_t)(l + 1);
+			code[base + k] = (pc << 3) | (uint64_t)corner_to_morton(k);
+		}
+	}
+}
+
+__device__ __forceinline__ int32_t cell_id_of(const LevelTable &t, int level, int x, int y, int z) {
+	// id of the EXISTING cell (level, x, y, z), or -1 when its parent is not internal
+	if (level == 0) return x + t.roots[0] * (y + t.roots[1] * z);
+	const int64_t r = internal_rank(t, level - 1, morton3(x >> 1, y >> 1, z >> 1));
+	if (r < 0) return -1;
+	return (int32_t)(t.n_roots + 8 * r + morton_to_corner((x & 1) | ((y & 1) << 1) | ((z & 1) << 2)));
+}
+
+__global__ void __launch_bounds__(256)
+cell_links_kernel(LevelTable t, const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int64_t n_cells,
+                  int32_t *__restrict__ first_child, int32_t *__restrict__ neigh, uint8_t *__restrict__ leaf_flag)
+{
+	for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n_cells; id += (int64_t)gridDim.x * blockDim.x) {
+		const int l = lvl[id];
+		const uint64_t c = code[id];
+		const int64_t r = internal_rank(t, l, c);
+		first_child[id] = r < 0 ? -1 : (int32_t)(t.n_roots + 8 * r);
+		leaf_flag[id] = r < 0;
+		const int x = (int)compact1by2(c), y = (int)compact1by2(c >> 1), z = (int)compact1by2(c >> 2);
+		const int bound[3] = {t.roots[0] << l, t.roots[1] << l, t.roots[2] << l};
+#pragma unroll
+		for (int ax = 0; ax < 3; ++ax) {
+#pragma unroll
+			for (int dir = 0; dir < 2; ++dir) {
+				int q[3] = {x, y, z};
+				q[ax] += dir ? 1 : -1;
+				int32_t res = -1;
+				if (q[ax] >= 0 && q[ax] < bound[ax]) {
+					// same-size neighbour if it exists, else the (larger) leaf that contains it:
+					// updateSubcellLinks, octree.cpp:255-281
+					for (int ll = l; ll >= 0 && res < 0; --ll) {
+						const int sh = l - ll;
+						res = cell_id_of(t, ll, q[0] >> sh, q[1] >> sh, q[2] >> sh);
+					}
+				}
+				neigh[6 * id + 2 * ax + dir] = res;
+			}
+		}
+	}
+}
+
+// node keys: Morton code of (corner position >> node_shift); 8 per leaf
+__global__ void leaf_corner_keys_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const uint8_t *__restrict__ lvl,
+                                        const uint64_t *__restrict__ code, int depth, int node_shift, uint64_t *__restrict__ keys)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_leaves; i += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t id = leaf_cell[i];
+		const int l = lvl[id];
+		const uint64_t c = code[id];
+		const int sh = depth - l - node_shift; // extent in key units = 1 << sh
+		const uint32_t x = compact1by2(c) << sh, y = compact1by2(c >> 1) << sh, z = compact1by2(c >> 2) << sh;
+		const uint32_t e = 1u << sh;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int m = corner_to_morton(k);
+			keys[8 * i + k] = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
+		}
+	}
+}
+
+__global__ void node_pos_kernel(const uint64_t *__restrict__ key, int64_t n, int node_shift, int32_t *__restrict__ pos) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint64_t k = key[i];
+		pos[3 * i] = (int32_t)(compact1by2(k) << node_shift);
+		pos[3 * i + 1] = (int32_t)(compact1by2(k >> 1) << node_shift);
+		pos[3 * i + 2] = (int32_t)(compact1by2(k >> 2) << node_shift);
+	}
+}
+
+// cornerNodeId for ALL cells + shortest leaf edge leaving every node in each of the 6 directions
+__global__ void __launch_bounds__(256)
+cell_corners_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, const uint8_t *__restrict__ leaf_flag,
+                    int64_t n_cells, int depth, int node_shift, const uint64_t *__restrict__ node_key, int64_t n_nodes,
+                    int32_t *__restrict__ corner, int32_t *__restrict__ edge_len)
+{
+	for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n_cells; id += (int64_t)gridDim.x * blockDim.x) {
+		const int l = lvl[id];
+		const uint64_t c = code[id];
+		const int sh = depth - l - node_shift;
+		const uint32_t x = compact1by2(c) << sh, y = compact1by2(c >> 1) << sh, z = compact1by2(c >> 2) << sh;
+		const uint32_t e = 1u << sh;
+		int32_t nid[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int m = corner_to_morton(k);
+			const uint64_t key = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
+			nid[k] = (int32_t)lower_bound_u64(node_key, 0, n_nodes, key);
+			corner[8 * id + k] = nid[k];
+		}
+		if (leaf_flag[id]) {
+			const int len = (int)(e << node_shift);
+			// 12 edges as (lower corner, upper corner, axis) in corner numbering (octree.h:85-94)
+			const int ea[12] = {0, 3, 4, 7, 0, 1, 4, 5, 0, 1, 3, 2};
+			const int eb[12] = {1, 2, 5, 6, 3, 2, 7, 6, 4, 5, 7, 6};
+#pragma unroll
+			for (int k = 0; k < 12; ++k) {
+				const int ax = k >> 2;
+				atomicMin(&edge_len[6 * (int64_t)nid[ea[k]] + 2 * ax + 1], len);
+				atomicMin(&edge_len[6 * (int64_t)nid[eb[k]] + 2 * ax], len);
+			}
+		}
+	}
+}
+
+// Node::neighNodeId: other end of the finest leaf edge leaving the node in that direction, -1 if none
+__global__ void node_links_kernel(const uint64_t *__restrict__ node_key, int64_t n_nodes, int node_shift,
+                                  const int32_t *__restrict__ edge_len, int32_t *__restrict__ neigh)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint64_t k = node_key[i];
+		const int p[3] = {(int)compact1by2(k), (int)compact1by2(k >> 1), (int)compact1by2(k >> 2)};
+#pragma unroll
+		for (int d = 0; d < 6; ++d) {
+			const int len = edge_len[6 * i + d];
+			int32_t res = -1;
+			if (len != 0x7fffffff) {
+				int q[3] = {p[0], p[1], p[2]};
+				q[d >> 1] += ((d & 1) ? 1 : -1) * (len >> node_shift);
+				const uint64_t key = morton3(q[0], q[1], q[2]);
+				const int64_t j = lower_bound_u64(node_key, 0, n_nodes, key);
+				res = (j < n_nodes && node_key[j] == key) ? (int32_t)j : -1;
+			}
+			neigh[6 * i + d] = res;
+		}
+	}
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void iota_i32_kernel(int32_t *p, int64_t n) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+
+// octree_mesh export, ghm.cpp:531-562
+__global__ void hex_vertices_kernel(const int32_t *__restrict__ pos, int64_t n, double bx, double by, double bz, double vs,
+                                    double *__restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * n; i += (int64_t)gridDim.x * blockDim.x) {
+		const int c = (int)(i % 3);
+		const double b = c == 0 ? bx : (c == 1 ? by : bz);
+		out[i] = b + (double)pos[i] * vs; // (mesh_transform + o) + nodePos * s
+	}
+}
+__global__ void hex_cells_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const int32_t *__restrict__ corner,
+                                 uint32_t *__restrict__ hex)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 8 * n_leaves; i += (int64_t)gridDim.x * blockDim.x)
+		hex[i] = (uint32_t)corner[8 * (int64_t)leaf_cell[i >> 3] + (i & 7)];
+}
+
+// is2to1Graded / isPaired, octree.cpp:148-202
+__global__ void check_kernel(const int32_t *__restrict__ first_child, const int32_t *__restrict__ corner,
+                             const int32_t *__restrict__ nneigh, int64_t n_cells, int32_t *__restrict__ bad /*[2]*/)
+{
+	for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n_cells; id += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t fc = first_child[id];
+		if (fc >= 0) {
+			const bool all_leaf = first_child[fc] < 0;
+			for (int k = 1; k < 8; ++k) if ((first_child[fc + k] < 0) != all_leaf) atomicAdd(&bad[1], 1);
+		} else {
+			const int32_t *v = corner + 8 * id;
+			const int ea[12] = {0, 3, 4, 7, 0, 1, 4, 5, 0, 1, 3, 2};
+			const int eb[12] = {1, 2, 5, 6, 3, 2, 7, 6, 4, 5, 7, 6};
+			for (int k = 0; k < 12; ++k) {
+				const int ax = k >> 2;
+				const int32_t a = v[ea[k]], b = v[eb[k]];
+				const int32_t na = nneigh[6 * (int64_t)a + 2 * ax + 1], pb = nneigh[6 * (int64_t)b + 2 * ax];
+				if (!(na == b || na == pb)) atomicAdd(&bad[0], 1);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct Sorter {
+	fpohm_ctx *ctx; cudaStream_t s;
+	// sort + unique, drop INVALID; returns count; result in `out` (allocated here)
+	int64_t sort_unique(DevBuf<uint64_t> &in, int64_t n, int bits, DevBuf<uint64_t> &out) {
+		if (n == 0) { out.alloc(0, s); return 0; }
+		DevBuf<uint64_t> sorted(n, s);
+		size_t tb = 0;
+		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, in.p, sorted.p, n, 0, 64, s));
+		(void)bits;
+		DevBuf<uint8_t> tmp((int64_t)tb, s);
+		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, in.p, sorted.p, n, 0, 64, s));
+		DevBuf<uint64_t> uniq(n, s);
+		DevBuf<int64_t> cnt(1, s);
+		size_t tb2 = 0;
+		FPOHM_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, sorted.p, uniq.p, cnt.p, n, s));
+		DevBuf<uint8_t> tmp2((int64_t)tb2, s);
+		FPOHM_CUDA(cub::DeviceSelect::Unique(tmp2.p, tb2, sorted.p, uniq.p, cnt.p, n, s));
+		ctx->launches += 6;
+		int64_t m = 0;
+		cnt.download(&m, 1);
+		uint64_t last = 0;
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+		if (m > 0) {
+			FPOHM_CUDA(cudaMemcpyAsync(&last, uniq.p + (m - 1), 8, cudaMemcpyDeviceToHost, s));
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+			if (last == INVALID) --m;
+		}
+		out.alloc(m, s);
+		if (m) FPOHM_CUDA(cudaMemcpyAsync(out.p, uniq.p, 8 * (size_t)m, cudaMemcpyDeviceToDevice, s));
+		return m;
+	}
+};
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+void setup_geometry(fpohm_octree *o, const int32_t gs[3]) {
+	for (int d = 0; d < 3; ++d) {
+		FPOHM_REQUIRE(gs[d] >= 1 && (gs[d] & (gs[d] - 1)) == 0, FPOHM_EINVAL, "octree: grid_size[%d]=%d is not a power of two (octree.cpp:26-28)", d, gs[d]);
+		FPOHM_REQUIRE(gs[d] <= (1 << 21), FPOHM_ERANGE, "octree: grid_size[%d]=%d exceeds 2^21", d, gs[d]);
+		o->prm.grid_size[d] = gs[d];
+	}
+	const int mn = std::min(gs[0], std::min(gs[1], gs[2]));
+	o->depth = ilog2(mn);
+	o->n_roots = 1;
+	for (int d = 0; d < 3; ++d) { o->roots[d] = gs[d] / mn; o->n_roots *= o->roots[d]; }
+	FPOHM_REQUIRE(o->depth < FPOHM_MAX_LEVELS, FPOHM_ERANGE, "octree: depth %d too large", o->depth);
+}
+
+LevelTable make_table(const fpohm_octree *o) {
+	LevelTable t;
+	t.code = o->icode.p;
+	for (int l = 0; l < FPOHM_MAX_LEVELS + 2; ++l) t.off[l] = o->lvl_off[std::min(l, o->n_levels)];
+	t.n_levels = o->n_levels;
+	for (int d = 0; d < 3; ++d) t.roots[d] = o->roots[d];
+	t.n_roots = o->n_roots;
+	t.depth = o->depth;
+	return t;
+}
+
+// phase 2 + 3 given the predicate-true sets P[l] (sorted device arrays) — shared by build / from_marks / refine
+void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::vector<int64_t> &nP) {
+	fpohm_ctx *ctx = o->ctx;
+	cudaStream_t s = ctx->stream;
+	Sorter sorter{ctx, s};
+	const int blk = 256;
+	const bool graded = o->prm.graded != 0, paired = o->prm.paired != 0;
+	int Lmax = -1;
+	for (int l = 0; l < (int)P.size(); ++l) if (nP[l] > 0) Lmax = l;
+	std::vector<DevBuf<uint64_t>> I((size_t)std::max(Lmax + 1, 0));
+	std::vector<int64_t> nI((size_t)std::max(Lmax + 1, 0), 0);
+	for (int l = Lmax; l >= 0; --l) {
+		const int64_t n_forced = (l < Lmax) ? 7 * nI[l + 1] : 0;
+		const int64_t n_cand = nP[l] + n_forced;
+		DevBuf<uint64_t> cand(n_cand, s);
+		if (nP[l]) FPOHM_CUDA(cudaMemcpyAsync(cand.p, P[l].p, 8 * (size_t)nP[l], cudaMemcpyDeviceToDevice, s));
+		if (n_forced) {
+			forced_kernel<<<grid_for(ctx, nI[l + 1], blk), blk, 0, s>>>(I[l + 1].p, nI[l + 1], graded ? 1 : 0,
+				o->roots[0] << l, o->roots[1] << l, o->roots[2] << l, cand.p + nP[l]);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		DevBuf<uint64_t> uq;
+		int64_t m = sorter.sort_unique(cand, n_cand, 64, uq);
+		if (paired && m > 0) {
+			if (l == 0) {
+				// root rule, octree.cpp:577-581: one root split => all roots split
+				uq.alloc(o->n_roots, s);
+				roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(uq.p, o->roots[0], o->roots[1], o->roots[2]);
+				FPOHM_LAUNCH_CHECK(ctx);
+				DevBuf<uint64_t> sorted_roots;
+				m = sorter.sort_unique(uq, o->n_roots, 64, sorted_roots);
+				uq = std::move(sorted_roots);
+			} else {
+				// sibling rule, octree.cpp:583-587 (+ makeCellPaired :632-643): whole families
+				DevBuf<uint64_t> fam(m, s), famu;
+				family_kernel<<<grid_for(ctx, m, blk), blk, 0, s>>>(uq.p, m, fam.p);
+				FPOHM_LAUNCH_CHECK(ctx);
+				const int64_t nf = sorter.sort_unique(fam, m, 64, famu);
+				uq.alloc(8 * nf, s);
+				children_kernel<<<grid_for(ctx, 8 * nf, blk), blk, 0, s>>>(famu.p, nf, uq.p);
+				FPOHM_LAUNCH_CHECK(ctx);
+				m = 8 * nf;
+			}
+		}
+		I[l] = std::move(uq);
+		nI[l] = m;
+	}
+	// concatenate levels
+	o->n_levels = Lmax + 1;
+	int64_t tot = 0;
+	for (int l = 0; l <= Lmax; ++l) { o->lvl_off[l] = tot; tot += nI[l]; }
+	for (int l = Lmax + 1; l < FPOHM_MAX_LEVELS + 2; ++l) o->lvl_off[l] = tot;
+	o->icode.alloc(std::max<int64_t>(tot, 1), s);
+	for (int l = 0; l <= Lmax; ++l)
+		if (nI[l]) FPOHM_CUDA(cudaMemcpyAsync(o->icode.p + o->lvl_off[l], I[l].p, 8 * (size_t)nI[l], cudaMemcpyDeviceToDevice, s));
+
+	// ---- phase 3: numbering -------------------------------------------------------------------
+	const int64_t n_internal = tot;
+	const int64_t n_cells = o->n_roots + 8 * n_internal;
+	FPOHM_REQUIRE(n_cells < (1ll << 31), FPOHM_ERANGE, "octree: %lld cells exceed int32 ids (octree.h:140-143)", (long long)n_cells);
+	o->n_cells = n_cells;
+	o->cell_level.alloc(n_cells, s);
+	o->cell_code.alloc(n_cells, s);
+	root_cells_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(o->cell_level.p, o->cell_code.p, o->roots[0], o->roots[1], o->roots[2]);
+	FPOHM_LAUNCH_CHECK(ctx);
+	const LevelTable t = make_table(o);
+	if (n_internal) {
+		child_cells_kernel<<<grid_for(ctx, n_internal, blk), blk, 0, s>>>(t, n_internal, o->cell_level.p, o->cell_code.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
+	o->cell_first_child.alloc(n_cells, s);
+	o->cell_neigh.alloc(6 * n_cells, s);
+	DevBuf<uint8_t> leaf_flag(n_cells, s);
+	cell_links_kernel<<<grid_for(ctx, n_cells, blk), blk, 0, s>>>(t, o->cell_level.p, o->cell_code.p, n_cells,
+		o->cell_first_child.p, o->cell_neigh.p, leaf_flag.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	// leaves in cell order (hex2Octree_map, ghm.cpp:551)
+	{
+		DevBuf<int32_t> ids(n_cells, s), sel(n_cells, s);
+		DevBuf<int64_t> cnt(1, s);
+		iota_i32_kernel<<<grid_for(ctx, n_cells, blk), blk, 0, s>>>(ids.p, n_cells);
+		FPOHM_LAUNCH_CHECK(ctx);
+		size_t tb = 0;
+		FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids.p, leaf_flag.p, sel.p, cnt.p, n_cells, s));
+		DevBuf<uint8_t> tmp((int64_t)tb, s);
+		FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids.p, leaf_flag.p, sel.p, cnt.p, n_cells, s));
+		ctx->launches += 2;
+		int64_t nl = 0;
+		cnt.download(&nl, 1);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+		o->n_leaves = nl;
+		o->leaf_cell.alloc(nl, s);
+		FPOHM_CUDA(cudaMemcpyAsync(o->leaf_cell.p, sel.p, 4 * (size_t)nl, cudaMemcpyDeviceToDevice, s));
+	}
+	// nodes: unique corners of leaves, Morton order of (pos >> node_shift)
+	const int finest_level = o->n_levels; // deepest cells live one level below the deepest internal level
+	o->node_shift = o->depth - finest_level;
+	FPOHM_REQUIRE(o->node_shift >= 0, FPOHM_ESTATE, "octree: internal cell below extent 1");
+	for (int d = 0; d < 3; ++d)
+		FPOHM_REQUIRE((o->prm.grid_size[d] >> o->node_shift) < (1 << 21), FPOHM_ERANGE,
+		              "octree: %d node positions per axis after shift do not fit 21-bit Morton keys", (o->prm.grid_size[d] >> o->node_shift) + 1);
+	{
+		DevBuf<uint64_t> keys(8 * o->n_leaves, s);
+		leaf_corner_keys_kernel<<<grid_for(ctx, o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->cell_level.p,
+			o->cell_code.p, o->depth, o->node_shift, keys.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		o->n_nodes = sorter.sort_unique(keys, 8 * o->n_leaves, 64, o->node_key);
+	}
+	FPOHM_REQUIRE(o->n_nodes < (1ll << 31), FPOHM_ERANGE, "octree: %lld nodes exceed int32 ids", (long long)o->n_nodes);
+	o->node_pos.alloc(3 * o->n_nodes, s);
+	node_pos_kernel<<<grid_for(ctx, o->n_nodes, blk), blk, 0, s>>>(o->node_key.p, o->n_nodes, o->node_shift, o->node_pos.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	o->cell_corner.alloc(8 * n_cells, s);
+	DevBuf<int32_t> edge_len(6 * o->n_nodes, s);
+	fill_i32_kernel<<<grid_for(ctx, 6 * o->n_nodes, blk), blk, 0, s>>>(edge_len.p, 6 * o->n_nodes, 0x7fffffff);
+	FPOHM_LAUNCH_CHECK(ctx);
+	cell_corners_kernel<<<grid_for(ctx, n_cells, blk), blk, 0, s>>>(o->cell_level.p, o->cell_code.p, leaf_flag.p, n_cells, o->depth,
+		o->node_shift, o->node_key.p, o->n_nodes, o->cell_corner.p, edge_len.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	o->node_neigh.alloc(6 * o->n_nodes, s);
+	node_links_kernel<<<grid_for(ctx, o->n_nodes, blk), blk, 0, s>>>(o->node_key.p, o->n_nodes, o->node_shift, edge_len.p, o->node_neigh.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+}
+
+// leaf codes of the level-l cells of an already numbered octree (cells of one level are a contiguous id range)
+__global__ void old_leaf_codes_kernel(const uint64_t *__restrict__ code, const int32_t *__restrict__ first_child, int64_t id0, int64_t n,
+                                      uint64_t *__restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+		out[i] = first_child[id0 + i] < 0 ? code[id0 + i] : INVALID;
+}
+
+// phase 1 with the bbox predicate.  BFS of octree.cpp:648-690: the queue starts with every current leaf
+// (roots on a fresh tree) and a cell's children are queued iff its predicate is true, so
+//   T_l = old_leaves(l) ∪ children(P_{l-1}),  P_l = {c in T_l : pred(c)}.
+// On return P[l] = old internal cells of level l ∪ P_l (unsorted; phase 2 sorts).
+void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bool fresh,
+                    std::vector<DevBuf<uint64_t>> &P, std::vector<int64_t> &nP)
+{
+	fpohm_ctx *ctx = o->ctx;
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	Sorter sorter{ctx, s};
+	mesh_ensure_pred(ctx, const_cast<fpohm_mesh *>(mesh), s);
+	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
+	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
+	DevBuf<uint64_t> kids;   // children(P_{l-1})
+	int64_t n_kids = 0;
+	for (int l = 0; l <= o->depth; ++l) {
+		// old leaves / old internal cells of this level
+		DevBuf<uint64_t> old_leaves;
+		int64_t n_old_leaves = 0;
+		const int64_t n_old_int = (!fresh && l < o->n_levels) ? o->lvl_off[l + 1] - o->lvl_off[l] : 0;
+		if (fresh) {
+			if (l == 0) {
+				old_leaves.alloc(o->n_roots, s);
+				roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(old_leaves.p, o->roots[0], o->roots[1], o->roots[2]);
+				FPOHM_LAUNCH_CHECK(ctx);
+				n_old_leaves = o->n_roots;
+			}
+		} else if (l <= o->n_levels) {
+			const int64_t id0 = l == 0 ? 0 : o->n_roots + 8 * o->lvl_off[l - 1];
+			const int64_t cnt = l == 0 ? o->n_roots : 8 * (o->lvl_off[l] - o->lvl_off[l - 1]);
+			if (cnt > 0) {
+				DevBuf<uint64_t> raw(cnt, s);
+				old_leaf_codes_kernel<<<grid_for(ctx, cnt, blk), blk, 0, s>>>(o->cell_code.p, o->cell_first_child.p, id0, cnt, raw.p);
+				FPOHM_LAUNCH_CHECK(ctx);
+				n_old_leaves = sorter.sort_unique(raw, cnt, 64, old_leaves);
+			}
+		}
+		const int64_t nT = n_old_leaves + n_kids;
+		const int extent = 1 << (o->depth - l);
+		const bool testable = extent > stop_extent && extent > 1; // ghm.cpp:503 ; octree.cpp:670-671
+		int64_t np = 0;
+		DevBuf<uint64_t> sel;
+		if (testable && nT > 0) {
+			DevBuf<uint64_t> T(nT, s);
+			if (n_old_leaves) FPOHM_CUDA(cudaMemcpyAsync(T.p, old_leaves.p, 8 * (size_t)n_old_leaves, cudaMemcpyDeviceToDevice, s));
+			if (n_kids) FPOHM_CUDA(cudaMemcpyAsync(T.p + n_old_leaves, kids.p, 8 * (size_t)n_kids, cudaMemcpyDeviceToDevice, s));
+			DevBuf<uint8_t> flag(nT, s);
+			predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T.p, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
+				mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			sel.alloc(nT, s);
+			DevBuf<int64_t> cnt(1, s);
+			size_t tb = 0;
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, T.p, flag.p, sel.p, cnt.p, nT, s));
+			DevBuf<uint8_t> tmp((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, T.p, flag.p, sel.p, cnt.p, nT, s));
+			ctx->launches += 2;
+			cnt.download(&np, 1);
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+		}
+		P.emplace_back(np + n_old_int, s);
+		nP.push_back(np + n_old_int);
+		if (np) FPOHM_CUDA(cudaMemcpyAsync(P.back().p, sel.p, 8 * (size_t)np, cudaMemcpyDeviceToDevice, s));
+		if (n_old_int) FPOHM_CUDA(cudaMemcpyAsync(P.back().p + np, o->icode.p + o->lvl_off[l], 8 * (size_t)n_old_int, cudaMemcpyDeviceToDevice, s));
+		n_kids = 8 * np;
+		FPOHM_REQUIRE(n_kids < (1ll << 31), FPOHM_ERANGE, "octree: level %d has %lld cells to test", l + 1, (long long)n_kids);
+		if (n_kids) {
+			kids.alloc(n_kids, s);
+			children_kernel<<<grid_for(ctx, n_kids, blk), blk, 0, s>>>(sel.p, np, kids.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		FPOHM_CUDA(cudaStreamSynchronize(s)); // sel / T die here
+		if (fresh && n_kids == 0) break;
+		if (!fresh && n_kids == 0 && l >= o->n_levels) break;
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+int fpohm_octree_grid_setup(const double *V, int64_t nV, int32_t num_voxels, fpohm_octree_params *p) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(V && p && nV > 0 && num_voxels > 0, FPOHM_EINVAL, "fpohm_octree_grid_setup: bad argument");
+	// GEO::get_bbox + ghm.cpp:463-493, expression order preserved
+	double mn[3] = {V[0], V[1], V[2]}, mx[3] = {V[0], V[1], V[2]};
+	for (int64_t i = 1; i < nV; ++i)
+		for (int c = 0; c < 3; ++c) { mn[c] = std::min(mn[c], V[3 * i + c]); mx[c] = std::max(mx[c], V[3 * i + c]); }
+	double center[3], extent[3];
+	for (int c = 0; c < 3; ++c) { center[c] = (mn[c] + mx[c]) / 2; extent[c] = mx[c] - mn[c]; }
+	const double max_extent = std::max(extent[0], std::max(extent[1], extent[2]));
+	const double voxel_size = max_extent / num_voxels;
+	auto next_pow2 = [](unsigned x) { x -= 1; x |= (x >> 1); x |= (x >> 2); x |= (x >> 4); x |= (x >> 8); x |= (x >> 16); return x + 1; };
+	for (int c = 0; c < 3; ++c) {
+		const double origin = mn[c] - 0 * voxel_size * 1.0; // padding = 0
+		const unsigned gs = next_pow2((unsigned)(std::ceil(extent[c] / voxel_size) + 2 * 0));
+		FPOHM_REQUIRE(gs >= 1 && gs <= (1u << 21), FPOHM_ERANGE, "fpohm_octree_grid_setup: grid size %u out of range", gs);
+		const double origin_max = origin + voxel_size * (int)gs;
+		const double origin_center = (origin_max + origin) * 0.5;
+		p->grid_size[c] = (int32_t)gs;
+		p->origin[c] = origin;
+		p->mesh_transform[c] = center[c] - origin_center;
+	}
+	p->voxel_size = voxel_size;
+	FPOHM_API_END
+}
+
+int fpohm_octree_build(fpohm_ctx *ctx, const fpohm_mesh *mesh, const fpohm_octree_params *p, fpohm_octree **out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && p && out, FPOHM_EINVAL, "fpohm_octree_build: null argument");
+	FPOHM_REQUIRE(p->voxel_size > 0, FPOHM_EINVAL, "fpohm_octree_build: voxel_size must be positive");
+	DeviceGuard g(ctx->device);
+	fpohm_octree *o = new fpohm_octree;
+	try {
+		o->ctx = ctx; o->prm = *p;
+		setup_geometry(o, p->grid_size);
+		KernelTimer t(ctx, ctx->stream);
+		std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
+		predicate_sets(o, mesh, p->stop_extent, true, P, nP);
+		close_and_number(o, P, nP);
+		t.stop();
+	} catch (...) { delete o; throw; }
+	*out = o;
+	FPOHM_API_END
+}
+
+int fpohm_octree_build_from_marks(fpohm_ctx *ctx, const int32_t grid_size[3], const int32_t *marks, int64_t n_marks,
+                                  int32_t graded, int32_t paired, fpohm_octree **out)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && grid_size && out && (marks || n_marks == 0), FPOHM_EINVAL, "fpohm_octree_build_from_marks: null argument");
+	DeviceGuard g(ctx->device);
+	fpohm_octree *o = new fpohm_octree;
+	try {
+		o->ctx = ctx;
+		o->prm.graded = graded; o->prm.paired = paired; o->prm.voxel_size = 1; o->prm.stop_extent = 1;
+		setup_geometry(o, grid_size);
+		// host: the BFS only tests roots and children of predicate-true cells (octree.cpp:669-678)
+		std::vector<std::set<uint64_t>> M((size_t)o->depth + 1);
+		for (int64_t i = 0; i < n_marks; ++i) {
+			const int32_t x = marks[4 * i], y = marks[4 * i + 1], z = marks[4 * i + 2], e = marks[4 * i + 3];
+			if (e <= 1 || (e & (e - 1)) || e > (1 << o->depth)) continue;
+			const int sh = ilog2(e), l = o->depth - sh;
+			if (x < 0 || y < 0 || z < 0 || x >= grid_size[0] || y >= grid_size[1] || z >= grid_size[2]) continue;
+			if ((x & (e - 1)) || (y & (e - 1)) || (z & (e - 1))) continue;
+			M[(size_t)l].insert(morton3(x >> sh, y >> sh, z >> sh));
+		}
+		std::vector<std::vector<uint64_t>> Ph;
+		for (int l = 0; l <= o->depth; ++l) {
+			std::vector<uint64_t> cur;
+			for (uint64_t c : M[(size_t)l])
+				if (l == 0 || std::binary_search(Ph[(size_t)l - 1].begin(), Ph[(size_t)l - 1].end(), c >> 3)) cur.push_back(c);
+			if (cur.empty()) break;
+			Ph.push_back(std::move(cur));
+		}
+		std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
+		for (auto &v : Ph) {
+			P.emplace_back((int64_t)v.size(), ctx->stream);
+			P.back().upload(v.data(), (int64_t)v.size());
+			nP.push_back((int64_t)v.size());
+		}
+		FPOHM_CUDA(cudaStreamSynchronize(ctx->stream));
+		KernelTimer t(ctx, ctx->stream);
+		close_and_number(o, P, nP);
+		t.stop();
+	} catch (...) { delete o; throw; }
+	*out = o;
+	FPOHM_API_END
+}
+
+int fpohm_octree_subdivide(fpohm_octree *o, const fpohm_mesh *mesh, int32_t stop_extent) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o && mesh, FPOHM_EINVAL, "fpohm_octree_subdivide: null argument");
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	KernelTimer t(ctx, ctx->stream);
+	std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
+	predicate_sets(o, mesh, stop_extent, false, P, nP);
+	close_and_number(o, P, nP);
+	t.stop();
+	FPOHM_API_END
+}
+
+int fpohm_octree_refine(fpohm_octree *o, const fpohm_mesh *mesh, const int32_t *cell_ids, int64_t n, int32_t stop_extent) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o && mesh && (cell_ids || n == 0), FPOHM_EINVAL, "fpohm_octree_refine: null argument");
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	// listed LEAF cells, per level (host: the list is the pipeline's tb_subdivided_cells, small)
+	std::vector<uint8_t> lvl((size_t)o->n_cells);
+	std::vector<uint64_t> code((size_t)o->n_cells);
+	std::vector<int32_t> fc((size_t)o->n_cells);
+	o->cell_level.download(lvl.data(), o->n_cells);
+	o->cell_code.download(code.data(), o->n_cells);
+	o->cell_first_child.download(fc.data(), o->n_cells);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	std::vector<std::set<uint64_t>> L((size_t)o->depth + 1);
+	for (int64_t i = 0; i < n; ++i) {
+		const int32_t id = cell_ids[i];
+		FPOHM_REQUIRE(id >= 0 && id < o->n_cells, FPOHM_EINVAL, "fpohm_octree_refine: cell id %d out of range", id);
+		if (fc[(size_t)id] >= 0) continue; // octree.cpp:694: only leaves are queued
+		const int extent = 1 << (o->depth - lvl[(size_t)id]);
+		if (extent <= stop_extent || extent <= 1) continue;
+		L[lvl[(size_t)id]].insert(code[(size_t)id]);
+	}
+	mesh_ensure_pred(ctx, const_cast<fpohm_mesh *>(mesh), s);
+	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
+	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
+	// P_l = old internal cells of level l  ∪  listed leaves whose predicate is true
+	std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
+	const int top = std::max(o->n_levels, o->depth + 1);
+	for (int l = 0; l < top; ++l) {
+		const int64_t n_old = l < o->n_levels ? o->lvl_off[l + 1] - o->lvl_off[l] : 0;
+		std::vector<uint64_t> cand;
+		if (l <= o->depth) cand.assign(L[(size_t)l].begin(), L[(size_t)l].end());
+		DevBuf<uint64_t> merged(n_old + (int64_t)cand.size(), s);
+		if (n_old) FPOHM_CUDA(cudaMemcpyAsync(merged.p, o->icode.p + o->lvl_off[l], 8 * (size_t)n_old, cudaMemcpyDeviceToDevice, s));
+		int64_t n_new = 0;
+		if (!cand.empty()) {
+			DevBuf<uint64_t> dc((int64_t)cand.size(), s), sel((int64_t)cand.size(), s);
+			DevBuf<uint8_t> flag((int64_t)cand.size(), s);
+			DevBuf<int64_t> cnt(1, s);
+			dc.upload(cand.data(), (int64_t)cand.size());
+			predicate_kernel<<<grid_for(ctx, (int64_t)cand.size(), blk), blk, 0, s>>>(dc.p, (int64_t)cand.size(), o->depth - l, bx, by, bz,
+				o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			size_t tb = 0;
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, dc.p, flag.p, sel.p, cnt.p, (int64_t)cand.size(), s));
+			DevBuf<uint8_t> tmp((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, dc.p, flag.p, sel.p, cnt.p, (int64_t)cand.size(), s));
+			ctx->launches += 2;
+			cnt.download(&n_new, 1);
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+			if (n_new) FPOHM_CUDA(cudaMemcpyAsync(merged.p + n_old, sel.p, 8 * (size_t)n_new, cudaMemcpyDeviceToDevice, s));
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+		}
+		merged.n = n_old + n_new;
+		nP.push_back(n_old + n_new);
+		P.push_back(std::move(merged));
+	}
+	KernelTimer t(ctx, s);
+	close_and_number(o, P, nP);
+	t.stop();
+	FPOHM_API_END
+}
+
+void fpohm_octree_free(fpohm_octree *o) {
+	if (!o) return;
+	DeviceGuard g(o->ctx->device);
+	cudaStreamSynchronize(o->ctx->stream);
+	delete o;
+}
+
+int fpohm_octree_sizes(const fpohm_octree *o, int64_t *n_nodes, int64_t *n_cells, int64_t *n_leaves, int32_t *n_roots, int32_t *max_depth) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o, FPOHM_EINVAL, "fpohm_octree_sizes: null octree");
+	if (n_nodes) *n_nodes = o->n_nodes;
+	if (n_cells) *n_cells = o->n_cells;
+	if (n_leaves) *n_leaves = o->n_leaves;
+	if (n_roots) *n_roots = o->n_roots;
+	if (max_depth) *max_depth = o->depth;
+	FPOHM_API_END
+}
+
+int fpohm_octree_export(const fpohm_octree *o, int32_t *node_pos, int32_t *node_neigh, int32_t *cell_first_child,
+                        int32_t *cell_corner, int32_t *cell_neigh)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o, FPOHM_EINVAL, "fpohm_octree_export: null octree");
+	DeviceGuard g(o->ctx->device);
+	if (node_pos) o->node_pos.download(node_pos, 3 * o->n_nodes);
+	if (node_neigh) o->node_neigh.download(node_neigh, 6 * o->n_nodes);
+	if (cell_first_child) o->cell_first_child.download(cell_first_child, o->n_cells);
+	if (cell_corner) o->cell_corner.download(cell_corner, 8 * o->n_cells);
+	if (cell_neigh) o->cell_neigh.download(cell_neigh, 6 * o->n_cells);
+	FPOHM_CUDA(cudaStreamSynchronize(o->ctx->stream));
+	FPOHM_API_END
+}
+
+int fpohm_octree_hexes(const fpohm_octree *o, double *Vpos, uint32_t *hex, int32_t *hex2cell) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o, FPOHM_EINVAL, "fpohm_octree_hexes: null octree");
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
+	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
+	if (Vpos) {
+		DevBuf<double> dV(3 * o->n_nodes, s);
+		hex_vertices_kernel<<<grid_for(ctx, 3 * o->n_nodes, blk), blk, 0, s>>>(o->node_pos.p, o->n_nodes, bx, by, bz, o->prm.voxel_size, dV.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		dV.download(Vpos, 3 * o->n_nodes);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	if (hex) {
+		DevBuf<uint32_t> dH(8 * o->n_leaves, s);
+		hex_cells_kernel<<<grid_for(ctx, 8 * o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->cell_corner.p, dH.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		dH.download(hex, 8 * o->n_leaves);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	if (hex2cell) { o->leaf_cell.download(hex2cell, o->n_leaves); FPOHM_CUDA(cudaStreamSynchronize(s)); }
+	FPOHM_API_END
+}
+
+int fpohm_octree_check(const fpohm_octree *o, int32_t *flags) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o && flags, FPOHM_EINVAL, "fpohm_octree_check: null argument");
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	DevBuf<int32_t> bad(2, s);
+	bad.zero();
+	check_kernel<<<grid_for(ctx, o->n_cells, 256), 256, 0, s>>>(o->cell_first_child.p, o->cell_corner.p, o->node_neigh.p, o->n_cells, bad.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	int32_t h[2] = {0, 0};
+	bad.download(h, 2);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	*flags = (h[0] == 0 ? 1 : 0) | (h[1] == 0 ? 2 : 0);
+	FPOHM_API_END
+}
+
+} // extern "C"

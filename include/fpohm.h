@@ -1,0 +1,212 @@
+/*
+ * fpohm.h — C-ABI of the B200-native geometry core (libfpohm.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of
+ * gaoxifeng/Feature-Preserving-Octree-Hex-Meshing.  The reference has no FFI layer (plain C++
+ * headers), so every entry point below names the reference function(s) whose body it replaces
+ * (paths relative to the reference root; ghm.cpp = grid_meshing/grid_hex_meshing.cpp,
+ * gf.cpp = global_functions.cpp, igl/ = extern/libigl/include/igl/).  The C++ shim in
+ * `feature-preserving-octree-hex-meshing_b200/host/fpohm_shim.hpp` re-creates the reference
+ * signatures on top of this header; INTEGRATION.md shows how a maintainer wires it in.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FPOHM_E* code otherwise; it never throws,
+ *     aborts or prints.  fpohm_last_error() returns the message of the calling thread's last failure.
+ *   - plain pointers + sizes only.  Unless a name ends in `_dev`, pointers are HOST pointers and the
+ *     call performs its own H2D/D2H copies (this is what a drop-in caller uses).  `_dev` variants take
+ *     device pointers plus a cudaStream_t (passed as void*) and never synchronise: they are what a
+ *     caller with HBM-resident data (and bench.py's device-timed `value`) uses.
+ *   - vertex arrays are "xyz per vertex", i.e. the memory of the reference's `Mesh::V` (3 x n,
+ *     column-major Eigen, global_types.h:516) or of a row-major n x 3 array — they are the same bytes.
+ *   - there is NO CPU fallback: every compute entry point fails with FPOHM_ENODEV without a CUDA device.
+ */
+#ifndef FPOHM_H
+#define FPOHM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPOHM_OK        0
+#define FPOHM_EINVAL   -1   /* bad argument */
+#define FPOHM_ENODEV   -2   /* no CUDA device / wrong architecture */
+#define FPOHM_ECUDA    -3   /* CUDA runtime error (message in fpohm_last_error) */
+#define FPOHM_ENOMEM   -4
+#define FPOHM_ERANGE   -5   /* integer range exceeded (e.g. > 2^21 finest cells per axis after shift) */
+#define FPOHM_ESTATE   -6   /* object not in the state the call needs */
+
+typedef struct fpohm_ctx    fpohm_ctx;     /* one per GPU: device id, streams, scratch arena            */
+typedef struct fpohm_mesh   fpohm_mesh;    /* device-resident triangle soup + facet bboxes (+ trees)     */
+typedef struct fpohm_octree fpohm_octree;  /* device-resident graded/paired octree                       */
+typedef struct fpohm_conn   fpohm_conn;    /* result of fpohm_hex_connectivity                           */
+
+const char *fpohm_last_error(void);
+const char *fpohm_version(void);
+/* number of visible CUDA devices (0 when none); never fails */
+int fpohm_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* context                                                                                            */
+int  fpohm_ctx_create(int device, fpohm_ctx **out);
+void fpohm_ctx_destroy(fpohm_ctx *ctx);
+int  fpohm_ctx_sync(fpohm_ctx *ctx);
+/* milliseconds of the kernels launched by the last host-pointer call on this ctx (CUDA events) */
+int  fpohm_ctx_last_kernel_ms(fpohm_ctx *ctx, double *ms);
+/* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
+int  fpohm_ctx_launch_count(fpohm_ctx *ctx, int64_t *n);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* triangle mesh (the reference's GEO::Mesh M_i / Mesh mf.tri)                                        */
+int  fpohm_mesh_upload(fpohm_ctx *ctx, const double *V, int64_t nV, const int32_t *F, int64_t nF, fpohm_mesh **out);
+void fpohm_mesh_free(fpohm_mesh *mesh);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* octree (OctreeGrid, grid_meshing/octree.h:62-270, octree.cpp; octree_mesh, ghm.cpp:460-567)        */
+typedef struct fpohm_octree_params {
+	int32_t grid_size[3];      /* finest-cell grid, each a power of two (octree.cpp:26-28)               */
+	double  origin[3];         /* ghm.cpp:484                                                            */
+	double  mesh_transform[3]; /* ghm.cpp:493                                                            */
+	double  voxel_size;        /* ghm.cpp:467-470                                                        */
+	int32_t stop_extent;       /* cells with extent <= stop_extent are never split (ghm.cpp:503)        */
+	int32_t graded;            /* 2:1 over faces and edges (octree.cpp:598-627)                          */
+	int32_t paired;            /* sibling/root pairing (octree.cpp:574-590,632-643)                      */
+	int32_t reserved;
+} fpohm_octree_params;
+
+/* ghm.cpp:463-493: bbox -> voxel_size, grid_size = next_pow2(ceil(extent/voxel_size)), origin, mesh_transform.
+ * Pure host arithmetic in the reference's exact expression order; fills p->grid_size/origin/mesh_transform/voxel_size. */
+int fpohm_octree_grid_setup(const double *V, int64_t nV, int32_t num_voxels, fpohm_octree_params *p);
+
+/* OctreeGrid_initialize + subdivide(should_subdivide, graded, paired): octree.cpp:39-117,648-690 with the
+ * bbox-overlap predicate of ghm.cpp:502-517 (== voxelization.cpp:367-380 when mesh_transform = 0). */
+int  fpohm_octree_build(fpohm_ctx *ctx, const fpohm_mesh *mesh, const fpohm_octree_params *p, fpohm_octree **out);
+/* Same closure, but the set of cells whose predicate is true is given explicitly as (x,y,z,extent) rows:
+ * the floating-point-free form of subdivide(), used for predicate-independent topology parity
+ * (and the equivalent of OctreeGrid::testSubdivideRandom, octree.cpp:900-961). */
+int  fpohm_octree_build_from_marks(fpohm_ctx *ctx, const int32_t grid_size[3], const int32_t *marks, int64_t n_marks,
+                                   int32_t graded, int32_t paired, fpohm_octree **out);
+/* subdivide(pred, graded, paired) on an EXISTING octree with a (smaller) stop_extent — what octree_mesh does on the
+ * later passes of the pipeline's outer loop (ghm.cpp:495-500,523-524): every current leaf is tested, children of
+ * predicate-true cells recursively.  The octree is re-numbered afterwards. */
+int  fpohm_octree_subdivide(fpohm_octree *oct, const fpohm_mesh *mesh, int32_t stop_extent);
+/* subdivide(pred, cells, graded, paired): octree.cpp:691-729 via ghm.cpp:518-521.  cell_ids index the cell
+ * numbering of this octree (fpohm_octree_export); only listed LEAF cells are tested, no recursion into children.
+ * The octree is re-numbered afterwards. */
+int  fpohm_octree_refine(fpohm_octree *oct, const fpohm_mesh *mesh, const int32_t *cell_ids, int64_t n, int32_t stop_extent);
+void fpohm_octree_free(fpohm_octree *oct);
+
+int  fpohm_octree_sizes(const fpohm_octree *oct, int64_t *n_nodes, int64_t *n_cells, int64_t *n_leaves,
+                        int32_t *n_roots, int32_t *max_depth);
+/* m_Nodes / m_Cells (octree.h:16-61,113-114) as SoA: node_pos 3/node, node_neigh 6/node (prev/next per axis),
+ * cell_first_child 1/cell, cell_corner 8/cell (Cube::delta order, common.h:147), cell_neigh 6/cell.
+ * Any pointer may be NULL.  Numbering is canonical (DESIGN.md "octree numbering"), not the reference's
+ * split-order artefact; every structural invariant the pipeline relies on holds. */
+int  fpohm_octree_export(const fpohm_octree *oct, int32_t *node_pos, int32_t *node_neigh, int32_t *cell_first_child,
+                         int32_t *cell_corner, int32_t *cell_neigh);
+/* octree_mesh export, ghm.cpp:527-562: Vpos[3*node] = mesh_transform + origin + nodePos*voxel_size;
+ * hex[8*leaf + lv] = cellCornerId(leaf cell, lv) for leaves in cell order; hex2cell = hex2Octree_map. */
+int  fpohm_octree_hexes(const fpohm_octree *oct, double *Vpos, uint32_t *hex, int32_t *hex2cell);
+/* is2to1Graded / isPaired (octree.cpp:148-202) evaluated on the device; bit0 graded, bit1 paired */
+int  fpohm_octree_check(const fpohm_octree *oct, int32_t *flags);
+/* compute_sign(M, aabb, octree, origin, spacing), voxelization.cpp:101-163: z-ray parity per cell (all cells) */
+int  fpohm_octree_cell_sign(const fpohm_octree *oct, const fpohm_mesh *mesh, const double origin[3], double spacing, float *inside);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* dense voxel grid (VoxelGrid<num_t>, voxelization.h:41-91) + compute_sign (voxelization.h:220-272)  */
+/* dims[d] = ceil(extent[d]/spacing) + 2*padding; origin_out = origin - padding*spacing (voxelization.h:71-82) */
+int fpohm_voxel_grid_setup(const double origin[3], const double extent[3], double spacing, int32_t padding,
+                           int32_t dims[3], double origin_out[3]);
+/* out: dims[0]*dims[1]*dims[2] bytes, x fastest (voxelization.cpp:26-28); 1 = inside */
+int fpohm_voxel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                     const int32_t dims[3], uint8_t *out);
+int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                         const int32_t dims[3], uint8_t *out_dev, void *stream);
+/* subdivision predicate on a dense grid: out[x + nx*(y + ny*z)] = 1 iff some facet AABB overlaps the closed
+ * cell box (geo/basic/geometry.h:612-622 with the box of voxelization.cpp:370-375, extent = 1) */
+int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                          const int32_t dims[3], uint8_t *out);
+/* DexelGrid<double> + compute_sign (voxelization.h:95-138,275-331).  Two-phase: call with values == NULL to get
+ * *total; offsets has dims2[0]*dims2[1]+1 entries (x fastest). */
+int fpohm_dexel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                     const int32_t dims2[2], int64_t *offsets, double *values, int64_t *total);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* query layer                                                                                        */
+/* build_aabb_tree (ghm.cpp:4231-4248): igl::AABB::init (igl/AABB.cpp:94-200, identical tree) + per_face /
+ * per_vertex(ANGLE) / per_edge(UNIFORM) normals.  Idempotent; called lazily by the query entry points. */
+int fpohm_mesh_build_query_tree(fpohm_ctx *ctx, fpohm_mesh *mesh);
+/* Treestr normals (global_types.h:681-691).  n_edges via fpohm_mesh_num_edges.  Any pointer may be NULL. */
+int fpohm_mesh_num_edges(const fpohm_mesh *mesh, int64_t *n_edges);
+int fpohm_mesh_normals(const fpohm_mesh *mesh, double *FN, double *VN, double *EN, int32_t *E, int32_t *EMAP);
+/* pre-order flattening of the igl-identical tree for inspection: box 6/node, primitive, left/right (-1 leaf) */
+int fpohm_mesh_tree_nodes(const fpohm_mesh *mesh, int64_t *n_nodes);
+int fpohm_mesh_tree_export(const fpohm_mesh *mesh, double *box, int32_t *prim, int32_t *lr);
+
+/* The two builders above are host code (they must call the same std:: algorithms as igl); these
+ * device-free variants expose them for CPU-side verification.  Two-phase: pass the capacity in *n_nodes / *n_edges
+ * with output pointers, or NULL outputs to get the sizes. */
+int fpohm_host_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, int64_t *n_nodes,
+                        double *box, int32_t *prim, int32_t *lr);
+int fpohm_host_igl_normals(const double *V, int64_t nV, const int32_t *F, int64_t nF, int64_t *n_edges,
+                           double *FN, double *VN, double *EN, int32_t *E, int32_t *EMAP);
+
+/* igl::signed_distance_pseudonormal batch (igl/signed_distance.cpp:186-218): P np x 3;
+ * S signed distance, I closest facet, C closest point np x 3, N pseudonormal np x 3.  Any output may be NULL.
+ * Callers: points_inside_mesh gf.cpp:4024-4048 (S only), projection_smooth ghm.cpp:3760-3781,
+ * dirty_graph_projection ghm.cpp:4034-4081, node_mapping ghm.cpp:2273, curve_mapping ghm.cpp:2603. */
+int fpohm_signed_distance(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P, int64_t np,
+                          double *S, int32_t *I, double *C, double *N);
+int fpohm_signed_distance_dev(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P_dev, int64_t np,
+                              double *S_dev, int32_t *I_dev, double *C_dev, double *N_dev, void *stream);
+/* igl::point_mesh_squared_distance (igl/point_mesh_squared_distance.cpp:17-46; hausdorff_dis gf.cpp:3590-3604) */
+int fpohm_point_mesh_sqdist(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P, int64_t np,
+                            double *sqrD, int32_t *I, double *C);
+/* hausdorff_dis(mesh0, mesh1, outlierVs, thr), gf.cpp:3590-3628: vertices of A vs B and back; outliers written to
+ * outlier_vs (capacity nV of B), *n_outliers set; the threshold decays x0.9 until the list is non-empty. */
+int fpohm_hausdorff_outliers(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, double dis_threshold,
+                             int32_t *outlier_vs, int64_t *n_outliers);
+
+/* feature-curve projection, LINE branch of dirty_graph_projection (ghm.cpp:3967-3994) + point_line_projection
+ * (gf.cpp:3454-3465).  Curves in CSR over vertex ids of Vc; circle[c] != 0 closes the polyline. */
+int fpohm_polyline_project(fpohm_ctx *ctx, const double *Vc, int64_t nVc, const int64_t *curve_off, const int32_t *curve_vs,
+                           const uint8_t *circle, int64_t n_curves, const double *P, const int32_t *curve_id, int64_t np,
+                           double *origin_L, double *axis_L);
+
+/* scaled_jacobian, Hex branch (gf.cpp:2309-2358) + a_jacobian (gf.cpp:2422-2442), table global_types.h:163-173.
+ * V_Js 8/hex, H_Js 1/hex (either may be NULL), min_ave_dev = {min_Jacobian, ave_Jacobian, deviation_Jacobian}. */
+int fpohm_scaled_jacobian(fpohm_ctx *ctx, const double *V, int64_t nV, const uint32_t *hex, int64_t H,
+                          double *V_Js, double *H_Js, double min_ave_dev[3], int64_t *flipped);
+int fpohm_scaled_jacobian_dev(fpohm_ctx *ctx, const double *V_dev, int64_t nV, const uint32_t *hex_dev, int64_t H,
+                              double *V_Js_dev, double *H_Js_dev, double *min_ave_dev_dev /*3*/, int64_t *flipped_dev,
+                              void *stream);
+
+/* metro two-sided sampled Hausdorff, compute(...) x3 (metro_hausdorff.cpp:12,196,358) with the reference's flags
+ * (vertex sampling only, metro_hausdorff.cpp:39-48).  out = {bbox_diag, max_ab, max_ba, mean_ab, mean_ba,
+ * rms_ab, rms_ba}; n_samples = {n_ab, n_ba}.  extra_face_samples > 0 adds that many similar-triangle face
+ * samples per direction (sampling.h:496-540 rule) — 0 reproduces the reference. */
+int fpohm_hausdorff(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, int64_t extra_face_samples,
+                    double out[7], int64_t n_samples[2]);
+
+/* build_connectivity, Hex branch (gf.cpp:121-186) + adjacency (gf.cpp:226-264) */
+int  fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, fpohm_conn **out);
+int  fpohm_conn_sizes(const fpohm_conn *c, int64_t *nF, int64_t *nE);
+/* F_vs 4/F, F_es 4/F, F_boundary 1/F, E_vs 2/E, E_boundary 1/E, V_boundary 1/V, H_fs 6/H; any may be NULL */
+int  fpohm_conn_fixed(const fpohm_conn *c, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs,
+                      uint8_t *E_boundary, uint8_t *V_boundary, uint32_t *H_fs);
+/* CSR relations; which: 0 F.neighbor_hs 1 E.neighbor_fs 2 E.neighbor_hs 3 V.neighbor_vs 4 V.neighbor_es
+ * 5 V.neighbor_fs 6 V.neighbor_hs.  Call with val == NULL for the total. */
+int  fpohm_conn_csr(const fpohm_conn *c, int32_t which, int64_t *off, uint32_t *val, int64_t *total);
+void fpohm_conn_free(fpohm_conn *c);
+
+/* voxel_meshing lattice (ghm.cpp:215-296, the `--o 0` path): dim[d] = ceil(extent/len), float grid_length,
+ * vertex (i,j,k) id = i*dimY*dimZ + j*dimZ + k; hexes in hex_ref_shape corner order. Two-phase via dims. */
+int fpohm_voxel_lattice_dims(const double bb_min[3], const double bb_max[3], int32_t num_voxels, int32_t dim[3]);
+int fpohm_voxel_lattice(fpohm_ctx *ctx, const double bb_min[3], const double bb_max[3], int32_t num_voxels,
+                        double *Vpos, uint32_t *hex);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPOHM_H */
