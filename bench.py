@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the hot path (BASELINE.json: "voxel+octree build ms and closest-point
+queries/s at 1/2/4/8 B200 vs CPU").
+
+Workload (config[1] of BASELINE.json): procedural CAD gear, 199 680 triangles, feature-preserving octree at max depth 8
+(`--e 12`: stop_extent 2^12 on the 2^20 finest grid).  One STEP = one batch of closest-point + pseudonormal-sign queries
+(igl::signed_distance_pseudonormal, what clean_hex_mesh / projection_smooth / dirty_graph_projection call) over Q query
+points = centres of the octree's leaf hexes plus three jittered copies (Q ~ 4-5 M, 84 B/query => inputs+outputs > 126 MB L2).
+`value` = queries/s with inputs resident in HBM; `e2e` = the same through the host-pointer C-ABI call with pinned host
+buffers (H2D + kernel + D2H inside the timed region).  The octree build (predicate + 2:1/pairing closure + numbering + hex
+export, all on device) and the scaled-Jacobian pass over the same hexes are timed with the same discipline and reported
+under `also`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1: launched under torchrun, one rank per GPU; queries are sharded by range (weak scaling: Q per rank), mesh + tree
+replicated, no data-path collective.  Timing = CUDA events on the launching stream, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+STOP_E = 12            # --e 12  => depth 8 on the 2^20 grid
+BYTES_PER_QUERY = 84   # 24 B read + 8 (S) + 4 (I) + 24 (C) + 24 (N) written
+BYTES_PER_HEX = 104    # J1: 32 B ids + 72 B written ; + 24 B per vertex once
+
+
+def workload(fp):
+    pm = fp.procedural
+    V, F, crease = pm.gear()            # 199 680 triangles, sharp rims + tooth edges
+    return V, F
+
+
+def make_queries(Vh, H, extent_of_leaf, copies=3, seed=1234):
+    centres = Vh[H.astype(np.int64)].mean(1)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = [centres]
+    for _ in range(copies):
+        out.append(centres + (rng.random(centres.shape) - 0.5) * extent_of_leaf[:, None])
+    # keep the spatial (Morton-ish) order of the leaves: copy k of leaf i sits next to leaf i
+    return np.ascontiguousarray(np.stack(out, 1).reshape(-1, 3))
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.samples, self.stop_flag, self.index = [], False, index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5)
+                p = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(p) >= 7:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_reference(V, F, P, seconds_target=12.0):
+    """oracle/_ref (the reference's own igl code) on a bounded sample of the same queries, 1 thread — how the
+    reference runs on Linux (no -fopenmp)."""
+    from oracle import ref_oracle as R
+    rt = R.RefTree(V, F)
+    n = min(len(P), 20000)
+    idx = np.linspace(0, len(P) - 1, n).astype(np.int64)
+    t = time.perf_counter(); rt.signed_distance(P[idx]); dt = time.perf_counter() - t
+    n2 = int(min(len(P), max(n, n * seconds_target / max(dt, 1e-6))))
+    idx = np.linspace(0, len(P) - 1, n2).astype(np.int64)
+    t = time.perf_counter(); rt.signed_distance(P[idx]); dt = time.perf_counter() - t
+    return {"value": n2 / dt, "unit": "queries/s", "cores": 1, "kind": "reference",
+            "sample": f"{n2} of the {len(P)} queries (every k-th), igl::signed_distance_pseudonormal via oracle/_ref, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU code (oracle/_ref) on the same workload, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fpohm_b200 as fp  # procedural generators only; no kernels are launched on this arm
+    from oracle import ref_oracle as R
+    V, F = workload(fp)
+    gs, org, mt, vs = R.octree_grid_setup(V, F, 1 << 20)
+    t = time.perf_counter()
+    ro = R.RefOctree.build(V, F, gs, org, mt, vs, 1 << STOP_E)
+    Vh, H, _ = ro.hexes()
+    build_ms = (time.perf_counter() - t) * 1e3
+    ext = (Vh[H[:, 1].astype(np.int64), 0] - Vh[H[:, 0].astype(np.int64), 0])
+    P = make_queries(Vh, H, ext)
+    rt = R.RefTree(V, F)
+    cores = os.cpu_count() or 1
+    n_step = 40000 * cores
+    idx = np.linspace(0, len(P) - 1, min(n_step, len(P))).astype(np.int64)
+    sample = P[idx]
+    chunks = np.array_split(sample, cores)
+
+    def step():
+        th = [threading.Thread(target=rt.signed_distance, args=(c,)) for c in chunks]
+        [x.start() for x in th]; [x.join() for x in th]
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t) / args.steps
+    val = len(sample) / dt
+    t = time.perf_counter(); R.scaled_jacobian(Vh, H); jac_s = time.perf_counter() - t
+    line = {"impl": "reference", "metric": "closest_point_queries_per_s", "value": val, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "gear 199680 tris, octree depth 8 (--e 12), signed-distance queries = leaf-hex centres x4",
+                       "queries_total": int(len(P)), "queries_per_step": int(len(sample)), "tris": int(len(F)), "leaves": int(len(H))},
+            "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "reference",
+                             "sample": f"{len(sample)} queries per step (every k-th of {len(P)}), {cores} threads over query slices "
+                                       "(what igl's inert `#pragma omp parallel for` would do); oracle/_ref"},
+            "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "also": {"octree_build_ms": build_ms, "octree_build_note": "OctreeGrid::subdivide + hex export, serial (no parallel form exists)",
+                     "jacobian_hexes_per_s": len(H) / jac_s}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import fpohm_b200 as fp
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = fp.Context(local)
+
+    # ---- workload -------------------------------------------------------------------------------------------
+    V, F = workload(fp)
+    mesh = fp.TriMesh(ctx, V, F)
+    prm = fp.octree_grid_setup(V, 1 << 20)
+    prm.c.stop_extent = 1 << STOP_E
+    t0 = time.perf_counter(); mesh.build_aabb_tree(); tree_build_s = time.perf_counter() - t0
+    oct_ = fp.Octree.build(ctx, mesh, prm)
+    Vh, H, _ = oct_.hexes()
+    sizes = oct_.sizes()
+    ext = (Vh[H[:, 1].astype(np.int64), 0] - Vh[H[:, 0].astype(np.int64), 0])
+    P = make_queries(Vh, H, ext)
+    Q = len(P)
+
+    # ---- octree build timing (device work + host orchestration, wall clock bracketed by syncs) ----------------
+    build_ms = []
+    for i in range(args.warmup + 5):
+        ctx.sync(); t0 = time.perf_counter()
+        o2 = fp.Octree.build(ctx, mesh, prm)
+        ctx.sync(); dt = (time.perf_counter() - t0) * 1e3
+        o2.close()
+        if i >= args.warmup:
+            build_ms.append(dt)
+
+    # ---- resident-in-HBM query throughput -----------------------------------------------------------------------
+    stream = torch.cuda.current_stream()
+    dP = torch.from_numpy(P).to(dev)
+    dS = torch.empty(Q, dtype=torch.float64, device=dev); dI = torch.empty(Q, dtype=torch.int32, device=dev)
+    dC = torch.empty(Q, 3, dtype=torch.float64, device=dev); dN = torch.empty(Q, 3, dtype=torch.float64, device=dev)
+
+    def step_dev():
+        mesh.signed_distance_dev(dP.data_ptr(), Q, dS.data_ptr(), dI.data_ptr(), dC.data_ptr(), dN.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
+        step_dev()
+        evs[k + 1].record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * Q / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-pointer C-ABI call, pinned host buffers -------------------------------------------
+    hP = torch.from_numpy(P).pin_memory()
+    hS = torch.empty(Q, dtype=torch.float64).pin_memory(); hI = torch.empty(Q, dtype=torch.int32).pin_memory()
+    hC = torch.empty(Q, 3, dtype=torch.float64).pin_memory(); hN = torch.empty(Q, 3, dtype=torch.float64).pin_memory()
+    import ctypes as C
+
+    def step_e2e():
+        rc = fp.lib().fpohm_signed_distance(ctx.h, mesh.h, C.c_void_p(hP.data_ptr()), C.c_int64(Q), C.c_void_p(hS.data_ptr()),
+                                            C.c_void_p(hI.data_ptr()), C.c_void_p(hC.data_ptr()), C.c_void_p(hN.data_ptr()))
+        assert rc == 0, fp.lib().fpohm_last_error()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, args.steps // 2)
+    for _ in range(n_e2e):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * Q / float(t.item())
+    assert torch.equal(hS.to(dev), dS) and torch.equal(hI.to(dev), dI)  # both paths produce the same bits
+
+    # ---- scaled Jacobian over the same hexes (resident) -----------------------------------------------------------
+    nH, nVh = len(H), len(Vh)
+    dV = torch.from_numpy(Vh).to(dev); dH = torch.from_numpy(H.view(np.int32)).to(dev)
+    dVJ = torch.empty(8 * nH, dtype=torch.float64, device=dev); dHJ = torch.empty(nH, dtype=torch.float64, device=dev)
+    dst = torch.empty(3, dtype=torch.float64, device=dev); dfl = torch.empty(1, dtype=torch.int64, device=dev)
+
+    def step_jac():
+        fp.scaled_jacobian_dev(ctx, dV.data_ptr(), nVh, dH.data_ptr(), nH, dVJ.data_ptr(), dHJ.data_ptr(), dst.data_ptr(), dfl.data_ptr(),
+                               stream.cuda_stream)
+    for _ in range(3):
+        step_jac()
+    torch.cuda.synchronize()
+    ja, jb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ja.record(stream)
+    for _ in range(20):
+        step_jac()
+    jb.record(stream); torch.cuda.synchronize()
+    jac_ms = ja.elapsed_time(jb) / 20
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        k_ms = float(np.mean(kernel_ms))
+        achieved = BYTES_PER_QUERY * Q / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "closest_point_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        jac_bytes = BYTES_PER_HEX * nH + 24 * nVh
+        line = {"metric": "closest_point_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "gear 199680 tris, octree depth 8 (--e 12), signed-distance queries = leaf-hex centres x4",
+                           "queries_per_gpu": int(Q), "tris": int(len(F)), "leaves": int(sizes["leaves"]), "cells": int(sizes["cells"]),
+                           "nodes": int(sizes["nodes"]), "l2_policy": "inputs+outputs per step (%.0f MB) larger than L2 (126 MB)" % (BYTES_PER_QUERY * Q / 1e6),
+                           "sharding": "query range per rank, mesh+tree replicated, no data-path collective"},
+                "roofline": {"bound": "hbm", "kernel": "closest_point_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "note": "84 B/query algorithmic; BVH traversal is L2/latency/fp64-ALU bound by nature (SURVEY.md §7.3 H5)"},
+                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 24 * Q, "d2h_bytes_per_step": 60 * Q},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "also": {"octree_build_ms": float(np.median(build_ms)), "octree_build_ms_min": float(np.min(build_ms)),
+                         "octree_build_note": "fpohm_octree_build: predicate + closure + numbering, device work + host orchestration, wall clock",
+                         "query_tree_build_s_host": tree_build_s,
+                         "jacobian_hexes_per_s": nH / (jac_ms * 1e-3), "jacobian_ms": jac_ms,
+                         "jacobian_roofline": {"bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                               "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak}}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_reference(V, F, P)
+            except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
