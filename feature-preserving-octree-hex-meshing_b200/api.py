@@ -13,7 +13,8 @@ import numpy as np
 
 __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree",
-    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev",
+    "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -319,6 +320,77 @@ class HexConnectivity:
                 setattr(self, nm, (off, val))
         finally:
             lib().fpohm_conn_free(h)
+
+
+class VoxelGrid:
+    """VoxelGrid<num_t> (voxelization.h:41-91): origin/extent/spacing/padding -> dims + padded origin; x-fastest bytes."""
+
+    def __init__(self, origin, extent, spacing: float, padding: int = 0):
+        o, e = _f64(origin), _f64(extent)
+        self.dims = np.zeros(3, np.int32); self.origin = np.zeros(3); self.spacing = float(spacing)
+        _chk(lib().fpohm_voxel_grid_setup(_p(o), _p(e), C.c_double(spacing), C.c_int32(padding), _p(self.dims), _p(self.origin)))
+        self.data = None
+
+    def num_voxels(self):
+        return int(self.dims[0]) * int(self.dims[1]) * int(self.dims[2])
+
+
+# compute_sign(M, aabb, VoxelGrid&), voxelization.h:220-272
+def compute_sign_voxels(ctx: Context, mesh: TriMesh, grid: VoxelGrid):
+    out = np.zeros(grid.num_voxels(), np.uint8)
+    _chk(lib().fpohm_voxel_sign(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(grid.dims), _p(out)))
+    grid.data = out.reshape(grid.dims[2], grid.dims[1], grid.dims[0])
+    return grid.data
+
+
+def voxel_sign_dev(ctx: Context, mesh: TriMesh, grid: VoxelGrid, out_ptr: int, stream: int = 0):
+    _chk(lib().fpohm_voxel_sign_dev(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(grid.dims), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def voxel_occupancy(ctx: Context, mesh: TriMesh, grid: VoxelGrid):
+    out = np.zeros(grid.num_voxels(), np.uint8)
+    _chk(lib().fpohm_voxel_occupancy(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(grid.dims), _p(out)))
+    return out.reshape(grid.dims[2], grid.dims[1], grid.dims[0])
+
+
+# compute_sign(M, aabb, DexelGrid&), voxelization.h:275-331 -> CSR (offsets x-fastest, values)
+def compute_sign_dexels(ctx: Context, mesh: TriMesh, grid: VoxelGrid):
+    d2 = np.ascontiguousarray(grid.dims[:2])
+    tot = C.c_int64()
+    off = np.zeros(int(d2[0]) * int(d2[1]) + 1, np.int64)
+    _chk(lib().fpohm_dexel_sign(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(d2), _p(off), None, C.byref(tot)))
+    val = np.zeros(tot.value)
+    _chk(lib().fpohm_dexel_sign(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(d2), _p(off), _p(val), C.byref(tot)))
+    return off, val
+
+
+# LINE branch of dirty_graph_projection, ghm.cpp:3967-3994
+def polyline_project(ctx: Context, Vc, curve_off, curve_vs, circle, P, curve_id):
+    Vc, P = _f64(Vc), _f64(P).reshape(-1, 3)
+    co = np.ascontiguousarray(curve_off, np.int64); cv = _i32(curve_vs); ci = np.ascontiguousarray(circle, np.uint8); cid = _i32(curve_id)
+    n = len(P)
+    oL = np.zeros((n, 3)); aL = np.zeros((n, 3))
+    _chk(lib().fpohm_polyline_project(ctx.h, _p(Vc), C.c_int64(len(Vc)), _p(co), _p(cv), _p(ci), C.c_int64(len(ci)), _p(P), _p(cid),
+                                      C.c_int64(n), _p(oL), _p(aL)))
+    return oL, aL
+
+
+# metro compute(...), metro_hausdorff.cpp:12,196,358
+def hausdorff(ctx: Context, A: TriMesh, B: TriMesh, extra_face_samples: int = 0):
+    out = np.zeros(7); ns = np.zeros(2, np.int64)
+    _chk(lib().fpohm_hausdorff(ctx.h, A.h, B.h, C.c_int64(extra_face_samples), _p(out), _p(ns)))
+    d = dict(diag=out[0], max_ab=out[1], max_ba=out[2], mean_ab=out[3], mean_ba=out[4], rms_ab=out[5], rms_ba=out[6],
+             n_ab=int(ns[0]), n_ba=int(ns[1]))
+    d["max"] = max(out[1], out[2]); d["mean"] = max(out[3], out[4])
+    d["ratio"] = float(np.float32(d["max"])) / out[0]        # `(float)mesh_dist_max / bbox.Diag()`, metro_hausdorff.cpp:186
+    return d
+
+
+# hausdorff_dis(mesh0, mesh1, outlierVs, thr), gf.cpp:3590-3628
+def hausdorff_outliers(ctx: Context, A: TriMesh, B: TriMesh, dis_threshold: float):
+    out = np.zeros(len(B.V), np.int32); n = C.c_int64()
+    _chk(lib().fpohm_hausdorff_outliers(ctx.h, A.h, B.h, C.c_double(dis_threshold), _p(out), C.byref(n)))
+    return out[:n.value].copy()
 
 
 def voxel_lattice(ctx: Context, bb_min, bb_max, num_voxels: int):

@@ -89,7 +89,9 @@ void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	int64_t P = 1;
 	while (P < nF) P <<= 1;
 	DevBuf<uint32_t> code(nF, s), code2(nF, s);
-	DevBuf<int32_t> idx(nF, s), order(nF, s);
+	DevBuf<int32_t> idx(nF, s);
+	DevBuf<int32_t> &order = m->pred_order;
+	order.alloc(nF, s);
 	const double ex = m->bbox[3] - m->bbox[0], ey = m->bbox[4] - m->bbox[1], ez = m->bbox[5] - m->bbox[2];
 	const int blk = 256;
 	facet_morton_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(m->tri.p, nF, m->bbox[0], m->bbox[1], m->bbox[2],

@@ -44,6 +44,7 @@ struct fpohm_mesh {
 	bool has_pred = false;
 	int64_t pred_nodes = 0;
 	fpohm::DevBuf<double> pred_box;
+	fpohm::DevBuf<int32_t> pred_order; // leaf j of the tree holds facet pred_order[j]
 
 	// query structure
 	bool has_tree = false;
@@ -60,4 +61,8 @@ struct fpohm_mesh {
 namespace fpohm {
 void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
 void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
+// closest point (+ pseudonormal sign when with_sign) of np device-resident points; S = signed distance, or the
+// SQUARED distance when !with_sign.  Any output may be null.
+void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
+                          double *S, int32_t *I, double *C, double *N, cudaStream_t s);
 } // namespace fpohm

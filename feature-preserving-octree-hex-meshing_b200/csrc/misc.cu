@@ -1,0 +1,431 @@
+// Remaining query-layer entry points: feature-curve projection, metro Hausdorff, Hausdorff outliers, voxel lattice,
+// dense subdivision-predicate occupancy.
+#include "mesh.h"
+#include <math_constants.h>
+#include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <cmath>
+
+using namespace fpohm;
+
+namespace {
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 sub(const V3 &a, const V3 &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double dot3(const V3 &a, const V3 &b) { return a.x * b.x + (a.y * b.y + a.z * b.z); } // fixed-size Eigen redux
+__device__ __forceinline__ double sqnorm(const V3 &a) { return a.x * a.x + (a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ V3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
+
+// LINE branch of dirty_graph_projection (ghm.cpp:3967-3994) + point_line_projection (gf.cpp:3454-3465)
+__global__ void polyline_kernel(const double *__restrict__ Vc, const int64_t *__restrict__ off, const int32_t *__restrict__ cvs,
+                                const uint8_t *__restrict__ circle, const double *__restrict__ P, const int32_t *__restrict__ cid,
+                                int64_t np, double *__restrict__ origin_L, double *__restrict__ axis_L)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+		const V3 v = ld3(P + 3 * i);
+		const int c = cid[i];
+		const int32_t *curve = cvs + off[c];
+		const uint32_t size = (uint32_t)(off[c + 1] - off[c]);
+		uint32_t curve_len = size;
+		if (!circle[c]) curve_len--;
+		V3 pv = {0, 0, 0};                 // the reference's pv survives iterations (only matters for NaN t)
+		V3 best_pv = {0, 0, 0}, best_t = {1, 0, 0};
+		double best_d = CUDART_INF;
+		bool have = false;
+		for (uint32_t j = 0; j < curve_len; ++j) {
+			const V3 a = ld3(Vc + 3 * (int64_t)curve[j]), b = ld3(Vc + 3 * (int64_t)curve[(j + 1) % size]);
+			const V3 vv1 = sub(v, a), v21 = sub(b, a);
+			const double nv21_2 = sqnorm(v21);
+			double t;
+			if (nv21_2 >= 1.e-7) t = dot3(vv1, v21) / nv21_2; else t = 0;
+			if (t >= 0.0 && t <= 1.0) pv = {a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z)};
+			else if (t < 0.0) pv = a;
+			else if (t > 1.0) pv = b;
+			const double d = sqrt(sqnorm(sub(v, pv)));
+			// std::sort of pair<dist, idx>: smallest dist, ties -> smallest idx; a NaN dist never wins unless first
+			if (!have || d < best_d) {
+				have = true; best_d = d; best_pv = pv;
+				const double n = sqrt(sqnorm(v21));
+				best_t = {v21.x / n, v21.y / n, v21.z / n}; // (b - a).normalized(): true division in Eigen 3.2
+			}
+		}
+		origin_L[3 * i] = best_pv.x; origin_L[3 * i + 1] = best_pv.y; origin_L[3 * i + 2] = best_pv.z;
+		axis_L[3 * i] = best_t.x; axis_L[3 * i + 1] = best_t.y; axis_L[3 * i + 2] = best_t.z;
+	}
+}
+
+// ---- metro -------------------------------------------------------------------------------------------------------
+__global__ void mark_referenced_kernel(const int32_t *__restrict__ F, int64_t n3, uint8_t *__restrict__ flag) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) flag[F[t]] = 1;
+}
+__global__ void gather_points_kernel(const double *__restrict__ V, const int32_t *__restrict__ idx, int64_t n, double *__restrict__ P) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * n; t += (int64_t)gridDim.x * blockDim.x) P[t] = V[3 * (int64_t)idx[t / 3] + t % 3];
+}
+__global__ void iota_kernel(int32_t *p, int64_t n) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = (int32_t)t;
+}
+// similar-triangle face samples (extern/vcg/sampling.h:496-540 lattice; per-face count from the cumulative density so
+// that faces are independent — the reference never enables face sampling, metro_hausdorff.cpp:47-48)
+__global__ void face_sample_count_kernel(const double *__restrict__ tri, int64_t nF, double density, const double *__restrict__ cum_area,
+                                         int64_t *__restrict__ cnt, int32_t *__restrict__ per_edge)
+{
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x) {
+		const double hi = cum_area[f + 1] * density, lo = cum_area[f] * density;
+		const long long want = (long long)floor(hi) - (long long)floor(lo);
+		int m = 0; long long got = 0;
+		if (want > 0) {
+			m = (int)((sqrt(1.0 + 8.0 * (double)want) + 5.0) / 2.0);
+			got = m >= 4 ? (long long)(m - 2) * (m - 3) / 2 : 0;
+		}
+		cnt[f] = got; per_edge[f] = m;
+	}
+}
+__global__ void tri_area_kernel(const double *__restrict__ tri, int64_t nF, double *__restrict__ area) {
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x) {
+		const double *t = tri + 9 * f;
+		const V3 a = sub(ld3(t + 3), ld3(t)), b = sub(ld3(t + 6), ld3(t));
+		const V3 c = {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+		area[f] = 0.5 * sqrt(sqnorm(c));
+	}
+}
+__global__ void face_samples_kernel(const double *__restrict__ tri, int64_t nF, const int64_t *__restrict__ off, const int32_t *__restrict__ per_edge,
+                                    double *__restrict__ P)
+{
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x) {
+		const int m = per_edge[f];
+		if (m < 4) continue;
+		const double *t = tri + 9 * f;
+		const V3 v0 = ld3(t), v1 = ld3(t + 3), v2 = ld3(t + 6);
+		const double inv = (double)(m - 1);
+		const V3 V1 = {(v1.x - v0.x) / inv, (v1.y - v0.y) / inv, (v1.z - v0.z) / inv};
+		const V3 V2 = {(v2.x - v0.x) / inv, (v2.y - v0.y) / inv, (v2.z - v0.z) / inv};
+		int64_t o = off[f];
+		for (int i = 1; i < m - 1; ++i)
+			for (int j = 1; j < m - 1 - i; ++j) {
+				P[3 * o] = v0.x + (V1.x * (double)i + V2.x * (double)j);
+				P[3 * o + 1] = v0.y + (V1.y * (double)i + V2.y * (double)j);
+				P[3 * o + 2] = v0.z + (V1.z * (double)i + V2.z * (double)j);
+				++o;
+			}
+	}
+}
+
+struct DistPartial { double mx, sum, sumsq; long long n; };
+// AddSample statistics (extern/vcg/sampling.h:244-251) from squared distances
+__global__ void __launch_bounds__(256)
+dist_stats_kernel(const double *__restrict__ sq, int64_t n, double upper, DistPartial *__restrict__ partials) {
+	__shared__ DistPartial sm[8];
+	DistPartial a{-CUDART_INF, 0.0, 0.0, 0};
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const double d = sqrt(sq[i]);
+		if (d >= upper) continue;          // dist == dist_upper_bound: nothing found inside the search radius
+		a.mx = fmax(a.mx, d); a.sum += d; a.sumsq += d * d; a.n += 1;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		a.mx = fmax(a.mx, __shfl_down_sync(0xffffffffu, a.mx, o));
+		a.sum += __shfl_down_sync(0xffffffffu, a.sum, o);
+		a.sumsq += __shfl_down_sync(0xffffffffu, a.sumsq, o);
+		a.n += __shfl_down_sync(0xffffffffu, a.n, o);
+	}
+	if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a.mx = fmax(a.mx, sm[w].mx); a.sum += sm[w].sum; a.sumsq += sm[w].sumsq; a.n += sm[w].n; }
+		partials[blockIdx.x] = a;
+	}
+}
+
+// hausdorff_dis outliers (gf.cpp:3606-3626), one decay round
+__global__ void outlier_flag_kernel(const double *__restrict__ sqAB, const int32_t *__restrict__ I0, int64_t nA, const int32_t *__restrict__ FB,
+                                    const double *__restrict__ sqBA, int64_t nB, double thr, uint8_t *__restrict__ flag)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nA + nB; i += (int64_t)gridDim.x * blockDim.x) {
+		if (i < nA) {
+			if (sqAB[i] > thr) { const int64_t f = I0[i]; flag[FB[3 * f]] = 1; flag[FB[3 * f + 1]] = 1; flag[FB[3 * f + 2]] = 1; }
+		} else {
+			const int64_t j = i - nA;
+			if (sqBA[j] > thr) flag[j] = 1;
+		}
+	}
+}
+
+// voxel_meshing lattice, ghm.cpp:226-291
+__global__ void lattice_vertices_kernel(double mx, double my, double mz, float gx, float gy, float gz, int d0, int d1, int d2,
+                                        double *__restrict__ V)
+{
+	const int64_t n = (int64_t)d0 * d1 * d2;
+	for (int64_t vn = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vn < n; vn += (int64_t)gridDim.x * blockDim.x) {
+		const int i = (int)(vn / ((int64_t)d1 * d2)), j = (int)((vn % ((int64_t)d1 * d2)) / d2), k = (int)(vn % d2);
+		V[3 * vn] = mx + (double)__fmul_rn(gx, (float)i);       // `grid_length[0] * i` is a float product (Vector3f)
+		V[3 * vn + 1] = my + (double)__fmul_rn(gy, (float)j);
+		V[3 * vn + 2] = mz + (double)__fmul_rn(gz, (float)k);
+	}
+}
+__global__ void lattice_hexes_kernel(int d0, int d1, int d2, uint32_t *__restrict__ hex) {
+	const int64_t n = (int64_t)(d0 - 1) * (d1 - 1) * (d2 - 1);
+	for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < n; h += (int64_t)gridDim.x * blockDim.x) {
+		const int a = (int)(h / ((int64_t)(d1 - 1) * (d2 - 1))), b = (int)((h % ((int64_t)(d1 - 1) * (d2 - 1))) / (d2 - 1)), c = (int)(h % (d2 - 1));
+		const int da[8] = {0, 1, 1, 0, 0, 1, 1, 0}, db[8] = {0, 0, 1, 1, 0, 0, 1, 1}, dc[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+		for (int j = 0; j < 8; ++j) hex[8 * h + j] = (uint32_t)(((int64_t)(a + da[j]) * d1 + (b + db[j])) * d2 + (c + dc[j]));
+	}
+}
+
+// dense subdivision predicate: cell (x,y,z) box = origin + spacing*x ... + spacing*1 (voxelization.cpp:370-375, extent 1)
+__global__ void __launch_bounds__(256)
+occupancy_kernel(int nx, int ny, int nz, double ox, double oy, double oz, double sp, const double *__restrict__ box, int64_t P,
+                 uint8_t *__restrict__ out)
+{
+	const int64_t n = (int64_t)nx * ny * nz;
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((int64_t)nx * ny));
+		const double mn0 = ox + sp * x, mn1 = oy + sp * y, mn2 = oz + sp * z;
+		const double mx0 = mn0 + sp * 1, mx1 = mn1 + sp * 1, mx2 = mn2 + sp * 1;
+		int64_t stack[40]; int spx = 0; stack[spx++] = 1;
+		bool hit = false;
+		while (spx > 0) {
+			const int64_t nd = stack[--spx];
+			const double *b = box + 6 * nd;
+			if (mx0 < b[0] || mn0 > b[3] || mx1 < b[1] || mn1 > b[4] || mx2 < b[2] || mn2 > b[5]) continue;
+			if (nd >= P) { hit = true; break; }
+			stack[spx++] = 2 * nd + 1; stack[spx++] = 2 * nd;
+		}
+		out[i] = hit;
+	}
+}
+
+struct Stats { double mx, mean, rms; int64_t n; };
+
+// one direction of Sampling<>::Hausdorff (sampling.h:547-602): samples = referenced vertices of A (+ optional face samples)
+Stats directed(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, int64_t extra, double upper, cudaStream_t s) {
+	const int blk = 256;
+	mesh_ensure_tree(ctx, B, s);
+	DevBuf<uint8_t> flag(A->nV, s);
+	flag.zero();
+	mark_referenced_kernel<<<grid_for(ctx, 3 * A->nF, blk), blk, 0, s>>>(A->F.p, 3 * A->nF, flag.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	DevBuf<int32_t> ids(A->nV, s), sel(A->nV, s);
+	DevBuf<int64_t> cnt(1, s);
+	iota_kernel<<<grid_for(ctx, A->nV, blk), blk, 0, s>>>(ids.p, A->nV);
+	FPOHM_LAUNCH_CHECK(ctx);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids.p, flag.p, sel.p, cnt.p, A->nV, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids.p, flag.p, sel.p, cnt.p, A->nV, s));
+	ctx->launches += 2;
+	int64_t nv = 0;
+	cnt.download(&nv, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	// optional face samples
+	int64_t nf_samples = 0;
+	DevBuf<int64_t> foff;
+	DevBuf<int32_t> per_edge;
+	if (extra > 0) {
+		DevBuf<double> area(A->nF + 1, s), cum(A->nF + 1, s);
+		area.zero();
+		tri_area_kernel<<<grid_for(ctx, A->nF, blk), blk, 0, s>>>(A->tri.p, A->nF, area.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		size_t t2 = 0;
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, area.p, cum.p, A->nF + 1, s));
+		DevBuf<uint8_t> tmp2((int64_t)t2, s);
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, t2, area.p, cum.p, A->nF + 1, s));
+		double total_area = 0;
+		FPOHM_CUDA(cudaMemcpyAsync(&total_area, cum.p + A->nF, 8, cudaMemcpyDeviceToHost, s));
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+		const double density = total_area > 0 ? (double)extra / total_area : 0.0;
+		DevBuf<int64_t> fc(A->nF + 1, s);
+		fc.zero();
+		foff.alloc(A->nF + 1, s); per_edge.alloc(A->nF, s);
+		face_sample_count_kernel<<<grid_for(ctx, A->nF, blk), blk, 0, s>>>(A->tri.p, A->nF, density, cum.p, fc.p, per_edge.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		size_t t3 = 0;
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t3, fc.p, foff.p, A->nF + 1, s));
+		DevBuf<uint8_t> tmp3((int64_t)t3, s);
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp3.p, t3, fc.p, foff.p, A->nF + 1, s));
+		ctx->launches += 2;
+		FPOHM_CUDA(cudaMemcpyAsync(&nf_samples, foff.p + A->nF, 8, cudaMemcpyDeviceToHost, s));
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	const int64_t n = nv + nf_samples;
+	DevBuf<double> P(3 * n, s), sq(n, s);
+	gather_points_kernel<<<grid_for(ctx, 3 * nv, blk), blk, 0, s>>>(A->V.p, sel.p, nv, P.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	if (nf_samples) {
+		face_samples_kernel<<<grid_for(ctx, A->nF, blk), blk, 0, s>>>(A->tri.p, A->nF, foff.p, per_edge.p, P.p + 3 * nv);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
+	launch_closest_point(ctx, B, false, P.p, n, sq.p, nullptr, nullptr, nullptr, s);
+	const int grid = grid_for(ctx, n, blk, 4);
+	DevBuf<DistPartial> part(grid, s);
+	dist_stats_kernel<<<grid, blk, 0, s>>>(sq.p, n, upper, part.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	std::vector<DistPartial> hp((size_t)grid);
+	part.download(hp.data(), grid);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	Stats st{-HUGE_VAL, 0, 0, 0};
+	double sum = 0, sumsq = 0;
+	for (auto &p : hp) { st.mx = std::max(st.mx, p.mx); sum += p.sum; sumsq += p.sumsq; st.n += p.n; } // fixed order
+	st.mean = sum / (double)st.n;
+	st.rms = std::sqrt(sumsq / (double)st.n);
+	return st;
+}
+
+} // namespace
+
+extern "C" {
+
+int fpohm_polyline_project(fpohm_ctx *ctx, const double *Vc, int64_t nVc, const int64_t *curve_off, const int32_t *curve_vs,
+                           const uint8_t *circle, int64_t n_curves, const double *P, const int32_t *curve_id, int64_t np,
+                           double *origin_L, double *axis_L)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && Vc && curve_off && curve_vs && circle && P && curve_id && origin_L && axis_L && nVc > 0 && n_curves > 0 && np >= 0,
+	              FPOHM_EINVAL, "fpohm_polyline_project: bad argument");
+	const int64_t tot = curve_off[n_curves];
+	for (int64_t c = 0; c < n_curves; ++c)
+		FPOHM_REQUIRE(curve_off[c + 1] - curve_off[c] >= 2, FPOHM_EINVAL, "fpohm_polyline_project: curve %lld has fewer than 2 vertices", (long long)c);
+	for (int64_t i = 0; i < tot; ++i) FPOHM_REQUIRE(curve_vs[i] >= 0 && curve_vs[i] < nVc, FPOHM_EINVAL, "fpohm_polyline_project: vertex id out of range");
+	for (int64_t i = 0; i < np; ++i) FPOHM_REQUIRE(curve_id[i] >= 0 && curve_id[i] < n_curves, FPOHM_EINVAL, "fpohm_polyline_project: curve id out of range");
+	if (np == 0) return FPOHM_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	DevBuf<double> dV(3 * nVc, s), dP(3 * np, s), dO(3 * np, s), dA(3 * np, s);
+	DevBuf<int64_t> doff(n_curves + 1, s);
+	DevBuf<int32_t> dcv(tot, s), dcid(np, s);
+	DevBuf<uint8_t> dci(n_curves, s);
+	dV.upload(Vc, 3 * nVc); dP.upload(P, 3 * np); doff.upload(curve_off, n_curves + 1); dcv.upload(curve_vs, tot);
+	dcid.upload(curve_id, np); dci.upload(circle, n_curves);
+	KernelTimer t(ctx, s);
+	polyline_kernel<<<grid_for(ctx, np, 128), 128, 0, s>>>(dV.p, doff.p, dcv.p, dci.p, dP.p, dcid.p, np, dO.p, dA.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	t.stop();
+	dO.download(origin_L, 3 * np); dA.download(axis_L, 3 * np);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_hausdorff(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, int64_t extra_face_samples, double out[7], int64_t n_samples[2]) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && A && B && out && extra_face_samples >= 0, FPOHM_EINVAL, "fpohm_hausdorff: bad argument");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	// joint bbox over ALL vertices, inflated by 2 % of its diagonal (metro_hausdorff.cpp:113-118; vcg Box3::Diag, Offset)
+	double mn[3], mx[3];
+	for (int c = 0; c < 3; ++c) { mn[c] = std::min(A->bbox[c], B->bbox[c]); mx[c] = std::max(A->bbox[3 + c], B->bbox[3 + c]); }
+	auto diag = [&]() { const double dx = mn[0] - mx[0], dy = mn[1] - mx[1], dz = mn[2] - mx[2]; return std::sqrt(dx * dx + dy * dy + dz * dz); };
+	const double off = diag() * 0.02;
+	for (int c = 0; c < 3; ++c) { mn[c] -= off; mx[c] += off; }
+	const double D = diag();
+	KernelTimer t(ctx, s);
+	const Stats ab = directed(ctx, A, B, extra_face_samples, D, s);
+	const Stats ba = directed(ctx, B, A, extra_face_samples, D, s);
+	t.stop();
+	out[0] = D; out[1] = ab.mx; out[2] = ba.mx; out[3] = ab.mean; out[4] = ba.mean; out[5] = ab.rms; out[6] = ba.rms;
+	if (n_samples) { n_samples[0] = ab.n; n_samples[1] = ba.n; }
+	FPOHM_API_END
+}
+
+int fpohm_hausdorff_outliers(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, double dis_threshold, int32_t *outlier_vs, int64_t *n_outliers) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && A && B && outlier_vs && n_outliers, FPOHM_EINVAL, "fpohm_hausdorff_outliers: bad argument");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	mesh_ensure_tree(ctx, A, s); mesh_ensure_tree(ctx, B, s);
+	DevBuf<double> sqAB(A->nV, s), sqBA(B->nV, s);
+	DevBuf<int32_t> I0(A->nV, s);
+	KernelTimer t(ctx, s);
+	launch_closest_point(ctx, B, false, A->V.p, A->nV, sqAB.p, I0.p, nullptr, nullptr, s);   // point_mesh_squared_distance(A, B, FB)
+	launch_closest_point(ctx, A, false, B->V.p, B->nV, sqBA.p, nullptr, nullptr, nullptr, s); // point_mesh_squared_distance(B, A, FA)
+	double thr = dis_threshold * dis_threshold;
+	DevBuf<uint8_t> flag(B->nV, s);
+	DevBuf<int32_t> ids(B->nV, s), sel(B->nV, s);
+	DevBuf<int64_t> cnt(1, s);
+	iota_kernel<<<grid_for(ctx, B->nV, blk), blk, 0, s>>>(ids.p, B->nV);
+	FPOHM_LAUNCH_CHECK(ctx);
+	flag.zero();
+	int64_t n = 0;
+	for (int round = 0; round < 4096 && n == 0; ++round) {      // `while (!outlierVs.size())`, flags persist across rounds
+		outlier_flag_kernel<<<grid_for(ctx, A->nV + B->nV, blk), blk, 0, s>>>(sqAB.p, I0.p, A->nV, B->F.p, sqBA.p, B->nV, thr, flag.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		size_t tb = 0;
+		FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids.p, flag.p, sel.p, cnt.p, B->nV, s));
+		DevBuf<uint8_t> tmp((int64_t)tb, s);
+		FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids.p, flag.p, sel.p, cnt.p, B->nV, s));
+		ctx->launches += 2;
+		cnt.download(&n, 1);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+		thr *= 0.9;
+	}
+	t.stop();
+	*n_outliers = n;
+	sel.download(outlier_vs, n);   // ascending vertex id; the reference's push order differs, the SET is identical
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_voxel_lattice_dims(const double bb_min[3], const double bb_max[3], int32_t num_voxels, int32_t dim[3]) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(bb_min && bb_max && dim && num_voxels > 0, FPOHM_EINVAL, "fpohm_voxel_lattice_dims: bad argument");
+	double extent[3];
+	for (int c = 0; c < 3; ++c) extent[c] = bb_max[c] - bb_min[c];
+	const double max_extent = std::max(extent[0], std::max(extent[1], extent[2]));
+	const double len = max_extent / num_voxels;
+	for (int c = 0; c < 3; ++c) dim[c] = (int32_t)std::ceil(extent[c] / len);
+	FPOHM_API_END
+}
+
+int fpohm_voxel_lattice(fpohm_ctx *ctx, const double bb_min[3], const double bb_max[3], int32_t num_voxels, double *Vpos, uint32_t *hex) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && bb_min && bb_max && num_voxels > 0, FPOHM_EINVAL, "fpohm_voxel_lattice: bad argument");
+	int32_t d[3];
+	int rc = fpohm_voxel_lattice_dims(bb_min, bb_max, num_voxels, d);
+	if (rc) return rc;
+	FPOHM_REQUIRE(d[0] >= 2 && d[1] >= 2 && d[2] >= 2, FPOHM_EINVAL, "fpohm_voxel_lattice: degenerate lattice %d x %d x %d", d[0], d[1], d[2]);
+	float gl[3];
+	for (int c = 0; c < 3; ++c) gl[c] = (float)((bb_max[c] - bb_min[c]) / d[c]);
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int64_t nv = (int64_t)d[0] * d[1] * d[2], nh = (int64_t)(d[0] - 1) * (d[1] - 1) * (d[2] - 1);
+	FPOHM_REQUIRE(nv < (1ll << 31), FPOHM_ERANGE, "fpohm_voxel_lattice: too many vertices");
+	KernelTimer t(ctx, s);
+	if (Vpos) {
+		DevBuf<double> dV(3 * nv, s);
+		lattice_vertices_kernel<<<grid_for(ctx, nv, 256), 256, 0, s>>>(bb_min[0], bb_min[1], bb_min[2], gl[0], gl[1], gl[2], d[0], d[1], d[2], dV.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		dV.download(Vpos, 3 * nv);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	if (hex) {
+		DevBuf<uint32_t> dH(8 * nh, s);
+		lattice_hexes_kernel<<<grid_for(ctx, nh, 256), 256, 0, s>>>(d[0], d[1], d[2], dH.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		dH.download(hex, 8 * nh);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	t.stop();
+	FPOHM_API_END
+}
+
+int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing, const int32_t dims[3], uint8_t *out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims && out && spacing > 0, FPOHM_EINVAL, "fpohm_voxel_occupancy: bad argument");
+	const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+	FPOHM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n < (1ll << 31), FPOHM_ERANGE, "fpohm_voxel_occupancy: bad dims");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	fpohm_mesh *m = const_cast<fpohm_mesh *>(mesh);
+	mesh_ensure_pred(ctx, m, s);
+	DevBuf<uint8_t> d(n, s);
+	KernelTimer t(ctx, s);
+	occupancy_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, s>>>(dims[0], dims[1], dims[2], grid_origin[0], grid_origin[1], grid_origin[2], spacing,
+		m->pred_box.p, m->pred_nodes / 2, d.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	t.stop();
+	d.download(out, n);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+} // extern "C"

@@ -1,0 +1,385 @@
+// z-ray parity inside/outside classification: compute_sign x3.
+//   VoxelGrid   voxelization.h:220-272     DexelGrid  voxelization.h:275-331     OctreeGrid cells  voxelization.cpp:101-163
+//   intersect_ray_z  voxelization.h:194-217      point_in_triangle_2d / orientation (SoS)  voxelization.cpp:57-93
+//   orient_2d_inexact  voxelization.h:169-182    VoxelGrid ctor / voxel_center  voxelization.h:71-91
+//
+// Two stages.
+//   (1) column_hits_kernel — one thread per (x,y) column (or per octree cell): stack descent of the facet-box tree
+//       with the reference's query box (degenerate vertical line for grids, the cell footprint for octree cells,
+//       z range = mesh bbox -/+ spacing, i.e. always overlapping), SoS point-in-triangle at the column centre,
+//       barycentric z and orientation sign.  Hits go to a fixed-capacity per-column scratch (overflow is reported,
+//       never truncated silently).
+//   (2) a consumer per flavour.  The VoxelGrid rule "voxel = [ sum of signs of hits with z < centre_z ] < 0" is
+//       order independent, so voxel_fill_kernel never sorts: it converts each hit to the first layer k0 whose centre
+//       lies above it and streams the column top-down, writing every voxel exactly once (1 B/voxel, 4 columns per
+//       thread -> 128 B per warp store).  Dexel / octree-cell rules need (z, sign) order: tiny in-register sort.
+#include "mesh.h"
+#include "octree.h"
+
+#include <cub/device/device_scan.cuh>
+
+using namespace fpohm;
+
+namespace {
+
+constexpr int HIT_CAP = 32;
+
+// voxelization.cpp:57-68
+__device__ __forceinline__ int orientation(double x1, double y1, double x2, double y2, double &twice_signed_area) {
+	twice_signed_area = y1 * x2 - x1 * y2;
+	if (twice_signed_area > 0) return 1;
+	else if (twice_signed_area < 0) return -1;
+	else if (y2 > y1) return 1;
+	else if (y2 < y1) return -1;
+	else if (x1 > x2) return 1;
+	else if (x1 < x2) return -1;
+	else return 0;
+}
+
+// voxelization.cpp:74-93
+__device__ __forceinline__ bool point_in_triangle_2d(double x0, double y0, double x1, double y1, double x2, double y2,
+                                                     double x3, double y3, double &a, double &b, double &c)
+{
+	x1 -= x0; x2 -= x0; x3 -= x0;
+	y1 -= y0; y2 -= y0; y3 -= y0;
+	const int signa = orientation(x2, y2, x3, y3, a);
+	if (signa == 0) return false;
+	const int signb = orientation(x3, y3, x1, y1, b);
+	if (signb != signa) return false;
+	const int signc = orientation(x1, y1, x2, y2, c);
+	if (signc != signa) return false;
+	const double sum = a + b + c;
+	a /= sum; b /= sum; c /= sum;
+	return true;
+}
+
+// intersect_ray_z, voxelization.h:194-217
+__device__ __forceinline__ int intersect_ray_z(const double *__restrict__ t, double qx, double qy, double &z) {
+	double u, v, w;
+	if (point_in_triangle_2d(qx, qy, t[0], t[1], t[3], t[4], t[6], t[7], u, v, w)) {
+		z = u * t[2] + v * t[5] + w * t[8];
+		const double a11 = t[3] - t[0], a12 = t[4] - t[1], a21 = t[6] - t[0], a22 = t[7] - t[1];
+		const double delta = a11 * a22 - a12 * a21; // GEO::det2x2
+		return delta > 0 ? 1 : (delta < 0 ? -1 : 0);
+	}
+	return 0;
+}
+
+struct ColumnGrid {      // VoxelGrid / DexelGrid columns
+	double ox, oy, spacing;
+	int nx, ny;
+};
+
+// gather hits of the vertical ray through (qx,qy); facets are pre-filtered by the reference's xy box [bx0,bx1]x[by0,by1]
+__device__ __forceinline__ int gather_hits(const double *__restrict__ box, int64_t P, const int32_t *__restrict__ order,
+                                           const double *__restrict__ tri, double bx0, double bx1, double by0, double by1,
+                                           double qx, double qy, double *hz, int8_t *hs, int cap, bool &overflow)
+{
+	int64_t stack[40];
+	int sp = 0, n = 0;
+	stack[sp++] = 1;
+	while (sp > 0) {
+		const int64_t nd = stack[--sp];
+		const double *b = box + 6 * nd;
+		if (bx1 < b[0] || bx0 > b[3] || by1 < b[1] || by0 > b[4]) continue; // bboxes_overlap, z always overlaps
+		if (nd >= P) {
+			double z;
+			const int s = intersect_ray_z(tri + 9 * (int64_t)order[nd - P], qx, qy, z);
+			if (s) {
+				if (n < cap) { hz[n] = z; hs[n] = (int8_t)s; ++n; } else overflow = true;
+			}
+			continue;
+		}
+		stack[sp++] = 2 * nd + 1;
+		stack[sp++] = 2 * nd;
+	}
+	return n;
+}
+
+// std::sort of pair<double,int>: ascending z, then ascending sign
+__device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
+	for (int i = 1; i < n; ++i) {
+		const double z = hz[i]; const int8_t s = hs[i];
+		int j = i - 1;
+		while (j >= 0 && (hz[j] > z || (hz[j] == z && hs[j] > s))) { hz[j + 1] = hz[j]; hs[j + 1] = hs[j]; --j; }
+		hz[j + 1] = z; hs[j + 1] = s;
+	}
+}
+
+__global__ void __launch_bounds__(128)
+column_hits_kernel(ColumnGrid g, const double *__restrict__ box, int64_t P, const int32_t *__restrict__ order,
+                   const double *__restrict__ tri, double *__restrict__ hit_z, int8_t *__restrict__ hit_s,
+                   int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag)
+{
+	const int64_t ncol = (int64_t)g.nx * g.ny;
+	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
+		const int x = (int)(col % g.nx), y = (int)(col / g.nx);
+		const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
+		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
+		bool ov = false;
+		const int n = gather_hits(box, P, order, tri, cx, cx, cy, cy, cx, cy, hz, hs, HIT_CAP, ov);
+		if (ov) atomicExch(overflow_flag, 1);
+		hit_n[col] = n;
+		for (int i = 0; i < n; ++i) { hit_z[col * HIT_CAP + i] = hz[i]; hit_s[col * HIT_CAP + i] = hs[i]; }
+	}
+}
+
+// first layer index k in [0, nz] with  hit_z < (k + 0.5) * spacing + oz   (exactly the comparison of voxelization.h:259-261)
+__device__ __forceinline__ int first_layer_above(double z, double oz, double spacing, int nz) {
+	int k = (int)floor((z - oz) / spacing - 0.5);
+	if (k < 0) k = 0;
+	if (k > nz) k = nz;
+	while (k > 0 && z < ((k - 1) + 0.5) * spacing + oz) --k;
+	while (k < nz && !(z < (k + 0.5) * spacing + oz)) ++k;
+	return k;
+}
+
+// 4 adjacent columns per thread; every voxel written once.
+__global__ void __launch_bounds__(256)
+voxel_fill_kernel(int nx, int ny, int nz, double oz, double spacing, const double *__restrict__ hit_z,
+                  const int8_t *__restrict__ hit_s, const int32_t *__restrict__ hit_n, uint8_t *__restrict__ out)
+{
+	const int gx = (nx + 3) / 4;
+	const int64_t nthreads = (int64_t)gx * ny;
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nthreads; t += (int64_t)gridDim.x * blockDim.x) {
+		const int x4 = (int)(t % gx) * 4, y = (int)(t / gx);
+		// per column: delta[k] applied when the sweep reaches layer k; kept as a sorted small list of (k0, sign)
+		int k0[4][HIT_CAP]; int8_t sg[4][HIT_CAP]; int n[4];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			n[c] = 0;
+			const int x = x4 + c;
+			if (x < nx) {
+				const int64_t col = (int64_t)y * nx + x;
+				const int m = hit_n[col];
+				for (int i = 0; i < m; ++i) {
+					const int k = first_layer_above(hit_z[col * HIT_CAP + i], oz, spacing, nz);
+					const int8_t s = hit_s[col * HIT_CAP + i];
+					int j = n[c] - 1;
+					while (j >= 0 && k0[c][j] > k) { k0[c][j + 1] = k0[c][j]; sg[c][j + 1] = sg[c][j]; --j; }
+					k0[c][j + 1] = k; sg[c][j + 1] = s;
+					++n[c];
+				}
+			}
+		}
+		int cur[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+		const bool vec = (x4 + 3 < nx) && ((nx & 3) == 0);
+		for (int z = 0; z < nz; ++z) {
+			uint8_t v[4];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				while (cur[c] < n[c] && k0[c][cur[c]] <= z) { s[c] += sg[c][cur[c]]; ++cur[c]; }
+				v[c] = s[c] < 0 ? 1 : 0;
+			}
+			const int64_t base = ((int64_t)z * ny + y) * nx + x4; // index_from_index3, voxelization.cpp:26-28
+			if (vec) *reinterpret_cast<uchar4 *>(out + base) = make_uchar4(v[0], v[1], v[2], v[3]);
+			else for (int c = 0; c < 4; ++c) if (x4 + c < nx) out[base + c] = v[c];
+		}
+	}
+}
+
+// DexelGrid: sorted hits reduced to entry/exit events, voxelization.h:312-321
+__global__ void dexel_reduce_kernel(int64_t ncol, double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
+                                    int64_t *__restrict__ count)
+{
+	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
+		const int n = hit_n[col];
+		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
+		for (int i = 0; i < n; ++i) { hz[i] = hit_z[col * HIT_CAP + i]; hs[i] = hit_s[col * HIT_CAP + i]; }
+		sort_hits(hz, hs, n);
+		int m = 0;
+		for (int i = 0, s = 0; i < n; ++i) {
+			const int ds = hs[i];
+			s += ds;
+			if ((s == -1 && ds < 0) || (s == 0 && ds > 0)) hit_z[col * HIT_CAP + m++] = hz[i];
+		}
+		hit_n[col] = m;
+		count[col] = m;
+	}
+}
+__global__ void dexel_emit_kernel(int64_t ncol, const double *__restrict__ hit_z, const int32_t *__restrict__ hit_n,
+                                  const int64_t *__restrict__ off, double *__restrict__ values)
+{
+	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
+		const int n = hit_n[col];
+		for (int i = 0; i < n; ++i) values[off[col] + i] = hit_z[col * HIT_CAP + i];
+	}
+}
+
+// compute_sign(OctreeGrid), voxelization.cpp:114-158: one thread per cell (ALL cells, leaves and internal)
+__global__ void __launch_bounds__(128)
+cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int64_t n_cells, int depth,
+                 double ox, double oy, double oz, double spacing, const double *__restrict__ box, int64_t P,
+                 const int32_t *__restrict__ order, const double *__restrict__ tri, float *__restrict__ inside,
+                 int32_t *__restrict__ overflow_flag)
+{
+	for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n_cells; id += (int64_t)gridDim.x * blockDim.x) {
+		const int sh = depth - lvl[id];
+		const uint64_t c = code[id];
+		const int x = (int)(compact1by2(c) << sh), y = (int)(compact1by2(c >> 1) << sh), z = (int)(compact1by2(c >> 2) << sh);
+		const int extent = 1 << sh;
+		const double bx0 = ox + spacing * x, by0 = oy + spacing * y;
+		const double bx1 = bx0 + spacing * extent, by1 = by0 + spacing * extent;
+		const double cx = bx0 + 0.5 * spacing * extent, cy = by0 + 0.5 * spacing * extent;
+		const double cz = oz + spacing * z + 0.5 * spacing * extent;
+		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
+		bool ov = false;
+		const int n = gather_hits(box, P, order, tri, bx0, bx1, by0, by1, cx, cy, hz, hs, HIT_CAP, ov);
+		if (ov) atomicExch(overflow_flag, 1);
+		sort_hits(hz, hs, n);
+		int num_before = 0;
+		for (int i = 0, s = 0; i < n; ++i) {
+			const int ds = hs[i];
+			s += ds;
+			if ((s == -1 && ds < 0) || (s == 0 && ds > 0)) { if (hz[i] < cz) ++num_before; }
+		}
+		inside[id] = (num_before % 2 == 1) ? 1.0f : 0.0f;
+	}
+}
+
+struct HitScratch {
+	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> n, ov;
+};
+
+void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s) {
+	mesh_ensure_pred(ctx, mesh, s);
+	const int64_t ncol = (int64_t)g.nx * g.ny;
+	h.z.alloc(ncol * HIT_CAP, s); h.s.alloc(ncol * HIT_CAP, s); h.n.alloc(ncol, s); h.ov.alloc(1, s);
+	h.ov.zero();
+	column_hits_kernel<<<grid_for(ctx, ncol, 128, 16), 128, 0, s>>>(g, mesh->pred_box.p, mesh->pred_nodes / 2, mesh->pred_order.p,
+		mesh->tri.p, h.z.p, h.s.p, h.n.p, h.ov.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+}
+
+void check_overflow(HitScratch &h, cudaStream_t s, const char *who) {
+	int32_t ov = 0;
+	h.ov.download(&ov, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_REQUIRE(ov == 0, FPOHM_ERANGE, "%s: more than %d ray/facet hits in one column", who, HIT_CAP);
+}
+
+void check_dims(const int32_t *dims, int nd, const char *who) {
+	int64_t prod = 1;
+	for (int d = 0; d < nd; ++d) {
+		FPOHM_REQUIRE(dims[d] > 0, FPOHM_EINVAL, "%s: dims[%d]=%d", who, d, dims[d]);
+		prod *= dims[d];
+	}
+	FPOHM_REQUIRE(prod < (1ll << 31), FPOHM_ERANGE, "%s: %lld voxels overflow the reference's int indexing (voxelization.h:55)", who, (long long)prod);
+}
+
+} // namespace
+
+extern "C" {
+
+int fpohm_voxel_grid_setup(const double origin[3], const double extent[3], double spacing, int32_t padding,
+                           int32_t dims[3], double origin_out[3])
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(origin && extent && dims && origin_out && spacing > 0 && padding >= 0, FPOHM_EINVAL, "fpohm_voxel_grid_setup: bad argument");
+	for (int d = 0; d < 3; ++d) {
+		origin_out[d] = origin[d] - padding * spacing * 1.0;             // m_origin -= padding * spacing * vec3(1,1,1)
+		dims[d] = (int)std::ceil(extent[d] / spacing) + 2 * padding;     // voxelization.h:76-78
+	}
+	FPOHM_API_END
+}
+
+int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                         const int32_t dims[3], uint8_t *out_dev, void *stream)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims && out_dev && spacing > 0, FPOHM_EINVAL, "fpohm_voxel_sign_dev: bad argument");
+	check_dims(dims, 3, "fpohm_voxel_sign_dev");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	HitScratch h;
+	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1]};
+	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
+	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1];
+	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 8), 256, 0, s>>>(dims[0], dims[1], dims[2], grid_origin[2], spacing, h.z.p, h.s.p, h.n.p, out_dev);
+	FPOHM_LAUNCH_CHECK(ctx);
+	check_overflow(h, s, "fpohm_voxel_sign");
+	FPOHM_API_END
+}
+
+int fpohm_voxel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                     const int32_t dims[3], uint8_t *out)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims && out && spacing > 0, FPOHM_EINVAL, "fpohm_voxel_sign: bad argument");
+	check_dims(dims, 3, "fpohm_voxel_sign");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+	DevBuf<uint8_t> d(n, s);
+	KernelTimer t(ctx, s);
+	const int rc = fpohm_voxel_sign_dev(ctx, mesh, grid_origin, spacing, dims, d.p, s);
+	t.stop();
+	if (rc != FPOHM_OK) return rc;
+	d.download(out, n);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_dexel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                     const int32_t dims2[2], int64_t *offsets, double *values, int64_t *total)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims2 && total && spacing > 0, FPOHM_EINVAL, "fpohm_dexel_sign: bad argument");
+	check_dims(dims2, 2, "fpohm_dexel_sign");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	HitScratch h;
+	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims2[0], dims2[1]};
+	const int64_t ncol = (int64_t)dims2[0] * dims2[1];
+	KernelTimer t(ctx, s);
+	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
+	DevBuf<int64_t> cnt(ncol + 1, s), off(ncol + 1, s);
+	cnt.zero();
+	dexel_reduce_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, ncol + 1, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, ncol + 1, s));
+	ctx->launches += 2;
+	int64_t tot = 0;
+	FPOHM_CUDA(cudaMemcpyAsync(&tot, off.p + ncol, 8, cudaMemcpyDeviceToHost, s));
+	check_overflow(h, s, "fpohm_dexel_sign");
+	*total = tot;
+	if (values) {
+		DevBuf<double> dv(tot, s);
+		dexel_emit_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.n.p, off.p, dv.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		dv.download(values, tot);
+	}
+	t.stop();
+	if (offsets) off.download(offsets, ncol + 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_octree_cell_sign(const fpohm_octree *o, const fpohm_mesh *mesh, const double origin[3], double spacing, float *inside) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(o && mesh && origin && inside && spacing > 0, FPOHM_EINVAL, "fpohm_octree_cell_sign: bad argument");
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	fpohm_mesh *m = const_cast<fpohm_mesh *>(mesh);
+	mesh_ensure_pred(ctx, m, s);
+	DevBuf<float> d(o->n_cells, s);
+	DevBuf<int32_t> ov(1, s);
+	ov.zero();
+	KernelTimer t(ctx, s);
+	cell_sign_kernel<<<grid_for(ctx, o->n_cells, 128, 16), 128, 0, s>>>(o->cell_level.p, o->cell_code.p, o->n_cells, o->depth,
+		origin[0], origin[1], origin[2], spacing, m->pred_box.p, m->pred_nodes / 2, m->pred_order.p, m->tri.p, d.p, ov.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	t.stop();
+	int32_t hov = 0;
+	ov.download(&hov, 1);
+	d.download(inside, o->n_cells);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_REQUIRE(hov == 0, FPOHM_ERANGE, "fpohm_octree_cell_sign: more than %d ray/facet hits for one cell", HIT_CAP);
+	FPOHM_API_END
+}
+
+} // extern "C"

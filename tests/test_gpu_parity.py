@@ -140,3 +140,163 @@ def test_octree_subdivide_and_refine_vs_reference(fp, ctx, ref):
     o.refine(m, opick, 1 << 14)
     assert_octree_equal(r.export(), o.export())
     o.close(); m.close()
+
+
+def test_hex_connectivity_vs_reference(fp, ctx, ref):
+    pm = fp.procedural
+    V, H = pm.warped_hex_block(6)
+    cases = [(H, len(V))]
+    # an octree hex mesh has T-junction faces (a big face vs four small ones are DIFFERENT faces): many boundary faces
+    Vt, Ft = pm.torus(40, 24)
+    m = fp.TriMesh(ctx, Vt, Ft)
+    p = fp.octree_grid_setup(Vt); p.c.stop_extent = 1 << 16
+    o = fp.Octree.build(ctx, m, p)
+    Vh, Hh, _ = o.hexes()
+    cases.append((Hh, len(Vh)))
+    for Hx, nV in cases:
+        c = fp.HexConnectivity(ctx, Hx, nV)
+        r = ref.hex_connectivity(Hx, nV)
+        for k in ("F_vs", "F_es", "F_boundary", "E_vs", "E_boundary", "V_boundary", "H_fs"):
+            assert np.array_equal(getattr(c, k), r[k]), k
+        for k in fp.HexConnectivity.NAMES:
+            off, val = getattr(c, k)
+            assert np.array_equal(off, r[k][0]) and np.array_equal(val, r[k][1]), k
+    o.close(); m.close()
+
+
+def test_voxel_sign_vs_reference(fp, ctx, ref):
+    for name, (V, F) in _meshes(fp).items():
+        m = fp.TriMesh(ctx, V, F)
+        mn, ext = V.min(0), V.max(0) - V.min(0)
+        for spacing, padding in ((1 / 24, 1), (1 / 37.5, 2)):
+            g = fp.VoxelGrid(mn, ext, spacing, padding)
+            vox = fp.compute_sign_voxels(ctx, m, g)
+            rvox, rdims = ref.voxel_sign(V, F, mn, ext, spacing, padding)
+            assert np.array_equal(g.dims, rdims)
+            assert np.array_equal(vox, rvox), (name, int((vox != rvox).sum()))
+            assert vox.sum() > 0
+            off, val = fp.compute_sign_dexels(ctx, m, g)
+            roff, rval, rd2 = ref.dexel_sign(V, F, mn, ext, spacing, padding)
+            assert np.array_equal(off, roff) and np.array_equal(val, rval), name
+        m.close()
+
+
+def test_octree_cell_sign_vs_reference(fp, ctx, ref):
+    V, F = fp.procedural.torus(60, 40)
+    mn, ext = V.min(0), V.max(0) - V.min(0)
+    spacing = 1 / 64
+    # compute_octree (voxelization.cpp:353-391): mesh_transform = 0, split down to extent 1
+    gs = np.array([1 << int(np.ceil(np.log2(np.ceil(e / spacing)))) for e in ext], np.int32)
+    m = fp.TriMesh(ctx, V, F)
+    p = fp.OctreeParams(gs, mn, [0, 0, 0], spacing, 1)
+    o = fp.Octree.build(ctx, m, p)
+    r = ref.RefOctree.build(V, F, gs, mn, [0, 0, 0], spacing, 1)
+    assert_octree_equal(r.export(), o.export())
+    ins = o.cell_sign(m, mn, spacing)
+    rins = r.cell_sign(mn, spacing)
+
+    def keyed(ex, val):
+        c0 = ex["node_pos"][ex["corner"][:, 0]]
+        e = ex["node_pos"][ex["corner"][:, 1]][:, 0] - c0[:, 0]
+        k = np.concatenate([c0, e[:, None], val[:, None].astype(np.int64)], 1)
+        return k[np.lexsort(k.T[::-1])]
+    assert np.array_equal(keyed(o.export(), ins), keyed(r.export(), rins))
+    assert 0 < ins.sum() < len(ins)
+    # the one public end-to-end entry, compute_octree: same leaves / inside flags
+    rV, rH, rin = ref.compute_octree(V, F, mn, ext, spacing, 0, True, True)
+    assert len(rH) == o.sizes()["leaves"] and int(rin.sum()) == int(ins[o.export()["first_child"] < 0].sum())
+    o.close(); m.close()
+
+
+def test_voxel_occupancy_matches_octree_predicate(fp, ctx, ref):
+    V, F = fp.procedural.torus(40, 24)
+    mn, ext = V.min(0), V.max(0) - V.min(0)
+    spacing = 1 / 32
+    gs = np.array([1 << int(np.ceil(np.log2(np.ceil(e / spacing)))) for e in ext], np.int32)
+    m = fp.TriMesh(ctx, V, F)
+    g = fp.VoxelGrid(mn, gs * spacing - 1e-9, spacing, 0)
+    assert np.array_equal(g.dims, gs)
+    occ = fp.voxel_occupancy(ctx, m, g)
+    # reference: ungraded, unpaired bbox-predicate octree down to extent 1: a cell is split iff every ancestor's and its
+    # own predicate is true, so every occupied voxel lies in a split extent-2 cell
+    r = ref.RefOctree.build(V, F, gs, mn, [0, 0, 0], spacing, 1, graded=False, paired=False)
+    ex = r.export()
+    c0 = ex["node_pos"][ex["corner"][:, 0]]; e = ex["node_pos"][ex["corner"][:, 1]][:, 0] - c0[:, 0]
+    split2 = c0[(e == 2) & (ex["first_child"] >= 0)]
+    cover = np.zeros_like(occ)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                cover[split2[:, 2] + dz, split2[:, 1] + dy, split2[:, 0] + dx] = 1
+    assert occ.sum() > 0 and np.all(cover[occ > 0] == 1)
+    m.close()
+
+
+def test_polyline_projection_vs_reference(fp, ctx, ref):
+    V, F, crease = fp.procedural.gear(teeth=8, n_radial=3, n_axial=5, n_arc=2)
+    rng = np.random.default_rng(2)
+    loops = [np.arange(0, 40, dtype=np.int32), np.arange(100, 130, dtype=np.int32), np.array([5, 9, 17, 33, 2], np.int32)]
+    circle = np.array([1, 1, 0], np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(l) for l in loops])]).astype(np.int64)
+    cvs = np.concatenate(loops)
+    P = rng.uniform(-0.5, 0.5, (3000, 3)); cid = rng.integers(0, 3, 3000).astype(np.int32)
+    oL, aL = fp.polyline_project(ctx, V, off, cvs, circle, P, cid)
+    roL, raL = ref.polyline_project(V, off, cvs, circle, P, cid)
+    assert np.array_equal(oL, roL) and np.array_equal(aL, raL)
+
+
+def test_hausdorff_vs_reference(fp, ctx, ref):
+    pm = fp.procedural
+    VA, FA = pm.torus(60, 40)
+    VB, FB = pm.torus(33, 21)
+    VB = VB * 1.01 + 0.003
+    A, B = fp.TriMesh(ctx, VA, FA), fp.TriMesh(ctx, VB, FB)
+    h = fp.hausdorff(ctx, A, B)
+    r = ref.hausdorff(VA, FA, VB, FB)
+    # north star: Hausdorff distance within 1e-5 relative (VCG's PointDistanceEP is not our exact closest point)
+    np.testing.assert_allclose([h["diag"], h["max"], h["mean"]], [r["diag"], r["max"], r["mean"]], rtol=1e-5)
+    assert h["diag"] == r["diag"]
+    ok, ratio = ref.hausdorff_ratio(VA, FA, VB, FB, 0.005)
+    np.testing.assert_allclose(h["ratio"], ratio, rtol=1e-5)
+    assert h["n_ab"] == len(VA) and h["n_ba"] == len(VB)
+    h2 = fp.hausdorff(ctx, A, B, extra_face_samples=200000)
+    assert h2["n_ab"] > h["n_ab"] and h2["max_ab"] >= h["max_ab"] - 1e-15
+    A.close(); B.close()
+
+
+def test_hausdorff_outliers_vs_reference(fp, ctx, ref):
+    pm = fp.procedural
+    VA, FA = pm.torus(40, 24)
+    VB, FB = pm.torus(30, 20)
+    VB = VB.copy(); VB[:50] *= 1.05
+    A, B = fp.TriMesh(ctx, VA, FA), fp.TriMesh(ctx, VB, FB)
+    out = fp.hausdorff_outliers(ctx, A, B, 0.02)
+    dAB, I0, _ = ref.point_mesh_sqdist(VB, FB, VA)
+    dBA, _, _ = ref.point_mesh_sqdist(VA, FA, VB)
+    thr = 0.02 ** 2
+    flag = np.zeros(len(VB), bool)
+    while not flag.any():
+        flag[FB[I0[dAB > thr]].reshape(-1)] = True
+        flag[np.nonzero(dBA > thr)[0]] = True
+        thr *= 0.9
+    assert np.array_equal(np.sort(out), np.nonzero(flag)[0])
+    A.close(); B.close()
+
+
+def test_voxel_lattice(fp, ctx):
+    mn, mx = np.array([-0.5, -0.31, -0.2]), np.array([0.5, 0.33, 0.21])
+    Vp, H, dim = fp.voxel_lattice(ctx, mn, mx, 40)
+    # numpy restatement of ghm.cpp:226-291 (float grid_length, float product)
+    ext = mx - mn
+    ln = ext.max() / 40
+    d = np.ceil(ext / ln).astype(np.int64)
+    assert np.array_equal(dim, d)
+    gl = (ext / d).astype(np.float32)
+    i, j, k = np.meshgrid(np.arange(d[0]), np.arange(d[1]), np.arange(d[2]), indexing="ij")
+    ref_V = np.stack([mn[0] + (gl[0] * i.astype(np.float32)).astype(np.float64), mn[1] + (gl[1] * j.astype(np.float32)).astype(np.float64),
+                      mn[2] + (gl[2] * k.astype(np.float32)).astype(np.float64)], -1).reshape(-1, 3)
+    assert np.array_equal(Vp, ref_V)
+    idx = np.arange(d.prod()).reshape(d)
+    c = lambda a, b, cc: idx[a:d[0] - 1 + a, b:d[1] - 1 + b, cc:d[2] - 1 + cc].reshape(-1)
+    ref_H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
+    assert np.array_equal(H, ref_H.astype(np.uint32))
