@@ -1,0 +1,224 @@
+"""CPU suite (-m "not gpu"): the oracle port against the golden vectors (and against oracle/_ref when present), the host
+logic of the product library, the C-ABI surface, and the multi-process sharding logic over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from canon import canon_octree, canon_hexes
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(ROOT / "tests" / "golden" / "golden_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port_oracle
+    if not port_oracle.available():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle" / "port")], check=True)
+    return port_oracle
+
+
+def _canon_equal(canon, G, prefix):
+    for k, v in canon.items():
+        g = G[f"{prefix}_{k}"]
+        assert v.shape == g.shape and np.array_equal(v, g), f"{prefix}_{k}"
+
+
+# ---- oracle port vs golden (golden = reference output) ----------------------------------------------------------
+def test_port_scaled_jacobian(port, G):
+    VJ, HJ, mad, fl = port.scaled_jacobian(G["jac_V"], G["jac_H"])
+    assert np.array_equal(VJ, G["jac_VJ"]) and np.array_equal(HJ, G["jac_HJ"]) and fl == int(G["jac_flipped"])
+    assert np.array_equal(mad, G["jac_mad"])          # same sequential sums as gf.cpp:2341-2354
+    assert fl > 0                                     # the fixture really has flipped hexes
+
+
+def test_port_tree_normals_signed_distance(port, G):
+    t = port.PortTree(G["sd_V"], G["sd_F"])
+    box, prim, lr = t.flatten()
+    assert np.array_equal(box, G["sd_box"]) and np.array_equal(prim, G["sd_prim"]) and np.array_equal(lr, G["sd_lr"])
+    FN, VN, EN, EMAP = t.normals()
+    assert np.array_equal(FN, G["sd_FN"]) and np.array_equal(VN, G["sd_VN"]) and np.array_equal(EN, G["sd_EN"]) and np.array_equal(EMAP, G["sd_EMAP"])
+    S, I, Cc, N = t.signed_distance(G["sd_P"])
+    assert np.array_equal(S, G["sd_S"]) and np.array_equal(I, G["sd_I"]) and np.array_equal(Cc, G["sd_C"]) and np.array_equal(N, G["sd_N"])
+    D2 = t.signed_distance(G["sd_P"], with_sign=False)[0]
+    assert np.array_equal(D2, G["sd_D2"])
+    assert (S < 0).any() and (S > 0).any()
+
+
+def test_port_signed_distance_on_tied_mesh(port, G):
+    """Structured mesh with tied barycentre coordinates: the port's tree may differ from igl's (documented in
+    fpohm_port.c), so the facet index may differ — but only at exact distance ties."""
+    t = port.PortTree(G["tie_V"], G["tie_F"])
+    S, I, Cc, N = t.signed_distance(G["tie_P"])
+    assert np.array_equal(np.abs(S), np.abs(G["tie_S"]))
+    same = I == G["tie_I"]
+    assert np.array_equal(S[same], G["tie_S"][same]) and np.array_equal(Cc[same], G["tie_C"][same]) and np.array_equal(N[same], G["tie_N"][same])
+    np.testing.assert_allclose(Cc, G["tie_C"], rtol=0, atol=1e-12)
+    assert same.mean() > 0.9
+
+
+def test_port_octree(port, G):
+    gs, org, mt, vs = port.octree_grid_setup(G["sd_V"], 1 << 20)
+    assert np.array_equal(gs, G["oct_gs"]) and np.array_equal(org, G["oct_origin"]) and np.array_equal(mt, G["oct_mt"]) and vs == float(G["oct_vs"])
+    for E in (17, 16):
+        o = port.octree_build(G["sd_V"], G["sd_F"], gs, org, mt, vs, 1 << E)
+        ex = o.export()
+        _canon_equal(canon_octree(ex), G, f"oct{E}")
+        Vp, Hx, _ = port.octree_hexes(ex, org, mt, vs)
+        assert np.array_equal(canon_hexes(Vp, Hx), G[f"oct{E}_hexpos"])
+
+
+def test_port_octree_marks_all_modes(port, G):
+    for ci in range(int(G["marks_n"])):
+        gr, pa = G[f"marks{ci}_mode"]
+        o = port.octree_from_marks(G[f"marks{ci}_gs"], G[f"marks{ci}_marks"], bool(gr), bool(pa))
+        _canon_equal(canon_octree(o.export()), G, f"marks{ci}")
+
+
+def test_port_ray_parity(port, G):
+    V, F = G["sd_V"], G["sd_F"]
+    mn, ext = V.min(0), V.max(0) - V.min(0)
+    vox, dims = port.voxel_sign(V, F, mn, ext, float(G["vox_spacing"]), int(G["vox_pad"]))
+    assert np.array_equal(dims, G["vox_dims"]) and np.array_equal(vox, G["vox_out"]) and vox.sum() > 0
+    off, val, _ = port.dexel_sign(V, F, mn, ext, float(G["vox_spacing"]), int(G["vox_pad"]))
+    assert np.array_equal(off, G["dex_off"]) and np.array_equal(val, G["dex_val"])
+    sp = float(G["cs_spacing"])
+    o = port.octree_build(V, F, G["cs_gs"], mn, [0, 0, 0], sp, 1)
+    ex = o.export()
+    ins = port.octree_cell_sign(V, F, ex, mn, sp)
+    c0 = ex["node_pos"][ex["corner"][:, 0]]; e = ex["node_pos"][ex["corner"][:, 1]][:, 0] - c0[:, 0]
+    key = np.concatenate([c0, e[:, None], ins[:, None].astype(np.int64)], 1)
+    assert np.array_equal(key[np.lexsort(key.T[::-1])], G["cs_keyed"])
+
+
+def test_port_connectivity(port, G):
+    c = port.hex_connectivity(G["conn_H"], int(G["conn_nV"]))
+    for k in ("F_vs", "F_es", "F_boundary", "E_vs", "E_boundary", "V_boundary", "H_fs"):
+        assert np.array_equal(c[k], G[f"conn_{k}"]), k
+    for k in ("F_nhs", "E_nfs", "E_nhs", "V_nvs", "V_nes", "V_nfs", "V_nhs"):
+        assert np.array_equal(c[k][0], G[f"conn_{k}_off"]) and np.array_equal(c[k][1], G[f"conn_{k}_val"]), k
+
+
+def test_port_polyline_and_hausdorff(port, G):
+    oL, aL = port.polyline_project(G["sd_V"], G["pl_off"], G["pl_vs"], G["pl_circle"], G["pl_P"], G["pl_cid"])
+    assert np.array_equal(oL, G["pl_origin"]) and np.array_equal(aL, G["pl_axis"])
+    h = port.hausdorff(G["sd_V"], G["sd_F"], G["hd_VB"], G["hd_FB"])
+    assert h["diag"] == G["hd_out"][0]
+    np.testing.assert_allclose([h["max"], h["mean"]], G["hd_out"][1:], rtol=1e-5)   # tolerance of the north star
+
+
+# ---- golden vs the live reference (only where oracle/_ref exists): keeps the fixtures honest ------------------------
+def test_golden_matches_live_reference(ref, G):
+    VJ, HJ, mad, fl = ref.scaled_jacobian(G["jac_V"], G["jac_H"])
+    assert np.array_equal(VJ, G["jac_VJ"]) and np.array_equal(mad, G["jac_mad"])
+    S, I, Cc, N = ref.RefTree(G["sd_V"], G["sd_F"]).signed_distance(G["sd_P"])
+    assert np.array_equal(S, G["sd_S"]) and np.array_equal(I, G["sd_I"])
+    ro = ref.RefOctree.build(G["sd_V"], G["sd_F"], G["oct_gs"], G["oct_origin"], G["oct_mt"], float(G["oct_vs"]), 1 << 16)
+    _canon_equal(canon_octree(ro.export()), G, "oct16")
+
+
+def test_reference_random_split_fuzz_is_valid(ref):
+    """OctreeGrid::testSubdivideRandom (octree.cpp:900-961), the reference's only self-check, runs clean."""
+    o = ref.RefOctree.random([16, 16, 8], True, True)
+    assert o.flags() == (True, True) and o.sizes()["cells"] > 2
+
+
+# ---- host logic of the product (no GPU needed) -------------------------------------------------------------------------
+def test_host_igl_tree_identical_to_reference_even_with_ties(fp, G):
+    for tag in ("sd", "tie"):     # "tie": structured gear, equal barycentre coordinates -> std::sort / nth_element tie order
+        box, prim, lr = fp.host_igl_tree(G[f"{tag}_V"], G[f"{tag}_F"])
+        assert np.array_equal(box, G[f"{tag}_box"]) and np.array_equal(prim, G[f"{tag}_prim"]) and np.array_equal(lr, G[f"{tag}_lr"]), tag
+    FN, VN, EN, E, EMAP = fp.host_igl_normals(G["sd_V"], G["sd_F"])
+    assert np.array_equal(FN, G["sd_FN"]) and np.array_equal(VN, G["sd_VN"]) and np.array_equal(EN, G["sd_EN"]) and np.array_equal(EMAP, G["sd_EMAP"])
+
+
+def test_host_grid_setups(fp, port, G):
+    p = fp.octree_grid_setup(G["sd_V"], 1 << 20)
+    assert np.array_equal(p.grid_size, G["oct_gs"]) and np.array_equal(p.origin, G["oct_origin"])
+    assert np.array_equal(p.mesh_transform, G["oct_mt"]) and p.voxel_size == float(G["oct_vs"])
+    V = G["sd_V"]
+    g = fp.VoxelGrid(V.min(0), V.max(0) - V.min(0), float(G["vox_spacing"]), int(G["vox_pad"]))
+    assert np.array_equal(g.dims, G["vox_dims"])
+    dims, o = port.voxel_grid_setup(V.min(0), V.max(0) - V.min(0), float(G["vox_spacing"]), int(G["vox_pad"]))
+    assert np.array_equal(g.origin, o)
+
+
+def test_tiny_meshes_host_tree(fp):
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    for F in ([[0, 1, 2]], [[0, 1, 2], [0, 1, 3]], [[0, 1, 2], [0, 1, 3], [0, 2, 3]]):   # 1, 2 (igl::sort2), 3 (igl::sort3) facets
+        box, prim, lr = fp.host_igl_tree(V, np.array(F, np.int32))
+        assert len(prim) == 2 * len(F) - 1 and sorted(prim[prim >= 0].tolist()) == list(range(len(F)))
+
+
+# ---- C-ABI surface --------------------------------------------------------------------------------------------------------
+def test_abi_exports_every_declared_symbol(fp):
+    hdr = (ROOT / "include" / "fpohm.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(fpohm_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 40
+    lib = fp.lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", str(fp.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fpohm_[a-z0-9_]+)", out))
+    assert exported == set(declared), (exported ^ set(declared))
+
+
+def test_abi_argument_validation_and_no_cpu_fallback(fp):
+    lib = fp.lib()
+    assert lib.fpohm_octree_grid_setup(None, C.c_int64(0), C.c_int32(1), None) == -1       # FPOHM_EINVAL
+    assert b"bad argument" in lib.fpohm_last_error()
+    if fp.device_count() == 0:
+        h = C.c_void_p()
+        assert lib.fpohm_ctx_create(C.c_int(0), C.byref(h)) == -2                           # FPOHM_ENODEV, loud
+        assert b"no CPU fallback" in lib.fpohm_last_error()
+        with pytest.raises(fp.FpohmError):
+            fp.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is a checker: nothing under the product package (or the import shim) may reference it."""
+    pkg = ROOT / "feature-preserving-octree-hex-meshing_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + [ROOT / "fpohm_b200.py"]:
+        txt = p.read_text()
+        assert "oracle" not in txt.replace("oracle/", "").lower() or p.name == "build.py", p
+        assert "port_oracle" not in txt and "ref_oracle" not in txt and "libfpohm_ref" not in txt and "libfpohm_port" not in txt, p
+
+
+# ---- multi-process sharding logic (gloo, world_size 2) ------------------------------------------------------------------
+def test_query_sharding_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {str(ROOT)!r})
+import fpohm_b200 as fp
+from fpohm_b200 import sharding
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+n = 1001
+lo, hi = sharding.shard_range(n, r, w)
+x = torch.arange(n, dtype=torch.float64)
+part = (x[lo:hi] * 2).contiguous()                     # stands in for a per-rank kernel result
+full = sharding.gather_ranges(part, n, r, w)
+assert torch.equal(full, x * 2), "gather"
+st = sharding.reduce_stats(dict(min=float(part.min()), sum=float(part.sum()), sumsq=float((part*part).sum()), count=hi-lo, max=float(part.max())))
+assert st["count"] == n and st["min"] == 0.0 and st["max"] == 2.0*(n-1) and abs(st["sum"] - float((x*2).sum())) < 1e-6
+zs = sharding.z_slabs(64, w)
+assert zs[0][0] == 0 and zs[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(zs, zs[1:]))
+dist.destroy_process_group()
+print("ok", r)
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
