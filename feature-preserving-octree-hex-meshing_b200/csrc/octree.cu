@@ -65,34 +65,95 @@ __global__ void roots_kernel(uint64_t *__restrict__ code, int rx, int ry, int rz
 	}
 }
 
-// should_subdivide (ghm.cpp:502-517) for every cell of T_l.  One thread per cell; stack descent of the complete
-// binary facet-box tree with early exit on the first overlapping facet (the reference visits every overlapping
-// leaf, mesh_AABB.h:214-239, but only ORs a flag — same result).
+// should_subdivide (ghm.cpp:502-517) for every cell of T_l over the complete binary facet-box tree (the reference
+// visits every overlapping leaf, mesh_AABB.h:214-239, but only ORs a flag — any-hit is the same result).
+//
+// Phase A: one thread per cell, depth-first with early exit, at most PRED_BUDGET node visits.  Nearly every cell
+// finishes here.  Phase B: the few cells that overlap many internal union boxes without touching a facet box (cells in
+// concavities: the serial chain was ~2 300 dependent L2 loads = 350 us for ONE thread on the first ncu capture) are
+// finished by the whole warp: the frontier lives in shared memory and 32 nodes are tested per step.
+#define PRED_BUDGET 48
+#define PRED_WCAP 1024
+
+__device__ __forceinline__ bool box_overlap(const double *__restrict__ b, double mn0, double mn1, double mn2, double mx0, double mx1, double mx2) {
+	// bboxes_overlap, geo/basic/geometry.h:612-622 (closed intervals)
+	return !(mx0 < b[0] || mn0 > b[3] || mx1 < b[1] || mn1 > b[4] || mx2 < b[2] || mn2 > b[5]);
+}
+
+__device__ bool coop_any_overlap(const double *__restrict__ box, uint32_t P, double mn0, double mn1, double mn2, double mx0, double mx1,
+                                 double mx2, uint32_t *stk, int lane)
+{
+	int top = 1;
+	if (lane == 0) stk[0] = 1;
+	__syncwarp();
+	while (top > 0) {
+		int take = top < 32 ? top : 32;
+		if (top > PRED_WCAP - 64) take = 1;          // nearly full: pure DFS, growth bounded by the tree depth
+		uint32_t nd = 0;
+		bool ov = false;
+		if (lane < take) {
+			nd = stk[top - 1 - lane];
+			ov = box_overlap(box + 6 * (int64_t)nd, mn0, mn1, mn2, mx0, mx1, mx2);
+		}
+		__syncwarp();
+		top -= take;
+		if (__any_sync(0xffffffffu, ov && nd >= P)) return true;
+		const unsigned m = __ballot_sync(0xffffffffu, ov);
+		if (ov) {
+			const int r = __popc(m & ((1u << lane) - 1));
+			stk[top + 2 * r] = 2 * nd + 1;
+			stk[top + 2 * r + 1] = 2 * nd;
+		}
+		top += 2 * __popc(m);
+		__syncwarp();
+	}
+	return false;
+}
+
 __global__ void __launch_bounds__(256)
 predicate_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift /*depth - level*/, double bx, double by, double bz,
-                 double vs, const double *__restrict__ box, int64_t P, uint8_t *__restrict__ flag)
+                 double vs, const double *__restrict__ box, int64_t P64, uint8_t *__restrict__ flag)
 {
-	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-		const uint64_t c = cells[i];
-		const int x = (int)(compact1by2(c) << shift), y = (int)(compact1by2(c >> 1) << shift), z = (int)(compact1by2(c >> 2) << shift);
-		const int extent = 1 << shift;
-		// box.xyz_min = (mesh_transform + origin) + voxel_size * x ; box.xyz_max = box.xyz_min + voxel_size * extent
-		const double mn0 = bx + vs * x, mn1 = by + vs * y, mn2 = bz + vs * z;
-		const double mx0 = mn0 + vs * extent, mx1 = mn1 + vs * extent, mx2 = mn2 + vs * extent;
-		int64_t stack[40];
-		int sp = 0;
-		stack[sp++] = 1;
-		bool hit = false;
-		while (sp > 0 && !hit) {
-			const int64_t nd = stack[--sp];
-			const double *b = box + 6 * nd;
-			// bboxes_overlap, geo/basic/geometry.h:612-622 (closed intervals)
-			if (mx0 < b[0] || mn0 > b[3] || mx1 < b[1] || mn1 > b[4] || mx2 < b[2] || mn2 > b[5]) continue;
-			if (nd >= P) { hit = true; break; }
+	__shared__ uint32_t wstack[8][PRED_WCAP];
+	const uint32_t P = (uint32_t)P64;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {   // warp-uniform trip count
+		const int64_t i = base + lane;
+		const bool valid = i < n;
+		double mn0 = 0, mn1 = 0, mn2 = 0, mx0 = 0, mx1 = 0, mx2 = 0;
+		if (valid) {
+			const uint64_t c = cells[i];
+			const int x = (int)(compact1by2(c) << shift), y = (int)(compact1by2(c >> 1) << shift), z = (int)(compact1by2(c >> 2) << shift);
+			const int extent = 1 << shift;
+			// box.xyz_min = (mesh_transform + origin) + voxel_size * x ; box.xyz_max = box.xyz_min + voxel_size * extent
+			mn0 = bx + vs * x; mn1 = by + vs * y; mn2 = bz + vs * z;
+			mx0 = mn0 + vs * extent; mx1 = mn1 + vs * extent; mx2 = mn2 + vs * extent;
+		}
+		uint32_t stack[34];
+		int sp = 0, visits = 0;
+		bool hit = false, done = !valid;
+		if (valid) stack[sp++] = 1;
+		while (!done) {
+			if (sp == 0) { done = true; break; }
+			if (visits >= PRED_BUDGET) break;
+			const uint32_t nd = stack[--sp];
+			++visits;
+			if (!box_overlap(box + 6 * (int64_t)nd, mn0, mn1, mn2, mx0, mx1, mx2)) continue;
+			if (nd >= P) { hit = true; done = true; break; }
 			stack[sp++] = 2 * nd + 1;
 			stack[sp++] = 2 * nd;
 		}
-		flag[i] = hit;
+		unsigned todo = __ballot_sync(0xffffffffu, !done);
+		while (todo) {
+			const int src = __ffs(todo) - 1;
+			const double a0 = __shfl_sync(0xffffffffu, mn0, src), a1 = __shfl_sync(0xffffffffu, mn1, src), a2 = __shfl_sync(0xffffffffu, mn2, src);
+			const double b0 = __shfl_sync(0xffffffffu, mx0, src), b1 = __shfl_sync(0xffffffffu, mx1, src), b2 = __shfl_sync(0xffffffffu, mx2, src);
+			const bool h = coop_any_overlap(box, P, a0, a1, a2, b0, b1, b2, wstack[warp], lane);
+			if (lane == src) hit = h;
+			todo &= todo - 1;
+		}
+		if (valid) flag[i] = hit;
 	}
 }
 
@@ -338,10 +399,10 @@ struct Sorter {
 		if (n == 0) { out.alloc(0, s); return 0; }
 		DevBuf<uint64_t> sorted(n, s);
 		size_t tb = 0;
-		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, in.p, sorted.p, n, 0, 64, s));
-		(void)bits;
+		const int end_bit = bits + 1 < 64 ? bits + 1 : 64;   // bit `bits` is 0 in every valid key and 1 in INVALID
+		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, in.p, sorted.p, n, 0, end_bit, s));
 		DevBuf<uint8_t> tmp((int64_t)tb, s);
-		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, in.p, sorted.p, n, 0, 64, s));
+		FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, in.p, sorted.p, n, 0, end_bit, s));
 		DevBuf<uint64_t> uniq(n, s);
 		DevBuf<int64_t> cnt(1, s);
 		size_t tb2 = 0;
@@ -365,6 +426,8 @@ struct Sorter {
 };
 
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+// number of Morton key bits for per-axis coordinates in [0, max_coord]
+int key_bits(int64_t max_coord) { int b = 1; while ((1ll << b) <= max_coord) ++b; return 3 * b; }
 
 void setup_geometry(fpohm_octree *o, const int32_t gs[3]) {
 	for (int d = 0; d < 3; ++d) {
@@ -412,7 +475,8 @@ void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::ve
 			FPOHM_LAUNCH_CHECK(ctx);
 		}
 		DevBuf<uint64_t> uq;
-		int64_t m = sorter.sort_unique(cand, n_cand, 64, uq);
+		const int lbits = key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << l) - 1);
+		int64_t m = sorter.sort_unique(cand, n_cand, lbits, uq);
 		if (paired && m > 0) {
 			if (l == 0) {
 				// root rule, octree.cpp:577-581: one root split => all roots split
@@ -420,14 +484,14 @@ void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::ve
 				roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(uq.p, o->roots[0], o->roots[1], o->roots[2]);
 				FPOHM_LAUNCH_CHECK(ctx);
 				DevBuf<uint64_t> sorted_roots;
-				m = sorter.sort_unique(uq, o->n_roots, 64, sorted_roots);
+				m = sorter.sort_unique(uq, o->n_roots, lbits, sorted_roots);
 				uq = std::move(sorted_roots);
 			} else {
 				// sibling rule, octree.cpp:583-587 (+ makeCellPaired :632-643): whole families
 				DevBuf<uint64_t> fam(m, s), famu;
 				family_kernel<<<grid_for(ctx, m, blk), blk, 0, s>>>(uq.p, m, fam.p);
 				FPOHM_LAUNCH_CHECK(ctx);
-				const int64_t nf = sorter.sort_unique(fam, m, 64, famu);
+				const int64_t nf = sorter.sort_unique(fam, m, lbits, famu);
 				uq.alloc(8 * nf, s);
 				children_kernel<<<grid_for(ctx, 8 * nf, blk), blk, 0, s>>>(famu.p, nf, uq.p);
 				FPOHM_LAUNCH_CHECK(ctx);
@@ -496,7 +560,8 @@ void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::ve
 		leaf_corner_keys_kernel<<<grid_for(ctx, o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->cell_level.p,
 			o->cell_code.p, o->depth, o->node_shift, keys.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		o->n_nodes = sorter.sort_unique(keys, 8 * o->n_leaves, 64, o->node_key);
+		const int64_t gmax = std::max(o->prm.grid_size[0], std::max(o->prm.grid_size[1], o->prm.grid_size[2]));
+		o->n_nodes = sorter.sort_unique(keys, 8 * o->n_leaves, key_bits(gmax >> o->node_shift), o->node_key);
 	}
 	FPOHM_REQUIRE(o->n_nodes < (1ll << 31), FPOHM_ERANGE, "octree: %lld nodes exceed int32 ids", (long long)o->n_nodes);
 	o->node_pos.alloc(3 * o->n_nodes, s);
@@ -558,7 +623,7 @@ void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bo
 				DevBuf<uint64_t> raw(cnt, s);
 				old_leaf_codes_kernel<<<grid_for(ctx, cnt, blk), blk, 0, s>>>(o->cell_code.p, o->cell_first_child.p, id0, cnt, raw.p);
 				FPOHM_LAUNCH_CHECK(ctx);
-				n_old_leaves = sorter.sort_unique(raw, cnt, 64, old_leaves);
+				n_old_leaves = sorter.sort_unique(raw, cnt, key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << l) - 1), old_leaves);
 			}
 		}
 		const int64_t nT = n_old_leaves + n_kids;
