@@ -16,20 +16,21 @@ using namespace fpohm;
 
 namespace {
 
-// global_types.h:163-173
-__constant__ int c_hex_tetra[8][4] = {
-	{0, 3, 4, 1}, {1, 0, 5, 2}, {2, 1, 6, 3}, {3, 2, 7, 0}, {4, 7, 5, 0}, {5, 4, 6, 1}, {6, 5, 7, 2}, {7, 6, 4, 3}};
-
 struct V3 { double x, y, z; };
 
-// a_jacobian(Vector3d...), gf.cpp:2422-2442; Eigen 3.2 determinant (bruteforce_det3_helper) and norm association
-__device__ __forceinline__ double a_jacobian(const V3 &v0, const V3 &v1, const V3 &v2, const V3 &v3) {
-	const double m00 = (v1.x - v0.x) * .5, m10 = (v1.y - v0.y) * .5, m20 = (v1.z - v0.z) * .5;
-	const double m01 = (v2.x - v0.x) * .5, m11 = (v2.y - v0.y) * .5, m21 = (v2.z - v0.z) * .5;
-	const double m02 = (v3.x - v0.x) * .5, m12 = (v3.y - v0.y) * .5, m22 = (v3.z - v0.z) * .5;
-	const double norm1 = sqrt(m00 * m00 + (m10 * m10 + m20 * m20));
-	const double norm2 = sqrt(m01 * m01 + (m11 * m11 + m21 * m21));
-	const double norm3 = sqrt(m02 * m02 + (m12 * m12 + m22 * m22));
+// The 8 corner frames of hex_tetra_table use the 12 hex edges twice each, once per end point and with opposite
+// orientation.  IEEE subtraction is exactly antisymmetric and *0.5 is exact, so (a - b)*.5 == -((b - a)*.5) bit for bit,
+// the norms of the two are identical, and negating a column of the 3x3 negates every product and every partial sum of
+// Eigen's cofactor expansion exactly.  Hence: 12 half-edge vectors + 12 norms per hex (instead of 24 + 24), each corner
+// picks +-e and evaluates the SAME expression tree as a_jacobian (gf.cpp:2422-2442) — results are bit-identical to the
+// reference while the fp64 pipe, which bounds this kernel (ncu: 44 % fp64 pipe vs 19 % DRAM on the first version),
+// does ~1/3 less work.
+//   edge k = (lo, hi): 0:(0,1) 1:(1,2) 2:(3,2) 3:(0,3) 4:(4,5) 5:(5,6) 6:(7,6) 7:(4,7) 8:(0,4) 9:(1,5) 10:(2,6) 11:(3,7)
+//   corner j of hex_tetra_table (global_types.h:163-173) -> columns (edge, sign): sign +1 means e = hi - lo is used as is
+
+// a_jacobian(Vector3d...), gf.cpp:2422-2442 on precomputed halved columns; Eigen 3.2 determinant (bruteforce_det3_helper)
+__device__ __forceinline__ double a_jacobian_cols(const V3 &c0, const V3 &c1, const V3 &c2, double norm1, double norm2, double norm3) {
+	const double m00 = c0.x, m10 = c0.y, m20 = c0.z, m01 = c1.x, m11 = c1.y, m21 = c1.z, m02 = c2.x, m12 = c2.y, m22 = c2.z;
 	const double det = m00 * (m11 * m22 - m12 * m21) - m01 * (m10 * m22 - m12 * m20) + m02 * (m10 * m21 - m11 * m20);
 	if (norm1 < 1.e-7 || norm2 < 1.e-7 || norm3 < 1.e-7) return det; // "Potential Bug" branch, gf.cpp:2436-2439
 	return det / (norm1 * norm2 * norm3);
@@ -59,7 +60,7 @@ __device__ __forceinline__ void block_reduce(Partial &p, Partial *smem) {
 	}
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 jacobian_kernel(const double *__restrict__ V, const uint32_t *__restrict__ hex, int64_t H,
                 double *__restrict__ V_Js, double *__restrict__ H_Js, Partial *__restrict__ partials)
 {
@@ -75,11 +76,27 @@ jacobian_kernel(const double *__restrict__ V, const uint32_t *__restrict__ hex, 
 			const double *v = V + 3 * (int64_t)id[k];
 			p[k] = {__ldg(v), __ldg(v + 1), __ldg(v + 2)};
 		}
+		// 12 halved edge vectors (hi - lo) * .5 and their norms (Eigen: sqrt(x^2 + (y^2 + z^2)))
+		constexpr int elo[12] = {0, 1, 3, 0, 4, 5, 7, 4, 0, 1, 2, 3}, ehi[12] = {1, 2, 2, 3, 5, 6, 6, 7, 4, 5, 6, 7};
+		V3 e[12]; double en[12];
+#pragma unroll
+		for (int k = 0; k < 12; ++k) {
+			e[k] = {(p[ehi[k]].x - p[elo[k]].x) * .5, (p[ehi[k]].y - p[elo[k]].y) * .5, (p[ehi[k]].z - p[elo[k]].z) * .5};
+			en[k] = sqrt(e[k].x * e[k].x + (e[k].y * e[k].y + e[k].z * e[k].z));
+		}
+		constexpr int ce[8][3] = {{3, 8, 0}, {0, 9, 1}, {1, 10, 2}, {2, 11, 3}, {7, 4, 8}, {4, 5, 9}, {5, 6, 10}, {6, 7, 11}};
+		constexpr int cs[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, 1, -1}, {1, 1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}, {1, -1, -1}};
 		double j[8];
 		double hex_min = 1;
 #pragma unroll
 		for (int c = 0; c < 8; ++c) {
-			j[c] = a_jacobian(p[c_hex_tetra[c][0]], p[c_hex_tetra[c][1]], p[c_hex_tetra[c][2]], p[c_hex_tetra[c][3]]);
+			V3 col[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const V3 &v = e[ce[c][k]];
+				col[k] = cs[c][k] > 0 ? v : V3{-v.x, -v.y, -v.z};
+			}
+			j[c] = a_jacobian_cols(col[0], col[1], col[2], en[ce[c][0]], en[ce[c][1]], en[ce[c][2]]);
 			if (hex_min > j[c]) hex_min = j[c];
 		}
 		if (V_Js) {
@@ -140,11 +157,12 @@ void launch_scaled_jacobian(fpohm_ctx *ctx, const double *V, const uint32_t *hex
                             double *stats3, long long *flipped, cudaStream_t s)
 {
 	const int blk = 256;
-	const int grid = grid_for(ctx, H, blk, 8);
+	const int jblk = 128;                        // 144 registers/thread: 3 CTAs of 128 per SM keep 12 warps resident
+	const int grid = grid_for(ctx, H, jblk, 6);
 	DevBuf<Partial> partials(grid, s);
 	DevBuf<double> tmpH;
 	if (!H_Js) { tmpH.alloc(H, s); H_Js = tmpH.p; }
-	jacobian_kernel<<<grid, blk, 0, s>>>(V, hex, H, V_Js, H_Js, partials.p);
+	jacobian_kernel<<<grid, jblk, 0, s>>>(V, hex, H, V_Js, H_Js, partials.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	finalize_kernel<0><<<1, blk, 0, s>>>(partials.p, grid, H, stats3, flipped);
 	FPOHM_LAUNCH_CHECK(ctx);

@@ -157,6 +157,27 @@ predicate_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift /*dept
 	}
 }
 
+// Coarse levels have few cells (16 ... a few thousand) but each cell is large: one WARP per cell, spread over the whole
+// chip, so a level costs the latency of ONE cooperative descent instead of 32 serial ones per warp.
+__global__ void __launch_bounds__(256)
+predicate_warp_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift, double bx, double by, double bz, double vs,
+                      const double *__restrict__ box, int64_t P64, uint8_t *__restrict__ flag)
+{
+	__shared__ uint32_t wstack[8][PRED_WCAP];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t nwarps = (int64_t)gridDim.x * 8;
+	for (int64_t i = blockIdx.x * 8 + warp; i < n; i += nwarps) {
+		const uint64_t c = cells[i];
+		const int x = (int)(compact1by2(c) << shift), y = (int)(compact1by2(c >> 1) << shift), z = (int)(compact1by2(c >> 2) << shift);
+		const int extent = 1 << shift;
+		const double mn0 = bx + vs * x, mn1 = by + vs * y, mn2 = bz + vs * z;
+		const double mx0 = mn0 + vs * extent, mx1 = mn1 + vs * extent, mx2 = mn2 + vs * extent;
+		const bool h = coop_any_overlap(box, (uint32_t)P64, mn0, mn1, mn2, mx0, mx1, mx2, wstack[warp], lane);
+		if (lane == 0) flag[i] = h;
+		__syncwarp();
+	}
+}
+
 __global__ void children_kernel(const uint64_t *__restrict__ parents, int64_t n, uint64_t *__restrict__ out) {
 	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 8 * n; i += (int64_t)gridDim.x * blockDim.x)
 		out[i] = (parents[i >> 3] << 3) | (uint64_t)(i & 7);
@@ -636,8 +657,12 @@ void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bo
 			if (n_old_leaves) FPOHM_CUDA(cudaMemcpyAsync(T.p, old_leaves.p, 8 * (size_t)n_old_leaves, cudaMemcpyDeviceToDevice, s));
 			if (n_kids) FPOHM_CUDA(cudaMemcpyAsync(T.p + n_old_leaves, kids.p, 8 * (size_t)n_kids, cudaMemcpyDeviceToDevice, s));
 			DevBuf<uint8_t> flag(nT, s);
-			predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T.p, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
-				mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+			if (nT <= 32768)
+				predicate_warp_kernel<<<(int)std::min<int64_t>((nT + 7) / 8, (int64_t)ctx->sm_count * 8), blk, 0, s>>>(T.p, nT, o->depth - l,
+					bx, by, bz, o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+			else
+				predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T.p, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
+					mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
 			FPOHM_LAUNCH_CHECK(ctx);
 			sel.alloc(nT, s);
 			DevBuf<int64_t> cnt(1, s);

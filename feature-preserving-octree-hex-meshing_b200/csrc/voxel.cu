@@ -106,21 +106,68 @@ __device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
 	}
 }
 
-__global__ void __launch_bounds__(128)
-column_hits_kernel(ColumnGrid g, const double *__restrict__ box, int64_t P, const int32_t *__restrict__ order,
-                   const double *__restrict__ tri, double *__restrict__ hit_z, int8_t *__restrict__ hit_s,
-                   int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag)
+// ---- hits of all columns of a regular grid, TRIANGLE-parallel ------------------------------------------------------
+// The reference gathers, per column, the facets whose box contains the column's (x,y) (a degenerate query box) and
+// tests those.  Seen from the facet: facet f is tested by exactly the columns whose centre lies inside its closed xy
+// box — an index rectangle [x0,x1] x [y0,y1] found with the reference's own centre expression (x + 0.5) * spacing + ox.
+// (1) rect kernel: rectangle + pair count per facet; (2) exclusive scan; (3) pair kernel: thread t finds its facet by
+// binary search in the scan and its column inside the rectangle, runs intersect_ray_z, and appends a hit to the
+// column's fixed-capacity list with one atomicAdd.  Work is proportional to the number of (facet, column) pairs the
+// reference tests, instead of one tree descent per column (first version: 6.9 of 7.1 ms at 1024^2 columns, 2 M facets).
+__device__ __forceinline__ int first_center_ge(double lo, double o, double sp, int n) {
+	// smallest index i in [0, n] with (i + 0.5) * sp + o >= lo
+	int i = (int)floor((lo - o) / sp - 0.5);
+	if (i < 0) i = 0;
+	if (i > n) i = n;
+	while (i > 0 && ((i - 1) + 0.5) * sp + o >= lo) --i;
+	while (i < n && !((i + 0.5) * sp + o >= lo)) ++i;
+	return i;
+}
+__device__ __forceinline__ int last_center_le(double hi, double o, double sp, int n) {
+	// largest index i in [-1, n-1] with (i + 0.5) * sp + o <= hi
+	int i = (int)floor((hi - o) / sp - 0.5);
+	if (i < -1) i = -1;
+	if (i > n - 1) i = n - 1;
+	while (i < n - 1 && ((i + 1) + 0.5) * sp + o <= hi) ++i;
+	while (i >= 0 && !((i + 0.5) * sp + o <= hi)) --i;
+	return i;
+}
+
+__global__ void facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ rect, int64_t *__restrict__ cnt) {
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f <= nF; f += (int64_t)gridDim.x * blockDim.x) {
+		if (f == nF) { cnt[f] = 0; continue; }
+		const double *t = tri + 9 * f;
+		const double xmin = fmin(t[0], fmin(t[3], t[6])), xmax = fmax(t[0], fmax(t[3], t[6]));
+		const double ymin = fmin(t[1], fmin(t[4], t[7])), ymax = fmax(t[1], fmax(t[4], t[7]));
+		const int x0 = first_center_ge(xmin, g.ox, g.spacing, g.nx), x1 = last_center_le(xmax, g.ox, g.spacing, g.nx);
+		const int y0 = first_center_ge(ymin, g.oy, g.spacing, g.ny), y1 = last_center_le(ymax, g.oy, g.spacing, g.ny);
+		const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+		rect[f] = make_int4(x0, y0, w > 0 ? w : 0, h > 0 ? h : 0);
+		cnt[f] = (w > 0 && h > 0) ? (int64_t)w * h : 0;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, const int4 *__restrict__ rect, const int64_t *__restrict__ off,
+                 int64_t n_pairs, double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
+                 int32_t *__restrict__ overflow_flag)
 {
-	const int64_t ncol = (int64_t)g.nx * g.ny;
-	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
-		const int x = (int)(col % g.nx), y = (int)(col / g.nx);
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
+		int64_t lo = 0, hi = nF;                       // largest f with off[f] <= t
+		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+		const int64_t f = lo;
+		const int4 r = rect[f];
+		const int64_t k = t - off[f];
+		const int x = r.x + (int)(k % r.z), y = r.y + (int)(k / r.z);
 		const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
-		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
-		bool ov = false;
-		const int n = gather_hits(box, P, order, tri, cx, cx, cy, cy, cx, cy, hz, hs, HIT_CAP, ov);
-		if (ov) atomicExch(overflow_flag, 1);
-		hit_n[col] = n;
-		for (int i = 0; i < n; ++i) { hit_z[col * HIT_CAP + i] = hz[i]; hit_s[col * HIT_CAP + i] = hs[i]; }
+		double z;
+		const int s = intersect_ray_z(tri + 9 * f, cx, cy, z);
+		if (s) {
+			const int64_t col = (int64_t)y * g.nx + x;
+			const int slot = atomicAdd(&hit_n[col], 1);
+			if (slot < HIT_CAP) { hit_z[col * HIT_CAP + slot] = z; hit_s[col * HIT_CAP + slot] = (int8_t)s; }
+			else atomicExch(overflow_flag, 1);
+		}
 	}
 }
 
@@ -134,7 +181,9 @@ __device__ __forceinline__ int first_layer_above(double z, double oz, double spa
 	return k;
 }
 
-// 4 adjacent columns per thread; every voxel written once.
+// 4 adjacent columns per thread, the whole z range; every voxel is written exactly once (1 B/voxel, one uchar4 = 128 B
+// per warp and layer).  Per column the hits become (k0, sign) events; only the NEXT event layer lives in a register, the
+// rest of the (short) list is re-scanned when an event fires, so the steady-state loop is compare + store.
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, double oz, double spacing, const double *__restrict__ hit_z,
                   const int8_t *__restrict__ hit_s, const int32_t *__restrict__ hit_n, uint8_t *__restrict__ out)
@@ -143,32 +192,29 @@ voxel_fill_kernel(int nx, int ny, int nz, double oz, double spacing, const doubl
 	const int64_t nthreads = (int64_t)gx * ny;
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nthreads; t += (int64_t)gridDim.x * blockDim.x) {
 		const int x4 = (int)(t % gx) * 4, y = (int)(t / gx);
-		// per column: delta[k] applied when the sweep reaches layer k; kept as a sorted small list of (k0, sign)
-		int k0[4][HIT_CAP]; int8_t sg[4][HIT_CAP]; int n[4];
+		int n[4], next[4], s[4] = {0, 0, 0, 0};
+		int64_t colbase[4];
 #pragma unroll
 		for (int c = 0; c < 4; ++c) {
-			n[c] = 0;
 			const int x = x4 + c;
-			if (x < nx) {
-				const int64_t col = (int64_t)y * nx + x;
-				const int m = hit_n[col];
-				for (int i = 0; i < m; ++i) {
-					const int k = first_layer_above(hit_z[col * HIT_CAP + i], oz, spacing, nz);
-					const int8_t s = hit_s[col * HIT_CAP + i];
-					int j = n[c] - 1;
-					while (j >= 0 && k0[c][j] > k) { k0[c][j + 1] = k0[c][j]; sg[c][j + 1] = sg[c][j]; --j; }
-					k0[c][j + 1] = k; sg[c][j + 1] = s;
-					++n[c];
-				}
-			}
+			colbase[c] = ((int64_t)y * nx + (x < nx ? x : nx - 1)) * HIT_CAP;
+			n[c] = x < nx ? min(hit_n[(int64_t)y * nx + x], HIT_CAP) : 0;
+			next[c] = nz;                                   // layer of the earliest event
+			for (int i = 0; i < n[c]; ++i) next[c] = min(next[c], first_layer_above(hit_z[colbase[c] + i], oz, spacing, nz));
 		}
-		int cur[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
 		const bool vec = (x4 + 3 < nx) && ((nx & 3) == 0);
 		for (int z = 0; z < nz; ++z) {
 			uint8_t v[4];
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
-				while (cur[c] < n[c] && k0[c][cur[c]] <= z) { s[c] += sg[c][cur[c]]; ++cur[c]; }
+				if (z == next[c]) {                         // rare: apply every event of this layer, find the following one
+					int nn = nz;
+					for (int i = 0; i < n[c]; ++i) {
+						const int k = first_layer_above(hit_z[colbase[c] + i], oz, spacing, nz);
+						if (k == z) s[c] += hit_s[colbase[c] + i]; else if (k > z) nn = min(nn, k);
+					}
+					next[c] = nn;
+				}
 				v[c] = s[c] < 0 ? 1 : 0;
 			}
 			const int64_t base = ((int64_t)z * ny + y) * nx + x4; // index_from_index3, voxelization.cpp:26-28
@@ -183,7 +229,7 @@ __global__ void dexel_reduce_kernel(int64_t ncol, double *__restrict__ hit_z, in
                                     int64_t *__restrict__ count)
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
-		const int n = hit_n[col];
+		const int n = min(hit_n[col], HIT_CAP);
 		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
 		for (int i = 0; i < n; ++i) { hz[i] = hit_z[col * HIT_CAP + i]; hs[i] = hit_s[col * HIT_CAP + i]; }
 		sort_hits(hz, hs, n);
@@ -242,13 +288,25 @@ struct HitScratch {
 };
 
 void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s) {
-	mesh_ensure_pred(ctx, mesh, s);
-	const int64_t ncol = (int64_t)g.nx * g.ny;
+	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
 	h.z.alloc(ncol * HIT_CAP, s); h.s.alloc(ncol * HIT_CAP, s); h.n.alloc(ncol, s); h.ov.alloc(1, s);
-	h.ov.zero();
-	column_hits_kernel<<<grid_for(ctx, ncol, 128, 16), 128, 0, s>>>(g, mesh->pred_box.p, mesh->pred_nodes / 2, mesh->pred_order.p,
-		mesh->tri.p, h.z.p, h.s.p, h.n.p, h.ov.p);
+	h.ov.zero(); h.n.zero();
+	DevBuf<int4> rect(nF, s);
+	DevBuf<int64_t> cnt(nF + 1, s), off(nF + 1, s);
+	facet_rect_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, cnt.p);
 	FPOHM_LAUNCH_CHECK(ctx);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nF + 1, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nF + 1, s));
+	ctx->launches += 1;
+	int64_t n_pairs = 0;
+	FPOHM_CUDA(cudaMemcpyAsync(&n_pairs, off.p + nF, 8, cudaMemcpyDeviceToHost, s));
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	if (n_pairs > 0) {
+		pair_hits_kernel<<<grid_for(ctx, n_pairs, 256, 8), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, n_pairs, h.z.p, h.s.p, h.n.p, h.ov.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
 }
 
 void check_overflow(HitScratch &h, cudaStream_t s, const char *who) {
