@@ -4,15 +4,15 @@
 //   orient_2d_inexact  voxelization.h:169-182    VoxelGrid ctor / voxel_center  voxelization.h:71-91
 //
 // Two stages.
-//   (1) column_hits_kernel — one thread per (x,y) column (or per octree cell): stack descent of the facet-box tree
-//       with the reference's query box (degenerate vertical line for grids, the cell footprint for octree cells,
-//       z range = mesh bbox -/+ spacing, i.e. always overlapping), SoS point-in-triangle at the column centre,
-//       barycentric z and orientation sign.  Hits go to a fixed-capacity per-column scratch (overflow is reported,
-//       never truncated silently).
+//   (1) hits.  Regular grids (VoxelGrid, DexelGrid): TRIANGLE-parallel — facet_rect_kernel / pair_hits_kernel below enumerate
+//       exactly the (facet, column) pairs the reference's per-column box query would test, run the SoS point-in-triangle
+//       at the column centre and append (z, sign) to a fixed-capacity per-column list (overflow is reported, never
+//       truncated silently).  Octree cells: one thread per cell, stack descent of the facet-box tree with the cell
+//       footprint as query box (cells of all sizes have their own centres, there is no shared column structure).
 //   (2) a consumer per flavour.  The VoxelGrid rule "voxel = [ sum of signs of hits with z < centre_z ] < 0" is
-//       order independent, so voxel_fill_kernel never sorts: it converts each hit to the first layer k0 whose centre
-//       lies above it and streams the column top-down, writing every voxel exactly once (1 B/voxel, 4 columns per
-//       thread -> 128 B per warp store).  Dexel / octree-cell rules need (z, sign) order: tiny in-register sort.
+//       order independent, so nothing is sorted: each hit becomes an event (first layer k0 above it, sign) and
+//       voxel_fill_kernel writes every voxel exactly once (1 B/voxel).  Dexel / octree-cell rules need (z, sign)
+//       order: tiny in-register insertion sort.
 #include "mesh.h"
 #include "octree.h"
 
@@ -114,6 +114,16 @@ __device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
 // binary search in the scan and its column inside the rectangle, runs intersect_ray_z, and appends a hit to the
 // column's fixed-capacity list with one atomicAdd.  Work is proportional to the number of (facet, column) pairs the
 // reference tests, instead of one tree descent per column (first version: 6.9 of 7.1 ms at 1024^2 columns, 2 M facets).
+// first layer index k in [0, nz] with  hit_z < (k + 0.5) * spacing + oz   (exactly the comparison of voxelization.h:259-261)
+__device__ __forceinline__ int first_layer_above(double z, double oz, double spacing, int nz) {
+	int k = (int)floor((z - oz) / spacing - 0.5);
+	if (k < 0) k = 0;
+	if (k > nz) k = nz;
+	while (k > 0 && z < ((k - 1) + 0.5) * spacing + oz) --k;
+	while (k < nz && !(z < (k + 0.5) * spacing + oz)) ++k;
+	return k;
+}
+
 __device__ __forceinline__ int first_center_ge(double lo, double o, double sp, int n) {
 	// smallest index i in [0, n] with (i + 0.5) * sp + o >= lo
 	int i = (int)floor((lo - o) / sp - 0.5);
@@ -133,7 +143,25 @@ __device__ __forceinline__ int last_center_le(double hi, double o, double sp, in
 	return i;
 }
 
-__global__ void facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ rect, int64_t *__restrict__ cnt) {
+// append one hit to its column (VoxelGrid: packed (k0, sign) event; otherwise (z, sign))
+__device__ __forceinline__ void append_hit(const ColumnGrid &g, int x, int y, double z, int s, double *__restrict__ hit_z, int8_t *__restrict__ hit_s,
+                                           int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag, int32_t *__restrict__ hit_ev, double oz, int nz)
+{
+	const int64_t col = (int64_t)y * g.nx + x;
+	const int slot = atomicAdd(&hit_n[col], 1);
+	if (slot >= HIT_CAP) atomicExch(overflow_flag, 1);
+	else if (hit_ev) hit_ev[col * HIT_CAP + slot] = (first_layer_above(z, oz, g.spacing, nz) << 2) | (s + 1);
+	else { hit_z[col * HIT_CAP + slot] = z; hit_s[col * HIT_CAP + slot] = (int8_t)s; }
+}
+
+// Rectangle of columns per facet.  Facets covering at most RECT_INLINE columns (the common case on fine meshes) are
+// finished right here; larger ones are left to the load-balanced pair kernel through cnt[]/rect[].
+#define RECT_INLINE 16
+__global__ void __launch_bounds__(256)
+facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ rect, int64_t *__restrict__ cnt,
+                  double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag,
+                  int32_t *__restrict__ hit_ev, double oz, int nz)
+{
 	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f <= nF; f += (int64_t)gridDim.x * blockDim.x) {
 		if (f == nF) { cnt[f] = 0; continue; }
 		const double *t = tri + 9 * f;
@@ -142,15 +170,28 @@ __global__ void facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, 
 		const int x0 = first_center_ge(xmin, g.ox, g.spacing, g.nx), x1 = last_center_le(xmax, g.ox, g.spacing, g.nx);
 		const int y0 = first_center_ge(ymin, g.oy, g.spacing, g.ny), y1 = last_center_le(ymax, g.oy, g.spacing, g.ny);
 		const int w = x1 - x0 + 1, h = y1 - y0 + 1;
-		rect[f] = make_int4(x0, y0, w > 0 ? w : 0, h > 0 ? h : 0);
-		cnt[f] = (w > 0 && h > 0) ? (int64_t)w * h : 0;
+		const int64_t n = (w > 0 && h > 0) ? (int64_t)w * h : 0;
+		if (n <= RECT_INLINE) {
+			for (int y = y0; y <= y1; ++y)
+				for (int x = x0; x <= x1; ++x) {
+					const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
+					double z;
+					const int s = intersect_ray_z(t, cx, cy, z);
+					if (s) append_hit(g, x, y, z, s, hit_z, hit_s, hit_n, overflow_flag, hit_ev, oz, nz);
+				}
+			rect[f] = make_int4(0, 0, 0, 0);
+			cnt[f] = 0;
+		} else {
+			rect[f] = make_int4(x0, y0, w, h);
+			cnt[f] = n;
+		}
 	}
 }
 
 __global__ void __launch_bounds__(256)
 pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, const int4 *__restrict__ rect, const int64_t *__restrict__ off,
                  int64_t n_pairs, double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
-                 int32_t *__restrict__ overflow_flag)
+                 int32_t *__restrict__ overflow_flag, int32_t *__restrict__ hit_ev, double oz, int nz)
 {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
 		int64_t lo = 0, hi = nF;                       // largest f with off[f] <= t
@@ -162,64 +203,119 @@ pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, const
 		const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
 		double z;
 		const int s = intersect_ray_z(tri + 9 * f, cx, cy, z);
-		if (s) {
-			const int64_t col = (int64_t)y * g.nx + x;
-			const int slot = atomicAdd(&hit_n[col], 1);
-			if (slot < HIT_CAP) { hit_z[col * HIT_CAP + slot] = z; hit_s[col * HIT_CAP + slot] = (int8_t)s; }
-			else atomicExch(overflow_flag, 1);
+		if (s) append_hit(g, x, y, z, s, hit_z, hit_s, hit_n, overflow_flag, hit_ev, oz, nz);
+	}
+}
+
+// VoxelGrid fill.  voxel(x,y,z) = [ sum of sign_i over the column's hits with k0_i <= z ] < 0 — order independent, so no
+// sort.  The z range is cut into chunks of 32 layers.
+//   column_summary_kernel  one thread per column: decodes the column's events ONCE and writes two bits per chunk —
+//                          "inside at chunk start" and "an event fires inside the chunk" (8 B per column for nz <= 1024:
+//                          L2 resident).
+//   voxel_fill_kernel      one thread = 4 adjacent columns x one chunk; reads the two summary words of its columns; a
+//                          clean chunk needs no event at all (mask = all ones / zero), a dirty one (a few % of the tiles)
+//                          re-decodes its events.  Every voxel is written exactly once as part of a 4-byte store: a warp
+//                          stores 128 contiguous bytes per layer — the "columns4 zchunk=32" pattern of
+//                          scripts/micro/write_patterns.cu, which sustains 5.97 TB/s on B200.
+// History (ncu, 1024^3, 2 M facets, profiles/r01_ncu_summary.md): per-column z stack 3.7 ms; per-tile event decode
+// 1.08 ms with 1.0 GB of DRAM reads and ~2 400 instructions per thread; events in registers per column 1.66 ms (128 regs).
+#define FILL_Z 32
+__device__ __forceinline__ uint32_t bit_range(int a, int b) {          // bits [a, b), 0 <= a <= b <= 32
+	const int len = b - a;
+	return len <= 0 ? 0u : ((len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << a);
+}
+// events of one column, SORTED by layer and carrying the running sign sum AFTER the event: (k << 8) | (sum + 128)
+__device__ __forceinline__ uint32_t chunk_mask_sorted(const int32_t *__restrict__ ev, int n, int z0, int z1) {
+	uint32_t mask = 0;
+	int s = 0, prev = z0;
+	for (int i = 0; i < n; ++i) {
+		const int32_t e = ev[i];
+		const int k = e >> 8, rs = (e & 0xff) - 128;
+		if (k > z0) {
+			if (k >= z1) break;
+			if (s < 0) mask |= bit_range(prev - z0, k - z0);
+			prev = k;
+		}
+		s = rs;
+	}
+	if (s < 0) mask |= bit_range(prev - z0, z1 - z0);
+	return mask;
+}
+
+// summary layout: word w of column col at sum[(2 * w) * ncol + col] (inside bits) and sum[(2 * w + 1) * ncol + col] (dirty bits).
+// Also rewrites the column's events in place: sorted by k0, packed with the running sum (see chunk_mask_sorted).
+__global__ void __launch_bounds__(256)
+column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
+                      uint32_t *__restrict__ sum)
+{
+	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
+		const int n = min(hit_n[col], HIT_CAP);
+		int32_t *ev = hit_ev + col * HIT_CAP;
+		if (n == 0) {
+			for (int w = 0; w < 2 * n_words; ++w) sum[(int64_t)w * ncol + col] = 0u;
+			continue;
+		}
+		int32_t e[HIT_CAP];
+		for (int i = 0; i < n; ++i) {                       // insertion sort by k0 (order among equal k0 is irrelevant)
+			const int32_t v = ev[i];
+			int j = i - 1;
+			while (j >= 0 && (e[j] >> 2) > (v >> 2)) { e[j + 1] = e[j]; --j; }
+			e[j + 1] = v;
+		}
+		int run = 0;
+		for (int i = 0; i < n; ++i) { run += (e[i] & 3) - 1; e[i] = ((e[i] >> 2) << 8) | (run + 128); ev[i] = e[i]; }
+		int i = 0, s = 0;
+		for (int w = 0; w < n_words; ++w) {
+			uint32_t inside = 0, dirty = 0;
+			for (int b = 0; b < 32; ++b) {
+				const int z0 = (w * 32 + b) * FILL_Z, z1 = z0 + FILL_Z;
+				if (z0 >= nz) break;
+				while (i < n && (e[i] >> 8) <= z0) { s = (e[i] & 0xff) - 128; ++i; }   // state entering the chunk
+				if (s < 0) inside |= 1u << b;
+				if (i < n && (e[i] >> 8) < z1) dirty |= 1u << b;
+			}
+			sum[(int64_t)(2 * w) * ncol + col] = inside;
+			sum[(int64_t)(2 * w + 1) * ncol + col] = dirty;
 		}
 	}
 }
 
-// first layer index k in [0, nz] with  hit_z < (k + 0.5) * spacing + oz   (exactly the comparison of voxelization.h:259-261)
-__device__ __forceinline__ int first_layer_above(double z, double oz, double spacing, int nz) {
-	int k = (int)floor((z - oz) / spacing - 0.5);
-	if (k < 0) k = 0;
-	if (k > nz) k = nz;
-	while (k > 0 && z < ((k - 1) + 0.5) * spacing + oz) --k;
-	while (k < nz && !(z < (k + 0.5) * spacing + oz)) ++k;
-	return k;
-}
-
-// 4 adjacent columns per thread, the whole z range; every voxel is written exactly once (1 B/voxel, one uchar4 = 128 B
-// per warp and layer).  Per column the hits become (k0, sign) events; only the NEXT event layer lives in a register, the
-// rest of the (short) list is re-scanned when an event fires, so the steady-state loop is compare + store.
 __global__ void __launch_bounds__(256)
-voxel_fill_kernel(int nx, int ny, int nz, double oz, double spacing, const double *__restrict__ hit_z,
-                  const int8_t *__restrict__ hit_s, const int32_t *__restrict__ hit_n, uint8_t *__restrict__ out)
+voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
+                  const uint32_t *__restrict__ sum, uint8_t *__restrict__ out)
 {
-	const int gx = (nx + 3) / 4;
-	const int64_t nthreads = (int64_t)gx * ny;
+	const int gx = (nx + 3) / 4, gz = (nz + FILL_Z - 1) / FILL_Z;
+	const int64_t nthreads = (int64_t)gx * ny * gz;
+	const int64_t layer = (int64_t)nx * ny;
+	const bool aligned = (nx & 3) == 0;               // rows are 4-byte aligned, no ragged tail
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nthreads; t += (int64_t)gridDim.x * blockDim.x) {
-		const int x4 = (int)(t % gx) * 4, y = (int)(t / gx);
-		int n[4], next[4], s[4] = {0, 0, 0, 0};
-		int64_t colbase[4];
+		const int x0 = (int)(t % gx) * 4, y = (int)((t / gx) % ny), zc = (int)(t / ((int64_t)gx * ny));
+		const int z0 = zc * FILL_Z, z1 = min(z0 + FILL_Z, nz);
+		const int64_t col0 = (int64_t)y * nx + x0;
+		const uint32_t *si = sum + (int64_t)(2 * (zc >> 5)) * layer + col0, *sd = si + layer;
+		const int bit = zc & 31;
+		uint32_t m[4];
 #pragma unroll
 		for (int c = 0; c < 4; ++c) {
-			const int x = x4 + c;
-			colbase[c] = ((int64_t)y * nx + (x < nx ? x : nx - 1)) * HIT_CAP;
-			n[c] = x < nx ? min(hit_n[(int64_t)y * nx + x], HIT_CAP) : 0;
-			next[c] = nz;                                   // layer of the earliest event
-			for (int i = 0; i < n[c]; ++i) next[c] = min(next[c], first_layer_above(hit_z[colbase[c] + i], oz, spacing, nz));
+			m[c] = 0;
+			if (x0 + c >= nx) continue;
+			if ((sd[c] >> bit) & 1u) m[c] = chunk_mask_sorted(hit_ev + (col0 + c) * HIT_CAP, min(hit_n[col0 + c], HIT_CAP), z0, z1);
+			else m[c] = ((si[c] >> bit) & 1u) ? 0xffffffffu : 0u;
 		}
-		const bool vec = (x4 + 3 < nx) && ((nx & 3) == 0);
-		for (int z = 0; z < nz; ++z) {
-			uint8_t v[4];
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				if (z == next[c]) {                         // rare: apply every event of this layer, find the following one
-					int nn = nz;
-					for (int i = 0; i < n[c]; ++i) {
-						const int k = first_layer_above(hit_z[colbase[c] + i], oz, spacing, nz);
-						if (k == z) s[c] += hit_s[colbase[c] + i]; else if (k > z) nn = min(nn, k);
-					}
-					next[c] = nn;
-				}
-				v[c] = s[c] < 0 ? 1 : 0;
+		uint8_t *o = out + (int64_t)z0 * layer + col0;     // index_from_index3, voxelization.cpp:26-28
+		const uint32_t any = m[0] | m[1] | m[2] | m[3], all = m[0] & m[1] & m[2] & m[3];
+		if (aligned && (any == 0u || all == 0xffffffffu)) {            // uniform tile: store only
+			const uint32_t w = any ? 0x01010101u : 0u;
+			for (int z = z0; z < z1; ++z, o += layer) *reinterpret_cast<uint32_t *>(o) = w;
+		} else if (aligned) {
+			uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+			for (int z = z0; z < z1; ++z, o += layer) {
+				*reinterpret_cast<uint32_t *>(o) = (m0 & 1u) | ((m1 & 1u) << 8) | ((m2 & 1u) << 16) | ((m3 & 1u) << 24);
+				m0 >>= 1; m1 >>= 1; m2 >>= 1; m3 >>= 1;
 			}
-			const int64_t base = ((int64_t)z * ny + y) * nx + x4; // index_from_index3, voxelization.cpp:26-28
-			if (vec) *reinterpret_cast<uchar4 *>(out + base) = make_uchar4(v[0], v[1], v[2], v[3]);
-			else for (int c = 0; c < 4; ++c) if (x4 + c < nx) out[base + c] = v[c];
+		} else {
+			for (int z = z0; z < z1; ++z, o += layer)
+				for (int c = 0; c < 4; ++c) if (x0 + c < nx) o[c] = (m[c] >> (z - z0)) & 1u;
 		}
 	}
 }
@@ -284,16 +380,21 @@ cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ c
 }
 
 struct HitScratch {
-	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> n, ov;
+	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> n, ov, ev;
 };
 
-void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s) {
+// voxel_events: store packed (k0, sign) events for the VoxelGrid fill instead of (z, sign) pairs
+void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s, bool voxel_events = false,
+                     double oz = 0, int nz = 0)
+{
 	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
-	h.z.alloc(ncol * HIT_CAP, s); h.s.alloc(ncol * HIT_CAP, s); h.n.alloc(ncol, s); h.ov.alloc(1, s);
+	if (voxel_events) h.ev.alloc(ncol * HIT_CAP, s); else { h.z.alloc(ncol * HIT_CAP, s); h.s.alloc(ncol * HIT_CAP, s); }
+	h.n.alloc(ncol, s); h.ov.alloc(1, s);
 	h.ov.zero(); h.n.zero();
 	DevBuf<int4> rect(nF, s);
 	DevBuf<int64_t> cnt(nF + 1, s), off(nF + 1, s);
-	facet_rect_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, cnt.p);
+	facet_rect_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, cnt.p, h.z.p, h.s.p, h.n.p, h.ov.p,
+		voxel_events ? h.ev.p : nullptr, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 	size_t tb = 0;
 	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nF + 1, s));
@@ -304,7 +405,8 @@ void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitS
 	FPOHM_CUDA(cudaMemcpyAsync(&n_pairs, off.p + nF, 8, cudaMemcpyDeviceToHost, s));
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 	if (n_pairs > 0) {
-		pair_hits_kernel<<<grid_for(ctx, n_pairs, 256, 8), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, n_pairs, h.z.p, h.s.p, h.n.p, h.ov.p);
+		pair_hits_kernel<<<grid_for(ctx, n_pairs, 256, 8), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, n_pairs, h.z.p, h.s.p, h.n.p, h.ov.p,
+			voxel_events ? h.ev.p : nullptr, oz, nz);
 		FPOHM_LAUNCH_CHECK(ctx);
 	}
 }
@@ -351,9 +453,14 @@ int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double gr
 	cudaStream_t s = (cudaStream_t)stream;
 	HitScratch h;
 	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1]};
-	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
-	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1];
-	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 8), 256, 0, s>>>(dims[0], dims[1], dims[2], grid_origin[2], spacing, h.z.p, h.s.p, h.n.p, out_dev);
+	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s, true, grid_origin[2], dims[2]);
+	const int gz = (dims[2] + FILL_Z - 1) / FILL_Z, n_words = (gz + 31) / 32;
+	const int64_t ncol = (int64_t)dims[0] * dims[1];
+	DevBuf<uint32_t> summary(2 * n_words * ncol, s);
+	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * gz;
+	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], dims[2], h.ev.p, h.n.p, summary.p, out_dev);
 	FPOHM_LAUNCH_CHECK(ctx);
 	check_overflow(h, s, "fpohm_voxel_sign");
 	FPOHM_API_END
