@@ -13,6 +13,8 @@
 // the device evaluates the same IEEE operations as the reference's SSE2 build.
 #include "mesh.h"
 #include <math_constants.h>
+#include <cstdlib>
+#include <algorithm>
 
 using namespace fpohm;
 
@@ -69,13 +71,14 @@ __device__ __forceinline__ bool box_contains(const double *mn, const double *mx,
 	return mn[0] <= p.x && mn[1] <= p.y && mn[2] <= p.z && p.x <= mx[0] && p.y <= mx[1] && p.z <= mx[2];
 }
 
-struct Hit { double sqr_d; int32_t f; V3 c; };
+struct Hit { double sqr_d; int32_t f; V3 c; int nodes, leaves; };
 
 __device__ __forceinline__ void test_leaf(const double *__restrict__ tri, int32_t prim, const V3 &p, Hit &h) {
 	const double *t = tri + 9 * (int64_t)prim;
 	const V3 c = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6));
 	const double d = sqnorm(sub(p, c));
 	if (d < h.sqr_d) { h.sqr_d = d; h.f = prim; h.c = c; }
+	++h.leaves;
 }
 
 // igl/AABB.cpp:364-441 with the recursion unrolled onto an explicit stack.  Per node igl does:
@@ -87,11 +90,11 @@ __device__ __forceinline__ void test_leaf(const double *__restrict__ tri, int32_
 // NOTE (round 1, measured): a "while-while" restructuring (inner loop over internal nodes only, leaf tests batched per
 // warp) ran 2.6x SLOWER on B200 (37.3 ms vs 14.2 ms for 4.6 M queries) — igl's order visits few leaves per query and the
 // forced reconvergence serialises the short box steps; the plain form below is kept.  profiles/r01_ncu_summary.md.
-#define FPOHM_STACK 64
+#define FPOHM_STACK 48
 __device__ __forceinline__ void traverse(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri,
                                          const V3 &p, Hit &h)
 {
-	h.sqr_d = CUDART_INF; h.f = -1; h.c = {0, 0, 0};
+	h.sqr_d = CUDART_INF; h.f = -1; h.c = {0, 0, 0}; h.nodes = 0; h.leaves = 0;
 	if (root < 0) { test_leaf(tri, ~root, p, h); return; }
 	int32_t st_node[FPOHM_STACK];
 	double st_d[FPOHM_STACK];
@@ -99,6 +102,7 @@ __device__ __forceinline__ void traverse(const QNode *__restrict__ nodes, int32_
 	int32_t cur = root;
 	for (;;) {
 		const QNode *n = nodes + cur;
+		++h.nodes;
 		const double dl = box_ext_sqdist(n->lmin, n->lmax, p);
 		const double dr = box_ext_sqdist(n->rmin, n->rmax, p);
 		const bool in_l = box_contains(n->lmin, n->lmax, p);
@@ -183,12 +187,12 @@ __device__ __forceinline__ double pseudonormal(const double *__restrict__ V, con
 	return dot3(qc, n) >= 0 ? 1. : -1.;
 }
 
-template <bool SIGNED>
-__global__ void __launch_bounds__(128)
+// Pass 1: traversal only.  Writes facet, closest point and SQUARED distance (into S).  Keeping the pseudonormal code out
+// of this kernel keeps it at <= 64 registers (8 CTAs of 128 threads per SM) and removes a long divergent tail per query.
+template <bool STATS>
+__global__ void __launch_bounds__(128, 6)
 closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri,
-                     const double *__restrict__ V, const int32_t *__restrict__ F, int64_t nF,
-                     const double *__restrict__ FN, const double *__restrict__ VN, const double *__restrict__ EN,
-                     const int32_t *__restrict__ EMAP, const double *__restrict__ P, int64_t np,
+                     const double *__restrict__ P, int64_t np,
                      double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, double *__restrict__ N)
 {
 	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
@@ -197,14 +201,24 @@ closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double
 		traverse(nodes, root, tri, p, h);
 		if (I) I[i] = h.f;
 		if (C) { C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z; }
-		if (SIGNED) {
-			V3 n = {0, 0, 0};
-			const double s = pseudonormal(V, F, nF, FN, VN, EN, EMAP, p, h.f, h.c, n);
-			if (S) S[i] = s * sqrt(h.sqr_d);
-			if (N) { N[3 * i] = n.x; N[3 * i + 1] = n.y; N[3 * i + 2] = n.z; }
-		} else {
-			if (S) S[i] = h.sqr_d; // squared distance for point_mesh_squared_distance
-		}
+		if (S) S[i] = h.sqr_d;
+		if (STATS && N) { N[3 * i] = h.nodes; N[3 * i + 1] = h.leaves; }   // debug: traversal counters
+	}
+}
+
+// Pass 2 (signed queries only): pseudonormal_test on (q, facet, closest point); fully coherent, one thread per query.
+__global__ void __launch_bounds__(128)
+pseudonormal_kernel(const double *__restrict__ V, const int32_t *__restrict__ F, int64_t nF,
+                    const double *__restrict__ FN, const double *__restrict__ VN, const double *__restrict__ EN,
+                    const int32_t *__restrict__ EMAP, const double *__restrict__ P, int64_t np,
+                    const int32_t *__restrict__ I, const double *__restrict__ C, double *__restrict__ S, double *__restrict__ N, bool keep_n)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+		const V3 p = ld3(P + 3 * i), c = ld3(C + 3 * i);
+		V3 n = {0, 0, 0};
+		const double s = pseudonormal(V, F, nF, FN, VN, EN, EMAP, p, I[i], c, n);
+		if (S) S[i] = s * sqrt(S[i]);                       // S held the squared distance
+		if (N && keep_n) { N[3 * i] = n.x; N[3 * i + 1] = n.y; N[3 * i + 2] = n.z; }
 	}
 }
 
@@ -218,13 +232,21 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 	if (np <= 0) return;
 	const int blk = 128;
 	const int grid = grid_for(ctx, np, blk, 16);
-	if (with_sign)
-		closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->V.p, m->F.p, m->nF,
-			m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, S, I, C, N);
-	else
-		closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->V.p, m->F.p, m->nF,
-			m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, S, I, C, N);
+	static const bool stats = getenv("FPOHM_CP_STATS") != nullptr;   // debug only: N[:,0:2] := (node visits, leaf tests)
+	// the sign pass needs facet + closest point even when the caller did not ask for them
+	DevBuf<int32_t> tmpI; DevBuf<double> tmpC, tmpS;
+	if (with_sign) {
+		if (!I) { tmpI.alloc(np, s); I = tmpI.p; }
+		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
+		if (!S && N) { tmpS.alloc(np, s); S = tmpS.p; }
+	}
+	if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
+	else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 	FPOHM_LAUNCH_CHECK(ctx);
+	if (with_sign && (S || N)) {
+		pseudonormal_kernel<<<grid, blk, 0, s>>>(m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, I, C, S, N, !stats);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
 }
 
 } // namespace fpohm
@@ -243,6 +265,10 @@ int fpohm_signed_distance_dev(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P_
 	FPOHM_API_END
 }
 
+// Host-pointer path.  Queries are independent, so the batch is cut into chunks that rotate over three streams:
+// chunk k+1 is on its way up (H2D) while chunk k computes and chunk k-1 is on its way down (D2H).  With pinned caller
+// buffers the PCIe copies (84 B/query) hide behind the traversal; with pageable memory CUDA stages the copies and the
+// pipeline degrades gracefully to the serial order.
 static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const double *P, int64_t np,
                       double *S, int32_t *I, double *C, double *N, const char *who)
 {
@@ -255,14 +281,28 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	mesh_ensure_tree(ctx, mesh, s);
 	DevBuf<double> dP(3 * np, s), dS(S ? np : 0, s), dC(C ? 3 * np : 0, s), dN(N ? 3 * np : 0, s);
 	DevBuf<int32_t> dI(I ? np : 0, s);
-	dP.upload(P, 3 * np);
 	KernelTimer t(ctx, s);
-	launch_closest_point(ctx, mesh, with_sign, dP.p, np, dS.p, dI.p, dC.p, dN.p, s);
+	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, s));              // allocations are ordered on s
+	cudaStream_t lanes[3] = {s, ctx->aux[0], ctx->aux[1]};
+	for (int k = 1; k < 3; ++k) FPOHM_CUDA(cudaStreamWaitEvent(lanes[k], ctx->ev_sync, 0));
+	const int64_t chunk = 1 << 19;
+	int k = 0;
+	for (int64_t o = 0; o < np; o += chunk, ++k) {
+		const int64_t n = std::min(chunk, np - o);
+		cudaStream_t ls = lanes[k % 3];
+		FPOHM_CUDA(cudaMemcpyAsync(dP.p + 3 * o, P + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, ls));
+		launch_closest_point(ctx, mesh, with_sign, dP.p + 3 * o, n, S ? dS.p + o : nullptr, I ? dI.p + o : nullptr,
+		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, ls);
+		if (S) FPOHM_CUDA(cudaMemcpyAsync(S + o, dS.p + o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ls));
+		if (I) FPOHM_CUDA(cudaMemcpyAsync(I + o, dI.p + o, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ls));
+		if (C) FPOHM_CUDA(cudaMemcpyAsync(C + 3 * o, dC.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ls));
+		if (N) FPOHM_CUDA(cudaMemcpyAsync(N + 3 * o, dN.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ls));
+	}
+	for (int j = 1; j < 3; ++j) {                             // join the side lanes back into s before the buffers die
+		FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, lanes[j]));
+		FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
+	}
 	t.stop();
-	if (S) dS.download(S, np);
-	if (I) dI.download(I, np);
-	if (C) dC.download(C, 3 * np);
-	if (N) dN.download(N, 3 * np);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 	FPOHM_API_END
 }

@@ -41,6 +41,9 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	c->device = device;
 	c->sm_count = prop.multiProcessorCount;
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[0], cudaStreamNonBlocking));
+	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[1], cudaStreamNonBlocking));
+	FPOHM_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
 	FPOHM_CUDA(cudaEventCreate(&c->ev0));
 	FPOHM_CUDA(cudaEventCreate(&c->ev1));
 	// keep freed blocks in the stream-ordered pool: the pipeline calls these entry points in loops
@@ -59,6 +62,9 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->aux[0]);
+	cudaStreamDestroy(ctx->aux[1]);
+	cudaEventDestroy(ctx->ev_sync);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

@@ -83,7 +83,8 @@ struct fpohm_ctx {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t aux[2] = {nullptr, nullptr};   // copy/compute pipelining of the host-pointer entry points
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
 	double last_ms = 0;
 	int64_t launches = 0;
 };
