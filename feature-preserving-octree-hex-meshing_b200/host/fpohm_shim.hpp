@@ -1,0 +1,416 @@
+// fpohm_shim.hpp — C++ drop-in over the C-ABI (include/fpohm.h) with the REFERENCE'S OWN SIGNATURES.
+//
+// Include this header AFTER the reference headers it shadows (global_types.h, grid_meshing/octree.h is replaced,
+// see INTEGRATION.md) and link libfpohm.so.  Everything is a template or inline so that the header itself needs
+// neither Eigen nor geogram: the reference's types (Mesh, Mesh_Quality, Treestr, Eigen::MatrixXd, GEO::Mesh ...) are
+// bound at instantiation time, through the members the reference code itself uses.
+//
+//   reference entry point (file:line)                                   shim (namespace fpohm_shim)
+//   -----------------------------------------------------------------   ------------------------------------------
+//   scaled_jacobian(Mesh&, Mesh_Quality&)          gf.cpp:2309           scaled_jacobian(hmi, mq)
+//   points_inside_mesh(MatrixXd&, Mesh&, VectorXd&) gf.cpp:4024          points_inside_mesh(Ps, tmi, signed_dis)
+//   build_aabb_tree(Mesh&, Treestr&, bool)         ghm.cpp:4231          build_aabb_tree(tmi, a_tree, is_tri)
+//   igl::signed_distance_pseudonormal(P,V,F,tree,FN,VN,EN,EMAP,S,I,C,N)  signed_distance_pseudonormal(P, a_tree, S, I, C, N)
+//        callers ghm.cpp:2273,2603,3771,4045,4074
+//   build_connectivity(Mesh&)  [Hex]               gf.cpp:16,121-264     build_connectivity(hmi)
+//   OctreeGrid                                     octree.h:62-270       class OctreeGrid (same public members)
+//   octree_mesh(GEO::Mesh&, Mesh&, OctreeGrid&, Vector3i&) ghm.cpp:460   octree_mesh(ctx, V, nV, F, nF, mo, octree, grid_size, ...)
+//   compute_sign(M, aabb, VoxelGrid<T>&)           voxelization.h:220    compute_sign(mesh, voxels)
+//   compute(mesh0, mesh1, diag, max, ave)          metro_hausdorff.cpp:358   compute(mesh0, mesh1, diag, max, ave)
+//   hausdorff_ratio_check / compute(..., ratio, thr) metro_hausdorff.cpp:12  compute(mesh0, mesh1, ratio, thr)
+//   hausdorff_dis(mesh0, mesh1, outlierVs, thr)    gf.cpp:3590           hausdorff_dis(mesh0, mesh1, outlierVs, thr)
+//
+// Error behaviour mirrors the reference: bool returns and a line on std::cout/cerr, never an exception out of a call the
+// reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <queue>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fpohm.h"
+
+namespace fpohm_shim {
+
+// ---------------------------------------------------------------------------------------------------------------------
+inline void check(int rc, const char *what) {
+	if (rc != FPOHM_OK) {
+		std::cerr << "[fpohm] " << what << " failed (" << rc << "): " << fpohm_last_error() << std::endl;
+		throw std::runtime_error(std::string(what) + ": " + fpohm_last_error());
+	}
+}
+
+// one context per process and device (env FPOHM_DEVICE, default 0) — the reference is single threaded
+inline fpohm_ctx *context() {
+	static fpohm_ctx *ctx = nullptr;
+	if (!ctx) {
+		const char *d = std::getenv("FPOHM_DEVICE");
+		check(fpohm_ctx_create(d ? std::atoi(d) : 0, &ctx), "fpohm_ctx_create");
+	}
+	return ctx;
+}
+
+// RAII device mesh built from the reference's Mesh (V is 3 x n column-major == xyz per vertex; Fs[i].vs = 3 ids)
+struct DeviceMesh {
+	fpohm_mesh *h = nullptr;
+	std::vector<int32_t> F;
+	template <class MeshT>
+	explicit DeviceMesh(const MeshT &tmi) {
+		F.resize(3 * tmi.Fs.size());
+		for (size_t i = 0; i < tmi.Fs.size(); ++i)
+			for (int k = 0; k < 3; ++k) F[3 * i + k] = (int32_t)tmi.Fs[i].vs[k];
+		check(fpohm_mesh_upload(context(), tmi.V.data(), (int64_t)tmi.V.cols(), F.data(), (int64_t)tmi.Fs.size(), &h), "fpohm_mesh_upload");
+	}
+	DeviceMesh(const double *V, int64_t nV, const int32_t *Fp, int64_t nF) {
+		check(fpohm_mesh_upload(context(), V, nV, Fp, nF, &h), "fpohm_mesh_upload");
+	}
+	DeviceMesh(const DeviceMesh &) = delete;
+	DeviceMesh &operator=(const DeviceMesh &) = delete;
+	~DeviceMesh() { fpohm_mesh_free(h); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// scaled_jacobian(Mesh &hmi, Mesh_Quality &mq), gf.cpp:2309-2358 (Hex branch; other element types are not on the hot path)
+template <class MeshT, class MeshQualityT>
+bool scaled_jacobian(MeshT &hmi, MeshQualityT &mq) {
+	if (hmi.type != 5 /* Mesh_type::Hex, global_types.h:457-465 */) return false;
+	const int64_t H = (int64_t)hmi.Hs.size();
+	std::vector<uint32_t> hex(8 * (size_t)H);
+	for (int64_t i = 0; i < H; ++i)
+		for (int k = 0; k < 8; ++k) hex[8 * i + k] = hmi.Hs[i].vs[k];
+	mq.V_Js.resize(8 * H); mq.H_Js.resize(H);
+	double mad[3]; int64_t flipped = 0;
+	check(fpohm_scaled_jacobian(context(), hmi.V.data(), (int64_t)hmi.V.cols(), hex.data(), H, mq.V_Js.data(), mq.H_Js.data(), mad, &flipped),
+	      "fpohm_scaled_jacobian");
+	mq.min_Jacobian = mad[0]; mq.ave_Jacobian = mad[1]; mq.deviation_Jacobian = mad[2];
+	if (flipped > 0) std::cout << "flipped elements: " << flipped << std::endl;   // gf.cpp:2356
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// build_aabb_tree(Mesh &tmi, Treestr &a_tree, bool is_tri), ghm.cpp:4231-4248.  The device tree lives beside the Treestr.
+inline std::map<const void *, DeviceMesh *> &tree_table() { static std::map<const void *, DeviceMesh *> t; return t; }
+
+template <class MeshT, class TreestrT>
+void build_aabb_tree(MeshT &tmi, TreestrT &a_tree, bool /*is_tri*/ = false) {
+	auto &tab = tree_table();
+	auto it = tab.find(&a_tree);
+	if (it != tab.end()) { delete it->second; tab.erase(it); }
+	DeviceMesh *dm = new DeviceMesh(tmi);
+	tab[&a_tree] = dm;
+	check(fpohm_mesh_build_query_tree(context(), dm->h), "fpohm_mesh_build_query_tree");
+	const int64_t nV = (int64_t)tmi.V.cols(), nF = (int64_t)tmi.Fs.size();
+	int64_t nE = 0;
+	check(fpohm_mesh_num_edges(dm->h, &nE), "fpohm_mesh_num_edges");
+	// Treestr fields (global_types.h:681-691); Eigen is column-major, the C-ABI row-major: fill through operator()
+	a_tree.TriV = tmi.V.transpose();
+	a_tree.TriF.resize(nF, 3);
+	for (int64_t i = 0; i < nF; ++i) for (int k = 0; k < 3; ++k) a_tree.TriF(i, k) = dm->F[3 * i + k];
+	std::vector<double> FN(3 * nF), VN(3 * nV), EN(3 * nE);
+	std::vector<int32_t> E(2 * nE), EMAP(3 * nF);
+	check(fpohm_mesh_normals(dm->h, FN.data(), VN.data(), EN.data(), E.data(), EMAP.data()), "fpohm_mesh_normals");
+	a_tree.TriFN.resize(nF, 3); a_tree.TriVN.resize(nV, 3); a_tree.TriEN.resize(nE, 3); a_tree.TriE.resize(nE, 2); a_tree.TriEMAP.resize(3 * nF);
+	for (int64_t i = 0; i < nF; ++i) for (int k = 0; k < 3; ++k) a_tree.TriFN(i, k) = FN[3 * i + k];
+	for (int64_t i = 0; i < nV; ++i) for (int k = 0; k < 3; ++k) a_tree.TriVN(i, k) = VN[3 * i + k];
+	for (int64_t i = 0; i < nE; ++i) { for (int k = 0; k < 3; ++k) a_tree.TriEN(i, k) = EN[3 * i + k]; a_tree.TriE(i, 0) = E[2 * i]; a_tree.TriE(i, 1) = E[2 * i + 1]; }
+	for (int64_t i = 0; i < 3 * nF; ++i) a_tree.TriEMAP(i) = EMAP[i];
+}
+
+// igl::signed_distance_pseudonormal(P, V, F, tree, FN, VN, EN, EMAP, S, I, C, N) with the tree looked up from its Treestr
+template <class MatP, class TreestrT, class VecS, class VecI, class MatC, class MatN>
+void signed_distance_pseudonormal(const MatP &P, const TreestrT &a_tree, VecS &S, VecI &I, MatC &C, MatN &N) {
+	auto it = tree_table().find(&a_tree);
+	if (it == tree_table().end()) throw std::runtime_error("signed_distance_pseudonormal: build_aabb_tree was not called for this Treestr");
+	const int64_t np = (int64_t)P.rows();
+	std::vector<double> p(3 * np), s(np), c(3 * np), n(3 * np);
+	std::vector<int32_t> idx(np);
+	for (int64_t i = 0; i < np; ++i) for (int k = 0; k < 3; ++k) p[3 * i + k] = P(i, k);
+	check(fpohm_signed_distance(context(), it->second->h, p.data(), np, s.data(), idx.data(), c.data(), n.data()), "fpohm_signed_distance");
+	S.resize(np); I.resize(np); C.resize(np, 3); N.resize(np, 3);
+	for (int64_t i = 0; i < np; ++i) { S(i) = s[i]; I(i) = idx[i]; for (int k = 0; k < 3; ++k) { C(i, k) = c[3 * i + k]; N(i, k) = n[3 * i + k]; } }
+}
+
+// points_inside_mesh(MatrixXd &Ps, Mesh &tmi, VectorXd &signed_dis), gf.cpp:4024-4048
+template <class MatP, class MeshT, class VecS>
+void points_inside_mesh(MatP &Ps, MeshT &tmi, VecS &signed_dis) {
+	DeviceMesh dm(tmi);
+	const int64_t np = (int64_t)Ps.rows();
+	std::vector<double> p(3 * np), s(np);
+	for (int64_t i = 0; i < np; ++i) for (int k = 0; k < 3; ++k) p[3 * i + k] = Ps(i, k);
+	check(fpohm_signed_distance(context(), dm.h, p.data(), np, s.data(), nullptr, nullptr, nullptr), "fpohm_signed_distance");
+	signed_dis.resize(np);
+	for (int64_t i = 0; i < np; ++i) signed_dis(i) = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// build_connectivity(Mesh &hmi), Hex branch gf.cpp:121-186 + adjacency 226-264.  HybridF / HybridE are the reference's
+// Hybrid_F / Hybrid_E; they are template parameters only so this header does not need global_types.h.
+template <class MeshT>
+void build_connectivity(MeshT &hmi) {
+	if (hmi.type != 5 /* Mesh_type::Hex */) throw std::runtime_error("fpohm_shim::build_connectivity: only the Hex branch is on the hot path");
+	const int64_t H = (int64_t)hmi.Hs.size(), nV = (int64_t)hmi.Vs.size();
+	std::vector<uint32_t> hex(8 * (size_t)H);
+	for (int64_t i = 0; i < H; ++i) for (int k = 0; k < 8; ++k) hex[8 * i + k] = hmi.Hs[i].vs[k];
+	fpohm_conn *c = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), H, nV, &c), "fpohm_hex_connectivity");
+	int64_t nF = 0, nE = 0;
+	fpohm_conn_sizes(c, &nF, &nE);
+	std::vector<uint32_t> F_vs(4 * nF), F_es(4 * nF), E_vs(2 * nE), H_fs(6 * H);
+	std::vector<uint8_t> Fb(nF), Eb(nE), Vb(nV);
+	check(fpohm_conn_fixed(c, F_vs.data(), F_es.data(), Fb.data(), E_vs.data(), Eb.data(), Vb.data(), H_fs.data()), "fpohm_conn_fixed");
+	hmi.Fs.clear(); hmi.Fs.resize(nF); hmi.Es.clear(); hmi.Es.resize(nE);
+	for (int64_t f = 0; f < nF; ++f) {
+		auto &x = hmi.Fs[f]; x.id = (uint32_t)f; x.boundary = Fb[f];
+		x.vs.assign(F_vs.begin() + 4 * f, F_vs.begin() + 4 * f + 4); x.es.assign(F_es.begin() + 4 * f, F_es.begin() + 4 * f + 4);
+	}
+	for (int64_t e = 0; e < nE; ++e) { auto &x = hmi.Es[e]; x.id = (uint32_t)e; x.boundary = Eb[e]; x.vs = {E_vs[2 * e], E_vs[2 * e + 1]}; }
+	for (int64_t v = 0; v < nV; ++v) hmi.Vs[v].boundary = Vb[v];
+	for (int64_t h = 0; h < H; ++h) hmi.Hs[h].fs.assign(H_fs.begin() + 6 * h, H_fs.begin() + 6 * h + 6);
+	auto fill = [&](int which, int64_t n, auto &&dst) {
+		int64_t tot = 0;
+		check(fpohm_conn_csr(c, which, nullptr, nullptr, &tot), "fpohm_conn_csr");
+		std::vector<int64_t> off(n + 1); std::vector<uint32_t> val((size_t)tot);
+		check(fpohm_conn_csr(c, which, off.data(), val.data(), &tot), "fpohm_conn_csr");
+		for (int64_t i = 0; i < n; ++i) dst(i).assign(val.begin() + off[i], val.begin() + off[i + 1]);
+	};
+	fill(0, nF, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Fs[i].neighbor_hs; });
+	fill(1, nE, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Es[i].neighbor_fs; });
+	fill(2, nE, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Es[i].neighbor_hs; });
+	fill(3, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_vs; });
+	fill(4, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_es; });
+	fill(5, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_fs; });
+	fill(6, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_hs; });
+	fpohm_conn_free(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// OctreeGrid, octree.h:62-270.  Same public data (m_Nodes, m_Cells, ...) and accessors; construction happens on the GPU.
+struct Node {                                        // octree.h:16-33
+	std::array<int, 6> neighNodeId;
+	std::array<int, 3> position;
+	Node() { neighNodeId.fill(-1); position.fill(0); }
+	int prev(int axis) const { return neighNodeId[2 * axis]; }
+	int next(int axis) const { return neighNodeId[2 * axis + 1]; }
+};
+struct Cell {                                        // octree.h:38-61
+	int firstChild;
+	std::array<int, 8> cornerNodeId;
+	std::array<int, 6> neighCellId;
+	Cell() : firstChild(-1) { neighCellId.fill(-1); cornerNodeId.fill(-1); }
+	int corner(int localId) const { return cornerNodeId[localId]; }
+	int adj(int axis, int dir) const { return neighCellId[2 * axis + dir]; }
+	int prev(int axis) const { return neighCellId[2 * axis]; }
+	int next(int axis) const { return neighCellId[2 * axis + 1]; }
+};
+
+class OctreeGrid {
+public:
+	std::array<int, 3> m_NodeGridSize{{0, 0, 0}}, m_CellGridSize{{0, 0, 0}};
+	int m_MaxDepth = 0, m_NumRootCells = 0;
+	std::vector<Node> m_Nodes;
+	std::vector<Cell> m_Cells;
+
+	OctreeGrid() {}
+	explicit OctreeGrid(std::array<int, 3> fineCellGridSize) { OctreeGrid_initialize(fineCellGridSize); }
+	~OctreeGrid() { fpohm_octree_free(h_); }
+	OctreeGrid(const OctreeGrid &) = delete;
+	OctreeGrid &operator=(const OctreeGrid &) = delete;
+
+	// octree.cpp:39-60 (+ createRootCells :64-117): an empty tree of root cells
+	void OctreeGrid_initialize(std::array<int, 3> fineCellGridSize) {
+		m_CellGridSize = fineCellGridSize;
+		for (int d = 0; d < 3; ++d) m_NodeGridSize[d] = fineCellGridSize[d] + 1;
+		fpohm_octree_free(h_); h_ = nullptr;
+		const int32_t gs[3] = {fineCellGridSize[0], fineCellGridSize[1], fineCellGridSize[2]};
+		check(fpohm_octree_build_from_marks(context(), gs, nullptr, 0, 1, 1, &h_), "fpohm_octree_build_from_marks");
+		pull();
+	}
+
+	int numNodes() const { return (int)m_Nodes.size(); }
+	int numCells() const { return (int)m_Cells.size(); }
+	int maxDepth() const { return m_MaxDepth; }
+	std::array<int, 3> nodePos(int nodeId) const { return m_Nodes[nodeId].position; }
+	std::array<int, 3> cellCornerPos(int cellId, int k) const { return m_Nodes[m_Cells[cellId].corner(k)].position; }
+	int cellCornerId(int cellId, int k) const { return m_Cells[cellId].corner(k); }
+	int cellExtent(int cellId) const { return cellCornerPos(cellId, 1)[0] - cellCornerPos(cellId, 0)[0]; }
+	bool cellIsLeaf(int cellId) const { return m_Cells[cellId].firstChild == -1; }
+	bool is2to1Graded() const { int32_t f = 0; check(fpohm_octree_check(h_, &f), "fpohm_octree_check"); return f & 1; }
+	bool isPaired() const { int32_t f = 0; check(fpohm_octree_check(h_, &f), "fpohm_octree_check"); return (f & 2) != 0; }
+
+	// subdivide(predicate, graded, paired), octree.cpp:648-690, for an ARBITRARY host predicate: the BFS (which cells get
+	// tested) runs here exactly as in the reference; the closure (splits forced by grading / pairing), numbering and all
+	// link tables are computed on the GPU from the predicate-true set.
+	void subdivide(std::function<bool(int, int, int, int)> predicate, bool graded = false, bool paired = false, int /*maxCells*/ = -1) {
+		std::vector<int32_t> marks;
+		std::queue<std::array<int, 4>> pending;
+		for (int c = 0; c < numCells(); ++c) {
+			const auto p = cellCornerPos(c, 0);
+			if (cellIsLeaf(c)) pending.push({{p[0], p[1], p[2], cellExtent(c)}});
+			else marks.insert(marks.end(), {p[0], p[1], p[2], cellExtent(c)});           // already split: stays split
+		}
+		while (!pending.empty()) {
+			const auto c = pending.front(); pending.pop();
+			if (!predicate(c[0], c[1], c[2], c[3])) continue;
+			if (c[3] == 1) { std::cerr << "[OctreeGrid] Cannot subdivide cell of length 1." << std::endl; continue; }
+			marks.insert(marks.end(), {c[0], c[1], c[2], c[3]});
+			const int e = c[3] / 2;
+			for (int k = 0; k < 8; ++k) pending.push({{c[0] + (k & 1) * e, c[1] + ((k >> 1) & 1) * e, c[2] + (k >> 2) * e, e}});
+		}
+		rebuild(marks, graded, paired);
+	}
+	// subdivide(predicate, tb_subdivided_cells, graded, paired), octree.cpp:691-729: listed leaves only, no recursion
+	void subdivide(std::function<bool(int, int, int, int)> predicate, std::vector<int> &cells, bool graded = false, bool paired = false, int = -1) {
+		std::vector<int32_t> marks;
+		for (int c = 0; c < numCells(); ++c)
+			if (!cellIsLeaf(c)) { const auto p = cellCornerPos(c, 0); marks.insert(marks.end(), {p[0], p[1], p[2], cellExtent(c)}); }
+		for (int cid : cells) {
+			if (!cellIsLeaf(cid)) continue;
+			const auto p = cellCornerPos(cid, 0); const int e = cellExtent(cid);
+			if (!predicate(p[0], p[1], p[2], e)) continue;
+			if (e == 1) { std::cerr << "[OctreeGrid] Cannot subdivide cell of length 1." << std::endl; continue; }
+			marks.insert(marks.end(), {p[0], p[1], p[2], e});
+		}
+		rebuild(marks, graded, paired);
+	}
+
+	// bbox-predicate build entirely on the device (what octree_mesh / compute_octree do); see octree_mesh below
+	void build_bbox(const DeviceMesh &mesh, const fpohm_octree_params &prm) {
+		fpohm_octree_free(h_); h_ = nullptr;
+		for (int d = 0; d < 3; ++d) { m_CellGridSize[d] = prm.grid_size[d]; m_NodeGridSize[d] = prm.grid_size[d] + 1; }
+		check(fpohm_octree_build(context(), mesh.h, &prm, &h_), "fpohm_octree_build");
+		pull();
+	}
+	void subdivide_bbox(const DeviceMesh &mesh, int stop_extent) { check(fpohm_octree_subdivide(h_, mesh.h, stop_extent), "fpohm_octree_subdivide"); pull(); }
+	void refine_bbox(const DeviceMesh &mesh, const std::vector<int> &cells, int stop_extent) {
+		std::vector<int32_t> c(cells.begin(), cells.end());
+		check(fpohm_octree_refine(h_, mesh.h, c.data(), (int64_t)c.size(), stop_extent), "fpohm_octree_refine");
+		pull();
+	}
+	fpohm_octree *handle() const { return h_; }
+
+private:
+	fpohm_octree *h_ = nullptr;
+	void rebuild(const std::vector<int32_t> &marks, bool graded, bool paired) {
+		fpohm_octree_free(h_); h_ = nullptr;
+		const int32_t gs[3] = {m_CellGridSize[0], m_CellGridSize[1], m_CellGridSize[2]};
+		check(fpohm_octree_build_from_marks(context(), gs, marks.data(), (int64_t)marks.size() / 4, graded, paired, &h_), "fpohm_octree_build_from_marks");
+		pull();
+	}
+	void pull() {
+		int64_t nn = 0, nc = 0, nl = 0; int32_t nr = 0, md = 0;
+		check(fpohm_octree_sizes(h_, &nn, &nc, &nl, &nr, &md), "fpohm_octree_sizes");
+		m_NumRootCells = nr; m_MaxDepth = md;
+		std::vector<int32_t> np(3 * nn), ng(6 * nn), fc(nc), cc(8 * nc), cn(6 * nc);
+		check(fpohm_octree_export(h_, np.data(), ng.data(), fc.data(), cc.data(), cn.data()), "fpohm_octree_export");
+		m_Nodes.assign((size_t)nn, Node()); m_Cells.assign((size_t)nc, Cell());
+		for (int64_t i = 0; i < nn; ++i) { for (int k = 0; k < 3; ++k) m_Nodes[i].position[k] = np[3 * i + k]; for (int k = 0; k < 6; ++k) m_Nodes[i].neighNodeId[k] = ng[6 * i + k]; }
+		for (int64_t i = 0; i < nc; ++i) { m_Cells[i].firstChild = fc[i]; for (int k = 0; k < 8; ++k) m_Cells[i].cornerNodeId[k] = cc[8 * i + k]; for (int k = 0; k < 6; ++k) m_Cells[i].neighCellId[k] = cn[6 * i + k]; }
+	}
+};
+
+// octree_mesh(GEO::Mesh &mi, Mesh &mo, OctreeGrid &octree, Vector3i &grid_size), ghm.cpp:460-567, minus the class state it
+// reads (num_voxels, STOP_EXTENT_MIN/MAX, tb_subdivided_cells, hex2Octree_map), which become arguments.
+//   first call / re_Octree_Meshing: stop_extent = 2^STOP_EXTENT_MIN, fresh tree; later calls: tb_subdivided_cells (already
+//   mapped through hex2Octree_map, ghm.cpp:519) or a global re-subdivide with 2^STOP_EXTENT_MAX.
+template <class MeshT, class Vec3i>
+bool octree_mesh(const DeviceMesh &mi, const double *V, int64_t nV, MeshT &mo, OctreeGrid &octree, Vec3i &grid_size, int num_voxels,
+                 int stop_extent, bool fresh, std::vector<int> &tb_subdivided_cells, std::vector<uint32_t> &hex2Octree_map)
+{
+	fpohm_octree_params prm{};
+	check(fpohm_octree_grid_setup(V, nV, num_voxels, &prm), "fpohm_octree_grid_setup");
+	prm.stop_extent = stop_extent; prm.graded = 1; prm.paired = 1;
+	for (int d = 0; d < 3; ++d) grid_size[d] = prm.grid_size[d];
+	if (fresh || !octree.numNodes()) octree.build_bbox(mi, prm);
+	else if (!tb_subdivided_cells.empty()) { octree.refine_bbox(mi, tb_subdivided_cells, stop_extent); tb_subdivided_cells.clear(); }
+	else octree.subdivide_bbox(mi, stop_extent);
+	int64_t nn = 0, nc = 0, nl = 0;
+	fpohm_octree_sizes(octree.handle(), &nn, &nc, &nl, nullptr, nullptr);
+	std::vector<double> Vp(3 * nn); std::vector<uint32_t> hex(8 * nl); std::vector<int32_t> h2c(nl);
+	check(fpohm_octree_hexes(octree.handle(), Vp.data(), hex.data(), h2c.data()), "fpohm_octree_hexes");
+	hex2Octree_map.assign(h2c.begin(), h2c.end());
+	mo.Vs.clear(); mo.Vs.resize(nn);
+	mo.V.resize(3, nn);
+	for (int64_t i = 0; i < nn; ++i) {
+		mo.Vs[i].id = (uint32_t)i; mo.Vs[i].v = {Vp[3 * i], Vp[3 * i + 1], Vp[3 * i + 2]};
+		for (int k = 0; k < 3; ++k) mo.V(k, i) = Vp[3 * i + k];
+	}
+	mo.Hs.clear(); mo.Hs.resize(nl);
+	for (int64_t c = 0; c < nl; ++c) { mo.Hs[c].id = (uint32_t)c; mo.Hs[c].vs.assign(hex.begin() + 8 * c, hex.begin() + 8 * c + 8); }
+	if (!mo.Hs.size()) { std::cout << "No octants, exit!" << std::endl; return false; }   // ghm.cpp:563
+	build_connectivity(mo);
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// VoxelGrid<T> + compute_sign, voxelization.h:41-91,220-272
+template <class T>
+class VoxelGrid {
+	std::vector<T> m_data;
+	std::array<double, 3> m_origin;
+	double m_spacing;
+	std::array<int, 3> m_grid_size;
+public:
+	VoxelGrid(std::array<double, 3> origin, std::array<double, 3> extent, double voxel_size, int padding) : m_spacing(voxel_size) {
+		int32_t dims[3]; double o[3];
+		check(fpohm_voxel_grid_setup(origin.data(), extent.data(), voxel_size, padding, dims, o), "fpohm_voxel_grid_setup");
+		for (int d = 0; d < 3; ++d) { m_grid_size[d] = dims[d]; m_origin[d] = o[d]; }
+		m_data.assign((size_t)dims[0] * dims[1] * dims[2], T(0));
+	}
+	std::array<int, 3> grid_size() const { return m_grid_size; }
+	int num_voxels() const { return m_grid_size[0] * m_grid_size[1] * m_grid_size[2]; }
+	std::array<double, 3> origin() const { return m_origin; }
+	double spacing() const { return m_spacing; }
+	const T at(int idx) const { return m_data[idx]; }
+	T &at(int idx) { return m_data[idx]; }
+	const T *rawbuf() const { return m_data.data(); }
+	T *raw_layer(int z) { return m_data.data() + (size_t)z * m_grid_size[1] * m_grid_size[0]; }
+};
+template <class T>
+void compute_sign(const DeviceMesh &M, VoxelGrid<T> &voxels) {
+	const auto gs = voxels.grid_size(); const auto o = voxels.origin();
+	const int32_t dims[3] = {gs[0], gs[1], gs[2]};
+	std::vector<uint8_t> out((size_t)voxels.num_voxels());
+	check(fpohm_voxel_sign(context(), M.h, o.data(), voxels.spacing(), dims, out.data()), "fpohm_voxel_sign");
+	for (size_t i = 0; i < out.size(); ++i) voxels.at((int)i) = T(out[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// metro: compute(const Mesh&, const Mesh&, double &bbox_diagonal, double &max, double &ave), metro_hausdorff.cpp:358-505
+template <class MeshT>
+void compute(const MeshT &mesh0, const MeshT &mesh1, double &bbox_diagonal, double &max_hausdorff_dis, double &ave_hausdorff_dis) {
+	DeviceMesh a(mesh0), b(mesh1);
+	double out[7]; int64_t ns[2];
+	check(fpohm_hausdorff(context(), a.h, b.h, 0, out, ns), "fpohm_hausdorff");
+	bbox_diagonal = out[0];
+	max_hausdorff_dis = out[1] > out[2] ? out[1] : out[2];
+	ave_hausdorff_dis = out[3] > out[4] ? out[3] : out[4];
+}
+// compute(Mesh&, Mesh&, double &hausdorff_ratio, double &hausdorff_ratio_threshold), metro_hausdorff.cpp:12-195
+template <class MeshT>
+int compute(MeshT &mesh0, MeshT &mesh1, double &hausdorff_ratio, double &hausdorff_ratio_threshold) {
+	double diag, mx, ave;
+	compute(static_cast<const MeshT &>(mesh0), static_cast<const MeshT &>(mesh1), diag, mx, ave);
+	hausdorff_ratio = (float)mx / diag;                                     // metro_hausdorff.cpp:186
+	std::printf("%f  wrt bounding box diagonal\n", hausdorff_ratio);
+	return hausdorff_ratio > hausdorff_ratio_threshold ? false : true;
+}
+// hausdorff_dis(mesh0, mesh1, outlierVs, hausdorff_dis_threshold), gf.cpp:3590-3628
+template <class MeshT>
+bool hausdorff_dis(MeshT &mesh0, MeshT &mesh1, std::vector<int> &outlierVs, double &hausdorff_dis_threshold) {
+	DeviceMesh a(mesh0), b(mesh1);
+	std::vector<int32_t> out((size_t)mesh1.Vs.size()); int64_t n = 0;
+	check(fpohm_hausdorff_outliers(context(), a.h, b.h, hausdorff_dis_threshold, out.data(), &n), "fpohm_hausdorff_outliers");
+	outlierVs.assign(out.begin(), out.begin() + n);
+	std::cout << "refered total: " << outlierVs.size() << " " << mesh1.Vs.size() << std::endl;
+	return true;
+}
+
+} // namespace fpohm_shim

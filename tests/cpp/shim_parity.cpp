@@ -1,0 +1,127 @@
+// C++ end-to-end parity of the drop-in shim against the reference's own functions, both linked into one executable:
+//   reference side : libfpohm_ref.so  (unmodified octree.cpp / global_functions.cpp / metro_hausdorff.cpp ...)
+//   product side   : fpohm_shim.hpp over libfpohm.so (CUDA)
+// Built by `make -C oracle/ref shim_parity` (needs the reference headers, so only where /root/reference exists); the
+// binary travels to the GPU box inside oracle/_ref/ and is run by tests/test_gpu_parity.py::test_cpp_shim_parity.
+#include "grid_meshing/octree.h"
+#include "global_types.h"
+#include "global_functions.h"
+#include "metro_hausdorff.h"
+#include <igl/signed_distance.h>
+#include <geogram/basic/common.h>
+#include <geogram/basic/logger.h>
+#include <geogram/basic/command_line.h>
+#include <geogram/basic/command_line_args.h>
+
+#include "fpohm_shim.hpp"
+
+#include <cmath>
+#include <cstdio>
+
+static int failures = 0;
+#define EXPECT(cond, what) do { if (cond) std::printf("PASS %s\n", what); else { std::printf("FAIL %s\n", what); ++failures; } } while (0)
+
+static void torus(int nu, int nv, Mesh &m) {
+	const double R = 1.0, r = 0.35, PI = 3.14159265358979323846;
+	m.type = Mesh_type::Tri;
+	m.V.resize(3, nu * nv); m.Vs.resize(nu * nv);
+	for (int i = 0; i < nu; ++i) for (int j = 0; j < nv; ++j) {
+		const double u = 2 * PI * i / nu, v = 2 * PI * j / nv;
+		const int id = i * nv + j;
+		m.V(0, id) = (R + r * std::cos(v)) * std::cos(u) / 2.7; m.V(1, id) = (R + r * std::cos(v)) * std::sin(u) / 2.7; m.V(2, id) = r * std::sin(v) / 2.7;
+		m.Vs[id].id = id;
+	}
+	for (int i = 0; i < nu; ++i) for (int j = 0; j < nv; ++j) {
+		const uint32_t a = i * nv + j, b = ((i + 1) % nu) * nv + j, c = ((i + 1) % nu) * nv + (j + 1) % nv, d = i * nv + (j + 1) % nv;
+		Hybrid_F f0, f1; f0.vs = {a, b, c}; f1.vs = {a, c, d};
+		f0.id = (uint32_t)m.Fs.size(); m.Fs.push_back(f0); f1.id = (uint32_t)m.Fs.size(); m.Fs.push_back(f1);
+	}
+}
+static void hex_block(int n, double amp, Mesh &m) {
+	m.type = Mesh_type::Hex;
+	const int s = n + 1;
+	m.V.resize(3, s * s * s); m.Vs.resize(s * s * s);
+	for (int i = 0; i < s; ++i) for (int j = 0; j < s; ++j) for (int k = 0; k < s; ++k) {
+		const int id = (i * s + j) * s + k;
+		m.V(0, id) = i / (double)n + amp / n * std::sin(7.0 * j + k); m.V(1, id) = j / (double)n + amp / n * std::cos(3.0 * i + 2 * k);
+		m.V(2, id) = k / (double)n + amp / n * std::sin(5.0 * i * j + 1);
+		m.Vs[id].id = id;
+	}
+	auto vid = [&](int i, int j, int k) { return (uint32_t)((i * s + j) * s + k); };
+	for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) {
+		Hybrid h; h.id = (uint32_t)m.Hs.size();
+		h.vs = {vid(i, j, k), vid(i + 1, j, k), vid(i + 1, j + 1, k), vid(i, j + 1, k), vid(i, j, k + 1), vid(i + 1, j, k + 1), vid(i + 1, j + 1, k + 1), vid(i, j + 1, k + 1)};
+		m.Hs.push_back(h);
+	}
+}
+
+int main() {
+	GEO::initialize();
+	GEO::CmdLine::import_arg_group("standard");
+	GEO::Logger::instance()->set_quiet(true);
+
+	// ---- scaled_jacobian + build_connectivity on a tangled hex block
+	{
+		Mesh a, b; hex_block(7, 1.4, a); hex_block(7, 1.4, b);
+		Mesh_Quality qa, qb;
+		::scaled_jacobian(a, qa);
+		fpohm_shim::scaled_jacobian(b, qb);
+		EXPECT(qa.V_Js == qb.V_Js && qa.H_Js == qb.H_Js && qa.min_Jacobian == qb.min_Jacobian, "scaled_jacobian bit-exact (V_Js, H_Js, min)");
+		EXPECT(std::fabs(qa.ave_Jacobian - qb.ave_Jacobian) <= 1e-12 * std::fabs(qa.ave_Jacobian) && std::fabs(qa.deviation_Jacobian - qb.deviation_Jacobian) <= 1e-9 * qa.deviation_Jacobian,
+		       "scaled_jacobian ave/deviation within 1e-9 (north star 1e-5)");
+		::build_connectivity(a);
+		fpohm_shim::build_connectivity(b);
+		bool same = a.Fs.size() == b.Fs.size() && a.Es.size() == b.Es.size();
+		for (size_t i = 0; same && i < a.Fs.size(); ++i) same = a.Fs[i].vs == b.Fs[i].vs && a.Fs[i].es == b.Fs[i].es && a.Fs[i].boundary == b.Fs[i].boundary && a.Fs[i].neighbor_hs == b.Fs[i].neighbor_hs;
+		for (size_t i = 0; same && i < a.Es.size(); ++i) same = a.Es[i].vs == b.Es[i].vs && a.Es[i].boundary == b.Es[i].boundary && a.Es[i].neighbor_fs == b.Es[i].neighbor_fs && a.Es[i].neighbor_hs == b.Es[i].neighbor_hs;
+		for (size_t i = 0; same && i < a.Vs.size(); ++i) same = a.Vs[i].boundary == b.Vs[i].boundary && a.Vs[i].neighbor_vs == b.Vs[i].neighbor_vs && a.Vs[i].neighbor_es == b.Vs[i].neighbor_es && a.Vs[i].neighbor_fs == b.Vs[i].neighbor_fs && a.Vs[i].neighbor_hs == b.Vs[i].neighbor_hs;
+		for (size_t i = 0; same && i < a.Hs.size(); ++i) same = a.Hs[i].fs == b.Hs[i].fs;
+		EXPECT(same, "build_connectivity identical (F/E/V/H relations)");
+	}
+	// ---- points_inside_mesh + Treestr + signed_distance_pseudonormal + metro
+	{
+		Mesh t; torus(48, 30, t);
+		Eigen::MatrixXd Ps(4000, 3);
+		for (int i = 0; i < 4000; ++i) { Ps(i, 0) = std::sin(i * 0.37) * 0.55; Ps(i, 1) = std::cos(i * 0.91) * 0.55; Ps(i, 2) = std::sin(i * 1.73) * 0.2; }
+		Eigen::VectorXd sa, sb;
+		::points_inside_mesh(Ps, t, sa);
+		fpohm_shim::points_inside_mesh(Ps, t, sb);
+		EXPECT(sa == sb, "points_inside_mesh bit-exact");
+		Treestr tr;
+		fpohm_shim::build_aabb_tree(t, tr);
+		Eigen::MatrixXd V = t.V.transpose(), FN, VN, EN; Eigen::MatrixXi F = tr.TriF, E; Eigen::VectorXi EMAP;
+		igl::per_face_normals(V, F, FN);
+		igl::per_vertex_normals(V, F, igl::PER_VERTEX_NORMALS_WEIGHTING_TYPE_ANGLE, FN, VN);
+		igl::per_edge_normals(V, F, igl::PER_EDGE_NORMALS_WEIGHTING_TYPE_UNIFORM, FN, EN, E, EMAP);
+		EXPECT(FN == tr.TriFN && VN == tr.TriVN && EN == tr.TriEN && EMAP == tr.TriEMAP, "build_aabb_tree normals bit-exact (TriFN, TriVN, TriEN, TriEMAP)");
+		igl::AABB<Eigen::MatrixXd, 3> tree; tree.init(V, F);
+		Eigen::VectorXd S, S2; Eigen::VectorXi I, I2; Eigen::MatrixXd C, N, C2, N2;
+		igl::signed_distance_pseudonormal(Ps, V, F, tree, FN, VN, EN, EMAP, S, I, C, N);
+		fpohm_shim::signed_distance_pseudonormal(Ps, tr, S2, I2, C2, N2);
+		EXPECT(S == S2 && I == I2 && C == C2 && N == N2, "signed_distance_pseudonormal bit-exact (S, I, C, N)");
+		Mesh t2; torus(31, 19, t2); t2.V *= 1.01;
+		double d0, m0, a0, d1, m1, a1;
+		::compute((const Mesh &)t, (const Mesh &)t2, d0, m0, a0);
+		fpohm_shim::compute((const Mesh &)t, (const Mesh &)t2, d1, m1, a1);
+		EXPECT(d0 == d1 && std::fabs(m0 - m1) <= 1e-5 * m0 && std::fabs(a0 - a1) <= 1e-5 * a0, "metro compute within 1e-5");
+	}
+	// ---- OctreeGrid with an arbitrary host predicate (sphere shell), graded + paired
+	{
+		auto pred = [](int x, int y, int z, int e) {
+			if (e <= 2) return false;
+			const double cx = x + e * 0.5 - 32, cy = y + e * 0.5 - 32, cz = z + e * 0.5 - 16, r = std::sqrt(cx * cx + cy * cy + cz * cz);
+			return std::fabs(r - 13.0) < e * 0.9;
+		};
+		::OctreeGrid ref(Eigen::Vector3i(64, 64, 32));
+		ref.subdivide(pred, true, true);
+		fpohm_shim::OctreeGrid mine(std::array<int, 3>{{64, 64, 32}});
+		mine.subdivide(pred, true, true);
+		bool same = ref.numCells() == mine.numCells() && ref.numNodes() == mine.numNodes();
+		std::set<std::array<int, 4>> la, lb;
+		for (int c = 0; same && c < ref.numCells(); ++c) if (ref.cellIsLeaf(c)) { auto p = ref.cellCornerPos(c, 0); la.insert({{p[0], p[1], p[2], ref.cellExtent(c)}}); }
+		for (int c = 0; same && c < mine.numCells(); ++c) if (mine.cellIsLeaf(c)) { auto p = mine.cellCornerPos(c, 0); lb.insert({{p[0], p[1], p[2], mine.cellExtent(c)}}); }
+		EXPECT(same && la == lb && mine.is2to1Graded() && mine.isPaired() && ref.is2to1Graded() && ref.isPaired(), "OctreeGrid::subdivide(std::function) same leaf set, graded, paired");
+	}
+	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
+	return failures ? 1 : 0;
+}

@@ -300,3 +300,17 @@ def test_voxel_lattice(fp, ctx):
     c = lambda a, b, cc: idx[a:d[0] - 1 + a, b:d[1] - 1 + b, cc:d[2] - 1 + cc].reshape(-1)
     ref_H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
     assert np.array_equal(H, ref_H.astype(np.uint32))
+
+
+def test_cpp_shim_parity():
+    """The C++ drop-in shim (host/fpohm_shim.hpp, reference signatures and types) against the reference's own functions,
+    both linked into one executable (tests/cpp/shim_parity.cpp, built by `make -C oracle/ref shim_parity`)."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "shim_parity"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/shim_parity not built (needs the reference headers)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "SHIM PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout.count("PASS") >= 8
