@@ -19,7 +19,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the parity contract is "same IEEE-754 operations as the reference's SSE2 build" 
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
                      "-ccbin", "/usr/bin/g++", "-Xptxas", "-v", "-I", str(HERE.parent / "include")]
-CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fno-fast-math", "-ffp-contract=off", "-I", "/usr/local/cuda/include",
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-fno-fast-math", "-ffp-contract=off", "-I", "/usr/local/cuda/include",
              "-I", str(HERE.parent / "include")]
 
 

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <thread>
 
 namespace fpohm {
 
@@ -45,17 +46,15 @@ void igl_sort_column(const std::vector<double> &data, std::vector<size_t> &order
 	std::sort(order.begin(), order.end(), IndexLess{data});
 }
 
+// A tree over n facets is a full binary tree with 2n-1 nodes, so DFS pre-order positions are known up front
+// (left child = me + 1, right child = me + 2 * n_left): subtrees can be filled independently and the top levels are
+// built by parallel tasks.  Every std:: call still sees exactly the data igl would pass it.
 struct Builder {
-	const int32_t *F;
 	const std::vector<double> &tbox; // 6 per facet
 	const std::vector<int32_t> &SI;  // 3 per facet: rank on each axis
 	HostTree &out;
 
-	int32_t build(std::vector<int32_t> &I) {
-		const int32_t me = (int32_t)out.prim.size();
-		out.prim.push_back(-1);
-		out.lr.push_back(-1); out.lr.push_back(-1);
-		out.box.resize(out.box.size() + 6);
+	void build(std::vector<int32_t> &I, int32_t me, int depth) {
 		double mn[3] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max(), std::numeric_limits<double>::max()};
 		double mx[3] = {-mn[0], -mn[1], -mn[2]};
 		for (int32_t f : I) {
@@ -69,7 +68,7 @@ struct Builder {
 		const size_t n = I.size();
 		if (n == 1) {
 			out.prim[me] = I[0];
-			return me;
+			return;
 		}
 		// longest direction: Eigen maxCoeff keeps the first strict maximum
 		int max_d = 0;
@@ -99,12 +98,18 @@ struct Builder {
 		}
 		std::vector<int32_t>().swap(I);
 		std::vector<int>().swap(SIdI);
-		int32_t l = -1, r = -1;
-		if (!LI.empty()) l = build(LI);
-		if (!RI.empty()) r = build(RI);
+		// ranks are distinct, so both sides are non-empty (igl sizes them (n+1)/2 and n/2, AABB.cpp:168)
+		const int32_t l = me + 1, r = me + 2 * (int32_t)LI.size();
 		out.lr[2 * (size_t)me] = l;
 		out.lr[2 * (size_t)me + 1] = r;
-		return me;
+		if (depth < 4 && n > 4096) {
+			std::thread t([&]() { build(LI, l, depth + 1); });
+			build(RI, r, depth + 1);
+			t.join();
+		} else {
+			build(LI, l, depth + 1);
+			build(RI, r, depth + 1);
+		}
 	}
 };
 
@@ -114,7 +119,8 @@ void build_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, H
 	(void)nV;
 	out.box.clear(); out.prim.clear(); out.lr.clear();
 	if (nF <= 0) return;
-	out.prim.reserve(2 * (size_t)nF); out.lr.reserve(4 * (size_t)nF); out.box.reserve(12 * (size_t)nF);
+	const size_t nn = 2 * (size_t)nF - 1;
+	out.prim.assign(nn, -1); out.lr.assign(2 * nn, -1); out.box.assign(6 * nn, 0.0);
 	// barycentres, igl/barycenter.cpp: ((0 + v0) + v1) + v2, then `/= 3.0`.  NB Eigen 3.2's operator/=(scalar)
 	// multiplies by Scalar(1)/other (Eigen/src/Core/SelfCwiseBinaryOp.h:181-193) — also for per_face_normals' `N.row(i) /= r` below.
 	std::vector<double> col[3];
@@ -133,22 +139,47 @@ void build_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, H
 	}
 	std::vector<int32_t> SI(3 * (size_t)nF);
 	{
-		std::vector<size_t> order;
-		for (int d = 0; d < 3; ++d) {
+		// the three per-axis sorts are independent (igl/sort.cpp:50-79 loops over columns): one thread each
+		auto sort_axis = [&](int d) {
+			std::vector<size_t> order;
 			igl_sort_column(col[d], order);
 			for (size_t i = 0; i < (size_t)nF; ++i) SI[3 * order[i] + d] = (int32_t)i;
 			std::vector<double>().swap(col[d]);
+		};
+		if (nF > 4096) {
+			std::thread t0(sort_axis, 0), t1(sort_axis, 1);
+			sort_axis(2);
+			t0.join(); t1.join();
+		} else {
+			for (int d = 0; d < 3; ++d) sort_axis(d);
 		}
 	}
 	std::vector<int32_t> I((size_t)nF);
 	for (int64_t f = 0; f < nF; ++f) I[(size_t)f] = (int32_t)f;
-	Builder b{F, tbox, SI, out};
-	b.build(I);
+	Builder b{tbox, SI, out};
+	b.build(I, 0, 0);
 }
 
 // per_face_normals (igl/per_face_normals.cpp:13-36), per_vertex_normals ANGLE (igl/per_vertex_normals.cpp:38-108,
 // igl/internal_angles.cpp:64-87, igl/squared_edge_lengths.cpp:30-44), per_edge_normals UNIFORM
 // (igl/per_edge_normals.cpp:20-77, igl/all_edges.cpp:35-42, igl/unique_simplices.cpp:16-33).
+// static range split over host threads (results do not depend on the thread count: every output element is produced
+// by exactly one thread with the reference's sequential order of operations)
+template <class Fn>
+static void parallel_ranges(int64_t n, const Fn &fn) {
+	unsigned T = std::thread::hardware_concurrency();
+	if (T == 0) T = 1;
+	if (T > 16) T = 16;
+	if (n < 50000) T = 1;
+	if (T == 1) { fn((int64_t)0, n); return; }
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < T; ++t) {
+		const int64_t lo = n * t / T, hi = n * (t + 1) / T;
+		th.emplace_back([&fn, lo, hi]() { fn(lo, hi); });
+	}
+	for (auto &x : th) x.join();
+}
+
 void build_igl_normals(const double *V, int64_t nV, const int32_t *F, int64_t nF,
                        std::vector<double> &FN, std::vector<double> &VN, std::vector<double> &EN,
                        std::vector<int32_t> &E, std::vector<int32_t> &EMAP)
@@ -157,52 +188,75 @@ void build_igl_normals(const double *V, int64_t nV, const int32_t *F, int64_t nF
 	VN.assign(3 * (size_t)nV, 0.0);
 	// rows of dynamic-size Eigen matrices reduce sequentially: (x^2 + y^2) + z^2 (Eigen 3.2 DefaultTraversal/NoUnrolling)
 	auto sqn = [](double x, double y, double z) { return (x * x + y * y) + z * z; };
-	for (int64_t f = 0; f < nF; ++f) {
-		const double *p0 = V + 3 * (int64_t)F[3 * f], *p1 = V + 3 * (int64_t)F[3 * f + 1], *p2 = V + 3 * (int64_t)F[3 * f + 2];
-		const double a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
-		const double b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-		double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-		const double r = std::sqrt(sqn(n[0], n[1], n[2]));
-		if (r == 0) { n[0] = n[1] = n[2] = 0; } else { const double ir = 1.0 / r; n[0] *= ir; n[1] *= ir; n[2] *= ir; }
-		for (int c = 0; c < 3; ++c) FN[3 * (size_t)f + c] = n[c];
-	}
-	for (int64_t f = 0; f < nF; ++f) {
-		const double *p0 = V + 3 * (int64_t)F[3 * f], *p1 = V + 3 * (int64_t)F[3 * f + 1], *p2 = V + 3 * (int64_t)F[3 * f + 2];
-		double L[3];
-		L[0] = sqn(p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]);
-		L[1] = sqn(p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]);
-		L[2] = sqn(p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]);
-		for (int d = 0; d < 3; ++d) {
-			const double s1 = L[d], s2 = L[(d + 1) % 3], s3 = L[(d + 2) % 3];
-			const double w = std::acos((s3 + s2 - s1) / (2. * std::sqrt(s3 * s2)));
-			double *vn = &VN[3 * (size_t)F[3 * f + d]];
-			for (int c = 0; c < 3; ++c) vn[c] += w * FN[3 * (size_t)f + c];
+	std::vector<double> W(3 * (size_t)nF);       // internal angles, igl/internal_angles.cpp:64-87
+	parallel_ranges(nF, [&](int64_t lo, int64_t hi) {
+		for (int64_t f = lo; f < hi; ++f) {
+			const double *p0 = V + 3 * (int64_t)F[3 * f], *p1 = V + 3 * (int64_t)F[3 * f + 1], *p2 = V + 3 * (int64_t)F[3 * f + 2];
+			const double a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+			const double b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+			double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+			const double r = std::sqrt(sqn(n[0], n[1], n[2]));
+			if (r == 0) { n[0] = n[1] = n[2] = 0; } else { const double ir = 1.0 / r; n[0] *= ir; n[1] *= ir; n[2] *= ir; }
+			for (int c = 0; c < 3; ++c) FN[3 * (size_t)f + c] = n[c];
+			double L[3];
+			L[0] = sqn(p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]);
+			L[1] = sqn(p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]);
+			L[2] = sqn(p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]);
+			for (int d = 0; d < 3; ++d) {
+				const double s1 = L[d], s2 = L[(d + 1) % 3], s3 = L[(d + 2) % 3];
+				W[3 * (size_t)f + d] = std::acos((s3 + s2 - s1) / (2. * std::sqrt(s3 * s2)));
+			}
 		}
-	}
-	for (int64_t v = 0; v < nV; ++v) {
-		double *vn = &VN[3 * (size_t)v];
-		// N.rowwise().normalize() is a cwiseQuotient by the row norm (Eigen/src/Core/VectorwiseOp.h:539-550): true division
-		const double r = std::sqrt(sqn(vn[0], vn[1], vn[2]));
-		vn[0] /= r; vn[1] /= r; vn[2] /= r;
-	}
-	// undirected edges: directed edge (f,c) = (F[(c+1)%3], F[(c+2)%3]), stored at row f + c*nF
+	});
+	// N.row(F(i,j)) += W(i,j) * FN.row(i) for i ascending (igl/per_vertex_normals.cpp:66-73): each thread owns a vertex
+	// range and walks ALL faces in order, so every vertex sees its contributions in the reference's order
+	parallel_ranges(nV, [&](int64_t vlo, int64_t vhi) {
+		for (int64_t f = 0; f < nF; ++f)
+			for (int d = 0; d < 3; ++d) {
+				const int64_t v = F[3 * f + d];
+				if (v < vlo || v >= vhi) continue;
+				const double w = W[3 * (size_t)f + d];
+				double *vn = &VN[3 * (size_t)v];
+				for (int c = 0; c < 3; ++c) vn[c] += w * FN[3 * (size_t)f + c];
+			}
+		for (int64_t v = vlo; v < vhi; ++v) {
+			double *vn = &VN[3 * (size_t)v];
+			// N.rowwise().normalize() is a cwiseQuotient by the row norm (Eigen/src/Core/VectorwiseOp.h:539-550): true division
+			const double r = std::sqrt(sqn(vn[0], vn[1], vn[2]));
+			vn[0] /= r; vn[1] /= r; vn[2] /= r;
+		}
+	});
+	std::vector<double>().swap(W);
+	// undirected edges: directed edge (f,c) = (F[(c+1)%3], F[(c+2)%3]), stored at row f + c*nF; unique rows in
+	// lexicographic (min, max) order (igl/unique_simplices.cpp:16-33).  LSD radix sort (16-bit digits) on (min << b) | max.
 	const size_t m = (size_t)nF;
+	int vb = 1;
+	while ((1ll << vb) < nV) ++vb;
 	std::vector<uint64_t> key(3 * m);
 	for (size_t f = 0; f < m; ++f)
 		for (int c = 0; c < 3; ++c) {
-			uint32_t a = (uint32_t)F[3 * f + (c + 1) % 3], b = (uint32_t)F[3 * f + (c + 2) % 3];
+			uint64_t a = (uint32_t)F[3 * f + (c + 1) % 3], b = (uint32_t)F[3 * f + (c + 2) % 3];
 			if (a > b) std::swap(a, b);
-			key[f + (size_t)c * m] = ((uint64_t)a << 32) | b;
+			key[f + (size_t)c * m] = (a << vb) | b;
 		}
-	std::vector<uint64_t> uniq(key);
-	std::sort(uniq.begin(), uniq.end());
+	std::vector<uint64_t> uniq(key), tmp(3 * m);
+	for (int shift = 0; shift < 2 * vb; shift += 16) {
+		size_t cnt[65537] = {0};
+		for (uint64_t k : uniq) ++cnt[((k >> shift) & 0xffff) + 1];
+		for (int i = 0; i < 65536; ++i) cnt[i + 1] += cnt[i];
+		for (uint64_t k : uniq) tmp[cnt[(k >> shift) & 0xffff]++] = k;
+		uniq.swap(tmp);
+	}
 	uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+	const uint64_t lowmask = (1ull << vb) - 1;
 	E.resize(2 * uniq.size());
-	for (size_t e = 0; e < uniq.size(); ++e) { E[2 * e] = (int32_t)(uniq[e] >> 32); E[2 * e + 1] = (int32_t)(uniq[e] & 0xffffffffu); }
+	for (size_t e = 0; e < uniq.size(); ++e) { E[2 * e] = (int32_t)(uniq[e] >> vb); E[2 * e + 1] = (int32_t)(uniq[e] & lowmask); }
 	EMAP.resize(3 * m);
-	for (size_t i = 0; i < 3 * m; ++i) EMAP[i] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), key[i]) - uniq.begin());
+	parallel_ranges((int64_t)(3 * m), [&](int64_t lo, int64_t hi) {
+		for (int64_t i = lo; i < hi; ++i) EMAP[(size_t)i] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), key[(size_t)i]) - uniq.begin());
+	});
 	EN.assign(3 * uniq.size(), 0.0);
-	for (size_t f = 0; f < m; ++f)
+	for (size_t f = 0; f < m; ++f)                      // N.row(EMAP(f + c*m)) += FN.row(f), f then c (igl/per_edge_normals.cpp:63-75)
 		for (int c = 0; c < 3; ++c) {
 			double *en = &EN[3 * (size_t)EMAP[f + (size_t)c * m]];
 			for (int k = 0; k < 3; ++k) en[k] += FN[3 * f + k];
