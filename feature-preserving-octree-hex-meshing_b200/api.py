@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree",
-    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
 
@@ -345,6 +345,11 @@ def compute_sign_voxels(ctx: Context, mesh: TriMesh, grid: VoxelGrid):
 
 def voxel_sign_dev(ctx: Context, mesh: TriMesh, grid: VoxelGrid, out_ptr: int, stream: int = 0):
     _chk(lib().fpohm_voxel_sign_dev(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(grid.dims), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def voxel_sign_slab_dev(ctx: Context, mesh: TriMesh, grid: VoxelGrid, z_begin: int, z_end: int, out_ptr: int, stream: int = 0):
+    _chk(lib().fpohm_voxel_sign_slab_dev(ctx.h, mesh.h, _p(grid.origin), C.c_double(grid.spacing), _p(grid.dims), C.c_int32(z_begin),
+                                         C.c_int32(z_end), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def voxel_occupancy(ctx: Context, mesh: TriMesh, grid: VoxelGrid):

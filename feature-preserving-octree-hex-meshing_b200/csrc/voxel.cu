@@ -116,7 +116,7 @@ __device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
 // reference tests, instead of one tree descent per column (first version: 6.9 of 7.1 ms at 1024^2 columns, 2 M facets).
 // first layer index k in [0, nz] with  hit_z < (k + 0.5) * spacing + oz   (exactly the comparison of voxelization.h:259-261)
 __device__ __forceinline__ int first_layer_above(double z, double oz, double spacing, int nz) {
-	int k = (int)floor((z - oz) / spacing - 0.5);
+	int k = (int)floor((z - oz) * __drcp_rn(spacing) - 0.5);   // guess only: the two loops below decide with the exact expression
 	if (k < 0) k = 0;
 	if (k > nz) k = nz;
 	while (k > 0 && z < ((k - 1) + 0.5) * spacing + oz) --k;
@@ -126,7 +126,7 @@ __device__ __forceinline__ int first_layer_above(double z, double oz, double spa
 
 __device__ __forceinline__ int first_center_ge(double lo, double o, double sp, int n) {
 	// smallest index i in [0, n] with (i + 0.5) * sp + o >= lo
-	int i = (int)floor((lo - o) / sp - 0.5);
+	int i = (int)floor((lo - o) * __drcp_rn(sp) - 0.5);          // guess only
 	if (i < 0) i = 0;
 	if (i > n) i = n;
 	while (i > 0 && ((i - 1) + 0.5) * sp + o >= lo) --i;
@@ -135,7 +135,7 @@ __device__ __forceinline__ int first_center_ge(double lo, double o, double sp, i
 }
 __device__ __forceinline__ int last_center_le(double hi, double o, double sp, int n) {
 	// largest index i in [-1, n-1] with (i + 0.5) * sp + o <= hi
-	int i = (int)floor((hi - o) / sp - 0.5);
+	int i = (int)floor((hi - o) * __drcp_rn(sp) - 0.5);          // guess only
 	if (i < -1) i = -1;
 	if (i > n - 1) i = n - 1;
 	while (i < n - 1 && ((i + 1) + 0.5) * sp + o <= hi) ++i;
@@ -280,42 +280,58 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ h
 	}
 }
 
+#define FILL_CH 2      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
-                  const uint32_t *__restrict__ sum, uint8_t *__restrict__ out)
+                  const uint32_t *__restrict__ sum, uint8_t *__restrict__ out, int zc_begin, int zc_end)
 {
-	const int gx = (nx + 3) / 4, gz = (nz + FILL_Z - 1) / FILL_Z;
+	// layers [zc_begin * 32, min(zc_end * 32, nz)) are written, the first of them at `out` (z-slab sharding)
+	const int gx = (nx + 3) / 4, gzc = zc_end, gz = (zc_end - zc_begin + FILL_CH - 1) / FILL_CH;
 	const int64_t nthreads = (int64_t)gx * ny * gz;
 	const int64_t layer = (int64_t)nx * ny;
 	const bool aligned = (nx & 3) == 0;               // rows are 4-byte aligned, no ragged tail
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nthreads; t += (int64_t)gridDim.x * blockDim.x) {
-		const int x0 = (int)(t % gx) * 4, y = (int)((t / gx) % ny), zc = (int)(t / ((int64_t)gx * ny));
-		const int z0 = zc * FILL_Z, z1 = min(z0 + FILL_Z, nz);
+		const int x0 = (int)(t % gx) * 4, y = (int)((t / gx) % ny), zg = (int)(t / ((int64_t)gx * ny));
 		const int64_t col0 = (int64_t)y * nx + x0;
-		const uint32_t *si = sum + (int64_t)(2 * (zc >> 5)) * layer + col0, *sd = si + layer;
-		const int bit = zc & 31;
-		uint32_t m[4];
+		uint32_t si[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
+		int cur_word = -1;
 #pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			m[c] = 0;
-			if (x0 + c >= nx) continue;
-			if ((sd[c] >> bit) & 1u) m[c] = chunk_mask_sorted(hit_ev + (col0 + c) * HIT_CAP, min(hit_n[col0 + c], HIT_CAP), z0, z1);
-			else m[c] = ((si[c] >> bit) & 1u) ? 0xffffffffu : 0u;
-		}
-		uint8_t *o = out + (int64_t)z0 * layer + col0;     // index_from_index3, voxelization.cpp:26-28
-		const uint32_t any = m[0] | m[1] | m[2] | m[3], all = m[0] & m[1] & m[2] & m[3];
-		if (aligned && (any == 0u || all == 0xffffffffu)) {            // uniform tile: store only
-			const uint32_t w = any ? 0x01010101u : 0u;
-			for (int z = z0; z < z1; ++z, o += layer) *reinterpret_cast<uint32_t *>(o) = w;
-		} else if (aligned) {
-			uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
-			for (int z = z0; z < z1; ++z, o += layer) {
-				*reinterpret_cast<uint32_t *>(o) = (m0 & 1u) | ((m1 & 1u) << 8) | ((m2 & 1u) << 16) | ((m3 & 1u) << 24);
-				m0 >>= 1; m1 >>= 1; m2 >>= 1; m3 >>= 1;
+		for (int ch = 0; ch < FILL_CH; ++ch) {
+			const int zc = zc_begin + zg * FILL_CH + ch;
+			if (zc >= gzc) break;
+			if ((zc >> 5) != cur_word) {
+				cur_word = zc >> 5;
+				const uint32_t *pi = sum + (int64_t)(2 * cur_word) * layer + col0, *pd = pi + layer;
+				if (aligned) {
+					const uint4 a = __ldg(reinterpret_cast<const uint4 *>(pi)), b = __ldg(reinterpret_cast<const uint4 *>(pd));
+					si[0] = a.x; si[1] = a.y; si[2] = a.z; si[3] = a.w; sd[0] = b.x; sd[1] = b.y; sd[2] = b.z; sd[3] = b.w;
+				} else {
+					for (int c = 0; c < 4; ++c) if (x0 + c < nx) { si[c] = pi[c]; sd[c] = pd[c]; }
+				}
 			}
-		} else {
-			for (int z = z0; z < z1; ++z, o += layer)
-				for (int c = 0; c < 4; ++c) if (x0 + c < nx) o[c] = (m[c] >> (z - z0)) & 1u;
+			const int z0 = zc * FILL_Z, z1 = min(z0 + FILL_Z, nz);
+			const int bit = zc & 31;
+			uint32_t m[4];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				if ((sd[c] >> bit) & 1u) m[c] = chunk_mask_sorted(hit_ev + (col0 + c) * HIT_CAP, min(hit_n[col0 + c], HIT_CAP), z0, z1);
+				else m[c] = ((si[c] >> bit) & 1u) ? 0xffffffffu : 0u;
+			}
+			uint8_t *o = out + (int64_t)(z0 - zc_begin * FILL_Z) * layer + col0;     // index_from_index3, voxelization.cpp:26-28
+			const uint32_t any = m[0] | m[1] | m[2] | m[3], all = m[0] & m[1] & m[2] & m[3];
+			if (aligned && (any == 0u || all == 0xffffffffu)) {            // uniform tile: store only
+				const uint32_t w = any ? 0x01010101u : 0u;
+				for (int z = z0; z < z1; ++z, o += layer) *reinterpret_cast<uint32_t *>(o) = w;
+			} else if (aligned) {
+				uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+				for (int z = z0; z < z1; ++z, o += layer) {
+					*reinterpret_cast<uint32_t *>(o) = (m0 & 1u) | ((m1 & 1u) << 8) | ((m2 & 1u) << 16) | ((m3 & 1u) << 24);
+					m0 >>= 1; m1 >>= 1; m2 >>= 1; m3 >>= 1;
+				}
+			} else {
+				for (int z = z0; z < z1; ++z, o += layer)
+					for (int c = 0; c < 4; ++c) if (x0 + c < nx) o[c] = (m[c] >> (z - z0)) & 1u;
+			}
 		}
 	}
 }
@@ -443,26 +459,39 @@ int fpohm_voxel_grid_setup(const double origin[3], const double extent[3], doubl
 	FPOHM_API_END
 }
 
-int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
-                         const int32_t dims[3], uint8_t *out_dev, void *stream)
+int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                              const int32_t dims[3], int32_t z_begin, int32_t z_end, uint8_t *out_dev, void *stream)
 {
 	FPOHM_API_BEGIN
-	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims && out_dev && spacing > 0, FPOHM_EINVAL, "fpohm_voxel_sign_dev: bad argument");
-	check_dims(dims, 3, "fpohm_voxel_sign_dev");
+	FPOHM_REQUIRE(ctx && mesh && grid_origin && dims && out_dev && spacing > 0, FPOHM_EINVAL, "fpohm_voxel_sign_slab_dev: bad argument");
+	check_dims(dims, 3, "fpohm_voxel_sign_slab_dev");
+	FPOHM_REQUIRE(z_begin >= 0 && z_begin < z_end && z_end <= dims[2] && z_begin % FILL_Z == 0 && (z_end % FILL_Z == 0 || z_end == dims[2]), FPOHM_EINVAL,
+	              "fpohm_voxel_sign_slab_dev: slab [%d,%d) must be non-empty, inside [0,%d) and aligned to %d layers", z_begin, z_end, dims[2], FILL_Z);
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = (cudaStream_t)stream;
 	HitScratch h;
 	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1]};
+	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
 	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s, true, grid_origin[2], dims[2]);
 	const int gz = (dims[2] + FILL_Z - 1) / FILL_Z, n_words = (gz + 31) / 32;
 	const int64_t ncol = (int64_t)dims[0] * dims[1];
 	DevBuf<uint32_t> summary(2 * n_words * ncol, s);
 	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p);
 	FPOHM_LAUNCH_CHECK(ctx);
-	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * gz;
-	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], dims[2], h.ev.p, h.n.p, summary.p, out_dev);
+	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
+	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + FILL_CH - 1) / FILL_CH);
+	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], z_end, h.ev.p, h.n.p, summary.p, out_dev, zc0, zc1);
 	FPOHM_LAUNCH_CHECK(ctx);
 	check_overflow(h, s, "fpohm_voxel_sign");
+	FPOHM_API_END
+}
+
+int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                         const int32_t dims[3], uint8_t *out_dev, void *stream)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(dims, FPOHM_EINVAL, "fpohm_voxel_sign_dev: bad argument");
+	return fpohm_voxel_sign_slab_dev(ctx, mesh, grid_origin, spacing, dims, 0, dims[2], out_dev, stream);
 	FPOHM_API_END
 }
 

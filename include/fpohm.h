@@ -123,6 +123,11 @@ int fpohm_voxel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_o
                      const int32_t dims[3], uint8_t *out);
 int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
                          const int32_t dims[3], uint8_t *out_dev, void *stream);
+/* z-slab of the same grid (multi-GPU sharding): writes layers [z_begin, z_end) only, the first at out_dev.
+ * z_begin must be a multiple of 32 and z_end a multiple of 32 or dims[2]; concatenating the slabs is bit-identical to the
+ * unsliced call (hits and parity are evaluated on the whole column, only the fill is sliced). */
+int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
+                              const int32_t dims[3], int32_t z_begin, int32_t z_end, uint8_t *out_dev, void *stream);
 /* subdivision predicate on a dense grid: out[x + nx*(y + ny*z)] = 1 iff some facet AABB overlaps the closed
  * cell box (geo/basic/geometry.h:612-622 with the box of voxelization.cpp:370-375, extent = 1) */
 int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,

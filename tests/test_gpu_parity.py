@@ -314,3 +314,50 @@ def test_cpp_shim_parity():
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "SHIM PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     assert r.stdout.count("PASS") >= 8
+
+
+def test_shard_invariance_single_gpu(fp, ctx, ref):
+    """an N-shard result must equal the 1-shard result bit for bit.  Shards are run one after the other on
+    one GPU here; bench.py --gpus N runs them on N GPUs."""
+    import torch
+    from fpohm_b200 import sharding
+    pm = fp.procedural
+    dev = torch.device("cuda", 0)
+    V, F = pm.torus(60, 40)
+    m = fp.TriMesh(ctx, V, F)
+    # --- queries by range
+    P = np.random.default_rng(9).uniform(-0.6, 0.6, (10007, 3))
+    S, I, C, N = m.signed_distance_pseudonormal(P)
+    for W in (2, 3):
+        parts = [m.signed_distance_pseudonormal(P[slice(*sharding.shard_range(len(P), r, W))]) for r in range(W)]
+        for k, whole in enumerate((S, I, C, N)):
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), whole)
+    # --- voxel grid by z slabs (aligned to 32 layers)
+    mn, ext = V.min(0), V.max(0) - V.min(0)
+    g = fp.VoxelGrid(mn, ext, 1 / 160, 1)
+    whole = torch.empty(g.num_voxels(), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    fp.voxel_sign_dev(ctx, m, g, whole.data_ptr(), st)
+    nz, layer = int(g.dims[2]), int(g.dims[0]) * int(g.dims[1])
+    for W in (2, 3):
+        chunks = (nz + 31) // 32
+        pieces = []
+        for r in range(W):
+            c0, c1 = sharding.shard_range(chunks, r, W)
+            z0, z1 = c0 * 32, min(c1 * 32, nz)
+            if z0 >= z1:
+                continue
+            buf = torch.empty((z1 - z0) * layer, dtype=torch.uint8, device=dev)
+            fp.voxel_sign_slab_dev(ctx, m, g, z0, z1, buf.data_ptr(), st)
+            pieces.append(buf)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(pieces), whole)
+    assert int(whole.sum()) > 0
+    # --- hexes by range: per-hex values identical, statistics through the fixed-order reduction
+    Vh, H = pm.warped_hex_block(12, 1.2)
+    VJ, HJ, mad, fl = fp.scaled_jacobian(ctx, Vh, H)
+    parts = [fp.scaled_jacobian(ctx, Vh, H[slice(*sharding.shard_range(len(H), r, 2))]) for r in range(2)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), VJ) and np.array_equal(np.concatenate([p[1] for p in parts]), HJ)
+    assert min(p[2][0] for p in parts) == mad[0] and sum(p[3] for p in parts) == fl
+    np.testing.assert_allclose(sum(p[2][1] * len(p[1]) for p in parts) / len(HJ), mad[1], rtol=1e-14)
+    m.close()
