@@ -89,7 +89,10 @@ __device__ __forceinline__ void test_leaf(const double *__restrict__ tri, int32_
 // when it is popped).  A contained child visited with best == 0 cannot change the result (strict '<').
 // NOTE (round 1, measured): a "while-while" restructuring (inner loop over internal nodes only, leaf tests batched per
 // warp) ran 2.6x SLOWER on B200 (37.3 ms vs 14.2 ms for 4.6 M queries) — igl's order visits few leaves per query and the
-// forced reconvergence serialises the short box steps; the plain form below is kept.  profiles/r01_ncu_summary.md.
+// forced reconvergence serialises the short box steps; an explicit warp-voted variant (leaf tests batched once >= 20 lanes
+// hold one) took 25.0 ms, and an order-free search seeded with the previous query's facet (+ an igl visiting-order
+// comparator at ties, bit-identical results) did not reduce the work (65 -> 61 node visits, 14.5 -> 12.8 leaf tests per query:
+// intrinsic to the tree and geometry).  The plain form below is kept.  profiles/r01_ncu_summary.md.
 #define FPOHM_STACK 48
 __device__ __forceinline__ void traverse(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri,
                                          const V3 &p, Hit &h)
