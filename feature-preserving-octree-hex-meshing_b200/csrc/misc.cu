@@ -172,26 +172,71 @@ __global__ void lattice_hexes_kernel(int d0, int d1, int d2, uint32_t *__restric
 	}
 }
 
-// dense subdivision predicate: cell (x,y,z) box = origin + spacing*x ... + spacing*1 (voxelization.cpp:370-375, extent 1)
+// Dense subdivision predicate, FACET-parallel.  Cell (x,y,z) has the box [o + sp*x, (o + sp*x) + sp*1] per axis
+// (voxelization.cpp:370-375 with extent 1) and is occupied iff some facet box overlaps it in closed intervals
+// (geo/basic/geometry.h:612-622).  Per axis the overlap condition is monotone in the cell index, so every facet owns an
+// index BOX [x0,x1] x [y0,y1] x [z0,z1] whose limits are found with the reference's own expressions; the grid is zeroed
+// once and each facet stamps its box.  Work ~ number of (facet, cell) overlaps instead of one tree descent per voxel.
+__device__ __forceinline__ int first_cell_max_ge(double lo, double o, double sp, int n) {
+	// smallest i in [0, n] with (o + sp*i) + sp*1 >= lo      (cell.max < tri.min fails)
+	int i = (int)floor((lo - o) * __drcp_rn(sp) - 1.0);
+	if (i < 0) i = 0;
+	if (i > n) i = n;
+	while (i > 0 && (o + sp * (i - 1)) + sp * 1 >= lo) --i;
+	while (i < n && !((o + sp * i) + sp * 1 >= lo)) ++i;
+	return i;
+}
+__device__ __forceinline__ int last_cell_min_le(double hi, double o, double sp, int n) {
+	// largest i in [-1, n-1] with o + sp*i <= hi             (cell.min > tri.max fails)
+	int i = (int)floor((hi - o) * __drcp_rn(sp));
+	if (i < -1) i = -1;
+	if (i > n - 1) i = n - 1;
+	while (i < n - 1 && o + sp * (i + 1) <= hi) ++i;
+	while (i >= 0 && !(o + sp * i <= hi)) --i;
+	return i;
+}
+
+struct OccGrid { int nx, ny, nz; double ox, oy, oz, sp; };
+#define OCC_INLINE 64
 __global__ void __launch_bounds__(256)
-occupancy_kernel(int nx, int ny, int nz, double ox, double oy, double oz, double sp, const double *__restrict__ box, int64_t P,
-                 uint8_t *__restrict__ out)
+occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, int *__restrict__ box6, int64_t *__restrict__ cnt,
+                       uint8_t *__restrict__ out)
 {
-	const int64_t n = (int64_t)nx * ny * nz;
-	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-		const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((int64_t)nx * ny));
-		const double mn0 = ox + sp * x, mn1 = oy + sp * y, mn2 = oz + sp * z;
-		const double mx0 = mn0 + sp * 1, mx1 = mn1 + sp * 1, mx2 = mn2 + sp * 1;
-		int64_t stack[40]; int spx = 0; stack[spx++] = 1;
-		bool hit = false;
-		while (spx > 0) {
-			const int64_t nd = stack[--spx];
-			const double *b = box + 6 * nd;
-			if (mx0 < b[0] || mn0 > b[3] || mx1 < b[1] || mn1 > b[4] || mx2 < b[2] || mn2 > b[5]) continue;
-			if (nd >= P) { hit = true; break; }
-			stack[spx++] = 2 * nd + 1; stack[spx++] = 2 * nd;
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f <= nF; f += (int64_t)gridDim.x * blockDim.x) {
+		if (f == nF) { cnt[f] = 0; continue; }
+		const double *t = tri + 9 * f;
+		int lo[3], hi[3];
+		const int n[3] = {g.nx, g.ny, g.nz};
+		const double o[3] = {g.ox, g.oy, g.oz};
+		int64_t vol = 1;
+#pragma unroll
+		for (int c = 0; c < 3; ++c) {
+			const double mn = fmin(t[c], fmin(t[3 + c], t[6 + c])), mx = fmax(t[c], fmax(t[3 + c], t[6 + c]));
+			lo[c] = first_cell_max_ge(mn, o[c], g.sp, n[c]);
+			hi[c] = last_cell_min_le(mx, o[c], g.sp, n[c]);
+			vol *= hi[c] >= lo[c] ? (hi[c] - lo[c] + 1) : 0;
 		}
-		out[i] = hit;
+		if (vol <= OCC_INLINE) {
+			for (int z = lo[2]; z <= hi[2] && vol; ++z)
+				for (int y = lo[1]; y <= hi[1]; ++y)
+					for (int x = lo[0]; x <= hi[0]; ++x) out[((int64_t)z * g.ny + y) * g.nx + x] = 1;
+			cnt[f] = 0;
+		} else {
+			cnt[f] = vol;
+			for (int c = 0; c < 3; ++c) { box6[6 * f + c] = lo[c]; box6[6 * f + 3 + c] = hi[c] - lo[c] + 1; }
+		}
+	}
+}
+__global__ void __launch_bounds__(256)
+occupancy_pairs_kernel(OccGrid g, int64_t nF, const int *__restrict__ box6, const int64_t *__restrict__ off, int64_t n_pairs, uint8_t *__restrict__ out) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
+		int64_t lo = 0, hi = nF;
+		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+		const int *b = box6 + 6 * lo;
+		int64_t k = t - off[lo];
+		const int x = b[0] + (int)(k % b[3]); k /= b[3];
+		const int y = b[1] + (int)(k % b[4]), z = b[2] + (int)(k / b[4]);
+		out[((int64_t)z * g.ny + y) * g.nx + x] = 1;
 	}
 }
 
@@ -415,13 +460,27 @@ int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double g
 	FPOHM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n < (1ll << 31), FPOHM_ERANGE, "fpohm_voxel_occupancy: bad dims");
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
-	fpohm_mesh *m = const_cast<fpohm_mesh *>(mesh);
-	mesh_ensure_pred(ctx, m, s);
 	DevBuf<uint8_t> d(n, s);
 	KernelTimer t(ctx, s);
-	occupancy_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, s>>>(dims[0], dims[1], dims[2], grid_origin[0], grid_origin[1], grid_origin[2], spacing,
-		m->pred_box.p, m->pred_nodes / 2, d.p);
+	d.zero();
+	const OccGrid og{dims[0], dims[1], dims[2], grid_origin[0], grid_origin[1], grid_origin[2], spacing};
+	const int64_t nF = mesh->nF;
+	DevBuf<int> box6(6 * nF, s);
+	DevBuf<int64_t> cnt(nF + 1, s), off(nF + 1, s);
+	occupancy_boxes_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(og, mesh->tri.p, nF, box6.p, cnt.p, d.p);
 	FPOHM_LAUNCH_CHECK(ctx);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nF + 1, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nF + 1, s));
+	ctx->launches += 1;
+	int64_t n_pairs = 0;
+	FPOHM_CUDA(cudaMemcpyAsync(&n_pairs, off.p + nF, 8, cudaMemcpyDeviceToHost, s));
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	if (n_pairs > 0) {
+		occupancy_pairs_kernel<<<grid_for(ctx, n_pairs, 256, 8), 256, 0, s>>>(og, nF, box6.p, off.p, n_pairs, d.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
 	t.stop();
 	d.download(out, n);
 	FPOHM_CUDA(cudaStreamSynchronize(s));

@@ -15,7 +15,7 @@ try:
     PEAK = float(json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
 except Exception:
     pass
-which = set(sys.argv[1:]) or {"jacobian", "voxel", "octree", "hausdorff", "connectivity", "query"}
+which = set(sys.argv[1:]) or {"jacobian", "voxel", "occupancy", "octree", "hausdorff", "connectivity", "query"}
 pm = fp.procedural
 dev = torch.device("cuda", 0)
 ctx = fp.Context(0)
@@ -51,7 +51,7 @@ if "jacobian" in which:   # C4: 216^3 = 10 077 696 hexes
     out["jacobian_C4"] = dict(hexes=nH, ms=ms, hexes_per_s=nH / ms * 1e3, GBs=by / ms / 1e6, frac=by / ms / 1e6 / PEAK, stats=st.tolist())
     del dV, dH, dVJ, dHJ
 
-if which & {"voxel", "octree", "hausdorff", "query"}:
+if which & {"voxel", "occupancy", "octree", "hausdorff", "query"}:
     t = time.perf_counter(); V, F = c3_mesh(); gen_s = time.perf_counter() - t
     mesh = fp.TriMesh(ctx, V, F)
     out["C3_mesh"] = dict(tris=len(F), verts=len(V), gen_s=gen_s)
@@ -66,6 +66,20 @@ if "voxel" in which:
         out[f"voxel_sign_{n}"] = dict(dims=g.dims.tolist(), voxels=g.num_voxels(), ms=ms, GBs=by / ms / 1e6, frac=by / ms / 1e6 / PEAK,
                                       inside=int(buf.sum().item()))
         del buf
+
+if "occupancy" in which:
+    mn, ext = V.min(0), V.max(0) - V.min(0)
+    for n in (512, 1024):
+        g = fp.VoxelGrid(mn, ext, 1.0 / n, 0)
+        out_h = np.zeros(g.num_voxels(), np.uint8)
+        import ctypes as C
+        for _ in range(3):
+            rc = fp.lib().fpohm_voxel_occupancy(ctx.h, mesh.h, g.origin.ctypes.data_as(C.c_void_p), C.c_double(g.spacing), g.dims.ctypes.data_as(C.c_void_p),
+                                                out_h.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+        ms = ctx.last_kernel_ms()
+        by = g.num_voxels() + 72 * len(F)
+        out[f"voxel_occupancy_{n}"] = dict(voxels=g.num_voxels(), kernel_ms=ms, GBs=by / ms / 1e6, frac=by / ms / 1e6 / PEAK, occupied=int(out_h.sum()))
 
 if "octree" in which:
     p = fp.octree_grid_setup(V, 1 << 20)

@@ -34,3 +34,13 @@ def ctx(fp):
     c = fp.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def port():
+    """CPU restatement oracle (oracle/port); built on demand."""
+    import subprocess
+    from oracle import port_oracle
+    if not port_oracle.available():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle" / "port")], check=True)
+    return port_oracle

@@ -361,3 +361,36 @@ def test_shard_invariance_single_gpu(fp, ctx, ref):
     assert min(p[2][0] for p in parts) == mad[0] and sum(p[3] for p in parts) == fl
     np.testing.assert_allclose(sum(p[2][1] * len(p[1]) for p in parts) / len(HJ), mad[1], rtol=1e-14)
     m.close()
+
+
+def test_voxel_occupancy_bit_exact_vs_predicate(fp, ctx, ref, port):
+    """Dense occupancy == the reference's should_subdivide predicate evaluated per extent-1 cell (voxelization.cpp:367-380),
+    checked bit for bit against the brute-force restatement (oracle/port: port_box_overlaps_any) on an awkward grid."""
+    import ctypes as C
+    V, F = fp.procedural.torus(40, 24)
+    m = fp.TriMesh(ctx, V, F)
+    mn = V.min(0) - 0.0137
+    g = fp.VoxelGrid(mn, V.max(0) - mn + 0.021, 1 / 23.7, 0)
+    occ = fp.voxel_occupancy(ctx, m, g)
+    tb = port.facet_boxes(V, F)
+    L = port.lib()
+    exp = np.zeros_like(occ)
+    for z in range(g.dims[2]):
+        for y in range(g.dims[1]):
+            for x in range(g.dims[0]):
+                exp[z, y, x] = L.port_box_overlaps_any(tb.ctypes.data_as(C.c_void_p), C.c_int64(len(tb)), C.c_double(g.origin[0]), C.c_double(g.origin[1]),
+                                                       C.c_double(g.origin[2]), C.c_double(g.spacing), C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(1))
+    assert np.array_equal(occ, exp) and 0 < occ.sum() < occ.size
+    # facets larger than 64 cells take the load-balanced pair path: coarse mesh on a fine grid
+    V2, F2 = fp.procedural.torus(8, 5)
+    m2 = fp.TriMesh(ctx, V2, F2)
+    g2 = fp.VoxelGrid(V2.min(0), V2.max(0) - V2.min(0), 1 / 40, 1)
+    occ2 = fp.voxel_occupancy(ctx, m2, g2)
+    tb2 = port.facet_boxes(V2, F2)
+    idx = np.random.default_rng(0).integers(0, occ2.size, 4000)
+    for i in idx:
+        z, r = divmod(int(i), int(g2.dims[0]) * int(g2.dims[1])); y, x = divmod(r, int(g2.dims[0]))
+        e = L.port_box_overlaps_any(tb2.ctypes.data_as(C.c_void_p), C.c_int64(len(tb2)), C.c_double(g2.origin[0]), C.c_double(g2.origin[1]),
+                                    C.c_double(g2.origin[2]), C.c_double(g2.spacing), C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(1))
+        assert occ2[z, y, x] == e
+    m.close(); m2.close()

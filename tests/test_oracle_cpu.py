@@ -20,14 +20,6 @@ def G():
     return dict(np.load(ROOT / "tests" / "golden" / "golden_v1.npz"))
 
 
-@pytest.fixture(scope="module")
-def port():
-    from oracle import port_oracle
-    if not port_oracle.available():
-        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle" / "port")], check=True)
-    return port_oracle
-
-
 def _canon_equal(canon, G, prefix):
     for k, v in canon.items():
         g = G[f"{prefix}_{k}"]
