@@ -16,6 +16,7 @@
 //   OctreeGrid                                     octree.h:62-270       class OctreeGrid (same public members)
 //   octree_mesh(GEO::Mesh&, Mesh&, OctreeGrid&, Vector3i&) ghm.cpp:460   octree_mesh(ctx, V, nV, F, nF, mo, octree, grid_size, ...)
 //   compute_sign(M, aabb, VoxelGrid<T>&)           voxelization.h:220    compute_sign(mesh, voxels)
+//   compute_octree(M, mo, aabb, ...)               voxelization.cpp:353  compute_octree(mesh, octree, ..., Vpos, hex, inside)
 //   compute(mesh0, mesh1, diag, max, ave)          metro_hausdorff.cpp:358   compute(mesh0, mesh1, diag, max, ave)
 //   hausdorff_ratio_check / compute(..., ratio, thr) metro_hausdorff.cpp:12  compute(mesh0, mesh1, ratio, thr)
 //   hausdorff_dis(mesh0, mesh1, outlierVs, thr)    gf.cpp:3590           hausdorff_dis(mesh0, mesh1, outlierVs, thr)
@@ -24,6 +25,7 @@
 // reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -347,6 +349,38 @@ bool octree_mesh(const DeviceMesh &mi, const double *V, int64_t nV, MeshT &mo, O
 	if (!mo.Hs.size()) { std::cout << "No octants, exit!" << std::endl; return false; }   // ghm.cpp:563
 	build_connectivity(mo);
 	return true;
+}
+
+// compute_octree(M, mo, aabb, filename, min_corner, extent, spacing, padding, graded, paired), voxelization.cpp:353-391:
+// bbox-predicate octree down to extent 1 + z-ray parity per cell + hex export.  The GEO::Mesh the reference fills becomes
+// three arrays: vertex positions (origin + nodePos * spacing, octree.cpp:744-747), hexes in GEOGRAM corner order
+// (Cube::invDelta(diff[lv]), octree.cpp:759-767) and the "inside" cell attribute of the leaves (octree.cpp:838-849).
+inline void compute_octree(const DeviceMesh &M, OctreeGrid &octree, const double min_corner[3], const double extent[3], double spacing,
+                           int padding, bool graded, bool paired, std::vector<double> &Vpos, std::vector<uint32_t> &hex,
+                           std::vector<float> &inside)
+{
+	auto next_pow2 = [](unsigned x) { x -= 1; x |= (x >> 1); x |= (x >> 2); x |= (x >> 4); x |= (x >> 8); x |= (x >> 16); return x + 1; };
+	fpohm_octree_params prm{};
+	for (int d = 0; d < 3; ++d) {
+		prm.origin[d] = min_corner[d] - padding * spacing * 1.0;
+		prm.grid_size[d] = (int32_t)next_pow2((unsigned)(std::ceil(extent[d] / spacing) + 2 * padding));
+		prm.mesh_transform[d] = 0.0;
+	}
+	prm.voxel_size = spacing; prm.stop_extent = 1; prm.graded = graded; prm.paired = paired;
+	octree.build_bbox(M, prm);
+	int64_t nn = 0, nc = 0, nl = 0;
+	fpohm_octree_sizes(octree.handle(), &nn, &nc, &nl, nullptr, nullptr);
+	std::vector<float> cell_inside((size_t)nc);
+	check(fpohm_octree_cell_sign(octree.handle(), M.h, prm.origin, spacing, cell_inside.data()), "fpohm_octree_cell_sign");
+	std::vector<uint32_t> h8(8 * (size_t)nl); std::vector<int32_t> h2c((size_t)nl);
+	Vpos.resize(3 * (size_t)nn);
+	check(fpohm_octree_hexes(octree.handle(), Vpos.data(), h8.data(), h2c.data()), "fpohm_octree_hexes");
+	static const int geo[8] = {0, 1, 3, 2, 4, 5, 7, 6};          // lv -> Cube::invDelta((lv&1, lv>>1&1, lv>>2&1))
+	hex.resize(8 * (size_t)nl); inside.resize((size_t)nl);
+	for (int64_t c = 0; c < nl; ++c) {
+		for (int lv = 0; lv < 8; ++lv) hex[8 * c + lv] = h8[8 * c + geo[lv]];
+		inside[c] = cell_inside[(size_t)h2c[c]];
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 //   product side   : fpohm_shim.hpp over libfpohm.so (CUDA)
 // Built by `make -C oracle/ref shim_parity` (needs the reference headers, so only where /root/reference exists); the
 // binary travels to the GPU box inside oracle/_ref/ and is run by tests/test_gpu_parity.py::test_cpp_shim_parity.
-#include "grid_meshing/octree.h"
+#include "grid_meshing/voxelization.h"
 #include "global_types.h"
 #include "global_functions.h"
 #include "metro_hausdorff.h"
@@ -121,6 +121,40 @@ int main() {
 		for (int c = 0; same && c < ref.numCells(); ++c) if (ref.cellIsLeaf(c)) { auto p = ref.cellCornerPos(c, 0); la.insert({{p[0], p[1], p[2], ref.cellExtent(c)}}); }
 		for (int c = 0; same && c < mine.numCells(); ++c) if (mine.cellIsLeaf(c)) { auto p = mine.cellCornerPos(c, 0); lb.insert({{p[0], p[1], p[2], mine.cellExtent(c)}}); }
 		EXPECT(same && la == lb && mine.is2to1Graded() && mine.isPaired() && ref.is2to1Graded() && ref.isPaired(), "OctreeGrid::subdivide(std::function) same leaf set, graded, paired");
+	}
+	// ---- compute_octree: the one public end-to-end entry of voxelization.h (bbox octree to extent 1 + ray parity + hex export)
+	{
+		Mesh t; torus(40, 24, t);
+		GEO::Mesh M, mo;
+		M.vertices.create_vertices((GEO::index_t)t.V.cols());
+		for (int i = 0; i < t.V.cols(); ++i) M.vertices.point(i) = GEO::vec3(t.V(0, i), t.V(1, i), t.V(2, i));
+		M.facets.create_triangles((GEO::index_t)t.Fs.size());
+		for (size_t f = 0; f < t.Fs.size(); ++f) for (int c = 0; c < 3; ++c) M.facets.set_vertex((GEO::index_t)f, c, t.Fs[f].vs[c]);
+		GEO::vec3 mn, mx; GEO::get_bbox(M, &mn[0], &mx[0]);
+		const GEO::vec3 ext = mx - mn;
+		const double spacing = 1.0 / 48;
+		fpohm_shim::DeviceMesh dm(t);                       // before MeshFacetsAABB reorders M's facets (results do not depend on facet order)
+		GEO::MeshFacetsAABB aabb(M);
+		::compute_octree(M, mo, aabb, "", mn, ext, spacing, 1, true, true);
+		fpohm_shim::OctreeGrid oc;
+		std::vector<double> Vp; std::vector<uint32_t> hex; std::vector<float> inside;
+		const double mnp[3] = {mn[0], mn[1], mn[2]}, exp_[3] = {ext[0], ext[1], ext[2]};
+		fpohm_shim::compute_octree(dm, oc, mnp, exp_, spacing, 1, true, true, Vp, hex, inside);
+		bool same = mo.cells.nb() == inside.size() && mo.vertices.nb() * 3 == Vp.size();
+		// id-free comparison: multiset of (8 corner positions in geogram order, inside flag) per hex
+		std::multiset<std::array<double, 25>> a, b;
+		GEO::Attribute<float> rin(mo.cells.attributes(), "inside");
+		for (GEO::index_t c = 0; same && c < mo.cells.nb(); ++c) {
+			std::array<double, 25> ka, kb;
+			for (int lv = 0; lv < 8; ++lv) for (int d = 0; d < 3; ++d) {
+				ka[3 * lv + d] = mo.vertices.point(mo.cells.vertex(c, lv))[d];
+				kb[3 * lv + d] = Vp[3 * (size_t)hex[8 * (size_t)c + lv] + d];
+			}
+			ka[24] = rin[c]; kb[24] = inside[c];
+			a.insert(ka); b.insert(kb);
+		}
+		int n_in = 0; for (float v : inside) n_in += v > 0.5f;
+		EXPECT(same && a == b && n_in > 0, "compute_octree identical hexes (positions bit-exact, geogram corner order) and inside flags");
 	}
 	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
 	return failures ? 1 : 0;
