@@ -281,6 +281,20 @@ def main():
         step_jac()
     jb.record(stream); torch.cuda.synchronize()
     jac_ms = ja.elapsed_time(jb) / 20
+    # ---- dense z-ray parity voxelization of the same mesh at 512^3 (resident output) -------------------------------
+    mn_, ext_ = V.min(0), V.max(0) - V.min(0)
+    vg = fp.VoxelGrid(mn_, ext_, 1.0 / 512, 0)
+    dvox = torch.empty(vg.num_voxels(), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        fp.voxel_sign_dev(ctx, mesh, vg, dvox.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    va, vb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    va.record(stream)
+    for _ in range(10):
+        fp.voxel_sign_dev(ctx, mesh, vg, dvox.data_ptr(), stream.cuda_stream)
+    vb.record(stream); torch.cuda.synchronize()
+    vox_ms = va.elapsed_time(vb) / 10
+    vox_bytes = vg.num_voxels() + 72 * len(F)
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     if rank == 0:
@@ -313,7 +327,10 @@ def main():
                          "query_tree_build_s_host": tree_build_s,
                          "jacobian_hexes_per_s": nH / (jac_ms * 1e-3), "jacobian_ms": jac_ms,
                          "jacobian_roofline": {"bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                               "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak}}}
+                                               "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak},
+                         "voxel_sign_ms": vox_ms, "voxel_sign_dims": vg.dims.tolist(),
+                         "voxel_sign_roofline": {"bound": "hbm", "achieved": vox_bytes / (vox_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                 "frac": vox_bytes / (vox_ms * 1e-3) / 1e9 / peak}}}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_reference(V, F, P)
