@@ -295,6 +295,33 @@ def main():
     vb.record(stream); torch.cuda.synchronize()
     vox_ms = va.elapsed_time(vb) / 10
     vox_bytes = vg.num_voxels() + 72 * len(F)
+    # ---- z-slab sharded octree build (N > 1): slab refine + per-level halo all-gather over NCCL + replicated numbering ----
+    sharded = None
+    if world > 1:
+        from fpohm_b200 import sharding
+        comm = sharding.TorchComm()
+        sharded = {}
+        for e in (STOP_E, STOP_E - 2):
+            prm_e = fp.OctreeParams(prm.grid_size, prm.origin, prm.mesh_transform, prm.voxel_size, 1 << e, True, True)
+            single, multi = [], []
+            for i in range(3 + 3):
+                barrier(); t0 = time.perf_counter()
+                o1 = fp.Octree.build(ctx, mesh, prm_e)
+                barrier(); single.append((time.perf_counter() - t0) * 1e3)
+                st = {}
+                barrier(); t0 = time.perf_counter()
+                oN = sharding.build_octree_sharded(fp, ctx, mesh, prm_e, comm, device=dev, stats=st)
+                barrier(); multi.append((time.perf_counter() - t0) * 1e3)
+                same = o1.sizes() == oN.sizes()
+                if i == 0:
+                    a, b = o1.export(), oN.export()
+                    same = same and all(np.array_equal(a[k], b[k]) for k in ("node_pos", "node_neigh", "first_child", "corner", "neigh"))
+                assert same, "sharded octree differs from the single-GPU octree"
+                cells = o1.sizes()["cells"]
+                o1.close(); oN.close()
+            sharded[f"e{e}"] = {"cells": int(cells), "single_gpu_ms": float(np.median(single[3:])), "sharded_ms": float(np.median(multi[3:])),
+                                "replicated_levels": st["replicated_levels"], "slab_bounds": st["slab_bounds"],
+                                "halo_codes_sent_rank0": int(sum(st["halo_codes"].values())), "bit_identical": True}
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     if rank == 0:
@@ -331,6 +358,8 @@ def main():
                          "voxel_sign_ms": vox_ms, "voxel_sign_dims": vg.dims.tolist(),
                          "voxel_sign_roofline": {"bound": "hbm", "achieved": vox_bytes / (vox_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                  "frac": vox_bytes / (vox_ms * 1e-3) / 1e9 / peak}}}
+        if sharded is not None:
+            line["also"]["octree_build_zslab_sharded"] = sharded
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_reference(V, F, P)

@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 __all__ = [
-    "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree",
+    "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
@@ -278,6 +278,63 @@ class Octree:
             self.close()
         except Exception:
             pass
+
+class OctreeShard:
+    """One rank of the z-slab sharded octree build (include/fpohm.h "z-slab sharded octree build").  The class only
+    wraps the C-ABI steps; the collective between them is the caller's (sharding.build_octree_sharded)."""
+
+    def __init__(self, ctx: Context, mesh: TriMesh, params: OctreeParams, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        _chk(lib().fpohm_octree_shard_create(ctx.h, mesh.h, C.byref(params.c), C.c_int32(rank), C.c_int32(world), C.byref(self.h)))
+
+    def refine(self) -> int:
+        lm = C.c_int32()
+        _chk(lib().fpohm_octree_shard_refine(self.h, C.byref(lm)))
+        return lm.value
+
+    def info(self):
+        rl = C.c_int32(); b = (C.c_int32 * (self.world + 1))(); t = C.c_int64()
+        _chk(lib().fpohm_octree_shard_info(self.h, C.byref(rl), b, C.byref(t)))
+        return dict(replicated_levels=rl.value, slab_bounds=list(b), owned_true_cells=t.value)
+
+    def level_outgoing(self, global_max_level: int, level: int) -> int:
+        n = C.c_int64()
+        _chk(lib().fpohm_octree_shard_level_outgoing(self.h, C.c_int32(global_max_level), C.c_int32(level), C.byref(n)))
+        return n.value
+
+    def outgoing_copy(self, dst_ptr: int):
+        _chk(lib().fpohm_octree_shard_outgoing_copy(self.h, C.c_void_p(dst_ptr)))
+
+    def level_close(self, level: int, gathered_ptr: int, n: int) -> int:
+        m = C.c_int64()
+        _chk(lib().fpohm_octree_shard_level_close(self.h, C.c_int32(level), C.c_void_p(gathered_ptr), C.c_int64(n), C.byref(m)))
+        return m.value
+
+    def level_result(self, level: int, dst_ptr: int = 0) -> int:
+        n = C.c_int64()
+        _chk(lib().fpohm_octree_shard_level_result(self.h, C.c_int32(level), C.c_void_p(dst_ptr), C.byref(n)))
+        return n.value
+
+    def finish(self, ptrs, counts) -> "Octree":
+        L = len(ptrs)
+        pa = (C.c_void_p * max(L, 1))(*[C.c_void_p(int(x)) for x in ptrs]) if L else (C.c_void_p * 1)()
+        ca = (C.c_int64 * max(L, 1))(*[int(c) for c in counts]) if L else (C.c_int64 * 1)()
+        h = C.c_void_p()
+        _chk(lib().fpohm_octree_shard_finish(self.h, pa, ca, C.byref(h)))
+        return Octree(self.ctx, h)
+
+    def close(self):
+        if self.h:
+            lib().fpohm_octree_shard_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 
 # scaled_jacobian, gf.cpp:2309-2358 — returns (V_Js, H_Js, (min, ave, deviation), flipped) like Mesh_Quality

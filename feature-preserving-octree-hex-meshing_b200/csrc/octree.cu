@@ -471,54 +471,79 @@ LevelTable make_table(const fpohm_octree *o) {
 	return t;
 }
 
-// phase 2 + 3 given the predicate-true sets P[l] (sorted device arrays) — shared by build / from_marks / refine
-void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::vector<int64_t> &nP) {
+// one level of phase 2: I_l = family_close(sort_unique(cand)); `cand` may hold INVALID entries
+int64_t close_level(fpohm_octree *o, int l, DevBuf<uint64_t> &cand, int64_t n_cand, DevBuf<uint64_t> &uq) {
 	fpohm_ctx *ctx = o->ctx;
 	cudaStream_t s = ctx->stream;
 	Sorter sorter{ctx, s};
 	const int blk = 256;
-	const bool graded = o->prm.graded != 0, paired = o->prm.paired != 0;
+	const bool paired = o->prm.paired != 0;
+	const int lbits = key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << l) - 1);
+	int64_t m = sorter.sort_unique(cand, n_cand, lbits, uq);
+	if (paired && m > 0) {
+		if (l == 0) {
+			// root rule, octree.cpp:577-581: one root split => all roots split
+			uq.alloc(o->n_roots, s);
+			roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(uq.p, o->roots[0], o->roots[1], o->roots[2]);
+			FPOHM_LAUNCH_CHECK(ctx);
+			DevBuf<uint64_t> sorted_roots;
+			m = sorter.sort_unique(uq, o->n_roots, lbits, sorted_roots);
+			uq = std::move(sorted_roots);
+		} else {
+			// sibling rule, octree.cpp:583-587 (+ makeCellPaired :632-643): whole families
+			DevBuf<uint64_t> fam(m, s), famu;
+			family_kernel<<<grid_for(ctx, m, blk), blk, 0, s>>>(uq.p, m, fam.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			const int64_t nf = sorter.sort_unique(fam, m, lbits, famu);
+			uq.alloc(8 * nf, s);
+			children_kernel<<<grid_for(ctx, 8 * nf, blk), blk, 0, s>>>(famu.p, nf, uq.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			m = 8 * nf;
+		}
+	}
+	return m;
+}
+
+// candidates of level l: P_l ∪ forced(I_{l+1})
+int64_t level_candidates(fpohm_octree *o, int l, const uint64_t *Pl, int64_t nPl, const uint64_t *Iup, int64_t nIup, DevBuf<uint64_t> &cand) {
+	fpohm_ctx *ctx = o->ctx;
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	const int64_t n_forced = 7 * nIup;
+	const int64_t n_cand = nPl + n_forced;
+	cand.alloc(n_cand, s);
+	if (nPl) FPOHM_CUDA(cudaMemcpyAsync(cand.p, Pl, 8 * (size_t)nPl, cudaMemcpyDeviceToDevice, s));
+	if (n_forced) {
+		forced_kernel<<<grid_for(ctx, nIup, blk), blk, 0, s>>>(Iup, nIup, o->prm.graded ? 1 : 0,
+			o->roots[0] << l, o->roots[1] << l, o->roots[2] << l, cand.p + nPl);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
+	return n_cand;
+}
+
+void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vector<int64_t> &nI);
+
+// phase 2 + 3 given the predicate-true sets P[l] (device arrays) — shared by build / from_marks / refine
+void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::vector<int64_t> &nP) {
 	int Lmax = -1;
 	for (int l = 0; l < (int)P.size(); ++l) if (nP[l] > 0) Lmax = l;
 	std::vector<DevBuf<uint64_t>> I((size_t)std::max(Lmax + 1, 0));
 	std::vector<int64_t> nI((size_t)std::max(Lmax + 1, 0), 0);
 	for (int l = Lmax; l >= 0; --l) {
-		const int64_t n_forced = (l < Lmax) ? 7 * nI[l + 1] : 0;
-		const int64_t n_cand = nP[l] + n_forced;
-		DevBuf<uint64_t> cand(n_cand, s);
-		if (nP[l]) FPOHM_CUDA(cudaMemcpyAsync(cand.p, P[l].p, 8 * (size_t)nP[l], cudaMemcpyDeviceToDevice, s));
-		if (n_forced) {
-			forced_kernel<<<grid_for(ctx, nI[l + 1], blk), blk, 0, s>>>(I[l + 1].p, nI[l + 1], graded ? 1 : 0,
-				o->roots[0] << l, o->roots[1] << l, o->roots[2] << l, cand.p + nP[l]);
-			FPOHM_LAUNCH_CHECK(ctx);
-		}
-		DevBuf<uint64_t> uq;
-		const int lbits = key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << l) - 1);
-		int64_t m = sorter.sort_unique(cand, n_cand, lbits, uq);
-		if (paired && m > 0) {
-			if (l == 0) {
-				// root rule, octree.cpp:577-581: one root split => all roots split
-				uq.alloc(o->n_roots, s);
-				roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(uq.p, o->roots[0], o->roots[1], o->roots[2]);
-				FPOHM_LAUNCH_CHECK(ctx);
-				DevBuf<uint64_t> sorted_roots;
-				m = sorter.sort_unique(uq, o->n_roots, lbits, sorted_roots);
-				uq = std::move(sorted_roots);
-			} else {
-				// sibling rule, octree.cpp:583-587 (+ makeCellPaired :632-643): whole families
-				DevBuf<uint64_t> fam(m, s), famu;
-				family_kernel<<<grid_for(ctx, m, blk), blk, 0, s>>>(uq.p, m, fam.p);
-				FPOHM_LAUNCH_CHECK(ctx);
-				const int64_t nf = sorter.sort_unique(fam, m, lbits, famu);
-				uq.alloc(8 * nf, s);
-				children_kernel<<<grid_for(ctx, 8 * nf, blk), blk, 0, s>>>(famu.p, nf, uq.p);
-				FPOHM_LAUNCH_CHECK(ctx);
-				m = 8 * nf;
-			}
-		}
-		I[l] = std::move(uq);
-		nI[l] = m;
+		DevBuf<uint64_t> cand;
+		const int64_t n_cand = level_candidates(o, l, P[l].p, nP[l], l < Lmax ? I[l + 1].p : nullptr, l < Lmax ? nI[l + 1] : 0, cand);
+		nI[l] = close_level(o, l, cand, n_cand, I[l]);
 	}
+	number_levels(o, I, nI);
+}
+
+// phase 3 given the closed internal sets I[l] (sorted device arrays)
+void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vector<int64_t> &nI) {
+	fpohm_ctx *ctx = o->ctx;
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	int Lmax = -1;
+	for (int l = 0; l < (int)I.size(); ++l) if (nI[l] > 0) Lmax = l;
 	// concatenate levels
 	o->n_levels = Lmax + 1;
 	int64_t tot = 0;
@@ -630,6 +655,34 @@ __global__ void old_leaf_codes_kernel(const uint64_t *__restrict__ code, const i
 		out[i] = first_child[id0 + i] < 0 ? code[id0 + i] : INVALID;
 }
 
+// P = {c in T : should_subdivide(c)} for cells of level l, compacted in input order
+int64_t test_cells(fpohm_octree *o, const fpohm_mesh *mesh, int l, const uint64_t *T, int64_t nT, DevBuf<uint64_t> &sel) {
+	fpohm_ctx *ctx = o->ctx;
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
+	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
+	DevBuf<uint8_t> flag(nT, s);
+	if (nT <= 32768)
+		predicate_warp_kernel<<<(int)std::min<int64_t>((nT + 7) / 8, (int64_t)ctx->sm_count * 8), blk, 0, s>>>(T, nT, o->depth - l,
+			bx, by, bz, o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+	else
+		predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
+			mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	sel.alloc(nT, s);
+	DevBuf<int64_t> cnt(1, s);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, T, flag.p, sel.p, cnt.p, nT, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, T, flag.p, sel.p, cnt.p, nT, s));
+	ctx->launches += 2;
+	int64_t np = 0;
+	cnt.download(&np, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	return np;
+}
+
 // phase 1 with the bbox predicate.  BFS of octree.cpp:648-690: the queue starts with every current leaf
 // (roots on a fresh tree) and a cell's children are queued iff its predicate is true, so
 //   T_l = old_leaves(l) ∪ children(P_{l-1}),  P_l = {c in T_l : pred(c)}.
@@ -642,8 +695,6 @@ void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bo
 	const int blk = 256;
 	Sorter sorter{ctx, s};
 	mesh_ensure_pred(ctx, const_cast<fpohm_mesh *>(mesh), s);
-	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
-	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
 	DevBuf<uint64_t> kids;   // children(P_{l-1})
 	int64_t n_kids = 0;
 	for (int l = 0; l <= o->depth; ++l) {
@@ -677,23 +728,7 @@ void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bo
 			DevBuf<uint64_t> T(nT, s);
 			if (n_old_leaves) FPOHM_CUDA(cudaMemcpyAsync(T.p, old_leaves.p, 8 * (size_t)n_old_leaves, cudaMemcpyDeviceToDevice, s));
 			if (n_kids) FPOHM_CUDA(cudaMemcpyAsync(T.p + n_old_leaves, kids.p, 8 * (size_t)n_kids, cudaMemcpyDeviceToDevice, s));
-			DevBuf<uint8_t> flag(nT, s);
-			if (nT <= 32768)
-				predicate_warp_kernel<<<(int)std::min<int64_t>((nT + 7) / 8, (int64_t)ctx->sm_count * 8), blk, 0, s>>>(T.p, nT, o->depth - l,
-					bx, by, bz, o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
-			else
-				predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T.p, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
-					mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
-			FPOHM_LAUNCH_CHECK(ctx);
-			sel.alloc(nT, s);
-			DevBuf<int64_t> cnt(1, s);
-			size_t tb = 0;
-			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, T.p, flag.p, sel.p, cnt.p, nT, s));
-			DevBuf<uint8_t> tmp((int64_t)tb, s);
-			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, T.p, flag.p, sel.p, cnt.p, nT, s));
-			ctx->launches += 2;
-			cnt.download(&np, 1);
-			FPOHM_CUDA(cudaStreamSynchronize(s));
+			np = test_cells(o, mesh, l, T.p, nT, sel);
 		}
 		P.emplace_back(np + n_old_int, s);
 		nP.push_back(np + n_old_int);
@@ -709,6 +744,95 @@ void predicate_sets(fpohm_octree *o, const fpohm_mesh *mesh, int stop_extent, bo
 		FPOHM_CUDA(cudaStreamSynchronize(s)); // sel / T die here
 		if (fresh && n_kids == 0) break;
 		if (!fresh && n_kids == 0 && l >= o->n_levels) break;
+	}
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// z-slab sharded build.
+//
+// Rank r of W owns the cells whose z range lies in slab r of the level-`ls` grid; slabs are cut on level-ls cell
+// boundaries, so for l > ls a whole sibling family has one owner and pairing never crosses ranks.  Levels <= ls are
+// REPLICATED: every rank computes them in full (at most (8 W)^3 cells).  The only constraints that cross a slab face
+// are the grading candidates parents(N18(c)) of boundary cells — the halo.  Per level of phase 2 each rank emits the
+// candidates it does not own (`outgoing`), the host all-gathers them (NCCL; this library does not link it), and each
+// rank keeps what it owns from everybody's emissions.  The fix-point is a set, so the union over ranks of the closed
+// sets is bit-identical to the single-GPU result; phase 3 then numbers the gathered sets canonically.
+struct SlabBounds { int32_t W; int32_t b[65]; };   // slab r = level-ls z layers [b[r], b[r+1])
+
+__global__ void owner_flag_kernel(const uint64_t *__restrict__ code, int64_t n, int dl /* l - ls */, SlabBounds sb, int rank,
+                                  uint8_t *__restrict__ own)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint64_t c = code[i];
+		uint8_t f = 0;
+		if (c != INVALID) {
+			const int zs = (int)(compact1by2(c >> 2) >> dl);
+			f = (zs >= sb.b[rank] && zs < sb.b[rank + 1]) ? 1 : 0;
+		}
+		own[i] = f;
+	}
+}
+__global__ void invalid_flag_kernel(const uint64_t *__restrict__ code, int64_t n, const uint8_t *__restrict__ own, uint8_t *__restrict__ foreign) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+		foreign[i] = (code[i] != INVALID && !own[i]) ? 1 : 0;
+}
+
+int64_t select_flagged(fpohm_ctx *ctx, cudaStream_t s, const uint64_t *in, const uint8_t *flag, int64_t n, DevBuf<uint64_t> &out) {
+	out.alloc(n, s);
+	if (n == 0) return 0;
+	DevBuf<int64_t> cnt(1, s);
+	size_t tb = 0;
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, in, flag, out.p, cnt.p, n, s));
+	DevBuf<uint8_t> tmp((int64_t)tb, s);
+	FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, in, flag, out.p, cnt.p, n, s));
+	ctx->launches += 2;
+	int64_t m = 0;
+	cnt.download(&m, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	return m;
+}
+
+} // namespace
+
+struct fpohm_octree_shard {
+	fpohm_octree *o = nullptr;          // geometry + (after finish) nothing else: the numbered tree is a fresh object
+	const fpohm_mesh *mesh = nullptr;
+	int rank = 0, world = 1;
+	int ls = 0;                          // last replicated level
+	SlabBounds sb{};
+	std::vector<DevBuf<uint64_t>> P, I;  // per level: P = predicate-true (owned, or all for l <= ls); I = closed (same)
+	std::vector<int64_t> nP, nI;
+	std::vector<uint8_t> closed;
+	int gmax = -1;                       // global deepest level with predicate-true cells (set by the first level_outgoing)
+	// per-level scratch between level_outgoing and level_close
+	int pending_level = -1;
+	DevBuf<uint64_t> own_cand, out_cand;
+	int64_t n_own = 0, n_out = 0;
+	~fpohm_octree_shard() { delete o; }
+};
+
+namespace {
+
+void shard_split(fpohm_octree_shard *sh, int l, const uint64_t *cand, int64_t n, DevBuf<uint64_t> &own, int64_t &n_own,
+                 DevBuf<uint64_t> *foreign, int64_t *n_foreign)
+{
+	fpohm_ctx *ctx = sh->o->ctx;
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	DevBuf<uint8_t> f(n, s);
+	if (n) {
+		owner_flag_kernel<<<grid_for(ctx, n, blk), blk, 0, s>>>(cand, n, l - sh->ls, sh->sb, sh->rank, f.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+	}
+	n_own = select_flagged(ctx, s, cand, f.p, n, own);
+	if (foreign) {
+		DevBuf<uint8_t> g(n, s);
+		if (n) {
+			invalid_flag_kernel<<<grid_for(ctx, n, blk), blk, 0, s>>>(cand, n, f.p, g.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		*n_foreign = select_flagged(ctx, s, cand, g.p, n, *foreign);
 	}
 }
 
@@ -880,6 +1004,268 @@ int fpohm_octree_refine(fpohm_octree *o, const fpohm_mesh *mesh, const int32_t *
 	KernelTimer t(ctx, s);
 	close_and_number(o, P, nP);
 	t.stop();
+	FPOHM_API_END
+}
+
+
+// ---- z-slab sharded build ---------------------------------------------------------------------------------------------
+int fpohm_octree_shard_create(fpohm_ctx *ctx, const fpohm_mesh *mesh, const fpohm_octree_params *p, int32_t rank, int32_t world,
+                              fpohm_octree_shard **out)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mesh && p && out, FPOHM_EINVAL, "fpohm_octree_shard_create: null argument");
+	FPOHM_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, FPOHM_EINVAL, "fpohm_octree_shard_create: rank %d / world %d", rank, world);
+	FPOHM_REQUIRE(p->voxel_size > 0, FPOHM_EINVAL, "fpohm_octree_shard_create: voxel_size must be positive");
+	DeviceGuard g(ctx->device);
+	fpohm_octree_shard *sh = new fpohm_octree_shard;
+	try {
+		sh->o = new fpohm_octree;
+		sh->o->ctx = ctx; sh->o->prm = *p;
+		setup_geometry(sh->o, p->grid_size);
+		sh->mesh = mesh; sh->rank = rank; sh->world = world;
+		// last replicated level.  Balance wants >= 8 z layers per rank at level ls (the cut is weighted by layer), but the
+		// two deepest predicate levels hold ~94 % of the work and must stay sharded; at least one layer per rank if possible.
+		const int depth = sh->o->depth;
+		auto first_level_with = [&](int64_t layers) { int l = 0; while (((int64_t)sh->o->roots[2] << l) < layers && l < depth) ++l; return l; };
+		int ltest = -1;                                  // deepest level the predicate is evaluated on (ghm.cpp:503, octree.cpp:670)
+		for (int l = 0; l <= depth; ++l) { const int e = 1 << (depth - l); if (e > p->stop_extent && e > 1) ltest = l; }
+		int ls = std::min(std::max(ltest - 2, first_level_with(world)), first_level_with(8ll * world));
+		ls = std::max(0, std::min(ls, depth - 1));
+		sh->ls = ls;
+	} catch (...) { delete sh; throw; }
+	*out = sh;
+	FPOHM_API_END
+}
+
+void fpohm_octree_shard_free(fpohm_octree_shard *sh) {
+	if (!sh) return;
+	DeviceGuard g(sh->o->ctx->device);
+	cudaStreamSynchronize(sh->o->ctx->stream);
+	delete sh;
+}
+
+// phase 1: replicated down to level ls, then only the owned slab.  No communication.
+int fpohm_octree_shard_refine(fpohm_octree_shard *sh, int32_t *local_max_level) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && local_max_level, FPOHM_EINVAL, "fpohm_octree_shard_refine: null argument");
+	fpohm_octree *o = sh->o;
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const int blk = 256;
+	mesh_ensure_pred(ctx, const_cast<fpohm_mesh *>(sh->mesh), s);
+	sh->P.clear(); sh->nP.clear();
+	DevBuf<uint64_t> T(o->n_roots, s);
+	int64_t nT = o->n_roots;
+	roots_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(T.p, o->roots[0], o->roots[1], o->roots[2]);
+	FPOHM_LAUNCH_CHECK(ctx);
+	const int nz_s = o->roots[2] << sh->ls;
+	// default bounds: equal layer counts (replaced below by the weighted cut when level ls has predicate-true cells)
+	sh->sb.W = sh->world;
+	for (int r = 0; r <= sh->world; ++r) sh->sb.b[r] = (int32_t)((int64_t)nz_s * r / sh->world);
+	int lmax = -1;
+	for (int l = 0; l <= o->depth; ++l) {
+		const int extent = 1 << (o->depth - l);
+		const bool testable = extent > o->prm.stop_extent && extent > 1;
+		DevBuf<uint64_t> sel;
+		int64_t np = 0;
+		if (testable && nT > 0) np = test_cells(o, sh->mesh, l, T.p, nT, sel);
+		sh->P.emplace_back(np, s);
+		sh->nP.push_back(np);
+		if (np) { FPOHM_CUDA(cudaMemcpyAsync(sh->P.back().p, sel.p, 8 * (size_t)np, cudaMemcpyDeviceToDevice, s)); lmax = l; }
+		if (l == sh->ls && np > 0) {
+			// weighted slab cut: balance the number of predicate-true level-ls cells per rank (identical on every rank:
+			// level ls is replicated).  The surface is where all the deeper work is.
+			std::vector<uint64_t> h((size_t)np);
+			sel.download(h.data(), np);
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+			std::vector<int64_t> hist((size_t)nz_s + 1, 0);
+			for (uint64_t c : h) hist[(size_t)compact1by2(c >> 2) + 1]++;
+			for (int z = 0; z < nz_s; ++z) hist[(size_t)z + 1] += hist[(size_t)z];
+			for (int r = 1; r < sh->world; ++r) {
+				const int64_t want = np * r / sh->world;
+				int z = (int)(std::lower_bound(hist.begin(), hist.end(), want) - hist.begin());
+				if (z > 0 && want - hist[(size_t)z - 1] < hist[(size_t)std::min(z, nz_s)] - want) --z;   // nearest layer boundary
+				z = std::max(z, sh->sb.b[r - 1]);
+				sh->sb.b[r] = std::min(z, nz_s);
+			}
+			sh->sb.b[0] = 0; sh->sb.b[sh->world] = nz_s;
+		}
+		int64_t n_kids = 8 * np;
+		FPOHM_REQUIRE(n_kids < (1ll << 31), FPOHM_ERANGE, "octree shard: level %d has %lld cells to test", l + 1, (long long)n_kids);
+		if (n_kids == 0) { nT = 0; if (l >= sh->ls) break; else continue; }
+		DevBuf<uint64_t> kids(n_kids, s);
+		children_kernel<<<grid_for(ctx, n_kids, blk), blk, 0, s>>>(sel.p, np, kids.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		if (l == sh->ls) {
+			// entering the sharded levels: keep the children this rank owns
+			int64_t n_own = 0;
+			shard_split(sh, l + 1, kids.p, n_kids, T, n_own, nullptr, nullptr);
+			nT = n_own;
+		} else {
+			T = std::move(kids);
+			nT = n_kids;
+		}
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
+	while ((int)sh->P.size() <= o->depth) { sh->P.emplace_back((int64_t)0, s); sh->nP.push_back(0); }
+	*local_max_level = lmax;
+	sh->gmax = -1;
+	FPOHM_API_END
+}
+
+int fpohm_octree_shard_info(const fpohm_octree_shard *sh, int32_t *replicated_levels, int32_t *slab_bounds /*world+1, level-ls z layers*/,
+                            int64_t *owned_true_cells)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh, FPOHM_EINVAL, "fpohm_octree_shard_info: null shard");
+	if (replicated_levels) *replicated_levels = sh->ls + 1;
+	if (slab_bounds) for (int r = 0; r <= sh->world; ++r) slab_bounds[r] = sh->sb.b[r];
+	if (owned_true_cells) {
+		int64_t t = 0;
+		for (int l = sh->ls + 1; l < (int)sh->nP.size(); ++l) t += sh->nP[l];
+		*owned_true_cells = t;
+	}
+	FPOHM_API_END
+}
+
+// phase 2, level l (call for l = global_max_level ... 0 in order): candidates of level l that other ranks must see.
+//   l >  ls : the forced cells this rank does not own (halo)            -> all-gather -> level_close
+//   l == ls : every forced cell of the owned level ls+1 set              -> all-gather -> level_close (replicated close)
+//   l <  ls : nothing (level l+1 is replicated, every rank derives the same candidates)
+int fpohm_octree_shard_level_outgoing(fpohm_octree_shard *sh, int32_t global_max_level, int32_t level, int64_t *n_out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && n_out, FPOHM_EINVAL, "fpohm_octree_shard_level_outgoing: null argument");
+	fpohm_octree *o = sh->o;
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	FPOHM_REQUIRE(level >= 0 && level <= global_max_level && global_max_level <= o->depth, FPOHM_EINVAL,
+	              "fpohm_octree_shard_level_outgoing: level %d / max %d", level, global_max_level);
+	if (sh->gmax < 0) {
+		sh->gmax = global_max_level;
+		sh->I.clear(); sh->nI.clear();
+		for (int l = 0; l <= global_max_level; ++l) { sh->I.emplace_back((int64_t)0, s); sh->nI.push_back(0); }
+		sh->closed.assign((size_t)global_max_level + 1, 0);
+	}
+	FPOHM_REQUIRE(global_max_level == sh->gmax, FPOHM_ESTATE, "fpohm_octree_shard_level_outgoing: max level changed");
+	FPOHM_REQUIRE(level == sh->gmax || sh->closed[(size_t)level + 1], FPOHM_ESTATE,
+	              "fpohm_octree_shard_level_outgoing: level %d before level %d was closed", level, level + 1);
+	const bool has_up = level < sh->gmax;
+	DevBuf<uint64_t> cand;
+	const int64_t n_cand = level_candidates(o, level, sh->P[(size_t)level].p, sh->nP[(size_t)level],
+	                                        has_up ? sh->I[(size_t)level + 1].p : nullptr, has_up ? sh->nI[(size_t)level + 1] : 0, cand);
+	Sorter sorter{ctx, s};
+	const int lbits = key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << level) - 1);
+	DevBuf<uint64_t> uq;
+	const int64_t m = sorter.sort_unique(cand, n_cand, lbits, uq);
+	if (level > sh->ls) {
+		shard_split(sh, level, uq.p, m, sh->own_cand, sh->n_own, &sh->out_cand, &sh->n_out);
+	} else if (level == sh->ls) {
+		// P_ls is replicated, the forced part is not: ship everything (duplicates of P_ls across ranks are harmless)
+		sh->own_cand.alloc(0, s); sh->n_own = 0;
+		sh->out_cand = std::move(uq); sh->n_out = m;
+	} else {
+		sh->own_cand = std::move(uq); sh->n_own = m;
+		sh->out_cand.alloc(0, s); sh->n_out = 0;
+	}
+	sh->pending_level = level;
+	*n_out = sh->n_out;
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_octree_shard_outgoing_copy(fpohm_octree_shard *sh, uint64_t *dst_dev) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && (dst_dev || sh->n_out == 0), FPOHM_EINVAL, "fpohm_octree_shard_outgoing_copy: null argument");
+	FPOHM_REQUIRE(sh->pending_level >= 0, FPOHM_ESTATE, "fpohm_octree_shard_outgoing_copy: no pending level");
+	DeviceGuard g(sh->o->ctx->device);
+	if (sh->n_out) FPOHM_CUDA(cudaMemcpyAsync(dst_dev, sh->out_cand.p, 8 * (size_t)sh->n_out, cudaMemcpyDeviceToDevice, sh->o->ctx->stream));
+	FPOHM_CUDA(cudaStreamSynchronize(sh->o->ctx->stream));
+	FPOHM_API_END
+}
+
+// close level l with everybody's outgoing candidates (the concatenation of all ranks' buffers, this rank's included)
+int fpohm_octree_shard_level_close(fpohm_octree_shard *sh, int32_t level, const uint64_t *gathered_dev, int64_t n_gathered, int64_t *n_closed) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && (gathered_dev || n_gathered == 0), FPOHM_EINVAL, "fpohm_octree_shard_level_close: null argument");
+	FPOHM_REQUIRE(level == sh->pending_level, FPOHM_ESTATE, "fpohm_octree_shard_level_close: level %d is not the pending level %d", level, sh->pending_level);
+	fpohm_octree *o = sh->o;
+	fpohm_ctx *ctx = o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	DevBuf<uint64_t> mine;
+	int64_t n_mine = 0;
+	if (level > sh->ls) {
+		if (n_gathered) shard_split(sh, level, gathered_dev, n_gathered, mine, n_mine, nullptr, nullptr);
+	} else if (level == sh->ls) {
+		mine.alloc(n_gathered, s);
+		if (n_gathered) FPOHM_CUDA(cudaMemcpyAsync(mine.p, gathered_dev, 8 * (size_t)n_gathered, cudaMemcpyDeviceToDevice, s));
+		n_mine = n_gathered;
+	}
+	DevBuf<uint64_t> cand(sh->n_own + n_mine, s);
+	if (sh->n_own) FPOHM_CUDA(cudaMemcpyAsync(cand.p, sh->own_cand.p, 8 * (size_t)sh->n_own, cudaMemcpyDeviceToDevice, s));
+	if (n_mine) FPOHM_CUDA(cudaMemcpyAsync(cand.p + sh->n_own, mine.p, 8 * (size_t)n_mine, cudaMemcpyDeviceToDevice, s));
+	sh->nI[(size_t)level] = close_level(o, level, cand, sh->n_own + n_mine, sh->I[(size_t)level]);
+	sh->closed[(size_t)level] = 1;
+	sh->pending_level = -1;
+	sh->own_cand.release(); sh->out_cand.release();
+	sh->n_own = sh->n_out = 0;
+	if (n_closed) *n_closed = sh->nI[(size_t)level];
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+// owned closed cells of a sharded level (l > ls), for the final gather; replicated levels report 0 (every rank has them)
+int fpohm_octree_shard_level_result(const fpohm_octree_shard *sh, int32_t level, uint64_t *dst_dev, int64_t *n) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && n, FPOHM_EINVAL, "fpohm_octree_shard_level_result: null argument");
+	FPOHM_REQUIRE(level >= 0 && level <= sh->gmax && sh->closed[(size_t)level], FPOHM_ESTATE, "fpohm_octree_shard_level_result: level %d not closed", level);
+	const int64_t m = level > sh->ls ? sh->nI[(size_t)level] : 0;
+	*n = m;
+	if (dst_dev && m) {
+		DeviceGuard g(sh->o->ctx->device);
+		FPOHM_CUDA(cudaMemcpyAsync(dst_dev, sh->I[(size_t)level].p, 8 * (size_t)m, cudaMemcpyDeviceToDevice, sh->o->ctx->stream));
+		FPOHM_CUDA(cudaStreamSynchronize(sh->o->ctx->stream));
+	}
+	FPOHM_API_END
+}
+
+// phase 3 on this rank: `gathered[l]` = concatenation over ranks of level_result(l) for every sharded level
+// (entries for replicated levels are ignored and may be NULL).  Returns the complete, canonically numbered octree.
+int fpohm_octree_shard_finish(fpohm_octree_shard *sh, const uint64_t *const *gathered_dev, const int64_t *counts, fpohm_octree **out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(sh && out, FPOHM_EINVAL, "fpohm_octree_shard_finish: null argument");
+	fpohm_ctx *ctx = sh->o->ctx;
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	for (int l = 0; l <= sh->gmax; ++l)
+		FPOHM_REQUIRE(sh->closed[(size_t)l], FPOHM_ESTATE, "fpohm_octree_shard_finish: level %d not closed", l);
+	fpohm_octree *o = new fpohm_octree;
+	try {
+		o->ctx = ctx; o->prm = sh->o->prm;
+		setup_geometry(o, o->prm.grid_size);
+		std::vector<DevBuf<uint64_t>> I((size_t)sh->gmax + 1);
+		std::vector<int64_t> nI((size_t)sh->gmax + 1, 0);
+		Sorter sorter{ctx, s};
+		for (int l = 0; l <= sh->gmax; ++l) {
+			if (l <= sh->ls) {
+				nI[(size_t)l] = sh->nI[(size_t)l];
+				I[(size_t)l].alloc(nI[(size_t)l], s);
+				if (nI[(size_t)l]) FPOHM_CUDA(cudaMemcpyAsync(I[(size_t)l].p, sh->I[(size_t)l].p, 8 * (size_t)nI[(size_t)l], cudaMemcpyDeviceToDevice, s));
+			} else {
+				FPOHM_REQUIRE(gathered_dev && counts && (counts[l] == 0 || gathered_dev[l]), FPOHM_EINVAL, "fpohm_octree_shard_finish: level %d missing", l);
+				DevBuf<uint64_t> in(counts[l], s);
+				if (counts[l]) FPOHM_CUDA(cudaMemcpyAsync(in.p, gathered_dev[l], 8 * (size_t)counts[l], cudaMemcpyDeviceToDevice, s));
+				const int lbits = key_bits(((int64_t)std::max(o->roots[0], std::max(o->roots[1], o->roots[2])) << l) - 1);
+				nI[(size_t)l] = sorter.sort_unique(in, counts[l], lbits, I[(size_t)l]);   // slab order -> Morton order
+			}
+		}
+		KernelTimer t(ctx, s);
+		number_levels(o, I, nI);
+		t.stop();
+	} catch (...) { delete o; throw; }
+	*out = o;
 	FPOHM_API_END
 }
 

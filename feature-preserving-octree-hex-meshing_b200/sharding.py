@@ -5,6 +5,12 @@ queries / hexes / samples are split into contiguous ranges, the triangle mesh an
 The only collectives are the final gather of per-range results and the 5-scalar statistics reduction; both are
 fixed-order so an N-rank result is bit-identical to the 1-rank result for integer outputs and for min/max, and
 equal up to the documented summation order for fp sums.
+
+The octree closure is the one path with a real exchange step: `build_octree_sharded` cuts the grid into z slabs,
+each rank refines and balances its slab on its GPU, and per level the 2:1 candidates that cross a slab face (the
+halo) are all-gathered as Morton codes.  The communicator is a two-method object (`allreduce_max`, `allgather_var`):
+`TorchComm` is torch.distributed (NCCL on GPUs, gloo on CPU tensors), `ThreadComm` runs W ranks as threads of one
+process for single-GPU tests of the same code path.
 """
 from __future__ import annotations
 
@@ -46,3 +52,115 @@ def reduce_stats(st: dict) -> dict:
     sm = torch.tensor([st["sum"], st["sumsq"], float(st["count"])], dtype=torch.float64, device=dev)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     return dict(min=float(mn), max=float(mx), sum=float(sm[0]), sumsq=float(sm[1]), count=int(round(float(sm[2]))))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# z-slab sharded octree build
+class TorchComm:
+    """torch.distributed plumbing for variable-length int64 device buffers."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def allreduce_max(self, v: int, device) -> int:
+        t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def allgather_var(self, t: torch.Tensor) -> torch.Tensor:
+        """Concatenation, in rank order, of every rank's 1-D tensor (lengths may differ, may be 0)."""
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+        ns = torch.empty(self.world, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(ns, n, group=self.group)
+        ns = ns.tolist()
+        mx = max(ns)
+        if mx == 0:
+            return t.new_empty(0)
+        pad = t.new_empty(mx)
+        pad[: t.numel()] = t
+        out = t.new_empty(self.world * mx)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        if all(k == mx for k in ns):
+            return out
+        return torch.cat([out[r * mx: r * mx + k] for r, k in enumerate(ns)])
+
+
+class ThreadComm:
+    """W ranks as W threads of one process (all on one GPU): the same protocol without a process group."""
+
+    class _Shared:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.slots = [None] * world
+            self.barrier = threading.Barrier(world)
+
+    def __init__(self, shared, rank):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+
+    @classmethod
+    def make(cls, world):
+        sh = cls._Shared(world)
+        return [cls(sh, r) for r in range(world)]
+
+    def _exchange(self, v):
+        self.sh.slots[self.rank] = v
+        self.sh.barrier.wait()
+        got = list(self.sh.slots)
+        self.sh.barrier.wait()
+        return got
+
+    def allreduce_max(self, v: int, device) -> int:
+        return max(self._exchange(int(v)))
+
+    def allgather_var(self, t: torch.Tensor) -> torch.Tensor:
+        torch.cuda.current_stream(t.device).synchronize() if t.is_cuda else None
+        parts = self._exchange(t)
+        out = torch.cat([p.to(t.device) for p in parts]) if any(p.numel() for p in parts) else t.new_empty(0)
+        torch.cuda.current_stream(t.device).synchronize() if t.is_cuda else None
+        self.sh.barrier.wait()       # nobody reuses its buffer before everyone has copied
+        return out
+
+
+def build_octree_sharded(fp, ctx, mesh, params, comm, device=None, stats: dict | None = None):
+    """fpohm_octree_build over `comm.world` z slabs (include/fpohm.h protocol).  Every rank returns the complete,
+    canonically numbered octree, bit-identical to `fp.Octree.build` on one GPU.  `fp` is the fpohm_b200 module.
+    `stats`, if given, receives halo sizes (codes sent per level) and the slab cut."""
+    device = device if device is not None else torch.device("cuda", ctx.device)
+    sh = fp.OctreeShard(ctx, mesh, params, comm.rank, comm.world)
+    try:
+        lmax = sh.refine()
+        G = comm.allreduce_max(lmax, device)
+        if stats is not None:
+            stats.update(sh.info()); stats["halo_codes"] = {}; stats["global_max_level"] = G
+        for l in range(G, -1, -1):
+            n = sh.level_outgoing(G, l)
+            buf = torch.empty(n, dtype=torch.int64, device=device)
+            if n:
+                sh.outgoing_copy(buf.data_ptr())
+            got = comm.allgather_var(buf)
+            _sync(got)
+            sh.level_close(l, got.data_ptr() if got.numel() else 0, got.numel())
+            if stats is not None:
+                stats["halo_codes"][l] = n
+        ptrs, counts, keep = [], [], []
+        for l in range(G + 1):
+            n = sh.level_result(l)
+            buf = torch.empty(n, dtype=torch.int64, device=device)
+            if n:
+                sh.level_result(l, buf.data_ptr())
+            got = comm.allgather_var(buf)
+            _sync(got)
+            keep.append(got)
+            ptrs.append(got.data_ptr() if got.numel() else 0)
+            counts.append(got.numel())
+        return sh.finish(ptrs, counts)
+    finally:
+        sh.close()
+
+
+def _sync(t: torch.Tensor):
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()

@@ -97,6 +97,29 @@ int  fpohm_octree_subdivide(fpohm_octree *oct, const fpohm_mesh *mesh, int32_t s
 int  fpohm_octree_refine(fpohm_octree *oct, const fpohm_mesh *mesh, const int32_t *cell_ids, int64_t n, int32_t stop_extent);
 void fpohm_octree_free(fpohm_octree *oct);
 
+/* ---- z-slab sharded octree build (multi-GPU).  The reference has no distributed form; these entry
+ * points split fpohm_octree_build (OctreeGrid::subdivide, octree.cpp:648-690 + makeCellGraded :598-627 + pairing
+ * :574-590) so that the 2:1 grading constraints crossing a slab face can be exchanged by the HOST's collective
+ * (NCCL all-gather of Morton codes; this library links no communication layer).  Protocol, identical on every rank:
+ *     shard_create -> shard_refine(&lmax) -> G = allreduce_max(lmax)
+ *     for l = G .. 0:  level_outgoing(G, l, &n) ; outgoing_copy(buf) ; gathered = allgather(buf) ; level_close(l, gathered)
+ *     for each l:      level_result(l, buf, &n) ; gathered[l] = allgather(buf)
+ *     shard_finish(gathered, counts, &octree)       -- every rank holds the complete canonical octree
+ * The result is bit-identical to fpohm_octree_build for every world size.  All *_dev pointers are device memory of
+ * the shard's context; codes are per-level Morton codes (x bit 0, y bit 1, z bit 2 interleaved). */
+typedef struct fpohm_octree_shard fpohm_octree_shard;
+int  fpohm_octree_shard_create(fpohm_ctx *ctx, const fpohm_mesh *mesh, const fpohm_octree_params *p, int32_t rank, int32_t world,
+                               fpohm_octree_shard **out);
+void fpohm_octree_shard_free(fpohm_octree_shard *sh);
+int  fpohm_octree_shard_refine(fpohm_octree_shard *sh, int32_t *local_max_level);
+int  fpohm_octree_shard_info(const fpohm_octree_shard *sh, int32_t *replicated_levels, int32_t *slab_bounds, int64_t *owned_true_cells);
+int  fpohm_octree_shard_level_outgoing(fpohm_octree_shard *sh, int32_t global_max_level, int32_t level, int64_t *n_out);
+int  fpohm_octree_shard_outgoing_copy(fpohm_octree_shard *sh, uint64_t *dst_dev);
+int  fpohm_octree_shard_level_close(fpohm_octree_shard *sh, int32_t level, const uint64_t *gathered_dev, int64_t n_gathered, int64_t *n_closed);
+int  fpohm_octree_shard_level_result(const fpohm_octree_shard *sh, int32_t level, uint64_t *dst_dev, int64_t *n);
+int  fpohm_octree_shard_finish(fpohm_octree_shard *sh, const uint64_t *const *gathered_dev, const int64_t *counts, fpohm_octree **out);
+
+
 int  fpohm_octree_sizes(const fpohm_octree *oct, int64_t *n_nodes, int64_t *n_cells, int64_t *n_leaves,
                         int32_t *n_roots, int32_t *max_depth);
 /* m_Nodes / m_Cells (octree.h:16-61,113-114) as SoA: node_pos 3/node, node_neigh 6/node (prev/next per axis),

@@ -394,3 +394,65 @@ def test_voxel_occupancy_bit_exact_vs_predicate(fp, ctx, ref, port):
                                     C.c_double(g2.origin[2]), C.c_double(g2.spacing), C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(1))
         assert occ2[z, y, x] == e
     m.close(); m2.close()
+
+
+def _sharded_octree(fp, V, F, prm, W):
+    """Run build_octree_sharded with W ranks as W threads on cuda:0 (sharding.ThreadComm); returns rank exports + stats."""
+    import threading
+    from fpohm_b200 import sharding
+    comms = sharding.ThreadComm.make(W)
+    out, err, stats = [None] * W, [None] * W, [dict() for _ in range(W)]
+
+    def run(r):
+        try:
+            c = fp.Context(0)
+            m = fp.TriMesh(c, V, F)
+            o = sharding.build_octree_sharded(fp, c, m, prm, comms[r], stats=stats[r])
+            out[r] = (o.export(), o.flags())
+            o.close(); m.close(); c.close()
+        except BaseException as e:  # noqa: BLE001
+            err[r] = e
+            comms[r].sh.barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+    [t.start() for t in th]; [t.join(timeout=300) for t in th]
+    for e in err:
+        if e is not None:
+            raise e
+    return out, stats
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["torus_e11", "gear_e12", "linked_e12_ungraded_pairs", "torus_e11_unpaired"])
+def test_octree_zslab_sharded_equals_single(fp, ctx, case):
+    """z-slab build with halo exchange of 2:1 candidates == single-GPU build, bit for bit, for
+    every world size (ids included: phase 3 numbers the gathered sets canonically)."""
+    pm = fp.procedural
+    graded, paired = True, True
+    if case == "torus_e11":
+        V, F = pm.torus(48, 24); e = 11
+    elif case == "gear_e12":
+        V, F, _ = pm.gear(); e = 12
+    elif case == "linked_e12_ungraded_pairs":
+        V, F = pm.linked_tori(); e = 12; graded = False
+    else:
+        V, F = pm.torus(40, 20); e = 11; paired = False
+    prm = fp.octree_grid_setup(V, 1 << 20)
+    prm = fp.OctreeParams(prm.grid_size, prm.origin, prm.mesh_transform, prm.voxel_size, 1 << e, graded, paired)
+    m = fp.TriMesh(ctx, V, F)
+    whole = fp.Octree.build(ctx, m, prm)
+    ew = whole.export()
+    for W in (1, 2, 3, 5):
+        outs, stats = _sharded_octree(fp, V, F, prm, W)
+        for r in range(W):
+            ex, fl = outs[r]
+            for k in ("node_pos", "node_neigh", "first_child", "corner", "neigh"):
+                assert np.array_equal(ex[k], ew[k]), (case, W, r, k)
+            assert fl == whole.flags()
+        if W > 1:
+            b = stats[0]["slab_bounds"]
+            assert b[0] == 0 and all(b[i] <= b[i + 1] for i in range(W)) and all(s["slab_bounds"] == b for s in stats)
+            if graded:
+                assert sum(sum(s["halo_codes"].values()) for s in stats) > 0      # something did cross a slab face
+            total = sum(s["owned_true_cells"] for s in stats)
+            assert total > 0, stats[0]
+            print(case, W, "slabs", b, "owned", [s["owned_true_cells"] for s in stats], "halo", [sum(s["halo_codes"].values()) for s in stats])

@@ -214,3 +214,30 @@ print("ok", r)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_allgather_var_gloo_world2(tmp_path):
+    """The halo exchange primitive of the z-slab octree build (sharding.TorchComm.allgather_var): ragged, empty and
+    equal-length contributions over a real process group."""
+    script = tmp_path / "ag.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {str(ROOT)!r})
+from fpohm_b200 import sharding
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+c = sharding.TorchComm()
+assert c.allreduce_max(3 + 4 * r, torch.device("cpu")) == 3 + 4 * (w - 1)
+for lens in ([5, 2], [0, 7], [0, 0], [4, 4]):
+    t = torch.arange(lens[r], dtype=torch.int64) + 1000 * r
+    got = c.allgather_var(t)
+    want = torch.cat([torch.arange(lens[k], dtype=torch.int64) + 1000 * k for k in range(w)])
+    assert torch.equal(got, want), (lens, got)
+dist.barrier()
+print("OK", r)
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("OK") == 2
