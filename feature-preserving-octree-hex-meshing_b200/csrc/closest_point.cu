@@ -209,6 +209,373 @@ closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Packet search (default path).  Three kernels, each handing on only what it could not finish:
+//
+//  K1 packet   one WARP walks the tree once for its 32 consecutive queries.  The per-lane igl-order kernel above is
+//              bound by instruction issue, a third of it fp64 box arithmetic, at 10 of 32 lanes active
+//              (profiles/r01_ncu_summary.md).  Here the walk, the stack and every node / triangle load are
+//              warp-uniform and the box tests are a CONSERVATIVE fp32 FILTER: child boxes rounded outwards to float
+//              (QNodeF, 64 B per node), the query rounded down/up, every operation rounded down and the result shrunk
+//              by 2^-20, so a lane's bound is always below the exact distance to anything in the box.  A lane wants a
+//              child iff bound <= its best distance (rounded up).  The only fp64 work left is the exact igl
+//              closest-point evaluation of the leaves that pass the filter, so a lane that sees the walk through holds
+//              the exact minimum distance over ALL facets, whatever the visiting order was.
+//  K2 lane     one THREAD per query K1 did not settle (compacted list): queries of a warp that stopped sharing its
+//              search (checked every 32 visits) restart an order-free per-lane search seeded with the bound they
+//              already have; queries with near-ties get igl's tie-break (below).  Bounded work per thread.
+//  K3 heavy    one WARP per query that exceeded K2's budgets, 32 tree nodes per step (0.2 % of the bench queries hold
+//              the tail: one near the gear's bore axis needs 6 590 node visits, milliseconds for a lone thread).
+//
+// Ties.  What the visiting order decides in igl is which facet wins when several are at (nearly) the same distance:
+// igl keeps the first one its depth-first order reaches — left child first if it contains p or is nearer
+// (AABB.cpp:392-437), independent of the running minimum, so for a given p the order is a fixed total order of the
+// leaves — and its strict pruning on the COMPUTED box distances can even skip a facet that is an ulp closer.  A lane
+// therefore counts the leaves within (1 + 2^-40) of its minimum.  With more than one, K2 re-walks the tree in exact igl
+// order (`traverse_limited`) restricted to boxes within (1 + 2^-38) of the minimum.  Restricting is exact: leaves
+// outside those boxes are farther than every near-minimal candidate, so they can neither win nor make igl prune an
+// ancestor of a candidate (its box distance is below their distance); by induction over igl's order the restricted
+// walk evaluates the same candidates with the same running minimum as the full walk.  The walk stops at the first
+// facet at exactly the minimum distance (igl replaces its candidate only by a strictly closer one).  K3 finds that
+// facet in parallel instead: every stack entry carries its rank in igl's order as a bit string (0 = the child igl looks
+// at first), the exact-minimum leaf with the smallest rank is igl's winner PROVIDED igl reaches it, which holds when
+// no box on its path is farther than the minimum (checked; otherwise one lane does the rigorous re-walk).
+#define PK_STACK 64
+#define PK_WINDOW 32
+#define PK_MIN_WANT 5
+#define PK_A_BUDGET 1024
+#define PK_EPS_TIE 9.094947017729282e-13      /* 2^-40 */
+#define PK_EPS_WALK 3.637978807091713e-12     /* 2^-38 */
+#define K2_STACK 64
+#define K2_SEARCH_BUDGET 320
+#define K2_WALK_BUDGET 96
+#define HV_STACK 768
+
+__device__ __forceinline__ float box_low(const float *__restrict__ mn, const float *__restrict__ mx,
+                                         float plx, float ply, float plz, float phx, float phy, float phz)
+{
+	const float gx = fmaxf(fmaxf(__fsub_rd(mn[0], phx), __fsub_rd(plx, mx[0])), 0.f);
+	const float gy = fmaxf(fmaxf(__fsub_rd(mn[1], phy), __fsub_rd(ply, mx[1])), 0.f);
+	const float gz = fmaxf(fmaxf(__fsub_rd(mn[2], phz), __fsub_rd(plz, mx[2])), 0.f);
+	return __fmul_rd(__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))), 0.99999905f);
+}
+
+struct Packet {
+	V3 p;
+	double best;
+	float best_hi;
+	int32_t bf;
+	V3 bc;
+	int near;       // leaves within (1 + PK_EPS_TIE) of best, the best one included
+};
+
+template <bool KEEP_C>
+__device__ __forceinline__ void lane_update(Packet &k, int32_t prim, const V3 &q, double d) {
+	if (d < k.best) {
+		k.near = (d + d * PK_EPS_TIE < k.best) ? 1 : k.near + 1;
+		k.best = d; k.bf = prim;
+		if (KEEP_C) k.bc = q;
+		k.best_hi = __double2float_ru(d);
+	} else if (d <= k.best + k.best * PK_EPS_TIE) {
+		++k.near;
+	}
+}
+// exact evaluation of one leaf: warp-uniform triangle (K1) / per-lane triangle (K2)
+__device__ __forceinline__ void packet_leaf(const double *__restrict__ tri, int32_t prim, bool want, Packet &k) {
+	const double *t = tri + 9 * (int64_t)prim;
+	const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
+	if (want) {
+		const V3 q = closest_on_triangle(k.p, a, b, c);
+		lane_update<false>(k, prim, q, sqnorm(sub(k.p, q)));      // K1 recomputes the closest point of the winner at the end
+	}
+}
+__device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_t prim, Packet &k) {
+	const double *t = tri + 9 * (int64_t)prim;
+	const V3 q = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6));
+	lane_update<true>(k, prim, q, sqnorm(sub(k.p, q)));
+}
+
+// work-list entry codes
+#define TODO_WALK 1      /* minimum is exact, near-ties need igl's tie-break */
+#define TODO_SEARCH 2    /* S holds an upper bound (or +inf): search not finished */
+
+// ---- K1 ---------------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128, 8)
+cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
+                 const double *__restrict__ P, int64_t np,
+                 double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, double *__restrict__ N,
+                 int32_t *__restrict__ todo, int32_t *__restrict__ todo_count)
+{
+	__shared__ int32_t s_stack[4][PK_STACK];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int32_t *stk = s_stack[warp];
+	const int64_t nwarps = (int64_t)gridDim.x * 4;
+	for (int64_t w = blockIdx.x * 4ll + warp; w * 32 < np; w += nwarps) {
+		const int64_t i = w * 32 + lane;
+		const bool valid = i < np;
+		Packet k;
+		k.p = {0, 0, 0};
+		if (valid) k.p = ld3(P + 3 * i);
+		k.best = valid ? CUDART_INF : -1.0;            // an idle lane never wants a node (bounds are >= 0)
+		k.best_hi = valid ? CUDART_INF_F : -1.f;
+		k.bf = -1; k.bc = {0, 0, 0}; k.near = 0;
+		const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
+		const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
+		int visits = 0, window = 0, leaf_steps = 0;
+		int top = 0;
+		stk[top++] = root;                              // every lane writes the same value: no synchronisation needed
+		long long t0 = 0;
+		if (STATS) t0 = clock64();
+		while (top > 0) {
+			const int32_t cur = stk[--top];
+			const QNodeF *n = fnodes + cur;
+			const float dl = box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz);
+			const float dr = box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz);
+			const bool wl = dl <= k.best_hi, wr = dr <= k.best_hi;
+			const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+			if (!(ml | mr)) continue;
+			if ((visits & (PK_WINDOW - 1)) == PK_WINDOW - 1) {
+				if (window < PK_WINDOW * PK_MIN_WANT) { top = -1; break; }     // the lanes stopped sharing their search
+				window = 0;
+			}
+			if (visits >= PK_A_BUDGET || top + 2 > PK_STACK) { top = -1; break; }
+			++visits;
+			window += __popc(ml | mr);
+			// nearer child first: majority vote of the lanes that still want this node
+			const unsigned near_l = __ballot_sync(0xffffffffu, (wl || wr) && (dl < dr || dl == 0.f));
+			const bool left_first = 2 * __popc(near_l) >= __popc(ml | mr);
+			const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
+			const float d2 = left_first ? dr : dl;
+			const bool w1 = left_first ? wl : wr;
+			const unsigned m1 = left_first ? ml : mr, m2 = left_first ? mr : ml;
+			if (c1 < 0) {
+				if (m1) { packet_leaf(tri, ~c1, w1, k); if (STATS) ++leaf_steps; }
+				const unsigned m2b = __ballot_sync(0xffffffffu, d2 <= k.best_hi);       // the bound may have dropped
+				if (m2b) {
+					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k); if (STATS) ++leaf_steps; }
+					else stk[top++] = c2;
+				}
+			} else {
+				if (m2) {
+					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k); if (STATS) ++leaf_steps; }
+					else stk[top++] = c2;
+				}
+				if (m1) stk[top++] = c1;
+			}
+		}
+		const int code = !valid ? 0 : (top < 0 ? TODO_SEARCH : (k.near > 1 ? TODO_WALK : 0));
+		if (valid) {
+			if (k.bf >= 0) { const double *t = tri + 9 * (int64_t)k.bf; k.bc = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6)); }
+			I[i] = k.bf;
+			C[3 * i] = k.bc.x; C[3 * i + 1] = k.bc.y; C[3 * i + 2] = k.bc.z;
+			S[i] = k.best;
+		}
+		// warp-aggregated append to the work list; entry = query index within this launch, code in the top two bits
+		const unsigned mt = __ballot_sync(0xffffffffu, code != 0);
+		if (mt) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(todo_count, __popc(mt));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (code) todo[base + __popc(mt & ((1u << lane) - 1))] = (int32_t)i | (code << 30);
+		}
+		if (STATS && N && valid) { N[3 * i] = visits + 65536.0 * leaf_steps; N[3 * i + 1] = (double)(clock64() - t0); N[3 * i + 2] = code; }
+	}
+}
+
+// igl-order walk (as `traverse`) that additionally skips every box farther than `limit`, stops as soon as it holds a
+// facet at distance `dmin` (the exact minimum over all facets) and gives up after `budget` node visits (returns false).
+__device__ __forceinline__ bool traverse_limited(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri,
+                                                 const V3 &p, double limit, double dmin, int budget, Hit &h)
+{
+	h.sqr_d = CUDART_INF; h.f = -1; h.c = {0, 0, 0};
+	int32_t st_node[FPOHM_STACK];
+	double st_d[FPOHM_STACK];
+	int sp = 0;
+	int32_t cur = root;
+	for (;;) {
+		if (--budget < 0) return false;
+		const QNode *n = nodes + cur;
+		const double dl = box_ext_sqdist(n->lmin, n->lmax, p);
+		const double dr = box_ext_sqdist(n->rmin, n->rmax, p);
+		const bool in_l = box_contains(n->lmin, n->lmax, p);
+		const bool left_first = in_l || dl < dr;
+		const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
+		const double d1 = left_first ? dl : dr, d2 = left_first ? dr : dl;
+		if (d2 < h.sqr_d && d2 <= limit && sp < FPOHM_STACK) { st_node[sp] = c2; st_d[sp] = d2; ++sp; }
+		int32_t next = -1;
+		bool have_next = false;
+		if (d1 < h.sqr_d && d1 <= limit) {
+			if (c1 < 0) { test_leaf(tri, ~c1, p, h); if (h.sqr_d == dmin) return true; } else { next = c1; have_next = true; }
+		}
+		while (!have_next && sp > 0) {
+			--sp;
+			if (st_d[sp] < h.sqr_d) {
+				const int32_t c = st_node[sp];
+				if (c < 0) { test_leaf(tri, ~c, p, h); if (h.sqr_d == dmin) return true; } else { next = c; have_next = true; }
+			}
+		}
+		if (!have_next) break;
+		cur = next;
+	}
+	return true;
+}
+
+// ---- K2 ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cp_lane_kernel(const QNode *__restrict__ nodes, const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
+               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_count,
+               double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
+               int32_t *__restrict__ heavy, int32_t *__restrict__ heavy_count)
+{
+	const int n_todo = *todo_count;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_todo; t += gridDim.x * blockDim.x) {
+		const int32_t e = todo[t];
+		const int64_t i = e & 0x3fffffff;
+		const int code = (e >> 30) & 3;
+		Packet k;
+		k.p = ld3(P + 3 * i);
+		k.best = S[i];
+		k.best_hi = __double2float_ru(k.best);
+		k.bf = I[i]; k.bc = ld3(C + 3 * i);
+		k.near = 2;
+		bool give_up = false;
+		if (code == TODO_SEARCH) {
+			// order-free search from the root with the bound already known; it meets facet bf again (counted in near)
+			k.near = 0;
+			const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
+			const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
+			int32_t lst[K2_STACK];
+			int sp = 0, budget = K2_SEARCH_BUDGET;
+			lst[sp++] = root;
+			while (sp > 0) {
+				const QNodeF *n = fnodes + lst[--sp];
+				const float dl = box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz);
+				const float dr = box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz);
+				if (!(dl <= k.best_hi || dr <= k.best_hi)) continue;
+				if (--budget < 0 || sp + 2 > K2_STACK) { give_up = true; break; }
+				const bool left_first = dl < dr || dl == 0.f;
+				const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
+				const float d1 = left_first ? dl : dr, d2 = left_first ? dr : dl;
+				if (c1 < 0) {
+					if (d1 <= k.best_hi) lane_leaf(tri, ~c1, k);
+					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k); else lst[sp++] = c2; }
+				} else {
+					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k); else lst[sp++] = c2; }
+					if (d1 <= k.best_hi) lst[sp++] = c1;
+				}
+			}
+		}
+		Hit h;
+		h.sqr_d = k.best; h.f = k.bf; h.c = k.bc;
+		if (!give_up && k.near > 1)
+			give_up = !traverse_limited(nodes, root, tri, k.p, k.best + k.best * PK_EPS_WALK, k.best, K2_WALK_BUDGET, h);
+		if (give_up) {
+			S[i] = k.best;                                   // still a valid upper bound for K3
+			heavy[atomicAdd(heavy_count, 1)] = (int32_t)i;
+		} else {
+			I[i] = h.f;
+			C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z;
+			S[i] = h.sqr_d;
+		}
+	}
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
+                const double *__restrict__ P, const int32_t *__restrict__ heavy, const int32_t *__restrict__ heavy_count,
+                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C)
+{
+	__shared__ int32_t s_node[4][HV_STACK];
+	__shared__ unsigned long long s_key[4][HV_STACK];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int32_t *stk = s_node[warp];
+	unsigned long long *stkk = s_key[warp];
+	const int n_heavy = *heavy_count;
+	const unsigned lt = (1u << lane) - 1;
+	for (int hq = blockIdx.x * 4 + warp; hq < n_heavy; hq += gridDim.x * 4) {
+		const int64_t i = heavy[hq];
+		const V3 p = ld3(P + 3 * i);
+		double best = S[i];                               // exact distance of some facet (or +inf): a valid upper bound
+		unsigned long long bkey = ~0ull;
+		int32_t bfac = -1;
+		bool deep = false;                                // a rank did not fit 62 bits
+		int top = 1;
+		if (lane == 0) { stk[0] = root; stkk[0] = 0ull; }
+		__syncwarp();
+		while (top > 0) {
+			int take = top < 32 ? top : 32;
+			if (top > HV_STACK - 64) take = 1;              // nearly full: pure depth-first, growth bounded by the tree depth
+			int32_t cl = 0, cr = 0;
+			unsigned long long kl = 0, kr = 0;
+			bool wl = false, wr = false;
+			const double lim = best + best * PK_EPS_TIE;
+			if (lane < take) {
+				const QNode *n = nodes + stk[top - 1 - lane];
+				const unsigned long long key = stkk[top - 1 - lane];
+				const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
+				const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
+				const int depth = n->depth;
+				if (depth > 61) deep = true;
+				const unsigned long long bit = depth > 61 ? 0ull : 1ull << (61 - depth);
+				kl = left_first ? key : key | bit; kr = left_first ? key | bit : key;
+				wl = dl <= lim; wr = dr <= lim;
+				cl = n->left; cr = n->right;
+			}
+			__syncwarp();
+			top -= take;
+			// leaves: exact distance; candidate ordered by (distance, igl rank)
+			double d = CUDART_INF; unsigned long long dk = ~0ull; int32_t df = -1;
+			if (wl && cl < 0) { const double *t = tri + 9 * (int64_t)~cl; d = sqnorm(sub(p, closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6)))); dk = kl; df = ~cl; }
+			if (wr && cr < 0) {
+				const double *t = tri + 9 * (int64_t)~cr;
+				const double d2 = sqnorm(sub(p, closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6))));
+				if (d2 < d || (d2 == d && kr < dk)) { d = d2; dk = kr; df = ~cr; }
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const double od = __shfl_xor_sync(0xffffffffu, d, o);
+				const unsigned long long ok = __shfl_xor_sync(0xffffffffu, dk, o);
+				const int32_t of = __shfl_xor_sync(0xffffffffu, df, o);
+				if (od < d || (od == d && ok < dk)) { d = od; dk = ok; df = of; }
+			}
+			if (df >= 0 && (d < best || (d == best && dk < bkey))) { best = d; bkey = dk; bfac = df; }
+			const bool pl = wl && cl >= 0, pr = wr && cr >= 0;
+			const unsigned mpl = __ballot_sync(0xffffffffu, pl), mpr = __ballot_sync(0xffffffffu, pr);
+			if (pl) { const int q = top + __popc(mpl & lt); stk[q] = cl; stkk[q] = kl; }
+			if (pr) { const int q = top + __popc(mpl) + __popc(mpr & lt); stk[q] = cr; stkk[q] = kr; }
+			top += __popc(mpl) + __popc(mpr);
+			__syncwarp();
+		}
+		deep = __any_sync(0xffffffffu, deep);
+		if (lane == 0) {
+			// igl reaches the first-ranked exact-minimum leaf if every box on its path is at most `best` away
+			bool ok = !deep && bfac >= 0;
+			if (ok) {
+				int32_t child = ~bfac, nd = prim_parent[bfac];
+				while (nd >= 0 && ok) {
+					const QNode *n = nodes + nd;
+					const double bd = n->left == child ? box_ext_sqdist(n->lmin, n->lmax, p) : box_ext_sqdist(n->rmin, n->rmax, p);
+					ok = bd <= best;
+					child = nd; nd = n->parent;
+				}
+			}
+			Hit h;
+			if (ok) {
+				const double *t = tri + 9 * (int64_t)bfac;
+				h.f = bfac; h.sqr_d = best; h.c = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6));
+			} else {
+				traverse_limited(nodes, root, tri, p, best + best * PK_EPS_WALK, best, 0x7fffffff, h);
+			}
+			if (I) I[i] = h.f;
+			if (C) { C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z; }
+			if (S) S[i] = h.sqr_d;
+		}
+		__syncwarp();
+	}
+}
+
 // Pass 2 (signed queries only): pseudonormal_test on (q, facet, closest point); fully coherent, one thread per query.
 __global__ void __launch_bounds__(128)
 pseudonormal_kernel(const double *__restrict__ V, const int32_t *__restrict__ F, int64_t nF,
@@ -219,6 +586,11 @@ pseudonormal_kernel(const double *__restrict__ V, const int32_t *__restrict__ F,
 	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
 		const V3 p = ld3(P + 3 * i), c = ld3(C + 3 * i);
 		V3 n = {0, 0, 0};
+		if (I[i] < 0) {                                     // no facet: NaN query coordinates (igl leaves its outputs untouched)
+			if (S) S[i] = CUDART_NAN;
+			if (N && keep_n) { N[3 * i] = 0; N[3 * i + 1] = 0; N[3 * i + 2] = 0; }
+			continue;
+		}
 		const double s = pseudonormal(V, F, nF, FN, VN, EN, EMAP, p, I[i], c, n);
 		if (S) S[i] = s * sqrt(S[i]);                       // S held the squared distance
 		if (N && keep_n) { N[3 * i] = n.x; N[3 * i + 1] = n.y; N[3 * i + 2] = n.z; }
@@ -243,8 +615,26 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
 		if (!S && N) { tmpS.alloc(np, s); S = tmpS.p; }
 	}
-	if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
-	else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
+	static const int mode = getenv("FPOHM_CP_MODE") ? atoi(getenv("FPOHM_CP_MODE")) : 1;   // debug A/B: 0 = per-lane igl order only
+	if (mode == 1 && m->qroot >= 0) {
+		FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "closest point: %lld queries in one launch", (long long)np);
+		// K1/K2/K3 hand unfinished queries on through S/I/C, so all three must exist
+		if (!I) { tmpI.alloc(np, s); I = tmpI.p; }
+		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
+		if (!S) { tmpS.alloc(np, s); S = tmpS.p; }
+		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
+		DevBuf<int32_t> todo(np, s), heavy(np, s), cnt(2, s);
+		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int32_t), s));
+		if (stats) cp_packet_kernel<true><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, cnt.p);
+		else cp_packet_kernel<false><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, cnt.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_lane_kernel<<<ctx->sm_count * 16, blk, 0, s>>>(m->qnodes.p, m->qfnodes.p, m->qroot, m->tri.p, P_dev, todo.p, cnt.p, S, I, C, heavy.p, cnt.p + 1);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_heavy_kernel<<<ctx->sm_count * 4, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, heavy.p, cnt.p + 1, S, I, C);
+	} else {
+		if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
+		else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
+	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	if (with_sign && (S || N)) {
 		pseudonormal_kernel<<<grid, blk, 0, s>>>(m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, I, C, S, N, !stats);

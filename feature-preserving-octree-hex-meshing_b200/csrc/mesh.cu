@@ -2,6 +2,7 @@
 #include "mesh.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
 
@@ -134,8 +135,37 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 			n.rmin[c] = t.box[6 * (size_t)r + c]; n.rmax[c] = t.box[6 * (size_t)r + 3 + c];
 		}
 		n.left = child_ref(l); n.right = child_ref(r);
-		n.pad[0] = n.pad[1] = n.pad[2] = n.pad[3] = 0;
+		n.pad[0] = n.pad[1] = 0;
 	}
+	// parents / depths (pre-order: a parent precedes its children)
+	int32_t maxd = 0;
+	if (ni) { q[0].parent = -1; q[0].depth = 0; }
+	for (int32_t i = 0; i < ni; ++i)
+		for (int32_t c : {q[(size_t)i].left, q[(size_t)i].right})
+			if (c >= 0) { q[(size_t)c].parent = i; q[(size_t)c].depth = q[(size_t)i].depth + 1; maxd = std::max(maxd, q[(size_t)c].depth); }
+	m->qdepth = maxd;
+	std::vector<int32_t> pp((size_t)std::max<int64_t>(m->nF, 1), -1);
+	for (int32_t i = 0; i < ni; ++i) {
+		if (q[(size_t)i].left < 0) pp[(size_t)~q[(size_t)i].left] = i;
+		if (q[(size_t)i].right < 0) pp[(size_t)~q[(size_t)i].right] = i;
+	}
+	m->prim_parent.alloc((int64_t)pp.size(), s);
+	m->prim_parent.upload(pp.data(), (int64_t)pp.size());
+	// fp32 filter copy, boxes rounded outwards
+	auto f_dn = [](double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; };
+	auto f_up = [](double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; };
+	std::vector<QNodeF> qf((size_t)std::max<int32_t>(ni, 1));
+	for (int32_t i = 0; i < ni; ++i) {
+		const QNode &n = q[(size_t)i];
+		QNodeF &f = qf[(size_t)i];
+		for (int c = 0; c < 3; ++c) {
+			f.lmin[c] = f_dn(n.lmin[c]); f.lmax[c] = f_up(n.lmax[c]);
+			f.rmin[c] = f_dn(n.rmin[c]); f.rmax[c] = f_up(n.rmax[c]);
+		}
+		f.left = n.left; f.right = n.right; f.pad[0] = f.pad[1] = 0;
+	}
+	m->qfnodes.alloc((int64_t)qf.size(), s);
+	m->qfnodes.upload(qf.data(), (int64_t)qf.size());
 	m->n_qnodes = ni;
 	m->qroot = nn ? (t.prim[0] >= 0 ? ~t.prim[0] : 0) : 0;
 	m->qnodes.alloc(std::max<int64_t>(ni, 1), s);

@@ -11,9 +11,20 @@ struct alignas(128) QNode {
 	double lmin[3], lmax[3];
 	double rmin[3], rmax[3];
 	int32_t left, right;
-	int32_t pad[4];
+	int32_t parent;   // internal node index of the parent, -1 for the root
+	int32_t depth;    // root = 0
+	int32_t pad[2];
 };
 static_assert(sizeof(QNode) == 128, "QNode must be one cache line");
+
+// The same node for the packet search's conservative fp32 filter: child boxes rounded OUTWARDS to float.
+struct alignas(64) QNodeF {
+	float lmin[3], lmax[3];
+	float rmin[3], rmax[3];
+	int32_t left, right;
+	int32_t pad[2];
+};
+static_assert(sizeof(QNodeF) == 64, "QNodeF must be half a cache line");
 
 // host-side result of the igl::AABB::init restatement, in DFS pre-order (node 0 = root)
 struct HostTree {
@@ -52,6 +63,9 @@ struct fpohm_mesh {
 	int64_t n_qnodes = 0;
 	fpohm::DevBuf<fpohm::QNode> qnodes;
 	int32_t qroot = 0;             // >= 0 internal node, < 0 leaf (~prim) when nF == 1
+	int32_t qdepth = 0;            // deepest internal node
+	fpohm::DevBuf<fpohm::QNodeF> qfnodes;
+	fpohm::DevBuf<int32_t> prim_parent; // internal node holding facet f as a child
 	std::vector<double> hFN, hVN, hEN;
 	std::vector<int32_t> hE, hEMAP;
 	fpohm::DevBuf<double> FN, VN, EN;

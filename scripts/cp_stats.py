@@ -21,3 +21,9 @@ print("leaves/query mean %.1f median %.0f p99 %.0f max %.0f" % (leaves.mean(), n
 w = nodes.reshape(-1, 32) if len(nodes) % 32 == 0 else nodes[: len(nodes) // 32 * 32].reshape(-1, 32)
 print("per-warp max/mean node visits: %.2f" % (w.max(1).mean() / w.mean()))
 d = np.abs(S); print("distance/leaf-extent median %.2f" % np.median(d / np.repeat(ext, 4)))
+srt = np.sort(nodes)[::-1]
+for frac in (1e-5, 1e-4, 1e-3, 1e-2, 1e-1):
+    k = max(1, int(len(srt) * frac))
+    print("top %.3f%% of queries hold %.1f%% of the node visits (min visits in that set %.0f)" % (100 * frac, 100 * srt[:k].sum() / srt.sum(), srt[k - 1]))
+wm = w.max(1)
+print("per-warp max visits: mean %.0f p99 %.0f p99.9 %.0f max %.0f" % (wm.mean(), np.percentile(wm, 99), np.percentile(wm, 99.9), wm.max()))
