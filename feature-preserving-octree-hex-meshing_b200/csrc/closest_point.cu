@@ -260,6 +260,7 @@ __device__ __forceinline__ float box_low(const float *__restrict__ mn, const flo
 	return __fmul_rd(__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))), 0.99999905f);
 }
 
+#define PK_TIES 3
 struct Packet {
 	V3 p;
 	double best;
@@ -267,32 +268,75 @@ struct Packet {
 	int32_t bf;
 	V3 bc;
 	int near;       // leaves within (1 + PK_EPS_TIE) of best, the best one included
+	int nt;         // leaves at EXACTLY best besides bf; the first PK_TIES are kept in the tie slots
 };
 
-template <bool KEEP_C>
-__device__ __forceinline__ void lane_update(Packet &k, int32_t prim, const V3 &q, double d) {
+template <bool KEEP_C, int STRIDE>
+__device__ __forceinline__ void lane_update(Packet &k, int32_t *__restrict__ ties, int32_t prim, const V3 &q, double d) {
 	if (d < k.best) {
 		k.near = (d + d * PK_EPS_TIE < k.best) ? 1 : k.near + 1;
+		k.nt = 0;
 		k.best = d; k.bf = prim;
 		if (KEEP_C) k.bc = q;
 		k.best_hi = __double2float_ru(d);
 	} else if (d <= k.best + k.best * PK_EPS_TIE) {
 		++k.near;
+		if (d == k.best) { if (k.nt < PK_TIES) ties[k.nt * STRIDE] = prim; ++k.nt; }
 	}
 }
 // exact evaluation of one leaf: warp-uniform triangle (K1) / per-lane triangle (K2)
-__device__ __forceinline__ void packet_leaf(const double *__restrict__ tri, int32_t prim, bool want, Packet &k) {
+__device__ __forceinline__ void packet_leaf(const double *__restrict__ tri, int32_t prim, bool want, Packet &k, int32_t *__restrict__ ties) {
 	const double *t = tri + 9 * (int64_t)prim;
 	const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
 	if (want) {
 		const V3 q = closest_on_triangle(k.p, a, b, c);
-		lane_update<false>(k, prim, q, sqnorm(sub(k.p, q)));      // K1 recomputes the closest point of the winner at the end
+		lane_update<false, 32>(k, ties, prim, q, sqnorm(sub(k.p, q)));      // K1 recomputes the closest point of the winner at the end
 	}
 }
-__device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_t prim, Packet &k) {
+__device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_t prim, Packet &k, int32_t *__restrict__ ties) {
 	const double *t = tri + 9 * (int64_t)prim;
 	const V3 q = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6));
-	lane_update<true>(k, prim, q, sqnorm(sub(k.p, q)));
+	lane_update<true, 1>(k, ties, prim, q, sqnorm(sub(k.p, q)));
+}
+
+// true iff igl's depth-first order for query p reaches facet fa before facet fb: decided at their lowest common
+// ancestor, where igl looks first at the child that contains p or is nearer (AABB.cpp:392-437).
+__device__ __forceinline__ bool igl_visits_first(const QNode *__restrict__ nodes, const int32_t *__restrict__ prim_parent,
+                                                 const V3 &p, int32_t fa, int32_t fb)
+{
+	int32_t na = prim_parent[fa], nb = prim_parent[fb];
+	int32_t ca = ~fa, cb = ~fb;                      // child reference through which each side enters the ancestor
+	int da = nodes[na].depth, db = nodes[nb].depth;
+	while (da > db) { ca = na; na = nodes[na].parent; --da; }
+	while (db > da) { cb = nb; nb = nodes[nb].parent; --db; }
+	while (na != nb) { ca = na; na = nodes[na].parent; cb = nb; nb = nodes[nb].parent; }
+	const QNode *n = nodes + na;
+	const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
+	const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
+	return (n->left == ca) == left_first;
+}
+
+// igl's winner among the facets at exactly the minimum distance, when it can be named without walking the tree:
+// a* = the first of them in igl's order.  igl reaches a* if no box on its path is farther than the minimum; boxes nest,
+// so every per-axis gap of an ancestor is <= the gap of a*'s own box and, the fp operations being monotone, the computed
+// distance of every ancestor box is <= the computed distance of a*'s box: ONE box test proves the whole path.  Until
+// a* is evaluated igl's running minimum is above the true minimum (a* is the first facet at that distance), so the
+// strict test on those boxes passes, a* is evaluated, and nothing later can replace it.  Returns -1 if the box test
+// fails (then only the walk in igl's order can tell).
+__device__ __forceinline__ int32_t igl_tie_winner(const QNode *__restrict__ nodes, const int32_t *__restrict__ prim_parent,
+                                                  const double *__restrict__ tri, const V3 &p, double dmin, int32_t bf,
+                                                  const int32_t *__restrict__ ties, int stride, int nt)
+{
+	int32_t win = bf;
+	for (int j = 0; j < nt; ++j) {
+		const int32_t f = ties[j * stride];
+		if (igl_visits_first(nodes, prim_parent, p, f, win)) win = f;
+	}
+	const double *t = tri + 9 * (int64_t)win;
+	const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
+	const double mn[3] = {fmin(a.x, fmin(b.x, c.x)), fmin(a.y, fmin(b.y, c.y)), fmin(a.z, fmin(b.z, c.z))};
+	const double mx[3] = {fmax(a.x, fmax(b.x, c.x)), fmax(a.y, fmax(b.y, c.y)), fmax(a.z, fmax(b.z, c.z))};
+	return box_ext_sqdist(mn, mx, p) <= dmin ? win : -1;
 }
 
 // work-list entry codes
@@ -300,16 +344,18 @@ __device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_
 #define TODO_SEARCH 2    /* S holds an upper bound (or +inf): search not finished */
 
 // ---- K1 ---------------------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(128, 8)
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
                  const double *__restrict__ P, int64_t np,
                  double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, double *__restrict__ N,
-                 int32_t *__restrict__ todo, int32_t *__restrict__ todo_count)
+                 int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties, int32_t *__restrict__ todo_count)
 {
 	__shared__ int32_t s_stack[4][PK_STACK];
+	__shared__ int32_t s_tie[4][PK_TIES][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *stk = s_stack[warp];
+	int32_t *ties = &s_tie[warp][0][lane];
 	const int64_t nwarps = (int64_t)gridDim.x * 4;
 	for (int64_t w = blockIdx.x * 4ll + warp; w * 32 < np; w += nwarps) {
 		const int64_t i = w * 32 + lane;
@@ -319,11 +365,12 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 		if (valid) k.p = ld3(P + 3 * i);
 		k.best = valid ? CUDART_INF : -1.0;            // an idle lane never wants a node (bounds are >= 0)
 		k.best_hi = valid ? CUDART_INF_F : -1.f;
-		k.bf = -1; k.bc = {0, 0, 0}; k.near = 0;
+		k.bf = -1; k.bc = {0, 0, 0}; k.near = 0; k.nt = 0;
 		const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
 		const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
 		int visits = 0, window = 0, leaf_steps = 0;
 		int top = 0;
+		bool bail = false;
 		stk[top++] = root;                              // every lane writes the same value: no synchronisation needed
 		long long t0 = 0;
 		if (STATS) t0 = clock64();
@@ -336,10 +383,10 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
 			if (!(ml | mr)) continue;
 			if ((visits & (PK_WINDOW - 1)) == PK_WINDOW - 1) {
-				if (window < PK_WINDOW * PK_MIN_WANT) { top = -1; break; }     // the lanes stopped sharing their search
+				if (window < PK_WINDOW * PK_MIN_WANT) { stk[top++] = cur; bail = true; break; }     // the lanes stopped sharing their search
 				window = 0;
 			}
-			if (visits >= PK_A_BUDGET || top + 2 > PK_STACK) { top = -1; break; }
+			if (visits >= PK_A_BUDGET || top + 2 > PK_STACK) { stk[top++] = cur; bail = true; break; }
 			++visits;
 			window += __popc(ml | mr);
 			// nearer child first: majority vote of the lanes that still want this node
@@ -350,21 +397,30 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			const bool w1 = left_first ? wl : wr;
 			const unsigned m1 = left_first ? ml : mr, m2 = left_first ? mr : ml;
 			if (c1 < 0) {
-				if (m1) { packet_leaf(tri, ~c1, w1, k); if (STATS) ++leaf_steps; }
+				if (m1) { packet_leaf(tri, ~c1, w1, k, ties); if (STATS) ++leaf_steps; }
 				const unsigned m2b = __ballot_sync(0xffffffffu, d2 <= k.best_hi);       // the bound may have dropped
 				if (m2b) {
-					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k); if (STATS) ++leaf_steps; }
+					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k, ties); if (STATS) ++leaf_steps; }
 					else stk[top++] = c2;
 				}
 			} else {
 				if (m2) {
-					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k); if (STATS) ++leaf_steps; }
+					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k, ties); if (STATS) ++leaf_steps; }
 					else stk[top++] = c2;
 				}
 				if (m1) stk[top++] = c1;
 			}
 		}
-		const int code = !valid ? 0 : (top < 0 ? TODO_SEARCH : (k.near > 1 ? TODO_WALK : 0));
+		// a warp that gave up: only the lanes that still want something on the stack have an unfinished search
+		bool unfinished = false;
+		if (bail) {
+			for (int j = 0; j < top; ++j) {
+				const QNodeF *n = fnodes + stk[j];
+				unfinished |= box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz) <= k.best_hi ||
+				              box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz) <= k.best_hi;
+			}
+		}
+		const int code = !valid ? 0 : (unfinished ? TODO_SEARCH : (k.near > 1 ? TODO_WALK : 0));
 		if (valid) {
 			if (k.bf >= 0) { const double *t = tri + 9 * (int64_t)k.bf; k.bc = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6)); }
 			I[i] = k.bf;
@@ -377,7 +433,13 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			int base = 0;
 			if (lane == 0) base = atomicAdd(todo_count, __popc(mt));
 			base = __shfl_sync(0xffffffffu, base, 0);
-			if (code) todo[base + __popc(mt & ((1u << lane) - 1))] = (int32_t)i | (code << 30);
+			if (code) {
+				const int slot = base + __popc(mt & ((1u << lane) - 1));
+				todo[slot] = (int32_t)i | (code << 30);
+				int32_t *tr = todo_ties + 4 * (int64_t)slot;
+				tr[0] = k.nt;
+				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < k.nt ? ties[32 * j] : -1;
+			}
 		}
 		if (STATS && N && valid) { N[3 * i] = visits + 65536.0 * leaf_steps; N[3 * i + 1] = (double)(clock64() - t0); N[3 * i + 2] = code; }
 	}
@@ -424,9 +486,11 @@ __device__ __forceinline__ bool traverse_limited(const QNode *__restrict__ nodes
 // ---- K2 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 cp_lane_kernel(const QNode *__restrict__ nodes, const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
-               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_count,
+               const int32_t *__restrict__ prim_parent,
+               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_ties,
+               const int32_t *__restrict__ todo_count,
                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
-               int32_t *__restrict__ heavy, int32_t *__restrict__ heavy_count)
+               int32_t *__restrict__ heavy, int32_t *__restrict__ heavy_count, int search_budget, int walk_budget)
 {
 	const int n_todo = *todo_count;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_todo; t += gridDim.x * blockDim.x) {
@@ -439,14 +503,21 @@ cp_lane_kernel(const QNode *__restrict__ nodes, const QNodeF *__restrict__ fnode
 		k.best_hi = __double2float_ru(k.best);
 		k.bf = I[i]; k.bc = ld3(C + 3 * i);
 		k.near = 2;
+		int32_t ties[PK_TIES];
+		k.nt = todo_ties[4 * (int64_t)t];
+		for (int j = 0; j < PK_TIES; ++j) ties[j] = todo_ties[4 * (int64_t)t + 1 + j];
 		bool give_up = false;
 		if (code == TODO_SEARCH) {
 			// order-free search from the root with the bound already known; it meets facet bf again (counted in near)
-			k.near = 0;
+			k.near = 0; k.nt = 0;
+			const int32_t bf0 = k.bf;
+			k.bf = -1;                                       // so that meeting bf0 again registers it as the (first) best
+			if (bf0 >= 0) k.best = k.best + k.best * PK_EPS_TIE * 4;   // still an upper bound; lets bf0 itself pass 'd < best'
+			k.best_hi = __double2float_ru(k.best);
 			const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
 			const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
 			int32_t lst[K2_STACK];
-			int sp = 0, budget = K2_SEARCH_BUDGET;
+			int sp = 0, budget = search_budget;
 			lst[sp++] = root;
 			while (sp > 0) {
 				const QNodeF *n = fnodes + lst[--sp];
@@ -458,18 +529,26 @@ cp_lane_kernel(const QNode *__restrict__ nodes, const QNodeF *__restrict__ fnode
 				const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
 				const float d1 = left_first ? dl : dr, d2 = left_first ? dr : dl;
 				if (c1 < 0) {
-					if (d1 <= k.best_hi) lane_leaf(tri, ~c1, k);
-					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k); else lst[sp++] = c2; }
+					if (d1 <= k.best_hi) lane_leaf(tri, ~c1, k, ties);
+					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
 				} else {
-					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k); else lst[sp++] = c2; }
+					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
 					if (d1 <= k.best_hi) lst[sp++] = c1;
 				}
 			}
+			if (give_up && k.bf < 0) { k.best = S[i]; k.bf = bf0; }      // nothing better met before the budget ran out
 		}
 		Hit h;
 		h.sqr_d = k.best; h.f = k.bf; h.c = k.bc;
-		if (!give_up && k.near > 1)
-			give_up = !traverse_limited(nodes, root, tri, k.p, k.best + k.best * PK_EPS_WALK, k.best, K2_WALK_BUDGET, h);
+		if (!give_up && k.near > 1) {
+			int32_t win = -1;
+			if (k.nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, k.p, k.best, k.bf, ties, 1, k.nt);
+			if (win >= 0) {
+				if (win != k.bf) { const double *tt = tri + 9 * (int64_t)win; h.f = win; h.c = closest_on_triangle(k.p, ld3(tt), ld3(tt + 3), ld3(tt + 6)); }
+			} else {
+				give_up = !traverse_limited(nodes, root, tri, k.p, k.best + k.best * PK_EPS_WALK, k.best, walk_budget, h);
+			}
+		}
 		if (give_up) {
 			S[i] = k.best;                                   // still a valid upper bound for K3
 			heavy[atomicAdd(heavy_count, 1)] = (int32_t)i;
@@ -623,14 +702,20 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
 		if (!S) { tmpS.alloc(np, s); S = tmpS.p; }
 		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
-		DevBuf<int32_t> todo(np, s), heavy(np, s), cnt(2, s);
+		DevBuf<int32_t> todo(np, s), todo_ties(4 * np, s), heavy(np, s), cnt(2, s);
 		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int32_t), s));
-		if (stats) cp_packet_kernel<true><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, cnt.p);
-		else cp_packet_kernel<false><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, cnt.p);
+		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
+		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
+		static const int minb = getenv("FPOHM_K1_MINB") ? atoi(getenv("FPOHM_K1_MINB")) : 7;
+		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		else if (minb == 6) cp_packet_kernel<false, 6><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		else if (minb == 7) cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		else if (minb == 5) cp_packet_kernel<false, 5><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		else cp_packet_kernel<false, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_lane_kernel<<<ctx->sm_count * 16, blk, 0, s>>>(m->qnodes.p, m->qfnodes.p, m->qroot, m->tri.p, P_dev, todo.p, cnt.p, S, I, C, heavy.p, cnt.p + 1);
+		cp_lane_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qfnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, cnt.p + 1, k2_search, k2_walk);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_heavy_kernel<<<ctx->sm_count * 4, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, heavy.p, cnt.p + 1, S, I, C);
+		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, heavy.p, cnt.p + 1, S, I, C);
 	} else {
 		if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 		else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
