@@ -427,18 +427,22 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			C[3 * i] = k.bc.x; C[3 * i + 1] = k.bc.y; C[3 * i + 2] = k.bc.z;
 			S[i] = k.best;
 		}
-		// warp-aggregated append to the work list; entry = query index within this launch, code in the top two bits
-		const unsigned mt = __ballot_sync(0xffffffffu, code != 0);
-		if (mt) {
-			int base = 0;
-			if (lane == 0) base = atomicAdd(todo_count, __popc(mt));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (code) {
-				const int slot = base + __popc(mt & ((1u << lane) - 1));
-				todo[slot] = (int32_t)i | (code << 30);
+		// warp-aggregated append to the work lists (tie-breaks grow from the front of `todo`, unfinished searches from
+		// the back, so that each completion kernel gets warps full of one kind of work)
+		const unsigned mw = __ballot_sync(0xffffffffu, code == TODO_WALK), ms = __ballot_sync(0xffffffffu, code == TODO_SEARCH);
+		if (mw | ms) {
+			int bw = 0, bs = 0;
+			if (lane == 0) { if (mw) bw = atomicAdd(todo_count, __popc(mw)); if (ms) bs = atomicAdd(todo_count + 2, __popc(ms)); }
+			bw = __shfl_sync(0xffffffffu, bw, 0); bs = __shfl_sync(0xffffffffu, bs, 0);
+			const unsigned lt = (1u << lane) - 1;
+			if (code == TODO_WALK) {
+				const int slot = bw + __popc(mw & lt);
+				todo[slot] = (int32_t)i;
 				int32_t *tr = todo_ties + 4 * (int64_t)slot;
 				tr[0] = k.nt;
 				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < k.nt ? ties[32 * j] : -1;
+			} else if (code == TODO_SEARCH) {
+				todo[2 * np - 1 - (bs + __popc(ms & lt))] = (int32_t)i;
 			}
 		}
 		if (STATS && N && valid) { N[3 * i] = visits + 65536.0 * leaf_steps; N[3 * i + 1] = (double)(clock64() - t0); N[3 * i + 2] = code; }
@@ -483,79 +487,144 @@ __device__ __forceinline__ bool traverse_limited(const QNode *__restrict__ nodes
 	return true;
 }
 
-// ---- K2 ---------------------------------------------------------------------------------------------------------
+// ---- K2 (tie-break) -----------------------------------------------------------------------------------------
+// One thread per query whose minimum is exact but shared (nearly) by several facets: name igl's winner from the exact-tie
+// list when one box test proves it (`igl_tie_winner`), else re-walk in igl order; a walk that exceeds its budget goes on
+// to the heavy kernel.
 __global__ void __launch_bounds__(128)
-cp_lane_kernel(const QNode *__restrict__ nodes, const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
-               const int32_t *__restrict__ prim_parent,
-               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_ties,
-               const int32_t *__restrict__ todo_count,
-               double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
-               int32_t *__restrict__ heavy, int32_t *__restrict__ heavy_count, int search_budget, int walk_budget)
+cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
+              const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_ties,
+              int32_t *__restrict__ counters, double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
+              int32_t *__restrict__ heavy, int walk_budget)
 {
-	const int n_todo = *todo_count;
+	const int n_todo = counters[0];
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_todo; t += gridDim.x * blockDim.x) {
-		const int32_t e = todo[t];
-		const int64_t i = e & 0x3fffffff;
-		const int code = (e >> 30) & 3;
-		Packet k;
-		k.p = ld3(P + 3 * i);
-		k.best = S[i];
-		k.best_hi = __double2float_ru(k.best);
-		k.bf = I[i]; k.bc = ld3(C + 3 * i);
-		k.near = 2;
+		const int64_t i = todo[t];
+		const V3 p = ld3(P + 3 * i);
+		const double best = S[i];
+		const int32_t bf = I[i];
+		const int nt = todo_ties[4 * (int64_t)t];
 		int32_t ties[PK_TIES];
-		k.nt = todo_ties[4 * (int64_t)t];
 		for (int j = 0; j < PK_TIES; ++j) ties[j] = todo_ties[4 * (int64_t)t + 1 + j];
-		bool give_up = false;
-		if (code == TODO_SEARCH) {
-			// order-free search from the root with the bound already known; it meets facet bf again (counted in near)
-			k.near = 0; k.nt = 0;
-			const int32_t bf0 = k.bf;
-			k.bf = -1;                                       // so that meeting bf0 again registers it as the (first) best
-			if (bf0 >= 0) k.best = k.best + k.best * PK_EPS_TIE * 4;   // still an upper bound; lets bf0 itself pass 'd < best'
-			k.best_hi = __double2float_ru(k.best);
-			const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
-			const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
-			int32_t lst[K2_STACK];
-			int sp = 0, budget = search_budget;
-			lst[sp++] = root;
-			while (sp > 0) {
-				const QNodeF *n = fnodes + lst[--sp];
-				const float dl = box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz);
-				const float dr = box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz);
-				if (!(dl <= k.best_hi || dr <= k.best_hi)) continue;
-				if (--budget < 0 || sp + 2 > K2_STACK) { give_up = true; break; }
-				const bool left_first = dl < dr || dl == 0.f;
-				const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
-				const float d1 = left_first ? dl : dr, d2 = left_first ? dr : dl;
-				if (c1 < 0) {
-					if (d1 <= k.best_hi) lane_leaf(tri, ~c1, k, ties);
-					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
+		int32_t win = -1;
+		if (nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, p, best, bf, ties, 1, nt);
+		if (win >= 0) {
+			if (win != bf) {
+				const double *tt = tri + 9 * (int64_t)win;
+				const V3 c = closest_on_triangle(p, ld3(tt), ld3(tt + 3), ld3(tt + 6));
+				I[i] = win;
+				C[3 * i] = c.x; C[3 * i + 1] = c.y; C[3 * i + 2] = c.z;
+			}
+		} else {
+			Hit h;
+			if (traverse_limited(nodes, root, tri, p, best + best * PK_EPS_WALK, best, walk_budget, h)) {
+				I[i] = h.f;
+				C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z;
+				S[i] = h.sqr_d;
+			} else {
+				heavy[atomicAdd(counters + 1, 1)] = (int32_t)i;      // S[i] stays a valid upper bound for K3
+			}
+		}
+	}
+}
+
+// ---- K2 (search) --------------------------------------------------------------------------------------------
+// Unfinished searches have very uneven lengths (tens to thousands of node visits), and a thread per query makes every
+// warp wait for its longest lane.  Persistent lanes instead: every loop iteration is ONE node visit for every lane that
+// has a query, and a lane that finishes fetches the next query from the list at once (warp-aggregated counter), so the
+// warp's lanes stay busy and its time follows the mean search length, not the maximum.
+__global__ void __launch_bounds__(128, 5)
+cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
+                 const double *__restrict__ P, int64_t np, int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties,
+                 int32_t *__restrict__ counters /* [0] walk entries, [1] heavy, [2] search entries, [3] next search entry */,
+                 double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
+                 int32_t *__restrict__ heavy, int search_budget)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1;
+	const int n_todo = counters[2];
+	Packet k;
+	int32_t ties[PK_TIES];
+	int32_t lst[K2_STACK];
+	int sp = 0, budget = 0;
+	int64_t i = -1;
+	int32_t bf0 = -1;
+	float plx = 0, ply = 0, plz = 0, phx = 0, phy = 0, phz = 0;
+	bool active = false, exhausted = false;
+	k.p = {0, 0, 0}; k.best = 0; k.best_hi = 0; k.bf = -1; k.bc = {0, 0, 0}; k.near = 0; k.nt = 0;
+	for (;;) {
+		// ---- fetch ----
+		const unsigned need = __ballot_sync(0xffffffffu, !active && !exhausted);
+		if (need) {
+			int base = 0;
+			if (lane == __ffs(need) - 1) base = atomicAdd(counters + 3, __popc(need));
+			base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+			if (!active && !exhausted) {
+				const int t = base + __popc(need & lt);
+				if (t < n_todo) {
+					i = todo[2 * np - 1 - t];
+					k.p = ld3(P + 3 * i);
+					bf0 = I[i];
+					k.best = S[i];
+					if (bf0 >= 0) k.best = k.best + k.best * PK_EPS_TIE * 4;   // still an upper bound; lets bf0 itself pass 'd < best'
+					k.best_hi = __double2float_ru(k.best);
+					k.bf = -1; k.near = 0; k.nt = 0;
+					plx = __double2float_rd(k.p.x); ply = __double2float_rd(k.p.y); plz = __double2float_rd(k.p.z);
+					phx = __double2float_ru(k.p.x); phy = __double2float_ru(k.p.y); phz = __double2float_ru(k.p.z);
+					sp = 0; lst[sp++] = root; budget = search_budget;
+					active = true;
 				} else {
-					if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
-					if (d1 <= k.best_hi) lst[sp++] = c1;
+					exhausted = true;
 				}
 			}
-			if (give_up && k.bf < 0) { k.best = S[i]; k.bf = bf0; }      // nothing better met before the budget ran out
 		}
-		Hit h;
-		h.sqr_d = k.best; h.f = k.bf; h.c = k.bc;
-		if (!give_up && k.near > 1) {
-			int32_t win = -1;
-			if (k.nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, k.p, k.best, k.bf, ties, 1, k.nt);
-			if (win >= 0) {
-				if (win != k.bf) { const double *tt = tri + 9 * (int64_t)win; h.f = win; h.c = closest_on_triangle(k.p, ld3(tt), ld3(tt + 3), ld3(tt + 6)); }
-			} else {
-				give_up = !traverse_limited(nodes, root, tri, k.p, k.best + k.best * PK_EPS_WALK, k.best, walk_budget, h);
+		if (!__any_sync(0xffffffffu, active)) break;
+		// ---- one node visit ----
+		bool give_up = false;
+		if (active && sp > 0) {
+			const QNodeF *n = fnodes + lst[--sp];
+			const float dl = box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz);
+			const float dr = box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz);
+			if (dl <= k.best_hi || dr <= k.best_hi) {
+				if (--budget < 0 || sp + 2 > K2_STACK) give_up = true;
+				else {
+					const bool left_first = dl < dr || dl == 0.f;
+					const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
+					const float d1 = left_first ? dl : dr, d2 = left_first ? dr : dl;
+					if (c1 < 0) {
+						if (d1 <= k.best_hi) lane_leaf(tri, ~c1, k, ties);
+						if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
+					} else {
+						if (d2 <= k.best_hi) { if (c2 < 0) lane_leaf(tri, ~c2, k, ties); else lst[sp++] = c2; }
+						if (d1 <= k.best_hi) lst[sp++] = c1;
+					}
+				}
 			}
 		}
-		if (give_up) {
-			S[i] = k.best;                                   // still a valid upper bound for K3
-			heavy[atomicAdd(heavy_count, 1)] = (int32_t)i;
-		} else {
-			I[i] = h.f;
-			C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z;
-			S[i] = h.sqr_d;
+		// ---- retire ----
+		const bool finished = active && (give_up || sp == 0);
+		const unsigned mh = __ballot_sync(0xffffffffu, finished && give_up);
+		const unsigned mw = __ballot_sync(0xffffffffu, finished && !give_up && k.near > 1);
+		if (mh | mw) {
+			int bh = 0, bw = 0;
+			if (lane == 0) { if (mh) bh = atomicAdd(counters + 1, __popc(mh)); if (mw) bw = atomicAdd(counters, __popc(mw)); }
+			bh = __shfl_sync(0xffffffffu, bh, 0); bw = __shfl_sync(0xffffffffu, bw, 0);
+			if (finished && give_up) heavy[bh + __popc(mh & lt)] = (int32_t)i;
+			else if (finished && k.near > 1) {
+				const int slot = bw + __popc(mw & lt);          // the walk list grows from the front, we consume from the back
+				todo[slot] = (int32_t)i;
+				int32_t *tr = todo_ties + 4 * (int64_t)slot;
+				tr[0] = k.nt;
+				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < k.nt ? ties[j] : -1;
+			}
+		}
+		if (finished) {
+			if (k.bf >= 0) {                                 // (a give-up before any facet was met keeps K1's upper bound)
+				I[i] = k.bf;
+				C[3 * i] = k.bc.x; C[3 * i + 1] = k.bc.y; C[3 * i + 2] = k.bc.z;
+				S[i] = k.best;
+			}
+			active = false;
 		}
 	}
 }
@@ -702,8 +771,8 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
 		if (!S) { tmpS.alloc(np, s); S = tmpS.p; }
 		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
-		DevBuf<int32_t> todo(np, s), todo_ties(4 * np, s), heavy(np, s), cnt(2, s);
-		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int32_t), s));
+		DevBuf<int32_t> todo(2 * np, s), todo_ties(4 * np, s), heavy(np, s), cnt(4, s);   // cnt: walk entries, heavy, search entries
+		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int32_t), s));
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
 		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
 		static const int minb = getenv("FPOHM_K1_MINB") ? atoi(getenv("FPOHM_K1_MINB")) : 7;
@@ -713,7 +782,9 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 		else if (minb == 5) cp_packet_kernel<false, 5><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
 		else cp_packet_kernel<false, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_lane_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qfnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, cnt.p + 1, k2_search, k2_walk);
+		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, k2_search);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, k2_walk);
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, heavy.p, cnt.p + 1, S, I, C);
 	} else {

@@ -6,5 +6,5 @@ import csv
 rows=[r for r in csv.reader(open("gpurun_out/cp_launch.csv")) if len(r)>5]
 h=rows[0]; k=h.index("Kernel Name"); v=h.index("Metric Value")
 for j in (0,8,16,24,32):
-  print([ (r[k].split("(")[0][-16:], round(float(r[v])/1e6,3)) for r in rows[1+3*j:4+3*j]])
+  print([ (r[k].split("(")[0][-16:], round(float(r[v])/1e6,3)) for r in rows[1+4*j:5+4*j]])
 PY
