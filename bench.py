@@ -229,6 +229,7 @@ def main():
         evs[k + 1].record(stream)
     barrier()
     launches = ctx.launch_count() - l0
+    packet_ms = ctx.query_kernel_ms(min(args.steps, 32))   # CUDA events around the dominant kernel of the timed steps
     total_ms = evs[0].elapsed_time(evs[-1])
     kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -327,7 +328,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k_ms = float(np.mean(kernel_ms))
-        achieved = BYTES_PER_QUERY * Q / (k_ms * 1e-3) / 1e9
+        achieved = BYTES_PER_QUERY * Q / (packet_ms * 1e-3) / 1e9
         traffic = None
         tf = ROOT / "profiles" / "closest_point_traffic.json"
         if tf.exists():
@@ -343,9 +344,12 @@ def main():
                            "queries_per_gpu": int(Q), "tris": int(len(F)), "leaves": int(sizes["leaves"]), "cells": int(sizes["cells"]),
                            "nodes": int(sizes["nodes"]), "l2_policy": "inputs+outputs per step (%.0f MB) larger than L2 (126 MB)" % (BYTES_PER_QUERY * Q / 1e6),
                            "sharding": "query range per rank, mesh+tree replicated, no data-path collective"},
-                "roofline": {"bound": "hbm", "kernel": "closest_point_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "cp_packet_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "note": "84 B/query algorithmic; BVH traversal is L2/latency/fp64-ALU bound by nature (SURVEY.md §7.3 H5)"},
+                             "kernel_ms": packet_ms, "kernel_share_of_step": packet_ms / k_ms,
+                             "note": "84 B/query algorithmic over the packet-walk kernel's own duration (CUDA events inside the library, "
+                                     "fpohm_ctx_query_kernel_ms); the walk is instruction-issue bound (70 % of issue slots, DRAM < 2 %), "
+                                     "see profiles/r01_ncu_summary.md"},
                 "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 24 * Q, "d2h_bytes_per_step": 60 * Q},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),

@@ -80,6 +80,11 @@ class Context:
         _chk(lib().fpohm_ctx_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def query_kernel_ms(self, last_n: int = 1) -> float:
+        ms = C.c_double()
+        _chk(lib().fpohm_ctx_query_kernel_ms(self.h, C.c_int32(last_n), C.byref(ms)))
+        return ms.value
+
     def launch_count(self) -> int:
         n = C.c_int64()
         _chk(lib().fpohm_ctx_launch_count(self.h, C.byref(n)))

@@ -775,12 +775,12 @@ void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const d
 		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int32_t), s));
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
 		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
-		static const int minb = getenv("FPOHM_K1_MINB") ? atoi(getenv("FPOHM_K1_MINB")) : 7;
+		const int qslot = (int)(ctx->q_launches % fpohm_ctx::QRING);
+		FPOHM_CUDA(cudaEventRecord(ctx->q_ev0[qslot], s));
 		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
-		else if (minb == 6) cp_packet_kernel<false, 6><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
-		else if (minb == 7) cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
-		else if (minb == 5) cp_packet_kernel<false, 5><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
-		else cp_packet_kernel<false, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		else cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		FPOHM_CUDA(cudaEventRecord(ctx->q_ev1[qslot], s));
+		ctx->q_launches++;
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, k2_search);
 		FPOHM_LAUNCH_CHECK(ctx);

@@ -1,5 +1,6 @@
 // Context, error reporting, library identity.
 #include "internal.h"
+#include <algorithm>
 
 namespace fpohm {
 static thread_local std::string g_err;
@@ -44,6 +45,7 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[0], cudaStreamNonBlocking));
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[1], cudaStreamNonBlocking));
 	FPOHM_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
+	for (int k = 0; k < fpohm_ctx::QRING; ++k) { FPOHM_CUDA(cudaEventCreate(&c->q_ev0[k])); FPOHM_CUDA(cudaEventCreate(&c->q_ev1[k])); }
 	FPOHM_CUDA(cudaEventCreate(&c->ev0));
 	FPOHM_CUDA(cudaEventCreate(&c->ev1));
 	// keep freed blocks in the stream-ordered pool: the pipeline calls these entry points in loops
@@ -60,6 +62,7 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	if (!ctx) return;
 	DeviceGuard g(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	for (int k = 0; k < fpohm_ctx::QRING; ++k) { cudaEventDestroy(ctx->q_ev0[k]); cudaEventDestroy(ctx->q_ev1[k]); }
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->aux[0]);
@@ -81,6 +84,24 @@ int fpohm_ctx_last_kernel_ms(fpohm_ctx *ctx, double *ms) {
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(ctx && ms, FPOHM_EINVAL, "fpohm_ctx_last_kernel_ms: null argument");
 	*ms = ctx->last_ms;
+	FPOHM_API_END
+}
+
+int fpohm_ctx_query_kernel_ms(fpohm_ctx *ctx, int32_t last_n, double *mean_ms) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && mean_ms && last_n > 0, FPOHM_EINVAL, "fpohm_ctx_query_kernel_ms: bad argument");
+	DeviceGuard g(ctx->device);
+	const int64_t have = std::min<int64_t>(std::min<int64_t>(ctx->q_launches, fpohm_ctx::QRING), last_n);
+	FPOHM_REQUIRE(have > 0, FPOHM_ESTATE, "fpohm_ctx_query_kernel_ms: no query launched on this context yet");
+	double sum = 0;
+	for (int64_t k = 0; k < have; ++k) {
+		const int slot = (int)((ctx->q_launches - 1 - k) % fpohm_ctx::QRING);
+		FPOHM_CUDA(cudaEventSynchronize(ctx->q_ev1[slot]));
+		float ms = 0;
+		FPOHM_CUDA(cudaEventElapsedTime(&ms, ctx->q_ev0[slot], ctx->q_ev1[slot]));
+		sum += ms;
+	}
+	*mean_ms = sum / (double)have;
 	FPOHM_API_END
 }
 

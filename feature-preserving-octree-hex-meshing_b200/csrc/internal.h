@@ -86,6 +86,10 @@ struct fpohm_ctx {
 	cudaStream_t aux[2] = {nullptr, nullptr};   // copy/compute pipelining of the host-pointer entry points
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
 	double last_ms = 0;
+	// CUDA-event ring around the dominant query kernel (packet walk) of the last resident/host query launches
+	static constexpr int QRING = 32;
+	cudaEvent_t q_ev0[QRING] = {}, q_ev1[QRING] = {};
+	int64_t q_launches = 0;
 	int64_t launches = 0;
 };
 

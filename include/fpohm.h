@@ -54,6 +54,9 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx);
 int  fpohm_ctx_sync(fpohm_ctx *ctx);
 /* milliseconds of the kernels launched by the last host-pointer call on this ctx (CUDA events) */
 int  fpohm_ctx_last_kernel_ms(fpohm_ctx *ctx, double *ms);
+/* mean duration (CUDA events on the launching stream) of the dominant query kernel — the packet walk — over the last
+ * `last_n` (<= 32) query launches on this ctx; synchronises on those launches.  bench.py's roofline numerator. */
+int  fpohm_ctx_query_kernel_ms(fpohm_ctx *ctx, int32_t last_n, double *mean_ms);
 /* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
 int  fpohm_ctx_launch_count(fpohm_ctx *ctx, int64_t *n);
 
