@@ -749,53 +749,67 @@ pseudonormal_kernel(const double *__restrict__ V, const int32_t *__restrict__ F,
 
 namespace fpohm {
 
-void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
-                          double *S, int32_t *I, double *C, double *N, cudaStream_t s)
+// Scratch of one query launch (stream-ordered allocations, released when the launch has been queued).
+struct QueryScratch {
+	DevBuf<int32_t> tmpI, todo, todo_ties, heavy, cnt;
+	DevBuf<double> tmpC, tmpS;
+};
+
+static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
+                                    double *S, int32_t *I, double *C, double *N, cudaStream_t s, QueryScratch &q)
 {
 	if (np <= 0) return;
 	const int blk = 128;
 	const int grid = grid_for(ctx, np, blk, 16);
-	static const bool stats = getenv("FPOHM_CP_STATS") != nullptr;   // debug only: N[:,0:2] := (node visits, leaf tests)
+	static const bool stats = getenv("FPOHM_CP_STATS") != nullptr;   // debug only: N := traversal counters
 	// the sign pass needs facet + closest point even when the caller did not ask for them
-	DevBuf<int32_t> tmpI; DevBuf<double> tmpC, tmpS;
 	if (with_sign) {
-		if (!I) { tmpI.alloc(np, s); I = tmpI.p; }
-		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
-		if (!S && N) { tmpS.alloc(np, s); S = tmpS.p; }
+		if (!I) { q.tmpI.alloc(np, s); I = q.tmpI.p; }
+		if (!C) { q.tmpC.alloc(3 * np, s); C = q.tmpC.p; }
+		if (!S && N) { q.tmpS.alloc(np, s); S = q.tmpS.p; }
 	}
 	static const int mode = getenv("FPOHM_CP_MODE") ? atoi(getenv("FPOHM_CP_MODE")) : 1;   // debug A/B: 0 = per-lane igl order only
+	cudaStream_t sc = s;   // (completion kernels run on the same stream)
 	if (mode == 1 && m->qroot >= 0) {
 		FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "closest point: %lld queries in one launch", (long long)np);
-		// K1/K2/K3 hand unfinished queries on through S/I/C, so all three must exist
-		if (!I) { tmpI.alloc(np, s); I = tmpI.p; }
-		if (!C) { tmpC.alloc(3 * np, s); C = tmpC.p; }
-		if (!S) { tmpS.alloc(np, s); S = tmpS.p; }
+		// the kernels hand unfinished queries on through S/I/C, so all three must exist
+		if (!I) { q.tmpI.alloc(np, s); I = q.tmpI.p; }
+		if (!C) { q.tmpC.alloc(3 * np, s); C = q.tmpC.p; }
+		if (!S) { q.tmpS.alloc(np, s); S = q.tmpS.p; }
 		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
-		DevBuf<int32_t> todo(2 * np, s), todo_ties(4 * np, s), heavy(np, s), cnt(4, s);   // cnt: walk entries, heavy, search entries
-		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int32_t), s));
+		q.todo.alloc(2 * np, s); q.todo_ties.alloc(4 * np, s); q.heavy.alloc(np, s);
+		q.cnt.alloc(4, s);                                 // walk entries, heavy entries, search entries, next search entry
+		FPOHM_CUDA(cudaMemsetAsync(q.cnt.p, 0, 4 * sizeof(int32_t), s));
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
 		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
 		const int qslot = (int)(ctx->q_launches % fpohm_ctx::QRING);
 		FPOHM_CUDA(cudaEventRecord(ctx->q_ev0[qslot], s));
-		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
-		else cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, todo.p, todo_ties.p, cnt.p);
+		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p);
+		else cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p);
 		FPOHM_CUDA(cudaEventRecord(ctx->q_ev1[qslot], s));
 		ctx->q_launches++;
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, k2_search);
+		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, sc>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, todo.p, todo_ties.p, cnt.p, S, I, C, heavy.p, k2_walk);
+		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, heavy.p, cnt.p + 1, S, I, C);
+		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C);
 	} else {
 		if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 		else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	if (with_sign && (S || N)) {
-		pseudonormal_kernel<<<grid, blk, 0, s>>>(m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, I, C, S, N, !stats);
+		pseudonormal_kernel<<<grid, blk, 0, sc>>>(m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, P_dev, np, I, C, S, N, !stats);
 		FPOHM_LAUNCH_CHECK(ctx);
 	}
+}
+
+void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
+                          double *S, int32_t *I, double *C, double *N, cudaStream_t s)
+{
+	QueryScratch q;
+	launch_closest_point_ex(ctx, m, with_sign, P_dev, np, S, I, C, N, s, q);
 }
 
 } // namespace fpohm
@@ -814,10 +828,11 @@ int fpohm_signed_distance_dev(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P_
 	FPOHM_API_END
 }
 
-// Host-pointer path.  Queries are independent, so the batch is cut into chunks that rotate over three streams:
-// chunk k+1 is on its way up (H2D) while chunk k computes and chunk k-1 is on its way down (D2H).  With pinned caller
-// buffers the PCIe copies (84 B/query) hide behind the traversal; with pageable memory CUDA stages the copies and the
-// pipeline degrades gracefully to the serial order.
+// Host-pointer path.  Queries are independent, so the batch is cut into chunks: an upload stream runs ahead with every
+// H2D copy, two compute streams alternate over the chunks (the tail of one chunk's kernels overlaps the start of the
+// next), a download stream trails with the D2H copies; per-chunk events order the three.  With pinned caller buffers the
+// PCIe copies (84 B/query, 55 GB/s each way) hide behind the search; with pageable memory CUDA stages the copies and
+// the pipeline degrades gracefully to the serial order.
 static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const double *P, int64_t np,
                       double *S, int32_t *I, double *C, double *N, const char *who)
 {
@@ -831,26 +846,44 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	DevBuf<double> dP(3 * np, s), dS(S ? np : 0, s), dC(C ? 3 * np : 0, s), dN(N ? 3 * np : 0, s);
 	DevBuf<int32_t> dI(I ? np : 0, s);
 	KernelTimer t(ctx, s);
+	static const int64_t chunk = getenv("FPOHM_CP_CHUNK") ? atoll(getenv("FPOHM_CP_CHUNK")) : (1 << 19);
+	static const int n_comp = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 2;
+	const int64_t n_chunks = (np + chunk - 1) / chunk;
+	while ((int64_t)ctx->ev_pool.size() < 2 * n_chunks) {
+		cudaEvent_t e;
+		FPOHM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		ctx->ev_pool.push_back(e);
+	}
+	cudaStream_t up = ctx->aux[0], down = ctx->aux[1];
+	cudaStream_t comp[2] = {s, ctx->aux[2]};
 	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, s));              // allocations are ordered on s
-	cudaStream_t lanes[3] = {s, ctx->aux[0], ctx->aux[1]};
-	for (int k = 1; k < 3; ++k) FPOHM_CUDA(cudaStreamWaitEvent(lanes[k], ctx->ev_sync, 0));
-	const int64_t chunk = 1 << 19;
-	int k = 0;
-	for (int64_t o = 0; o < np; o += chunk, ++k) {
-		const int64_t n = std::min(chunk, np - o);
-		cudaStream_t ls = lanes[k % 3];
-		FPOHM_CUDA(cudaMemcpyAsync(dP.p + 3 * o, P + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, ls));
+	FPOHM_CUDA(cudaStreamWaitEvent(up, ctx->ev_sync, 0));
+	FPOHM_CUDA(cudaStreamWaitEvent(down, ctx->ev_sync, 0));
+	FPOHM_CUDA(cudaStreamWaitEvent(comp[1], ctx->ev_sync, 0));
+	// every upload is queued at once on its own stream: the copy engine runs ahead of the kernels
+	for (int64_t k = 0; k < n_chunks; ++k) {
+		const int64_t o = k * chunk, n = std::min(chunk, np - o);
+		FPOHM_CUDA(cudaMemcpyAsync(dP.p + 3 * o, P + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, up));
+		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k)], up));
+	}
+	for (int64_t k = 0; k < n_chunks; ++k) {
+		const int64_t o = k * chunk, n = std::min(chunk, np - o);
+		cudaStream_t cs = comp[n_comp > 1 ? k & 1 : 0];
+		FPOHM_CUDA(cudaStreamWaitEvent(cs, ctx->ev_pool[(size_t)(2 * k)], 0));
 		launch_closest_point(ctx, mesh, with_sign, dP.p + 3 * o, n, S ? dS.p + o : nullptr, I ? dI.p + o : nullptr,
-		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, ls);
-		if (S) FPOHM_CUDA(cudaMemcpyAsync(S + o, dS.p + o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ls));
-		if (I) FPOHM_CUDA(cudaMemcpyAsync(I + o, dI.p + o, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ls));
-		if (C) FPOHM_CUDA(cudaMemcpyAsync(C + 3 * o, dC.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ls));
-		if (N) FPOHM_CUDA(cudaMemcpyAsync(N + 3 * o, dN.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ls));
+		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs);
+		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k + 1)], cs));
+		FPOHM_CUDA(cudaStreamWaitEvent(down, ctx->ev_pool[(size_t)(2 * k + 1)], 0));
+		if (S) FPOHM_CUDA(cudaMemcpyAsync(S + o, dS.p + o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, down));
+		if (I) FPOHM_CUDA(cudaMemcpyAsync(I + o, dI.p + o, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, down));
+		if (C) FPOHM_CUDA(cudaMemcpyAsync(C + 3 * o, dC.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, down));
+		if (N) FPOHM_CUDA(cudaMemcpyAsync(N + 3 * o, dN.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, down));
 	}
-	for (int j = 1; j < 3; ++j) {                             // join the side lanes back into s before the buffers die
-		FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, lanes[j]));
-		FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
-	}
+	// join everything back into s before the buffers die
+	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, down));
+	FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
+	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, comp[1]));
+	FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
 	t.stop();
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 	FPOHM_API_END
