@@ -344,6 +344,32 @@ __device__ __forceinline__ int32_t igl_tie_winner(const QNode *__restrict__ node
 #define TODO_SEARCH 2    /* S holds an upper bound (or +inf): search not finished */
 
 // ---- K1 ---------------------------------------------------------------------------------------------------------
+// Register diet (ncu: at 72 registers the first version re-loaded five spilled query coordinates from local memory in
+// EVERY node step and fetched the node with twelve 4-byte loads): the node step only needs the query as three floats
+// and one threshold, so the fp64 query and the running minimum live in global / shared memory and are read in the leaf
+// steps only (2.5x rarer).  Filter for a query p, pf = float(p), delta >= |p - pf|: the exact distance D to anything in
+// the box obeys D >= D_f - delta with D_f = dist(pf, box_f); so D^2 <= best implies D_f^2 <= (sqrt(best) + delta)^2 =: thr.
+// D_f^2 is evaluated rounded down, thr rounded up and widened by 2^-19.
+struct NodeBoxes { float4 a, b, c; int32_t left, right; };
+__device__ __forceinline__ NodeBoxes load_node(const QNodeF *__restrict__ n) {
+	const float4 *q = reinterpret_cast<const float4 *>(n);
+	NodeBoxes r;
+	r.a = __ldg(q); r.b = __ldg(q + 1); r.c = __ldg(q + 2);
+	const int2 lr = __ldg(reinterpret_cast<const int2 *>(q + 3));
+	r.left = lr.x; r.right = lr.y;
+	return r;
+}
+__device__ __forceinline__ float gap2_low(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float px, float py, float pz) {
+	const float gx = fmaxf(fmaxf(__fsub_rd(mnx, px), __fsub_rd(px, mxx)), 0.f);
+	const float gy = fmaxf(fmaxf(__fsub_rd(mny, py), __fsub_rd(py, mxy)), 0.f);
+	const float gz = fmaxf(fmaxf(__fsub_rd(mnz, pz), __fsub_rd(pz, mxz)), 0.f);
+	return __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
+}
+__device__ __forceinline__ float filter_threshold(double best, float delta) {
+	const float r = __fadd_ru(__fsqrt_ru(__double2float_ru(best)), delta);
+	return __fmul_ru(__fmul_ru(r, r), 1.0000020f);      // (sqrt(best) + delta)^2, up, widened by 2^-19
+}
+
 template <bool STATS, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
@@ -353,33 +379,60 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 {
 	__shared__ int32_t s_stack[4][PK_STACK];
 	__shared__ int32_t s_tie[4][PK_TIES][32];
+	__shared__ double s_best[4][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int32_t *stk = s_stack[warp];
 	int32_t *ties = &s_tie[warp][0][lane];
+	double *bestp = &s_best[warp][lane];
 	const int64_t nwarps = (int64_t)gridDim.x * 4;
 	for (int64_t w = blockIdx.x * 4ll + warp; w * 32 < np; w += nwarps) {
 		const int64_t i = w * 32 + lane;
 		const bool valid = i < np;
-		Packet k;
-		k.p = {0, 0, 0};
-		if (valid) k.p = ld3(P + 3 * i);
-		k.best = valid ? CUDART_INF : -1.0;            // an idle lane never wants a node (bounds are >= 0)
-		k.best_hi = valid ? CUDART_INF_F : -1.f;
-		k.bf = -1; k.bc = {0, 0, 0}; k.near = 0; k.nt = 0;
-		const float plx = __double2float_rd(k.p.x), ply = __double2float_rd(k.p.y), plz = __double2float_rd(k.p.z);
-		const float phx = __double2float_ru(k.p.x), phy = __double2float_ru(k.p.y), phz = __double2float_ru(k.p.z);
+		const double *pp = P + 3 * (valid ? i : 0);
+		float pfx = 0, pfy = 0, pfz = 0, delta = 0;
+		{
+			const V3 p = ld3(pp);
+			pfx = (float)p.x; pfy = (float)p.y; pfz = (float)p.z;
+			const double ex = p.x - (double)pfx, ey = p.y - (double)pfy, ez = p.z - (double)pfz;
+			delta = __double2float_ru(sqrt(ex * ex + ey * ey + ez * ez) * 1.0000001);
+		}
+		*bestp = CUDART_INF;
+		float thr = valid ? CUDART_INF_F : -1.f;        // an idle lane never wants a node (bounds are >= 0)
+		int32_t bf = -1;
+		int near = 0, nt = 0;
 		int visits = 0, window = 0, leaf_steps = 0;
 		int top = 0;
 		bool bail = false;
 		stk[top++] = root;                              // every lane writes the same value: no synchronisation needed
 		long long t0 = 0;
 		if (STATS) t0 = clock64();
+		// exact evaluation of one (warp-uniform) leaf by the lanes whose filter passed
+		auto leaf = [&](int32_t prim, bool want) {
+			const double *t = tri + 9 * (int64_t)prim;
+			const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
+			if (want) {
+				const V3 p = ld3(pp);
+				const V3 q = closest_on_triangle(p, a, b, c);
+				const double d = sqnorm(sub(p, q));
+				const double best = *bestp;
+				if (d < best) {
+					near = (d + d * PK_EPS_TIE < best) ? 1 : near + 1;
+					nt = 0; bf = prim;
+					*bestp = d;
+					thr = filter_threshold(d, delta);
+				} else if (d <= best + best * PK_EPS_TIE) {
+					++near;
+					if (d == best) { if (nt < PK_TIES) ties[32 * nt] = prim; ++nt; }
+				}
+			}
+			if (STATS) ++leaf_steps;
+		};
 		while (top > 0) {
 			const int32_t cur = stk[--top];
-			const QNodeF *n = fnodes + cur;
-			const float dl = box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz);
-			const float dr = box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz);
-			const bool wl = dl <= k.best_hi, wr = dr <= k.best_hi;
+			const NodeBoxes nb = load_node(fnodes + cur);
+			const float dl = gap2_low(nb.a.x, nb.a.y, nb.a.z, nb.a.w, nb.b.x, nb.b.y, pfx, pfy, pfz);
+			const float dr = gap2_low(nb.b.z, nb.b.w, nb.c.x, nb.c.y, nb.c.z, nb.c.w, pfx, pfy, pfz);
+			const bool wl = dl <= thr, wr = dr <= thr;
 			const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
 			if (!(ml | mr)) continue;
 			if ((visits & (PK_WINDOW - 1)) == PK_WINDOW - 1) {
@@ -392,20 +445,20 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			// nearer child first: majority vote of the lanes that still want this node
 			const unsigned near_l = __ballot_sync(0xffffffffu, (wl || wr) && (dl < dr || dl == 0.f));
 			const bool left_first = 2 * __popc(near_l) >= __popc(ml | mr);
-			const int32_t c1 = left_first ? n->left : n->right, c2 = left_first ? n->right : n->left;
+			const int32_t c1 = left_first ? nb.left : nb.right, c2 = left_first ? nb.right : nb.left;
 			const float d2 = left_first ? dr : dl;
 			const bool w1 = left_first ? wl : wr;
 			const unsigned m1 = left_first ? ml : mr, m2 = left_first ? mr : ml;
 			if (c1 < 0) {
-				if (m1) { packet_leaf(tri, ~c1, w1, k, ties); if (STATS) ++leaf_steps; }
-				const unsigned m2b = __ballot_sync(0xffffffffu, d2 <= k.best_hi);       // the bound may have dropped
+				if (m1) leaf(~c1, w1);
+				const unsigned m2b = __ballot_sync(0xffffffffu, d2 <= thr);       // the bound may have dropped
 				if (m2b) {
-					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k, ties); if (STATS) ++leaf_steps; }
+					if (c2 < 0) leaf(~c2, d2 <= thr);
 					else stk[top++] = c2;
 				}
 			} else {
 				if (m2) {
-					if (c2 < 0) { packet_leaf(tri, ~c2, d2 <= k.best_hi, k, ties); if (STATS) ++leaf_steps; }
+					if (c2 < 0) leaf(~c2, d2 <= thr);
 					else stk[top++] = c2;
 				}
 				if (m1) stk[top++] = c1;
@@ -415,17 +468,18 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 		bool unfinished = false;
 		if (bail) {
 			for (int j = 0; j < top; ++j) {
-				const QNodeF *n = fnodes + stk[j];
-				unfinished |= box_low(n->lmin, n->lmax, plx, ply, plz, phx, phy, phz) <= k.best_hi ||
-				              box_low(n->rmin, n->rmax, plx, ply, plz, phx, phy, phz) <= k.best_hi;
+				const NodeBoxes nb = load_node(fnodes + stk[j]);
+				unfinished |= gap2_low(nb.a.x, nb.a.y, nb.a.z, nb.a.w, nb.b.x, nb.b.y, pfx, pfy, pfz) <= thr ||
+				              gap2_low(nb.b.z, nb.b.w, nb.c.x, nb.c.y, nb.c.z, nb.c.w, pfx, pfy, pfz) <= thr;
 			}
 		}
-		const int code = !valid ? 0 : (unfinished ? TODO_SEARCH : (k.near > 1 ? TODO_WALK : 0));
+		const int code = !valid ? 0 : (unfinished ? TODO_SEARCH : (near > 1 ? TODO_WALK : 0));
 		if (valid) {
-			if (k.bf >= 0) { const double *t = tri + 9 * (int64_t)k.bf; k.bc = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6)); }
-			I[i] = k.bf;
-			C[3 * i] = k.bc.x; C[3 * i + 1] = k.bc.y; C[3 * i + 2] = k.bc.z;
-			S[i] = k.best;
+			V3 bc = {0, 0, 0};
+			if (bf >= 0) { const double *t = tri + 9 * (int64_t)bf; bc = closest_on_triangle(ld3(pp), ld3(t), ld3(t + 3), ld3(t + 6)); }
+			I[i] = bf;
+			C[3 * i] = bc.x; C[3 * i + 1] = bc.y; C[3 * i + 2] = bc.z;
+			S[i] = *bestp;
 		}
 		// warp-aggregated append to the work lists (tie-breaks grow from the front of `todo`, unfinished searches from
 		// the back, so that each completion kernel gets warps full of one kind of work)
@@ -439,13 +493,14 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 				const int slot = bw + __popc(mw & lt);
 				todo[slot] = (int32_t)i;
 				int32_t *tr = todo_ties + 4 * (int64_t)slot;
-				tr[0] = k.nt;
-				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < k.nt ? ties[32 * j] : -1;
+				tr[0] = nt;
+				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? ties[32 * j] : -1;
 			} else if (code == TODO_SEARCH) {
 				todo[2 * np - 1 - (bs + __popc(ms & lt))] = (int32_t)i;
 			}
 		}
 		if (STATS && N && valid) { N[3 * i] = visits + 65536.0 * leaf_steps; N[3 * i + 1] = (double)(clock64() - t0); N[3 * i + 2] = code; }
+		__syncwarp();
 	}
 }
 
