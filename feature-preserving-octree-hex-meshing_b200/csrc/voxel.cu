@@ -156,34 +156,58 @@ __device__ __forceinline__ void append_hit(const ColumnGrid &g, int x, int y, do
 
 // Rectangle of columns per facet.  Facets covering at most RECT_INLINE columns (the common case on fine meshes) are
 // finished right here; larger ones are left to the load-balanced pair kernel through cnt[]/rect[].
+// The small rectangles of a warp's 32 facets are pooled: a warp prefix sum over the pair counts, then the lanes take
+// the (facet, column) pairs 32 at a time whatever facet they belong to.  (ncu on the first version, where each lane
+// looped over its own facet's columns: 8.8 of 32 lanes active, 154 M warp instructions, 0.29 of the 0.77 ms at 1024^3.)
 #define RECT_INLINE 16
 __global__ void __launch_bounds__(256)
 facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ rect, int64_t *__restrict__ cnt,
                   double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag,
                   int32_t *__restrict__ hit_ev, double oz, int nz)
 {
-	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f <= nF; f += (int64_t)gridDim.x * blockDim.x) {
-		if (f == nF) { cnt[f] = 0; continue; }
-		const double *t = tri + 9 * f;
-		const double xmin = fmin(t[0], fmin(t[3], t[6])), xmax = fmax(t[0], fmax(t[3], t[6]));
-		const double ymin = fmin(t[1], fmin(t[4], t[7])), ymax = fmax(t[1], fmax(t[4], t[7]));
-		const int x0 = first_center_ge(xmin, g.ox, g.spacing, g.nx), x1 = last_center_le(xmax, g.ox, g.spacing, g.nx);
-		const int y0 = first_center_ge(ymin, g.oy, g.spacing, g.ny), y1 = last_center_le(ymax, g.oy, g.spacing, g.ny);
-		const int w = x1 - x0 + 1, h = y1 - y0 + 1;
-		const int64_t n = (w > 0 && h > 0) ? (int64_t)w * h : 0;
-		if (n <= RECT_INLINE) {
-			for (int y = y0; y <= y1; ++y)
-				for (int x = x0; x <= x1; ++x) {
-					const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
-					double z;
-					const int s = intersect_ray_z(t, cx, cy, z);
-					if (s) append_hit(g, x, y, z, s, hit_z, hit_s, hit_n, overflow_flag, hit_ev, oz, nz);
-				}
-			rect[f] = make_int4(0, 0, 0, 0);
-			cnt[f] = 0;
-		} else {
-			rect[f] = make_int4(x0, y0, w, h);
-			cnt[f] = n;
+	const int lane = threadIdx.x & 31;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base <= nF; base += stride) {   // warp-uniform trip count
+		const int64_t f = base + lane;
+		int x0 = 0, y0 = 0, w = 0, n_small = 0;
+		if (f == nF) cnt[f] = 0;
+		if (f < nF) {
+			const double *t = tri + 9 * f;
+			const double xmin = fmin(t[0], fmin(t[3], t[6])), xmax = fmax(t[0], fmax(t[3], t[6]));
+			const double ymin = fmin(t[1], fmin(t[4], t[7])), ymax = fmax(t[1], fmax(t[4], t[7]));
+			x0 = first_center_ge(xmin, g.ox, g.spacing, g.nx);
+			y0 = first_center_ge(ymin, g.oy, g.spacing, g.ny);
+			const int x1 = last_center_le(xmax, g.ox, g.spacing, g.nx), y1 = last_center_le(ymax, g.oy, g.spacing, g.ny);
+			w = x1 - x0 + 1;
+			const int h = y1 - y0 + 1;
+			const int64_t n = (w > 0 && h > 0) ? (int64_t)w * h : 0;
+			if (n <= RECT_INLINE) { n_small = (int)n; rect[f] = make_int4(0, 0, 0, 0); cnt[f] = 0; }
+			else { rect[f] = make_int4(x0, y0, w, h); cnt[f] = n; }
+		}
+		// exclusive prefix sum of the small pair counts over the warp
+		int incl = n_small;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		const int excl = incl - n_small;
+		const int total = __shfl_sync(0xffffffffu, incl, 31);
+		for (int p0 = 0; p0 < total; p0 += 32) {
+			const int p = p0 + lane;
+			int src = 0;                                    // largest lane with excl <= p
+#pragma unroll
+			for (int step = 16; step > 0; step >>= 1) {
+				const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
+				if (src + step < 32 && e <= p) src += step;
+			}
+			const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+			const int sw = __shfl_sync(0xffffffffu, w, src), se = __shfl_sync(0xffffffffu, excl, src);
+			if (p < total) {
+				const int k = p - se;
+				const int x = sx0 + k % sw, y = sy0 + k / sw;
+				const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
+				double z;
+				const int sgn = intersect_ray_z(tri + 9 * (base + src), cx, cy, z);
+				if (sgn) append_hit(g, x, y, z, sgn, hit_z, hit_s, hit_n, overflow_flag, hit_ev, oz, nz);
+			}
 		}
 	}
 }
@@ -280,7 +304,7 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ h
 	}
 }
 
-#define FILL_CH 2      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
+#define FILL_CH 4      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
                   const uint32_t *__restrict__ sum, uint8_t *__restrict__ out, int zc_begin, int zc_end)
@@ -321,11 +345,11 @@ voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, co
 			const uint32_t any = m[0] | m[1] | m[2] | m[3], all = m[0] & m[1] & m[2] & m[3];
 			if (aligned && (any == 0u || all == 0xffffffffu)) {            // uniform tile: store only
 				const uint32_t w = any ? 0x01010101u : 0u;
-				for (int z = z0; z < z1; ++z, o += layer) *reinterpret_cast<uint32_t *>(o) = w;
+				for (int z = z0; z < z1; ++z, o += layer) __stcs(reinterpret_cast<uint32_t *>(o), w);
 			} else if (aligned) {
 				uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
 				for (int z = z0; z < z1; ++z, o += layer) {
-					*reinterpret_cast<uint32_t *>(o) = (m0 & 1u) | ((m1 & 1u) << 8) | ((m2 & 1u) << 16) | ((m3 & 1u) << 24);
+					__stcs(reinterpret_cast<uint32_t *>(o), (m0 & 1u) | ((m1 & 1u) << 8) | ((m2 & 1u) << 16) | ((m3 & 1u) << 24));
 					m0 >>= 1; m1 >>= 1; m2 >>= 1; m3 >>= 1;
 				}
 			} else {
