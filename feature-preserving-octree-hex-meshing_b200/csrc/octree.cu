@@ -68,11 +68,12 @@ __global__ void roots_kernel(uint64_t *__restrict__ code, int rx, int ry, int rz
 // should_subdivide (ghm.cpp:502-517) for every cell of T_l over the complete binary facet-box tree (the reference
 // visits every overlapping leaf, mesh_AABB.h:214-239, but only ORs a flag — any-hit is the same result).
 //
-// Phase A: one thread per cell, depth-first with early exit, at most PRED_BUDGET node visits.  Nearly every cell
-// finishes here.  Phase B: the few cells that overlap many internal union boxes without touching a facet box (cells in
+// Phase A: one thread per cell, depth-first with early exit, at most PRED_BUDGET node visits (swept 48..512 on a 200 k and
+// a 2 M facet mesh: 256 is within 1 % of the best on both; 48 left too many lanes to phase B on the deeper tree).  Nearly
+// every cell finishes here.  Phase B: the few cells that overlap many internal union boxes without touching a facet box (cells in
 // concavities: the serial chain was ~2 300 dependent L2 loads = 350 us for ONE thread on the first ncu capture) are
 // finished by the whole warp: the frontier lives in shared memory and 32 nodes are tested per step.
-#define PRED_BUDGET 48
+#define PRED_BUDGET 256
 #define PRED_WCAP 1024
 
 __device__ __forceinline__ bool box_overlap(const double *__restrict__ b, double mn0, double mn1, double mn2, double mx0, double mx1, double mx2) {
@@ -112,7 +113,7 @@ __device__ bool coop_any_overlap(const double *__restrict__ box, uint32_t P, dou
 
 __global__ void __launch_bounds__(256)
 predicate_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift /*depth - level*/, double bx, double by, double bz,
-                 double vs, const double *__restrict__ box, int64_t P64, uint8_t *__restrict__ flag)
+                 double vs, const double *__restrict__ box, int64_t P64, uint8_t *__restrict__ flag, int budget)
 {
 	__shared__ uint32_t wstack[8][PRED_WCAP];
 	const uint32_t P = (uint32_t)P64;
@@ -136,7 +137,7 @@ predicate_kernel(const uint64_t *__restrict__ cells, int64_t n, int shift /*dept
 		if (valid) stack[sp++] = 1;
 		while (!done) {
 			if (sp == 0) { done = true; break; }
-			if (visits >= PRED_BUDGET) break;
+			if (visits >= budget) break;
 			const uint32_t nd = stack[--sp];
 			++visits;
 			if (!box_overlap(box + 6 * (int64_t)nd, mn0, mn1, mn2, mx0, mx1, mx2)) continue;
@@ -284,6 +285,76 @@ cell_links_kernel(LevelTable t, const uint8_t *__restrict__ lvl, const uint64_t 
 	}
 }
 
+// Top-down form of the same tables (replaces cell_links_kernel in the build: 12.2 of 73 ms at 59 M cells were its ~8
+// binary searches per cell).  (a) per INTERNAL cell g: its own cell id (one search of the parent) gives firstChild;
+// (b) per level, coarse to fine: a child's neighbour is a sibling, or hangs off the parent's neighbour q in that
+// direction: the mirrored child of q if q is internal (then q has the parent's size), else q itself — the larger (or
+// equal) leaf that contains the position, exactly what updateSubcellLinks leaves behind (octree.cpp:255-281).
+__global__ void __launch_bounds__(256)
+first_child_kernel(LevelTable t, int64_t n_internal, int32_t *__restrict__ first_child, uint8_t *__restrict__ leaf_flag,
+                   int32_t *__restrict__ icell)
+{
+	for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_internal; g += (int64_t)gridDim.x * blockDim.x) {
+		int l = 0;
+		while (g >= t.off[l + 1]) ++l;
+		const uint64_t c = t.code[g];
+		int32_t id;
+		if (l == 0) {
+			id = (int32_t)(compact1by2(c) + t.roots[0] * (compact1by2(c >> 1) + t.roots[1] * compact1by2(c >> 2)));
+		} else {
+			const int64_t r = internal_rank(t, l - 1, c >> 3);       // exists: the sets are closed under "parent"
+			id = (int32_t)(t.n_roots + 8 * r + morton_to_corner((int)(c & 7)));
+		}
+		first_child[id] = (int32_t)(t.n_roots + 8 * g);
+		leaf_flag[id] = 0;
+		icell[g] = id;
+	}
+}
+__global__ void root_links_kernel(LevelTable t, int32_t *__restrict__ neigh) {
+	const int n = t.n_roots;
+	for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const int x = id % t.roots[0], y = (id / t.roots[0]) % t.roots[1], z = (id / t.roots[0]) / t.roots[1];
+		const int q[3] = {x, y, z};
+		for (int ax = 0; ax < 3; ++ax)
+			for (int dir = 0; dir < 2; ++dir) {
+				const int v = q[ax] + (dir ? 1 : -1);
+				int p[3] = {x, y, z};
+				p[ax] = v;
+				neigh[6 * id + 2 * ax + dir] = (v >= 0 && v < t.roots[ax]) ? p[0] + t.roots[0] * (p[1] + t.roots[1] * p[2]) : -1;
+			}
+	}
+}
+// cells [id0, id0 + n) = one level >= 1; the parents' rows of `neigh` are complete
+__global__ void __launch_bounds__(256)
+child_links_kernel(int64_t id0, int64_t n, int32_t n_roots, const int32_t *__restrict__ icell, const int32_t *__restrict__ first_child,
+                   int32_t *__restrict__ neigh)
+{
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t id = id0 + t;
+		const int64_t g = (id - n_roots) >> 3;
+		const int m = corner_to_morton((int)((id - n_roots) & 7));
+		const int64_t base = id - ((id - n_roots) & 7);
+		const int32_t P = icell[g];
+#pragma unroll
+		for (int ax = 0; ax < 3; ++ax) {
+#pragma unroll
+			for (int dir = 0; dir < 2; ++dir) {
+				const int bit = (m >> ax) & 1;
+				const int mirrored = morton_to_corner(m ^ (1 << ax));
+				int32_t res;
+				if (bit != dir) {
+					res = (int32_t)(base + mirrored);                       // sibling
+				} else {
+					const int32_t q = neigh[6 * (int64_t)P + 2 * ax + dir];
+					if (q < 0) res = -1;
+					else { const int32_t fc = first_child[q]; res = fc >= 0 ? fc + mirrored : q; }
+				}
+				neigh[6 * id + 2 * ax + dir] = res;
+			}
+		}
+	}
+}
+
 // node keys: Morton code of (corner position >> node_shift); 8 per leaf, payload = 8 * leaf + corner
 __global__ void leaf_corner_keys_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const uint8_t *__restrict__ lvl,
                                         const uint64_t *__restrict__ code, int depth, int node_shift, uint64_t *__restrict__ keys,
@@ -363,6 +434,25 @@ leaf_edges_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const
 __global__ void node_links_kernel(const unsigned long long *__restrict__ link, int64_t n, int32_t *__restrict__ neigh) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
 		neigh[t] = link[t] == ~0ull ? -1 : (int32_t)(link[t] & 0xffffffffull);
+}
+
+// The same links without atomics: levels are processed coarse to fine with plain 4-byte stores, so the edge of the finest
+// (= shortest) leaf touching a node in a direction is the one that stays; leaves of one level that share an edge store
+// identical values.  (The atomicMin form was 14.2 of 73 ms at 59 M cells: 1.2 G 64-bit atomics.)
+__global__ void __launch_bounds__(256)
+level_edges_kernel(int64_t id0, int64_t n, const int32_t *__restrict__ first_child, const int32_t *__restrict__ corner,
+                   int32_t *__restrict__ node_neigh)
+{
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 12 * n; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t id = id0 + t / 12; const int k = (int)(t % 12);
+		if (first_child[id] >= 0) continue;
+		const int ea[12] = {0, 3, 4, 7, 0, 1, 4, 5, 0, 1, 3, 2};
+		const int eb[12] = {1, 2, 5, 6, 3, 2, 7, 6, 4, 5, 7, 6};
+		const int ax = k >> 2;
+		const int32_t a = corner[8 * id + ea[k]], b = corner[8 * id + eb[k]];
+		node_neigh[6 * (int64_t)a + 2 * ax + 1] = b;
+		node_neigh[6 * (int64_t)b + 2 * ax] = a;
+	}
 }
 
 __global__ void iota_i32_kernel(int32_t *p, int64_t n) {
@@ -570,9 +660,23 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 	o->cell_first_child.alloc(n_cells, s);
 	o->cell_neigh.alloc(6 * n_cells, s);
 	DevBuf<uint8_t> leaf_flag(n_cells, s);
-	cell_links_kernel<<<grid_for(ctx, n_cells, blk), blk, 0, s>>>(t, o->cell_level.p, o->cell_code.p, n_cells,
-		o->cell_first_child.p, o->cell_neigh.p, leaf_flag.p);
-	FPOHM_LAUNCH_CHECK(ctx);
+	{
+		FPOHM_CUDA(cudaMemsetAsync(o->cell_first_child.p, 0xff, 4 * (size_t)n_cells, s));
+		FPOHM_CUDA(cudaMemsetAsync(leaf_flag.p, 1, (size_t)n_cells, s));
+		DevBuf<int32_t> icell(std::max<int64_t>(n_internal, 1), s);
+		if (n_internal) {
+			first_child_kernel<<<grid_for(ctx, n_internal, blk), blk, 0, s>>>(t, n_internal, o->cell_first_child.p, leaf_flag.p, icell.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		root_links_kernel<<<grid_for(ctx, o->n_roots, blk), blk, 0, s>>>(t, o->cell_neigh.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		for (int l = 1; l <= o->n_levels; ++l) {
+			const int64_t id0 = o->n_roots + 8 * o->lvl_off[l - 1], n = 8 * (o->lvl_off[l] - o->lvl_off[l - 1]);
+			if (n == 0) continue;
+			child_links_kernel<<<grid_for(ctx, n, blk), blk, 0, s>>>(id0, n, o->n_roots, icell.p, o->cell_first_child.p, o->cell_neigh.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+	}
 	// leaves in cell order (hex2Octree_map, ghm.cpp:551)
 	{
 		DevBuf<int32_t> ids(n_cells, s), sel(n_cells, s);
@@ -635,14 +739,15 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 	internal_corners_kernel<<<grid_for(ctx, 8 * n_cells, blk), blk, 0, s>>>(o->cell_first_child.p, n_cells, o->cell_corner.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	{
-		DevBuf<unsigned long long> link(6 * o->n_nodes, s);
-		FPOHM_CUDA(cudaMemsetAsync(link.p, 0xff, 8 * (size_t)(6 * o->n_nodes), s));
-		leaf_edges_kernel<<<grid_for(ctx, 12 * o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->cell_level.p, o->depth,
-			o->cell_corner.p, link.p);
-		FPOHM_LAUNCH_CHECK(ctx);
 		o->node_neigh.alloc(6 * o->n_nodes, s);
-		node_links_kernel<<<grid_for(ctx, 6 * o->n_nodes, blk), blk, 0, s>>>(link.p, 6 * o->n_nodes, o->node_neigh.p);
-		FPOHM_LAUNCH_CHECK(ctx);
+		FPOHM_CUDA(cudaMemsetAsync(o->node_neigh.p, 0xff, 4 * (size_t)(6 * o->n_nodes), s));
+		for (int l = 0; l <= o->n_levels; ++l) {
+			const int64_t id0 = l == 0 ? 0 : o->n_roots + 8 * o->lvl_off[l - 1];
+			const int64_t n = l == 0 ? o->n_roots : 8 * (o->lvl_off[l] - o->lvl_off[l - 1]);
+			if (n == 0) continue;
+			level_edges_kernel<<<grid_for(ctx, 12 * n, blk), blk, 0, s>>>(id0, n, o->cell_first_child.p, o->cell_corner.p, o->node_neigh.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
 	}
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 }
@@ -662,13 +767,15 @@ int64_t test_cells(fpohm_octree *o, const fpohm_mesh *mesh, int l, const uint64_
 	const int blk = 256;
 	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
 	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
+	static const int budget_env = getenv("FPOHM_PRED_BUDGET") ? atoi(getenv("FPOHM_PRED_BUDGET")) : 0;
+	const int pred_budget = budget_env > 0 ? budget_env : PRED_BUDGET;
 	DevBuf<uint8_t> flag(nT, s);
 	if (nT <= 32768)
 		predicate_warp_kernel<<<(int)std::min<int64_t>((nT + 7) / 8, (int64_t)ctx->sm_count * 8), blk, 0, s>>>(T, nT, o->depth - l,
 			bx, by, bz, o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
 	else
 		predicate_kernel<<<grid_for(ctx, nT, blk, 8), blk, 0, s>>>(T, nT, o->depth - l, bx, by, bz, o->prm.voxel_size,
-			mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+			mesh->pred_box.p, mesh->pred_nodes / 2, flag.p, pred_budget);
 	FPOHM_LAUNCH_CHECK(ctx);
 	sel.alloc(nT, s);
 	DevBuf<int64_t> cnt(1, s);
@@ -985,7 +1092,7 @@ int fpohm_octree_refine(fpohm_octree *o, const fpohm_mesh *mesh, const int32_t *
 			DevBuf<int64_t> cnt(1, s);
 			dc.upload(cand.data(), (int64_t)cand.size());
 			predicate_kernel<<<grid_for(ctx, (int64_t)cand.size(), blk), blk, 0, s>>>(dc.p, (int64_t)cand.size(), o->depth - l, bx, by, bz,
-				o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p);
+				o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p, PRED_BUDGET);
 			FPOHM_LAUNCH_CHECK(ctx);
 			size_t tb = 0;
 			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, dc.p, flag.p, sel.p, cnt.p, (int64_t)cand.size(), s));
