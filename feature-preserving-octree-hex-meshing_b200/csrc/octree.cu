@@ -376,6 +376,100 @@ __global__ void leaf_corner_keys_kernel(const int32_t *__restrict__ leaf_cell, i
 	}
 }
 
+// Family-level node keys.  Most leaves sit in families of 8 sibling leaves, whose 64 corners are only 27 distinct lattice
+// points: such a family emits 27 keys (payload FAMILY | 27 * family + point), every other leaf its 8 corners (payload
+// 8 * slot + corner).  Halves the key/payload sort, which was the largest item of the numbering (15 of 57 ms at 59 M cells).
+#define NODE_FAMILY_BIT 0x80000000u
+__global__ void full_family_flags_kernel(const int32_t *__restrict__ icell, int64_t n_internal, const int32_t *__restrict__ first_child,
+                                         uint8_t *__restrict__ fam_flag)
+{
+	for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_internal; g += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t fc = first_child[icell[g]];
+		bool all = true;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) all &= first_child[fc + k] < 0;
+		fam_flag[g] = all;
+	}
+}
+// leaves whose family is not full (or that are roots) keep the per-leaf path
+__global__ void loose_leaf_flags_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, int32_t n_roots,
+                                        const uint8_t *__restrict__ fam_flag, uint8_t *__restrict__ loose)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_leaves; i += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t id = leaf_cell[i];
+		loose[i] = id < n_roots ? 1 : !fam_flag[(id - n_roots) >> 3];
+	}
+}
+__global__ void family_keys_kernel(const int32_t *__restrict__ fam /* internal ranks g */, int64_t n_fam, const int32_t *__restrict__ icell,
+                                   const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int depth, int node_shift,
+                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ payload)
+{
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 27 * n_fam; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t fi = t / 27; const int j = (int)(t % 27);
+		const int32_t id = icell[fam[fi]];                      // the internal cell whose 8 children are leaves
+		const int sh = depth - lvl[id] - 1 - node_shift;       // child extent in key units = 1 << sh
+		const uint64_t c = code[id];
+		const uint32_t x = (compact1by2(c) << (sh + 1)) + ((uint32_t)(j % 3) << sh);
+		const uint32_t y = (compact1by2(c >> 1) << (sh + 1)) + ((uint32_t)((j / 3) % 3) << sh);
+		const uint32_t z = (compact1by2(c >> 2) << (sh + 1)) + ((uint32_t)(j / 9) << sh);
+		keys[t] = morton3(x, y, z);
+		payload[t] = NODE_FAMILY_BIT | (uint32_t)t;
+	}
+}
+__global__ void loose_leaf_keys_kernel(const int32_t *__restrict__ loose_leaf /* cell ids */, int64_t n_loose, const uint8_t *__restrict__ lvl,
+                                       const uint64_t *__restrict__ code, int depth, int node_shift, uint64_t *__restrict__ keys,
+                                       uint32_t *__restrict__ payload)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_loose; i += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t id = loose_leaf[i];
+		const int l = lvl[id];
+		const uint64_t c = code[id];
+		const int sh = depth - l - node_shift; // extent in key units = 1 << sh
+		const uint32_t x = compact1by2(c) << sh, y = compact1by2(c >> 1) << sh, z = compact1by2(c >> 2) << sh;
+		const uint32_t e = 1u << sh;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int m = corner_to_morton(k);
+			keys[8 * i + k] = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
+			payload[8 * i + k] = (uint32_t)(8 * i + k);
+		}
+	}
+}
+// After the sort: node id = index of the key's run; leaf corners are written through the payload, no search.
+__global__ void node_scatter2_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, const int32_t *__restrict__ head,
+                                     const int32_t *__restrict__ nid_incl, int64_t n, const int32_t *__restrict__ fam,
+                                     const int32_t *__restrict__ icell, const int32_t *__restrict__ first_child,
+                                     const int32_t *__restrict__ loose_leaf, int node_shift,
+                                     uint64_t *__restrict__ node_key, int32_t *__restrict__ node_pos, int32_t *__restrict__ corner)
+{
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t nid = nid_incl[t] - 1;
+		const uint32_t pl = payload[t];
+		if (pl & NODE_FAMILY_BIT) {
+			const uint32_t q = pl & ~NODE_FAMILY_BIT;
+			const int j = (int)(q % 27);
+			const int32_t fc = first_child[icell[fam[q / 27]]];
+			const int a = j % 3, b = (j / 3) % 3, c = j / 9;       // lattice point; child (mx,my,mz) has it as local corner (a-mx, b-my, c-mz)
+			for (int mz = max(c - 1, 0); mz <= min(c, 1); ++mz)
+				for (int my = max(b - 1, 0); my <= min(b, 1); ++my)
+					for (int mx = max(a - 1, 0); mx <= min(a, 1); ++mx) {
+						const int child = morton_to_corner(mx | (my << 1) | (mz << 2));
+						const int loc = morton_to_corner((a - mx) | ((b - my) << 1) | ((c - mz) << 2));
+						corner[8 * (int64_t)(fc + child) + loc] = nid;
+					}
+		} else {
+			corner[8 * (int64_t)loose_leaf[pl >> 3] + (pl & 7)] = nid;
+		}
+		if (head[t]) {
+			const uint64_t k = key[t];
+			node_key[nid] = k;
+			node_pos[3 * (int64_t)nid] = (int32_t)(compact1by2(k) << node_shift);
+			node_pos[3 * (int64_t)nid + 1] = (int32_t)(compact1by2(k >> 1) << node_shift);
+			node_pos[3 * (int64_t)nid + 2] = (int32_t)(compact1by2(k >> 2) << node_shift);
+		}
+	}
+}
+
 __global__ void key_heads_kernel(const uint64_t *__restrict__ k, int64_t n, int32_t *__restrict__ head) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
 		head[t] = (t == 0 || k[t] != k[t - 1]) ? 1 : 0;
@@ -660,10 +754,10 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 	o->cell_first_child.alloc(n_cells, s);
 	o->cell_neigh.alloc(6 * n_cells, s);
 	DevBuf<uint8_t> leaf_flag(n_cells, s);
+	DevBuf<int32_t> icell(std::max<int64_t>(n_internal, 1), s);      // cell id of the g-th internal cell
 	{
 		FPOHM_CUDA(cudaMemsetAsync(o->cell_first_child.p, 0xff, 4 * (size_t)n_cells, s));
 		FPOHM_CUDA(cudaMemsetAsync(leaf_flag.p, 1, (size_t)n_cells, s));
-		DevBuf<int32_t> icell(std::max<int64_t>(n_internal, 1), s);
 		if (n_internal) {
 			first_child_kernel<<<grid_for(ctx, n_internal, blk), blk, 0, s>>>(t, n_internal, o->cell_first_child.p, leaf_flag.p, icell.p);
 			FPOHM_LAUNCH_CHECK(ctx);
@@ -677,23 +771,34 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 			FPOHM_LAUNCH_CHECK(ctx);
 		}
 	}
-	// leaves in cell order (hex2Octree_map, ghm.cpp:551)
+	// leaves in cell order (hex2Octree_map, ghm.cpp:551) and, in the same pass, the families of 8 sibling leaves
+	DevBuf<uint8_t> fam_flag(std::max<int64_t>(n_internal, 1), s);
+	DevBuf<int32_t> fam(std::max<int64_t>(n_internal, 1), s);
+	int64_t n_fam = 0;
 	{
 		DevBuf<int32_t> ids(n_cells, s), sel(n_cells, s);
-		DevBuf<int64_t> cnt(1, s);
+		DevBuf<int64_t> cnt(2, s);
+		FPOHM_CUDA(cudaMemsetAsync(cnt.p, 0, 16, s));
 		iota_i32_kernel<<<grid_for(ctx, n_cells, blk), blk, 0, s>>>(ids.p, n_cells);
 		FPOHM_LAUNCH_CHECK(ctx);
-		size_t tb = 0;
+		if (n_internal) {
+			full_family_flags_kernel<<<grid_for(ctx, n_internal, blk), blk, 0, s>>>(icell.p, n_internal, o->cell_first_child.p, fam_flag.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		size_t tb = 0, tb1 = 0;
 		FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids.p, leaf_flag.p, sel.p, cnt.p, n_cells, s));
-		DevBuf<uint8_t> tmp((int64_t)tb, s);
+		FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb1, ids.p, fam_flag.p, fam.p, cnt.p + 1, std::max<int64_t>(n_internal, 1), s));
+		DevBuf<uint8_t> tmp((int64_t)std::max(tb, tb1), s);
 		FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids.p, leaf_flag.p, sel.p, cnt.p, n_cells, s));
-		ctx->launches += 2;
-		int64_t nl = 0;
-		cnt.download(&nl, 1);
+		if (n_internal) FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb1, ids.p, fam_flag.p, fam.p, cnt.p + 1, n_internal, s));
+		ctx->launches += 4;
+		int64_t hc[2] = {0, 0};
+		cnt.download(hc, 2);
 		FPOHM_CUDA(cudaStreamSynchronize(s));
-		o->n_leaves = nl;
-		o->leaf_cell.alloc(nl, s);
-		FPOHM_CUDA(cudaMemcpyAsync(o->leaf_cell.p, sel.p, 4 * (size_t)nl, cudaMemcpyDeviceToDevice, s));
+		o->n_leaves = hc[0];
+		n_fam = hc[1];
+		o->leaf_cell.alloc(o->n_leaves, s);
+		FPOHM_CUDA(cudaMemcpyAsync(o->leaf_cell.p, sel.p, 4 * (size_t)o->n_leaves, cudaMemcpyDeviceToDevice, s));
 	}
 	// nodes: unique corners of leaves, Morton order of (pos >> node_shift)
 	const int finest_level = o->n_levels; // deepest cells live one level below the deepest internal level
@@ -704,13 +809,34 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 		              "octree: %d node positions per axis after shift do not fit 21-bit Morton keys", (o->prm.grid_size[d] >> o->node_shift) + 1);
 	o->cell_corner.alloc(8 * n_cells, s);
 	{
-		const int64_t nk = 8 * o->n_leaves;
-		FPOHM_REQUIRE(nk < (1ll << 32), FPOHM_ERANGE, "octree: %lld leaf corners exceed the 32-bit payload", (long long)nk);
+		// the leaves outside full families keep the per-leaf path; their number needs no read-back
+		const int64_t n_loose = o->n_leaves - 8 * n_fam;
+		DevBuf<uint8_t> loose_flag(std::max<int64_t>(o->n_leaves, 1), s);
+		DevBuf<int32_t> loose(std::max<int64_t>(o->n_leaves, 1), s);
+		if (n_loose > 0) {
+			DevBuf<int64_t> cnt2(1, s);
+			loose_leaf_flags_kernel<<<grid_for(ctx, o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->n_roots, fam_flag.p, loose_flag.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			size_t tb1 = 0;
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb1, o->leaf_cell.p, loose_flag.p, loose.p, cnt2.p, o->n_leaves, s));
+			DevBuf<uint8_t> tmp1((int64_t)tb1, s);
+			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp1.p, tb1, o->leaf_cell.p, loose_flag.p, loose.p, cnt2.p, o->n_leaves, s));
+			ctx->launches += 2;
+		}
+		const int64_t nk = 27 * n_fam + 8 * n_loose;
+		FPOHM_REQUIRE(nk < (1ll << 31), FPOHM_ERANGE, "octree: %lld node keys exceed the 31-bit payload", (long long)nk);
 		DevBuf<uint64_t> keys(nk, s), skeys(nk, s);
 		DevBuf<uint32_t> pay(nk, s), spay(nk, s);
-		leaf_corner_keys_kernel<<<grid_for(ctx, o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->cell_level.p,
-			o->cell_code.p, o->depth, o->node_shift, keys.p, pay.p);
-		FPOHM_LAUNCH_CHECK(ctx);
+		if (n_fam) {
+			family_keys_kernel<<<grid_for(ctx, 27 * n_fam, blk), blk, 0, s>>>(fam.p, n_fam, icell.p, o->cell_level.p, o->cell_code.p,
+				o->depth, o->node_shift, keys.p, pay.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
+		if (n_loose) {
+			loose_leaf_keys_kernel<<<grid_for(ctx, n_loose, blk), blk, 0, s>>>(loose.p, n_loose, o->cell_level.p, o->cell_code.p, o->depth,
+				o->node_shift, keys.p + 27 * n_fam, pay.p + 27 * n_fam);
+			FPOHM_LAUNCH_CHECK(ctx);
+		}
 		const int64_t gmax = std::max(o->prm.grid_size[0], std::max(o->prm.grid_size[1], o->prm.grid_size[2]));
 		const int bits = std::min(64, key_bits(gmax >> o->node_shift));
 		size_t tb = 0;
@@ -732,8 +858,8 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 		o->n_nodes = last;
 		o->node_key.alloc(o->n_nodes, s);
 		o->node_pos.alloc(3 * o->n_nodes, s);
-		node_scatter_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, spay.p, head.p, nid.p, nk, o->leaf_cell.p, o->node_shift,
-			o->node_key.p, o->node_pos.p, o->cell_corner.p);
+		node_scatter2_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, spay.p, head.p, nid.p, nk, fam.p, icell.p, o->cell_first_child.p,
+			loose.p, o->node_shift, o->node_key.p, o->node_pos.p, o->cell_corner.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 	}
 	internal_corners_kernel<<<grid_for(ctx, 8 * n_cells, blk), blk, 0, s>>>(o->cell_first_child.p, n_cells, o->cell_corner.p);
