@@ -4,23 +4,13 @@
 // sorted lists; every adjacency list is filled by loops that visit elements in ascending id.  All of it is therefore
 // reproduced by STABLE LSD radix sorts on the same composite keys (ties keep the original 6h+j / 4f+j order), run-head
 // flags + inclusive scan for the ids, and CSR offsets by binary search.  Integer work only: bit-exact.
-#include "internal.h"
+#include "conn.h"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
 using namespace fpohm;
-
-struct fpohm_conn {
-	fpohm_ctx *ctx = nullptr;
-	int64_t H = 0, nV = 0, nF = 0, nE = 0;
-	DevBuf<uint32_t> F_vs, F_es, E_vs, H_fs;
-	DevBuf<uint8_t> F_boundary, E_boundary, V_boundary;
-	DevBuf<int64_t> off[7];
-	DevBuf<uint32_t> val[7];
-	int64_t tot[7] = {0, 0, 0, 0, 0, 0, 0};
-};
 
 namespace {
 

@@ -231,6 +231,21 @@ int  fpohm_conn_fixed(const fpohm_conn *c, uint32_t *F_vs, uint32_t *F_es, uint8
 int  fpohm_conn_csr(const fpohm_conn *c, int32_t which, int64_t *off, uint32_t *val, int64_t *total);
 void fpohm_conn_free(fpohm_conn *c);
 
+/* ---- conforming_mesh (grid_meshing/grid_hex_meshing.cpp:568-696): the octree hex mesh with every big
+ * face at a T-junction replaced by the 4 small faces of the other side and the mid vertices inserted into the loops of
+ * the faces around it, as a polyhedral ("Hyb") mesh with the connectivity build_connectivity gives it (gf.cpp:187-264):
+ * faces = vertex loops (4..8), cells = face lists + sorted vertex sets, edges, boundary flags, F.neighbor_hs.
+ * `conn` must be fpohm_hex_connectivity of fpohm_octree_hexes(oct) (vertex i = octree node i).  Ids and orders are the
+ * reference's for the same input numbering.  sizes = {nV, nF, nH, nE, sum |F.vs|, sum |H.fs|, sum |H.vs|, sum |F.nhs|}. */
+typedef struct fpohm_hybrid fpohm_hybrid;
+int  fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_conn *conn, fpohm_hybrid **out);
+int  fpohm_hybrid_sizes(const fpohm_hybrid *hy, int64_t sizes[8], int64_t *n_replaced_faces);
+int  fpohm_hybrid_export(const fpohm_hybrid *hy, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs,
+                         uint8_t *E_boundary, uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs,
+                         int64_t *F_nhoff, uint32_t *F_nhs);
+void fpohm_hybrid_free(fpohm_hybrid *hy);
+
+
 /* voxel_meshing lattice (ghm.cpp:215-296, the `--o 0` path): dim[d] = ceil(extent/len), float grid_length,
  * vertex (i,j,k) id = i*dimY*dimZ + j*dimZ + k; hexes in hex_ref_shape corner order. Two-phase via dims. */
 int fpohm_voxel_lattice_dims(const double bb_min[3], const double bb_max[3], int32_t num_voxels, int32_t dim[3]);

@@ -280,6 +280,13 @@ void ref_octree_hexes(void *hv, double *Vpos, uint32_t *hex, int32_t *hex2cell) 
 }
 
 void ref_octree_free(void *hv) { delete (RefOctree *)hv; }
+// views for ref_driver_ghm.cpp
+const OctreeGrid *ref_octree_grid(void *hv) { return &((RefOctree *)hv)->octree; }
+void ref_octree_frame(void *hv, double origin[3], double mesh_transform[3], double *voxel_size, int32_t grid_size[3]) {
+	RefOctree *h = (RefOctree *)hv;
+	for (int d = 0; d < 3; ++d) { origin[d] = h->origin[d]; mesh_transform[d] = h->mesh_transform[d]; grid_size[d] = h->grid_size[d]; }
+	*voxel_size = h->voxel_size;
+}
 
 // ---------------------------------------------------------------------------------------
 // compute_octree, voxelization.cpp:353-391 (the one public end-to-end entry of voxelization.h)

@@ -1,0 +1,111 @@
+// TEST INFRASTRUCTURE ONLY — extern "C" driver for the reference's own conforming_mesh
+// (grid_meshing/grid_hex_meshing.cpp:568-696), compiled UNMODIFIED from /root/reference next to this file.
+// The octree comes from the handles of ref_driver.cpp; the octree hex mesh `mo` is filled the way octree_mesh
+// does (ghm.cpp:527-562: one vertex per node, one hex per leaf in cell order, then build_connectivity).
+#include "grid_meshing/grid_hex_meshing.h"
+#include <cstdint>
+
+struct RefOctreeView;   // ref_driver.cpp
+extern "C" {
+// provided by ref_driver.cpp
+const OctreeGrid *ref_octree_grid(void *hv);
+void ref_octree_frame(void *hv, double origin[3], double mesh_transform[3], double *voxel_size, int32_t grid_size[3]);
+
+struct RefHybrid { Mesh mo, hybrid; };
+
+static void fill_sizes(const Mesh &hy, int64_t sizes[8]) {
+	int64_t fv = 0, hf = 0, hv = 0, fn = 0;
+	for (auto &f : hy.Fs) { fv += (int64_t)f.vs.size(); fn += (int64_t)f.neighbor_hs.size(); }
+	for (auto &h : hy.Hs) { hf += (int64_t)h.fs.size(); hv += (int64_t)h.vs.size(); }
+	sizes[0] = (int64_t)hy.Vs.size(); sizes[1] = (int64_t)hy.Fs.size(); sizes[2] = (int64_t)hy.Hs.size(); sizes[3] = (int64_t)hy.Es.size();
+	sizes[4] = fv; sizes[5] = hf; sizes[6] = hv; sizes[7] = fn;
+}
+
+// conforming_mesh on an octree GIVEN AS TABLES (any numbering): node positions / node links fill OctreeGrid::m_Nodes — the
+// only octree members the function reads (numNodes, nodePos, m_Nodes[i].neighNodeId, ghm.cpp:572-583) — and `mo` is the
+// hex mesh with vertex i = node i.  This lets the product's canonical numbering be fed to the reference unchanged.
+void *ref_conforming_mesh_tables(const int32_t *node_pos, const int32_t *node_neigh, int64_t n_nodes, const double *Vpos,
+                                 const uint32_t *hex, int64_t n_hex, const int32_t grid_size_in[3], int64_t sizes[8])
+{
+	RefHybrid *r = new RefHybrid;
+	OctreeGrid octree;
+	octree.m_Nodes.resize((size_t)n_nodes);
+	for (int64_t i = 0; i < n_nodes; ++i) {
+		for (int d = 0; d < 3; ++d) octree.m_Nodes[(size_t)i].position[d] = node_pos[3 * i + d];
+		for (int k = 0; k < 6; ++k) octree.m_Nodes[(size_t)i].neighNodeId[k] = node_neigh[6 * i + k];
+	}
+	Mesh &mo = r->mo;
+	mo.type = Mesh_type::Hex;
+	mo.Vs.resize((size_t)n_nodes);
+	mo.V.resize(3, n_nodes);
+	for (int64_t i = 0; i < n_nodes; ++i) {
+		Hybrid_V v; v.id = (uint32_t)i;
+		for (int d = 0; d < 3; ++d) { v.v.push_back(Vpos[3 * i + d]); mo.V(d, i) = Vpos[3 * i + d]; }
+		mo.Vs[(size_t)i] = v;
+	}
+	mo.Hs.resize((size_t)n_hex);
+	for (int64_t h = 0; h < n_hex; ++h) { mo.Hs[(size_t)h].id = (uint32_t)h; mo.Hs[(size_t)h].vs.assign(hex + 8 * h, hex + 8 * h + 8); }
+	build_connectivity(mo);
+	grid_hex_meshing_bijective gm;
+	Eigen::Vector3i grid_size(grid_size_in[0], grid_size_in[1], grid_size_in[2]);
+	gm.conforming_mesh(mo, r->hybrid, octree, grid_size);
+	fill_sizes(r->hybrid, sizes);
+	return r;
+}
+
+void *ref_conforming_mesh(void *octree_handle, int64_t sizes[8]) {
+	const OctreeGrid &octree_c = *ref_octree_grid(octree_handle);
+	OctreeGrid &octree = const_cast<OctreeGrid &>(octree_c);
+	double org[3], mt[3], vs; int32_t gs[3];
+	ref_octree_frame(octree_handle, org, mt, &vs, gs);
+	RefHybrid *r = new RefHybrid;
+	Mesh &mo = r->mo;
+	mo.type = Mesh_type::Hex;
+	const int nn = octree.numNodes();
+	mo.Vs.resize(nn);
+	mo.V.resize(3, nn);
+	for (int i = 0; i < nn; ++i) {
+		const Eigen::Vector3i p = octree.nodePos(i);
+		Hybrid_V v; v.id = i;
+		for (int d = 0; d < 3; ++d) { const double x = (mt[d] + org[d]) + (double)p[d] * vs; v.v.push_back(x); mo.V(d, i) = x; }
+		mo.Vs[i] = v;
+	}
+	for (int q = 0; q < octree.numCells(); ++q) {
+		if (!octree.cellIsLeaf(q)) continue;
+		Hybrid h; h.id = (uint32_t)mo.Hs.size(); h.vs.resize(8);
+		for (int lv = 0; lv < 8; ++lv) h.vs[lv] = octree.cellCornerId(q, lv);
+		mo.Hs.push_back(h);
+	}
+	build_connectivity(mo);
+	grid_hex_meshing_bijective gm;
+	Eigen::Vector3i grid_size(gs[0], gs[1], gs[2]);
+	gm.conforming_mesh(mo, r->hybrid, octree, grid_size);
+	fill_sizes(r->hybrid, sizes);
+	return r;
+}
+// F_off nF+1, F_vs/F_es sizes[4], F_boundary nF, E_vs 2 nE, E_boundary nE, V_boundary nV,
+// H_foff nH+1, H_fs sizes[5], H_voff nH+1, H_vs sizes[6], F_nhoff nF+1, F_nhs sizes[7]
+void ref_hybrid_export(void *rv, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs, uint8_t *E_boundary,
+                       uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs, int64_t *F_nhoff, uint32_t *F_nhs)
+{
+	const Mesh &hy = ((RefHybrid *)rv)->hybrid;
+	int64_t t = 0, u = 0;
+	for (size_t f = 0; f < hy.Fs.size(); ++f) {
+		F_off[f] = t; F_nhoff[f] = u;
+		for (size_t k = 0; k < hy.Fs[f].vs.size(); ++k) { F_vs[t] = hy.Fs[f].vs[k]; F_es[t] = hy.Fs[f].es[k]; ++t; }
+		for (uint32_t h : hy.Fs[f].neighbor_hs) F_nhs[u++] = h;
+		F_boundary[f] = hy.Fs[f].boundary;
+	}
+	F_off[hy.Fs.size()] = t; F_nhoff[hy.Fs.size()] = u;
+	for (size_t e = 0; e < hy.Es.size(); ++e) { E_vs[2 * e] = hy.Es[e].vs[0]; E_vs[2 * e + 1] = hy.Es[e].vs[1]; E_boundary[e] = hy.Es[e].boundary; }
+	for (size_t v = 0; v < hy.Vs.size(); ++v) V_boundary[v] = hy.Vs[v].boundary;
+	int64_t a = 0, b = 0;
+	for (size_t h = 0; h < hy.Hs.size(); ++h) {
+		H_foff[h] = a; H_voff[h] = b;
+		for (uint32_t x : hy.Hs[h].fs) H_fs[a++] = x;
+		for (uint32_t x : hy.Hs[h].vs) H_vs[b++] = x;
+	}
+	H_foff[hy.Hs.size()] = a; H_voff[hy.Hs.size()] = b;
+}
+void ref_hybrid_free(void *rv) { delete (RefHybrid *)rv; }
+}

@@ -254,3 +254,26 @@ def hausdorff_ratio(VA, FA, VB, FB, thr):
     ok = lib().ref_hausdorff_ratio(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)),
                                    _p(FB), C.c_int64(len(FB)), C.c_double(thr), C.byref(r))
     return bool(ok), r.value
+
+
+# ---- §8(f)-1: conforming_mesh (grid_hex_meshing.cpp:568-696) -----------------------------------------------------------
+def _export_hybrid(h, sizes):
+    nV, nF, nH, nE, fv, hf, hv, fn = [int(x) for x in sizes]
+    out = dict(nV=nV, nF=nF, nH=nH, nE=nE,
+               F_off=np.zeros(nF + 1, np.int64), F_vs=np.zeros(fv, np.uint32), F_es=np.zeros(fv, np.uint32), F_boundary=np.zeros(nF, np.uint8),
+               E_vs=np.zeros((nE, 2), np.uint32), E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8),
+               H_foff=np.zeros(nH + 1, np.int64), H_fs=np.zeros(hf, np.uint32), H_voff=np.zeros(nH + 1, np.int64), H_vs=np.zeros(hv, np.uint32),
+               F_nhoff=np.zeros(nF + 1, np.int64), F_nhs=np.zeros(fn, np.uint32))
+    lib().ref_hybrid_export(h, _p(out["F_off"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["F_boundary"]), _p(out["E_vs"]), _p(out["E_boundary"]),
+                            _p(out["V_boundary"]), _p(out["H_foff"]), _p(out["H_fs"]), _p(out["H_voff"]), _p(out["H_vs"]), _p(out["F_nhoff"]), _p(out["F_nhs"]))
+    lib().ref_hybrid_free(h)
+    return out
+
+
+def conforming_mesh_tables(node_pos, node_neigh, Vpos, hexa, grid_size):
+    """The reference's conforming_mesh on an octree given as tables (vertex i = node i), any numbering."""
+    npos, nn, Vp, hx, gs = _i32(node_pos), _i32(node_neigh), _f64(Vpos), np.ascontiguousarray(hexa, np.uint32), _i32(grid_size)
+    sizes = (C.c_int64 * 8)()
+    lib().ref_conforming_mesh_tables.restype = C.c_void_p
+    h = C.c_void_p(lib().ref_conforming_mesh_tables(_p(npos), _p(nn), C.c_int64(len(npos)), _p(Vp), _p(hx), C.c_int64(len(hx)), _p(gs), sizes))
+    return _export_hybrid(h, list(sizes))

@@ -486,3 +486,37 @@ def test_signed_distance_exact_ties_and_packets(fp, ctx, ref):
             assert len(bad) == 0, (name, order, len(bad), bad[:5], I[bad[:5]], rI[bad[:5]])
             assert np.array_equal(S, rS) and np.array_equal(C, rC) and np.array_equal(N, rN), (name, order)
         m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["marks_unpaired", "marks_paired", "torus", "gear"])
+def test_conforming_mesh_vs_reference(fp, ctx, ref, case):
+    """conforming_mesh (ghm.cpp:568-696).  The reference function itself (compiled from
+    grid_hex_meshing.cpp) runs on the product's octree tables, so every id and every list order must be equal."""
+    rng = np.random.default_rng(5)
+    if case.startswith("marks"):
+        gs = np.array([32, 16, 16], np.int32)
+        marks = [[x, y, z, 16] for x in (0, 16) for y in (0,) for z in (0,)]
+        for e, k in ((8, 6), (4, 10), (2, 14)):
+            n = gs // e
+            for _ in range(k):
+                marks.append([int(rng.integers(0, n[0])) * e, int(rng.integers(0, n[1])) * e, int(rng.integers(0, n[2])) * e, e])
+        o = fp.Octree.from_marks(ctx, gs, np.array(marks, np.int32), True, case == "marks_paired")
+        grid = gs
+    else:
+        V, F = fp.procedural.torus(48, 24) if case == "torus" else fp.procedural.gear()[:2]
+        prm = fp.octree_grid_setup(V, 1 << 20)
+        prm.c.stop_extent = 1 << (14 if case == "torus" else 14)
+        o = fp.Octree.build(ctx, fp.TriMesh(ctx, V, F), prm)
+        grid = prm.grid_size
+    ex = o.export()
+    Vp, H, _ = o.hexes()
+    got = fp.conforming_mesh(ctx, o, H)
+    want = ref.conforming_mesh_tables(ex["node_pos"], ex["node_neigh"], Vp, H, grid)
+    assert got["n_replaced"] > 0, "the case has no T-junction face"
+    for k in ("nV", "nF", "nH", "nE"):
+        assert got[k] == want[k], (case, k, got[k], want[k])
+    for k in ("F_off", "F_vs", "H_foff", "H_fs", "H_voff", "H_vs", "E_vs", "F_es", "F_boundary", "E_boundary", "V_boundary", "F_nhoff", "F_nhs"):
+        assert np.array_equal(got[k], want[k]), (case, k)
+    sizes = np.bincount(np.diff(got["F_off"]))
+    assert sizes[:4].sum() == 0 and sizes[5:].sum() > 0        # loops of 4..8 vertices, some of them with inserted mid vertices
