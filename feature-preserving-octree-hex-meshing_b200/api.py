@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
-    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "conforming_mesh", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "conforming_mesh", "conforming_mesh_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
 
@@ -384,6 +384,21 @@ class HexConnectivity:
             lib().fpohm_conn_free(h)
 
 
+def _hybrid_to_dict(hy):
+    sizes = (C.c_int64 * 8)(); nrep = C.c_int64()
+    _chk(lib().fpohm_hybrid_sizes(hy, sizes, C.byref(nrep)))
+    nV, nF, nH, nE, fv, hf, hv, fn = [int(x) for x in sizes]
+    out = dict(nV=nV, nF=nF, nH=nH, nE=nE, n_replaced=nrep.value,
+               F_off=np.zeros(nF + 1, np.int64), F_vs=np.zeros(fv, np.uint32), F_es=np.zeros(fv, np.uint32), F_boundary=np.zeros(nF, np.uint8),
+               E_vs=np.zeros((nE, 2), np.uint32), E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8),
+               H_foff=np.zeros(nH + 1, np.int64), H_fs=np.zeros(hf, np.uint32), H_voff=np.zeros(nH + 1, np.int64), H_vs=np.zeros(hv, np.uint32),
+               F_nhoff=np.zeros(nF + 1, np.int64), F_nhs=np.zeros(fn, np.uint32))
+    _chk(lib().fpohm_hybrid_export(hy, _p(out["F_off"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["F_boundary"]), _p(out["E_vs"]),
+                                   _p(out["E_boundary"]), _p(out["V_boundary"]), _p(out["H_foff"]), _p(out["H_fs"]), _p(out["H_voff"]),
+                                   _p(out["H_vs"]), _p(out["F_nhoff"]), _p(out["F_nhs"])))
+    return out
+
+
 def conforming_mesh(ctx: Context, octree: "Octree", hexa=None, keep_timing: dict | None = None):
     """conforming_mesh (ghm.cpp:568-696) of the octree's hex mesh: polyhedral mesh as a dict of arrays (CSR for the
     variable-length relations).  `hexa` defaults to the octree's own hexes."""
@@ -399,18 +414,22 @@ def conforming_mesh(ctx: Context, octree: "Octree", hexa=None, keep_timing: dict
         _chk(lib().fpohm_conforming_mesh(ctx.h, octree.h, hc, C.byref(hy)))
         if keep_timing is not None:
             keep_timing["conforming_ms"] = ctx.last_kernel_ms()
-        sizes = (C.c_int64 * 8)(); nrep = C.c_int64()
-        _chk(lib().fpohm_hybrid_sizes(hy, sizes, C.byref(nrep)))
-        nV, nF, nH, nE, fv, hf, hv, fn = [int(x) for x in sizes]
-        out = dict(nV=nV, nF=nF, nH=nH, nE=nE, n_replaced=nrep.value,
-                   F_off=np.zeros(nF + 1, np.int64), F_vs=np.zeros(fv, np.uint32), F_es=np.zeros(fv, np.uint32), F_boundary=np.zeros(nF, np.uint8),
-                   E_vs=np.zeros((nE, 2), np.uint32), E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8),
-                   H_foff=np.zeros(nH + 1, np.int64), H_fs=np.zeros(hf, np.uint32), H_voff=np.zeros(nH + 1, np.int64), H_vs=np.zeros(hv, np.uint32),
-                   F_nhoff=np.zeros(nF + 1, np.int64), F_nhs=np.zeros(fn, np.uint32))
-        _chk(lib().fpohm_hybrid_export(hy, _p(out["F_off"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["F_boundary"]), _p(out["E_vs"]),
-                                       _p(out["E_boundary"]), _p(out["V_boundary"]), _p(out["H_foff"]), _p(out["H_fs"]), _p(out["H_voff"]),
-                                       _p(out["H_vs"]), _p(out["F_nhoff"]), _p(out["F_nhs"])))
-        return out
+        return _hybrid_to_dict(hy)
+    finally:
+        if hy:
+            lib().fpohm_hybrid_free(hy)
+        lib().fpohm_conn_free(hc)
+
+
+def conforming_mesh_tables(ctx: Context, node_pos, node_neigh, hexa, grid_size):
+    """The same for an octree given as tables in any numbering (vertex i = node i)."""
+    npos, nn, gs = _i32(node_pos), _i32(node_neigh), _i32(grid_size)
+    hexa = np.ascontiguousarray(hexa, np.uint32)
+    hc = C.c_void_p(); hy = C.c_void_p()
+    _chk(lib().fpohm_hex_connectivity(ctx.h, _p(hexa), C.c_int64(len(hexa)), C.c_int64(len(npos)), C.byref(hc)))
+    try:
+        _chk(lib().fpohm_conforming_mesh_tables(ctx.h, _p(npos), _p(nn), C.c_int64(len(npos)), _p(gs), hc, C.byref(hy)))
+        return _hybrid_to_dict(hy)
     finally:
         if hy:
             lib().fpohm_hybrid_free(hy)

@@ -271,14 +271,10 @@ int64_t last_of(const int64_t *dev, int64_t n, cudaStream_t s) {   // dev[n] aft
 
 } // namespace
 
-extern "C" {
-
-int fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_conn *conn, fpohm_hybrid **out) {
+static int conforming_impl(fpohm_ctx *ctx, const int32_t *node_pos_dev, const int32_t *node_neigh_dev, int64_t n_nodes, const int32_t gs[3],
+                           const fpohm_conn *conn, fpohm_hybrid **out)
+{
 	FPOHM_API_BEGIN
-	FPOHM_REQUIRE(ctx && oct && conn && out, FPOHM_EINVAL, "fpohm_conforming_mesh: null argument");
-	FPOHM_REQUIRE(conn->nV == oct->n_nodes && conn->H == oct->n_leaves, FPOHM_EINVAL,
-	              "fpohm_conforming_mesh: the connectivity (%lld vertices, %lld hexes) is not that of this octree's hex mesh (%lld nodes, %lld leaves)",
-	              (long long)conn->nV, (long long)conn->H, (long long)oct->n_nodes, (long long)oct->n_leaves);
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
 	const int blk = 256;
@@ -290,8 +286,7 @@ int fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_c
 		DevBuf<int32_t> rel(4 * nF, s), corv(5 * nF, s), e_midv(std::max<int64_t>(nE, 1), s);
 		FPOHM_CUDA(cudaMemsetAsync(rel.p, 0xff, 16 * (size_t)nF, s));
 		FPOHM_CUDA(cudaMemsetAsync(e_midv.p, 0xff, 4 * (size_t)nE, s));
-		tnode_kernel<<<grid_for(ctx, nV, 128), 128, 0, s>>>(oct->node_pos.p, oct->node_neigh.p, nV, oct->prm.grid_size[0], oct->prm.grid_size[1],
-			oct->prm.grid_size[2], conn->V_boundary.p, conn->off[5].p, conn->val[5].p, conn->F_vs.p, rel.p, corv.p);
+		tnode_kernel<<<grid_for(ctx, nV, 128), 128, 0, s>>>(node_pos_dev, node_neigh_dev, nV, gs[0], gs[1], gs[2], conn->V_boundary.p, conn->off[5].p, conn->val[5].p, conn->F_vs.p, rel.p, corv.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 		midv_kernel<<<grid_for(ctx, 4 * nF, 128), 128, 0, s>>>(rel.p, corv.p, nF, conn->F_es.p, conn->E_vs.p, conn->off[3].p, conn->val[3].p, e_midv.p);
 		FPOHM_LAUNCH_CHECK(ctx);
@@ -382,6 +377,33 @@ int fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_c
 		timer.stop();
 	} catch (...) { delete hy; throw; }
 	*out = hy;
+	(void)n_nodes;
+	FPOHM_API_END
+}
+
+extern "C" {
+
+int fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_conn *conn, fpohm_hybrid **out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && oct && conn && out, FPOHM_EINVAL, "fpohm_conforming_mesh: null argument");
+	FPOHM_REQUIRE(conn->nV == oct->n_nodes && conn->H == oct->n_leaves, FPOHM_EINVAL,
+	              "fpohm_conforming_mesh: the connectivity (%lld vertices, %lld hexes) is not that of this octree's hex mesh (%lld nodes, %lld leaves)",
+	              (long long)conn->nV, (long long)conn->H, (long long)oct->n_nodes, (long long)oct->n_leaves);
+	return conforming_impl(ctx, oct->node_pos.p, oct->node_neigh.p, oct->n_nodes, oct->prm.grid_size, conn, out);
+	FPOHM_API_END
+}
+
+int fpohm_conforming_mesh_tables(fpohm_ctx *ctx, const int32_t *node_pos, const int32_t *node_neigh, int64_t n_nodes,
+                                 const int32_t grid_size[3], const fpohm_conn *conn, fpohm_hybrid **out)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && node_pos && node_neigh && grid_size && conn && out, FPOHM_EINVAL, "fpohm_conforming_mesh_tables: null argument");
+	FPOHM_REQUIRE(conn->nV == n_nodes, FPOHM_EINVAL, "fpohm_conforming_mesh_tables: %lld nodes but the connectivity has %lld vertices",
+	              (long long)n_nodes, (long long)conn->nV);
+	DeviceGuard g(ctx->device);
+	DevBuf<int32_t> dpos(3 * n_nodes, ctx->stream), dnn(6 * n_nodes, ctx->stream);
+	dpos.upload(node_pos, 3 * n_nodes); dnn.upload(node_neigh, 6 * n_nodes);
+	return conforming_impl(ctx, dpos.p, dnn.p, n_nodes, grid_size, conn, out);     // (synchronises before returning)
 	FPOHM_API_END
 }
 

@@ -239,6 +239,10 @@ void fpohm_conn_free(fpohm_conn *c);
  * reference's for the same input numbering.  sizes = {nV, nF, nH, nE, sum |F.vs|, sum |H.fs|, sum |H.vs|, sum |F.nhs|}. */
 typedef struct fpohm_hybrid fpohm_hybrid;
 int  fpohm_conforming_mesh(fpohm_ctx *ctx, const fpohm_octree *oct, const fpohm_conn *conn, fpohm_hybrid **out);
+/* the same for an octree given as host tables in ANY numbering (e.g. the reference's own OctreeGrid: m_Nodes[i].position /
+ * .neighNodeId); vertex i of `conn` = node i */
+int  fpohm_conforming_mesh_tables(fpohm_ctx *ctx, const int32_t *node_pos, const int32_t *node_neigh, int64_t n_nodes,
+                                  const int32_t grid_size[3], const fpohm_conn *conn, fpohm_hybrid **out);
 int  fpohm_hybrid_sizes(const fpohm_hybrid *hy, int64_t sizes[8], int64_t *n_replaced_faces);
 int  fpohm_hybrid_export(const fpohm_hybrid *hy, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs,
                          uint8_t *E_boundary, uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs,

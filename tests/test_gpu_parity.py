@@ -1,4 +1,6 @@
 """GPU parity tests: CUDA path (through the C-ABI) vs the reference's own code (oracle/_ref)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -520,3 +522,15 @@ def test_conforming_mesh_vs_reference(fp, ctx, ref, case):
         assert np.array_equal(got[k], want[k]), (case, k)
     sizes = np.bincount(np.diff(got["F_off"]))
     assert sizes[:4].sum() == 0 and sizes[5:].sum() > 0        # loops of 4..8 vertices, some of them with inserted mid vertices
+
+
+@pytest.mark.gpu
+def test_conforming_mesh_tables_vs_golden(fp, ctx):
+    """The committed fixtures (reference octree numbering, reference conforming_mesh output) through the table entry."""
+    g = dict(np.load(Path(__file__).resolve().parent / "golden" / "golden_conforming_v1.npz"))
+    for name in ("a", "b", "c"):
+        got = fp.conforming_mesh_tables(ctx, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_hex"], g[f"{name}_grid"])
+        for k, v in g.items():
+            if k.startswith(f"{name}_out_"):
+                kk = k[len(name) + 5:]
+                assert np.array_equal(np.asarray(got[kk]).reshape(-1), np.asarray(v).reshape(-1)), (name, kk)

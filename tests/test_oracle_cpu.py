@@ -241,3 +241,27 @@ print("OK", r)
                           "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("OK") == 2
+
+
+# ---- §8(f)-1 conforming_mesh: port vs golden, golden vs live reference --------------------------------------------------
+def _conf_cases():
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_conforming_v1.npz"))
+    for name in ("a", "b", "c"):
+        want = {k[len(name) + 5:]: v for k, v in g.items() if k.startswith(f"{name}_out_")}
+        yield name, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_hex"], g[f"{name}_grid"], want
+
+
+def _same_hybrid(got, want):
+    for k, v in want.items():
+        assert np.array_equal(np.asarray(got[k]).reshape(-1), np.asarray(v).reshape(-1)), k
+
+
+def test_port_conforming_mesh_vs_golden(port):
+    for name, npos, nn, H, gs, want in _conf_cases():
+        _same_hybrid(port.conforming_mesh(npos, nn, H, gs), want)
+
+
+def test_golden_conforming_matches_live_reference(ref):
+    for name, npos, nn, H, gs, want in _conf_cases():
+        Vp = npos.astype(np.float64)
+        _same_hybrid(ref.conforming_mesh_tables(npos, nn, Vp, H, gs), want)
