@@ -14,6 +14,7 @@
 //        callers ghm.cpp:2273,2603,3771,4045,4074
 //   build_connectivity(Mesh&)  [Hex]               gf.cpp:16,121-264     build_connectivity(hmi)
 //   OctreeGrid                                     octree.h:62-270       class OctreeGrid (same public members)
+//   conforming_mesh(mo, hybrid, octree, grid_size) ghm.cpp:568           conforming_mesh(mo, hybrid, octree, grid_size)
 //   octree_mesh(GEO::Mesh&, Mesh&, OctreeGrid&, Vector3i&) ghm.cpp:460   octree_mesh(ctx, V, nV, F, nF, mo, octree, grid_size, ...)
 //   compute_sign(M, aabb, VoxelGrid<T>&)           voxelization.h:220    compute_sign(mesh, voxels)
 //   compute_octree(M, mo, aabb, ...)               voxelization.cpp:353  compute_octree(mesh, octree, ..., Vpos, hex, inside)
@@ -191,6 +192,68 @@ void build_connectivity(MeshT &hmi) {
 	fill(5, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_fs; });
 	fill(6, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_hs; });
 	fpohm_conn_free(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// grid_hex_meshing_bijective::conforming_mesh(Mesh &mo, Mesh &hybrid, OctreeGrid &octree, Vector3i &grid_size),
+// ghm.cpp:568-696.  `octree` is anything with the reference's public node table (m_Nodes[i].position /
+// .neighNodeId): the reference's own OctreeGrid or fpohm_shim::OctreeGrid.  `mo` is the octree hex mesh (vertex i = node i);
+// its connectivity is rebuilt on the device, so build_connectivity(mo) need not have run.  Fills `hybrid` completely,
+// including the adjacency lists build_connectivity(Hyb) leaves behind (gf.cpp:187-264).
+template <class MeshT, class OctreeT, class Vec3iT>
+void conforming_mesh(MeshT &mo, MeshT &hybrid, OctreeT &octree, Vec3iT &grid_size) {
+	const int64_t nV = (int64_t)mo.Vs.size(), H = (int64_t)mo.Hs.size();
+	std::vector<int32_t> npos(3 * (size_t)nV), nn(6 * (size_t)nV);
+	for (int64_t i = 0; i < nV; ++i) {
+		for (int d = 0; d < 3; ++d) npos[3 * i + d] = octree.m_Nodes[(size_t)i].position[d];
+		for (int k = 0; k < 6; ++k) nn[6 * i + k] = octree.m_Nodes[(size_t)i].neighNodeId[k];
+	}
+	std::vector<uint32_t> hex(8 * (size_t)H);
+	for (int64_t i = 0; i < H; ++i) for (int k = 0; k < 8; ++k) hex[8 * i + k] = mo.Hs[i].vs[k];
+	const int32_t gs[3] = {(int32_t)grid_size[0], (int32_t)grid_size[1], (int32_t)grid_size[2]};
+	fpohm_conn *c = nullptr; fpohm_hybrid *hy = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), H, nV, &c), "fpohm_hex_connectivity");
+	const int rc = fpohm_conforming_mesh_tables(context(), npos.data(), nn.data(), nV, gs, c, &hy);
+	fpohm_conn_free(c);
+	check(rc, "fpohm_conforming_mesh_tables");
+	int64_t sz[8];
+	fpohm_hybrid_sizes(hy, sz, nullptr);
+	const int64_t nF = sz[1], nE = sz[3];
+	std::vector<int64_t> F_off(nF + 1), H_foff(H + 1), H_voff(H + 1), F_nhoff(nF + 1);
+	std::vector<uint32_t> F_vs(sz[4]), F_es(sz[4]), E_vs(2 * nE), H_fs(sz[5]), H_vs(sz[6]), F_nhs(sz[7]);
+	std::vector<uint8_t> Fb(nF), Eb(nE), Vb(nV);
+	const int rc2 = fpohm_hybrid_export(hy, F_off.data(), F_vs.data(), F_es.data(), Fb.data(), E_vs.data(), Eb.data(), Vb.data(), H_foff.data(),
+	                                    H_fs.data(), H_voff.data(), H_vs.data(), F_nhoff.data(), F_nhs.data());
+	fpohm_hybrid_free(hy);
+	check(rc2, "fpohm_hybrid_export");
+	hybrid.type = decltype(mo.type)(4);               // Mesh_type::Hyb (global_types.h:457-465)
+	hybrid.V = mo.V;
+	hybrid.Vs.clear(); hybrid.Vs.resize(nV); hybrid.Fs.clear(); hybrid.Fs.resize(nF); hybrid.Es.clear(); hybrid.Es.resize(nE); hybrid.Hs.clear(); hybrid.Hs.resize(H);
+	for (int64_t v = 0; v < nV; ++v) { auto &x = hybrid.Vs[v]; x.id = (uint32_t)v; x.v = mo.Vs[v].v; x.boundary = Vb[v]; }
+	for (int64_t f = 0; f < nF; ++f) {
+		auto &x = hybrid.Fs[f]; x.id = (uint32_t)f; x.boundary = Fb[f];
+		x.vs.assign(F_vs.begin() + F_off[f], F_vs.begin() + F_off[f + 1]); x.es.assign(F_es.begin() + F_off[f], F_es.begin() + F_off[f + 1]);
+		x.neighbor_hs.assign(F_nhs.begin() + F_nhoff[f], F_nhs.begin() + F_nhoff[f + 1]);
+	}
+	for (int64_t e = 0; e < nE; ++e) { auto &x = hybrid.Es[e]; x.id = (uint32_t)e; x.boundary = Eb[e]; x.vs = {E_vs[2 * e], E_vs[2 * e + 1]}; }
+	for (int64_t h = 0; h < H; ++h) {
+		auto &x = hybrid.Hs[h]; x.id = (uint32_t)h;
+		x.fs.assign(H_fs.begin() + H_foff[h], H_fs.begin() + H_foff[h + 1]); x.vs.assign(H_vs.begin() + H_voff[h], H_vs.begin() + H_voff[h + 1]);
+	}
+	// remaining adjacency lists, in the reference's visiting orders (gf.cpp:231-264): plain appends of the tables above
+	for (int64_t f = 0; f < nF; ++f) {
+		for (uint32_t e : hybrid.Fs[f].es) hybrid.Es[e].neighbor_fs.push_back((uint32_t)f);
+		for (uint32_t v : hybrid.Fs[f].vs) hybrid.Vs[v].neighbor_fs.push_back((uint32_t)f);
+	}
+	for (int64_t e = 0; e < nE; ++e) {
+		const uint32_t v0 = hybrid.Es[e].vs[0], v1 = hybrid.Es[e].vs[1];
+		hybrid.Vs[v0].neighbor_es.push_back((uint32_t)e); hybrid.Vs[v1].neighbor_es.push_back((uint32_t)e);
+		hybrid.Vs[v0].neighbor_vs.push_back(v1); hybrid.Vs[v1].neighbor_vs.push_back(v0);
+		std::set<uint32_t> hs;
+		for (uint32_t f : hybrid.Es[e].neighbor_fs) hs.insert(hybrid.Fs[f].neighbor_hs.begin(), hybrid.Fs[f].neighbor_hs.end());
+		hybrid.Es[e].neighbor_hs.assign(hs.begin(), hs.end());
+	}
+	for (int64_t h = 0; h < H; ++h) for (uint32_t v : hybrid.Hs[h].vs) hybrid.Vs[v].neighbor_hs.push_back((uint32_t)h);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

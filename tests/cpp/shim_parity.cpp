@@ -7,6 +7,7 @@
 #include "global_types.h"
 #include "global_functions.h"
 #include "metro_hausdorff.h"
+#include "grid_meshing/grid_hex_meshing.h"
 #include <igl/signed_distance.h>
 #include <geogram/basic/common.h>
 #include <geogram/basic/logger.h>
@@ -121,6 +122,44 @@ int main() {
 		for (int c = 0; same && c < ref.numCells(); ++c) if (ref.cellIsLeaf(c)) { auto p = ref.cellCornerPos(c, 0); la.insert({{p[0], p[1], p[2], ref.cellExtent(c)}}); }
 		for (int c = 0; same && c < mine.numCells(); ++c) if (mine.cellIsLeaf(c)) { auto p = mine.cellCornerPos(c, 0); lb.insert({{p[0], p[1], p[2], mine.cellExtent(c)}}); }
 		EXPECT(same && la == lb && mine.is2to1Graded() && mine.isPaired() && ref.is2to1Graded() && ref.isPaired(), "OctreeGrid::subdivide(std::function) same leaf set, graded, paired");
+	}
+	// ---- conforming_mesh (ghm.cpp:568-696) on the reference's own OctreeGrid: the class method vs the shim
+	{
+		auto pred = [](int x, int y, int z, int e) {
+			if (e <= 2) return false;
+			const double cx = x + e * 0.5 - 20, cy = y + e * 0.5 - 14, cz = z + e * 0.5 - 9, r = std::sqrt(cx * cx + cy * cy + cz * cz);
+			return std::fabs(r - 9.0) < e * 0.8;
+		};
+		::OctreeGrid oct(Eigen::Vector3i(32, 32, 16));
+		oct.subdivide(pred, true, true);
+		auto octree_hex_mesh = [&](Mesh &m) {
+			m.type = Mesh_type::Hex;
+			m.Vs.resize(oct.numNodes()); m.V.resize(3, oct.numNodes());
+			for (int i = 0; i < oct.numNodes(); ++i) {
+				Hybrid_V v; v.id = i;
+				for (int d = 0; d < 3; ++d) { v.v.push_back(oct.nodePos(i)[d]); m.V(d, i) = oct.nodePos(i)[d]; }
+				m.Vs[i] = v;
+			}
+			for (int q = 0; q < oct.numCells(); ++q) if (oct.cellIsLeaf(q)) {
+				Hybrid h; h.id = (uint32_t)m.Hs.size(); h.vs.resize(8);
+				for (int lv = 0; lv < 8; ++lv) h.vs[lv] = oct.cellCornerId(q, lv);
+				m.Hs.push_back(h);
+			}
+		};
+		Mesh ma, mb, ha, hb;
+		octree_hex_mesh(ma); octree_hex_mesh(mb);
+		::build_connectivity(ma);
+		Eigen::Vector3i gs(32, 32, 16);
+		grid_hex_meshing_bijective gm;
+		gm.conforming_mesh(ma, ha, oct, gs);
+		fpohm_shim::conforming_mesh(mb, hb, oct, gs);
+		bool same = ha.Fs.size() == hb.Fs.size() && ha.Es.size() == hb.Es.size() && ha.Hs.size() == hb.Hs.size() && ha.Vs.size() == hb.Vs.size() && ha.type == hb.type;
+		size_t polygons = 0;
+		for (size_t i = 0; same && i < ha.Fs.size(); ++i) { same = ha.Fs[i].vs == hb.Fs[i].vs && ha.Fs[i].es == hb.Fs[i].es && ha.Fs[i].boundary == hb.Fs[i].boundary && ha.Fs[i].neighbor_hs == hb.Fs[i].neighbor_hs; polygons += ha.Fs[i].vs.size() > 4; }
+		for (size_t i = 0; same && i < ha.Es.size(); ++i) same = ha.Es[i].vs == hb.Es[i].vs && ha.Es[i].boundary == hb.Es[i].boundary && ha.Es[i].neighbor_fs == hb.Es[i].neighbor_fs && ha.Es[i].neighbor_hs == hb.Es[i].neighbor_hs;
+		for (size_t i = 0; same && i < ha.Vs.size(); ++i) same = ha.Vs[i].boundary == hb.Vs[i].boundary && ha.Vs[i].neighbor_vs == hb.Vs[i].neighbor_vs && ha.Vs[i].neighbor_es == hb.Vs[i].neighbor_es && ha.Vs[i].neighbor_fs == hb.Vs[i].neighbor_fs && ha.Vs[i].neighbor_hs == hb.Vs[i].neighbor_hs && ha.Vs[i].v == hb.Vs[i].v;
+		for (size_t i = 0; same && i < ha.Hs.size(); ++i) same = ha.Hs[i].fs == hb.Hs[i].fs && ha.Hs[i].vs == hb.Hs[i].vs;
+		EXPECT(same && polygons > 0 && ha.Fs.size() < ma.Fs.size(), "conforming_mesh identical polyhedral mesh (loops, cells, edges, all adjacency lists)");
 	}
 	// ---- compute_octree: the one public end-to-end entry of voxelization.h (bbox octree to extent 1 + ray parity + hex export)
 	{
