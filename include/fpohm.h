@@ -248,6 +248,14 @@ int  fpohm_hybrid_export(const fpohm_hybrid *hy, int64_t *F_off, uint32_t *F_vs,
                          uint8_t *E_boundary, uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs,
                          int64_t *F_nhoff, uint32_t *F_nhs);
 void fpohm_hybrid_free(fpohm_hybrid *hy);
+/* dual_conforming_mesh (grid_hex_meshing.cpp:697-872): the dual polyhedral mesh of `hy` (vertices = centres of the hexes
+ * of the octree mesh `Vpos`/`hex`, one face per interior edge, one cell per interior vertex), its connectivity, and the
+ * element-type census with each cell's vertex list re-ordered for its template (Element_Type, global_types.h:40-48:
+ * 0 tetrahedral (also: unrecognised, empty list) 1 slab 2 pyramid 3 prism 4 pyramid-combine 5 tet-combine 6 hexahedral).
+ * The result is read with fpohm_hybrid_sizes / _export plus fpohm_hybrid_dual_extra. */
+int  fpohm_dual_conforming_mesh(fpohm_ctx *ctx, const fpohm_hybrid *hy, const double *Vpos, int64_t nV, const uint32_t *hex, int64_t n_hex,
+                                fpohm_hybrid **out);
+int  fpohm_hybrid_dual_extra(const fpohm_hybrid *dual, double *V, int32_t *h_type, int64_t census[7]);
 
 
 /* voxel_meshing lattice (ghm.cpp:215-296, the `--o 0` path): dim[d] = ceil(extent/len), float grid_length,

@@ -11,7 +11,7 @@ extern "C" {
 const OctreeGrid *ref_octree_grid(void *hv);
 void ref_octree_frame(void *hv, double origin[3], double mesh_transform[3], double *voxel_size, int32_t grid_size[3]);
 
-struct RefHybrid { Mesh mo, hybrid; };
+struct RefHybrid { Mesh mo, hybrid, dual; std::vector<Element_Type> types; };
 
 static void fill_sizes(const Mesh &hy, int64_t sizes[8]) {
 	int64_t fv = 0, hf = 0, hv = 0, fn = 0;
@@ -85,10 +85,9 @@ void *ref_conforming_mesh(void *octree_handle, int64_t sizes[8]) {
 }
 // F_off nF+1, F_vs/F_es sizes[4], F_boundary nF, E_vs 2 nE, E_boundary nE, V_boundary nV,
 // H_foff nH+1, H_fs sizes[5], H_voff nH+1, H_vs sizes[6], F_nhoff nF+1, F_nhs sizes[7]
-void ref_hybrid_export(void *rv, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs, uint8_t *E_boundary,
-                       uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs, int64_t *F_nhoff, uint32_t *F_nhs)
+static void export_mesh(const Mesh &hy, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs, uint8_t *E_boundary,
+                        uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs, int64_t *F_nhoff, uint32_t *F_nhs)
 {
-	const Mesh &hy = ((RefHybrid *)rv)->hybrid;
 	int64_t t = 0, u = 0;
 	for (size_t f = 0; f < hy.Fs.size(); ++f) {
 		F_off[f] = t; F_nhoff[f] = u;
@@ -106,6 +105,29 @@ void ref_hybrid_export(void *rv, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es,
 		for (uint32_t x : hy.Hs[h].vs) H_vs[b++] = x;
 	}
 	H_foff[hy.Hs.size()] = a; H_voff[hy.Hs.size()] = b;
+}
+void ref_hybrid_export(void *rv, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs, uint8_t *E_boundary,
+                       uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs, int64_t *F_nhoff, uint32_t *F_nhs)
+{
+	export_mesh(((RefHybrid *)rv)->hybrid, F_off, F_vs, F_es, F_boundary, E_vs, E_boundary, V_boundary, H_foff, H_fs, H_voff, H_vs, F_nhoff, F_nhs);
+}
+
+// dual_conforming_mesh (ghm.cpp:697-872) on the result of ref_conforming_mesh*: dual polyhedral mesh + element types
+void ref_dual_conforming_mesh(void *rv, int64_t sizes[8]) {
+	RefHybrid *r = (RefHybrid *)rv;
+	grid_hex_meshing_bijective gm;
+	r->dual = Mesh(); r->types.clear();
+	gm.dual_conforming_mesh(r->mo, r->hybrid, r->dual, r->types);
+	fill_sizes(r->dual, sizes);
+}
+void ref_dual_export(void *rv, double *V, int32_t *h_type, int64_t *F_off, uint32_t *F_vs, uint32_t *F_es, uint8_t *F_boundary, uint32_t *E_vs,
+                     uint8_t *E_boundary, uint8_t *V_boundary, int64_t *H_foff, uint32_t *H_fs, int64_t *H_voff, uint32_t *H_vs, int64_t *F_nhoff, uint32_t *F_nhs)
+{
+	RefHybrid *r = (RefHybrid *)rv;
+	const Mesh &d = r->dual;
+	for (size_t v = 0; v < d.Vs.size(); ++v) for (int k = 0; k < 3; ++k) V[3 * v + k] = d.V(k, v);
+	for (size_t h = 0; h < d.Hs.size(); ++h) h_type[h] = (int32_t)r->types[h];
+	export_mesh(d, F_off, F_vs, F_es, F_boundary, E_vs, E_boundary, V_boundary, H_foff, H_fs, H_voff, H_vs, F_nhoff, F_nhs);
 }
 void ref_hybrid_free(void *rv) { delete (RefHybrid *)rv; }
 }

@@ -266,8 +266,32 @@ def _export_hybrid(h, sizes):
                F_nhoff=np.zeros(nF + 1, np.int64), F_nhs=np.zeros(fn, np.uint32))
     lib().ref_hybrid_export(h, _p(out["F_off"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["F_boundary"]), _p(out["E_vs"]), _p(out["E_boundary"]),
                             _p(out["V_boundary"]), _p(out["H_foff"]), _p(out["H_fs"]), _p(out["H_voff"]), _p(out["H_vs"]), _p(out["F_nhoff"]), _p(out["F_nhs"]))
-    lib().ref_hybrid_free(h)
     return out
+
+
+def _alloc_hybrid(sizes):
+    nV, nF, nH, nE, fv, hf, hv, fn = [int(x) for x in sizes]
+    return dict(nV=nV, nF=nF, nH=nH, nE=nE,
+                F_off=np.zeros(nF + 1, np.int64), F_vs=np.zeros(fv, np.uint32), F_es=np.zeros(fv, np.uint32), F_boundary=np.zeros(nF, np.uint8),
+                E_vs=np.zeros((nE, 2), np.uint32), E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8),
+                H_foff=np.zeros(nH + 1, np.int64), H_fs=np.zeros(hf, np.uint32), H_voff=np.zeros(nH + 1, np.int64), H_vs=np.zeros(hv, np.uint32),
+                F_nhoff=np.zeros(nF + 1, np.int64), F_nhs=np.zeros(fn, np.uint32))
+
+
+def conforming_and_dual_tables(node_pos, node_neigh, Vpos, hexa, grid_size):
+    """conforming_mesh followed by dual_conforming_mesh (ghm.cpp:697-872): (hybrid, dual) with dual["V"], dual["h_type"]."""
+    npos, nn, Vp, hx, gs = _i32(node_pos), _i32(node_neigh), _f64(Vpos), np.ascontiguousarray(hexa, np.uint32), _i32(grid_size)
+    sizes = (C.c_int64 * 8)()
+    lib().ref_conforming_mesh_tables.restype = C.c_void_p
+    h = C.c_void_p(lib().ref_conforming_mesh_tables(_p(npos), _p(nn), C.c_int64(len(npos)), _p(Vp), _p(hx), C.c_int64(len(hx)), _p(gs), sizes))
+    hyb = _export_hybrid(h, list(sizes))
+    lib().ref_dual_conforming_mesh(h, sizes)
+    d = _alloc_hybrid(list(sizes))
+    d["V"] = np.zeros((d["nV"], 3)); d["h_type"] = np.zeros(d["nH"], np.int32)
+    lib().ref_dual_export(h, _p(d["V"]), _p(d["h_type"]), _p(d["F_off"]), _p(d["F_vs"]), _p(d["F_es"]), _p(d["F_boundary"]), _p(d["E_vs"]), _p(d["E_boundary"]),
+                          _p(d["V_boundary"]), _p(d["H_foff"]), _p(d["H_fs"]), _p(d["H_voff"]), _p(d["H_vs"]), _p(d["F_nhoff"]), _p(d["F_nhs"]))
+    lib().ref_hybrid_free(h)
+    return hyb, d
 
 
 def conforming_mesh_tables(node_pos, node_neigh, Vpos, hexa, grid_size):
@@ -276,4 +300,6 @@ def conforming_mesh_tables(node_pos, node_neigh, Vpos, hexa, grid_size):
     sizes = (C.c_int64 * 8)()
     lib().ref_conforming_mesh_tables.restype = C.c_void_p
     h = C.c_void_p(lib().ref_conforming_mesh_tables(_p(npos), _p(nn), C.c_int64(len(npos)), _p(Vp), _p(hx), C.c_int64(len(hx)), _p(gs), sizes))
-    return _export_hybrid(h, list(sizes))
+    out = _export_hybrid(h, list(sizes))
+    lib().ref_hybrid_free(h)
+    return out

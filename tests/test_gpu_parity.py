@@ -534,3 +534,37 @@ def test_conforming_mesh_tables_vs_golden(fp, ctx):
             if k.startswith(f"{name}_out_"):
                 kk = k[len(name) + 5:]
                 assert np.array_equal(np.asarray(got[kk]).reshape(-1), np.asarray(v).reshape(-1)), (name, kk)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["marks_unpaired", "marks_paired", "torus", "gear"])
+def test_dual_conforming_mesh_vs_reference(fp, ctx, ref, case):
+    """SURVEY.md §8f-1, second half: dual_conforming_mesh (ghm.cpp:697-872) — dual vertices (bit-exact centres), ring
+    faces, cells, their connectivity, element types and the template-ordered vertex lists, against the reference method."""
+    rng = np.random.default_rng(6)
+    if case.startswith("marks"):
+        gs = np.array([32, 16, 16], np.int32)
+        marks = [[x, 0, 0, 16] for x in (0, 16)]
+        for e, k in ((8, 6), (4, 10), (2, 14)):
+            n = gs // e
+            for _ in range(k):
+                marks.append([int(rng.integers(0, n[0])) * e, int(rng.integers(0, n[1])) * e, int(rng.integers(0, n[2])) * e, e])
+        o = fp.Octree.from_marks(ctx, gs, np.array(marks, np.int32), True, case == "marks_paired")
+        grid = gs
+    else:
+        V, F = fp.procedural.torus(48, 24) if case == "torus" else fp.procedural.gear()[:2]
+        prm = fp.octree_grid_setup(V, 1 << 20)
+        prm.c.stop_extent = 1 << 14
+        o = fp.Octree.build(ctx, fp.TriMesh(ctx, V, F), prm)
+        grid = prm.grid_size
+    ex = o.export()
+    Vp, H, _ = o.hexes()
+    hyb, dual = fp.conforming_and_dual(ctx, o)
+    rh, rd = ref.conforming_and_dual_tables(ex["node_pos"], ex["node_neigh"], Vp, H, grid)
+    for k in ("nV", "nF", "nH", "nE"):
+        assert dual[k] == rd[k], (case, k, dual[k], rd[k])
+    assert np.array_equal(dual["V"], rd["V"]), case                                   # centres: same sums, bit for bit
+    for k in ("F_off", "F_vs", "H_foff", "H_fs", "h_type", "H_voff", "H_vs", "E_vs", "F_es", "F_boundary", "E_boundary", "V_boundary", "F_nhoff", "F_nhs"):
+        assert np.array_equal(dual[k], rd[k]), (case, k)
+    assert np.array_equal(dual["census"][1:], np.bincount(rd["h_type"], minlength=7)[1:])
+    assert len(np.unique(rd["h_type"])) >= 3                                            # the case exercises several templates
