@@ -15,6 +15,7 @@
 //   build_connectivity(Mesh&)  [Hex]               gf.cpp:16,121-264     build_connectivity(hmi)
 //   OctreeGrid                                     octree.h:62-270       class OctreeGrid (same public members)
 //   conforming_mesh(mo, hybrid, octree, grid_size) ghm.cpp:568           conforming_mesh(mo, hybrid, octree, grid_size)
+//   dual_conforming_mesh(mo, hybrid, hs, h_type)   ghm.cpp:697           conforming_and_dual_mesh(mo, hybrid, hs, h_type, octree, grid_size)
 //   octree_mesh(GEO::Mesh&, Mesh&, OctreeGrid&, Vector3i&) ghm.cpp:460   octree_mesh(ctx, V, nV, F, nF, mo, octree, grid_size, ...)
 //   compute_sign(M, aabb, VoxelGrid<T>&)           voxelization.h:220    compute_sign(mesh, voxels)
 //   compute_octree(M, mo, aabb, ...)               voxelization.cpp:353  compute_octree(mesh, octree, ..., Vpos, hex, inside)
@@ -254,6 +255,93 @@ void conforming_mesh(MeshT &mo, MeshT &hybrid, OctreeT &octree, Vec3iT &grid_siz
 		hybrid.Es[e].neighbor_hs.assign(hs.begin(), hs.end());
 	}
 	for (int64_t h = 0; h < H; ++h) for (uint32_t v : hybrid.Hs[h].vs) hybrid.Vs[v].neighbor_hs.push_back((uint32_t)h);
+}
+
+// helper: fill a reference Mesh of type Hyb from a device polyhedral mesh, adjacency lists included (gf.cpp:226-264 orders)
+template <class MeshT>
+void fill_hybrid_mesh(fpohm_hybrid *hy, MeshT &m) {
+	int64_t sz[8];
+	fpohm_hybrid_sizes(hy, sz, nullptr);
+	const int64_t nV = sz[0], nF = sz[1], H = sz[2], nE = sz[3];
+	std::vector<int64_t> F_off(nF + 1), H_foff(H + 1), H_voff(H + 1), F_nhoff(nF + 1);
+	std::vector<uint32_t> F_vs(sz[4]), F_es(sz[4]), E_vs(2 * nE), H_fs(sz[5]), H_vs(sz[6]), F_nhs(sz[7]);
+	std::vector<uint8_t> Fb(nF), Eb(nE), Vb(nV);
+	check(fpohm_hybrid_export(hy, F_off.data(), F_vs.data(), F_es.data(), Fb.data(), E_vs.data(), Eb.data(), Vb.data(), H_foff.data(), H_fs.data(),
+	                          H_voff.data(), H_vs.data(), F_nhoff.data(), F_nhs.data()), "fpohm_hybrid_export");
+	m.type = decltype(m.type)(4);                      // Mesh_type::Hyb (global_types.h:457-465)
+	m.Vs.resize(nV); m.Fs.clear(); m.Fs.resize(nF); m.Es.clear(); m.Es.resize(nE); m.Hs.clear(); m.Hs.resize(H);
+	for (int64_t v = 0; v < nV; ++v) {
+		auto &x = m.Vs[v]; x.id = (uint32_t)v; x.boundary = Vb[v];
+		x.neighbor_vs.clear(); x.neighbor_es.clear(); x.neighbor_fs.clear(); x.neighbor_hs.clear();
+	}
+	for (int64_t f = 0; f < nF; ++f) {
+		auto &x = m.Fs[f]; x.id = (uint32_t)f; x.boundary = Fb[f];
+		x.vs.assign(F_vs.begin() + F_off[f], F_vs.begin() + F_off[f + 1]); x.es.assign(F_es.begin() + F_off[f], F_es.begin() + F_off[f + 1]);
+		x.neighbor_hs.assign(F_nhs.begin() + F_nhoff[f], F_nhs.begin() + F_nhoff[f + 1]);
+	}
+	for (int64_t e = 0; e < nE; ++e) { auto &x = m.Es[e]; x.id = (uint32_t)e; x.boundary = Eb[e]; x.vs = {E_vs[2 * e], E_vs[2 * e + 1]}; }
+	for (int64_t h = 0; h < H; ++h) {
+		auto &x = m.Hs[h]; x.id = (uint32_t)h;
+		x.fs.assign(H_fs.begin() + H_foff[h], H_fs.begin() + H_foff[h + 1]); x.vs.assign(H_vs.begin() + H_voff[h], H_vs.begin() + H_voff[h + 1]);
+	}
+	for (int64_t f = 0; f < nF; ++f) {
+		for (uint32_t e : m.Fs[f].es) m.Es[e].neighbor_fs.push_back((uint32_t)f);
+		for (uint32_t v : m.Fs[f].vs) m.Vs[v].neighbor_fs.push_back((uint32_t)f);
+	}
+	for (int64_t e = 0; e < nE; ++e) {
+		const uint32_t v0 = m.Es[e].vs[0], v1 = m.Es[e].vs[1];
+		m.Vs[v0].neighbor_es.push_back((uint32_t)e); m.Vs[v1].neighbor_es.push_back((uint32_t)e);
+		m.Vs[v0].neighbor_vs.push_back(v1); m.Vs[v1].neighbor_vs.push_back(v0);
+		std::set<uint32_t> hs;
+		for (uint32_t f : m.Es[e].neighbor_fs) hs.insert(m.Fs[f].neighbor_hs.begin(), m.Fs[f].neighbor_hs.end());
+		m.Es[e].neighbor_hs.assign(hs.begin(), hs.end());
+	}
+}
+
+// conforming_mesh + dual_conforming_mesh in one call (the reference always runs them back to back, ghm.cpp:416-424):
+// dual_conforming_mesh(Mesh &mo, Mesh &hybrid, Mesh &hybrid_standard, vector<Element_Type> &h_type), ghm.cpp:697-872.
+// Note: `hybrid_standard.Vs[v].neighbor_hs` is left empty: the reference fills it from the vertex sets BEFORE the census
+// rewrites them (gf.cpp:260-263) and nothing downstream reads it (connectivity_modification works from Hs[].vs).
+template <class MeshT, class OctreeT, class Vec3iT, class TypeVecT>
+void conforming_and_dual_mesh(MeshT &mo, MeshT &hybrid, MeshT &hybrid_standard, TypeVecT &h_type, OctreeT &octree, Vec3iT &grid_size) {
+	const int64_t nV = (int64_t)mo.Vs.size(), H = (int64_t)mo.Hs.size();
+	std::vector<int32_t> npos(3 * (size_t)nV), nn(6 * (size_t)nV);
+	for (int64_t i = 0; i < nV; ++i) {
+		for (int d = 0; d < 3; ++d) npos[3 * i + d] = octree.m_Nodes[(size_t)i].position[d];
+		for (int k = 0; k < 6; ++k) nn[6 * i + k] = octree.m_Nodes[(size_t)i].neighNodeId[k];
+	}
+	std::vector<uint32_t> hex(8 * (size_t)H);
+	for (int64_t i = 0; i < H; ++i) for (int k = 0; k < 8; ++k) hex[8 * i + k] = mo.Hs[i].vs[k];
+	std::vector<double> Vp(3 * (size_t)nV);
+	for (int64_t i = 0; i < nV; ++i) for (int d = 0; d < 3; ++d) Vp[3 * i + d] = mo.Vs[i].v[d];
+	const int32_t gs[3] = {(int32_t)grid_size[0], (int32_t)grid_size[1], (int32_t)grid_size[2]};
+	fpohm_conn *c = nullptr; fpohm_hybrid *hy = nullptr, *du = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), H, nV, &c), "fpohm_hex_connectivity");
+	const int rc = fpohm_conforming_mesh_tables(context(), npos.data(), nn.data(), nV, gs, c, &hy);
+	fpohm_conn_free(c);
+	check(rc, "fpohm_conforming_mesh_tables");
+	const int rc2 = fpohm_dual_conforming_mesh(context(), hy, Vp.data(), nV, hex.data(), H, &du);
+	if (rc2 != FPOHM_OK) { fpohm_hybrid_free(hy); check(rc2, "fpohm_dual_conforming_mesh"); }
+	hybrid.V = mo.V; hybrid.Vs.clear(); hybrid.Vs.resize(nV);
+	for (int64_t v = 0; v < nV; ++v) hybrid.Vs[v].v = mo.Vs[v].v;
+	fill_hybrid_mesh(hy, hybrid);
+	for (int64_t h = 0; h < H; ++h) for (uint32_t v : hybrid.Hs[h].vs) hybrid.Vs[v].neighbor_hs.push_back((uint32_t)h);
+	fpohm_hybrid_free(hy);
+	int64_t sz[8];
+	fpohm_hybrid_sizes(du, sz, nullptr);
+	std::vector<double> Vd(3 * (size_t)sz[0]); std::vector<int32_t> ty((size_t)sz[2]); int64_t census[7];
+	check(fpohm_hybrid_dual_extra(du, Vd.data(), ty.data(), census), "fpohm_hybrid_dual_extra");
+	hybrid_standard.V.resize(3, sz[0]); hybrid_standard.Vs.clear(); hybrid_standard.Vs.resize((size_t)sz[0]);
+	for (int64_t v = 0; v < sz[0]; ++v) {
+		hybrid_standard.Vs[v].v = {Vd[3 * v], Vd[3 * v + 1], Vd[3 * v + 2]};
+		for (int d = 0; d < 3; ++d) hybrid_standard.V(d, v) = Vd[3 * v + d];
+	}
+	fill_hybrid_mesh(du, hybrid_standard);
+	fpohm_hybrid_free(du);
+	h_type.resize((size_t)sz[2]);
+	for (int64_t h = 0; h < sz[2]; ++h) h_type[(size_t)h] = (typename TypeVecT::value_type)ty[(size_t)h];
+	std::cout << "total, tetN, slabN, pyramidN, prismN, pyramidcombineN, tetcombineN, hexN: " << sz[2] << " " << census[0] << " " << census[1] << " "
+	          << census[2] << " " << census[3] << " " << census[4] << " " << census[5] << " " << census[6] << std::endl;   // ghm.cpp:871
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

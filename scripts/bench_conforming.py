@@ -23,3 +23,19 @@ for e in (12, 11, 10):
             t = time.perf_counter(); R.conforming_mesh_tables(ex["node_pos"], ex["node_neigh"], Vp, H, prm.grid_size); print(f"   reference (build_connectivity + conforming_mesh, 1 thread): {(time.perf_counter()-t)*1e3:.0f} ms")
         except Exception as ex_:
             print("   reference unavailable:", ex_)
+
+print("--- conforming + dual ---")
+for e in (12, 11):
+    prm = fp.octree_grid_setup(V, 1 << 20); prm.c.stop_extent = 1 << e
+    o = fp.Octree.build(ctx, m, prm)
+    for rep in range(3):
+        tm = {}
+        hyb, d = fp.conforming_and_dual(ctx, o, keep_timing=tm)
+    print(f"e={e}: conforming {tm['conforming_ms']:.2f} ms, dual {tm['dual_ms']:.2f} ms -> dual cells {d['nH']} faces {d['nF']} edges {d['nE']} census {d['census'].tolist()}")
+    if e == 12:
+        try:
+            ex = o.export(); Vp, H, _ = o.hexes()
+            t = time.perf_counter(); R.conforming_and_dual_tables(ex["node_pos"], ex["node_neigh"], Vp, H, prm.grid_size)
+            print(f"   reference (build_connectivity + conforming_mesh + dual_conforming_mesh, 1 thread): {(time.perf_counter()-t)*1e3:.0f} ms")
+        except Exception as ex_:
+            print("   reference unavailable:", ex_)

@@ -160,6 +160,19 @@ int main() {
 		for (size_t i = 0; same && i < ha.Vs.size(); ++i) same = ha.Vs[i].boundary == hb.Vs[i].boundary && ha.Vs[i].neighbor_vs == hb.Vs[i].neighbor_vs && ha.Vs[i].neighbor_es == hb.Vs[i].neighbor_es && ha.Vs[i].neighbor_fs == hb.Vs[i].neighbor_fs && ha.Vs[i].neighbor_hs == hb.Vs[i].neighbor_hs && ha.Vs[i].v == hb.Vs[i].v;
 		for (size_t i = 0; same && i < ha.Hs.size(); ++i) same = ha.Hs[i].fs == hb.Hs[i].fs && ha.Hs[i].vs == hb.Hs[i].vs;
 		EXPECT(same && polygons > 0 && ha.Fs.size() < ma.Fs.size(), "conforming_mesh identical polyhedral mesh (loops, cells, edges, all adjacency lists)");
+		// dual_conforming_mesh (ghm.cpp:697-872): dual mesh + element types, both halves through one shim call
+		Mesh da, mc, hc, dc;
+		std::vector<Element_Type> ta, tc;
+		gm.dual_conforming_mesh(ma, ha, da, ta);
+		octree_hex_mesh(mc);
+		fpohm_shim::conforming_and_dual_mesh(mc, hc, dc, tc, oct, gs);
+		bool sd = da.Fs.size() == dc.Fs.size() && da.Es.size() == dc.Es.size() && da.Hs.size() == dc.Hs.size() && da.Vs.size() == dc.Vs.size() && ta == tc && da.V == dc.V;
+		for (size_t i = 0; sd && i < da.Fs.size(); ++i) sd = da.Fs[i].vs == dc.Fs[i].vs && da.Fs[i].es == dc.Fs[i].es && da.Fs[i].boundary == dc.Fs[i].boundary && da.Fs[i].neighbor_hs == dc.Fs[i].neighbor_hs;
+		for (size_t i = 0; sd && i < da.Es.size(); ++i) sd = da.Es[i].vs == dc.Es[i].vs && da.Es[i].boundary == dc.Es[i].boundary && da.Es[i].neighbor_fs == dc.Es[i].neighbor_fs && da.Es[i].neighbor_hs == dc.Es[i].neighbor_hs;
+		for (size_t i = 0; sd && i < da.Vs.size(); ++i) sd = da.Vs[i].boundary == dc.Vs[i].boundary && da.Vs[i].neighbor_vs == dc.Vs[i].neighbor_vs && da.Vs[i].neighbor_es == dc.Vs[i].neighbor_es && da.Vs[i].neighbor_fs == dc.Vs[i].neighbor_fs && da.Vs[i].v == dc.Vs[i].v;
+		for (size_t i = 0; sd && i < da.Hs.size(); ++i) sd = da.Hs[i].fs == dc.Hs[i].fs && da.Hs[i].vs == dc.Hs[i].vs;
+		std::set<int> kinds(ta.begin(), ta.end());
+		EXPECT(sd && kinds.size() >= 3, "dual_conforming_mesh identical dual mesh, element types and template-ordered vertex lists");
 	}
 	// ---- compute_octree: the one public end-to-end entry of voxelization.h (bbox octree to extent 1 + ray parity + hex export)
 	{

@@ -251,6 +251,13 @@ def _conf_cases():
         yield name, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_hex"], g[f"{name}_grid"], want
 
 
+def _dual_cases():
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_conforming_v1.npz"))
+    for name in ("a", "b", "c"):
+        want = {k[len(name) + 6:]: v for k, v in g.items() if k.startswith(f"{name}_dual_")}
+        yield name, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_hex"], g[f"{name}_grid"], g[f"{name}_Vpos"], want
+
+
 def _same_hybrid(got, want):
     for k, v in want.items():
         assert np.array_equal(np.asarray(got[k]).reshape(-1), np.asarray(v).reshape(-1)), k
@@ -265,3 +272,13 @@ def test_golden_conforming_matches_live_reference(ref):
     for name, npos, nn, H, gs, want in _conf_cases():
         Vp = npos.astype(np.float64)
         _same_hybrid(ref.conforming_mesh_tables(npos, nn, Vp, H, gs), want)
+
+
+def test_port_dual_conforming_mesh_vs_golden(port):
+    for name, npos, nn, H, gs, Vp, want in _dual_cases():
+        _same_hybrid(port.dual_conforming_mesh(port.conforming_mesh(npos, nn, H, gs), Vp, H), want)
+
+
+def test_golden_dual_matches_live_reference(ref):
+    for name, npos, nn, H, gs, Vp, want in _dual_cases():
+        _same_hybrid(ref.conforming_and_dual_tables(npos, nn, Vp, H, gs)[1], want)
