@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
-    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
 
@@ -435,6 +435,28 @@ def conforming_and_dual(ctx: Context, octree: "Octree", keep_timing: dict | None
         _chk(lib().fpohm_dual_conforming_mesh(ctx.h, hy, _p(Vp), C.c_int64(len(Vp)), _p(hexa), C.c_int64(len(hexa)), C.byref(du)))
         if keep_timing is not None:
             keep_timing["dual_ms"] = ctx.last_kernel_ms()
+        hyb = _hybrid_to_dict(hy); d = _hybrid_to_dict(du)
+        d["V"] = np.zeros((d["nV"], 3)); d["h_type"] = np.zeros(d["nH"], np.int32); cen = (C.c_int64 * 7)()
+        _chk(lib().fpohm_hybrid_dual_extra(du, _p(d["V"]), _p(d["h_type"]), cen))
+        d["census"] = np.array(list(cen), np.int64)
+        return hyb, d
+    finally:
+        if du:
+            lib().fpohm_hybrid_free(du)
+        if hy:
+            lib().fpohm_hybrid_free(hy)
+        lib().fpohm_conn_free(hc)
+
+
+def conforming_and_dual_tables(ctx: Context, node_pos, node_neigh, Vpos, hexa, grid_size):
+    """conforming_mesh + dual_conforming_mesh for an octree given as tables in any numbering (vertex i = node i)."""
+    npos, nn, gs, Vp = _i32(node_pos), _i32(node_neigh), _i32(grid_size), _f64(Vpos)
+    hexa = np.ascontiguousarray(hexa, np.uint32)
+    hc = C.c_void_p(); hy = C.c_void_p(); du = C.c_void_p()
+    _chk(lib().fpohm_hex_connectivity(ctx.h, _p(hexa), C.c_int64(len(hexa)), C.c_int64(len(npos)), C.byref(hc)))
+    try:
+        _chk(lib().fpohm_conforming_mesh_tables(ctx.h, _p(npos), _p(nn), C.c_int64(len(npos)), _p(gs), hc, C.byref(hy)))
+        _chk(lib().fpohm_dual_conforming_mesh(ctx.h, hy, _p(Vp), C.c_int64(len(Vp)), _p(hexa), C.c_int64(len(hexa)), C.byref(du)))
         hyb = _hybrid_to_dict(hy); d = _hybrid_to_dict(du)
         d["V"] = np.zeros((d["nV"], 3)); d["h_type"] = np.zeros(d["nH"], np.int32); cen = (C.c_int64 * 7)()
         _chk(lib().fpohm_hybrid_dual_extra(du, _p(d["V"]), _p(d["h_type"]), cen))

@@ -529,11 +529,14 @@ def test_conforming_mesh_tables_vs_golden(fp, ctx):
     """The committed fixtures (reference octree numbering, reference conforming_mesh output) through the table entry."""
     g = dict(np.load(Path(__file__).resolve().parent / "golden" / "golden_conforming_v1.npz"))
     for name in ("a", "b", "c"):
-        got = fp.conforming_mesh_tables(ctx, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_hex"], g[f"{name}_grid"])
+        got, dual = fp.conforming_and_dual_tables(ctx, g[f"{name}_node_pos"], g[f"{name}_node_neigh"], g[f"{name}_Vpos"], g[f"{name}_hex"], g[f"{name}_grid"])
         for k, v in g.items():
             if k.startswith(f"{name}_out_"):
                 kk = k[len(name) + 5:]
                 assert np.array_equal(np.asarray(got[kk]).reshape(-1), np.asarray(v).reshape(-1)), (name, kk)
+            if k.startswith(f"{name}_dual_"):
+                kk = k[len(name) + 6:]
+                assert np.array_equal(np.asarray(dual[kk]).reshape(-1), np.asarray(v).reshape(-1)), (name, "dual", kk)
 
 
 @pytest.mark.gpu
