@@ -296,6 +296,17 @@ def main():
     vb.record(stream); torch.cuda.synchronize()
     vox_ms = va.elapsed_time(vb) / 10
     vox_bytes = vg.num_voxels() + 72 * len(F)
+    # ---- §8(f)-1: conforming + dual polyhedral meshes of the same octree (device kernels, CUDA-event timer of the library) ----
+    conf = None
+    try:
+        tm = {}
+        for _ in range(3):
+            hyb, dual = fp.conforming_and_dual(ctx, oct_, keep_timing=tm)
+        conf = {"conforming_ms": tm["conforming_ms"], "dual_ms": tm["dual_ms"], "faces": int(hyb["nF"]), "replaced_faces": int(hyb["n_replaced"]),
+                "dual_cells": int(dual["nH"]), "census": dual["census"].tolist()}
+        del hyb, dual
+    except Exception as e:  # never hide the headline behind the widening row
+        conf = {"error": str(e)}
     # ---- z-slab sharded octree build (N > 1): slab refine + per-level halo all-gather over NCCL + replicated numbering ----
     sharded = None
     if world > 1:
@@ -362,6 +373,7 @@ def main():
                          "voxel_sign_ms": vox_ms, "voxel_sign_dims": vg.dims.tolist(),
                          "voxel_sign_roofline": {"bound": "hbm", "achieved": vox_bytes / (vox_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                  "frac": vox_bytes / (vox_ms * 1e-3) / 1e9 / peak}}}
+        line["also"]["conforming_dual"] = conf
         if sharded is not None:
             line["also"]["octree_build_zslab_sharded"] = sharded
         if not args.no_cpu_baseline and world == 1:
