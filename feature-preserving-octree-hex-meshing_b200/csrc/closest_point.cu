@@ -242,7 +242,7 @@ closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double
 // no box on its path is farther than the minimum (checked; otherwise one lane does the rigorous re-walk).
 #define PK_STACK 64
 #define PK_WINDOW 32
-#define PK_MIN_WANT 5
+#define PK_MIN_WANT 3
 #define PK_A_BUDGET 1024
 #define PK_EPS_TIE 9.094947017729282e-13      /* 2^-40 */
 #define PK_EPS_WALK 3.637978807091713e-12     /* 2^-38 */
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128, MINB)
 cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *__restrict__ tri,
                  const double *__restrict__ P, int64_t np,
                  double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, double *__restrict__ N,
-                 int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties, int32_t *__restrict__ todo_count)
+                 int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties, int32_t *__restrict__ todo_count, int min_want_sum, int a_budget)
 {
 	__shared__ int32_t s_stack[4][PK_STACK];
 	__shared__ int32_t s_tie[4][PK_TIES][32];
@@ -436,10 +436,10 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
 			if (!(ml | mr)) continue;
 			if ((visits & (PK_WINDOW - 1)) == PK_WINDOW - 1) {
-				if (window < PK_WINDOW * PK_MIN_WANT) { stk[top++] = cur; bail = true; break; }     // the lanes stopped sharing their search
+				if (window < min_want_sum) { stk[top++] = cur; bail = true; break; }     // the lanes stopped sharing their search
 				window = 0;
 			}
-			if (visits >= PK_A_BUDGET || top + 2 > PK_STACK) { stk[top++] = cur; bail = true; break; }
+			if (visits >= a_budget || top + 2 > PK_STACK) { stk[top++] = cur; bail = true; break; }
 			++visits;
 			window += __popc(ml | mr);
 			// nearer child first: majority vote of the lanes that still want this node
@@ -837,10 +837,11 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_CUDA(cudaMemsetAsync(q.cnt.p, 0, 4 * sizeof(int32_t), s));
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
 		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
+		const int min_want = PK_WINDOW * PK_MIN_WANT, a_budget = PK_A_BUDGET;
 		const int qslot = (int)(ctx->q_launches % fpohm_ctx::QRING);
 		FPOHM_CUDA(cudaEventRecord(ctx->q_ev0[qslot], s));
-		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p);
-		else cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p);
+		if (stats) cp_packet_kernel<true, 8><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p, min_want, a_budget);
+		else cp_packet_kernel<false, 7><<<pgrid, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N, q.todo.p, q.todo_ties.p, q.cnt.p, min_want, a_budget);
 		FPOHM_CUDA(cudaEventRecord(ctx->q_ev1[qslot], s));
 		ctx->q_launches++;
 		FPOHM_LAUNCH_CHECK(ctx);
