@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
-    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
+    "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
 ]
 
@@ -382,6 +382,14 @@ class HexConnectivity:
                 setattr(self, nm, (off, val))
         finally:
             lib().fpohm_conn_free(h)
+
+
+def classify_hexes(ctx: Context, surface: "TriMesh", V, hexa):
+    """clean_hex_mesh head (ghm.cpp:1937-1951): (signed_dis at the hex bbox centres, H_flag = inside)."""
+    V = _f64(V); hexa = np.ascontiguousarray(hexa, np.uint32)
+    S = np.zeros(len(hexa)); flag = np.zeros(len(hexa), np.uint8)
+    _chk(lib().fpohm_classify_hexes(ctx.h, surface.h, _p(V), C.c_int64(len(V)), _p(hexa), C.c_int64(len(hexa)), _p(S), _p(flag)))
+    return S, flag
 
 
 def _hybrid_to_dict(hy):

@@ -800,6 +800,19 @@ pseudonormal_kernel(const double *__restrict__ V, const int32_t *__restrict__ F,
 	}
 }
 
+// clean_hex_mesh, ghm.cpp:1937-1951: per hex the centre of the bounding box of its 8 corners, then points_inside_mesh
+__global__ void hex_box_centres_kernel(const double *__restrict__ V, const uint32_t *__restrict__ hex, int64_t H, double *__restrict__ P) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * H; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t h = t / 3; const int c = (int)(t % 3);
+		double mn = V[3 * (int64_t)hex[8 * h] + c], mx = mn;
+		for (int k = 1; k < 8; ++k) { const double x = V[3 * (int64_t)hex[8 * h + k] + c]; mn = fmin(mn, x); mx = fmax(mx, x); }
+		P[t] = (mx + mn) / 2;
+	}
+}
+__global__ void inside_flags_kernel(const double *__restrict__ S, int64_t n, uint8_t *__restrict__ flag) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) flag[t] = S[t] < 0 ? 1 : 0;
+}
+
 } // namespace
 
 namespace fpohm {
@@ -949,6 +962,33 @@ int fpohm_signed_distance(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P, int
                           double *S, int32_t *I, double *C, double *N)
 {
 	return host_query(ctx, mesh, true, P, np, S, I, C, N, "fpohm_signed_distance");
+}
+
+int fpohm_classify_hexes(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, int64_t nV, const uint32_t *hex, int64_t H,
+                         double *signed_dis, uint8_t *H_flag)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && surface && V && hex && nV > 0 && H >= 0, FPOHM_EINVAL, "fpohm_classify_hexes: bad argument");
+	if (H == 0) return FPOHM_OK;
+	for (int64_t i = 0; i < 8 * H; ++i) FPOHM_REQUIRE((int64_t)hex[i] < nV, FPOHM_EINVAL, "fpohm_classify_hexes: corner id %u out of range at %lld", hex[i], (long long)i);
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	mesh_ensure_tree(ctx, surface, s);
+	DevBuf<double> dV(3 * nV, s), dP(3 * H, s), dS(H, s);
+	DevBuf<uint32_t> dhex(8 * H, s);
+	DevBuf<uint8_t> dF(H, s);
+	dV.upload(V, 3 * nV); dhex.upload(hex, 8 * H);
+	KernelTimer t(ctx, s);
+	hex_box_centres_kernel<<<grid_for(ctx, 3 * H, 256), 256, 0, s>>>(dV.p, dhex.p, H, dP.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	launch_closest_point(ctx, surface, true, dP.p, H, dS.p, nullptr, nullptr, nullptr, s);
+	inside_flags_kernel<<<grid_for(ctx, H, 256), 256, 0, s>>>(dS.p, H, dF.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	t.stop();
+	if (signed_dis) dS.download(signed_dis, H);
+	if (H_flag) dF.download(H_flag, H);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
 }
 
 int fpohm_point_mesh_sqdist(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P, int64_t np,

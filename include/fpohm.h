@@ -220,6 +220,11 @@ int fpohm_scaled_jacobian_dev(fpohm_ctx *ctx, const double *V_dev, int64_t nV, c
 int fpohm_hausdorff(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, int64_t extra_face_samples,
                     double out[7], int64_t n_samples[2]);
 
+/* The data-parallel head of clean_hex_mesh (grid_hex_meshing.cpp:1937-1951): per hex the centre of the bounding box of its 8
+ * corners ((max + min) / 2 per axis), points_inside_mesh against `surface`, H_flag = signed_dis < 0.  Either output may be NULL. */
+int  fpohm_classify_hexes(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, int64_t nV, const uint32_t *hex, int64_t H,
+                          double *signed_dis, uint8_t *H_flag);
+
 /* build_connectivity, Hex branch (gf.cpp:121-186) + adjacency (gf.cpp:226-264) */
 int  fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, fpohm_conn **out);
 int  fpohm_conn_sizes(const fpohm_conn *c, int64_t *nF, int64_t *nE);

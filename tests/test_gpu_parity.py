@@ -571,3 +571,20 @@ def test_dual_conforming_mesh_vs_reference(fp, ctx, ref, case):
         assert np.array_equal(dual[k], rd[k]), (case, k)
     assert np.array_equal(dual["census"][1:], np.bincount(rd["h_type"], minlength=7)[1:])
     assert len(np.unique(rd["h_type"])) >= 3                                            # the case exercises several templates
+
+
+@pytest.mark.gpu
+def test_classify_hexes_vs_reference(fp, ctx, ref):
+    """clean_hex_mesh head (ghm.cpp:1937-1951): bbox centre of every hex + points_inside_mesh + sign, vs the reference's
+    points_inside_mesh on the same centres."""
+    V, F = fp.procedural.torus(48, 24)
+    m = fp.TriMesh(ctx, V, F)
+    prm = fp.octree_grid_setup(V, 1 << 20); prm.c.stop_extent = 1 << 14
+    o = fp.Octree.build(ctx, m, prm)
+    Vh, H, _ = o.hexes()
+    S, flag = fp.classify_hexes(ctx, m, Vh, H)
+    corners = Vh[H.astype(np.int64)]
+    P = (corners.max(1) + corners.min(1)) / 2
+    rS = ref.points_inside_mesh(V, F, P)
+    assert np.array_equal(S, rS)
+    assert np.array_equal(flag, (rS < 0).astype(np.uint8)) and 0 < flag.sum() < len(flag)
