@@ -588,3 +588,18 @@ def test_classify_hexes_vs_reference(fp, ctx, ref):
     rS = ref.points_inside_mesh(V, F, P)
     assert np.array_equal(S, rS)
     assert np.array_equal(flag, (rS < 0).astype(np.uint8)) and 0 < flag.sum() < len(flag)
+
+
+@pytest.mark.gpu
+def test_conforming_dual_edge_cases(fp, ctx, ref):
+    """No T-junction at all (uniform tree), and a single unsplit root (no interior edge or vertex: empty dual)."""
+    for gs, marks in (([8, 8, 8], [[0, 0, 0, 8], [0, 0, 0, 4]]), ([4, 4, 4], []), ([8, 4, 4], [])):
+        gs = np.array(gs, np.int32)
+        o = fp.Octree.from_marks(ctx, gs, np.array(marks, np.int32).reshape(-1, 4), True, True)
+        ex = o.export(); Vp, H, _ = o.hexes()
+        hyb, dual = fp.conforming_and_dual(ctx, o)
+        rh, rd = ref.conforming_and_dual_tables(ex["node_pos"], ex["node_neigh"], Vp, H, gs)
+        assert hyb["n_replaced"] == 0
+        for got, want in ((hyb, rh), (dual, rd)):
+            for k, v in want.items():
+                assert np.array_equal(np.asarray(got[k]).reshape(-1), np.asarray(v).reshape(-1)), (gs.tolist(), k)
