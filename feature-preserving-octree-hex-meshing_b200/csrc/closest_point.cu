@@ -898,8 +898,10 @@ int fpohm_signed_distance_dev(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P_
 }
 
 // Host-pointer path.  Queries are independent, so the batch is cut into chunks: an upload stream runs ahead with every
-// H2D copy, two compute streams alternate over the chunks (the tail of one chunk's kernels overlaps the start of the
-// next), a download stream trails with the D2H copies; per-chunk events order the three.  With pinned caller buffers the
+// H2D copy, three compute lanes rotate over the chunks (the latency-bound tails of one chunk's completion kernels run under
+// the next chunks' packet walks), and each chunk's results go down on its own lane as soon as they exist — in completion
+// order: on the bench workload the first two chunks hold the heavy queries and finish after the four that follow them
+// (FPOHM_CP_TIMELINE=1 prints the per-chunk event times).  With pinned caller buffers the
 // PCIe copies (84 B/query, 55 GB/s each way) hide behind the search; with pageable memory CUDA stages the copies and
 // the pipeline degrades gracefully to the serial order.
 static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const double *P, int64_t np,
@@ -916,43 +918,65 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	DevBuf<int32_t> dI(I ? np : 0, s);
 	KernelTimer t(ctx, s);
 	static const int64_t chunk = getenv("FPOHM_CP_CHUNK") ? atoll(getenv("FPOHM_CP_CHUNK")) : (1 << 19);
-	static const int n_comp = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 2;
+	static const int n_comp = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 3;
 	const int64_t n_chunks = (np + chunk - 1) / chunk;
 	while ((int64_t)ctx->ev_pool.size() < 2 * n_chunks) {
 		cudaEvent_t e;
 		FPOHM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		ctx->ev_pool.push_back(e);
 	}
-	cudaStream_t up = ctx->aux[0], down = ctx->aux[1];
-	cudaStream_t comp[2] = {s, ctx->aux[2]};
+	cudaStream_t up = ctx->aux[0], down0 = ctx->aux[1];
+	cudaStream_t comp[4] = {s, ctx->aux[2], ctx->aux[3], ctx->aux[4]};
+	const int lanes_n = std::max(1, std::min(n_comp, 4));
 	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, s));              // allocations are ordered on s
 	FPOHM_CUDA(cudaStreamWaitEvent(up, ctx->ev_sync, 0));
-	FPOHM_CUDA(cudaStreamWaitEvent(down, ctx->ev_sync, 0));
-	FPOHM_CUDA(cudaStreamWaitEvent(comp[1], ctx->ev_sync, 0));
+	FPOHM_CUDA(cudaStreamWaitEvent(down0, ctx->ev_sync, 0));
+	for (int k = 1; k < lanes_n; ++k) FPOHM_CUDA(cudaStreamWaitEvent(comp[k], ctx->ev_sync, 0));
 	// every upload is queued at once on its own stream: the copy engine runs ahead of the kernels
 	for (int64_t k = 0; k < n_chunks; ++k) {
 		const int64_t o = k * chunk, n = std::min(chunk, np - o);
 		FPOHM_CUDA(cudaMemcpyAsync(dP.p + 3 * o, P + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, up));
 		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k)], up));
 	}
+	static const bool timeline = getenv("FPOHM_CP_TIMELINE") != nullptr;      // debug: per-chunk event timestamps on stderr
+	std::vector<cudaEvent_t> tl;
+	if (timeline) { tl.resize((size_t)(4 * n_chunks + 1)); for (auto &e : tl) cudaEventCreate(&e); cudaEventRecord(tl[(size_t)(4 * n_chunks)], s); }
 	for (int64_t k = 0; k < n_chunks; ++k) {
 		const int64_t o = k * chunk, n = std::min(chunk, np - o);
-		cudaStream_t cs = comp[n_comp > 1 ? k & 1 : 0];
+		cudaStream_t cs = comp[k % lanes_n];
 		FPOHM_CUDA(cudaStreamWaitEvent(cs, ctx->ev_pool[(size_t)(2 * k)], 0));
+		if (timeline) cudaEventRecord(tl[(size_t)(4 * k)], cs);
 		launch_closest_point(ctx, mesh, with_sign, dP.p + 3 * o, n, S ? dS.p + o : nullptr, I ? dI.p + o : nullptr,
 		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs);
 		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k + 1)], cs));
-		FPOHM_CUDA(cudaStreamWaitEvent(down, ctx->ev_pool[(size_t)(2 * k + 1)], 0));
+		if (timeline) cudaEventRecord(tl[(size_t)(4 * k + 1)], cs);
+		static const bool own_down = getenv("FPOHM_CP_DOWN") ? atoi(getenv("FPOHM_CP_DOWN")) != 0 : true;
+		cudaStream_t down = own_down ? cs : down0;      // results go down on the chunk's own lane: in COMPLETION order, not chunk order
+		if (!own_down) FPOHM_CUDA(cudaStreamWaitEvent(down, ctx->ev_pool[(size_t)(2 * k + 1)], 0));
+		if (timeline) cudaEventRecord(tl[(size_t)(4 * k + 2)], down);
 		if (S) FPOHM_CUDA(cudaMemcpyAsync(S + o, dS.p + o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, down));
 		if (I) FPOHM_CUDA(cudaMemcpyAsync(I + o, dI.p + o, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, down));
 		if (C) FPOHM_CUDA(cudaMemcpyAsync(C + 3 * o, dC.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, down));
 		if (N) FPOHM_CUDA(cudaMemcpyAsync(N + 3 * o, dN.p + 3 * o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, down));
+		if (timeline) cudaEventRecord(tl[(size_t)(4 * k + 3)], down);
+	}
+	if (timeline) {
+		cudaDeviceSynchronize();
+		for (int64_t k = 0; k < n_chunks; ++k) {
+			float a, b, c, d;
+			cudaEventElapsedTime(&a, tl[(size_t)(4 * n_chunks)], tl[(size_t)(4 * k)]); cudaEventElapsedTime(&b, tl[(size_t)(4 * n_chunks)], tl[(size_t)(4 * k + 1)]);
+			cudaEventElapsedTime(&c, tl[(size_t)(4 * n_chunks)], tl[(size_t)(4 * k + 2)]); cudaEventElapsedTime(&d, tl[(size_t)(4 * n_chunks)], tl[(size_t)(4 * k + 3)]);
+			fprintf(stderr, "[fpohm timeline] chunk %2lld compute %.3f .. %.3f ms   download %.3f .. %.3f ms\n", (long long)k, a, b, c, d);
+		}
+		for (auto &e : tl) cudaEventDestroy(e);
 	}
 	// join everything back into s before the buffers die
-	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, down));
+	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, down0));
 	FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
-	FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, comp[1]));
-	FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
+	for (int k = 1; k < lanes_n; ++k) {
+		FPOHM_CUDA(cudaEventRecord(ctx->ev_sync, comp[k]));
+		FPOHM_CUDA(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
+	}
 	t.stop();
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 	FPOHM_API_END

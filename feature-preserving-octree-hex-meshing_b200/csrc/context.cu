@@ -44,7 +44,7 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[0], cudaStreamNonBlocking));
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[1], cudaStreamNonBlocking));
-	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[2], cudaStreamNonBlocking));
+	for (int k = 2; k < 5; ++k) FPOHM_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
 	FPOHM_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
 	for (int k = 0; k < fpohm_ctx::QRING; ++k) { FPOHM_CUDA(cudaEventCreate(&c->q_ev0[k])); FPOHM_CUDA(cudaEventCreate(&c->q_ev1[k])); }
 	FPOHM_CUDA(cudaEventCreate(&c->ev0));
@@ -68,7 +68,7 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->aux[0]);
 	cudaStreamDestroy(ctx->aux[1]);
-	cudaStreamDestroy(ctx->aux[2]);
+	for (int k = 2; k < 5; ++k) cudaStreamDestroy(ctx->aux[k]);
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	cudaEventDestroy(ctx->ev_sync);
 	cudaStreamDestroy(ctx->stream);

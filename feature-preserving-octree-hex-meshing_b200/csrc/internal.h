@@ -83,7 +83,7 @@ struct fpohm_ctx {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
-	cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // upload / download / second compute lane of the host-pointer entry points
+	cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // upload / download / extra compute lanes of the host-pointer entry points
 	std::vector<cudaEvent_t> ev_pool;                     // per-chunk ordering events of those pipelines (grown on demand)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
 	double last_ms = 0;
