@@ -12,6 +12,9 @@
 // (3-term sums are a0 + (a1 + a2), Eigen 3.2 unrolled redux) and the library is built with -fmad=false, so
 // the device evaluates the same IEEE operations as the reference's SSE2 build.
 #include "mesh.h"
+#include "octree.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cmath>
 #include <math_constants.h>
 #include <cstdlib>
 #include <algorithm>
@@ -813,6 +816,34 @@ __global__ void inside_flags_kernel(const double *__restrict__ S, int64_t n, uin
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) flag[t] = S[t] < 0 ? 1 : 0;
 }
 
+// ---- incoherent batches: Morton order for the packets, original order for the caller ---------------------------------
+__global__ void query_keys_kernel(const double *__restrict__ P, int64_t np, double ox, double oy, double oz, double scale,
+                                  uint32_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+		const double fx = (P[3 * i] - ox) * scale, fy = (P[3 * i + 1] - oy) * scale, fz = (P[3 * i + 2] - oz) * scale;
+		const uint32_t x = (uint32_t)fmin(fmax(fx, 0.0), 1023.0), y = (uint32_t)fmin(fmax(fy, 0.0), 1023.0), z = (uint32_t)fmin(fmax(fz, 0.0), 1023.0);
+		key[i] = (uint32_t)morton3(x, y, z);
+		idx[i] = (uint32_t)i;
+	}
+}
+__global__ void gather_points_kernel(const double *__restrict__ P, const uint32_t *__restrict__ perm, int64_t np, double *__restrict__ out) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * np; t += (int64_t)gridDim.x * blockDim.x)
+		out[t] = P[3 * (int64_t)perm[t / 3] + t % 3];
+}
+__global__ void scatter_results_kernel(const uint32_t *__restrict__ perm, int64_t np, const double *__restrict__ S, const int32_t *__restrict__ I,
+                                       const double *__restrict__ C, const double *__restrict__ N, double *__restrict__ So, int32_t *__restrict__ Io,
+                                       double *__restrict__ Co, double *__restrict__ No)
+{
+	for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < np; j += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t i = perm[j];
+		if (So) So[i] = S[j];
+		if (Io) Io[i] = I[j];
+		if (Co) { Co[3 * i] = C[3 * j]; Co[3 * i + 1] = C[3 * j + 1]; Co[3 * i + 2] = C[3 * j + 2]; }
+		if (No) { No[3 * i] = N[3 * j]; No[3 * i + 1] = N[3 * j + 1]; No[3 * i + 2] = N[3 * j + 2]; }
+	}
+}
+
 } // namespace
 
 namespace fpohm {
@@ -917,6 +948,50 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	DevBuf<double> dP(3 * np, s), dS(S ? np : 0, s), dC(C ? 3 * np : 0, s), dN(N ? 3 * np : 0, s);
 	DevBuf<int32_t> dI(I ? np : 0, s);
 	KernelTimer t(ctx, s);
+	// The packet search lives on consecutive queries being close to each other.  Probe that on the host (4 096 sampled
+	// neighbours against the spacing np points would have if spread evenly over their box); a batch that fails is walked
+	// in Morton order and its results are scattered back to the caller's order (a shuffled 4.6 M batch: 3.6 x faster).
+	if (np >= (1 << 16)) {
+		const int64_t m = 4096, stride = (np - 1) / m;
+		double mn[3] = {P[0], P[1], P[2]}, mx[3] = {P[0], P[1], P[2]}, adj = 0;
+		for (int64_t k = 0; k < m; ++k) {
+			const double *a = P + 3 * (k * stride), *b = a + 3;
+			double d2 = 0;
+			for (int c = 0; c < 3; ++c) { d2 += (a[c] - b[c]) * (a[c] - b[c]); mn[c] = std::min(mn[c], a[c]); mx[c] = std::max(mx[c], a[c]); }
+			adj += d2;
+		}
+		adj /= (double)m;
+		const double D2 = (mx[0] - mn[0]) * (mx[0] - mn[0]) + (mx[1] - mn[1]) * (mx[1] - mn[1]) + (mx[2] - mn[2]) * (mx[2] - mn[2]);
+		static const bool never = getenv("FPOHM_CP_NOSORT") != nullptr;
+		if (!never && D2 > 0 && std::isfinite(adj) && adj > 64.0 * D2 / std::pow((double)np, 2.0 / 3.0)) {
+			FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "%s: %lld queries in one call", who, (long long)np);
+			const double ext = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+			dP.upload(P, 3 * np);
+			DevBuf<uint32_t> key(np, s), key2(np, s), idx(np, s), perm(np, s);
+			query_keys_kernel<<<grid_for(ctx, np, 256), 256, 0, s>>>(dP.p, np, mn[0], mn[1], mn[2], ext > 0 ? 1024.0 / ext : 0.0, key.p, idx.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			size_t tb = 0;
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, perm.p, (int)np, 0, 30, s));
+			DevBuf<uint8_t> tmp((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, perm.p, (int)np, 0, 30, s));
+			ctx->launches += 1;
+			DevBuf<double> sP(3 * np, s), sS(np, s), sC(3 * np, s), sN(N ? 3 * np : 0, s);
+			DevBuf<int32_t> sI(np, s);
+			gather_points_kernel<<<grid_for(ctx, 3 * np, 256), 256, 0, s>>>(dP.p, perm.p, np, sP.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			launch_closest_point(ctx, mesh, with_sign, sP.p, np, sS.p, sI.p, sC.p, N ? sN.p : nullptr, s);
+			scatter_results_kernel<<<grid_for(ctx, np, 256), 256, 0, s>>>(perm.p, np, sS.p, sI.p, sC.p, N ? sN.p : nullptr, S ? dS.p : nullptr,
+				I ? dI.p : nullptr, C ? dC.p : nullptr, N ? dN.p : nullptr);
+			FPOHM_LAUNCH_CHECK(ctx);
+			if (S) dS.download(S, np);
+			if (I) dI.download(I, np);
+			if (C) dC.download(C, 3 * np);
+			if (N) dN.download(N, 3 * np);
+			t.stop();
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+			return FPOHM_OK;
+		}
+	}
 	static const int64_t chunk = getenv("FPOHM_CP_CHUNK") ? atoll(getenv("FPOHM_CP_CHUNK")) : (1 << 19);
 	static const int n_comp = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 3;
 	const int64_t n_chunks = (np + chunk - 1) / chunk;

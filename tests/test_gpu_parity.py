@@ -603,3 +603,19 @@ def test_conforming_dual_edge_cases(fp, ctx, ref):
         for got, want in ((hyb, rh), (dual, rd)):
             for k, v in want.items():
                 assert np.array_equal(np.asarray(got[k]).reshape(-1), np.asarray(v).reshape(-1)), (gs.tolist(), k)
+
+
+@pytest.mark.gpu
+def test_signed_distance_incoherent_batch_is_sorted_internally(fp, ctx, ref):
+    """A large batch in random order takes the Morton-ordered path of the host entry point (>= 65 536 queries failing the
+    coherence probe); results must still come back in the caller's order and equal igl's bit for bit."""
+    V, F = fp.procedural.torus(64, 40)
+    m = fp.TriMesh(ctx, V, F)
+    rng = np.random.default_rng(33)
+    fi = rng.integers(0, len(F), 70001)
+    P = V[F[fi]].mean(1) + 0.02 * rng.standard_normal((70001, 3))          # near the surface, random order, odd count
+    S, I, C, N = m.signed_distance_pseudonormal(P)
+    rS, rI, rC, rN = ref.RefTree(V, F).signed_distance(P)
+    assert np.array_equal(I, rI) and np.array_equal(S, rS) and np.array_equal(C, rC) and np.array_equal(N, rN)
+    D, I2, C2 = m.point_mesh_squared_distance(P)                            # unsigned entry, same path
+    assert np.array_equal(I2, rI) and np.array_equal(C2, rC)
