@@ -7,10 +7,12 @@
 //   point_simplex_squared_distance (Ericson) igl/point_simplex_squared_distance.cpp:44-124 -> closest_on_triangle()
 //   pseudonormal_test        igl/pseudonormal_test.cpp:14-119 -> pseudonormal()
 //
-// One thread per query; the visiting order inside a query is exactly igl's (it decides which facet wins a
-// distance tie), parallelism is across queries only.  Every fp64 expression keeps igl/Eigen's association
-// (3-term sums are a0 + (a1 + a2), Eigen 3.2 unrolled redux) and the library is built with -fmad=false, so
-// the device evaluates the same IEEE operations as the reference's SSE2 build.
+// Two paths produce the same bits.  The reference path (`closest_point_kernel`, FPOHM_CP_MODE=0, and the fallback
+// of every other kernel) is one thread per query walking in exactly igl's order.  The shipped path ("Packet search"
+// below) finds the minimum distance with warp packets in any order and then reproduces igl's choice among equidistant
+// facets.  Every fp64 expression keeps igl/Eigen's association (3-term sums are a0 + (a1 + a2), Eigen 3.2 unrolled
+// redux) and the library is built with -fmad=false, so the device evaluates the same IEEE operations as the
+// reference's SSE2 build.
 #include "mesh.h"
 #include "octree.h"
 #include <cub/device/device_radix_sort.cuh>
@@ -213,9 +215,9 @@ closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Packet search (default path).  Three kernels, each handing on only what it could not finish:
+// Packet search (default path).  Four kernels, each handing on only what it could not finish:
 //
-//  K1 packet   one WARP walks the tree once for its 32 consecutive queries.  The per-lane igl-order kernel above is
+//  K1 packet   (cp_packet_kernel) one WARP walks the tree once for its 32 consecutive queries.  The per-lane igl-order kernel above is
 //              bound by instruction issue, a third of it fp64 box arithmetic, at 10 of 32 lanes active
 //              (profiles/r01_ncu_summary.md).  Here the walk, the stack and every node / triangle load are
 //              warp-uniform and the box tests are a CONSERVATIVE fp32 FILTER: child boxes rounded outwards to float
@@ -224,18 +226,21 @@ closest_point_kernel(const QNode *__restrict__ nodes, int32_t root, const double
 //              child iff bound <= its best distance (rounded up).  The only fp64 work left is the exact igl
 //              closest-point evaluation of the leaves that pass the filter, so a lane that sees the walk through holds
 //              the exact minimum distance over ALL facets, whatever the visiting order was.
-//  K2 lane     one THREAD per query K1 did not settle (compacted list): queries of a warp that stopped sharing its
-//              search (checked every 32 visits) restart an order-free per-lane search seeded with the bound they
-//              already have; queries with near-ties get igl's tie-break (below).  Bounded work per thread.
-//  K3 heavy    one WARP per query that exceeded K2's budgets, 32 tree nodes per step (0.2 % of the bench queries hold
+//  K2 search   (cp_search_kernel) queries of a warp that stopped sharing its search (checked every 32 visits) restart an
+//              order-free per-lane search seeded with the bound they already have: persistent lanes, one node visit per
+//              loop iteration, a lane that finishes fetches the next query at once.  Bounded work per query.
+//  K2 tie      (cp_tie_kernel) one THREAD per query with near-ties: igl's tie-break (below).
+//  K3 heavy    (cp_heavy_kernel) one WARP per query that exceeded K2's budgets, 32 tree nodes per step (0.2 % of the bench queries hold
 //              the tail: one near the gear's bore axis needs 6 590 node visits, milliseconds for a lone thread).
 //
 // Ties.  What the visiting order decides in igl is which facet wins when several are at (nearly) the same distance:
 // igl keeps the first one its depth-first order reaches — left child first if it contains p or is nearer
 // (AABB.cpp:392-437), independent of the running minimum, so for a given p the order is a fixed total order of the
 // leaves — and its strict pruning on the COMPUTED box distances can even skip a facet that is an ulp closer.  A lane
-// therefore counts the leaves within (1 + 2^-40) of its minimum.  With more than one, K2 re-walks the tree in exact igl
-// order (`traverse_limited`) restricted to boxes within (1 + 2^-38) of the minimum.  Restricting is exact: leaves
+// therefore counts the leaves within (1 + 2^-40) of its minimum and keeps the first three at EXACTLY the minimum.  With
+// more than one near-tie, K2 names the winner from that list when one box test proves igl reaches it (`igl_tie_winner`);
+// otherwise it re-walks the tree in exact igl order (`traverse_limited`) restricted to boxes within (1 + 2^-38) of the
+// minimum.  Restricting is exact: leaves
 // outside those boxes are farther than every near-minimal candidate, so they can neither win nor make igl prune an
 // ancestor of a candidate (its box distance is below their distance); by induction over igl's order the restricted
 // walk evaluates the same candidates with the same running minimum as the full walk.  The walk stops at the first
