@@ -15,6 +15,7 @@ __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
+    "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -360,9 +361,10 @@ class HexConnectivity:
     """build_connectivity, Hex branch (gf.cpp:121-186,226-264)."""
     NAMES = ["F_nhs", "E_nfs", "E_nhs", "V_nvs", "V_nes", "V_nfs", "V_nhs"]
 
-    def __init__(self, ctx: Context, hexa, nV: int):
+    def __init__(self, ctx: Context, hexa, nV: int, keep: bool = False):
         hexa = np.ascontiguousarray(hexa, np.uint32); H = len(hexa)
         h = C.c_void_p()
+        self.h = None
         _chk(lib().fpohm_hex_connectivity(ctx.h, _p(hexa), C.c_int64(H), C.c_int64(nV), C.byref(h)))
         try:
             nF, nE = C.c_int64(), C.c_int64()
@@ -381,7 +383,20 @@ class HexConnectivity:
                 _chk(lib().fpohm_conn_csr(h, C.c_int32(which), _p(off), _p(val), C.byref(tot)))
                 setattr(self, nm, (off, val))
         finally:
-            lib().fpohm_conn_free(h)
+            if keep:
+                self.h = h          # device tables stay alive for the cleaning stages (close() frees them)
+            else:
+                lib().fpohm_conn_free(h)
+
+    def close(self):
+        if self.h:
+            lib().fpohm_conn_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def classify_hexes(ctx: Context, surface: "TriMesh", V, hexa):
@@ -390,6 +405,64 @@ def classify_hexes(ctx: Context, surface: "TriMesh", V, hexa):
     S = np.zeros(len(hexa)); flag = np.zeros(len(hexa), np.uint8)
     _chk(lib().fpohm_classify_hexes(ctx.h, surface.h, _p(V), C.c_int64(len(V)), _p(hexa), C.c_int64(len(hexa)), _p(S), _p(flag)))
     return S, flag
+
+
+# ---- clean_hex_mesh stages (ghm.cpp:1932-2124) ----------------------------------------------------------
+def reorder_hexes(ctx: Context, V, hexa):
+    """reorder_hex_mesh (gf.cpp:2199-2229): (reordered hex list, number of mirrored hexes)."""
+    V = _f64(V); out = np.array(hexa, np.uint32, copy=True, order="C")
+    n = C.c_int64()
+    _chk(lib().fpohm_reorder_hexes(ctx.h, _p(V), C.c_int64(len(V)), _p(out), C.c_int64(len(out)), C.byref(n)))
+    return out, n.value
+
+
+def tag_uneven_elements(ctx: Context, conn: "HexConnectivity", H_flag):
+    """tagging_uneven_element (ghm.cpp:1983-2005); conn = HexConnectivity(..., keep=True).  Returns (flags, sweeps)."""
+    f = np.array(H_flag, np.uint8, copy=True); sweeps = C.c_int32()
+    _chk(lib().fpohm_tag_uneven_elements(ctx.h, conn.h, _p(f), C.byref(sweeps)))
+    return f, sweeps.value
+
+
+def reindex_submesh(ctx: Context, hexa, nV: int, H_flag):
+    """re_indexing_connectivity (gf.cpp:664-698): dict(V_map, V_map_reverse, H_map_reverse, hex)."""
+    hexa = np.ascontiguousarray(hexa, np.uint32); f = np.ascontiguousarray(H_flag, np.uint8); H = len(hexa)
+    V_map = np.zeros(nV, np.int32); V_rev = np.zeros(nV, np.int32); H_rev = np.zeros(H, np.int32); sub = np.zeros((H, 8), np.uint32)
+    nv, nh = C.c_int64(), C.c_int64()
+    _chk(lib().fpohm_reindex_submesh(ctx.h, _p(hexa), C.c_int64(H), C.c_int64(nV), _p(f), _p(V_map), _p(V_rev), C.byref(nv), _p(H_rev), C.byref(nh), _p(sub)))
+    return dict(V_map=V_map, V_map_reverse=V_rev[:nv.value].copy(), H_map_reverse=H_rev[:nh.value].copy(), hex=sub[:nh.value].copy())
+
+
+def clean_non_manifold(ctx: Context, hexa, nV: int, H_flag):
+    """clean_non_manifold_ve (ghm.cpp:2006-2080): (flags, rounds)."""
+    hexa = np.ascontiguousarray(hexa, np.uint32); f = np.array(H_flag, np.uint8, copy=True); r = C.c_int32()
+    _chk(lib().fpohm_clean_non_manifold(ctx.h, _p(hexa), C.c_int64(len(hexa)), C.c_int64(nV), _p(f), C.byref(r)))
+    return f, r.value
+
+
+def drop_small_pieces(ctx: Context, hexa, nV: int, H_flag):
+    """drop_small_pieces (ghm.cpp:2081-2124): (flags, number of pieces)."""
+    hexa = np.ascontiguousarray(hexa, np.uint32); f = np.array(H_flag, np.uint8, copy=True); n = C.c_int64()
+    _chk(lib().fpohm_drop_small_pieces(ctx.h, _p(hexa), C.c_int64(len(hexa)), C.c_int64(nV), _p(f), C.byref(n)))
+    return f, n.value
+
+
+def medial_surface_flags(ctx: Context, conn: "HexConnectivity", H_flag):
+    """tail of clean_hex_mesh (ghm.cpp:1970-1981): (F_medial, V_medial)."""
+    f = np.ascontiguousarray(H_flag, np.uint8)
+    Fm = np.zeros(len(conn.F_vs), np.uint8); Vm = np.zeros(len(conn.V_boundary), np.uint8)
+    _chk(lib().fpohm_medial_surface_flags(ctx.h, conn.h, _p(f), _p(Fm), _p(Vm)))
+    return Fm, Vm
+
+
+def clean_hex_mesh(ctx: Context, surface: "TriMesh", V, hexa, conn: "HexConnectivity | None" = None):
+    """clean_hex_mesh (ghm.cpp:1932-1981, scaffold_type 1): dict(hex (reordered), signed_dis, H_flag, F_medial, V_medial, stats)."""
+    V = _f64(V); hx = np.array(hexa, np.uint32, copy=True, order="C"); H = len(hx)
+    S = np.zeros(H); flag = np.zeros(H, np.uint8); Vm = np.zeros(len(V), np.uint8)
+    Fm = np.zeros(len(conn.F_vs), np.uint8) if conn is not None else None
+    stats = (C.c_int64 * 6)()
+    _chk(lib().fpohm_clean_hex_mesh(ctx.h, surface.h, _p(V), C.c_int64(len(V)), _p(hx), C.c_int64(H), conn.h if conn is not None else None,
+                                    _p(S), _p(flag), _p(Fm) if Fm is not None else None, _p(Vm), stats))
+    return dict(hex=hx, signed_dis=S, H_flag=flag, F_medial=Fm, V_medial=Vm, stats=list(stats))
 
 
 def _hybrid_to_dict(hy):

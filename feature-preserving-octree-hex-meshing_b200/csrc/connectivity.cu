@@ -192,23 +192,19 @@ struct Ops {
 
 } // namespace
 
-extern "C" {
-
-int fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, fpohm_conn **out) {
-	FPOHM_API_BEGIN
-	FPOHM_REQUIRE(ctx && hex && out && H > 0 && nV > 0, FPOHM_EINVAL, "fpohm_hex_connectivity: bad argument");
+// build_connectivity on a hex list that is already on the device (takes the buffer over: it stays in the result as
+// c->hex).  `full` = false skips E.neighbor_hs, V.neighbor_vs and V.neighbor_es (two sorts and two host read-backs that
+// the cleaning stages of cleaning.cu never look at).
+fpohm_conn *fpohm::conn_build_dev(fpohm_ctx *ctx, DevBuf<uint32_t> &&hex_in, int64_t H, int64_t nV, bool full) {
 	FPOHM_REQUIRE(12 * H < (1ll << 31), FPOHM_ERANGE, "fpohm_hex_connectivity: %lld hexes overflow uint32 tuple ids", (long long)H);
-	for (int64_t i = 0; i < 8 * H; ++i)
-		FPOHM_REQUIRE((int64_t)hex[i] < nV, FPOHM_EINVAL, "fpohm_hex_connectivity: corner id %u out of range at %lld", hex[i], (long long)i);
-	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
 	const int blk = 256;
 	Ops ops{ctx, s};
 	fpohm_conn *c = new fpohm_conn;
 	try {
 		c->ctx = ctx; c->H = H; c->nV = nV;
-		DevBuf<uint32_t> dhex(8 * H, s);
-		dhex.upload(hex, 8 * H);
+		c->hex = std::move(hex_in);
+		DevBuf<uint32_t> &dhex = c->hex;
 		KernelTimer timer(ctx, s);
 		const int vb = bits_for(nV);
 		// ---- faces: stable LSD sort on (lo = v2,v3) then (hi = v0,v1); ties keep id = 6h+j order
@@ -264,7 +260,7 @@ int fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64
 		boundary_kernel<<<grid_for(ctx, n4, blk), blk, 0, s>>>(c->F_boundary.p, c->F_es.p, c->E_vs.p, nF, c->E_boundary.p, c->V_boundary.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 		// ---- E.neighbor_hs: sorted unique hexes over the edge's faces
-		{
+		if (full) {
 			DevBuf<int64_t> cnt(n4 + 1, s), pos(n4 + 1, s);
 			cnt.zero();
 			ehs_count_kernel<<<grid_for(ctx, n4, blk), blk, 0, s>>>(c->val[1].p, n4, c->off[0].p, cnt.p);
@@ -300,7 +296,7 @@ int fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64
 			FPOHM_CUDA(cudaStreamSynchronize(s));
 		}
 		// ---- V.neighbor_es / V.neighbor_vs (gf.cpp:241-248)
-		{
+		if (full) {
 			const int64_t n2 = 2 * nE;
 			DevBuf<uint32_t> key(n2, s), ve(n2, s), vv(n2, s), key2(n2, s);
 			ves_items_kernel<<<grid_for(ctx, n2, blk), blk, 0, s>>>(c->E_vs.p, nE, key.p, ve.p, vv.p);
@@ -327,7 +323,21 @@ int fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64
 		timer.stop();
 		FPOHM_CUDA(cudaStreamSynchronize(s));
 	} catch (...) { delete c; throw; }
-	*out = c;
+	return c;
+}
+
+extern "C" {
+
+int fpohm_hex_connectivity(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, fpohm_conn **out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && hex && out && H > 0 && nV > 0, FPOHM_EINVAL, "fpohm_hex_connectivity: bad argument");
+	FPOHM_REQUIRE(12 * H < (1ll << 31), FPOHM_ERANGE, "fpohm_hex_connectivity: %lld hexes overflow uint32 tuple ids", (long long)H);
+	for (int64_t i = 0; i < 8 * H; ++i)
+		FPOHM_REQUIRE((int64_t)hex[i] < nV, FPOHM_EINVAL, "fpohm_hex_connectivity: corner id %u out of range at %lld", hex[i], (long long)i);
+	DeviceGuard g(ctx->device);
+	DevBuf<uint32_t> dhex(8 * H, ctx->stream);
+	dhex.upload(hex, 8 * H);
+	*out = conn_build_dev(ctx, std::move(dhex), H, nV, true);
 	FPOHM_API_END
 }
 
@@ -359,6 +369,7 @@ int fpohm_conn_fixed(const fpohm_conn *c, uint32_t *F_vs, uint32_t *F_es, uint8_
 int fpohm_conn_csr(const fpohm_conn *c, int32_t which, int64_t *off, uint32_t *val, int64_t *total) {
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(c && which >= 0 && which < 7, FPOHM_EINVAL, "fpohm_conn_csr: bad argument");
+	FPOHM_REQUIRE(c->off[which].p, FPOHM_EINVAL, "fpohm_conn_csr: relation %d was not built for this handle", which);
 	DeviceGuard g(c->ctx->device);
 	const int64_t n = which == 0 ? c->nF : (which <= 2 ? c->nE : c->nV);
 	if (total) *total = c->tot[which];

@@ -236,6 +236,38 @@ int  fpohm_conn_fixed(const fpohm_conn *c, uint32_t *F_vs, uint32_t *F_es, uint8
 int  fpohm_conn_csr(const fpohm_conn *c, int32_t which, int64_t *off, uint32_t *val, int64_t *total);
 void fpohm_conn_free(fpohm_conn *c);
 
+/* ---- clean_hex_mesh and its stages (grid_meshing/grid_hex_meshing.cpp:1932-2124).  H_flag is the
+ * reference's md.H_flag as one byte per hex of the ENTIRE mesh (1 = inside / kept); stages update it in place and give the
+ * flags the reference's sequential loops give (see csrc/cleaning.cu for why the data-parallel forms are equivalent).
+ *
+ * fpohm_reorder_hexes        reorder_hex_mesh (global_functions.cpp:2199-2229): a hex whose 8 corner determinants sum to a
+ *                            negative volume gets its vertex list mirrored (3,2,1,0,7,6,5,4), in place.
+ * fpohm_tag_uneven_elements  tagging_uneven_element (ghm.cpp:1983-2005) on the connectivity of the entire mesh.
+ * fpohm_reindex_submesh      re_indexing_connectivity (global_functions.cpp:664-698): V_map (nV, -1 = dropped), V_map_reverse
+ *                            and H_map_reverse (capacity nV / H, lengths returned), sub_hex = hexes of the sub-mesh in its
+ *                            own vertex numbering (8 x n_sub_h, capacity 8 H).  Any output may be NULL.  The reference's
+ *                            H_map stays empty (it is cleared and never filled).  The sub-mesh's connectivity is
+ *                            fpohm_hex_connectivity(sub_hex).
+ * fpohm_clean_non_manifold   clean_non_manifold_ve (ghm.cpp:2006-2080): the whole loop, re-indexing between rounds.
+ * fpohm_drop_small_pieces    drop_small_pieces (ghm.cpp:2081-2124); n_pieces = number of face-connected pieces found.
+ * fpohm_medial_surface_flags tail of clean_hex_mesh (ghm.cpp:1970-1981): Fs[].on_medial_surface / Vs[].on_medial_surface.
+ * fpohm_clean_hex_mesh       the composition (ghm.cpp:1932-1981) with args.scaffold_type 1 (the default, no scaffold
+ *                            layers): reorder (hex is rewritten) -> bbox centres + points_inside_mesh against `surface`
+ *                            -> tagging -> non-manifold loop -> small pieces -> medial flags.  `conn` = connectivity of
+ *                            the entire mesh (NULL: built inside; F_medial then has the face count of that build).
+ *                            stats = {mirrored hexes, tagging sweeps, non-manifold rounds, pieces, hexes kept, vertices
+ *                            kept}; signed_dis / F_medial / V_medial / stats may be NULL. */
+int  fpohm_reorder_hexes(fpohm_ctx *ctx, const double *V, int64_t nV, uint32_t *hex, int64_t H, int64_t *n_mirrored);
+int  fpohm_tag_uneven_elements(fpohm_ctx *ctx, const fpohm_conn *conn, uint8_t *H_flag, int32_t *n_sweeps);
+int  fpohm_reindex_submesh(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, const uint8_t *H_flag, int32_t *V_map,
+                           int32_t *V_map_reverse, int64_t *n_sub_v, int32_t *H_map_reverse, int64_t *n_sub_h, uint32_t *sub_hex);
+int  fpohm_clean_non_manifold(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, uint8_t *H_flag, int32_t *n_rounds);
+int  fpohm_drop_small_pieces(fpohm_ctx *ctx, const uint32_t *hex, int64_t H, int64_t nV, uint8_t *H_flag, int64_t *n_pieces);
+int  fpohm_medial_surface_flags(fpohm_ctx *ctx, const fpohm_conn *conn, const uint8_t *H_flag, uint8_t *F_medial, uint8_t *V_medial);
+int  fpohm_clean_hex_mesh(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, int64_t nV, uint32_t *hex, int64_t H,
+                          const fpohm_conn *conn, double *signed_dis, uint8_t *H_flag, uint8_t *F_medial, uint8_t *V_medial,
+                          int64_t stats[6]);
+
 /* ---- conforming_mesh (grid_meshing/grid_hex_meshing.cpp:568-696): the octree hex mesh with every big
  * face at a T-junction replaced by the 4 small faces of the other side and the mid vertices inserted into the loops of
  * the faces around it, as a polyhedral ("Hyb") mesh with the connectivity build_connectivity gives it (gf.cpp:187-264):

@@ -130,4 +130,102 @@ void ref_dual_export(void *rv, double *V, int32_t *h_type, int64_t *F_off, uint3
 	export_mesh(d, F_off, F_vs, F_es, F_boundary, E_vs, E_boundary, V_boundary, H_foff, H_fs, H_voff, H_vs, F_nhoff, F_nhs);
 }
 void ref_hybrid_free(void *rv) { delete (RefHybrid *)rv; }
+
+// ---- §8(f)-2: clean_hex_mesh and its stages (ghm.cpp:1932-2126, gf.cpp:664-698,2199-2229), the compiled reference
+// methods themselves on a hex mesh given as (Vpos, hex).  Every stage is callable on its own so that the product's
+// stage entry points can be compared one by one.
+struct RefClean { Mesh_Domain md; Eigen::VectorXd signed_dis; };
+
+void *ref_clean_new(const double *Vpos, int64_t nV, const uint32_t *hex, int64_t H) {
+	RefClean *r = new RefClean;
+	Mesh &m = r->md.mesh_entire;
+	m.type = Mesh_type::Hex;
+	m.Vs.resize((size_t)nV);
+	m.V.resize(3, nV);
+	for (int64_t i = 0; i < nV; ++i) {
+		Hybrid_V v; v.id = (uint32_t)i;
+		for (int d = 0; d < 3; ++d) { v.v.push_back(Vpos[3 * i + d]); m.V(d, i) = Vpos[3 * i + d]; }
+		m.Vs[(size_t)i] = v;
+	}
+	m.Hs.resize((size_t)H);
+	for (int64_t h = 0; h < H; ++h) { m.Hs[(size_t)h].id = (uint32_t)h; m.Hs[(size_t)h].vs.assign(hex + 8 * h, hex + 8 * h + 8); }
+	build_connectivity(m);
+	r->md.H_flag.assign((size_t)H, false);
+	r->signed_dis = Eigen::VectorXd::Zero(H);
+	return r;
+}
+void ref_clean_free(void *rv) { delete (RefClean *)rv; }
+void ref_clean_reorder(void *rv, uint32_t *hex_out) {
+	RefClean *r = (RefClean *)rv;
+	reorder_hex_mesh(r->md.mesh_entire);
+	const Mesh &m = r->md.mesh_entire;
+	for (size_t h = 0; h < m.Hs.size(); ++h) for (int k = 0; k < 8; ++k) hex_out[8 * h + k] = m.Hs[h].vs[k];
+}
+void ref_clean_set_flags(void *rv, const uint8_t *f) {
+	RefClean *r = (RefClean *)rv;
+	for (size_t i = 0; i < r->md.H_flag.size(); ++i) r->md.H_flag[i] = f[i] != 0;
+}
+void ref_clean_get_flags(void *rv, uint8_t *f) {
+	RefClean *r = (RefClean *)rv;
+	for (size_t i = 0; i < r->md.H_flag.size(); ++i) f[i] = r->md.H_flag[i] ? 1 : 0;
+}
+void ref_clean_tagging(void *rv) {
+	RefClean *r = (RefClean *)rv;
+	grid_hex_meshing_bijective gm;
+	gm.tagging_uneven_element(r->md.mesh_entire, r->md.H_flag);
+}
+void ref_clean_reindex(void *rv, int64_t sizes[4]) {
+	RefClean *r = (RefClean *)rv;
+	Mesh_Domain &md = r->md;
+	re_indexing_connectivity(md.mesh_entire, md.H_flag, md.mesh_subA, md.V_map, md.V_map_reverse, md.H_map, md.H_map_reverse);
+	sizes[0] = (int64_t)md.mesh_subA.Vs.size(); sizes[1] = (int64_t)md.mesh_subA.Hs.size();
+	sizes[2] = (int64_t)md.mesh_subA.Fs.size(); sizes[3] = (int64_t)md.mesh_subA.Es.size();
+}
+// V_map nV(entire), V_map_reverse nV(sub), H_map_reverse nH(sub), sub_hex 8 nH(sub), sub_V 3 nV(sub); any may be NULL
+void ref_clean_sub_export(void *rv, int32_t *V_map, int32_t *V_map_reverse, int32_t *H_map_reverse, uint32_t *sub_hex, double *sub_V) {
+	RefClean *r = (RefClean *)rv;
+	const Mesh_Domain &md = r->md;
+	if (V_map) for (size_t i = 0; i < md.V_map.size(); ++i) V_map[i] = md.V_map[i];
+	if (V_map_reverse) for (size_t i = 0; i < md.V_map_reverse.size(); ++i) V_map_reverse[i] = md.V_map_reverse[i];
+	if (H_map_reverse) for (size_t i = 0; i < md.H_map_reverse.size(); ++i) H_map_reverse[i] = md.H_map_reverse[i];
+	if (sub_hex) for (size_t h = 0; h < md.mesh_subA.Hs.size(); ++h) for (int k = 0; k < 8; ++k) sub_hex[8 * h + k] = md.mesh_subA.Hs[h].vs[k];
+	if (sub_V) for (size_t v = 0; v < md.mesh_subA.Vs.size(); ++v) for (int d = 0; d < 3; ++d) sub_V[3 * v + d] = md.mesh_subA.V(d, v);
+}
+// needs ref_clean_reindex first (mesh_subA + maps are inputs of both)
+void ref_clean_non_manifold(void *rv) {
+	RefClean *r = (RefClean *)rv;
+	Mesh_Domain &md = r->md;
+	grid_hex_meshing_bijective gm;
+	gm.clean_non_manifold_ve(md.mesh_entire, md.mesh_subA, md.V_map, md.V_map_reverse, md.H_map, md.H_map_reverse, r->signed_dis, md.H_flag);
+}
+void ref_clean_drop_small(void *rv) {
+	RefClean *r = (RefClean *)rv;
+	grid_hex_meshing_bijective gm;
+	gm.drop_small_pieces(r->md);
+}
+// the whole clean_hex_mesh (args.scaffold_type keeps its default 1: no scaffold layers)
+void ref_clean_full(void *rv, const double *tV, int64_t ntV, const int32_t *tF, int64_t ntF) {
+	RefClean *r = (RefClean *)rv;
+	Mesh tmi;
+	tmi.type = Mesh_type::Tri;
+	tmi.V.resize(3, ntV);
+	tmi.Vs.resize((size_t)ntV);
+	for (int64_t i = 0; i < ntV; ++i) { for (int c = 0; c < 3; ++c) tmi.V(c, i) = tV[3 * i + c]; tmi.Vs[(size_t)i].id = (uint32_t)i; }
+	tmi.Fs.resize((size_t)ntF);
+	for (int64_t f = 0; f < ntF; ++f) {
+		tmi.Fs[(size_t)f].id = (uint32_t)f;
+		tmi.Fs[(size_t)f].vs = {(uint32_t)tF[3 * f], (uint32_t)tF[3 * f + 1], (uint32_t)tF[3 * f + 2]};
+	}
+	grid_hex_meshing_bijective gm;
+	gm.clean_hex_mesh(tmi, r->md);
+}
+void ref_clean_entire_sizes(void *rv, int64_t sizes[4]) {
+	const Mesh &m = ((RefClean *)rv)->md.mesh_entire;
+	sizes[0] = (int64_t)m.Vs.size(); sizes[1] = (int64_t)m.Hs.size(); sizes[2] = (int64_t)m.Fs.size(); sizes[3] = (int64_t)m.Es.size();
+}
+void ref_clean_medial(void *rv, uint8_t *F_medial, uint8_t *V_medial) {
+	const Mesh &m = ((RefClean *)rv)->md.mesh_entire;
+	for (size_t f = 0; f < m.Fs.size(); ++f) F_medial[f] = m.Fs[f].on_medial_surface ? 1 : 0;
+	for (size_t v = 0; v < m.Vs.size(); ++v) V_medial[v] = m.Vs[v].on_medial_surface ? 1 : 0;
+}
 }

@@ -303,3 +303,65 @@ def conforming_mesh_tables(node_pos, node_neigh, Vpos, hexa, grid_size):
     out = _export_hybrid(h, list(sizes))
     lib().ref_hybrid_free(h)
     return out
+
+
+# ---- §8(f)-2: clean_hex_mesh and its stages (grid_hex_meshing.cpp:1932-2126, global_functions.cpp:664-698,2199-2229) -----
+class RefClean:
+    """The reference's own clean_hex_mesh stages on a hex mesh (Vpos, hexa); build_connectivity runs in the constructor."""
+
+    def __init__(self, Vpos, hexa):
+        self.Vp, self.hx = _f64(Vpos), np.ascontiguousarray(hexa, np.uint32)
+        self.nV, self.H = len(self.Vp), len(self.hx)
+        lib().ref_clean_new.restype = C.c_void_p
+        self.h = C.c_void_p(lib().ref_clean_new(_p(self.Vp), C.c_int64(self.nV), _p(self.hx), C.c_int64(self.H)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_clean_free(self.h); self.h = None
+
+    def reorder(self):
+        out = np.zeros((self.H, 8), np.uint32)
+        lib().ref_clean_reorder(self.h, _p(out))
+        return out
+
+    def set_flags(self, f):
+        f = np.ascontiguousarray(f, np.uint8); assert len(f) == self.H
+        lib().ref_clean_set_flags(self.h, _p(f))
+
+    def flags(self):
+        f = np.zeros(self.H, np.uint8)
+        lib().ref_clean_get_flags(self.h, _p(f))
+        return f
+
+    def tagging(self):
+        lib().ref_clean_tagging(self.h); return self.flags()
+
+    def reindex(self):
+        sizes = (C.c_int64 * 4)()
+        lib().ref_clean_reindex(self.h, sizes)
+        return self.sub(list(sizes))
+
+    def sub(self, sizes):
+        nv, nh = int(sizes[0]), int(sizes[1])
+        out = dict(nV=nv, nH=nh, nF=int(sizes[2]), nE=int(sizes[3]), V_map=np.zeros(self.nV, np.int32), V_map_reverse=np.zeros(nv, np.int32),
+                   H_map_reverse=np.zeros(nh, np.int32), hex=np.zeros((nh, 8), np.uint32), V=np.zeros((nv, 3)))
+        lib().ref_clean_sub_export(self.h, _p(out["V_map"]), _p(out["V_map_reverse"]), _p(out["H_map_reverse"]), _p(out["hex"]), _p(out["V"]))
+        return out
+
+    def non_manifold(self):
+        lib().ref_clean_non_manifold(self.h); return self.flags()
+
+    def drop_small(self):
+        lib().ref_clean_drop_small(self.h); return self.flags()
+
+    def full(self, tV, tF):
+        tV, tF = _f64(tV), _i32(tF)
+        lib().ref_clean_full(self.h, _p(tV), C.c_int64(len(tV)), _p(tF), C.c_int64(len(tF)))
+        return self.flags()
+
+    def medial(self):
+        sizes = (C.c_int64 * 4)()
+        lib().ref_clean_entire_sizes(self.h, sizes)
+        Fm, Vm = np.zeros(int(sizes[2]), np.uint8), np.zeros(int(sizes[0]), np.uint8)
+        lib().ref_clean_medial(self.h, _p(Fm), _p(Vm))
+        return Fm, Vm

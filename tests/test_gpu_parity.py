@@ -619,3 +619,112 @@ def test_signed_distance_incoherent_batch_is_sorted_internally(fp, ctx, ref):
     assert np.array_equal(I, rI) and np.array_equal(S, rS) and np.array_equal(C, rC) and np.array_equal(N, rN)
     D, I2, C2 = m.point_mesh_squared_distance(P)                            # unsigned entry, same path
     assert np.array_equal(I2, rI) and np.array_equal(C2, rC)
+
+
+# ---- §8(f)-2: clean_hex_mesh stages, against the reference's own methods (oracle/_ref) and the golden fixtures ------------
+def test_clean_stages_vs_reference(fp, ctx, ref):
+    from clean_cases import carved_block
+    for dims, p, seed in [((6, 5, 4), 0.6, 11), ((8, 8, 8), 0.5, 12), ((12, 7, 9), 0.75, 13), ((9, 9, 9), 0.35, 14), ((16, 16, 16), 0.55, 15),
+                          ((5, 4, 3), 1.0, 16), ((7, 7, 7), 0.08, 17)]:
+        V, H, flag, Hm = carved_block(dims, p, seed)
+        nV = len(V)
+        got, n_mirrored = fp.reorder_hexes(ctx, V, Hm)
+        want = ref.RefClean(V, Hm).reorder()
+        assert np.array_equal(got, want) and n_mirrored == int((want != Hm).any(1).sum()), dims
+        rc = ref.RefClean(V, H)
+        rc.set_flags(flag)
+        conn = fp.HexConnectivity(ctx, H, nV, keep=True)
+        t, sweeps = fp.tag_uneven_elements(ctx, conn, flag)
+        assert np.array_equal(t, rc.tagging()), (dims, "tagging")
+        if not t.any():
+            continue
+        s = rc.reindex()
+        mine = fp.reindex_submesh(ctx, H, nV, t)
+        for k in ("V_map", "V_map_reverse", "H_map_reverse", "hex"):
+            assert np.array_equal(mine[k], s[k]), (dims, k)
+        n, rounds = fp.clean_non_manifold(ctx, H, nV, t)
+        assert np.array_equal(n, rc.non_manifold()), (dims, "non-manifold", rounds)
+        if not n.any():
+            continue
+        d, pieces = fp.drop_small_pieces(ctx, H, nV, n)
+        assert np.array_equal(d, rc.drop_small()), (dims, "drop", pieces)
+        # medial flags of an arbitrary flag set against the port-free definition through the reference's tables
+        Fm, Vm = fp.medial_surface_flags(ctx, conn, d)
+        off, val = conn.F_nhs
+        two = np.diff(off) == 2
+        want_F = np.where(two, d[val[off[:-1]]] != d[val[np.minimum(off[:-1] + 1, len(val) - 1)]], d[val[off[:-1]]] != 0)
+        assert np.array_equal(Fm, want_F.astype(np.uint8))
+        want_V = np.zeros(nV, np.uint8); want_V[conn.F_vs[want_F].reshape(-1)] = 1
+        assert np.array_equal(Vm, want_V)
+        conn.close()
+
+
+def test_clean_hex_mesh_vs_reference_and_golden(fp, ctx, ref):
+    from clean_cases import lattice_around
+    g = dict(np.load(Path(__file__).resolve().parent / "golden" / "golden_clean_v1.npz"))
+    for name in ("torus", "tori"):
+        V, H, tV, tF = g[f"{name}_V"], g[f"{name}_hex"], g[f"{name}_tV"], g[f"{name}_tF"]
+        m = fp.TriMesh(ctx, tV, tF)
+        conn = fp.HexConnectivity(ctx, H, len(V), keep=True)
+        out = fp.clean_hex_mesh(ctx, m, V, H, conn)
+        assert np.array_equal(out["H_flag"], g[f"{name}_flag"]), name
+        assert np.array_equal(out["F_medial"], g[f"{name}_F_medial"]) and np.array_equal(out["V_medial"], g[f"{name}_V_medial"]), name
+        out2 = fp.clean_hex_mesh(ctx, m, V, H)                      # connectivity built inside
+        assert np.array_equal(out2["H_flag"], out["H_flag"]) and np.array_equal(out2["V_medial"], out["V_medial"])
+        conn.close(); m.close()
+    # live reference on a larger lattice with mirrored hexes (reorder inside the composition) and a gear
+    gV, gF = fp.procedural.gear(teeth=12, n_radial=4, n_axial=6, n_arc=2)[:2]
+    for (tV, tF), n in (((gV, gF), 28), (fp.procedural.linked_tori(2, 24, 12), 40)):
+        V, H = lattice_around(tV, n)
+        rng = np.random.default_rng(5)
+        mir = rng.random(len(H)) < 0.25
+        H = H.copy(); H[mir] = H[mir][:, [3, 2, 1, 0, 7, 6, 5, 4]]
+        rc = ref.RefClean(V, H)
+        want = rc.full(tV, tF)
+        wFm, wVm = rc.medial()
+        m = fp.TriMesh(ctx, tV, tF)
+        conn = fp.HexConnectivity(ctx, H, len(V), keep=True)
+        out = fp.clean_hex_mesh(ctx, m, V, H, conn)
+        assert out["stats"][0] == int(mir.sum())
+        assert np.array_equal(out["H_flag"], want), (n, int((out["H_flag"] != want).sum()))
+        assert np.array_equal(out["F_medial"], wFm) and np.array_equal(out["V_medial"], wVm)
+        sub = fp.reindex_submesh(ctx, out["hex"], len(V), out["H_flag"])
+        assert len(sub["H_map_reverse"]) == out["stats"][4] and len(sub["V_map_reverse"]) == out["stats"][5]
+        conn.close(); m.close()
+
+
+def test_clean_edge_cases(fp, ctx, ref):
+    from clean_cases import block
+    V, H = block(4, 4, 4)
+    nV = len(V)
+    # nothing inside: every stage leaves the flags alone and reports empty maps
+    z = np.zeros(len(H), np.uint8)
+    conn = fp.HexConnectivity(ctx, H, nV, keep=True)
+    t, _ = fp.tag_uneven_elements(ctx, conn, z)
+    rc = ref.RefClean(V, H); rc.set_flags(z)
+    assert np.array_equal(t, rc.tagging())
+    s = fp.reindex_submesh(ctx, H, nV, z)
+    assert len(s["hex"]) == 0 and (s["V_map"] == -1).all()
+    # two hexes sharing only an edge / only a vertex; a checkerboard (every interior vertex and edge non-manifold)
+    for pick in ([0, 5], [0, 21], None):
+        f = np.zeros(len(H), np.uint8)
+        if pick is None:
+            i, j, k = np.unravel_index(np.arange(len(H)), (4, 4, 4)); f[(i + j + k) % 2 == 0] = 1
+        else:
+            f[pick] = 1
+        rc = ref.RefClean(V, H); rc.set_flags(f); rc.reindex()
+        want = rc.non_manifold()
+        got, rounds = fp.clean_non_manifold(ctx, H, nV, f)
+        assert np.array_equal(got, want), (pick, rounds)
+        if want.any():
+            rc.reindex()
+            d, pieces = fp.drop_small_pieces(ctx, H, nV, got)
+            assert np.array_equal(d, rc.drop_small()), pick
+    # equal-sized pieces: the reference keeps the one found first
+    f = np.zeros(len(H), np.uint8); f[[0, 1, 62, 63]] = 1
+    rc = ref.RefClean(V, H); rc.set_flags(f); rc.reindex()
+    d, pieces = fp.drop_small_pieces(ctx, H, nV, f)
+    assert pieces == 2 and np.array_equal(d, rc.drop_small()) and d[0] == 1 and d[63] == 0
+    conn.close()
+    with pytest.raises(fp.FpohmError):
+        fp.reindex_submesh(ctx, H + 1000, nV, f)

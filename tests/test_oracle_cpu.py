@@ -282,3 +282,58 @@ def test_port_dual_conforming_mesh_vs_golden(port):
 def test_golden_dual_matches_live_reference(ref):
     for name, npos, nn, H, gs, Vp, want in _dual_cases():
         _same_hybrid(ref.conforming_and_dual_tables(npos, nn, Vp, H, gs)[1], want)
+
+
+# ---- §8(f)-2: clean_hex_mesh stages (golden_clean_v1.npz from the compiled reference, tests/golden/make_golden_clean.py) ----
+def _clean_golden():
+    return dict(np.load(ROOT / "tests" / "golden" / "golden_clean_v1.npz"))
+
+
+def test_port_clean_stages_vs_golden(port):
+    g = _clean_golden()
+    for name in "abcd":
+        V, H, flag = g[f"{name}_V"], g[f"{name}_hex"], g[f"{name}_flag"]
+        assert np.array_equal(port.reorder_hex_mesh(V, g[f"{name}_hex_mirrored"]), g[f"{name}_reordered"]), name
+        conn = port.hex_connectivity(H, len(V))
+        t = port.tagging_uneven_element(conn, flag)
+        assert np.array_equal(t, g[f"{name}_tagged"]), name
+        vm, vr, hr, sh = port.re_indexing_connectivity(H, len(V), t)
+        assert np.array_equal(vm, g[f"{name}_sub_V_map"]) and np.array_equal(vr, g[f"{name}_sub_V_map_reverse"])
+        assert np.array_equal(hr, g[f"{name}_sub_H_map_reverse"]) and np.array_equal(sh, g[f"{name}_sub_hex"])
+        n, _ = port.clean_non_manifold_ve(H, len(V), t)
+        assert np.array_equal(n, g[f"{name}_manifold"]), name
+        d, _ = port.drop_small_pieces(H, len(V), n)
+        assert np.array_equal(d, g[f"{name}_dropped"]), name
+
+
+def test_port_clean_hex_mesh_tail_vs_golden(port):
+    """Whole clean_hex_mesh from the signed distances on: the port's stages chained the way ghm.cpp:1953-1981 chains them."""
+    g = _clean_golden()
+    for name in ("torus", "tori"):
+        V, H, tV, tF = g[f"{name}_V"], g[f"{name}_hex"], g[f"{name}_tV"], g[f"{name}_tF"]
+        P = (V[H].max(1) + V[H].min(1)) / 2
+        t = port.PortTree(tV, tF)
+        S = t.signed_distance(P)[0]
+        flag = (S < 0).astype(np.uint8)
+        conn = port.hex_connectivity(H, len(V))
+        flag = port.tagging_uneven_element(conn, flag)
+        flag, _ = port.clean_non_manifold_ve(H, len(V), flag)
+        flag, _ = port.drop_small_pieces(H, len(V), flag)
+        assert np.array_equal(flag, g[f"{name}_flag"]), name
+        Fm, Vm = port.medial_surface_flags(conn, len(V), flag)
+        assert np.array_equal(Fm, g[f"{name}_F_medial"]) and np.array_equal(Vm, g[f"{name}_V_medial"]), name
+
+
+def test_golden_clean_matches_live_reference(ref):
+    g = _clean_golden()
+    for name in "ab":
+        rc = ref.RefClean(g[f"{name}_V"], g[f"{name}_hex"])
+        rc.set_flags(g[f"{name}_flag"])
+        assert np.array_equal(rc.tagging(), g[f"{name}_tagged"])
+        rc.reindex()
+        assert np.array_equal(rc.non_manifold(), g[f"{name}_manifold"])
+        assert np.array_equal(rc.drop_small(), g[f"{name}_dropped"])
+    rc = ref.RefClean(g["torus_V"], g["torus_hex"])
+    assert np.array_equal(rc.full(g["torus_tV"], g["torus_tF"]), g["torus_flag"])
+    Fm, Vm = rc.medial()
+    assert np.array_equal(Fm, g["torus_F_medial"]) and np.array_equal(Vm, g["torus_V_medial"])
