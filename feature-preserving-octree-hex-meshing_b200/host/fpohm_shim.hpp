@@ -22,6 +22,12 @@
 //   compute(mesh0, mesh1, diag, max, ave)          metro_hausdorff.cpp:358   compute(mesh0, mesh1, diag, max, ave)
 //   hausdorff_ratio_check / compute(..., ratio, thr) metro_hausdorff.cpp:12  compute(mesh0, mesh1, ratio, thr)
 //   hausdorff_dis(mesh0, mesh1, outlierVs, thr)    gf.cpp:3590           hausdorff_dis(mesh0, mesh1, outlierVs, thr)
+//   reorder_hex_mesh(Mesh&)                        gf.cpp:2199           reorder_hex_mesh(hmi)
+//   re_indexing_connectivity(hmi, H_flag, Ho, V_map, V_map_reverse, H_map, H_map_reverse) gf.cpp:664   same name and arguments
+//   tagging_uneven_element(mi, H_flag)             ghm.cpp:1983          tagging_uneven_element(mi, H_flag)
+//   clean_non_manifold_ve(mi, hmi_local, maps..., signed_dis, H_flag) ghm.cpp:2006   same name and arguments
+//   drop_small_pieces(Mesh_Domain&)                ghm.cpp:2081          drop_small_pieces(md)
+//   clean_hex_mesh(Mesh &tmi, Mesh_Domain &md)     ghm.cpp:1932          clean_hex_mesh(tmi, md)   (args.scaffold_type 1)
 //
 // Error behaviour mirrors the reference: bool returns and a line on std::cout/cerr, never an exception out of a call the
 // reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
@@ -193,6 +199,117 @@ void build_connectivity(MeshT &hmi) {
 	fill(5, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_fs; });
 	fill(6, nV, [&](int64_t i) -> std::vector<uint32_t> & { return hmi.Vs[i].neighbor_hs; });
 	fpohm_conn_free(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// clean_hex_mesh and its stages (ghm.cpp:1932-2124).  H_flag travels as one byte per hex.
+template <class MeshT>
+std::vector<uint32_t> hex_list(const MeshT &m) {
+	std::vector<uint32_t> hex(8 * m.Hs.size());
+	for (size_t i = 0; i < m.Hs.size(); ++i) for (int k = 0; k < 8; ++k) hex[8 * i + k] = m.Hs[i].vs[k];
+	return hex;
+}
+inline std::vector<uint8_t> to_bytes(const std::vector<bool> &f) { std::vector<uint8_t> b(f.size()); for (size_t i = 0; i < f.size(); ++i) b[i] = f[i]; return b; }
+inline void from_bytes(const std::vector<uint8_t> &b, std::vector<bool> &f) { f.resize(b.size()); for (size_t i = 0; i < b.size(); ++i) f[i] = b[i] != 0; }
+
+// reorder_hex_mesh(Mesh &hmi), gf.cpp:2199-2229
+template <class MeshT>
+void reorder_hex_mesh(MeshT &hmi) {
+	std::vector<uint32_t> hex = hex_list(hmi);
+	check(fpohm_reorder_hexes(context(), hmi.V.data(), (int64_t)hmi.V.cols(), hex.data(), (int64_t)hmi.Hs.size(), nullptr), "fpohm_reorder_hexes");
+	for (size_t i = 0; i < hmi.Hs.size(); ++i) hmi.Hs[i].vs.assign(hex.begin() + 8 * i, hex.begin() + 8 * i + 8);
+}
+
+// tagging_uneven_element(const Mesh &mi, vector<bool> &H_flag), ghm.cpp:1983-2005 (mi's connectivity is rebuilt on the device)
+template <class MeshT>
+void tagging_uneven_element(const MeshT &mi, std::vector<bool> &H_flag) {
+	const std::vector<uint32_t> hex = hex_list(mi);
+	fpohm_conn *c = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), (int64_t)mi.Hs.size(), (int64_t)mi.Vs.size(), &c), "fpohm_hex_connectivity");
+	std::vector<uint8_t> f = to_bytes(H_flag);
+	const int rc = fpohm_tag_uneven_elements(context(), c, f.data(), nullptr);
+	fpohm_conn_free(c);
+	check(rc, "fpohm_tag_uneven_elements");
+	from_bytes(f, H_flag);
+}
+
+// re_indexing_connectivity(Mesh &hmi, vector<bool> &H_flag, Mesh &Ho, V_map, V_map_reverse, H_map, H_map_reverse), gf.cpp:664-698
+template <class MeshT>
+void re_indexing_connectivity(MeshT &hmi, std::vector<bool> &H_flag, MeshT &Ho, std::vector<int32_t> &V_map, std::vector<int32_t> &V_map_reverse,
+                              std::vector<int32_t> &H_map, std::vector<int32_t> &H_map_reverse)
+{
+	const int64_t H = (int64_t)hmi.Hs.size(), nV = (int64_t)hmi.Vs.size();
+	const std::vector<uint32_t> hex = hex_list(hmi);
+	const std::vector<uint8_t> f = to_bytes(H_flag);
+	V_map.assign((size_t)nV, -1); V_map_reverse.assign((size_t)nV, 0); H_map.clear(); H_map_reverse.assign((size_t)H, 0);
+	std::vector<uint32_t> sub(8 * (size_t)H);
+	int64_t nv = 0, nh = 0;
+	check(fpohm_reindex_submesh(context(), hex.data(), H, nV, f.data(), V_map.data(), V_map_reverse.data(), &nv, H_map_reverse.data(), &nh, sub.data()),
+	      "fpohm_reindex_submesh");
+	V_map_reverse.resize((size_t)nv); H_map_reverse.resize((size_t)nh);
+	Ho = MeshT();
+	Ho.type = hmi.type;
+	Ho.Vs.resize((size_t)nv);
+	Ho.V.resize(3, nv);
+	for (int64_t j = 0; j < nv; ++j) {
+		auto &v = Ho.Vs[(size_t)j];
+		v.id = (uint32_t)j; v.v = hmi.Vs[(size_t)V_map_reverse[(size_t)j]].v;
+		for (int d = 0; d < 3; ++d) Ho.V(d, j) = v.v[d];
+	}
+	Ho.Hs.resize((size_t)nh);
+	for (int64_t h = 0; h < nh; ++h) { Ho.Hs[(size_t)h].id = (uint32_t)h; Ho.Hs[(size_t)h].vs.assign(sub.begin() + 8 * h, sub.begin() + 8 * h + 8); }
+	if (nh > 0) build_connectivity(Ho);
+}
+
+// clean_non_manifold_ve(mi, hmi_local, V_map, V_map_reverse, H_map, H_map_reverse, signed_dis, H_flag), ghm.cpp:2006-2080
+template <class MeshT, class VecS>
+void clean_non_manifold_ve(MeshT &mi, MeshT &hmi_local, std::vector<int> &V_map, std::vector<int> &V_map_reverse, std::vector<int> &H_map,
+                           std::vector<int> &H_map_reverse, VecS & /*signed_dis: unused by the reference too*/, std::vector<bool> &H_flag)
+{
+	const std::vector<uint32_t> hex = hex_list(mi);
+	std::vector<uint8_t> f = to_bytes(H_flag);
+	int32_t rounds = 0;
+	check(fpohm_clean_non_manifold(context(), hex.data(), (int64_t)mi.Hs.size(), (int64_t)mi.Vs.size(), f.data(), &rounds), "fpohm_clean_non_manifold");
+	from_bytes(f, H_flag);
+	if (rounds > 0) re_indexing_connectivity(mi, H_flag, hmi_local, V_map, V_map_reverse, H_map, H_map_reverse);   // what the last round leaves behind
+}
+
+// drop_small_pieces(Mesh_Domain &md), ghm.cpp:2081-2124
+template <class DomainT>
+void drop_small_pieces(DomainT &md) {
+	const std::vector<uint32_t> hex = hex_list(md.mesh_entire);
+	std::vector<uint8_t> f = to_bytes(md.H_flag);
+	int64_t pieces = 0;
+	check(fpohm_drop_small_pieces(context(), hex.data(), (int64_t)md.mesh_entire.Hs.size(), (int64_t)md.mesh_entire.Vs.size(), f.data(), &pieces), "fpohm_drop_small_pieces");
+	if (pieces > 1) {
+		from_bytes(f, md.H_flag);
+		re_indexing_connectivity(md.mesh_entire, md.H_flag, md.mesh_subA, md.V_map, md.V_map_reverse, md.H_map, md.H_map_reverse);
+	}
+}
+
+// clean_hex_mesh(Mesh &tmi, Mesh_Domain &md), ghm.cpp:1932-1981 with args.scaffold_type == 1.  md.mesh_entire must carry its
+// connectivity (Fs / Vs are where the medial flags go), as it does in the pipeline (ghm.cpp:205-209).
+template <class MeshT, class DomainT>
+void clean_hex_mesh(MeshT &tmi, DomainT &md) {
+	auto &mi = md.mesh_entire;
+	const int64_t H = (int64_t)mi.Hs.size(), nV = (int64_t)mi.Vs.size();
+	std::vector<uint32_t> hex = hex_list(mi);
+	DeviceMesh surface(tmi);
+	fpohm_conn *c = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), H, nV, &c), "fpohm_hex_connectivity");
+	int64_t nF = 0;
+	fpohm_conn_sizes(c, &nF, nullptr);
+	std::vector<uint8_t> f((size_t)H), Fm((size_t)nF), Vm((size_t)nV);
+	int64_t stats[6];
+	const int rc = fpohm_clean_hex_mesh(context(), surface.h, mi.V.data(), nV, hex.data(), H, c, nullptr, f.data(), Fm.data(), Vm.data(), stats);
+	fpohm_conn_free(c);
+	check(rc, "fpohm_clean_hex_mesh");
+	for (int64_t i = 0; i < H; ++i) mi.Hs[(size_t)i].vs.assign(hex.begin() + 8 * i, hex.begin() + 8 * i + 8);      // reorder_hex_mesh
+	from_bytes(f, md.H_flag);
+	re_indexing_connectivity(mi, md.H_flag, md.mesh_subA, md.V_map, md.V_map_reverse, md.H_map, md.H_map_reverse);
+	if (!md.mesh_subA.Hs.size()) { std::cout << "no elements inside the object, exit"; return; }
+	if ((int64_t)mi.Fs.size() == nF) for (int64_t i = 0; i < nF; ++i) if (Fm[(size_t)i]) mi.Fs[(size_t)i].on_medial_surface = true;
+	for (int64_t i = 0; i < nV; ++i) if (Vm[(size_t)i]) mi.Vs[(size_t)i].on_medial_surface = true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -208,6 +208,51 @@ int main() {
 		int n_in = 0; for (float v : inside) n_in += v > 0.5f;
 		EXPECT(same && a == b && n_in > 0, "compute_octree identical hexes (positions bit-exact, geogram corner order) and inside flags");
 	}
+	// ---- clean_hex_mesh (ghm.cpp:1932-1981) and its stages on a lattice around the torus, a quarter of the hexes mirrored
+	{
+		Mesh t; torus(40, 24, t);
+		auto lattice = [&](Mesh &m) {
+			hex_block(20, 0.0, m);
+			for (int i = 0; i < m.V.cols(); ++i) {
+				for (int d = 0; d < 3; ++d) m.V(d, i) = (m.V(d, i) - 0.5) * (d == 2 ? 0.4 : 1.1);
+				m.Vs[i].v = {m.V(0, i), m.V(1, i), m.V(2, i)};
+			}
+			for (size_t h = 0; h < m.Hs.size(); h += 4) { auto vs = m.Hs[h].vs; m.Hs[h].vs = {vs[3], vs[2], vs[1], vs[0], vs[7], vs[6], vs[5], vs[4]}; }
+			::build_connectivity(m);
+		};
+		Mesh_Domain a, b;
+		lattice(a.mesh_entire); lattice(b.mesh_entire);
+		grid_hex_meshing_bijective gm;
+		gm.clean_hex_mesh(t, a);
+		fpohm_shim::clean_hex_mesh(t, b);
+		bool same = a.H_flag == b.H_flag && a.V_map == b.V_map && a.V_map_reverse == b.V_map_reverse && a.H_map_reverse == b.H_map_reverse &&
+		            a.mesh_subA.Hs.size() == b.mesh_subA.Hs.size() && a.mesh_subA.Fs.size() == b.mesh_subA.Fs.size() && a.mesh_subA.V == b.mesh_subA.V;
+		size_t kept = 0, medial = 0;
+		for (bool x : a.H_flag) kept += x;
+		for (size_t i = 0; same && i < a.mesh_entire.Hs.size(); ++i) same = a.mesh_entire.Hs[i].vs == b.mesh_entire.Hs[i].vs;
+		for (size_t i = 0; same && i < a.mesh_subA.Hs.size(); ++i) same = a.mesh_subA.Hs[i].vs == b.mesh_subA.Hs[i].vs && a.mesh_subA.Hs[i].fs == b.mesh_subA.Hs[i].fs;
+		for (size_t i = 0; same && i < a.mesh_subA.Fs.size(); ++i) same = a.mesh_subA.Fs[i].vs == b.mesh_subA.Fs[i].vs && a.mesh_subA.Fs[i].boundary == b.mesh_subA.Fs[i].boundary;
+		for (size_t i = 0; same && i < a.mesh_entire.Fs.size(); ++i) { same = a.mesh_entire.Fs[i].on_medial_surface == b.mesh_entire.Fs[i].on_medial_surface; medial += a.mesh_entire.Fs[i].on_medial_surface; }
+		for (size_t i = 0; same && i < a.mesh_entire.Vs.size(); ++i) same = a.mesh_entire.Vs[i].on_medial_surface == b.mesh_entire.Vs[i].on_medial_surface;
+		EXPECT(same && kept > 0 && medial > 0, "clean_hex_mesh identical H_flag, maps, sub-mesh and medial-surface flags");
+		// stages on a carved flag set: every third hex dropped from what is inside, which leaves non-manifold vertices and edges
+		std::vector<bool> fa = a.H_flag, fb;
+		for (size_t i = 0; i < fa.size(); i += 3) fa[i] = false;
+		fb = fa;
+		gm.tagging_uneven_element(a.mesh_entire, fa);
+		fpohm_shim::tagging_uneven_element(b.mesh_entire, fb);
+		EXPECT(fa == fb, "tagging_uneven_element identical flags");
+		a.H_flag = fa; b.H_flag = fb;
+		::re_indexing_connectivity(a.mesh_entire, a.H_flag, a.mesh_subA, a.V_map, a.V_map_reverse, a.H_map, a.H_map_reverse);
+		fpohm_shim::re_indexing_connectivity(b.mesh_entire, b.H_flag, b.mesh_subA, b.V_map, b.V_map_reverse, b.H_map, b.H_map_reverse);
+		Eigen::VectorXd sd;
+		gm.clean_non_manifold_ve(a.mesh_entire, a.mesh_subA, a.V_map, a.V_map_reverse, a.H_map, a.H_map_reverse, sd, a.H_flag);
+		fpohm_shim::clean_non_manifold_ve(b.mesh_entire, b.mesh_subA, b.V_map, b.V_map_reverse, b.H_map, b.H_map_reverse, sd, b.H_flag);
+		EXPECT(a.H_flag == b.H_flag && a.H_flag != fa && a.mesh_subA.Hs.size() == b.mesh_subA.Hs.size() && a.V_map == b.V_map, "clean_non_manifold_ve identical flags and re-indexed sub-mesh");
+		gm.drop_small_pieces(a);
+		fpohm_shim::drop_small_pieces(b);
+		EXPECT(a.H_flag == b.H_flag && a.H_map_reverse == b.H_map_reverse && a.mesh_subA.Es.size() == b.mesh_subA.Es.size(), "drop_small_pieces identical flags and sub-mesh");
+	}
 	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
 	return failures ? 1 : 0;
 }
