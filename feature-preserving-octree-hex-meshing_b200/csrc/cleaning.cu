@@ -631,24 +631,33 @@ int fpohm_clean_hex_mesh(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, i
 	FPOHM_REQUIRE(!conn || (conn->H == H && conn->nV == nV), FPOHM_EINVAL, "fpohm_clean_hex_mesh: conn belongs to another mesh");
 	check_hex(hex, H, nV, "fpohm_clean_hex_mesh");
 	int64_t st[6] = {0, 0, 0, 0, 0, 0};      // mirrored hexes, tagging sweeps, non-manifold rounds, pieces, hexes kept, vertices kept
-	int rc = fpohm_reorder_hexes(ctx, V, nV, hex, H, &st[0]);                                   // ghm.cpp:1935
-	if (rc != FPOHM_OK) return rc;
-	rc = fpohm_classify_hexes(ctx, surface, V, nV, hex, H, signed_dis, H_flag);                 // ghm.cpp:1937-1951
-	if (rc != FPOHM_OK) return rc;
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
-	fpohm_conn *own = nullptr;
+	// one upload of V and hex; every stage below works on the device copies
+	DevBuf<double> dV(3 * nV, s), dS(H, s);
 	DevBuf<uint32_t> dhex(8 * H, s);
-	dhex.upload(hex, 8 * H);
+	DevBuf<unsigned long long> cnt(1, s);
+	DevBuf<uint8_t> flag(H, s);
+	dV.upload(V, 3 * nV); dhex.upload(hex, 8 * H); cnt.zero();
+	reorder_hexes_kernel<<<grid_for(ctx, H, 128), 128, 0, s>>>(dV.p, dhex.p, H, cnt.p);              // ghm.cpp:1935
+	FPOHM_LAUNCH_CHECK(ctx);
+	classify_hexes_dev(ctx, surface, dV.p, dhex.p, H, dS.p, flag.p, s);                              // ghm.cpp:1937-1951
+	{
+		unsigned long long n = 0;
+		cnt.download(&n, 1);
+		dhex.download(hex, 8 * H);
+		if (signed_dis) dS.download(signed_dis, H);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+		st[0] = (int64_t)n;
+	}
+	fpohm_conn *own = nullptr;
 	if (!conn) {
 		DevBuf<uint32_t> copy(8 * H, s);
-		copy.upload(hex, 8 * H);
+		FPOHM_CUDA(cudaMemcpyAsync(copy.p, dhex.p, 32 * (size_t)H, cudaMemcpyDeviceToDevice, s));
 		own = conn_build_dev(ctx, std::move(copy), H, nV, false);
 		conn = own;
 	}
 	try {
-		DevBuf<uint8_t> flag(H, s);
-		flag.upload(H_flag, H);
 		st[1] = tag_dev(ctx, conn, flag.p, s);                                                  // ghm.cpp:1954
 		SubConn sc;
 		build_sub(ctx, dhex.p, H, nV, flag.p, sc, s);                                           // ghm.cpp:1955

@@ -1068,6 +1068,23 @@ int fpohm_signed_distance(fpohm_ctx *ctx, fpohm_mesh *mesh, const double *P, int
 	return host_query(ctx, mesh, true, P, np, S, I, C, N, "fpohm_signed_distance");
 }
 
+} // extern "C"
+
+// device form of fpohm_classify_hexes, shared with cleaning.cu
+void fpohm::classify_hexes_dev(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V_dev, const uint32_t *hex_dev, int64_t H,
+                               double *S_dev, uint8_t *flag_dev, cudaStream_t s)
+{
+	mesh_ensure_tree(ctx, surface, s);
+	DevBuf<double> dP(3 * H, s);
+	hex_box_centres_kernel<<<grid_for(ctx, 3 * H, 256), 256, 0, s>>>(V_dev, hex_dev, H, dP.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	launch_closest_point(ctx, surface, true, dP.p, H, S_dev, nullptr, nullptr, nullptr, s);
+	inside_flags_kernel<<<grid_for(ctx, H, 256), 256, 0, s>>>(S_dev, H, flag_dev);
+	FPOHM_LAUNCH_CHECK(ctx);
+}
+
+extern "C" {
+
 int fpohm_classify_hexes(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, int64_t nV, const uint32_t *hex, int64_t H,
                          double *signed_dis, uint8_t *H_flag)
 {
@@ -1077,17 +1094,12 @@ int fpohm_classify_hexes(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, i
 	for (int64_t i = 0; i < 8 * H; ++i) FPOHM_REQUIRE((int64_t)hex[i] < nV, FPOHM_EINVAL, "fpohm_classify_hexes: corner id %u out of range at %lld", hex[i], (long long)i);
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
-	mesh_ensure_tree(ctx, surface, s);
-	DevBuf<double> dV(3 * nV, s), dP(3 * H, s), dS(H, s);
+	DevBuf<double> dV(3 * nV, s), dS(H, s);
 	DevBuf<uint32_t> dhex(8 * H, s);
 	DevBuf<uint8_t> dF(H, s);
 	dV.upload(V, 3 * nV); dhex.upload(hex, 8 * H);
 	KernelTimer t(ctx, s);
-	hex_box_centres_kernel<<<grid_for(ctx, 3 * H, 256), 256, 0, s>>>(dV.p, dhex.p, H, dP.p);
-	FPOHM_LAUNCH_CHECK(ctx);
-	launch_closest_point(ctx, surface, true, dP.p, H, dS.p, nullptr, nullptr, nullptr, s);
-	inside_flags_kernel<<<grid_for(ctx, H, 256), 256, 0, s>>>(dS.p, H, dF.p);
-	FPOHM_LAUNCH_CHECK(ctx);
+	classify_hexes_dev(ctx, surface, dV.p, dhex.p, H, dS.p, dF.p, s);
 	t.stop();
 	if (signed_dis) dS.download(signed_dis, H);
 	if (H_flag) dF.download(H_flag, H);

@@ -75,6 +75,9 @@ struct fpohm_mesh {
 namespace fpohm {
 void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
 void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
+// head of clean_hex_mesh on device arrays: bbox centres -> signed distance -> flag = S < 0 (closest_point.cu)
+void classify_hexes_dev(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V_dev, const uint32_t *hex_dev, int64_t H,
+                        double *S_dev, uint8_t *flag_dev, cudaStream_t s);
 // closest point (+ pseudonormal sign when with_sign) of np device-resident points; S = signed distance, or the
 // SQUARED distance when !with_sign.  Any output may be null.
 void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,

@@ -208,3 +208,17 @@ def warped_hex_block(n: int = 16, amp: float = 0.3, seed: int = 42):
     c = lambda dx, dy, dz: idx[dx:n + dx, dy:n + dy, dz:n + dz].reshape(-1)
     H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
     return np.ascontiguousarray(V), np.ascontiguousarray(H.astype(np.uint32))
+
+
+def hex_lattice_around(tV, n: int):
+    """Regular hex lattice (corner order of hex_ref_shape, vertex (i,j,k) at id (i*(ny+1)+j)*(nz+1)+k) with n cells along the
+    longest axis of the bounding box of tV, padded by one cell — the shape voxel_meshing hands to clean_hex_mesh."""
+    tV = np.asarray(tV, np.float64)
+    lo, hi = tV.min(0), tV.max(0)
+    h = (hi - lo).max() / n
+    nx, ny, nz = (int(d) for d in np.maximum(np.ceil((hi - lo) / h).astype(int) + 2, 3))
+    idx = np.arange((nx + 1) * (ny + 1) * (nz + 1), dtype=np.int64).reshape(nx + 1, ny + 1, nz + 1)
+    g = np.stack(np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    c = lambda dx, dy, dz: idx[dx:nx + dx, dy:ny + dy, dz:nz + dz].reshape(-1)
+    H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
+    return np.ascontiguousarray(g * h + (lo - h)), np.ascontiguousarray(H.astype(np.uint32))
