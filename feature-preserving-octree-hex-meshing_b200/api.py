@@ -15,7 +15,7 @@ __all__ = [
     "FpohmError", "LIB_PATH", "lib", "device_count", "Context", "TriMesh", "OctreeParams", "Octree", "OctreeShard",
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
-    "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh",
+    "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh", "extract_surface",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -463,6 +463,33 @@ def clean_hex_mesh(ctx: Context, surface: "TriMesh", V, hexa, conn: "HexConnecti
     _chk(lib().fpohm_clean_hex_mesh(ctx.h, surface.h, _p(V), C.c_int64(len(V)), _p(hx), C.c_int64(H), conn.h if conn is not None else None,
                                     _p(S), _p(flag), _p(Fm) if Fm is not None else None, _p(Vm), stats))
     return dict(hex=hx, signed_dis=S, H_flag=flag, F_medial=Fm, V_medial=Vm, stats=list(stats))
+
+
+def extract_surface(ctx: Context, conn: "HexConnectivity", V, as_triangles: bool = False):
+    """extract_surface_conforming_mesh + orient_surface_mesh (gf.cpp:1021-1112) on the hex mesh behind conn (keep=True)."""
+    V = _f64(V)
+    h = C.c_void_p()
+    _chk(lib().fpohm_extract_surface(ctx.h, conn.h, _p(V), C.c_int32(1 if as_triangles else 0), C.byref(h)))
+    try:
+        nV, nF, nE, lv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        vn = C.c_int32()
+        _chk(lib().fpohm_surface_sizes(h, C.byref(nV), C.byref(nF), C.byref(nE), C.byref(vn), C.byref(lv)))
+        nV, nF, nE, vn = nV.value, nF.value, nE.value, vn.value
+        out = dict(V=np.zeros((nV, 3)), F_vs=np.zeros((nF, vn), np.uint32), F_es=np.zeros((nF, vn), np.uint32), E_vs=np.zeros((nE, 2), np.uint32),
+                   E_boundary=np.zeros(nE, np.uint8), V_boundary=np.zeros(nV, np.uint8), V_map=np.zeros(len(V), np.int32),
+                   V_map_reverse=np.zeros(nV, np.int32), F_map=np.zeros(len(conn.F_vs), np.int32), F_map_reverse=np.zeros(nF, np.int32))
+        _chk(lib().fpohm_surface_export(h, _p(out["V"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["E_vs"]), _p(out["E_boundary"]), _p(out["V_boundary"]),
+                                        _p(out["V_map"]), _p(out["V_map_reverse"]), _p(out["F_map"]), _p(out["F_map_reverse"])))
+        for which, (nm, n) in enumerate((("E_nfs", nE), ("V_nvs", nV), ("V_nes", nV), ("V_nfs", nV))):
+            tot = C.c_int64()
+            _chk(lib().fpohm_surface_csr(h, C.c_int32(which), None, None, C.byref(tot)))
+            off = np.zeros(n + 1, np.int64); val = np.zeros(tot.value, np.uint32)
+            _chk(lib().fpohm_surface_csr(h, C.c_int32(which), _p(off), _p(val), C.byref(tot)))
+            out[nm] = (off, val)
+        out["bfs_levels"] = lv.value
+        return out
+    finally:
+        lib().fpohm_surface_free(h)
 
 
 def _hybrid_to_dict(hy):

@@ -40,6 +40,7 @@ extern "C" {
 typedef struct fpohm_ctx    fpohm_ctx;     /* one per GPU: device id, streams, scratch arena            */
 typedef struct fpohm_mesh   fpohm_mesh;    /* device-resident triangle soup + facet bboxes (+ trees)     */
 typedef struct fpohm_octree fpohm_octree;  /* device-resident graded/paired octree                       */
+typedef struct fpohm_surface fpohm_surface; /* result of fpohm_extract_surface                          */
 typedef struct fpohm_conn   fpohm_conn;    /* result of fpohm_hex_connectivity                           */
 
 const char *fpohm_last_error(void);
@@ -267,6 +268,22 @@ int  fpohm_medial_surface_flags(fpohm_ctx *ctx, const fpohm_conn *conn, const ui
 int  fpohm_clean_hex_mesh(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V, int64_t nV, uint32_t *hex, int64_t H,
                           const fpohm_conn *conn, double *signed_dis, uint8_t *H_flag, uint8_t *F_medial, uint8_t *V_medial,
                           int64_t stats[6]);
+
+/* ---- extract_surface_conforming_mesh (global_functions.cpp:1021-1072) with orient_surface_mesh (:1073-1112): the boundary
+ * faces of the hex mesh behind `conn` as a quad surface (as_triangles = 0; Mesh_type::Qua) or a triangle surface (two
+ * triangles (0,1,2), (2,3,0) per quad; Mesh_type::Tri), vertices renumbered, consistently oriented from face 0 and flipped
+ * as a whole when the signed volume is positive, with the tables build_connectivity leaves on a surface mesh.  V = the
+ * hex mesh's vertex positions (xyz per vertex).  The component of face 0 must be an orientable 2-manifold (what
+ * clean_hex_mesh leaves behind); otherwise FPOHM_EINVAL.
+ * export: V 3/vertex, F_vs and F_es vn/face, E_vs 2/edge, flags, V_map (per hex-mesh vertex, -1 = not on the boundary),
+ * V_map_reverse, F_map (per hex-mesh face; first triangle for a triangle surface), F_map_reverse.  Any may be NULL.
+ * csr which: 0 E.neighbor_fs 1 V.neighbor_vs 2 V.neighbor_es 3 V.neighbor_fs. */
+int  fpohm_extract_surface(fpohm_ctx *ctx, const fpohm_conn *conn, const double *V, int32_t as_triangles, fpohm_surface **out);
+int  fpohm_surface_sizes(const fpohm_surface *s, int64_t *nV, int64_t *nF, int64_t *nE, int32_t *vn, int64_t *bfs_levels);
+int  fpohm_surface_export(const fpohm_surface *s, double *V, uint32_t *F_vs, uint32_t *F_es, uint32_t *E_vs, uint8_t *E_boundary,
+                          uint8_t *V_boundary, int32_t *V_map, int32_t *V_map_reverse, int32_t *F_map, int32_t *F_map_reverse);
+int  fpohm_surface_csr(const fpohm_surface *s, int32_t which, int64_t *off, uint32_t *val, int64_t *total);
+void fpohm_surface_free(fpohm_surface *s);
 
 /* ---- conforming_mesh (grid_meshing/grid_hex_meshing.cpp:568-696): the octree hex mesh with every big
  * face at a T-junction replaced by the 4 small faces of the other side and the mid vertices inserted into the loops of

@@ -228,4 +228,59 @@ void ref_clean_medial(void *rv, uint8_t *F_medial, uint8_t *V_medial) {
 	for (size_t f = 0; f < m.Fs.size(); ++f) F_medial[f] = m.Fs[f].on_medial_surface ? 1 : 0;
 	for (size_t v = 0; v < m.Vs.size(); ++v) V_medial[v] = m.Vs[v].on_medial_surface ? 1 : 0;
 }
+
+// ---- extract_surface_conforming_mesh (global_functions.cpp:1021-1072: boundary faces -> quad / triangle surface,
+// build_connectivity, orient_surface_mesh :1073-1112, build_connectivity) on a hex mesh given as (Vpos, hex)
+struct RefSurface { Mesh hexm, sur; std::vector<int32_t> V_map, V_map_reverse, F_map, F_map_reverse; };
+void *ref_extract_surface(const double *Vpos, int64_t nV, const uint32_t *hex, int64_t H, int as_triangles, int64_t sizes[6]) {
+	RefSurface *r = new RefSurface;
+	Mesh &m = r->hexm;
+	m.type = Mesh_type::Hex;
+	m.Vs.resize((size_t)nV);
+	m.V.resize(3, nV);
+	for (int64_t i = 0; i < nV; ++i) {
+		Hybrid_V v; v.id = (uint32_t)i;
+		for (int d = 0; d < 3; ++d) { v.v.push_back(Vpos[3 * i + d]); m.V(d, i) = Vpos[3 * i + d]; }
+		m.Vs[(size_t)i] = v;
+	}
+	m.Hs.resize((size_t)H);
+	for (int64_t h = 0; h < H; ++h) { m.Hs[(size_t)h].id = (uint32_t)h; m.Hs[(size_t)h].vs.assign(hex + 8 * h, hex + 8 * h + 8); }
+	build_connectivity(m);
+	r->sur.type = as_triangles ? Mesh_type::Tri : Mesh_type::Qua;
+	extract_surface_conforming_mesh(m, r->sur, r->V_map, r->V_map_reverse, r->F_map, r->F_map_reverse);
+	int64_t nfs = 0, nvf = 0;
+	for (auto &e : r->sur.Es) nfs += (int64_t)e.neighbor_fs.size();
+	for (auto &v : r->sur.Vs) nvf += (int64_t)v.neighbor_fs.size();
+	sizes[0] = (int64_t)r->sur.Vs.size(); sizes[1] = (int64_t)r->sur.Fs.size(); sizes[2] = (int64_t)r->sur.Es.size();
+	sizes[3] = nfs; sizes[4] = nvf; sizes[5] = (int64_t)m.Fs.size();
+	return r;
+}
+// V 3 nV, F_vs / F_es vn nF, E_vs 2 nE, flags, V_map nV(hex mesh), V_map_reverse nV, F_map nF(hex mesh), F_map_reverse nF
+void ref_surface_export(void *rv, double *V, uint32_t *F_vs, uint32_t *F_es, uint32_t *E_vs, uint8_t *E_boundary, uint8_t *V_boundary,
+                        int32_t *V_map, int32_t *V_map_reverse, int32_t *F_map, int32_t *F_map_reverse)
+{
+	RefSurface *r = (RefSurface *)rv;
+	const Mesh &s = r->sur;
+	for (size_t v = 0; v < s.Vs.size(); ++v) { for (int d = 0; d < 3; ++d) V[3 * v + d] = s.V(d, v); V_boundary[v] = s.Vs[v].boundary; }
+	size_t t = 0;
+	for (size_t f = 0; f < s.Fs.size(); ++f) for (size_t k = 0; k < s.Fs[f].vs.size(); ++k, ++t) { F_vs[t] = s.Fs[f].vs[k]; F_es[t] = s.Fs[f].es[k]; }
+	for (size_t e = 0; e < s.Es.size(); ++e) { E_vs[2 * e] = s.Es[e].vs[0]; E_vs[2 * e + 1] = s.Es[e].vs[1]; E_boundary[e] = s.Es[e].boundary; }
+	for (size_t i = 0; i < r->V_map.size(); ++i) V_map[i] = r->V_map[i];
+	for (size_t i = 0; i < r->V_map_reverse.size(); ++i) V_map_reverse[i] = r->V_map_reverse[i];
+	for (size_t i = 0; i < r->F_map.size(); ++i) F_map[i] = r->F_map[i];
+	for (size_t i = 0; i < r->F_map_reverse.size(); ++i) F_map_reverse[i] = r->F_map_reverse[i];
+}
+// which: 0 E.neighbor_fs 1 V.neighbor_vs 2 V.neighbor_es 3 V.neighbor_fs; off has n+1 entries
+void ref_surface_csr(void *rv, int which, int64_t *off, uint32_t *val) {
+	const Mesh &s = ((RefSurface *)rv)->sur;
+	const size_t n = which == 0 ? s.Es.size() : s.Vs.size();
+	int64_t t = 0;
+	for (size_t i = 0; i < n; ++i) {
+		const std::vector<uint32_t> &l = which == 0 ? s.Es[i].neighbor_fs : which == 1 ? s.Vs[i].neighbor_vs : which == 2 ? s.Vs[i].neighbor_es : s.Vs[i].neighbor_fs;
+		off[i] = t;
+		for (uint32_t x : l) val[t++] = x;
+	}
+	off[n] = t;
+}
+void ref_surface_free(void *rv) { delete (RefSurface *)rv; }
 }

@@ -365,3 +365,24 @@ class RefClean:
         Fm, Vm = np.zeros(int(sizes[2]), np.uint8), np.zeros(int(sizes[0]), np.uint8)
         lib().ref_clean_medial(self.h, _p(Fm), _p(Vm))
         return Fm, Vm
+
+
+def extract_surface(Vpos, hexa, as_triangles=False):
+    """extract_surface_conforming_mesh (global_functions.cpp:1021-1072) incl. orient_surface_mesh, on the hex mesh (Vpos, hexa)."""
+    Vp, hx = _f64(Vpos), np.ascontiguousarray(hexa, np.uint32)
+    sizes = (C.c_int64 * 6)()
+    lib().ref_extract_surface.restype = C.c_void_p
+    h = C.c_void_p(lib().ref_extract_surface(_p(Vp), C.c_int64(len(Vp)), _p(hx), C.c_int64(len(hx)), C.c_int(1 if as_triangles else 0), sizes))
+    nv, nf, ne, nfs, nvf, nF_hex = [int(x) for x in sizes]
+    vn = 3 if as_triangles else 4
+    out = dict(V=np.zeros((nv, 3)), F_vs=np.zeros((nf, vn), np.uint32), F_es=np.zeros((nf, vn), np.uint32), E_vs=np.zeros((ne, 2), np.uint32),
+               E_boundary=np.zeros(ne, np.uint8), V_boundary=np.zeros(nv, np.uint8), V_map=np.zeros(len(Vp), np.int32),
+               V_map_reverse=np.zeros(nv, np.int32), F_map=np.zeros(nF_hex, np.int32), F_map_reverse=np.zeros(nf, np.int32))
+    lib().ref_surface_export(h, _p(out["V"]), _p(out["F_vs"]), _p(out["F_es"]), _p(out["E_vs"]), _p(out["E_boundary"]), _p(out["V_boundary"]),
+                             _p(out["V_map"]), _p(out["V_map_reverse"]), _p(out["F_map"]), _p(out["F_map_reverse"]))
+    for which, (nm, n, tot) in enumerate((("E_nfs", ne, nfs), ("V_nvs", nv, 2 * ne), ("V_nes", nv, 2 * ne), ("V_nfs", nv, nvf))):
+        off = np.zeros(n + 1, np.int64); val = np.zeros(tot, np.uint32)
+        lib().ref_surface_csr(h, C.c_int(which), _p(off), _p(val))
+        out[nm] = (off, val)
+    lib().ref_surface_free(h)
+    return out

@@ -43,6 +43,24 @@ for name, (tV, tF), n in (("torus", fp.procedural.torus(40, 24), 14), ("tori", f
     G[f"{name}_tV"] = tV; G[f"{name}_tF"] = tF; G[f"{name}_V"] = V; G[f"{name}_hex"] = H
     G[f"{name}_flag"] = flag; G[f"{name}_F_medial"] = Fm; G[f"{name}_V_medial"] = Vm
     print(name, "hexes", len(H), "inside", int(flag.sum()), "medial faces", int(Fm.sum()))
+# extract_surface_conforming_mesh + orient_surface_mesh (gf.cpp:1021-1112): a block with a cavity, and the cleaned sub-mesh of case b
+# with every third hex mirrored
+from clean_cases import block  # noqa: E402
+V, H = block(3, 3, 3); keep = np.ones(len(H), bool); keep[13] = False
+surf_cases = [("surf_cavity", V, H[keep])]
+rc = R.RefClean(G["b_V"], G["b_hex"]); rc.set_flags(G["b_dropped"]); s = rc.reindex()
+sh = s["hex"].copy(); sh[::3] = sh[::3][:, [3, 2, 1, 0, 7, 6, 5, 4]]
+surf_cases.append(("surf_carved", s["V"], sh))
+for name, V, H in surf_cases:
+    G[f"{name}_V"] = V; G[f"{name}_hex"] = H
+    for tri in (0, 1):
+        r = R.extract_surface(V, H, bool(tri))
+        for k, v in r.items():
+            if isinstance(v, tuple):
+                G[f"{name}_{tri}_{k}_off"] = v[0]; G[f"{name}_{tri}_{k}_val"] = v[1]
+            else:
+                G[f"{name}_{tri}_{k}"] = v
+    print(name, "hexes", len(H), "surface faces", len(r["F_vs"]))
 out = Path(__file__).resolve().parent / "golden_clean_v1.npz"
 np.savez_compressed(out, **G)
 print(f"wrote {out} ({out.stat().st_size / 1e3:.0f} kB, {len(G)} arrays)")

@@ -337,3 +337,14 @@ def test_golden_clean_matches_live_reference(ref):
     assert np.array_equal(rc.full(g["torus_tV"], g["torus_tF"]), g["torus_flag"])
     Fm, Vm = rc.medial()
     assert np.array_equal(Fm, g["torus_F_medial"]) and np.array_equal(Vm, g["torus_V_medial"])
+
+
+def test_port_extract_surface_vs_golden(port):
+    g = _clean_golden()
+    for name in ("surf_cavity", "surf_carved"):
+        for tri in (0, 1):
+            got = port.extract_surface_conforming_mesh(g[f"{name}_V"], g[f"{name}_hex"], bool(tri))
+            for k in ("V", "F_vs", "F_es", "E_vs", "E_boundary", "V_boundary", "V_map", "V_map_reverse", "F_map", "F_map_reverse"):
+                assert np.array_equal(np.asarray(got[k]), g[f"{name}_{tri}_{k}"]), (name, tri, k)
+            for k in ("E_nfs", "V_nvs", "V_nes", "V_nfs"):
+                assert np.array_equal(got[k][0], g[f"{name}_{tri}_{k}_off"]) and np.array_equal(got[k][1], g[f"{name}_{tri}_{k}_val"]), (name, tri, k)
