@@ -28,6 +28,7 @@
 //   clean_non_manifold_ve(mi, hmi_local, maps..., signed_dis, H_flag) ghm.cpp:2006   same name and arguments
 //   drop_small_pieces(Mesh_Domain&)                ghm.cpp:2081          drop_small_pieces(md)
 //   clean_hex_mesh(Mesh &tmi, Mesh_Domain &md)     ghm.cpp:1932          clean_hex_mesh(tmi, md)   (args.scaffold_type 1)
+//   extract_surface_conforming_mesh(meshi, mesho, V_map, V_map_reverse, F_map, F_map_reverse) gf.cpp:1021   same name and arguments
 //
 // Error behaviour mirrors the reference: bool returns and a line on std::cout/cerr, never an exception out of a call the
 // reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
@@ -310,6 +311,55 @@ void clean_hex_mesh(MeshT &tmi, DomainT &md) {
 	if (!md.mesh_subA.Hs.size()) { std::cout << "no elements inside the object, exit"; return; }
 	if ((int64_t)mi.Fs.size() == nF) for (int64_t i = 0; i < nF; ++i) if (Fm[(size_t)i]) mi.Fs[(size_t)i].on_medial_surface = true;
 	for (int64_t i = 0; i < nV; ++i) if (Vm[(size_t)i]) mi.Vs[(size_t)i].on_medial_surface = true;
+}
+
+// extract_surface_conforming_mesh(Mesh &meshi, Mesh &mesho, V_map, V_map_reverse, F_map, F_map_reverse), gf.cpp:1021-1072 (with
+// orient_surface_mesh :1073-1112 and the two build_connectivity calls).  mesho.type (Tri = 0 / Qua = 1 in Mesh_type) selects the
+// surface kind, as in the reference; meshi is a hex mesh (its connectivity is rebuilt on the device).
+template <class MeshT>
+void extract_surface_conforming_mesh(MeshT &meshi, MeshT &mesho, std::vector<int32_t> &V_map, std::vector<int32_t> &V_map_reverse,
+                                     std::vector<int32_t> &F_map, std::vector<int32_t> &F_map_reverse)
+{
+	const int64_t H = (int64_t)meshi.Hs.size(), nVh = (int64_t)meshi.Vs.size();
+	const std::vector<uint32_t> hex = hex_list(meshi);
+	fpohm_conn *c = nullptr;
+	check(fpohm_hex_connectivity(context(), hex.data(), H, nVh, &c), "fpohm_hex_connectivity");
+	int64_t nFh = 0;
+	fpohm_conn_sizes(c, &nFh, nullptr);
+	fpohm_surface *sf = nullptr;
+	const bool tri = (int)mesho.type == 0;              // Mesh_type::Tri
+	const int rc = fpohm_extract_surface(context(), c, meshi.V.data(), tri ? 1 : 0, &sf);
+	fpohm_conn_free(c);
+	check(rc, "fpohm_extract_surface");
+	int64_t nV = 0, nF = 0, nE = 0; int32_t vn = 4;
+	fpohm_surface_sizes(sf, &nV, &nF, &nE, &vn, nullptr);
+	std::vector<double> V(3 * (size_t)nV);
+	std::vector<uint32_t> F_vs((size_t)(vn * nF)), F_es((size_t)(vn * nF)), E_vs(2 * (size_t)nE);
+	std::vector<uint8_t> Eb((size_t)nE), Vb((size_t)nV);
+	V_map.assign((size_t)nVh, -1); V_map_reverse.assign((size_t)nV, 0); F_map.assign((size_t)nFh, -1); F_map_reverse.assign((size_t)nF, 0);
+	check(fpohm_surface_export(sf, V.data(), F_vs.data(), F_es.data(), E_vs.data(), Eb.data(), Vb.data(), V_map.data(), V_map_reverse.data(),
+	                           F_map.data(), F_map_reverse.data()), "fpohm_surface_export");
+	mesho.Vs.clear(); mesho.Es.clear(); mesho.Fs.clear(); mesho.Hs.clear();
+	mesho.Vs.resize((size_t)nV); mesho.Fs.resize((size_t)nF); mesho.Es.resize((size_t)nE);
+	mesho.V.resize(3, nV);
+	for (int64_t v = 0; v < nV; ++v) { mesho.Vs[(size_t)v].id = (uint32_t)v; mesho.Vs[(size_t)v].boundary = Vb[(size_t)v]; for (int d = 0; d < 3; ++d) mesho.V(d, v) = V[3 * v + d]; }
+	for (int64_t f = 0; f < nF; ++f) {
+		auto &x = mesho.Fs[(size_t)f]; x.id = (uint32_t)f;
+		x.vs.assign(F_vs.begin() + vn * f, F_vs.begin() + vn * (f + 1)); x.es.assign(F_es.begin() + vn * f, F_es.begin() + vn * (f + 1));
+	}
+	for (int64_t e = 0; e < nE; ++e) { auto &x = mesho.Es[(size_t)e]; x.id = (uint32_t)e; x.boundary = Eb[(size_t)e]; x.vs = {E_vs[2 * e], E_vs[2 * e + 1]}; }
+	auto fill = [&](int which, int64_t n, auto &&dst) {
+		int64_t tot = 0;
+		check(fpohm_surface_csr(sf, which, nullptr, nullptr, &tot), "fpohm_surface_csr");
+		std::vector<int64_t> off((size_t)n + 1); std::vector<uint32_t> val((size_t)tot);
+		check(fpohm_surface_csr(sf, which, off.data(), val.data(), &tot), "fpohm_surface_csr");
+		for (int64_t i = 0; i < n; ++i) dst(i).assign(val.begin() + off[(size_t)i], val.begin() + off[(size_t)i + 1]);
+	};
+	fill(0, nE, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Es[(size_t)i].neighbor_fs; });
+	fill(1, nV, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Vs[(size_t)i].neighbor_vs; });
+	fill(2, nV, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Vs[(size_t)i].neighbor_es; });
+	fill(3, nV, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Vs[(size_t)i].neighbor_fs; });
+	fpohm_surface_free(sf);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

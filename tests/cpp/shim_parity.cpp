@@ -252,6 +252,19 @@ int main() {
 		gm.drop_small_pieces(a);
 		fpohm_shim::drop_small_pieces(b);
 		EXPECT(a.H_flag == b.H_flag && a.H_map_reverse == b.H_map_reverse && a.mesh_subA.Es.size() == b.mesh_subA.Es.size(), "drop_small_pieces identical flags and sub-mesh");
+		// extract_surface_conforming_mesh (gf.cpp:1021-1112) of the cleaned sub-mesh, quad and triangle surfaces
+		for (int kind = 0; kind < 2; ++kind) {
+			Mesh sa, sb;
+			sa.type = sb.type = kind ? Mesh_type::Tri : Mesh_type::Qua;
+			std::vector<int32_t> vm_a, vr_a, fm_a, fr_a, vm_b, vr_b, fm_b, fr_b;
+			::extract_surface_conforming_mesh(a.mesh_subA, sa, vm_a, vr_a, fm_a, fr_a);
+			fpohm_shim::extract_surface_conforming_mesh(b.mesh_subA, sb, vm_b, vr_b, fm_b, fr_b);
+			bool ss = vm_a == vm_b && vr_a == vr_b && fm_a == fm_b && fr_a == fr_b && sa.V == sb.V && sa.Fs.size() == sb.Fs.size() && sa.Es.size() == sb.Es.size() && sa.Vs.size() == sb.Vs.size();
+			for (size_t i = 0; ss && i < sa.Fs.size(); ++i) ss = sa.Fs[i].vs == sb.Fs[i].vs && sa.Fs[i].es == sb.Fs[i].es;
+			for (size_t i = 0; ss && i < sa.Es.size(); ++i) ss = sa.Es[i].vs == sb.Es[i].vs && sa.Es[i].boundary == sb.Es[i].boundary && sa.Es[i].neighbor_fs == sb.Es[i].neighbor_fs;
+			for (size_t i = 0; ss && i < sa.Vs.size(); ++i) ss = sa.Vs[i].boundary == sb.Vs[i].boundary && sa.Vs[i].neighbor_vs == sb.Vs[i].neighbor_vs && sa.Vs[i].neighbor_es == sb.Vs[i].neighbor_es && sa.Vs[i].neighbor_fs == sb.Vs[i].neighbor_fs;
+			EXPECT(ss && sa.Fs.size() > 0, kind ? "extract_surface_conforming_mesh identical triangle surface, maps and adjacency" : "extract_surface_conforming_mesh identical quad surface, maps and adjacency");
+		}
 	}
 	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
 	return failures ? 1 : 0;
