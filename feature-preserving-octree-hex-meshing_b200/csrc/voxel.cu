@@ -214,9 +214,10 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
 
 __global__ void __launch_bounds__(256)
 pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, const int4 *__restrict__ rect, const int64_t *__restrict__ off,
-                 int64_t n_pairs, double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
+                 double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
                  int32_t *__restrict__ overflow_flag, int32_t *__restrict__ hit_ev, double oz, int nz)
 {
+	const int64_t n_pairs = off[nF];                // read on the device: no host round trip between the scan and this launch
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
 		int64_t lo = 0, hi = nF;                       // largest f with off[f] <= t
 		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
@@ -248,33 +249,17 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b) {          // bits [
 	const int len = b - a;
 	return len <= 0 ? 0u : ((len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << a);
 }
-// events of one column, SORTED by layer and carrying the running sign sum AFTER the event: (k << 8) | (sum + 128)
-__device__ __forceinline__ uint32_t chunk_mask_sorted(const int32_t *__restrict__ ev, int n, int z0, int z1) {
-	uint32_t mask = 0;
-	int s = 0, prev = z0;
-	for (int i = 0; i < n; ++i) {
-		const int32_t e = ev[i];
-		const int k = e >> 8, rs = (e & 0xff) - 128;
-		if (k > z0) {
-			if (k >= z1) break;
-			if (s < 0) mask |= bit_range(prev - z0, k - z0);
-			prev = k;
-		}
-		s = rs;
-	}
-	if (s < 0) mask |= bit_range(prev - z0, z1 - z0);
-	return mask;
-}
-
 // summary layout: word w of column col at sum[(2 * w) * ncol + col] (inside bits) and sum[(2 * w + 1) * ncol + col] (dirty bits).
-// Also rewrites the column's events in place: sorted by k0, packed with the running sum (see chunk_mask_sorted).
+// A dirty chunk's 32 layer bits are worked out here as well, once, and stored at dmask[chunk * ncol + col] (coalesced over
+// neighbouring columns): the fill then reads 4 bytes per dirty chunk instead of re-walking the column's 128-byte event list
+// (ncu: 0.24 GB of reads and a third of the fill's instructions at 1024^3 before).
 __global__ void __launch_bounds__(256)
-column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
-                      uint32_t *__restrict__ sum)
+column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
+                      uint32_t *__restrict__ sum, uint32_t *__restrict__ dmask)
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
 		const int n = min(hit_n[col], HIT_CAP);
-		int32_t *ev = hit_ev + col * HIT_CAP;
+		const int32_t *ev = hit_ev + col * HIT_CAP;
 		if (n == 0) {
 			for (int w = 0; w < 2 * n_words; ++w) sum[(int64_t)w * ncol + col] = 0u;
 			continue;
@@ -287,16 +272,28 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ h
 			e[j + 1] = v;
 		}
 		int run = 0;
-		for (int i = 0; i < n; ++i) { run += (e[i] & 3) - 1; e[i] = ((e[i] >> 2) << 8) | (run + 128); ev[i] = e[i]; }
+		for (int i = 0; i < n; ++i) { run += (e[i] & 3) - 1; e[i] = ((e[i] >> 2) << 8) | (run + 128); }   // (k << 8) | (sum after the event + 128)
 		int i = 0, s = 0;
 		for (int w = 0; w < n_words; ++w) {
 			uint32_t inside = 0, dirty = 0;
 			for (int b = 0; b < 32; ++b) {
-				const int z0 = (w * 32 + b) * FILL_Z, z1 = z0 + FILL_Z;
+				const int zc = w * 32 + b;
+				const int z0 = zc * FILL_Z, z1 = z0 + FILL_Z;
 				if (z0 >= nz) break;
 				while (i < n && (e[i] >> 8) <= z0) { s = (e[i] & 0xff) - 128; ++i; }   // state entering the chunk
 				if (s < 0) inside |= 1u << b;
-				if (i < n && (e[i] >> 8) < z1) dirty |= 1u << b;
+				if (i < n && (e[i] >> 8) < z1) {
+					dirty |= 1u << b;
+					uint32_t mask = 0;
+					int t = s, prev = z0, j = i;
+					for (; j < n && (e[j] >> 8) < z1; ++j) {
+						const int k = e[j] >> 8;
+						if (t < 0) mask |= bit_range(prev - z0, k - z0);
+						prev = k; t = (e[j] & 0xff) - 128;
+					}
+					if (t < 0) mask |= bit_range(prev - z0, z1 - z0);
+					dmask[(int64_t)zc * ncol + col] = mask;
+				}
 			}
 			sum[(int64_t)(2 * w) * ncol + col] = inside;
 			sum[(int64_t)(2 * w + 1) * ncol + col] = dirty;
@@ -306,8 +303,8 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, int32_t *__restrict__ h
 
 #define FILL_CH 4      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
 __global__ void __launch_bounds__(256)
-voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
-                  const uint32_t *__restrict__ sum, uint8_t *__restrict__ out, int zc_begin, int zc_end)
+voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, const uint32_t *__restrict__ sum, uint8_t *__restrict__ out,
+                  int zc_begin, int zc_end)
 {
 	// layers [zc_begin * 32, min(zc_end * 32, nz)) are written, the first of them at `out` (z-slab sharding)
 	const int gx = (nx + 3) / 4, gzc = zc_end, gz = (zc_end - zc_begin + FILL_CH - 1) / FILL_CH;
@@ -338,7 +335,7 @@ voxel_fill_kernel(int nx, int ny, int nz, const int32_t *__restrict__ hit_ev, co
 			uint32_t m[4];
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
-				if ((sd[c] >> bit) & 1u) m[c] = chunk_mask_sorted(hit_ev + (col0 + c) * HIT_CAP, min(hit_n[col0 + c], HIT_CAP), z0, z1);
+				if ((sd[c] >> bit) & 1u) m[c] = __ldg(dmask + (int64_t)zc * layer + col0 + c);
 				else m[c] = ((si[c] >> bit) & 1u) ? 0xffffffffu : 0u;
 			}
 			uint8_t *o = out + (int64_t)(z0 - zc_begin * FILL_Z) * layer + col0;     // index_from_index3, voxelization.cpp:26-28
@@ -441,14 +438,10 @@ void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitS
 	DevBuf<uint8_t> tmp((int64_t)tb, s);
 	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nF + 1, s));
 	ctx->launches += 1;
-	int64_t n_pairs = 0;
-	FPOHM_CUDA(cudaMemcpyAsync(&n_pairs, off.p + nF, 8, cudaMemcpyDeviceToHost, s));
-	FPOHM_CUDA(cudaStreamSynchronize(s));
-	if (n_pairs > 0) {
-		pair_hits_kernel<<<grid_for(ctx, n_pairs, 256, 8), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, n_pairs, h.z.p, h.s.p, h.n.p, h.ov.p,
-			voxel_events ? h.ev.p : nullptr, oz, nz);
-		FPOHM_LAUNCH_CHECK(ctx);
-	}
+	// the pair count stays on the device; on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
+	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, h.z.p, h.s.p, h.n.p, h.ov.p,
+		voxel_events ? h.ev.p : nullptr, oz, nz);
+	FPOHM_LAUNCH_CHECK(ctx);
 }
 
 void check_overflow(HitScratch &h, cudaStream_t s, const char *who) {
@@ -499,12 +492,12 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s, true, grid_origin[2], dims[2]);
 	const int gz = (dims[2] + FILL_Z - 1) / FILL_Z, n_words = (gz + 31) / 32;
 	const int64_t ncol = (int64_t)dims[0] * dims[1];
-	DevBuf<uint32_t> summary(2 * n_words * ncol, s);
-	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p);
+	DevBuf<uint32_t> summary(2 * n_words * ncol, s), dmask((int64_t)gz * ncol, s);      // dmask is only written / read where a chunk is dirty
+	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
 	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + FILL_CH - 1) / FILL_CH);
-	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], z_end, h.ev.p, h.n.p, summary.p, out_dev, zc0, zc1);
+	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1);
 	FPOHM_LAUNCH_CHECK(ctx);
 	check_overflow(h, s, "fpohm_voxel_sign");
 	FPOHM_API_END
