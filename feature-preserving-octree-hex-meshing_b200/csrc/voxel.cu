@@ -16,6 +16,7 @@
 #include "mesh.h"
 #include "octree.h"
 
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 using namespace fpohm;
@@ -301,7 +302,8 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 	}
 }
 
-#define FILL_CH 4      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
+#define FILL_CH_DEFAULT 4      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
+template <int FILL_CH>
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, const uint32_t *__restrict__ sum, uint8_t *__restrict__ out,
                   int zc_begin, int zc_end)
@@ -340,7 +342,11 @@ voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, co
 			}
 			uint8_t *o = out + (int64_t)(z0 - zc_begin * FILL_Z) * layer + col0;     // index_from_index3, voxelization.cpp:26-28
 			const uint32_t any = m[0] | m[1] | m[2] | m[3], all = m[0] & m[1] & m[2] & m[3];
-			if (aligned && (any == 0u || all == 0xffffffffu)) {            // uniform tile: store only
+			// the whole warp takes ONE store path: lanes split between the two loops would turn every 128-byte row into two
+			// partial-line stores (ncu: 3.37 of 4 sectors per store request, 22 of 32 lanes active)
+			const bool tile_uniform = any == 0u || all == 0xffffffffu;
+			const bool warp_uniform = __ballot_sync(__activemask(), !tile_uniform) == 0u;
+			if (aligned && warp_uniform) {                                 // uniform tiles: store only
 				const uint32_t w = any ? 0x01010101u : 0u;
 				for (int z = z0; z < z1; ++z, o += layer) __stcs(reinterpret_cast<uint32_t *>(o), w);
 			} else if (aligned) {
@@ -496,8 +502,16 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
-	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + FILL_CH - 1) / FILL_CH);
-	voxel_fill_kernel<<<grid_for(ctx, nthreads, 256, 16), 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1);
+	static const int fill_ch = getenv("FPOHM_FILL_CH") ? atoi(getenv("FPOHM_FILL_CH")) : FILL_CH_DEFAULT;
+	static const int fill_ctas = getenv("FPOHM_FILL_CTAS") ? atoi(getenv("FPOHM_FILL_CTAS")) : 32;
+	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + fill_ch - 1) / fill_ch);
+	const int fgrid = grid_for(ctx, nthreads, 256, fill_ctas);
+	switch (fill_ch) {
+	case 1: voxel_fill_kernel<1><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
+	case 2: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
+	case 8: voxel_fill_kernel<8><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
+	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
+	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	check_overflow(h, s, "fpohm_voxel_sign");
 	FPOHM_API_END
