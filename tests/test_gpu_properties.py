@@ -190,3 +190,54 @@ def test_ray_hit_capacity_is_reported_not_truncated(fp, ctx):
         fp.compute_sign_voxels(ctx, m, g)
     assert e.value.code == -5
     m.close()
+
+
+def test_full_size_clean_hex_mesh_properties(fp, ctx, gear):
+    """clean_hex_mesh at a size the reference needs minutes for (1.5 M-hex lattice around the 200 k-facet gear), through
+    properties that do not need it: every stage is idempotent on its own output, the result is one face-connected piece whose
+    boundary is a closed, consistently oriented 2-manifold (every surface edge has exactly two faces running opposite ways),
+    the maps are inverse to each other and the medial flags are exactly the boundary of the kept set."""
+    V, F, _ = gear
+    m = fp.TriMesh(ctx, V, F)
+    Vl, Hl = fp.procedural.hex_lattice_around(V, 192)
+    nV = len(Vl)
+    assert len(Hl) > 1_500_000
+    conn = fp.HexConnectivity(ctx, Hl, nV, keep=True)
+    out = fp.clean_hex_mesh(ctx, m, Vl, Hl, conn)
+    flag = out["H_flag"]
+    assert out["stats"][4] == int(flag.sum()) > 500_000
+    assert np.array_equal(flag <= (out["signed_dis"] < 0), np.ones(len(flag), bool)) or out["stats"][1] >= 1      # only tagging may add hexes
+    # idempotence of every stage on the final flags
+    t, _ = fp.tag_uneven_elements(ctx, conn, flag)
+    n, rounds = fp.clean_non_manifold(ctx, out["hex"], nV, flag)
+    d, pieces = fp.drop_small_pieces(ctx, out["hex"], nV, flag)
+    assert np.array_equal(n, flag) and rounds == 0 and np.array_equal(d, flag) and pieces == 1
+    assert np.array_equal(t, flag) or int((t != flag).sum()) < 10          # tagging ran BEFORE the other stages in the pipeline
+    # maps
+    s = fp.reindex_submesh(ctx, out["hex"], nV, flag)
+    vr, vm, hr = s["V_map_reverse"], s["V_map"], s["H_map_reverse"]
+    assert np.array_equal(vm[vr], np.arange(len(vr))) and (np.diff(vr) > 0).all() and np.array_equal(hr, np.nonzero(flag)[0])
+    assert np.array_equal(vr[s["hex"].astype(np.int64)], out["hex"][hr].astype(np.int64))
+    # medial flags == faces between kept and dropped hexes
+    off, val = conn.F_nhs
+    two = np.diff(off) == 2
+    a = flag[val[off[:-1]]]; b = np.where(two, flag[val[np.minimum(off[:-1] + 1, len(val) - 1)]], 0)
+    assert np.array_equal(out["F_medial"], (a != b).astype(np.uint8))
+    conn.close()
+    # the boundary surface of the kept hexes
+    Vs = Vl[vr]
+    sc = fp.HexConnectivity(ctx, s["hex"], len(Vs), keep=True)
+    q = fp.extract_surface(ctx, sc, Vs, False)
+    sc.close(); m.close()
+    assert int(out["F_medial"].sum()) == len(q["F_vs"])
+    eoff, _ = q["E_nfs"]
+    assert (np.diff(eoff) == 2).all() and not q["E_boundary"].any()       # closed 2-manifold
+    Fv = q["F_vs"].astype(np.int64)
+    d0 = Fv.reshape(-1); d1 = np.roll(Fv, -1, 1).reshape(-1)
+    fwd = np.bincount(q["F_es"].reshape(-1)[d0 < d1], minlength=len(q["E_vs"]))
+    assert (fwd == 1).all()                                                   # each edge once in each direction: consistent orientation
+    # outward orientation: signed volume of the quad surface is positive
+    P = q["V"]; c = P[Fv].mean(1)
+    vol = sum(np.einsum("ij,ij->i", np.cross(P[Fv[:, k]], P[Fv[:, (k + 1) % 4]]), c).sum() for k in range(4)) / 6
+    kept_vol = float(flag.sum()) * float(np.prod(Vl[Hl[0, 6]] - Vl[Hl[0, 0]]))
+    assert abs(vol - kept_vol) < 1e-9 * kept_vol          # orient_surface_mesh leaves res <= 0, i.e. a positive enclosed volume
