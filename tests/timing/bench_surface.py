@@ -3,7 +3,7 @@
 import json, sys, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import fpohm_b200 as fp
 ctx = fp.Context(0)
