@@ -328,6 +328,13 @@ def main():
             v3_ms = a3.elapsed_time(b3) / 5
             v3_bytes = g3.num_voxels() + 72 * len(F3)
             del d3
+            occ_ms = None
+            try:    # dense predicate occupancy of the same grid (host output buffer: only the library's CUDA-event kernel time is reported)
+                for _ in range(2):
+                    fp.voxel_occupancy(ctx, mesh3, g3)
+                occ_ms = ctx.last_kernel_ms()
+            except Exception:
+                pass
             p3 = fp.octree_grid_setup(V3, 1 << 20); p3.c.stop_extent = 1 << 10
             ts3 = []
             for _ in range(8):        # the stream-ordered allocator's pool needs a few builds of this size before it stops growing
@@ -337,6 +344,8 @@ def main():
             c3 = {"tris": int(len(F3)), "voxel_sign_1024_ms": v3_ms, "voxel_sign_dims": g3.dims.tolist(),
                   "voxel_sign_roofline": {"bound": "hbm", "achieved": v3_bytes / (v3_ms * 1e-3) / 1e9, "peak": pk3, "unit": "GB/s",
                                           "frac": v3_bytes / (v3_ms * 1e-3) / 1e9 / pk3},
+                  "voxel_occupancy_1024_kernel_ms": occ_ms,
+                  "voxel_occupancy_roofline_frac": (v3_bytes / (occ_ms * 1e-3) / 1e9 / pk3) if occ_ms else None,
                   "octree_e10_build_ms": float(min(ts3[1:])), "octree_e10_build_ms_all": [round(t, 1) for t in ts3], "octree_e10_cells": int(sz3["cells"]), "octree_e10_leaves": int(sz3["leaves"])}
             mesh3.close(); del V3, F3
     except Exception as e:
