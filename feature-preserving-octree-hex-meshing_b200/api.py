@@ -16,6 +16,7 @@ __all__ = [
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
     "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh", "extract_surface",
+    "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -490,6 +491,43 @@ def extract_surface(ctx: Context, conn: "HexConnectivity", V, as_triangles: bool
         return out
     finally:
         lib().fpohm_surface_free(h)
+
+
+# ---- SLIM per-element stages, tet branch (slim_m.cpp:84-381, 861-913) ------------------------------------------
+SLIM_ENERGIES = {"ARAP": 0, "LOG_ARAP": 1, "SYMMETRIC_DIRICHLET": 2, "CONFORMAL": 3, "EXP_CONFORMAL": 4, "EXP_SYMMETRIC_DIRICHLET": 5}
+
+
+def slim_jacobians(ctx: Context, off, col, vx, vy, vz, uv):
+    """compute_jacobians (slim_m.cpp:84-106): Dx, Dy, Dz as one CSR pattern with three value arrays; uv is nv x 3.  Returns Ji (n x 9)."""
+    off = np.ascontiguousarray(off, np.int64); col = _i32(col); uv = _f64(uv); n = len(off) - 1
+    Ji = np.zeros((n, 9))
+    _chk(lib().fpohm_slim_jacobians(ctx.h, C.c_int64(n), C.c_int64(len(uv)), _p(off), _p(col), _p(_f64(vx)), _p(_f64(vy)), _p(_f64(vz)), _p(uv), _p(Ji)))
+    return Ji
+
+
+def slim_weights_rotations(ctx: Context, Ji, energy: str, exp_factor: float = 1.0):
+    """update_weights_and_closest_rotations (slim_m.cpp:229-381): (W n x 9 = W_11..W_33, Ri n x 9 as s.Ri)."""
+    Ji = _f64(Ji).reshape(-1, 9); n = len(Ji)
+    W = np.zeros((n, 9)); Ri = np.zeros((n, 9))
+    _chk(lib().fpohm_slim_weights_rotations(ctx.h, _p(Ji), C.c_int64(n), C.c_int32(SLIM_ENERGIES[energy]), C.c_double(exp_factor), _p(W), _p(Ri)))
+    return W, Ri
+
+
+def slim_energy(ctx: Context, Ji, areas, energy: str, exp_factor: float = 1.0) -> float:
+    """compute_energy_with_jacobians (slim_m.cpp:861-913)."""
+    Ji = _f64(Ji).reshape(-1, 9); a = _f64(areas); e = C.c_double()
+    _chk(lib().fpohm_slim_energy(ctx.h, _p(Ji), C.c_int64(len(Ji)), _p(a), C.c_int32(SLIM_ENERGIES[energy]), C.c_double(exp_factor), C.byref(e)))
+    return e.value
+
+
+def slim_weights_rotations_dev(ctx: Context, Ji_ptr: int, n: int, energy: str, exp_factor: float, W_ptr: int, Ri_ptr: int, stream: int = 0):
+    _chk(lib().fpohm_slim_weights_rotations_dev(ctx.h, C.c_void_p(Ji_ptr), C.c_int64(n), C.c_int32(SLIM_ENERGIES[energy]), C.c_double(exp_factor),
+                                                C.c_void_p(W_ptr), C.c_void_p(Ri_ptr), C.c_void_p(stream)))
+
+
+def slim_energy_dev(ctx: Context, Ji_ptr: int, n: int, areas_ptr: int, energy: str, exp_factor: float, out_ptr: int, stream: int = 0):
+    _chk(lib().fpohm_slim_energy_dev(ctx.h, C.c_void_p(Ji_ptr), C.c_int64(n), C.c_void_p(areas_ptr), C.c_int32(SLIM_ENERGIES[energy]), C.c_double(exp_factor),
+                                     C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def _hybrid_to_dict(hy):

@@ -285,6 +285,27 @@ int  fpohm_surface_export(const fpohm_surface *s, double *V, uint32_t *F_vs, uin
 int  fpohm_surface_csr(const fpohm_surface *s, int32_t which, int64_t *off, uint32_t *val, int64_t *total);
 void fpohm_surface_free(fpohm_surface *s);
 
+/* ---- SLIM per-element stages, tet branch (slim_m.cpp).  Jacobians travel as the reference's s.Ji: n x 9
+ * row-major, entry 3r + c = ji(r, c).  energy = SLIM_ENERGY (global_types.h:56-64: 0 ARAP, 1 LOG_ARAP, 2 SYMMETRIC_DIRICHLET,
+ * 3 CONFORMAL, 4 EXP_CONFORMAL, 5 EXP_SYMMETRIC_DIRICHLET), exp_factor = s.exp_factor.  Floating point: 1e-5 relative.
+ *   fpohm_slim_jacobians          compute_jacobians (:84-106): Dx, Dy, Dz as ONE CSR pattern (off n+1, col nnz) with three value
+ *                                 arrays, uv = nv x 3 row-major; Ji = [Dx u, Dy u, Dz u, Dx v, Dy v, Dz v, Dx w, Dy w, Dz w].
+ *   fpohm_slim_weights_rotations  update_weights_and_closest_rotations (:229-381) after its compute_jacobians call: W n x 9
+ *                                 = (W_11, W_12, W_13, W_21, ... W_33), Ri n x 9 as s.Ri (ri stored column by column).
+ *   fpohm_slim_energy             compute_energy_with_jacobians (:861-913): sum_i areas[i] * f(singular values of ji).
+ * The _dev forms take device pointers and a cudaStream_t and do not synchronise (the optimisation loop keeps uv, Ji, W, Ri
+ * resident between the solve and the line search). */
+int  fpohm_slim_jacobians(fpohm_ctx *ctx, int64_t n, int64_t nv, const int64_t *off, const int32_t *col, const double *vx,
+                          const double *vy, const double *vz, const double *uv, double *Ji);
+int  fpohm_slim_weights_rotations(fpohm_ctx *ctx, const double *Ji, int64_t n, int32_t energy, double exp_factor, double *W, double *Ri);
+int  fpohm_slim_energy(fpohm_ctx *ctx, const double *Ji, int64_t n, const double *areas, int32_t energy, double exp_factor, double *energy_out);
+int  fpohm_slim_jacobians_dev(fpohm_ctx *ctx, int64_t n, const int64_t *off_dev, const int32_t *col_dev, const double *vx_dev,
+                              const double *vy_dev, const double *vz_dev, const double *uv_dev, double *Ji_dev, void *stream);
+int  fpohm_slim_weights_rotations_dev(fpohm_ctx *ctx, const double *Ji_dev, int64_t n, int32_t energy, double exp_factor, double *W_dev,
+                                      double *Ri_dev, void *stream);
+int  fpohm_slim_energy_dev(fpohm_ctx *ctx, const double *Ji_dev, int64_t n, const double *areas_dev, int32_t energy, double exp_factor,
+                           double *energy_dev, void *stream);
+
 /* ---- conforming_mesh (grid_meshing/grid_hex_meshing.cpp:568-696): the octree hex mesh with every big
  * face at a T-junction replaced by the 4 small faces of the other side and the mid vertices inserted into the loops of
  * the faces around it, as a polyhedral ("Hyb") mesh with the connectivity build_connectivity gives it (gf.cpp:187-264):

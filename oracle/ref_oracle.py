@@ -386,3 +386,30 @@ def extract_surface(Vpos, hexa, as_triangles=False):
         out[nm] = (off, val)
     lib().ref_surface_free(h)
     return out
+
+
+# ---- §8(f)-3: SLIM per-element stages (slim_m.cpp:84-381, 792-916), tet branch ------------------------------------------------
+SLIM_ENERGIES = {"ARAP": 0, "LOG_ARAP": 1, "SYMMETRIC_DIRICHLET": 2, "CONFORMAL": 3, "EXP_CONFORMAL": 4, "EXP_SYMMETRIC_DIRICHLET": 5}
+
+
+def slim_jacobians(off, col, vx, vy, vz, uv, nv):
+    """compute_jacobians (slim_m.cpp:84-106): Dx, Dy, Dz share one CSR pattern (n rows, nv columns); uv is nv x 3."""
+    off = np.ascontiguousarray(off, np.int64); col = _i32(col); uv = _f64(uv); n = len(off) - 1
+    Ji = np.zeros((n, 9))
+    lib().ref_slim_jacobians(C.c_int64(n), C.c_int64(nv), _p(off), _p(col), _p(_f64(vx)), _p(_f64(vy)), _p(_f64(vz)), _p(uv), _p(Ji))
+    return Ji
+
+
+def slim_weights_rotations(J, energy, exp_factor=1.0):
+    """update_weights_and_closest_rotations (slim_m.cpp:108-381, tet branch) on given Jacobians (n x 9, rows as s.Ji): (W, Ri)."""
+    J = _f64(J).reshape(-1, 9); n = len(J)
+    W = np.zeros((n, 9)); Ri = np.zeros((n, 9))
+    lib().ref_slim_weights_rotations(_p(J), C.c_int64(n), C.c_int(SLIM_ENERGIES[energy]), C.c_double(exp_factor), _p(W), _p(Ri))
+    return W, Ri
+
+
+def slim_energy(J, areas, energy, exp_factor=1.0):
+    """compute_energy_with_jacobians (slim_m.cpp:792-916, tet branch)."""
+    J = _f64(J).reshape(-1, 9); a = _f64(areas)
+    lib().ref_slim_energy.restype = C.c_double
+    return float(lib().ref_slim_energy(_p(J), C.c_int64(len(J)), _p(a), C.c_int(SLIM_ENERGIES[energy]), C.c_double(exp_factor)))

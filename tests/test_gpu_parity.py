@@ -774,3 +774,63 @@ def test_extract_surface_vs_reference(fp, ctx, ref):
     with pytest.raises(fp.FpohmError):
         fp.extract_surface(ctx, conn, V, False)
     conn.close()
+
+
+# ---- §8(f)-3: SLIM per-element stages (slim_m.cpp), against the compiled reference functions; tolerance of the north star 1e-5 ----
+def _slim_jacobian_set(n, seed):
+    rng = np.random.default_rng(seed)
+    J = np.eye(3)[None] + rng.normal(0, 0.35, (n, 3, 3))
+    J[::7] = J[::7] @ np.diag([1, 1, -1.0])                      # inverted elements: reflection branch of polar_svd
+    J[1] = np.eye(3); J[2] = np.diag([2.0, 1.0, 0.5]); J[3] = np.diag([1.0 + 5e-9, 1.0, 1.0 - 5e-9])     # |s - 1| < eps branch
+    Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    J[4] = Q @ np.diag([3.0, 3.0, 0.2]) @ Q.T                      # repeated singular value
+    J[5] = 1e-3 * J[5]; J[6] = 1e3 * J[6]                          # scale extremes
+    return J.reshape(n, 9)
+
+
+def test_slim_weights_rotations_and_energy_vs_reference(fp, ctx, ref):
+    J = _slim_jacobian_set(20000, 11)
+    areas = np.random.default_rng(12).uniform(0.5, 2.0, len(J))
+    for en in fp.SLIM_ENERGIES:
+        W, Ri = fp.slim_weights_rotations(ctx, J, en, 0.7)
+        rW, rRi = ref.slim_weights_rotations(J, en, 0.7)
+        fin = np.isfinite(rW).all(1) & np.isfinite(rRi).all(1)
+        assert np.array_equal(fin, np.isfinite(W).all(1) & np.isfinite(Ri).all(1)), en      # overflow / 0-over-0 rows coincide
+        scale_w = np.abs(rW[fin]).max(1, keepdims=True); scale_r = np.abs(rRi[fin]).max(1, keepdims=True)
+        assert (np.abs(W[fin] - rW[fin]) <= 1e-9 * scale_w).all(), (en, float((np.abs(W[fin] - rW[fin]) / scale_w).max()))
+        assert (np.abs(Ri[fin] - rRi[fin]) <= 1e-9 * scale_r).all(), (en, float((np.abs(Ri[fin] - rRi[fin]) / scale_r).max()))
+        sub = fin & (np.abs(J).max(1) < 50)           # the energy sum of the whole set overflows for the exponential energies
+        e = fp.slim_energy(ctx, J[sub], areas[sub], en, 0.7); re_ = ref.slim_energy(J[sub], areas[sub], en, 0.7)
+        assert (np.isfinite(re_) and abs(e - re_) <= 1e-10 * abs(re_)) or (not np.isfinite(re_) and not np.isfinite(e)), (en, e, re_)
+    # rotations really are rotations / W really is symmetric (size-independent properties)
+    W, Ri = fp.slim_weights_rotations(ctx, J, "SYMMETRIC_DIRICHLET")
+    R = Ri.reshape(-1, 3, 3)
+    ok = np.isfinite(R).all((1, 2))
+    assert np.abs(R[ok] @ np.swapaxes(R[ok], 1, 2) - np.eye(3)).max() < 1e-12 and (np.linalg.det(R[ok]) > 0).all()
+    Wm = W.reshape(-1, 3, 3); okw = np.isfinite(Wm).all((1, 2))
+    assert np.abs(Wm[okw] - np.swapaxes(Wm[okw], 1, 2)).max() <= 1e-12 * np.abs(Wm[okw]).max()
+    import ctypes as C
+    out = np.zeros(9)
+    rc = fp.lib().fpohm_slim_weights_rotations(ctx.h, J.ctypes.data_as(C.c_void_p), C.c_int64(1), C.c_int32(9), C.c_double(1.0),
+                                               out.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc != 0                                   # unknown SLIM_ENERGY is refused, not guessed
+
+
+def test_slim_jacobians_vs_reference(fp, ctx, ref):
+    """compute_jacobians on the gradient operator of a tet mesh: 4 non-zeros per row, Dx/Dy/Dz sharing the pattern (igl::grad)."""
+    rng = np.random.default_rng(21)
+    V, H = fp.procedural.warped_hex_block(12, 0.3)
+    tets = H[:, [[0, 1, 3, 4], [1, 2, 0, 5], [2, 3, 1, 6], [3, 0, 2, 7], [4, 7, 5, 0], [5, 4, 6, 1], [6, 5, 7, 2], [7, 6, 4, 3]]].reshape(-1, 4).astype(np.int64)
+    P = V[tets]                                                   # per tet: gradient of the 4 hat functions = rows of inv([p1-p0, p2-p0, p3-p0])
+    E = np.stack([P[:, 1] - P[:, 0], P[:, 2] - P[:, 0], P[:, 3] - P[:, 0]], 1)
+    G = np.linalg.inv(E)                                          # G[:, :, k] = gradient of hat function k+1
+    g = np.concatenate([-G.sum(2, keepdims=True), G], 2)          # 3 x 4 per tet
+    off = np.arange(0, 4 * len(tets) + 1, 4); col = tets.reshape(-1).astype(np.int32)
+    vx, vy, vz = g[:, 0].reshape(-1), g[:, 1].reshape(-1), g[:, 2].reshape(-1)
+    uv = V + rng.normal(0, 0.01, V.shape)
+    Ji = fp.slim_jacobians(ctx, off, col, vx, vy, vz, uv)
+    rJ = ref.slim_jacobians(off, col, vx, vy, vz, uv, len(V))
+    assert np.abs(Ji - rJ).max() <= 1e-12 * np.abs(rJ).max()
+    # the deformation gradient of the identity map is the identity
+    I = fp.slim_jacobians(ctx, off, col, vx, vy, vz, V)
+    assert np.abs(I - np.eye(3).reshape(9)).max() < 1e-9
