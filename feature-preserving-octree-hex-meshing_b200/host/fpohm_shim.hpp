@@ -29,6 +29,9 @@
 //   drop_small_pieces(Mesh_Domain&)                ghm.cpp:2081          drop_small_pieces(md)
 //   clean_hex_mesh(Mesh &tmi, Mesh_Domain &md)     ghm.cpp:1932          clean_hex_mesh(tmi, md)   (args.scaffold_type 1)
 //   extract_surface_conforming_mesh(meshi, mesho, V_map, V_map_reverse, F_map, F_map_reverse) gf.cpp:1021   same name and arguments
+//   compute_jacobians(SLIMData&, uv)               slim_m.cpp:84         compute_jacobians(s, uv)               (tet branch)
+//   update_weights_and_closest_rotations(s, V, F, uv) slim_m.cpp:108     update_weights_and_closest_rotations(s, V, F, uv)
+//   compute_energy_with_jacobians(s, V, F, Ji, uv, areas) slim_m.cpp:792 compute_energy_with_jacobians(s, V, F, Ji, uv, areas)
 //
 // Error behaviour mirrors the reference: bool returns and a line on std::cout/cerr, never an exception out of a call the
 // reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
@@ -360,6 +363,56 @@ void extract_surface_conforming_mesh(MeshT &meshi, MeshT &mesho, std::vector<int
 	fill(2, nV, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Vs[(size_t)i].neighbor_es; });
 	fill(3, nV, [&](int64_t i) -> std::vector<uint32_t> & { return mesho.Vs[(size_t)i].neighbor_fs; });
 	fpohm_surface_free(sf);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SLIM per-element stages, tet branch (slim_m.cpp).  SLIMDataT is the reference's SLIMData: the members the
+// reference functions touch (Dx, Dy, Dz, Ji, Ri, W_11..W_33, slim_energy, exp_factor, dim, f_n) are used the same way.
+// compute_jacobians(SLIMData &s, const MatrixXd &uv), slim_m.cpp:84-106.  Dx, Dy, Dz share igl::grad's pattern (4 entries per tet).
+template <class SLIMDataT, class MatT>
+void compute_jacobians(SLIMDataT &s, const MatT &uv) {
+	if (s.F.cols() == 3) throw std::runtime_error("fpohm_shim::compute_jacobians: only the tet branch is on the hot path");
+	const int64_t n = (int64_t)s.Dx.rows(), nv = (int64_t)s.Dx.cols();
+	// row-major CSR of the three operators from Eigen's column-major storage, entries of a row in ascending column
+	std::vector<int64_t> off((size_t)n + 1, 0);
+	for (int k = 0; k < s.Dx.outerSize(); ++k) for (typename decltype(s.Dx)::InnerIterator it(s.Dx, k); it; ++it) ++off[(size_t)it.row() + 1];
+	for (int64_t i = 0; i < n; ++i) off[(size_t)i + 1] += off[(size_t)i];
+	std::vector<int32_t> col((size_t)off[(size_t)n]);
+	std::vector<double> vx(col.size()), vy(col.size()), vz(col.size());
+	std::vector<int64_t> fill(off.begin(), off.end() - 1);
+	for (int k = 0; k < s.Dx.outerSize(); ++k) for (typename decltype(s.Dx)::InnerIterator it(s.Dx, k); it; ++it) {
+		const int64_t q = fill[(size_t)it.row()]++;
+		col[(size_t)q] = (int32_t)it.col(); vx[(size_t)q] = it.value(); vy[(size_t)q] = s.Dy.coeff(it.row(), it.col()); vz[(size_t)q] = s.Dz.coeff(it.row(), it.col());
+	}
+	std::vector<double> u(3 * (size_t)nv), J(9 * (size_t)n);
+	for (int64_t i = 0; i < nv; ++i) for (int c = 0; c < 3; ++c) u[3 * i + c] = uv(i, c);
+	check(fpohm_slim_jacobians(context(), n, nv, off.data(), col.data(), vx.data(), vy.data(), vz.data(), u.data(), J.data()), "fpohm_slim_jacobians");
+	for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) s.Ji(i, k) = J[9 * i + k];
+}
+// update_weights_and_closest_rotations(SLIMData &s, const MatrixXd &V, const MatrixXi &F, MatrixXd &uv), slim_m.cpp:108-381
+template <class SLIMDataT, class MatV, class MatF, class MatT>
+void update_weights_and_closest_rotations(SLIMDataT &s, const MatV &, const MatF &, MatT &uv) {
+	compute_jacobians(s, uv);
+	const int64_t n = (int64_t)s.Ji.rows();
+	std::vector<double> J(9 * (size_t)n), W(9 * (size_t)n), R(9 * (size_t)n);
+	for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) J[9 * i + k] = s.Ji(i, k);
+	check(fpohm_slim_weights_rotations(context(), J.data(), n, (int32_t)s.slim_energy, s.exp_factor, W.data(), R.data()), "fpohm_slim_weights_rotations");
+	for (int64_t i = 0; i < n; ++i) {
+		s.W_11(i) = W[9 * i]; s.W_12(i) = W[9 * i + 1]; s.W_13(i) = W[9 * i + 2]; s.W_21(i) = W[9 * i + 3]; s.W_22(i) = W[9 * i + 4];
+		s.W_23(i) = W[9 * i + 5]; s.W_31(i) = W[9 * i + 6]; s.W_32(i) = W[9 * i + 7]; s.W_33(i) = W[9 * i + 8];
+		for (int k = 0; k < 9; ++k) s.Ri(i, k) = R[9 * i + k];
+	}
+}
+// compute_energy_with_jacobians(SLIMData &s, V, F, const MatrixXd &Ji, MatrixXd &uv, VectorXd &areas), slim_m.cpp:792-916
+template <class SLIMDataT, class MatV, class MatF, class MatJ, class MatT, class VecA>
+double compute_energy_with_jacobians(SLIMDataT &s, const MatV &, const MatF &, const MatJ &Ji, MatT &, VecA &areas) {
+	if (s.dim != 3) throw std::runtime_error("fpohm_shim::compute_energy_with_jacobians: only the tet branch is on the hot path");
+	const int64_t n = (int64_t)s.f_n;
+	std::vector<double> J(9 * (size_t)n), a((size_t)n);
+	for (int64_t i = 0; i < n; ++i) { for (int k = 0; k < 9; ++k) J[9 * i + k] = Ji(i, k); a[(size_t)i] = areas(i); }
+	double e = 0;
+	check(fpohm_slim_energy(context(), J.data(), n, a.data(), (int32_t)s.slim_energy, s.exp_factor, &e), "fpohm_slim_energy");
+	return e;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "global_functions.h"
 #include "metro_hausdorff.h"
 #include "grid_meshing/grid_hex_meshing.h"
+#include "slim_m.h"
 #include <igl/signed_distance.h>
 #include <geogram/basic/common.h>
 #include <geogram/basic/logger.h>
@@ -18,6 +19,11 @@
 
 #include <cmath>
 #include <cstdio>
+
+// the reference's SLIM per-element functions (slim_m.cpp, external linkage, not declared in slim_m.h)
+void compute_jacobians(SLIMData &s, const Eigen::MatrixXd &uv);
+void update_weights_and_closest_rotations(SLIMData &s, const Eigen::MatrixXd &V, const Eigen::MatrixXi &F, Eigen::MatrixXd &uv);
+double compute_energy_with_jacobians(SLIMData &s, const Eigen::MatrixXd &V, const Eigen::MatrixXi &F, const Eigen::MatrixXd &Ji, Eigen::MatrixXd &uv, Eigen::VectorXd &areas);
 
 static int failures = 0;
 #define EXPECT(cond, what) do { if (cond) std::printf("PASS %s\n", what); else { std::printf("FAIL %s\n", what); ++failures; } } while (0)
@@ -265,6 +271,62 @@ int main() {
 			for (size_t i = 0; ss && i < sa.Vs.size(); ++i) ss = sa.Vs[i].boundary == sb.Vs[i].boundary && sa.Vs[i].neighbor_vs == sb.Vs[i].neighbor_vs && sa.Vs[i].neighbor_es == sb.Vs[i].neighbor_es && sa.Vs[i].neighbor_fs == sb.Vs[i].neighbor_fs;
 			EXPECT(ss && sa.Fs.size() > 0, kind ? "extract_surface_conforming_mesh identical triangle surface, maps and adjacency" : "extract_surface_conforming_mesh identical quad surface, maps and adjacency");
 		}
+	}
+	// ---- SLIM per-element stages (slim_m.cpp:84-381, 792-916) on the 8-tets-per-hex split of a warped block: gradient operators
+	// with 4 entries per tet, deformed positions uv, every energy
+	{
+		Mesh hb; hex_block(6, 0.8, hb);
+		static const int T[8][4] = {{0, 1, 3, 4}, {1, 2, 0, 5}, {2, 3, 1, 6}, {3, 0, 2, 7}, {4, 7, 5, 0}, {5, 4, 6, 1}, {6, 5, 7, 2}, {7, 6, 4, 3}};
+		const int nt = 8 * (int)hb.Hs.size(), nv = (int)hb.V.cols();
+		auto fill = [&](SLIMData &s) {
+			s.dim = 3; s.f_n = s.f_num = nt; s.v_num = nv;
+			s.F.resize(nt, 4); s.Ji.resize(nt, 9); s.Ri.resize(nt, 9);
+			for (Eigen::VectorXd *w : {&s.W_11, &s.W_12, &s.W_13, &s.W_21, &s.W_22, &s.W_23, &s.W_31, &s.W_32, &s.W_33}) w->resize(nt);
+			std::vector<Eigen::Triplet<double>> tx, ty, tz;
+			for (size_t h = 0; h < hb.Hs.size(); ++h) for (int k = 0; k < 8; ++k) {
+				const int t = 8 * (int)h + k;
+				int v[4]; for (int j = 0; j < 4; ++j) { v[j] = (int)hb.Hs[h].vs[T[k][j]]; s.F(t, j) = v[j]; }
+				Eigen::Matrix3d E; for (int j = 0; j < 3; ++j) E.row(j) = (hb.V.col(v[j + 1]) - hb.V.col(v[0])).transpose();
+				const Eigen::Matrix3d G = E.inverse();                          // column j = gradient of hat function j+1
+				const Eigen::Vector3d g0 = -(G.col(0) + G.col(1) + G.col(2));
+				for (int j = 0; j < 4; ++j) {
+					const Eigen::Vector3d g = j == 0 ? g0 : Eigen::Vector3d(G.col(j - 1));
+					tx.emplace_back(t, v[j], g[0]); ty.emplace_back(t, v[j], g[1]); tz.emplace_back(t, v[j], g[2]);
+				}
+			}
+			s.Dx.resize(nt, nv); s.Dy.resize(nt, nv); s.Dz.resize(nt, nv);
+			s.Dx.setFromTriplets(tx.begin(), tx.end()); s.Dy.setFromTriplets(ty.begin(), ty.end()); s.Dz.setFromTriplets(tz.begin(), tz.end());
+			s.Dx.makeCompressed(); s.Dy.makeCompressed(); s.Dz.makeCompressed();
+		};
+		Eigen::MatrixXd uv(nv, 3);
+		for (int i = 0; i < nv; ++i) for (int c = 0; c < 3; ++c) uv(i, c) = hb.V(c, i) * (1.0 + 0.2 * c) + 0.03 * std::sin(11.0 * i + c);
+		Eigen::VectorXd areas(nt); for (int i = 0; i < nt; ++i) areas(i) = 0.5 + 0.001 * (i % 97);
+		Eigen::MatrixXd Vd; Eigen::MatrixXi Fd;
+		bool ok = true; double worst = 0;
+		for (int en = 0; en < 6 && ok; ++en) {
+			SLIMData a, b; fill(a); fill(b);
+			a.slim_energy = b.slim_energy = (SLIM_ENERGY)en; a.exp_factor = b.exp_factor = 0.5;
+			Eigen::MatrixXd ua = uv, ub = uv;
+			::update_weights_and_closest_rotations(a, Vd, Fd, ua);
+			fpohm_shim::update_weights_and_closest_rotations(b, Vd, Fd, ub);
+			const Eigen::VectorXd *wa[9] = {&a.W_11, &a.W_12, &a.W_13, &a.W_21, &a.W_22, &a.W_23, &a.W_31, &a.W_32, &a.W_33};
+			const Eigen::VectorXd *wb[9] = {&b.W_11, &b.W_12, &b.W_13, &b.W_21, &b.W_22, &b.W_23, &b.W_31, &b.W_32, &b.W_33};
+			for (int i = 0; i < nt && ok; ++i) {
+				double sw = 0, sr = 0, sj = 0;
+				for (int k = 0; k < 9; ++k) { sw = std::max(sw, std::abs((*wa[k])(i))); sr = std::max(sr, std::abs(a.Ri(i, k))); sj = std::max(sj, std::abs(a.Ji(i, k))); }
+				for (int k = 0; k < 9 && ok; ++k) {
+					// overflowing exponential weights are inf / nan in both implementations: equal non-finite values agree
+					auto rel = [&](double x, double y, double sc) { return (x == y || (std::isnan(x) && std::isnan(y))) ? 0.0 : (std::isfinite(x) && std::isfinite(y) ? std::abs(x - y) / sc : 1.0); };
+					const double dw = rel((*wa[k])(i), (*wb[k])(i), sw), dr = rel(a.Ri(i, k), b.Ri(i, k), sr), dj = rel(a.Ji(i, k), b.Ji(i, k), sj);
+					worst = std::max(worst, std::max(dw, std::max(dr, dj)));
+					ok = dw <= 1e-9 && dr <= 1e-9 && dj <= 1e-10;     // Ji: Eigen sums a row of D over columns, the kernel over the CSR row
+				}
+			}
+			const double ea = ::compute_energy_with_jacobians(a, Vd, Fd, a.Ji, ua, areas), eb = fpohm_shim::compute_energy_with_jacobians(b, Vd, Fd, b.Ji, ub, areas);
+			if (!(ea == eb || std::abs(ea - eb) <= 1e-9 * std::abs(ea))) { std::printf("     energy %d: %.17g vs %.17g\n", en, ea, eb); ok = false; }
+		}
+		std::printf("     SLIM stages: worst relative difference %.2e\n", worst);
+		EXPECT(ok, "SLIM compute_jacobians / update_weights_and_closest_rotations / compute_energy_with_jacobians within 1e-9 (north star: 1e-5), all six energies");
 	}
 	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
 	return failures ? 1 : 0;

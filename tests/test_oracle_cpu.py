@@ -348,3 +348,27 @@ def test_port_extract_surface_vs_golden(port):
                 assert np.array_equal(np.asarray(got[k]), g[f"{name}_{tri}_{k}"]), (name, tri, k)
             for k in ("E_nfs", "V_nvs", "V_nes", "V_nfs"):
                 assert np.array_equal(got[k][0], g[f"{name}_{tri}_{k}_off"]) and np.array_equal(got[k][1], g[f"{name}_{tri}_{k}_val"]), (name, tri, k)
+
+
+# ---- §8(f)-3: SLIM per-element stages (golden_slim_v1.npz from the compiled slim_m.cpp, tests/golden/make_golden_slim.py) ----
+def test_port_slim_stages_vs_golden(port):
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
+    J, areas, ef = g["J"], g["areas"], float(g["exp_factor"])
+    for en in port.SLIM_ENERGIES:
+        W, Ri = port.slim_weights_rotations(J, en, ef)
+        fin = np.isfinite(g[f"{en}_W"]).all(1)
+        assert np.array_equal(fin, np.isfinite(W).all(1)), en
+        assert np.abs(W[fin] - g[f"{en}_W"][fin]).max() <= 1e-9 * np.abs(g[f"{en}_W"][fin]).max(), en      # LAPACK vs Eigen JacobiSVD: rounding only
+        assert np.abs(Ri - g[f"{en}_Ri"]).max() <= 1e-9 * max(1.0, np.abs(g[f"{en}_Ri"]).max()), en
+        e = port.slim_energy(J, areas, en, ef)
+        want = float(g[f"{en}_energy"])
+        assert (e == want) if not np.isfinite(want) else abs(e - want) <= 1e-10 * abs(want), en      # the exponential energy overflows to inf in both
+    Ji = port.slim_jacobians(g["jac_off"], g["jac_col"], g["jac_vx"], g["jac_vy"], g["jac_vz"], g["jac_uv"])
+    assert np.abs(Ji - g["jac_Ji"]).max() <= 1e-12 * np.abs(g["jac_Ji"]).max()
+
+
+def test_golden_slim_matches_live_reference(ref):
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
+    W, Ri = ref.slim_weights_rotations(g["J"], "SYMMETRIC_DIRICHLET", float(g["exp_factor"]))
+    assert np.array_equal(W, g["SYMMETRIC_DIRICHLET_W"]) and np.array_equal(Ri, g["SYMMETRIC_DIRICHLET_Ri"])
+    assert ref.slim_energy(g["J"], g["areas"], "CONFORMAL", float(g["exp_factor"])) == float(g["CONFORMAL_energy"])
