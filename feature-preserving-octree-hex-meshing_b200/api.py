@@ -16,7 +16,7 @@ __all__ = [
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
     "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh", "extract_surface",
-    "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev",
+    "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev", "slim_max_step",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -518,6 +518,13 @@ def slim_energy(ctx: Context, Ji, areas, energy: str, exp_factor: float = 1.0) -
     Ji = _f64(Ji).reshape(-1, 9); a = _f64(areas); e = C.c_double()
     _chk(lib().fpohm_slim_energy(ctx.h, _p(Ji), C.c_int64(len(Ji)), _p(a), C.c_int32(SLIM_ENERGIES[energy]), C.c_double(exp_factor), C.byref(e)))
     return e.value
+
+
+def slim_max_step(ctx: Context, uv, T, d):
+    """compute_max_step_from_singularities (igl/flip_avoiding_line_search.cpp:273-299, tets): (max_step, per-tet roots)."""
+    uv, d = _f64(uv), _f64(d); T = _i32(T); roots = np.zeros(len(T)); m = C.c_double()
+    _chk(lib().fpohm_slim_max_step(ctx.h, _p(uv), C.c_int64(len(uv)), _p(T), C.c_int64(len(T)), _p(d), _p(roots), C.byref(m)))
+    return m.value, roots
 
 
 def slim_weights_rotations_dev(ctx: Context, Ji_ptr: int, n: int, energy: str, exp_factor: float, W_ptr: int, Ri_ptr: int, stream: int = 0):

@@ -12,6 +12,7 @@
 #include "internal.h"
 
 #include <cmath>
+#include <math_constants.h>
 #include <vector>
 
 using namespace fpohm;
@@ -222,6 +223,100 @@ slim_jacobians_kernel(int64_t n, const int64_t *__restrict__ off, const int32_t 
 	}
 }
 
+// ---- flip-avoiding line search: largest step before some tet's volume changes sign
+// (igl::flip_avoiding::compute_max_step_from_singularities, igl/flip_avoiding_line_search.cpp:177-299, tet branch).
+// The volume along the search direction is the cubic det([b-a; c-a; d-a] + t [db-da; dc-da; dd-da]); its coefficients are the
+// row-wise multilinear expansion of that determinant — the same polynomial as the reference's symbolic expansion of the 4x4
+// volume determinant up to a common sign, on which the root selection does not depend.
+__device__ __forceinline__ double det_rows(const double *x, const double *y, const double *z) {
+	return x[0] * (y[1] * z[2] - y[2] * z[1]) - x[1] * (y[0] * z[2] - y[2] * z[0]) + x[2] * (y[0] * z[1] - y[1] * z[0]);
+}
+// smallest positive root of a t^2 + b t + c (igl/flip_avoiding_line_search.cpp:63-109)
+__device__ __forceinline__ double smallest_pos_quad_zero(double a, double b, double c) {
+	const double inf = CUDART_INF;
+	if (fabs(a) > 1.0e-10) {
+		const double delta_in = b * b - 4 * a * c;
+		if (delta_in <= 0) return inf;
+		const double delta = sqrt(delta_in);
+		double t1, t2;
+		if (b >= 0) { const double bd = -b - delta; t1 = 2 * c / bd; t2 = bd / (2 * a); }
+		else { const double bd = -b + delta; t1 = bd / (2 * a); t2 = (2 * c) / bd; }
+		if (a < 0) { const double t = t1; t1 = t2; t2 = t; }
+		if (t1 > 0) return t2 > 0 ? t2 : t1;
+		return inf;
+	}
+	if (b == 0) return inf;
+	const double t1 = -c / b;
+	return t1 > 0 ? t1 : inf;
+}
+// smallest positive root of t^3 + a t^2 + b t + c: trigonometric form for three real roots, Cardano otherwise (:24-61, :249-270)
+__device__ __forceinline__ double smallest_pos_cubic_zero(double a, double b, double c) {
+	const double inf = CUDART_INF;
+	const double a2 = a * a;
+	double q = (a2 - 3 * b) / 9;
+	const double r = (a * (2 * a2 - 9 * b) + 27 * c) / 54;
+	const double r2 = r * r, q3 = q * q * q;
+	if (r2 < q3) {
+		double t = r / sqrt(q3);
+		t = acos(fmin(1.0, fmax(-1.0, t)));
+		a /= 3; q = -2 * sqrt(q);
+		double x0 = q * cos(t / 3) - a, x1 = q * cos((t + 2 * CUDART_PI) / 3) - a, x2 = q * cos((t - 2 * CUDART_PI) / 3) - a;
+		double lo = x0, mid = x1, hi = x2, sw;                 // std::sort of the three roots
+		if (lo > mid) { sw = lo; lo = mid; mid = sw; }
+		if (mid > hi) { sw = mid; mid = hi; hi = sw; }
+		if (lo > mid) { sw = lo; lo = mid; mid = sw; }
+		if (lo > 0) return lo;
+		if (mid > 0) return mid;
+		if (hi > 0) return hi;
+		return inf;
+	}
+	double A = -pow(fabs(r) + sqrt(r2 - q3), 1. / 3);
+	if (r < 0) A = -A;
+	const double B = A == 0 ? 0 : q / A;
+	a /= 3;
+	const double x0 = (A + B) - a, x1 = -0.5 * (A + B) - a, x2 = 0.5 * sqrt(3.) * (A - B);
+	if (fabs(x2) < 1e-14) {                            // double real root
+		const double lo = fmin(x0, x1), hi = fmax(x0, x1);
+		if (lo > 0) return lo;
+		if (hi > 0) return hi;
+		return inf;
+	}
+	return x0 >= 0 ? x0 : inf;                         // one real root
+}
+__global__ void __launch_bounds__(256)
+slim_max_step_kernel(const double *__restrict__ uv, const int32_t *__restrict__ T, int64_t n, const double *__restrict__ d,
+                     double *__restrict__ roots, double *__restrict__ partial)
+{
+	__shared__ double sm[256];
+	double best = CUDART_INF;
+	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < n; f += (int64_t)gridDim.x * blockDim.x) {
+		const int4 t = *reinterpret_cast<const int4 *>(T + 4 * f);
+		const int v[4] = {t.x, t.y, t.z, t.w};
+		double P[3][3], D[3][3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				P[k][c] = uv[3 * (int64_t)v[k + 1] + c] - uv[3 * (int64_t)v[0] + c];
+				D[k][c] = d[3 * (int64_t)v[k + 1] + c] - d[3 * (int64_t)v[0] + c];
+			}
+		const double c0 = det_rows(P[0], P[1], P[2]);
+		const double c1 = det_rows(D[0], P[1], P[2]) + det_rows(P[0], D[1], P[2]) + det_rows(P[0], P[1], D[2]);
+		const double c2 = det_rows(D[0], D[1], P[2]) + det_rows(D[0], P[1], D[2]) + det_rows(P[0], D[1], D[2]);
+		const double c3 = det_rows(D[0], D[1], D[2]);
+		const double root = fabs(c3) <= 1.e-10 ? smallest_pos_quad_zero(c2, c1, c0) : smallest_pos_cubic_zero(c2 / c3, c1 / c3, c0 / c3);
+		if (roots) roots[f] = root;
+		best = fmin(best, root);
+	}
+	sm[threadIdx.x] = best;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] = fmin(sm[threadIdx.x], sm[threadIdx.x + o]); __syncthreads(); }
+	if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+__global__ void slim_min_final_kernel(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) { double m = CUDART_INF; for (int b = 0; b < nb; ++b) m = fmin(m, partial[b]); *out = m; }
+}
+
 void check_energy(int32_t energy, const char *who) {
 	FPOHM_REQUIRE(energy >= 0 && energy <= 5, FPOHM_EINVAL, "%s: unknown SLIM_ENERGY %d", who, energy);
 }
@@ -269,6 +364,41 @@ int fpohm_slim_energy_dev(fpohm_ctx *ctx, const double *Ji_dev, int64_t n, const
 	FPOHM_LAUNCH_CHECK(ctx);
 	slim_energy_final_kernel<<<1, 32, 0, s>>>(partial.p, nb, energy_dev);
 	FPOHM_LAUNCH_CHECK(ctx);
+	FPOHM_API_END
+}
+
+int fpohm_slim_max_step_dev(fpohm_ctx *ctx, const double *uv_dev, const int32_t *T_dev, int64_t n, const double *d_dev, double *roots_dev,
+                            double *max_step_dev, void *stream)
+{
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && n >= 0 && max_step_dev && (n == 0 || (uv_dev && T_dev && d_dev)), FPOHM_EINVAL, "fpohm_slim_max_step_dev: bad argument");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	const int nb = grid_for(ctx, n, 256, 4);
+	DevBuf<double> partial(nb, s);
+	slim_max_step_kernel<<<nb, 256, 0, s>>>(uv_dev, T_dev, n, d_dev, roots_dev, partial.p);
+	FPOHM_LAUNCH_CHECK(ctx);
+	slim_min_final_kernel<<<1, 32, 0, s>>>(partial.p, nb, max_step_dev);
+	FPOHM_LAUNCH_CHECK(ctx);
+	FPOHM_API_END
+}
+
+int fpohm_slim_max_step(fpohm_ctx *ctx, const double *uv, int64_t nv, const int32_t *T, int64_t n, const double *d, double *roots, double *max_step) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && uv && T && d && max_step && nv > 0 && n > 0, FPOHM_EINVAL, "fpohm_slim_max_step: bad argument");
+	for (int64_t i = 0; i < 4 * n; ++i) FPOHM_REQUIRE(T[i] >= 0 && T[i] < nv, FPOHM_EINVAL, "fpohm_slim_max_step: vertex id %d out of range at %lld", T[i], (long long)i);
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	DevBuf<double> duv(3 * nv, s), dd(3 * nv, s), dr(roots ? n : 0, s), dm(1, s);
+	DevBuf<int32_t> dT(4 * n, s);
+	duv.upload(uv, 3 * nv); dd.upload(d, 3 * nv); dT.upload(T, 4 * n);
+	KernelTimer t(ctx, s);
+	int rc = fpohm_slim_max_step_dev(ctx, duv.p, dT.p, n, dd.p, roots ? dr.p : nullptr, dm.p, s);
+	t.stop();
+	if (rc != FPOHM_OK) return rc;
+	if (roots) dr.download(roots, n);
+	dm.download(max_step, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
 	FPOHM_API_END
 }
 

@@ -299,6 +299,13 @@ int  fpohm_slim_jacobians(fpohm_ctx *ctx, int64_t n, int64_t nv, const int64_t *
                           const double *vy, const double *vz, const double *uv, double *Ji);
 int  fpohm_slim_weights_rotations(fpohm_ctx *ctx, const double *Ji, int64_t n, int32_t energy, double exp_factor, double *W, double *Ri);
 int  fpohm_slim_energy(fpohm_ctx *ctx, const double *Ji, int64_t n, const double *areas, int32_t energy, double exp_factor, double *energy_out);
+/* igl::flip_avoiding::compute_max_step_from_singularities (igl/flip_avoiding_line_search.cpp:177-299, tets; called by the line
+ * search of slim_solve, slim_m.cpp:1224-1387): the smallest positive t at which some tet (uv + t d) has zero volume, +inf if
+ * none.  uv, d = nv x 3 row-major, T = n x 4 vertex ids; roots (n, optional) = the per-tet values of get_min_pos_root_3D. */
+int  fpohm_slim_max_step(fpohm_ctx *ctx, const double *uv, int64_t nv, const int32_t *T, int64_t n, const double *d, double *roots,
+                         double *max_step);
+int  fpohm_slim_max_step_dev(fpohm_ctx *ctx, const double *uv_dev, const int32_t *T_dev, int64_t n, const double *d_dev, double *roots_dev,
+                             double *max_step_dev, void *stream);
 int  fpohm_slim_jacobians_dev(fpohm_ctx *ctx, int64_t n, const int64_t *off_dev, const int32_t *col_dev, const double *vx_dev,
                               const double *vy_dev, const double *vz_dev, const double *uv_dev, double *Ji_dev, void *stream);
 int  fpohm_slim_weights_rotations_dev(fpohm_ctx *ctx, const double *Ji_dev, int64_t n, int32_t energy, double exp_factor, double *W_dev,

@@ -2,6 +2,7 @@
 // compute_jacobians (:84-106), update_weights_and_closest_rotations (:108-381, tet branch) and compute_energy_with_jacobians
 // (:792-916).  The SLIMData is filled by hand with exactly the members those functions read.
 #include "slim_m.h"
+#include <igl/flip_avoiding_line_search.h>
 #include <cstdint>
 #include <vector>
 
@@ -69,6 +70,18 @@ double ref_slim_energy(const double *J, int64_t n, const double *areas, int ener
 	for (int64_t i = 0; i < n; ++i) a(i) = areas[i];
 	Eigen::MatrixXd V, uv; Eigen::MatrixXi F;
 	return compute_energy_with_jacobians(s, V, F, Ji, uv, a);
+}
+
+
+// igl::flip_avoiding::compute_max_step_from_singularities (igl/flip_avoiding_line_search.cpp:273-299, tet branch) and the per-tet
+// roots of get_min_pos_root_3D (:177-271).  uv, d row-major nv x 3; T row-major n x 4; roots may be NULL.
+double ref_slim_max_step(const double *uv, int64_t nv, const int32_t *T, int64_t n, const double *d, double *roots) {
+	Eigen::MatrixXd U(nv, 3), D(nv, 3);
+	for (int64_t i = 0; i < nv; ++i) for (int c = 0; c < 3; ++c) { U(i, c) = uv[3 * i + c]; D(i, c) = d[3 * i + c]; }
+	Eigen::MatrixXi F(n, 4);
+	for (int64_t i = 0; i < n; ++i) for (int c = 0; c < 4; ++c) F(i, c) = T[4 * i + c];
+	if (roots) for (int64_t i = 0; i < n; ++i) roots[i] = igl::flip_avoiding::get_min_pos_root_3D(U, F, D, (int)i);
+	return igl::flip_avoiding::compute_max_step_from_singularities(U, F, D);
 }
 
 }

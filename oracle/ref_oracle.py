@@ -413,3 +413,12 @@ def slim_energy(J, areas, energy, exp_factor=1.0):
     J = _f64(J).reshape(-1, 9); a = _f64(areas)
     lib().ref_slim_energy.restype = C.c_double
     return float(lib().ref_slim_energy(_p(J), C.c_int64(len(J)), _p(a), C.c_int(SLIM_ENERGIES[energy]), C.c_double(exp_factor)))
+
+
+def slim_max_step(uv, T, d):
+    """compute_max_step_from_singularities (igl/flip_avoiding_line_search.cpp:273-299, tets): (max_step, per-tet smallest positive roots)."""
+    uv, d = _f64(uv), _f64(d); T = _i32(T)
+    roots = np.zeros(len(T))
+    lib().ref_slim_max_step.restype = C.c_double
+    m = lib().ref_slim_max_step(_p(uv), C.c_int64(len(uv)), _p(T), C.c_int64(len(T)), _p(d), _p(roots))
+    return float(m), roots

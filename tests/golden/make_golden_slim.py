@@ -29,6 +29,15 @@ nv, nt = 200, 500
 col = rng.integers(0, nv, (nt, 4)).astype(np.int32); off = np.arange(0, 4 * nt + 1, 4)
 vx, vy, vz = rng.normal(size=(3, 4 * nt)); uv = rng.normal(size=(nv, 3))
 G.update(jac_off=off, jac_col=col.reshape(-1), jac_vx=vx, jac_vy=vy, jac_vz=vz, jac_uv=uv, jac_Ji=R.slim_jacobians(off, col.reshape(-1), vx, vy, vz, uv, nv))
+# flip-avoiding step bound (igl/flip_avoiding_line_search.cpp:177-299) on the 8-tets-per-hex split of a warped block
+import fpohm_b200 as fp  # procedural meshes only
+Vb, Hb = fp.procedural.warped_hex_block(5, 0.3)
+Tb = Hb[:, [[0, 1, 3, 4], [1, 2, 0, 5], [2, 3, 1, 6], [3, 0, 2, 7], [4, 7, 5, 0], [5, 4, 6, 1], [6, 5, 7, 2], [7, 6, 4, 3]]].reshape(-1, 4).astype(np.int32)
+G["step_uv"] = Vb; G["step_T"] = Tb
+for k, sc in enumerate((0.02, 0.2, 2.0)):
+    d = rng.normal(0, sc, Vb.shape)
+    m, r = R.slim_max_step(Vb, Tb, d)
+    G[f"step{k}_d"] = d; G[f"step{k}_max"] = np.float64(m); G[f"step{k}_roots"] = r
 out = Path(__file__).resolve().parent / "golden_slim_v1.npz"
 np.savez_compressed(out, **G)
 print(f"wrote {out} ({out.stat().st_size / 1e3:.0f} kB, {len(G)} arrays)")

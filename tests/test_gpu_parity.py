@@ -834,3 +834,29 @@ def test_slim_jacobians_vs_reference(fp, ctx, ref):
     # the deformation gradient of the identity map is the identity
     I = fp.slim_jacobians(ctx, off, col, vx, vy, vz, V)
     assert np.abs(I - np.eye(3).reshape(9)).max() < 1e-9
+
+
+def test_slim_max_step_vs_reference(fp, ctx, ref):
+    """compute_max_step_from_singularities (igl/flip_avoiding_line_search.cpp, tets): per-tet smallest positive roots and their minimum,
+    for search directions from tiny to mesh-inverting, incl. a zero direction (no root at all) and a rigid translation."""
+    V, H = fp.procedural.warped_hex_block(10, 0.3)
+    T = H[:, [[0, 1, 3, 4], [1, 2, 0, 5], [2, 3, 1, 6], [3, 0, 2, 7], [4, 7, 5, 0], [5, 4, 6, 1], [6, 5, 7, 2], [7, 6, 4, 3]]].reshape(-1, 4).astype(np.int32)
+    rng = np.random.default_rng(31)
+    for sc in (1e-4, 0.02, 0.2, 2.0):
+        d = rng.normal(0, sc, V.shape)
+        m, r = fp.slim_max_step(ctx, V, T, d)
+        rm, rr = ref.slim_max_step(V, T, d)
+        fin = np.isfinite(rr)
+        assert np.array_equal(fin, np.isfinite(r)), sc
+        assert (np.abs(r[fin] - rr[fin]) <= 1e-8 * np.abs(rr[fin])).all(), (sc, float((np.abs(r[fin] - rr[fin]) / np.abs(rr[fin])).max()))
+        assert abs(m - rm) <= 1e-9 * abs(rm), (sc, m, rm)
+        # the bound is tight: just before it no tet is inverted, just after it one is
+        vol = lambda X: np.einsum("ij,ij->i", X[T[:, 1]] - X[T[:, 0]], np.cross(X[T[:, 2]] - X[T[:, 0]], X[T[:, 3]] - X[T[:, 0]]))
+        s0 = np.sign(vol(V))
+        assert (np.sign(vol(V + 0.999 * m * d)) == s0).all() and (np.sign(vol(V + 1.001 * m * d)) != s0).any(), sc
+    for d in (np.zeros_like(V), np.ones_like(V) * 0.3):
+        m, r = fp.slim_max_step(ctx, V, T, d)
+        rm, rr = ref.slim_max_step(V, T, d)
+        assert m == rm == np.inf and np.array_equal(r, rr)
+    with pytest.raises(fp.FpohmError):
+        fp.slim_max_step(ctx, V, T + len(V), V)

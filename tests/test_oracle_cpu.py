@@ -367,6 +367,15 @@ def test_port_slim_stages_vs_golden(port):
     assert np.abs(Ji - g["jac_Ji"]).max() <= 1e-12 * np.abs(g["jac_Ji"]).max()
 
 
+def test_port_slim_max_step_vs_golden(port):
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
+    for k in range(3):
+        m, r = port.slim_max_step(g["step_uv"], g["step_T"], g[f"step{k}_d"])
+        want = g[f"step{k}_roots"]; fin = np.isfinite(want)
+        assert np.array_equal(fin, np.isfinite(r))
+        assert (np.abs(r[fin] - want[fin]) <= 1e-8 * np.abs(want[fin])).all() and abs(m - float(g[f"step{k}_max"])) <= 1e-9 * m
+
+
 def test_golden_slim_matches_live_reference(ref):
     g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
     W, Ri = ref.slim_weights_rotations(g["J"], "SYMMETRIC_DIRICHLET", float(g["exp_factor"]))
