@@ -850,13 +850,19 @@ def test_slim_max_step_vs_reference(fp, ctx, ref):
         assert np.array_equal(fin, np.isfinite(r)), sc
         assert (np.abs(r[fin] - rr[fin]) <= 1e-8 * np.abs(rr[fin])).all(), (sc, float((np.abs(r[fin] - rr[fin]) / np.abs(rr[fin])).max()))
         assert abs(m - rm) <= 1e-9 * abs(rm), (sc, m, rm)
+        if sc < 0.01:
+            continue      # |det(D)| <= 1e-10 there: the reference (and we) drop the cubic term, the bound is only approximate
         # the bound is tight: just before it no tet is inverted, just after it one is
         vol = lambda X: np.einsum("ij,ij->i", X[T[:, 1]] - X[T[:, 0]], np.cross(X[T[:, 2]] - X[T[:, 0]], X[T[:, 3]] - X[T[:, 0]]))
         s0 = np.sign(vol(V))
         assert (np.sign(vol(V + 0.999 * m * d)) == s0).all() and (np.sign(vol(V + 1.001 * m * d)) != s0).any(), sc
-    for d in (np.zeros_like(V), np.ones_like(V) * 0.3):
-        m, r = fp.slim_max_step(ctx, V, T, d)
-        rm, rr = ref.slim_max_step(V, T, d)
-        assert m == rm == np.inf and np.array_equal(r, rr)
+    m, r = fp.slim_max_step(ctx, V, T, np.zeros_like(V))
+    rm, rr = ref.slim_max_step(V, T, np.zeros_like(V))
+    assert m == rm == np.inf and np.array_equal(r, rr)
+    # rigid translation: no tet ever degenerates.  The difference form gives exactly zero coefficients -> +inf; the reference's
+    # expansion in absolute coordinates keeps rounding noise in them and reports a spurious root of order 1e12 (documented deviation)
+    m, r = fp.slim_max_step(ctx, V, T, np.ones_like(V) * 0.3)
+    rm, rr = ref.slim_max_step(V, T, np.ones_like(V) * 0.3)
+    assert m == np.inf and rm > 1e9
     with pytest.raises(fp.FpohmError):
         fp.slim_max_step(ctx, V, T + len(V), V)
