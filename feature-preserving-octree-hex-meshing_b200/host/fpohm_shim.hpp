@@ -32,6 +32,7 @@
 //   compute_jacobians(SLIMData&, uv)               slim_m.cpp:84         compute_jacobians(s, uv)               (tet branch)
 //   update_weights_and_closest_rotations(s, V, F, uv) slim_m.cpp:108     update_weights_and_closest_rotations(s, V, F, uv)
 //   compute_energy_with_jacobians(s, V, F, Ji, uv, areas) slim_m.cpp:792 compute_energy_with_jacobians(s, V, F, Ji, uv, areas)
+//   igl::flip_avoiding::compute_max_step_from_singularities(uv, F, d) igl/flip_avoiding_line_search.cpp:273   compute_max_step_from_singularities(uv, F, d)
 //
 // Error behaviour mirrors the reference: bool returns and a line on std::cout/cerr, never an exception out of a call the
 // reference declares noexcept-in-practice; a missing GPU is fatal by design (no CPU fallback) and reported loudly.
@@ -413,6 +414,21 @@ double compute_energy_with_jacobians(SLIMDataT &s, const MatV &, const MatF &, c
 	double e = 0;
 	check(fpohm_slim_energy(context(), J.data(), n, a.data(), (int32_t)s.slim_energy, s.exp_factor, &e), "fpohm_slim_energy");
 	return e;
+}
+
+// igl::flip_avoiding::compute_max_step_from_singularities(const MatrixXd &uv, const MatrixXi &F, MatrixXd &d), tet branch
+// (igl/flip_avoiding_line_search.cpp:273-299)
+template <class MatU, class MatF, class MatD>
+double compute_max_step_from_singularities(const MatU &uv, const MatF &F, MatD &d) {
+	if (uv.cols() != 3 || F.cols() != 4) throw std::runtime_error("fpohm_shim::compute_max_step_from_singularities: only the tet branch is on the hot path");
+	const int64_t nv = (int64_t)uv.rows(), n = (int64_t)F.rows();
+	std::vector<double> u(3 * (size_t)nv), dd(3 * (size_t)nv);
+	std::vector<int32_t> T(4 * (size_t)n);
+	for (int64_t i = 0; i < nv; ++i) for (int c = 0; c < 3; ++c) { u[3 * i + c] = uv(i, c); dd[3 * i + c] = d(i, c); }
+	for (int64_t i = 0; i < n; ++i) for (int c = 0; c < 4; ++c) T[4 * i + c] = (int32_t)F(i, c);
+	double m = 0;
+	check(fpohm_slim_max_step(context(), u.data(), nv, T.data(), n, dd.data(), nullptr, &m), "fpohm_slim_max_step");
+	return m;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include "metro_hausdorff.h"
 #include "grid_meshing/grid_hex_meshing.h"
 #include "slim_m.h"
+#include <igl/flip_avoiding_line_search.h>
 #include <igl/signed_distance.h>
 #include <geogram/basic/common.h>
 #include <geogram/basic/logger.h>
@@ -325,8 +326,17 @@ int main() {
 			const double ea = ::compute_energy_with_jacobians(a, Vd, Fd, a.Ji, ua, areas), eb = fpohm_shim::compute_energy_with_jacobians(b, Vd, Fd, b.Ji, ub, areas);
 			if (!(ea == eb || std::abs(ea - eb) <= 1e-9 * std::abs(ea))) { std::printf("     energy %d: %.17g vs %.17g\n", en, ea, eb); ok = false; }
 		}
+		// line-search step bound along a direction that inverts some tets
+		{
+			SLIMData a; fill(a);
+			Eigen::MatrixXd pos(nv, 3), dir(nv, 3);
+			for (int i = 0; i < nv; ++i) for (int c = 0; c < 3; ++c) { pos(i, c) = hb.V(c, i); dir(i, c) = 0.4 * std::sin(3.0 * i + 1.7 * c); }
+			const double ma = igl::flip_avoiding::compute_max_step_from_singularities(pos, a.F, dir), mb = fpohm_shim::compute_max_step_from_singularities(pos, a.F, dir);
+			std::printf("     step bound %.17g vs %.17g\n", ma, mb);
+			ok = ok && std::isfinite(ma) && std::abs(ma - mb) <= 1e-9 * ma;
+		}
 		std::printf("     SLIM stages: worst relative difference %.2e\n", worst);
-		EXPECT(ok, "SLIM compute_jacobians / update_weights_and_closest_rotations / compute_energy_with_jacobians within 1e-9 (north star: 1e-5), all six energies");
+		EXPECT(ok, "SLIM compute_jacobians / update_weights_and_closest_rotations / compute_energy_with_jacobians / max step within 1e-9 (north star: 1e-5), all six energies");
 	}
 	std::printf("%s (%d failures)\n", failures ? "SHIM PARITY FAILED" : "SHIM PARITY OK", failures);
 	return failures ? 1 : 0;
