@@ -29,6 +29,15 @@ for en in ("SYMMETRIC_DIRICHLET", "ARAP", "EXP_CONFORMAL"):
     ms_e = timed(lambda: fp.slim_energy_dev(ctx, J.data_ptr(), n, areas.data_ptr(), en, 1.0, E.data_ptr(), st.cuda_stream))
     out[en] = {"weights_rotations_ms": ms, "tets_per_s": n / ms * 1e3, "GBs": 216 * n / ms / 1e6, "frac": 216 * n / ms / 1e6 / PEAK,
                "energy_ms": ms_e, "energy_GBs": 80 * n / ms_e / 1e6, "energy_frac": 80 * n / ms_e / 1e6 / PEAK}
+# line-search step bound on the 8-tets-per-hex split of a 128^3 block (16.8 M tets), resident
+Vb, Hb = fp.procedural.warped_hex_block(128, 0.3)
+Tb = np.ascontiguousarray(Hb[:, [[0, 1, 3, 4], [1, 2, 0, 5], [2, 3, 1, 6], [3, 0, 2, 7], [4, 7, 5, 0], [5, 4, 6, 1], [6, 5, 7, 2], [7, 6, 4, 3]]].reshape(-1, 4).astype(np.int32))
+dV = torch.from_numpy(Vb).to(dev); dT = torch.from_numpy(Tb).to(dev); dD = 0.01 * torch.randn(len(Vb), 3, dtype=torch.float64, device=dev, generator=g)
+dM = torch.empty(1, dtype=torch.float64, device=dev)
+import ctypes as C
+ms = timed(lambda: fp.api._chk(fp.lib().fpohm_slim_max_step_dev(ctx.h, C.c_void_p(dV.data_ptr()), C.c_void_p(dT.data_ptr()), C.c_int64(len(Tb)), C.c_void_p(dD.data_ptr()),
+                                                                 None, C.c_void_p(dM.data_ptr()), C.c_void_p(st.cuda_stream))))
+out["max_step"] = {"tets": len(Tb), "ms": ms, "tets_per_s": len(Tb) / ms * 1e3, "bound": float(dM.item())}
 try:
     from oracle import ref_oracle as R
     if R.available():
@@ -36,6 +45,9 @@ try:
         Jh = J[:m].cpu().numpy(); ah = areas[:m].cpu().numpy()
         t0 = time.perf_counter(); R.slim_weights_rotations(Jh, "SYMMETRIC_DIRICHLET", 1.0); dt = time.perf_counter() - t0
         t0 = time.perf_counter(); R.slim_energy(Jh, ah, "SYMMETRIC_DIRICHLET", 1.0); de = time.perf_counter() - t0
+        mt = 400_000
+        t0 = time.perf_counter(); R.slim_max_step(Vb, Tb[:mt], dD.cpu().numpy()); dstep = time.perf_counter() - t0
+        out["reference_1core_max_step_tets_per_s"] = mt / dstep / 2      # the driver evaluates every tet twice (roots + bound)
         out["reference_1core"] = {"sample_tets": m, "weights_rotations_tets_per_s": m / dt, "energy_tets_per_s": m / de}
 except Exception as e:
     out["reference_1core"] = {"error": str(e)}
