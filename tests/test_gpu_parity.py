@@ -866,3 +866,14 @@ def test_slim_max_step_vs_reference(fp, ctx, ref):
     assert m == np.inf and rm > 1e9
     with pytest.raises(fp.FpohmError):
         fp.slim_max_step(ctx, V, T + len(V), V)
+
+
+def test_clean_hex_mesh_refuses_bad_ids(fp, ctx):
+    from clean_cases import block
+    V, H = block(3, 3, 3)
+    tV, tF = fp.procedural.torus(20, 12)
+    m = fp.TriMesh(ctx, tV, tF)
+    bad = H.copy(); bad[5, 3] = len(V) + 7
+    with pytest.raises(fp.FpohmError, match="out of range"):
+        fp.clean_hex_mesh(ctx, m, V, bad)
+    m.close()
