@@ -429,6 +429,7 @@ def main():
                          "jacobian_roofline": {"bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak},
                          "voxel_sign_ms": vox_ms, "voxel_sign_dims": vg.dims.tolist(),
+                         "voxel_sign_note": "gear grid of 27 MB (fits L2, 6 launches + 1 read-back): latency-bound; the 1 GiB case is c3_1024",
                          "voxel_sign_roofline": {"bound": "hbm", "achieved": vox_bytes / (vox_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                  "frac": vox_bytes / (vox_ms * 1e-3) / 1e9 / peak}}}
         line["also"]["conforming_dual"] = conf
