@@ -43,11 +43,12 @@ __device__ void svd3(const double A[3][3], Svd3 &o) {
 			const double alpha = B[0][p] * B[0][p] + B[1][p] * B[1][p] + B[2][p] * B[2][p];
 			const double beta = B[0][q] * B[0][q] + B[1][q] * B[1][q] + B[2][q] * B[2][q];
 			const double gamma = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
-			if (gamma == 0.0 || fabs(gamma) <= 1e-15 * sqrt(alpha * beta)) continue;
+			if (gamma == 0.0 || gamma * gamma <= 1e-30 * (alpha * beta)) continue;       // |cos| of the column angle <= 1e-15
 			rotated = true;
-			const double zeta = (beta - alpha) / (2.0 * gamma);
-			const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-			const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+			// smaller root of t^2 + 2 zeta t - 1 = 0, zeta = (beta - alpha) / (2 gamma), written with one division
+			const double dba = beta - alpha;
+			const double t = (dba >= 0 ? 2.0 * gamma : -2.0 * gamma) / (fabs(dba) + sqrt(dba * dba + 4.0 * gamma * gamma));
+			const double c = rsqrt(1.0 + t * t), s = c * t;
 			rot_cols(B, p, q, c, s);
 			rot_cols(o.V, p, q, c, s);
 		}
