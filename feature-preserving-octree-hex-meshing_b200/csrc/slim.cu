@@ -28,7 +28,8 @@ __device__ __forceinline__ void rot_cols(double M[3][3], int p, int q, double c,
 	for (int r = 0; r < 3; ++r) { const double a = M[r][p], b = M[r][q]; M[r][p] = c * a - s * b; M[r][q] = s * a + c * b; }
 }
 
-// A = U diag(s) V^T, s[0] >= s[1] >= s[2] >= 0
+// A = U diag(s) V^T, s[0] >= s[1] >= s[2] >= 0.  VECTORS = false: singular values only (the energy needs nothing else)
+template <bool VECTORS>
 __device__ void svd3(const double A[3][3], Svd3 &o) {
 	double B[3][3];
 #pragma unroll
@@ -50,7 +51,7 @@ __device__ void svd3(const double A[3][3], Svd3 &o) {
 			const double t = (dba >= 0 ? 2.0 * gamma : -2.0 * gamma) / (fabs(dba) + sqrt(dba * dba + 4.0 * gamma * gamma));
 			const double c = rsqrt(1.0 + t * t), s = c * t;
 			rot_cols(B, p, q, c, s);
-			rot_cols(o.V, p, q, c, s);
+			if (VECTORS) rot_cols(o.V, p, q, c, s);
 		}
 		if (!rotated) break;
 	}
@@ -62,6 +63,14 @@ __device__ void svd3(const double A[3][3], Svd3 &o) {
 	if (n[a] < n[b]) {                                                                                     \
 		double t_ = n[a]; n[a] = n[b]; n[b] = t_;                                                          \
 		for (int r = 0; r < 3; ++r) { t_ = B[r][a]; B[r][a] = B[r][b]; B[r][b] = t_; t_ = o.V[r][a]; o.V[r][a] = o.V[r][b]; o.V[r][b] = t_; } \
+	}
+	if (!VECTORS) {
+		double t_;
+		if (n[0] < n[1]) { t_ = n[0]; n[0] = n[1]; n[1] = t_; }
+		if (n[1] < n[2]) { t_ = n[1]; n[1] = n[2]; n[2] = t_; }
+		if (n[0] < n[1]) { t_ = n[0]; n[0] = n[1]; n[1] = t_; }
+		o.s[0] = n[0]; o.s[1] = n[1]; o.s[2] = n[2];
+		return;
 	}
 	FPOHM_COLSWAP(0, 1) FPOHM_COLSWAP(1, 2) FPOHM_COLSWAP(0, 1)
 #undef FPOHM_COLSWAP
@@ -107,7 +116,7 @@ slim_weights_kernel(const double *__restrict__ Ji, int64_t n, int energy, double
 		double A[3][3];
 		load_ji(Ji, i, A);
 		Svd3 f;
-		svd3(A, f);
+		svd3<true>(A, f);
 		const double s1 = f.s[0], s2 = f.s[1], s3 = f.s[2];
 		// ri = U V^T, last column of V negated under a reflection (igl/polar_svd.cpp:53-62)
 		double R[3][3];
@@ -194,7 +203,7 @@ slim_energy_kernel(const double *__restrict__ Ji, int64_t n, const double *__res
 		double A[3][3];
 		load_ji(Ji, i, A);
 		Svd3 f;
-		svd3(A, f);
+		svd3<false>(A, f);
 		acc += areas[i] * element_energy(energy, exp_f, f.s[0], f.s[1], f.s[2]);
 	}
 	sm[threadIdx.x] = acc;
