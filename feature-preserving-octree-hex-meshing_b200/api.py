@@ -16,7 +16,7 @@ __all__ = [
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
     "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh", "extract_surface",
-    "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev", "slim_max_step",
+    "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev", "slim_max_step", "slim_rhs_terms",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "libfpohm.so"
@@ -525,6 +525,13 @@ def slim_max_step(ctx: Context, uv, T, d):
     uv, d = _f64(uv), _f64(d); T = _i32(T); roots = np.zeros(len(T)); m = C.c_double()
     _chk(lib().fpohm_slim_max_step(ctx.h, _p(uv), C.c_int64(len(uv)), _p(T), C.c_int64(len(T)), _p(d), _p(roots), C.byref(m)))
     return m.value, roots
+
+
+def slim_rhs_terms(ctx: Context, W, Ri):
+    """per-element part of buildRhs (slim_m.cpp:1061-1083): f_rhs (9 n) from W (n x 9) and Ri (n x 9)."""
+    W = _f64(W).reshape(-1, 9); Ri = _f64(Ri).reshape(-1, 9); f = np.zeros(9 * len(W))
+    _chk(lib().fpohm_slim_rhs_terms(ctx.h, _p(W), _p(Ri), C.c_int64(len(W)), _p(f)))
+    return f
 
 
 def slim_weights_rotations_dev(ctx: Context, Ji_ptr: int, n: int, energy: str, exp_factor: float, W_ptr: int, Ri_ptr: int, stream: int = 0):

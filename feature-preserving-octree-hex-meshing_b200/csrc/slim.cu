@@ -327,6 +327,21 @@ __global__ void slim_min_final_kernel(const double *__restrict__ partial, int nb
 	if (blockIdx.x == 0 && threadIdx.x == 0) { double m = CUDART_INF; for (int b = 0; b < nb; ++b) m = fmin(m, partial[b]); *out = m; }
 }
 
+// per-element part of buildRhs (slim_m.cpp:1061-1083): f_rhs(i + (3a + b) n) = sum_k W_{a+1,k+1}(i) * ri(k, b)(i), evaluated left to right
+__global__ void __launch_bounds__(256)
+slim_rhs_terms_kernel(const double *__restrict__ W, const double *__restrict__ Ri, int64_t n, double *__restrict__ f_rhs) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		double w[9], r[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) { w[k] = W[9 * i + k]; r[k] = Ri[9 * i + k]; }
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+#pragma unroll
+			for (int b = 0; b < 3; ++b)
+				f_rhs[i + (int64_t)(3 * a + b) * n] = (w[3 * a] * r[3 * b] + w[3 * a + 1] * r[3 * b + 1]) + w[3 * a + 2] * r[3 * b + 2];
+	}
+}
+
 void check_energy(int32_t energy, const char *who) {
 	FPOHM_REQUIRE(energy >= 0 && energy <= 5, FPOHM_EINVAL, "%s: unknown SLIM_ENERGY %d", who, energy);
 }
@@ -408,6 +423,30 @@ int fpohm_slim_max_step(fpohm_ctx *ctx, const double *uv, int64_t nv, const int3
 	if (rc != FPOHM_OK) return rc;
 	if (roots) dr.download(roots, n);
 	dm.download(max_step, 1);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_API_END
+}
+
+int fpohm_slim_rhs_terms_dev(fpohm_ctx *ctx, const double *W_dev, const double *Ri_dev, int64_t n, double *f_rhs_dev, void *stream) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && n >= 0 && (n == 0 || (W_dev && Ri_dev && f_rhs_dev)), FPOHM_EINVAL, "fpohm_slim_rhs_terms_dev: bad argument");
+	if (n == 0) return FPOHM_OK;
+	DeviceGuard g(ctx->device);
+	slim_rhs_terms_kernel<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(W_dev, Ri_dev, n, f_rhs_dev);
+	FPOHM_LAUNCH_CHECK(ctx);
+	FPOHM_API_END
+}
+
+int fpohm_slim_rhs_terms(fpohm_ctx *ctx, const double *W, const double *Ri, int64_t n, double *f_rhs) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && n > 0 && W && Ri && f_rhs, FPOHM_EINVAL, "fpohm_slim_rhs_terms: bad argument");
+	DeviceGuard g(ctx->device);
+	cudaStream_t s = ctx->stream;
+	DevBuf<double> dW(9 * n, s), dR(9 * n, s), dF(9 * n, s);
+	dW.upload(W, 9 * n); dR.upload(Ri, 9 * n);
+	int rc = fpohm_slim_rhs_terms_dev(ctx, dW.p, dR.p, n, dF.p, s);
+	if (rc != FPOHM_OK) return rc;
+	dF.download(f_rhs, 9 * n);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 	FPOHM_API_END
 }

@@ -306,6 +306,10 @@ int  fpohm_slim_max_step(fpohm_ctx *ctx, const double *uv, int64_t nv, const int
                          double *max_step);
 int  fpohm_slim_max_step_dev(fpohm_ctx *ctx, const double *uv_dev, const int32_t *T_dev, int64_t n, const double *d_dev, double *roots_dev,
                              double *max_step_dev, void *stream);
+/* per-element part of buildRhs (slim_m.cpp:1061-1083): f_rhs (9 n, block layout i + (3a + b) n) = rows of W times columns of ri, the
+ * reference's left-to-right sums (bit-exact given W and Ri); the product with A^T and the proximal term stay with the caller's solve. */
+int  fpohm_slim_rhs_terms(fpohm_ctx *ctx, const double *W, const double *Ri, int64_t n, double *f_rhs);
+int  fpohm_slim_rhs_terms_dev(fpohm_ctx *ctx, const double *W_dev, const double *Ri_dev, int64_t n, double *f_rhs_dev, void *stream);
 int  fpohm_slim_jacobians_dev(fpohm_ctx *ctx, int64_t n, const int64_t *off_dev, const int32_t *col_dev, const double *vx_dev,
                               const double *vy_dev, const double *vz_dev, const double *uv_dev, double *Ji_dev, void *stream);
 int  fpohm_slim_weights_rotations_dev(fpohm_ctx *ctx, const double *Ji_dev, int64_t n, int32_t energy, double exp_factor, double *W_dev,

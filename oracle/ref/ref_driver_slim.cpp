@@ -10,6 +10,7 @@ void compute_jacobians(SLIMData &s, const Eigen::MatrixXd &uv);
 void update_weights_and_closest_rotations(SLIMData &s, const Eigen::MatrixXd &V, const Eigen::MatrixXi &F, Eigen::MatrixXd &uv);
 double compute_energy_with_jacobians(SLIMData &s, const Eigen::MatrixXd &V, const Eigen::MatrixXi &F, const Eigen::MatrixXd &Ji,
                                      Eigen::MatrixXd &uv, Eigen::VectorXd &areas);
+void buildRhs(SLIMData &s, const Eigen::SparseMatrix<double> &At);
 
 namespace {
 void size_tet_data(SLIMData &s, int64_t n, int energy, double exp_factor) {
@@ -82,6 +83,23 @@ double ref_slim_max_step(const double *uv, int64_t nv, const int32_t *T, int64_t
 	for (int64_t i = 0; i < n; ++i) for (int c = 0; c < 4; ++c) F(i, c) = T[4 * i + c];
 	if (roots) for (int64_t i = 0; i < n; ++i) roots[i] = igl::flip_avoiding::get_min_pos_root_3D(U, F, D, (int)i);
 	return igl::flip_avoiding::compute_max_step_from_singularities(U, F, D);
+}
+
+
+// per-element part of buildRhs (slim_m.cpp:1044-1093): with At = identity, unit weights and proximal_p = 0 the function returns f_rhs itself
+void ref_slim_rhs_terms(const double *W, const double *Ri, int64_t n, double *f_rhs) {
+	SLIMData s;
+	size_tet_data(s, n, 0, 0);
+	Eigen::VectorXd *w[9] = {&s.W_11, &s.W_12, &s.W_13, &s.W_21, &s.W_22, &s.W_23, &s.W_31, &s.W_32, &s.W_33};
+	for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) { (*w[k])(i) = W[9 * i + k]; s.Ri(i, k) = Ri[9 * i + k]; }
+	s.v_n = 1; s.V_o = Eigen::MatrixXd::Zero(1, 3); s.proximal_p = 0;
+	s.WGL_M = Eigen::VectorXd::Ones(9 * n);
+	Eigen::SparseMatrix<double> At((int)(9 * n), (int)(9 * n));
+	At.setIdentity();
+	// rhs has dim * v_n + ... entries in the real pipeline; here At is square, so rhs = f_rhs + 0 * uv_flat needs equal sizes
+	s.v_n = (int)(3 * n); s.V_o = Eigen::MatrixXd::Zero(3 * n, 3);
+	buildRhs(s, At);
+	for (int64_t i = 0; i < 9 * n; ++i) f_rhs[i] = s.rhs(i);
 }
 
 }

@@ -422,3 +422,10 @@ def slim_max_step(uv, T, d):
     lib().ref_slim_max_step.restype = C.c_double
     m = lib().ref_slim_max_step(_p(uv), C.c_int64(len(uv)), _p(T), C.c_int64(len(T)), _p(d), _p(roots))
     return float(m), roots
+
+
+def slim_rhs_terms(W, Ri):
+    """per-element part of buildRhs (slim_m.cpp:1061-1083), through the reference function with At = I."""
+    W = _f64(W).reshape(-1, 9); Ri = _f64(Ri).reshape(-1, 9); f = np.zeros(9 * len(W))
+    lib().ref_slim_rhs_terms(_p(W), _p(Ri), C.c_int64(len(W)), _p(f))
+    return f

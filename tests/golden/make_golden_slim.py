@@ -38,6 +38,7 @@ for k, sc in enumerate((0.02, 0.2, 2.0)):
     d = rng.normal(0, sc, Vb.shape)
     m, r = R.slim_max_step(Vb, Tb, d)
     G[f"step{k}_d"] = d; G[f"step{k}_max"] = np.float64(m); G[f"step{k}_roots"] = r
+G["rhs_terms"] = R.slim_rhs_terms(G["SYMMETRIC_DIRICHLET_W"], G["SYMMETRIC_DIRICHLET_Ri"])      # buildRhs with At = I (slim_m.cpp:1044-1093)
 out = Path(__file__).resolve().parent / "golden_slim_v1.npz"
 np.savez_compressed(out, **G)
 print(f"wrote {out} ({out.stat().st_size / 1e3:.0f} kB, {len(G)} arrays)")

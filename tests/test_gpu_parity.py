@@ -877,3 +877,12 @@ def test_clean_hex_mesh_refuses_bad_ids(fp, ctx):
     with pytest.raises(fp.FpohmError, match="out of range"):
         fp.clean_hex_mesh(ctx, m, V, bad)
     m.close()
+
+
+def test_slim_rhs_terms_bit_exact(fp, ctx, ref):
+    """per-element part of buildRhs (slim_m.cpp:1061-1083) against the reference function run with At = I: same IEEE operations."""
+    J = _slim_jacobian_set(5000, 41)
+    W, Ri = fp.slim_weights_rotations(ctx, J, "SYMMETRIC_DIRICHLET")
+    ok = np.isfinite(W).all(1) & np.isfinite(Ri).all(1)
+    got = fp.slim_rhs_terms(ctx, W[ok], Ri[ok]); want = ref.slim_rhs_terms(W[ok], Ri[ok])
+    assert np.array_equal(got, want)

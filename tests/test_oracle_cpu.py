@@ -376,6 +376,11 @@ def test_port_slim_max_step_vs_golden(port):
         assert (np.abs(r[fin] - want[fin]) <= 1e-8 * np.abs(want[fin])).all() and abs(m - float(g[f"step{k}_max"])) <= 1e-9 * m
 
 
+def test_port_slim_rhs_terms_vs_golden(port):
+    g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
+    assert np.array_equal(port.slim_rhs_terms(g["SYMMETRIC_DIRICHLET_W"], g["SYMMETRIC_DIRICHLET_Ri"]), g["rhs_terms"])      # same IEEE operations
+
+
 def test_golden_slim_matches_live_reference(ref):
     g = dict(np.load(ROOT / "tests" / "golden" / "golden_slim_v1.npz"))
     W, Ri = ref.slim_weights_rotations(g["J"], "SYMMETRIC_DIRICHLET", float(g["exp_factor"]))
