@@ -150,7 +150,29 @@ def run_reference(args):
             "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "also": {"octree_build_ms": build_ms, "octree_build_note": "OctreeGrid::subdivide + hex export, serial (no parallel form exists)",
                      "jacobian_hexes_per_s": len(H) / jac_s}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner when NCCL_DEBUG is set by the
+    environment or /etc/nccl.conf), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -162,6 +184,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the 1024^3 voxel / octree entry of 'also'")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -442,7 +465,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_reference(V, F, P)
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
