@@ -347,9 +347,32 @@ __device__ __forceinline__ int32_t igl_tie_winner(const QNode *__restrict__ node
 	return box_ext_sqdist(mn, mx, p) <= dmin ? win : -1;
 }
 
+// Sign finalisation shared by every kernel of the wide-packet pipeline (FPOHM_CP_MODE=2): whoever settles a query also runs
+// pseudonormal_test on it, so P / I / C are not read back by a separate pass.  S holds the SQUARED distance until then.
+struct SignArgs {
+	const double *V; const int32_t *F; int64_t nF;
+	const double *FN, *VN, *EN; const int32_t *EMAP;
+	double *N;          // may be null
+	int enabled;        // 0: unsigned query (S stays the squared distance) or the separate pseudonormal pass does it
+};
+__device__ __forceinline__ void finalize_sign(const SignArgs &sa, int64_t i, const V3 &p, int32_t f, const V3 &c, double d2,
+                                              double *__restrict__ S)
+{
+	if (!sa.enabled) return;
+	V3 n = {0, 0, 0};
+	if (f < 0) {
+		if (S) S[i] = CUDART_NAN;
+	} else {
+		const double s = pseudonormal(sa.V, sa.F, sa.nF, sa.FN, sa.VN, sa.EN, sa.EMAP, p, f, c, n);
+		if (S) S[i] = s * sqrt(d2);
+	}
+	if (sa.N) { sa.N[3 * i] = n.x; sa.N[3 * i + 1] = n.y; sa.N[3 * i + 2] = n.z; }
+}
+
 // work-list entry codes
 #define TODO_WALK 1      /* minimum is exact, near-ties need igl's tie-break */
 #define TODO_SEARCH 2    /* S holds an upper bound (or +inf): search not finished */
+#define TODO_HEAVY 3     /* as TODO_SEARCH, straight to the warp-per-query kernel */
 
 // ---- K1 ---------------------------------------------------------------------------------------------------------
 // Register diet (ncu: at 72 registers the first version re-loaded five spilled query coordinates from local memory in
@@ -512,6 +535,683 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 	}
 }
 
+// ---- K1, wide form (default, FPOHM_CP_MODE=2) --------------------------------------------------------------------
+// ncu on the binary packet walk above: 70 % of the issue slots busy, 2.93 G warp instructions = 101.6 node visits x 112
+// instructions + 40.7 warp-uniform fp64 leaf evaluations per packet, at 25 of 32 lanes.  A packet's lanes agree on almost every
+// box of the upper tree, so testing 2 boxes per step with 32 lanes each spends 32 lanes on one bit of information.  This
+// kernel turns the upper tree around:
+//   phase A  BOX-parallel: lane (j, c) of the warp tests child c of the j-th of the four wide nodes on top of the stack
+//            (32 boxes per step, one 32-byte WChild entry per lane) against the PACKET — the box of the lanes' float queries
+//            and T = the largest lane threshold.  box-box gap <= every lane's point-box gap and T >= every lane's thr, so
+//            nothing a lane could want is dropped.  Wanted inner nodes go back on the stack, wanted clusters (nodes of <= 8
+//            facets) and stray facets into a candidate list.
+//   phase B  QUERY-parallel: per candidate cluster one box test per lane with the lane's OWN threshold (this is what keeps
+//            far-away packets cheap: the union of the lanes' balls is far smaller than any ball around the packet), then the
+//            8 facet boxes; the facets a lane wants become bits of a per-lane mask over up to 4 staged clusters.
+//   phase C  exact fp64 evaluation, each lane walking its OWN mask (nearest box first, filter re-checked as the bound drops):
+//            the step count is the longest lane's list, not the union of all lists as in the warp-uniform leaf steps.
+// A greedy descent for the packet centre finds one facet; every lane's exact distance to it seeds thr / T.
+// Bookkeeping of the minimum, the near-tie count and the exact ties is the old one (`near`, `nt`, tie slots), so the
+// completion kernels and igl's tie-break are untouched.  Results are bit-identical to the binary walk (scripts/cp_ab.py).
+#define WK_STACK 160
+#define WK_CAND 64
+#define PK_CAND 48        /* pair form: candidates per round */
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ float boxgap2_low(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                             float qlx, float qly, float qlz, float qhx, float qhy, float qhz) {
+	const float gx = fmaxf(fmaxf(__fsub_rd(lox, qhx), __fsub_rd(qlx, hix)), 0.f);
+	const float gy = fmaxf(fmaxf(__fsub_rd(loy, qhy), __fsub_rd(qly, hiy)), 0.f);
+	const float gz = fmaxf(fmaxf(__fsub_rd(loz, qhz), __fsub_rd(qlz, hiz)), 0.f);
+	return __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
+}
+
+struct WideStage { uint4 e[4][16]; };      // four staged clusters, 8 entries of two uint4 each
+
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+cp_wide_kernel(const WNode *__restrict__ wnodes, const double *__restrict__ tri,
+               const double *__restrict__ P, int64_t np, const uint32_t *__restrict__ perm,
+               double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa,
+               int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties, int32_t *__restrict__ todo_count, double *__restrict__ stats)
+{
+	__shared__ int32_t s_stack[4][WK_STACK];
+	__shared__ int32_t s_cid[4][WK_CAND];
+	__shared__ float s_cbox[4][6][WK_CAND];
+	__shared__ WideStage s_stage[4];
+	__shared__ int32_t s_tie[4][PK_TIES][32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
+	int32_t *stk = s_stack[warp];
+	int32_t *cid = s_cid[warp];
+	float (*cbox)[WK_CAND] = s_cbox[warp];
+	uint4 (*stage)[16] = s_stage[warp].e;
+	int32_t *ties = &s_tie[warp][0][lane];
+	const uint4 *wn4 = reinterpret_cast<const uint4 *>(wnodes);
+	const int64_t nwarps = (int64_t)gridDim.x * 4;
+	for (int64_t w = blockIdx.x * 4ll + warp; w * 32 < np; w += nwarps) {
+		const int64_t slot = w * 32 + lane;
+		const bool in_range = slot < np;
+		const int64_t i = in_range ? (perm ? (int64_t)perm[slot] : slot) : 0;
+		const V3 p = ld3(P + 3 * i);
+		const bool valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+		const float pfx = (float)p.x, pfy = (float)p.y, pfz = (float)p.z;
+		float delta;
+		{
+			const double ex = p.x - (double)pfx, ey = p.y - (double)pfy, ez = p.z - (double)pfz;
+			delta = __double2float_ru(sqrt(ex * ex + ey * ey + ez * ez) * 1.0000001);
+		}
+		// packet box over the searching lanes
+		const float qlx = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfx) : 0x7fffffff)), qhx = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfx) : (int)0x80000000));
+		const float qly = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfy) : 0x7fffffff)), qhy = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfy) : (int)0x80000000));
+		const float qlz = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfz) : 0x7fffffff)), qhz = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfz) : (int)0x80000000));
+		double best = CUDART_INF;
+		float thr = valid ? CUDART_INF_F : -1.f;        // an idle lane never wants anything (bounds are >= 0)
+		int32_t bf = -1;
+		V3 bc = {0, 0, 0};
+		int near = 0, nt = 0;
+		int st_steps = 0, st_cand = 0, st_staged = 0, st_iters = 0, st_evals = 0;
+		long long t0 = 0;
+		if (STATS) t0 = clock64();
+		auto exact = [&](int32_t prim) {
+			const double *t = tri + 9 * (int64_t)prim;
+			const V3 q = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6));
+			const double d = sqnorm(sub(p, q));
+			if (d < best) {
+				near = (d + d * PK_EPS_TIE < best) ? 1 : near + 1;
+				nt = 0; bf = prim; bc = q;
+				best = d;
+				thr = filter_threshold(d, delta);
+			} else if (d <= best + best * PK_EPS_TIE) {
+				++near;
+				if (d == best) { if (nt < PK_TIES) ties[32 * nt] = prim; ++nt; }
+			}
+			if (STATS) ++st_evals;
+		};
+		bool bail = false;
+		int32_t seed = -1;
+		if (__any_sync(FULL, valid)) {
+			// ---- seed: greedy descent for the packet centre (all four lane groups do the same work) ----
+			{
+				const float cx = 0.5f * qlx + 0.5f * qhx, cy = 0.5f * qly + 0.5f * qhy, cz = 0.5f * qlz + 0.5f * qhz;
+				const int c = lane & 7;
+				int32_t nd = 0;
+				for (int guard = 0; guard < 64; ++guard) {
+					const uint4 a = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2), b = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2 + 1);
+					const float lox = __uint_as_float(a.x), loy = __uint_as_float(a.y), loz = __uint_as_float(a.z);
+					const float hix = __uint_as_float(a.w), hiy = __uint_as_float(b.x), hiz = __uint_as_float(b.y);
+					const int32_t ch = (int32_t)b.z;
+					const bool ok = ch != WCHILD_EMPTY;
+					const float gap = gap2_low(lox, loy, loz, hix, hiy, hiz, cx, cy, cz);
+					const float mx = 0.5f * lox + 0.5f * hix - cx, my = 0.5f * loy + 0.5f * hiy - cy, mz = 0.5f * loz + 0.5f * hiz - cz;
+					const float cd = mx * mx + my * my + mz * mz;
+					const unsigned m0 = __ballot_sync(FULL, ok && gap == 0.f) & 0xffu;
+					float key = !ok ? CUDART_INF_F : (m0 ? (gap == 0.f ? cd : CUDART_INF_F) : gap);
+					int kc = c;
+#pragma unroll
+					for (int o = 1; o < 8; o <<= 1) {
+						const float ok2 = __shfl_xor_sync(FULL, key, o);
+						const int oc = __shfl_xor_sync(FULL, kc, o);
+						if (ok2 < key || (ok2 == key && oc < kc)) { key = ok2; kc = oc; }
+					}
+					const int32_t wch = __shfl_sync(FULL, ch, kc);
+					if (wch < 0) { seed = wch == WCHILD_EMPTY ? -1 : ~wch; break; }
+					nd = wch;
+				}
+			}
+			if (seed >= 0 && valid) exact(seed);
+			float T = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(thr, 0.f))));
+			// ---- main loop ----
+			int top = 1, ncand = 0;
+			if (lane == 0) stk[0] = 0;
+			__syncwarp();
+			for (;;) {
+				// phase A
+				while (top > 0 && ncand <= WK_CAND - 32) {
+					const int j = lane >> 3, c = lane & 7;
+					const int take = top < 4 ? top : 4;
+					const bool act = j < take;
+					const int32_t nd = act ? stk[top - 1 - j] : 0;
+					__syncwarp();
+					top -= take;
+					const uint4 a = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2), b = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2 + 1);
+					const float g = boxgap2_low(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+					                            __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y), qlx, qly, qlz, qhx, qhy, qhz);
+					const int32_t ch = (int32_t)b.z;
+					const bool want = act && ch != WCHILD_EMPTY && g <= T;
+					const bool to_stack = want && ch >= 0 && !(b.w & 1u);
+					const bool to_cand = want && !to_stack;
+					const unsigned mi = __ballot_sync(FULL, to_stack), mc = __ballot_sync(FULL, to_cand);
+					if (top + __popc(mi) > WK_STACK) { bail = true; break; }
+					if (to_stack) stk[top + __popc(mi & lt)] = ch;
+					top += __popc(mi);
+					if (to_cand) {
+						const int k = ncand + __popc(mc & lt);
+						cid[k] = ch;
+						cbox[0][k] = __uint_as_float(a.x); cbox[1][k] = __uint_as_float(a.y); cbox[2][k] = __uint_as_float(a.z);
+						cbox[3][k] = __uint_as_float(a.w); cbox[4][k] = __uint_as_float(b.x); cbox[5][k] = __uint_as_float(b.y);
+					}
+					ncand += __popc(mc);
+					if (STATS) ++st_steps;
+					__syncwarp();
+				}
+				if (bail || ncand == 0) break;
+				if (STATS) st_cand += ncand;
+				// phase B + C
+				int nst = 0;
+				unsigned mask = 0;
+				float bestg = CUDART_INF_F;
+				int bestbit = -1;
+				auto run_exact = [&]() {
+					bool first = true;
+					while (__any_sync(FULL, mask != 0)) {
+						if (mask) {
+							const int bit = (first && bestbit >= 0) ? bestbit : __ffs(mask) - 1;
+							mask &= ~(1u << bit);
+							const uint4 a = stage[bit >> 3][2 * (bit & 7)], b = stage[bit >> 3][2 * (bit & 7) + 1];
+							const int32_t prim = ~(int32_t)b.z;
+							if (prim != seed &&
+							    (first || gap2_low(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+							                       __uint_as_float(b.x), __uint_as_float(b.y), pfx, pfy, pfz) <= thr))
+								exact(prim);
+						}
+						first = false;
+						if (STATS) ++st_iters;
+					}
+					nst = 0; bestg = CUDART_INF_F; bestbit = -1;
+					__syncwarp();
+				};
+				for (int k = 0; k < ncand; ++k) {
+					const bool wk = gap2_low(cbox[0][k], cbox[1][k], cbox[2][k], cbox[3][k], cbox[4][k], cbox[5][k], pfx, pfy, pfz) <= thr;
+					if (!__any_sync(FULL, wk)) continue;
+					const int32_t id = cid[k];
+					if (id >= 0) {
+						reinterpret_cast<uint2 *>(stage[nst])[lane] = __ldg(reinterpret_cast<const uint2 *>(wnodes + id) + lane);
+					} else if (lane < 8) {       // a stray facet: a cluster of one
+						uint4 a, b;
+						if (lane == 0) {
+							a = make_uint4(__float_as_uint(cbox[0][k]), __float_as_uint(cbox[1][k]), __float_as_uint(cbox[2][k]), __float_as_uint(cbox[3][k]));
+							b = make_uint4(__float_as_uint(cbox[4][k]), __float_as_uint(cbox[5][k]), (uint32_t)id, 0u);
+						} else {
+							a = make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0xff800000u);
+							b = make_uint4(0xff800000u, 0xff800000u, (uint32_t)WCHILD_EMPTY, 0u);
+						}
+						stage[nst][2 * lane] = a; stage[nst][2 * lane + 1] = b;
+					}
+					__syncwarp();
+					if (wk) {
+#pragma unroll
+						for (int c = 0; c < 8; ++c) {
+							const uint4 a = stage[nst][2 * c], b = stage[nst][2 * c + 1];
+							const float gc = gap2_low(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+							                          __uint_as_float(b.x), __uint_as_float(b.y), pfx, pfy, pfz);
+							if ((int32_t)b.z != WCHILD_EMPTY && gc <= thr) {
+								mask |= 1u << (nst * 8 + c);
+								if (gc < bestg) { bestg = gc; bestbit = nst * 8 + c; }
+							}
+						}
+					}
+					if (STATS) ++st_staged;
+					if (++nst == 4) run_exact();
+				}
+				if (nst) run_exact();
+				ncand = 0;
+				T = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(thr, 0.f))));
+			}
+		}
+		// ---- epilogue ----
+		const int code = !valid ? 0 : (bail ? TODO_SEARCH : (near > 1 ? TODO_WALK : 0));
+		if (in_range) {
+			I[i] = bf;
+			C[3 * i] = bc.x; C[3 * i + 1] = bc.y; C[3 * i + 2] = bc.z;
+			if (code == 0 && sa.enabled) finalize_sign(sa, i, p, bf, bc, best, S);
+			else S[i] = best;
+		}
+		const unsigned mw = __ballot_sync(FULL, code == TODO_WALK), ms = __ballot_sync(FULL, code == TODO_SEARCH);
+		if (mw | ms) {
+			int bw = 0, bs = 0;
+			if (lane == 0) { if (mw) bw = atomicAdd(todo_count, __popc(mw)); if (ms) bs = atomicAdd(todo_count + 2, __popc(ms)); }
+			bw = __shfl_sync(FULL, bw, 0); bs = __shfl_sync(FULL, bs, 0);
+			if (code == TODO_WALK) {
+				const int sl = bw + __popc(mw & lt);
+				todo[sl] = (int32_t)i;
+				int32_t *tr = todo_ties + 4 * (int64_t)sl;
+				tr[0] = nt;
+				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? ties[32 * j] : -1;
+			} else if (code == TODO_SEARCH) {
+				todo[2 * np - 1 - (bs + __popc(ms & lt))] = (int32_t)i;
+			}
+		}
+		if (STATS && stats && in_range) {
+			double *o = stats + 3 * i;
+			o[0] = st_steps + 65536.0 * st_cand + 4294967296.0 * code;
+			o[1] = st_staged + 65536.0 * st_iters + 4294967296.0 * st_evals;
+			o[2] = (double)(clock64() - t0);
+		}
+		__syncwarp();
+	}
+}
+
+// ---- K1, pair form (default, FPOHM_CP_MODE=3) -----------------------------------------------------------------------
+// Counters of the wide form above on the bench workload: 9.5 box-parallel steps, 76 candidate clusters, 23 of them staged
+// and 61 exact-loop iterations per packet at 26 % lane occupancy — the fp64 evaluations (15.7 per lane, which is what a
+// bounding-box filter leaves over in ANY order) cost more than the whole tree walk, and a lane tests the 8 facet boxes of
+// every staged cluster although it wants a third of the clusters.  This form keeps phase A and changes the rest:
+//   * everything below the candidate list is PAIR-parallel: (lane, cluster) pairs are queued in shared memory and each
+//     lane of the warp takes one pair, whatever query it belongs to (Q1 -> 8 facet-box tests); the (lane, facet) pairs
+//     that pass are queued again (Q2) and refined the same way.  Occupancy no longer depends on the lanes agreeing.
+//   * an fp32 REFINE between the box test and the fp64 evaluation: Ericson's closest point in float on the float-rounded
+//     triangle gives a point q on it, hence an UPPER bound U >= D (distance to a point of the triangle, rounding slack
+//     added) that tightens the owner's threshold without any fp64 work, and a LOWER bound L <= D from the supporting
+//     plane through the triangle's vertices normal to p - q: for every x in the triangle n.(p - x) >= min_v n.(p - v).
+//     Both are rigorous whatever q is: the dot products are rounded in the safe direction and the subtraction error of
+//     p - v is bounded term by term, so a facet is only dropped when it is provably farther than the threshold.
+//     Facets with L^2 <= thr go to the owner's survivor list; only those reach igl's exact fp64 evaluation — the facets
+//     within ~1e-6 of the minimum instead of everything whose box is near.
+//   * the survivors are evaluated by their owner (nearest bound first), with the old bookkeeping of minimum, near-tie
+//     count and exact ties, so the completion kernels and igl's tie-break are untouched and results stay bit-identical.
+#define PQ_CAP 64
+#define PQ2_CAP 352        /* < 64 pending + 8 x 32 from one B2 iteration */
+#define SL_CAP 8
+#define PB_SLOTS 6
+struct RefineOut { float L2, U; };
+__device__ __forceinline__ RefineOut refine_f32(float px, float py, float pz, const float4 A, const float4 B, const float4 Cv, float slack_q)
+{
+	const float abx = B.x - A.x, aby = B.y - A.y, abz = B.z - A.z;
+	const float acx = Cv.x - A.x, acy = Cv.y - A.y, acz = Cv.z - A.z;
+	const float apx = px - A.x, apy = py - A.y, apz = pz - A.z;
+	const float bpx = px - B.x, bpy = py - B.y, bpz = pz - B.z;
+	const float cpx = px - Cv.x, cpy = py - Cv.y, cpz = pz - Cv.z;
+	const float d1 = abx * apx + aby * apy + abz * apz, d2 = acx * apx + acy * apy + acz * apz;
+	const float d3 = abx * bpx + aby * bpy + abz * bpz, d4 = acx * bpx + acy * bpy + acz * bpz;
+	const float d5 = abx * cpx + aby * cpy + abz * cpz, d6 = acx * cpx + acy * cpy + acz * cpz;
+	const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+	float v, w;                                          // q = A + v ab + w ac — a heuristic: the bounds below hold for any v, w
+	if (d1 <= 0.f && d2 <= 0.f) { v = 0.f; w = 0.f; }
+	else if (d3 >= 0.f && d4 <= d3) { v = 1.f; w = 0.f; }
+	else if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { v = __fdividef(d1, d1 - d3); w = 0.f; }
+	else if (d6 >= 0.f && d5 <= d6) { v = 0.f; w = 1.f; }
+	else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { v = 0.f; w = __fdividef(d2, d2 - d6); }
+	else if (va <= 0.f && d4 - d3 >= 0.f && d5 - d6 >= 0.f) { w = __fdividef(d4 - d3, (d4 - d3) + (d5 - d6)); v = 1.f - w; }
+	else { const float den = __fdividef(1.f, va + vb + vc); v = vb * den; w = vc * den; }
+	v = fminf(fmaxf(v, 0.f), 1.f);                       // (fmaxf drops a NaN)
+	w = fminf(fmaxf(w, 0.f), __fsub_rd(1.f, v));         // v + w <= 1 exactly: A + v ab + w ac is a point of the float triangle
+	const float qx = fmaf(w, acx, fmaf(v, abx, A.x)), qy = fmaf(w, acy, fmaf(v, aby, A.y)), qz = fmaf(w, acz, fmaf(v, abz, A.z));
+	const float nx = px - qx, ny = py - qy, nz = pz - qz;
+	const float nn = __fmaf_ru(nz, nz, __fmaf_ru(ny, ny, __fmul_ru(nx, nx)));
+	RefineOut r;
+	// |p - x*| <= |p - q| + |q - x*|, x* the exact combination: slack_q bounds the rounding of q, (1 + 2^-22) that of n
+	r.U = __fmaf_ru(__fsqrt_ru(nn), 1.0000005f, slack_q);
+	// min over the vertices of n.(p - v), each rounded down; 2^-23 |n|.|p - v| covers the rounding of p - v
+	const float anx = fabsf(nx), any = fabsf(ny), anz = fabsf(nz);
+	const float sa = __fmaf_rd(__fmaf_ru(anz, fabsf(apz), __fmaf_ru(any, fabsf(apy), __fmul_ru(anx, fabsf(apx)))), -1.1920929e-7f,
+	                           __fmaf_rd(nz, apz, __fmaf_rd(ny, apy, __fmul_rd(nx, apx))));
+	const float sb = __fmaf_rd(__fmaf_ru(anz, fabsf(bpz), __fmaf_ru(any, fabsf(bpy), __fmul_ru(anx, fabsf(bpx)))), -1.1920929e-7f,
+	                           __fmaf_rd(nz, bpz, __fmaf_rd(ny, bpy, __fmul_rd(nx, bpx))));
+	const float sc = __fmaf_rd(__fmaf_ru(anz, fabsf(cpz), __fmaf_ru(any, fabsf(cpy), __fmul_ru(anx, fabsf(cpx)))), -1.1920929e-7f,
+	                           __fmaf_rd(nz, cpz, __fmaf_rd(ny, cpy, __fmul_rd(nx, cpx))));
+	const float sm = fminf(sa, fminf(sb, sc));
+	r.L2 = sm > 0.f ? __fdiv_rd(__fmul_rd(sm, sm), nn) : 0.f;
+	return r;
+}
+// threshold on squared float-side lower bounds from an upper bound ub of D(pf, T_f): (ub + 2 dq)^2, up, widened by 2^-19
+__device__ __forceinline__ float threshold_from_upper(float ub, float dq) {
+	const float x = __fadd_ru(ub, __fadd_ru(dq, dq));
+	return __fmul_ru(__fmul_ru(x, x), 1.0000020f);
+}
+
+// per-warp shared state of cp_pair_kernel.  Everything is indexed as s.x[warp][...] on the __shared__ object itself: pointer
+// variables into it decayed to generic addresses (ncu: an S2R SR_CgaCtaId + LEA window computation in front of every access).
+struct PairShared {
+	int32_t stack[4][WK_STACK];
+	float4 cand[4][PK_CAND][2];                  // candidate: (lo.xyz, hi.x) (hi.y, hi.z, id bits, -)
+	float qx[4][32], qy[4][32], qz[4][32], dq[4][32];
+	unsigned thr[4][32];                         // float bits of the lane's threshold (>= 0, so unsigned order = float order)
+	int32_t q1[4][PQ_CAP];                       // (slot << 8) | owner
+	int32_t q2[4][PQ2_CAP];                      // (owner << 27) | facet
+	uint4 stage[4][PB_SLOTS][16];                // clusters of the (lane, cluster) pairs in flight: 8 entries of two uint4
+	int32_t slot_id[4][PB_SLOTS];
+	int32_t sprim[4][SL_CAP][32];
+	float sl2[4][SL_CAP][32];
+	int scnt[4][32];
+	int32_t tie[4][PK_TIES][32];
+	double best[4][32];                          // running exact minimum (phase C only: kept out of the registers of the hot loops)
+	float pbox[4][8];                            // packet box (phase A only)
+	unsigned dead[4];                            // lanes whose survivor list overflowed: they leave the packet for the heavy kernel
+};
+
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+cp_pair_kernel(const WNode *__restrict__ wnodes, const float4 *__restrict__ trif, const double *__restrict__ tri,
+               const double *__restrict__ P, int64_t np, const uint32_t *__restrict__ perm,
+               double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa, float eps_v, float slack_q,
+               int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties, int32_t *__restrict__ todo_count, int32_t *__restrict__ heavy,
+               int b3_budget, int c_budget, double *__restrict__ stats)
+{
+	__shared__ PairShared s;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
+	const uint4 *wn4 = reinterpret_cast<const uint4 *>(wnodes);
+	// Persistent warps: packet costs spread over two orders of magnitude (p50 85 k cycles, p99 455 k), and a CTA that owns four
+	// fixed packets keeps its slots until the slowest one is done.  Every warp fetches its next packet from a global counter.
+	for (;;) {
+		int64_t w = 0;
+		if (lane == 0) w = atomicAdd(todo_count + 4, 1);
+		w = __shfl_sync(FULL, w, 0);
+		if (w * 32 >= np) break;
+		const int64_t slot = w * 32 + lane;
+		const bool in_range = slot < np;
+		const int64_t i = in_range ? (perm ? (int64_t)perm[slot] : slot) : 0;
+		// (the fp64 query is re-read where igl's arithmetic needs it; between those places only its float image is live)
+		float pfx, pfy, pfz, dq;
+		bool valid;
+		{
+			const V3 p = ld3(P + 3 * i);
+			valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+			pfx = (float)p.x; pfy = (float)p.y; pfz = (float)p.z;
+			const double ex = p.x - (double)pfx, ey = p.y - (double)pfy, ez = p.z - (double)pfz;
+			dq = __fadd_ru(__double2float_ru(sqrt(ex * ex + ey * ey + ez * ez) * 1.0000001), eps_v);
+		}
+		// (opaque to the optimiser: at 80 registers ptxas kept the fp64 query alive and re-converted it in front of every box test)
+		asm volatile("" : "+f"(pfx), "+f"(pfy), "+f"(pfz), "+f"(dq));
+		s.qx[warp][lane] = pfx; s.qy[warp][lane] = pfy; s.qz[warp][lane] = pfz; s.dq[warp][lane] = dq;
+		s.scnt[warp][lane] = 0;
+		if (lane == 0) s.dead[warp] = 0u;
+		{
+			const float qlx = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfx) : 0x7fffffff)), qhx = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfx) : (int)0x80000000));
+			const float qly = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfy) : 0x7fffffff)), qhy = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfy) : (int)0x80000000));
+			const float qlz = ord2f(__reduce_min_sync(FULL, valid ? f2ord(pfz) : 0x7fffffff)), qhz = ord2f(__reduce_max_sync(FULL, valid ? f2ord(pfz) : (int)0x80000000));
+			if (lane == 0) { s.pbox[warp][0] = qlx; s.pbox[warp][1] = qly; s.pbox[warp][2] = qlz; s.pbox[warp][3] = qhx; s.pbox[warp][4] = qhy; s.pbox[warp][5] = qhz; }
+		}
+		s.best[warp][lane] = CUDART_INF;
+		int32_t bf = -1;
+		int near = 0, nt = 0;
+		int st_steps = 0, st_cand = 0, st_p1 = 0, st_p2 = 0, st_iters = 0, st_evals = 0;
+		long long t0 = 0;
+		if (STATS) t0 = clock64();
+		bool bail = false;
+		// ---- seed: every lane walks down the wide tree for ITS OWN query, always into the child whose box is nearest
+		// (ties: nearest box centre), and takes the fp32 upper bound to the facet it ends at as its first threshold.  One facet
+		// for the whole packet left the far lanes with thresholds of the packet's diameter, and the candidate funnel below is
+		// quadratic in that (counters on the C3 mesh: 264 candidate clusters per packet before, against ~40 facets it spans). ----
+		{
+			float thr0 = 0.f;
+			if (valid) {
+				int32_t nd = 0;
+				thr0 = CUDART_INF_F;
+				for (int guard = 0; guard < 48; ++guard) {
+					float bk = CUDART_INF_F, bcd = CUDART_INF_F;
+					int32_t bch = WCHILD_EMPTY;
+#pragma unroll
+					for (int c = 0; c < 8; ++c) {
+						const uint4 a = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2), b = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2 + 1);
+						const float lox = __uint_as_float(a.x), loy = __uint_as_float(a.y), loz = __uint_as_float(a.z);
+						const float hix = __uint_as_float(a.w), hiy = __uint_as_float(b.x), hiz = __uint_as_float(b.y);
+						const float gap = gap2_low(lox, loy, loz, hix, hiy, hiz, pfx, pfy, pfz);
+						const float mx = 0.5f * lox + 0.5f * hix - pfx, my = 0.5f * loy + 0.5f * hiy - pfy, mz = 0.5f * loz + 0.5f * hiz - pfz;
+						const float cd = mx * mx + my * my + mz * mz;
+						if ((int32_t)b.z != WCHILD_EMPTY && (gap < bk || (gap == bk && cd < bcd))) { bk = gap; bcd = cd; bch = (int32_t)b.z; }
+					}
+					if (bch < 0) {
+						if (bch != WCHILD_EMPTY) {
+							const int64_t f = ~bch;
+							const RefineOut r = refine_f32(pfx, pfy, pfz, __ldg(trif + 3 * f), __ldg(trif + 3 * f + 1), __ldg(trif + 3 * f + 2), slack_q);
+							thr0 = threshold_from_upper(r.U, dq);
+						}
+						break;
+					}
+					nd = bch;
+				}
+			}
+			s.thr[warp][lane] = __float_as_uint(thr0);
+		}
+		__syncwarp();
+		if (__any_sync(FULL, valid)) {
+			float T = __uint_as_float(__reduce_max_sync(FULL, valid ? s.thr[warp][lane] : 0u));
+			int top = 1, ncand = 0, n1 = 0, n2 = 0, nslots = 0, b3_left = b3_budget, c_left = c_budget, cpass_left = 2 * c_budget;
+			unsigned dead = 0u;
+			if (lane == 0) s.stack[warp][0] = 0;
+			__syncwarp();
+			// Every stage below exists ONCE in the code (the first version inlined them at each call site: 9 200 instructions,
+			// spills, instruction-cache misses); the loops are arranged so that one site serves every trigger.
+			for (;;) {
+				// ---- phase A: box-parallel expansion of the upper tree against the packet box and the largest threshold ----
+				while (top > 0 && ncand <= PK_CAND - 32) {
+					const int j = lane >> 3, c = lane & 7;
+					const int take = top < 4 ? top : 4;
+					const bool act = j < take;
+					const int32_t nd = s.stack[warp][act ? top - 1 - j : 0];
+					__syncwarp();
+					top -= take;
+					const uint4 a = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2), b = __ldg(wn4 + ((int64_t)nd * 8 + c) * 2 + 1);
+					const float g = boxgap2_low(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+					                            __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y),
+					                            s.pbox[warp][0], s.pbox[warp][1], s.pbox[warp][2], s.pbox[warp][3], s.pbox[warp][4], s.pbox[warp][5]);
+					const int32_t ch = (int32_t)b.z;
+					// Everything that passes goes through the per-lane test of phase B1, inner nodes included: the packet-level
+					// test (box against box, largest threshold) is loose when the packet is large or its lanes are at different
+					// distances — far-away packets kept whole shells of the mesh alive (55 ns per far query before, 15 in the old walk).
+					const bool to_cand = act && ch != WCHILD_EMPTY && g <= T;
+					const unsigned mc = __ballot_sync(FULL, to_cand);
+					if (to_cand) {
+						const int k = ncand + __popc(mc & lt);
+						s.cand[warp][k][0] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+						s.cand[warp][k][1] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __int_as_float(ch), (ch >= 0 && !(b.w & 1u)) ? 1.f : 0.f);
+					}
+					ncand += __popc(mc);
+					if (STATS) ++st_steps;
+					__syncwarp();
+				}
+				if (bail) break;
+				const bool last = ncand == 0;                      // the stack is empty too: one more pass drains the queues
+				if (STATS) st_cand += ncand;
+				for (int k = 0; k <= ncand; ++k) {
+					const bool fin = k == ncand;
+					// ---- phase B1: candidate box against every lane's own threshold -> (lane, cluster) pairs ----
+					if (!fin) {
+						const float4 ca = s.cand[warp][k][0], cb = s.cand[warp][k][1];
+						const bool wk = valid && gap2_low(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, pfx, pfy, pfz) <= __uint_as_float(s.thr[warp][lane]) && !((dead >> lane) & 1u);
+						const unsigned m = __ballot_sync(FULL, wk);
+						if (!m) continue;
+						const int32_t id = __float_as_int(cb.z);
+						if (cb.w != 0.f) {                         // an inner node some lane wants: back on the stack
+							if (top >= WK_STACK) { bail = true; break; }
+							if (lane == 0) s.stack[warp][top] = id;
+							++top;
+							continue;
+						}
+						if (id < 0) {                              // a stray facet: its box has just been tested
+							if (wk) s.q2[warp][n2 + __popc(m & lt)] = (lane << 27) | ~id;
+							n2 += __popc(m);
+						} else {
+							if (wk) s.q1[warp][n1 + __popc(m & lt)] = (nslots << 8) | lane;
+							if (lane == 0) s.slot_id[warp][nslots] = id;
+							n1 += __popc(m);
+							++nslots;
+						}
+						__syncwarp();
+						if (n1 < 32 && nslots < PB_SLOTS && n2 < 32) continue;
+					}
+					// ---- flush: bring the queued pairs' clusters into shared memory, every load in flight at once ----
+					if (n1 > 0) {
+						uint2 r[PB_SLOTS];
+#pragma unroll
+						for (int sl = 0; sl < PB_SLOTS; ++sl)
+							if (sl < nslots) r[sl] = __ldg(reinterpret_cast<const uint2 *>(wnodes + s.slot_id[warp][sl]) + lane);
+#pragma unroll
+						for (int sl = 0; sl < PB_SLOTS; ++sl)
+							if (sl < nslots) reinterpret_cast<uint2 *>(s.stage[warp][sl])[lane] = r[sl];
+						__syncwarp();
+					}
+					for (;;) {
+						// ---- phase B2: one (owner, cluster) pair per lane, the 8 facet boxes against the owner's threshold ----
+						if (n1 > 0 && n2 < 64) {
+							const int cnt = n1 < 32 ? n1 : 32;
+							const bool has = lane < cnt;
+							const int32_t e = s.q1[warp][has ? n1 - cnt + lane : 0];
+							n1 -= cnt;
+							const int owner = e & 31, sl = e >> 8;
+							const float ox = s.qx[warp][owner], oy = s.qy[warp][owner], oz = s.qz[warp][owner];
+							const float othr = (has && !((dead >> owner) & 1u)) ? __uint_as_float(s.thr[warp][owner]) : -1.f;   // an idle lane passes nothing (bounds are >= 0)
+							const int32_t obits = owner << 27;
+							if (STATS) st_p1 += cnt;
+#pragma unroll
+							for (int c = 0; c < 8; ++c) {
+								const uint4 a = s.stage[warp][sl][2 * c], b = s.stage[warp][sl][2 * c + 1];
+								// (an empty slot has box (+inf, -inf): its bound is +inf and never passes)
+								const bool pass = gap2_low(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+								                           __uint_as_float(b.x), __uint_as_float(b.y), ox, oy, oz) <= othr;
+								const unsigned m = __ballot_sync(FULL, pass);
+								if (pass) s.q2[warp][n2 + __popc(m & lt)] = obits | ~(int32_t)b.z;
+								n2 += __popc(m);
+							}
+							__syncwarp();
+						}
+						// ---- phase B3: one (owner, facet) pair per lane — fp32 refine, tighten the owner's threshold, keep survivors ----
+						const bool more = n2 >= 32 || (fin && n1 == 0 && n2 > 0);
+						if (more) {
+							const int cnt = n2 < 32 ? n2 : 32;
+							const bool has = lane < cnt;
+							const int32_t ent = s.q2[warp][has ? n2 - cnt + lane : 0];
+							n2 -= cnt;
+							bool o = false;
+							if (has && !((dead >> (int)((uint32_t)ent >> 27)) & 1u)) {
+								const int owner = (int)((uint32_t)ent >> 27);
+								const int32_t prim = ent & 0x07ffffff;
+								const float4 A = __ldg(trif + 3 * (int64_t)prim), B = __ldg(trif + 3 * (int64_t)prim + 1), Cv = __ldg(trif + 3 * (int64_t)prim + 2);
+								const RefineOut r = refine_f32(s.qx[warp][owner], s.qy[warp][owner], s.qz[warp][owner], A, B, Cv, slack_q);
+								const float tu = threshold_from_upper(r.U, s.dq[warp][owner]);
+								const float told = __uint_as_float(atomicMin(&s.thr[warp][owner], __float_as_uint(tu)));
+								if (r.L2 <= fminf(told, tu)) {
+									const int pos = atomicAdd(&s.scnt[warp][owner], 1);
+									if (pos < SL_CAP) { s.sprim[warp][pos][owner] = prim; s.sl2[warp][pos][owner] = r.L2; }
+									else atomicOr(&s.dead[warp], 1u << owner);
+								}
+							}
+							if (STATS) st_p2 += cnt;
+							__syncwarp();
+							// More near-minimal facets than a list holds (a query on the axis of a bore sees thousands): that lane is
+							// finished by the warp-per-query heavy kernel; here it stops wanting anything, so the packet's other lanes
+							// are not held up (one such packet ran for 2.8 ms of a 4.4 ms launch).
+							dead = s.dead[warp];
+							if (--b3_left < 0) bail = true;
+						}
+						// ---- phase C: every lane walks its own survivor list, smallest lower bound first: igl's exact fp64 evaluation ----
+						const bool idle = !more && n1 == 0;
+						int mycnt = s.scnt[warp][lane];
+						const bool final_c = idle && fin && last;
+						if (!final_c && __any_sync(FULL, mycnt >= SL_CAP / 2)) {
+							// a list that fills up mostly holds facets that passed an EARLIER threshold: drop what the current one
+							// excludes before spending fp64 on it
+							const float th = __uint_as_float(s.thr[warp][lane]);
+							const int c0 = min(mycnt, SL_CAP);
+							int c1 = 0;
+							for (int j = 0; j < c0; ++j) {
+								const float l = s.sl2[warp][j][lane];
+								if (l <= th) { if (c1 != j) { s.sl2[warp][c1][lane] = l; s.sprim[warp][c1][lane] = s.sprim[warp][j][lane]; } ++c1; }
+							}
+							if (mycnt <= SL_CAP) { mycnt = c1; s.scnt[warp][lane] = c1; }
+							__syncwarp();
+						}
+						if (__any_sync(FULL, mycnt >= SL_CAP / 2) || (final_c && __any_sync(FULL, mycnt > 0))) {
+							const int cnt = min(mycnt, SL_CAP);
+							if (cnt > 1) {
+								int jm = 0; float lm = s.sl2[warp][0][lane];
+								for (int j = 1; j < cnt; ++j) { const float l = s.sl2[warp][j][lane]; if (l < lm) { lm = l; jm = j; } }
+								if (jm) {
+									const int32_t tp = s.sprim[warp][0][lane]; s.sprim[warp][0][lane] = s.sprim[warp][jm][lane]; s.sprim[warp][jm][lane] = tp;
+									s.sl2[warp][jm][lane] = s.sl2[warp][0][lane]; s.sl2[warp][0][lane] = lm;
+								}
+							}
+							float mythr = __uint_as_float(s.thr[warp][lane]);
+							const V3 p = ld3(P + 3 * i);
+							double best = s.best[warp][lane];
+							for (int j = 0; __any_sync(FULL, j < cnt); ++j) {
+								if (j < cnt && s.sl2[warp][j][lane] <= mythr) {
+									const int32_t prim = s.sprim[warp][j][lane];
+									const double *t = tri + 9 * (int64_t)prim;
+									const V3 q = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6));
+									const double d = sqnorm(sub(p, q));
+									if (d < best) {
+										near = (d + d * PK_EPS_TIE < best) ? 1 : near + 1;
+										nt = 0; bf = prim;
+										best = d;
+										mythr = fminf(mythr, filter_threshold(d, dq));
+									} else if (d <= best + best * PK_EPS_TIE) {
+										++near;
+										if (d == best) { if (nt < PK_TIES) s.tie[warp][nt][lane] = prim; ++nt; }
+									}
+									if (STATS) ++st_evals;
+								}
+								if (STATS) ++st_iters;
+							}
+							// a lane that has needed this many exact evaluations sits among a crowd of near-minimal facets (p99 is 11)
+							c_left -= cnt;
+							if (c_left < 0) atomicOr(&s.dead[warp], 1u << lane);
+							if (--cpass_left < 0) bail = true;
+							s.thr[warp][lane] = __float_as_uint(mythr);
+							s.best[warp][lane] = best;
+							s.scnt[warp][lane] = 0;
+							__syncwarp();
+							dead = s.dead[warp];
+						}
+						if (idle || bail) break;
+					}
+					nslots = 0;
+					if (bail) break;
+				}
+				if (last || bail) break;
+				ncand = 0;
+				T = __uint_as_float(__reduce_max_sync(FULL, valid ? s.thr[warp][lane] : 0u));
+			}
+			if ((dead >> lane) & 1u) near = -1;
+		}
+		// ---- epilogue ----
+		// a packet that ran out of budget holds queries with very many near-minimal facets: the per-lane search kernel would chew on
+		// each of them for a millisecond (its leaf evaluations are not budgeted), the warp-per-query kernel takes them in its stride
+		const int code = !valid ? 0 : ((near < 0 || bail) ? TODO_HEAVY : (near > 1 ? TODO_WALK : 0));
+		if (in_range) {
+			const V3 p = ld3(P + 3 * i);
+			const double best = s.best[warp][lane];
+			V3 bc = {0, 0, 0};
+			if (bf >= 0) { const double *t = tri + 9 * (int64_t)bf; bc = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6)); }
+			I[i] = bf;
+			C[3 * i] = bc.x; C[3 * i + 1] = bc.y; C[3 * i + 2] = bc.z;
+			if (code == 0 && sa.enabled) finalize_sign(sa, i, p, bf, bc, best, S);
+			else S[i] = best;
+		}
+		const unsigned mw = __ballot_sync(FULL, code == TODO_WALK), ms = __ballot_sync(FULL, code == TODO_SEARCH), mh = __ballot_sync(FULL, code == TODO_HEAVY);
+		if (mw | ms | mh) {
+			int bw = 0, bs = 0, bh = 0;
+			if (lane == 0) {
+				if (mw) bw = atomicAdd(todo_count, __popc(mw));
+				if (ms) bs = atomicAdd(todo_count + 2, __popc(ms));
+				if (mh) bh = atomicAdd(todo_count + 1, __popc(mh));
+			}
+			bw = __shfl_sync(FULL, bw, 0); bs = __shfl_sync(FULL, bs, 0); bh = __shfl_sync(FULL, bh, 0);
+			if (code == TODO_WALK) {
+				const int sl = bw + __popc(mw & lt);
+				todo[sl] = (int32_t)i;
+				int32_t *tr = todo_ties + 4 * (int64_t)sl;
+				tr[0] = nt;
+				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? s.tie[warp][j][lane] : -1;
+			} else if (code == TODO_SEARCH) {
+				todo[2 * np - 1 - (bs + __popc(ms & lt))] = (int32_t)i;
+			} else if (code == TODO_HEAVY) {
+				heavy[bh + __popc(mh & lt)] = (int32_t)i;
+			}
+		}
+		if (STATS && stats && in_range) {
+			double *o = stats + 3 * i;
+			o[0] = st_steps + 65536.0 * st_cand + 4294967296.0 * code;
+			o[1] = st_p1 + 65536.0 * st_iters + 4294967296.0 * st_evals;
+			o[2] = st_p2 + 1048576.0 * (double)((clock64() - t0) >> 4);
+		}
+		__syncwarp();
+	}
+}
+
+
 // igl-order walk (as `traverse`) that additionally skips every box farther than `limit`, stops as soon as it holds a
 // facet at distance `dmin` (the exact minimum over all facets) and gives up after `budget` node visits (returns false).
 __device__ __forceinline__ bool traverse_limited(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri,
@@ -558,7 +1258,7 @@ __global__ void __launch_bounds__(128)
 cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_ties,
               int32_t *__restrict__ counters, double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
-              int32_t *__restrict__ heavy, int walk_budget)
+              int32_t *__restrict__ heavy, int walk_budget, SignArgs sa)
 {
 	const int n_todo = counters[0];
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_todo; t += gridDim.x * blockDim.x) {
@@ -572,18 +1272,21 @@ cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__res
 		int32_t win = -1;
 		if (nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, p, best, bf, ties, 1, nt);
 		if (win >= 0) {
+			V3 c;
 			if (win != bf) {
 				const double *tt = tri + 9 * (int64_t)win;
-				const V3 c = closest_on_triangle(p, ld3(tt), ld3(tt + 3), ld3(tt + 6));
+				c = closest_on_triangle(p, ld3(tt), ld3(tt + 3), ld3(tt + 6));
 				I[i] = win;
 				C[3 * i] = c.x; C[3 * i + 1] = c.y; C[3 * i + 2] = c.z;
-			}
+			} else if (sa.enabled) c = ld3(C + 3 * i);
+			finalize_sign(sa, i, p, win, c, best, S);
 		} else {
 			Hit h;
 			if (traverse_limited(nodes, root, tri, p, best + best * PK_EPS_WALK, best, walk_budget, h)) {
 				I[i] = h.f;
 				C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z;
 				S[i] = h.sqr_d;
+				finalize_sign(sa, i, p, h.f, h.c, h.sqr_d, S);
 			} else {
 				heavy[atomicAdd(counters + 1, 1)] = (int32_t)i;      // S[i] stays a valid upper bound for K3
 			}
@@ -601,7 +1304,7 @@ cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
                  const double *__restrict__ P, int64_t np, int32_t *__restrict__ todo, int32_t *__restrict__ todo_ties,
                  int32_t *__restrict__ counters /* [0] walk entries, [1] heavy, [2] search entries, [3] next search entry */,
                  double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
-                 int32_t *__restrict__ heavy, int search_budget)
+                 int32_t *__restrict__ heavy, int search_budget, SignArgs sa)
 {
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1;
@@ -687,6 +1390,10 @@ cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 				C[3 * i] = k.bc.x; C[3 * i + 1] = k.bc.y; C[3 * i + 2] = k.bc.z;
 				S[i] = k.best;
 			}
+			if (sa.enabled && !give_up && k.near <= 1) {     // settled here: nobody else will look at this query again
+				if (k.bf >= 0) finalize_sign(sa, i, k.p, k.bf, k.bc, k.best, S);
+				else finalize_sign(sa, i, k.p, bf0, ld3(C + 3 * i), S[i], S);
+			}
 			active = false;
 		}
 	}
@@ -696,7 +1403,7 @@ cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 __global__ void __launch_bounds__(128)
 cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
                 const double *__restrict__ P, const int32_t *__restrict__ heavy, const int32_t *__restrict__ heavy_count,
-                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C)
+                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa)
 {
 	__shared__ int32_t s_node[4][HV_STACK];
 	__shared__ unsigned long long s_key[4][HV_STACK];
@@ -782,6 +1489,7 @@ cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__r
 			if (I) I[i] = h.f;
 			if (C) { C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z; }
 			if (S) S[i] = h.sqr_d;
+			finalize_sign(sa, i, p, h.f, h.c, h.sqr_d, S);
 		}
 		__syncwarp();
 	}
@@ -832,6 +1540,70 @@ __global__ void query_keys_kernel(const double *__restrict__ P, int64_t np, doub
 		idx[i] = (uint32_t)i;
 	}
 }
+// device-resident batches: bounding box of the finite queries (ordered-int min/max), then the same 30-bit keys
+__global__ void query_bbox_kernel(const double *__restrict__ P, int64_t np, int *__restrict__ box /* 6 ordered ints, pre-set */) {
+	int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+		const double x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+		if (isfinite(x) && isfinite(y) && isfinite(z)) {
+			lo[0] = min(lo[0], f2ord(__double2float_rd(x))); hi[0] = max(hi[0], f2ord(__double2float_ru(x)));
+			lo[1] = min(lo[1], f2ord(__double2float_rd(y))); hi[1] = max(hi[1], f2ord(__double2float_ru(y)));
+			lo[2] = min(lo[2], f2ord(__double2float_rd(z))); hi[2] = max(hi[2], f2ord(__double2float_ru(z)));
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		lo[c] = __reduce_min_sync(0xffffffffu, lo[c]); hi[c] = __reduce_max_sync(0xffffffffu, hi[c]);
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int c = 0; c < 3; ++c) { atomicMin(box + c, lo[c]); atomicMax(box + 3 + c, hi[c]); }
+	}
+}
+// Is the batch already coherent (consecutive queries close to each other)?  Mean squared distance of 4 096 sampled
+// neighbours against the spacing np points spread evenly over the batch's box would have.  box[6] := 1 if NOT coherent.
+// Packets cut from an already ordered batch (octree leaves, lattice rows of a sorted caller) are aligned with the caller's
+// hierarchy; re-sorting them along a Morton curve makes the packets straddle its jumps (measured: +37 % candidate clusters).
+__global__ void query_probe_kernel(const double *__restrict__ P, int64_t np, int *__restrict__ box, int force) {
+	__shared__ double s_sum[32];
+	const int64_t m = 4096, stride = (np - 1) / m;
+	double acc = 0;
+	for (int64_t k = threadIdx.x; k < m && stride > 0; k += blockDim.x) {
+		const double *a = P + 3 * (k * stride), *b = a + 3;
+		const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+		const double d2 = dx * dx + dy * dy + dz * dz;
+		if (isfinite(d2)) acc += d2;
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double t = 0;
+		for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_sum[k];
+		t /= (double)m;
+		const double ex = (double)ord2f(box[3]) - (double)ord2f(box[0]), ey = (double)ord2f(box[4]) - (double)ord2f(box[1]), ez = (double)ord2f(box[5]) - (double)ord2f(box[2]);
+		const double D2 = ex * ex + ey * ey + ez * ez;
+		box[6] = force ? 1 : ((D2 > 0 && t > 64.0 * D2 / pow((double)np, 2.0 / 3.0)) ? 1 : 0);
+	}
+}
+__global__ void query_keys_dev_kernel(const double *__restrict__ P, int64_t np, const int *__restrict__ box,
+                                      uint32_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+	if (box[6] == 0) {      // coherent batch: keys in the caller's order (the stable sort then returns the identity)
+		for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) { key[i] = (uint32_t)(i >> 2); idx[i] = (uint32_t)i; }
+		return;
+	}
+	const float lx = ord2f(box[0]), ly = ord2f(box[1]), lz = ord2f(box[2]);
+	const float ext = fmaxf(fmaxf(ord2f(box[3]) - lx, ord2f(box[4]) - ly), ord2f(box[5]) - lz);
+	const double scale = ext > 0.f ? 1024.0 / (double)ext : 0.0;
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+		const double fx = (P[3 * i] - lx) * scale, fy = (P[3 * i + 1] - ly) * scale, fz = (P[3 * i + 2] - lz) * scale;
+		// (NaN compares false: a non-finite query lands in cell 0, it never searches anyway)
+		const uint32_t x = fx > 0.0 ? (uint32_t)fmin(fx, 1023.0) : 0u, y = fy > 0.0 ? (uint32_t)fmin(fy, 1023.0) : 0u, z = fz > 0.0 ? (uint32_t)fmin(fz, 1023.0) : 0u;
+		key[i] = (uint32_t)morton3(x, y, z);
+		idx[i] = (uint32_t)i;
+	}
+}
 __global__ void gather_points_kernel(const double *__restrict__ P, const uint32_t *__restrict__ perm, int64_t np, double *__restrict__ out) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * np; t += (int64_t)gridDim.x * blockDim.x)
 		out[t] = P[3 * (int64_t)perm[t / 3] + t % 3];
@@ -857,12 +1629,80 @@ namespace fpohm {
 struct QueryScratch {
 	DevBuf<int32_t> tmpI, todo, todo_ties, heavy, cnt;
 	DevBuf<double> tmpC, tmpS;
+	DevBuf<uint32_t> key, key2, idx, perm;
+	DevBuf<uint8_t> sort_tmp;
+	DevBuf<int> qbox;
 };
+enum { CP_SORT_AUTO = 0, CP_SORT_NEVER = 1, CP_SORT_ALWAYS = 2 };
+static int cp_mode() {
+	static const int mode = getenv("FPOHM_CP_MODE") ? atoi(getenv("FPOHM_CP_MODE")) : 3;   // debug A/B: 0 per-lane igl order, 1 binary packets, 2 wide packets, 3 pair queues
+	return mode;
+}
 
 static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
-                                    double *S, int32_t *I, double *C, double *N, cudaStream_t s, QueryScratch &q)
+                                    double *S, int32_t *I, double *C, double *N, cudaStream_t s, QueryScratch &q, int sort_policy = CP_SORT_AUTO)
 {
 	if (np <= 0) return;
+	const int mode = cp_mode();
+	if (mode >= 2 && m->qroot >= 0 && m->n_wnodes > 0) {
+		static const bool stats = getenv("FPOHM_CP_STATS") != nullptr;   // debug only: N := traversal counters
+		static const int sort_env = getenv("FPOHM_CP_SORT") ? atoi(getenv("FPOHM_CP_SORT")) : -1;   // 0 never, 1 always
+		static const int64_t sort_min = getenv("FPOHM_CP_SORT_MIN") ? atoll(getenv("FPOHM_CP_SORT_MIN")) : (1 << 16);
+		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
+		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
+		static const int b3_budget = getenv("FPOHM_CP_B3") ? atoi(getenv("FPOHM_CP_B3")) : 512;
+		static const int c_budget = getenv("FPOHM_CP_CB") ? atoi(getenv("FPOHM_CP_CB")) : 32;
+		FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "closest point: %lld queries in one launch", (long long)np);
+		const int blk = 128;
+		// the kernels hand unfinished queries on through S/I/C, so all three must exist
+		if (!I) { q.tmpI.alloc(np, s); I = q.tmpI.p; }
+		if (!C) { q.tmpC.alloc(3 * np, s); C = q.tmpC.p; }
+		if (!S) { q.tmpS.alloc(np, s); S = q.tmpS.p; }
+		// packets want 32 neighbours: walk the batch in Morton order of a 1024^3 grid over its own bounding box.  Only keys and
+		// indices are sorted (8 B/query); the kernels read and write the caller's arrays through the permutation.
+		const uint32_t *perm = nullptr;
+		const bool do_sort = sort_env == 0 ? false : (sort_env == 1 || sort_policy == CP_SORT_ALWAYS || (sort_policy == CP_SORT_AUTO && np >= sort_min));
+		if (do_sort) {
+			q.qbox.alloc(8, s); q.key.alloc(np, s); q.key2.alloc(np, s); q.idx.alloc(np, s); q.perm.alloc(np, s);
+			static const int h_init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+			FPOHM_CUDA(cudaMemcpyAsync(q.qbox.p, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
+			query_bbox_kernel<<<grid_for(ctx, np, 256, 4), 256, 0, s>>>(P_dev, np, q.qbox.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			query_probe_kernel<<<1, 1024, 0, s>>>(P_dev, np, q.qbox.p, (sort_env == 1 || sort_policy == CP_SORT_ALWAYS) ? 1 : 0);
+			FPOHM_LAUNCH_CHECK(ctx);
+			query_keys_dev_kernel<<<grid_for(ctx, np, 256), 256, 0, s>>>(P_dev, np, q.qbox.p, q.key.p, q.idx.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			size_t tb = 0;
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, q.key.p, q.key2.p, q.idx.p, q.perm.p, (int)np, 0, 30, s));
+			q.sort_tmp.alloc((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(q.sort_tmp.p, tb, q.key.p, q.key2.p, q.idx.p, q.perm.p, (int)np, 0, 30, s));
+			ctx->launches += 1;
+			perm = q.perm.p;
+		}
+		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
+		q.todo.alloc(2 * np, s); q.todo_ties.alloc(4 * np, s); q.heavy.alloc(np, s);
+		q.cnt.alloc(8, s);                                 // walk entries, heavy entries, search entries, next search entry, next packet
+		FPOHM_CUDA(cudaMemsetAsync(q.cnt.p, 0, 8 * sizeof(int32_t), s));
+		SignArgs sa = {m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, stats ? nullptr : N, (with_sign && (S || N)) ? 1 : 0};
+		const int qslot = (int)(ctx->q_launches % fpohm_ctx::QRING);
+		FPOHM_CUDA(cudaEventRecord(ctx->q_ev0[qslot], s));
+		if (mode == 3 && m->nF < (1ll << 27)) {
+			const int pers = (int)std::min<int64_t>(pgrid, (int64_t)ctx->sm_count * 6);
+			if (stats && N) cp_pair_kernel<true, 3><<<pers, blk, 0, s>>>(m->wnodes.p, m->trif.p, m->tri.p, P_dev, np, perm, S, I, C, sa, m->eps_v, m->slack_q, q.todo.p, q.todo_ties.p, q.cnt.p, q.heavy.p, b3_budget, c_budget, N);
+			else cp_pair_kernel<false, 6><<<pers, blk, 0, s>>>(m->wnodes.p, m->trif.p, m->tri.p, P_dev, np, perm, S, I, C, sa, m->eps_v, m->slack_q, q.todo.p, q.todo_ties.p, q.cnt.p, q.heavy.p, b3_budget, c_budget, nullptr);
+		} else if (stats && N) cp_wide_kernel<true, 4><<<pgrid, blk, 0, s>>>(m->wnodes.p, m->tri.p, P_dev, np, perm, S, I, C, sa, q.todo.p, q.todo_ties.p, q.cnt.p, N);
+		else cp_wide_kernel<false, 5><<<pgrid, blk, 0, s>>>(m->wnodes.p, m->tri.p, P_dev, np, perm, S, I, C, sa, q.todo.p, q.todo_ties.p, q.cnt.p, nullptr);
+		FPOHM_CUDA(cudaEventRecord(ctx->q_ev1[qslot], s));
+		ctx->q_launches++;
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search, sa);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, sa);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, sa);
+		FPOHM_LAUNCH_CHECK(ctx);
+		return;
+	}
 	const int blk = 128;
 	const int grid = grid_for(ctx, np, blk, 16);
 	static const bool stats = getenv("FPOHM_CP_STATS") != nullptr;   // debug only: N := traversal counters
@@ -872,9 +1712,9 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		if (!C) { q.tmpC.alloc(3 * np, s); C = q.tmpC.p; }
 		if (!S && N) { q.tmpS.alloc(np, s); S = q.tmpS.p; }
 	}
-	static const int mode = getenv("FPOHM_CP_MODE") ? atoi(getenv("FPOHM_CP_MODE")) : 1;   // debug A/B: 0 = per-lane igl order only
 	cudaStream_t sc = s;   // (completion kernels run on the same stream)
-	if (mode == 1 && m->qroot >= 0) {
+	const SignArgs no_sign = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+	if (mode >= 1 && m->qroot >= 0) {
 		FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "closest point: %lld queries in one launch", (long long)np);
 		// the kernels hand unfinished queries on through S/I/C, so all three must exist
 		if (!I) { q.tmpI.alloc(np, s); I = q.tmpI.p; }
@@ -894,11 +1734,11 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_CUDA(cudaEventRecord(ctx->q_ev1[qslot], s));
 		ctx->q_launches++;
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, sc>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search);
+		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, sc>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search, no_sign);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk);
+		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, no_sign);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C);
+		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, no_sign);
 	} else {
 		if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 		else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
@@ -972,6 +1812,17 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 			FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "%s: %lld queries in one call", who, (long long)np);
 			const double ext = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
 			dP.upload(P, 3 * np);
+			if (cp_mode() >= 2 && mesh->n_wnodes > 0) {     // the wide-packet kernels walk a permutation themselves: no gather / scatter passes
+				QueryScratch q;
+				launch_closest_point_ex(ctx, mesh, with_sign, dP.p, np, S ? dS.p : nullptr, I ? dI.p : nullptr, C ? dC.p : nullptr, N ? dN.p : nullptr, s, q, CP_SORT_ALWAYS);
+				if (S) dS.download(S, np);
+				if (I) dI.download(I, np);
+				if (C) dC.download(C, 3 * np);
+				if (N) dN.download(N, 3 * np);
+				t.stop();
+				FPOHM_CUDA(cudaStreamSynchronize(s));
+				return FPOHM_OK;
+			}
 			DevBuf<uint32_t> key(np, s), key2(np, s), idx(np, s), perm(np, s);
 			query_keys_kernel<<<grid_for(ctx, np, 256), 256, 0, s>>>(dP.p, np, mn[0], mn[1], mn[2], ext > 0 ? 1024.0 / ext : 0.0, key.p, idx.p);
 			FPOHM_LAUNCH_CHECK(ctx);

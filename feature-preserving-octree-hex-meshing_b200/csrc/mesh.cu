@@ -24,6 +24,13 @@ __global__ void gather_triangles_kernel(const double *__restrict__ V, const int3
 	}
 }
 
+__global__ void float_triangles_kernel(const double *__restrict__ tri, int64_t nF, float4 *__restrict__ out) {
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * nF; t += (int64_t)gridDim.x * blockDim.x) {
+		const double *v = tri + 3 * t;
+		out[t] = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
+	}
+}
+
 // ---- facet-bbox tree for the subdivision predicate --------------------------------------------------
 // geogram sorts facets along a Morton curve and builds an implicit balanced tree (mesh_AABB.cpp:166-189,
 // 325-348).  The predicate "does ANY facet box overlap" does not depend on facet order or tree shape
@@ -115,7 +122,6 @@ void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 }
 
 void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
-	(void)ctx;
 	if (m->has_tree) return;
 	build_igl_tree(m->hV.data(), m->nV, m->hF.data(), m->nF, m->htree);
 	build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
@@ -166,6 +172,71 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	}
 	m->qfnodes.alloc((int64_t)qf.size(), s);
 	m->qfnodes.upload(qf.data(), (int64_t)qf.size());
+	// 8-wide collapse for the box-parallel packet search: starting from a binary node's two children, the child with the
+	// most facets is opened until there are eight (igl's median splits are balanced by count, so this regroups three
+	// binary levels; a subtree of <= 8 facets becomes one all-facet node, a "cluster").
+	if (ni > 0) {
+		std::vector<int32_t> leaves(nn, 1);
+		for (size_t i = nn; i-- > 0;) if (t.prim[i] < 0) leaves[i] = leaves[(size_t)t.lr[2 * i]] + leaves[(size_t)t.lr[2 * i + 1]];
+		std::vector<WNode> w;
+		w.reserve((size_t)ni / 3 + 8);
+		std::vector<std::pair<int32_t, int32_t>> work;   // (binary node, wide node index)
+		w.emplace_back();
+		work.push_back({0, 0});
+		while (!work.empty()) {
+			const auto [b, wi] = work.back();
+			work.pop_back();
+			int32_t kids[8];
+			int nk = 2;
+			kids[0] = t.lr[2 * (size_t)b]; kids[1] = t.lr[2 * (size_t)b + 1];
+			while (nk < 8) {
+				int best = -1;
+				for (int k = 0; k < nk; ++k)
+					if (t.prim[(size_t)kids[k]] < 0 && (best < 0 || leaves[(size_t)kids[k]] > leaves[(size_t)kids[best]])) best = k;
+				if (best < 0) break;
+				const int32_t o = kids[best];
+				for (int k = nk; k > best + 1; --k) kids[k] = kids[k - 1];      // keep the binary tree's left-to-right order
+				kids[best] = t.lr[2 * (size_t)o]; kids[best + 1] = t.lr[2 * (size_t)o + 1];
+				++nk;
+			}
+			for (int k = 0; k < 8; ++k) {
+				WChild e;
+				if (k < nk) {
+					const size_t c = (size_t)kids[k];
+					for (int a = 0; a < 3; ++a) { e.lo[a] = f_dn(t.box[6 * c + a]); e.hi[a] = f_up(t.box[6 * c + 3 + a]); }
+					if (t.prim[c] >= 0) { e.child = ~t.prim[c]; e.flags = 0; }
+					else {
+						e.child = (int32_t)w.size();
+						e.flags = leaves[c] <= 8 ? 1 : 0;
+						w.emplace_back();
+						work.push_back({kids[k], e.child});
+					}
+				} else {
+					for (int a = 0; a < 3; ++a) { e.lo[a] = INFINITY; e.hi[a] = -INFINITY; }
+					e.child = WCHILD_EMPTY; e.flags = 0;
+				}
+				w[(size_t)wi].c[k] = e;
+			}
+		}
+		m->n_wnodes = (int64_t)w.size();
+		m->wnodes.alloc(m->n_wnodes, s);
+		m->wnodes.upload(w.data(), m->n_wnodes);
+		m->trif.alloc(3 * m->nF, s);
+		float_triangles_kernel<<<grid_for(ctx, 3 * m->nF, 256), 256, 0, s>>>(m->tri.p, m->nF, m->trif.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		double ev = 0, mc = 0;
+		for (int64_t v = 0; v < m->nV; ++v) {
+			double e2 = 0;
+			for (int a = 0; a < 3; ++a) {
+				const double x = m->hV[(size_t)(3 * v + a)], e = x - (double)(float)x;
+				e2 += e * e; mc = std::max(mc, std::fabs(x));
+			}
+			ev = std::max(ev, e2);
+		}
+		m->eps_v = f_up(std::sqrt(ev) * 1.000001);
+		m->slack_q = f_up(36.0 * 5.9604644775390625e-8 * mc * 1.01);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
 	m->n_qnodes = ni;
 	m->qroot = nn ? (t.prim[0] >= 0 ? ~t.prim[0] : 0) : 0;
 	m->qnodes.alloc(std::max<int64_t>(ni, 1), s);

@@ -26,6 +26,21 @@ struct alignas(64) QNodeF {
 };
 static_assert(sizeof(QNodeF) == 64, "QNodeF must be half a cache line");
 
+// 8-wide collapse of the same tree for the box-parallel packet search (closest_point.cu, cp_wide_kernel): a node is
+// eight 32-byte child entries — one 256-byte line pair, lane (node, child) of a warp reads ONE entry with two 16-byte
+// loads.  Boxes are the igl boxes rounded OUTWARDS to float (a conservative filter only; exact arithmetic stays fp64).
+// child >= 0: wide node index; child < 0: facet ~child; child == WCHILD_EMPTY: unused slot (box = +inf/-inf).
+// flags bit 0 (children that are wide nodes only): every child of that node is a facet ("cluster").
+#define WCHILD_EMPTY ((int32_t)0x80000000)
+struct alignas(32) WChild {
+	float lo[3], hi[3];
+	int32_t child;
+	int32_t flags;
+};
+static_assert(sizeof(WChild) == 32, "WChild must be 32 bytes");
+struct alignas(128) WNode { WChild c[8]; };
+static_assert(sizeof(WNode) == 256, "WNode must be 256 bytes");
+
 // host-side result of the igl::AABB::init restatement, in DFS pre-order (node 0 = root)
 struct HostTree {
 	std::vector<double> box;    // 6 per node: min xyz, max xyz
@@ -66,6 +81,11 @@ struct fpohm_mesh {
 	int32_t qdepth = 0;            // deepest internal node
 	fpohm::DevBuf<fpohm::QNodeF> qfnodes;
 	fpohm::DevBuf<int32_t> prim_parent; // internal node holding facet f as a child
+	int64_t n_wnodes = 0;
+	fpohm::DevBuf<fpohm::WNode> wnodes; // 8-wide collapse (node 0 = root); empty when nF < 2
+	fpohm::DevBuf<float4> trif;         // 3 float4 per facet: vertices rounded to nearest float (fp32 refine filter)
+	float eps_v = 0.f;                  // >= max |v - float(v)| over the vertices
+	float slack_q = 0.f;                // >= the error of an fp32 barycentric combination of three vertices (36 u max|coordinate|)
 	std::vector<double> hFN, hVN, hEN;
 	std::vector<int32_t> hE, hEMAP;
 	fpohm::DevBuf<double> FN, VN, EN;

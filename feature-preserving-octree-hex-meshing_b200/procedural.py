@@ -222,3 +222,37 @@ def hex_lattice_around(tV, n: int):
     c = lambda dx, dy, dz: idx[dx:nx + dx, dy:ny + dy, dz:nz + dz].reshape(-1)
     H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
     return np.ascontiguousarray(g * h + (lo - h)), np.ascontiguousarray(H.astype(np.uint32))
+
+
+def c3_mesh():
+    """BASELINE config C3: 4^3 lattice of tori, one midpoint subdivision -> 2 027 520 triangles (high genus, closed)."""
+    return midpoint_subdivide(*linked_tori(4, 90, 44), 1)
+
+
+def c4_queries(V, F, n_jitter: int = 1_500_000, n_block: int = 216, h: float = 1.0 / 1024, seed: int = 7):
+    """BASELINE config C4 query sets against the surface (V, F):
+      project  — `n_jitter` points jittered +-2h around the surface (one barycentric sample of facet k*nF/n_jitter each, in
+                 facet order: what projection_smooth / dirty_graph_projection see, ghm.cpp:3760-3781) followed by the
+                 boundary vertices of the n_block^3 hex block laid over the bounding box (far-field queries);
+      classify — the n_block^3 hex centres of that block in the lattice's own order (id = i*ny*nz + j*nz + k, z fastest:
+                 voxel_meshing ghm.cpp:242 -> clean_hex_mesh's points_inside_mesh, ghm.cpp:1937-1951).
+    Returns (project [n,3], classify [n_block^3,3]) float64, C-contiguous."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    V = np.asarray(V, np.float64); F = np.asarray(F)
+    fid = (np.arange(n_jitter, dtype=np.int64) * len(F)) // n_jitter
+    b = rng.random((n_jitter, 2))
+    flip = b.sum(1) > 1.0
+    b[flip] = 1.0 - b[flip]
+    tri = V[F[fid].astype(np.int64)]
+    pts = tri[:, 0] + b[:, :1] * (tri[:, 1] - tri[:, 0]) + b[:, 1:] * (tri[:, 2] - tri[:, 0])
+    pts += (rng.random(pts.shape) - 0.5) * (4.0 * h)
+    lo, hi = V.min(0), V.max(0)
+    g = np.arange(n_block + 1, dtype=np.float64) / n_block
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    on_b = np.zeros(X.shape, bool)
+    on_b[[0, -1], :, :] = True; on_b[:, [0, -1], :] = True; on_b[:, :, [0, -1]] = True
+    bverts = np.stack([X[on_b], Y[on_b], Z[on_b]], -1) * (hi - lo) + lo
+    gc = (np.arange(n_block, dtype=np.float64) + 0.5) / n_block
+    Xc, Yc, Zc = np.meshgrid(gc, gc, gc, indexing="ij")
+    centres = np.stack([Xc, Yc, Zc], -1).reshape(-1, 3) * (hi - lo) + lo
+    return np.ascontiguousarray(np.concatenate([pts, bverts])), np.ascontiguousarray(centres)
