@@ -565,4 +565,43 @@ int ref_hausdorff_ratio(const double *VA, int64_t nVA, const int32_t *FA, int64_
 	return ok;
 }
 
+// hausdorff_dis(mesh0, mesh1, outlierVs, thr) itself, gf.cpp:3590-3628 (igl::point_mesh_squared_distance both ways, threshold
+// decaying x0.9 until the list is non-empty).  Two-phase: returns the count, fills `out` when it is large enough.  The list
+// comes back in the reference's own push order.
+int64_t ref_hausdorff_dis_outliers(const double *VA, int64_t nVA, const int32_t *FA, int64_t nFA,
+	const double *VB, int64_t nVB, const int32_t *FB, int64_t nFB, double thr, int32_t *out, int64_t cap)
+{
+	Mesh a, b; fill_trimesh(a, VA, nVA, FA, nFA); fill_trimesh(b, VB, nVB, FB, nFB);
+	std::vector<int> outliers;
+	double t = thr;
+	std::streambuf *old = std::cout.rdbuf(nullptr);      // "refered total: ..." per round
+	hausdorff_dis(a, b, outliers, t);
+	std::cout.rdbuf(old);
+	if (out && cap >= (int64_t)outliers.size()) for (size_t i = 0; i < outliers.size(); ++i) out[i] = outliers[i];
+	return (int64_t)outliers.size();
+}
+
+// a further OctreeGrid::subdivide pass over an EXISTING tree with a smaller stop extent — the later passes of the outer loop
+// (ghm.cpp:495-500,523-524: the same octree object is subdivided again after args.edge_length_ratio went down)
+void ref_octree_subdivide(void *hv, int stop_extent) {
+	RefOctree *h = (RefOctree *)hv;
+	const GEO::vec3 &o = h->origin; const Eigen::Vector3d &mt = h->mesh_transform; const double vs = h->voxel_size;
+	GEO::MeshFacetsAABB &aabb_tree = *h->aabb;
+	auto should_subdivide = [&](int x, int y, int z, int extent) {
+		if (extent <= stop_extent) return false;
+		GEO::Box box;
+		box.xyz_min[0] = mt[0] + o[0] + vs * x;
+		box.xyz_min[1] = mt[1] + o[1] + vs * y;
+		box.xyz_min[2] = mt[2] + o[2] + vs * z;
+		box.xyz_max[0] = box.xyz_min[0] + vs * extent;
+		box.xyz_max[1] = box.xyz_min[1] + vs * extent;
+		box.xyz_max[2] = box.xyz_min[2] + vs * extent;
+		bool has_triangles = false;
+		auto action = [&has_triangles](int) { has_triangles = true; };
+		aabb_tree.compute_bbox_facet_bbox_intersections(box, action);
+		return has_triangles;
+	};
+	h->octree.subdivide(should_subdivide, h->graded, h->paired);
+}
+
 } // extern "C"

@@ -283,4 +283,28 @@ void ref_surface_csr(void *rv, int which, int64_t *off, uint32_t *val) {
 	off[n] = t;
 }
 void ref_surface_free(void *rv) { delete (RefSurface *)rv; }
+// grid_hex_meshing_bijective::voxel_meshing itself (ghm.cpp:215-296, the `--o 0` lattice): bbox of the input GEO::Mesh,
+// dim = ceil(extent / (max_extent / num_voxels)), float grid_length, vertex lattice + unit hexes + build_connectivity.
+// Two-phase: sizes first (dims[3], nV, nH), then the arrays.
+struct RefLattice { Mesh hmi; };
+void *ref_voxel_meshing(const double *V, int64_t nV, const int32_t *F, int64_t nF, int num_voxels, int64_t sizes[2]) {
+	GEO::Mesh mi;
+	mi.vertices.create_vertices((GEO::index_t)nV);
+	for (int64_t i = 0; i < nV; ++i) mi.vertices.point((GEO::index_t)i) = GEO::vec3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
+	mi.facets.create_triangles((GEO::index_t)nF);
+	for (int64_t f = 0; f < nF; ++f) for (int c = 0; c < 3; ++c) mi.facets.set_vertex((GEO::index_t)f, c, (GEO::index_t)F[3 * f + c]);
+	RefLattice *r = new RefLattice;
+	r->hmi.type = Mesh_type::Hex;
+	grid_hex_meshing_bijective gm;
+	gm.num_voxels = num_voxels;
+	gm.voxel_meshing(mi, r->hmi);
+	sizes[0] = (int64_t)r->hmi.Vs.size(); sizes[1] = (int64_t)r->hmi.Hs.size();
+	return r;
+}
+void ref_voxel_meshing_export(void *rv, double *Vpos, uint32_t *hex) {
+	const Mesh &m = ((RefLattice *)rv)->hmi;
+	for (size_t v = 0; v < m.Vs.size(); ++v) for (int d = 0; d < 3; ++d) Vpos[3 * v + d] = m.V(d, v);
+	for (size_t h = 0; h < m.Hs.size(); ++h) for (int k = 0; k < 8; ++k) hex[8 * h + k] = m.Hs[h].vs[k];
+}
+void ref_voxel_meshing_free(void *rv) { delete (RefLattice *)rv; }
 }

@@ -87,6 +87,10 @@ class RefOctree:
         gs, m = _i32(grid_size), _i32(marks).reshape(-1, 4)
         return cls(lib().ref_octree_from_marks(_p(gs), _p(m), C.c_int64(len(m)), C.c_int(graded), C.c_int(paired)))
 
+    def subdivide(self, stop_extent):
+        """a further OctreeGrid::subdivide pass over this tree (ghm.cpp:495-500,523-524)"""
+        lib().ref_octree_subdivide(self.h, C.c_int(stop_extent))
+
     def refine(self, cells, stop_extent):
         c = _i32(cells)
         lib().ref_octree_refine(self.h, _p(c), C.c_int64(len(c)), C.c_int(stop_extent))
@@ -254,6 +258,32 @@ def hausdorff_ratio(VA, FA, VB, FB, thr):
     ok = lib().ref_hausdorff_ratio(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)),
                                    _p(FB), C.c_int64(len(FB)), C.c_double(thr), C.byref(r))
     return bool(ok), r.value
+
+
+def hausdorff_dis_outliers(VA, FA, VB, FB, thr):
+    """hausdorff_dis(mesh0, mesh1, outlierVs, thr), global_functions.cpp:3590-3628 — the compiled function; vertex ids of mesh1
+    in the reference's own push order."""
+    VA, FA, VB, FB = _f64(VA), _i32(FA), _f64(VB), _i32(FB)
+    f = lib().ref_hausdorff_dis_outliers
+    f.restype = C.c_int64
+    out = np.zeros(max(len(VB), 1), np.int32)
+    n = f(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)), _p(FB), C.c_int64(len(FB)),
+          C.c_double(thr), _p(out), C.c_int64(len(out)))
+    return out[:n].copy()
+
+
+def voxel_meshing(V, F, num_voxels):
+    """grid_hex_meshing_bijective::voxel_meshing, grid_hex_meshing.cpp:215-296 — the compiled member function on a GEO::Mesh
+    built from (V, F).  Returns (lattice vertex positions [nV,3], hexes [nH,8] uint32)."""
+    V, F = _f64(V), _i32(F)
+    f = lib().ref_voxel_meshing
+    f.restype = C.c_void_p
+    sizes = np.zeros(2, np.int64)
+    h = C.c_void_p(f(_p(V), C.c_int64(len(V)), _p(F), C.c_int64(len(F)), C.c_int(num_voxels), _p(sizes)))
+    Vp = np.zeros((int(sizes[0]), 3)); H = np.zeros((int(sizes[1]), 8), np.uint32)
+    lib().ref_voxel_meshing_export(h, _p(Vp), _p(H))
+    lib().ref_voxel_meshing_free(h)
+    return Vp, H
 
 
 # ---- §8(f)-1: conforming_mesh (grid_hex_meshing.cpp:568-696) -----------------------------------------------------------

@@ -261,41 +261,77 @@ def test_hausdorff_vs_reference(fp, ctx, ref):
 
 
 def test_hausdorff_outliers_vs_reference(fp, ctx, ref):
+    """a12: against the COMPILED hausdorff_dis(mesh0, mesh1, outlierVs, thr) (gf.cpp:3590-3628, oracle/ref/ref_driver.cpp), not a
+    restatement: same vertex set for a threshold that fires at once, one that has to decay (x0.9 rounds) and a gear pair."""
     pm = fp.procedural
     VA, FA = pm.torus(40, 24)
     VB, FB = pm.torus(30, 20)
     VB = VB.copy(); VB[:50] *= 1.05
-    A, B = fp.TriMesh(ctx, VA, FA), fp.TriMesh(ctx, VB, FB)
-    out = fp.hausdorff_outliers(ctx, A, B, 0.02)
-    dAB, I0, _ = ref.point_mesh_sqdist(VB, FB, VA)
-    dBA, _, _ = ref.point_mesh_sqdist(VA, FA, VB)
-    thr = 0.02 ** 2
-    flag = np.zeros(len(VB), bool)
-    while not flag.any():
-        flag[FB[I0[dAB > thr]].reshape(-1)] = True
-        flag[np.nonzero(dBA > thr)[0]] = True
-        thr *= 0.9
-    assert np.array_equal(np.sort(out), np.nonzero(flag)[0])
-    A.close(); B.close()
+    gV, gF, _ = pm.gear(teeth=12, n_radial=4, n_axial=6, n_arc=2)
+    gV2 = gV.copy(); gV2[::37] += 0.004
+    for (Va, Fa, Vb, Fb, thr) in [(VA, FA, VB, FB, 0.02), (VA, FA, VB, FB, 0.5), (gV, gF, gV2, gF, 0.003), (VB, FB, VA, FA, 0.01)]:
+        A, B = fp.TriMesh(ctx, Va, Fa), fp.TriMesh(ctx, Vb, Fb)
+        out = fp.hausdorff_outliers(ctx, A, B, thr)
+        r = ref.hausdorff_dis_outliers(Va, Fa, Vb, Fb, thr)
+        assert len(r) > 0 and len(np.unique(r)) == len(r)
+        assert np.array_equal(np.sort(out), np.sort(r)), (thr, len(out), len(r))
+        A.close(); B.close()
 
 
-def test_voxel_lattice(fp, ctx):
-    mn, mx = np.array([-0.5, -0.31, -0.2]), np.array([0.5, 0.33, 0.21])
-    Vp, H, dim = fp.voxel_lattice(ctx, mn, mx, 40)
-    # numpy restatement of ghm.cpp:226-291 (float grid_length, float product)
-    ext = mx - mn
-    ln = ext.max() / 40
-    d = np.ceil(ext / ln).astype(np.int64)
-    assert np.array_equal(dim, d)
-    gl = (ext / d).astype(np.float32)
-    i, j, k = np.meshgrid(np.arange(d[0]), np.arange(d[1]), np.arange(d[2]), indexing="ij")
-    ref_V = np.stack([mn[0] + (gl[0] * i.astype(np.float32)).astype(np.float64), mn[1] + (gl[1] * j.astype(np.float32)).astype(np.float64),
-                      mn[2] + (gl[2] * k.astype(np.float32)).astype(np.float64)], -1).reshape(-1, 3)
-    assert np.array_equal(Vp, ref_V)
-    idx = np.arange(d.prod()).reshape(d)
-    c = lambda a, b, cc: idx[a:d[0] - 1 + a, b:d[1] - 1 + b, cc:d[2] - 1 + cc].reshape(-1)
-    ref_H = np.stack([c(0, 0, 0), c(1, 0, 0), c(1, 1, 0), c(0, 1, 0), c(0, 0, 1), c(1, 0, 1), c(1, 1, 1), c(0, 1, 1)], -1)
-    assert np.array_equal(H, ref_H.astype(np.uint32))
+def test_voxel_lattice(fp, ctx, ref):
+    """a13: against the COMPILED grid_hex_meshing_bijective::voxel_meshing (ghm.cpp:215-296) run on a GEO::Mesh — vertex positions
+    bit-exact (float grid_length x int, then + min_corner in double), hexes identical, for three bounding boxes / resolutions."""
+    pm = fp.procedural
+    for (V, F), nv in [(pm.torus(40, 24), 40), (pm.gear(teeth=12, n_radial=4, n_axial=6, n_arc=2)[:2], 30), (pm.linked_tori(2, 16, 8), 57)]:
+        V = V * np.array([1.0, 0.83, 0.61]) + np.array([0.013, -0.2, 0.37])      # not a unit box: the three grid lengths differ
+        rV, rH = ref.voxel_meshing(V, F, nv)
+        Vp, H, dim = fp.voxel_lattice(ctx, V.min(0), V.max(0), nv)
+        assert int(np.prod(dim)) == len(rV) and len(H) == len(rH)
+        assert np.array_equal(Vp, rV)
+        assert np.array_equal(H, rH)
+
+
+def test_octree_subdivide_existing_tree_vs_reference(fp, ctx, ref):
+    """The later passes of the outer loop (ghm.cpp:495-500,523-524): OctreeGrid::subdivide called AGAIN on the tree of the previous
+    pass with a smaller stop extent — also after an incremental refine of listed cells in between (ghm.cpp:518-521)."""
+    for name, (V, F) in _meshes(fp).items():
+        p = fp.octree_grid_setup(V, 1 << 20)
+        gs, org, mt, vs = ref.octree_grid_setup(V, F, 1 << 20)
+        m = fp.TriMesh(ctx, V, F)
+        p.c.stop_extent = 1 << 16
+        r = ref.RefOctree.build(V, F, gs, org, mt, vs, 1 << 16)
+        o = fp.Octree.build(ctx, m, p)
+        for E in (15, 14):
+            r.subdivide(1 << E)
+            o.subdivide(m, 1 << E)
+            assert_octree_equal(r.export(), o.export())
+            rV, rH, _ = r.hexes(); oV, oH, _ = o.hexes()
+            assert np.array_equal(canon_hexes(rV, rH), canon_hexes(oV, oH)), (name, E)
+        # equal to building at the final extent from scratch (the closure is a least fix-point)
+        p.c.stop_extent = 1 << 14
+        o2 = fp.Octree.build(ctx, m, p)
+        assert_octree_equal(o.export(), o2.export())
+        o2.close()
+        # refine a few leaves, then one more pass
+        rex, oex = r.export(), o.export()
+
+        def leaf_keys(ex):
+            c0 = ex["node_pos"][ex["corner"][:, 0]]
+            ext = ex["node_pos"][ex["corner"][:, 1]][:, 0] - c0[:, 0]
+            return np.concatenate([c0, ext[:, None]], 1), ex["first_child"] < 0
+        rk, rleaf = leaf_keys(rex)
+        okk, _ = leaf_keys(oex)
+        big = np.nonzero(rleaf & (rk[:, 3] >= (1 << 15)))[0]
+        pick = np.random.default_rng(3).choice(big, min(12, len(big)), replace=False)
+        lut = {tuple(k): i for i, k in enumerate(okk)}
+        opick = np.array([lut[tuple(rk[i])] for i in pick], np.int32)
+        r.refine(pick.astype(np.int32), 1 << 13)
+        o.refine(m, opick, 1 << 13)
+        assert_octree_equal(r.export(), o.export())
+        r.subdivide(1 << 13)
+        o.subdivide(m, 1 << 13)
+        assert_octree_equal(r.export(), o.export())
+        o.close(); m.close()
 
 
 def test_cpp_shim_parity():
