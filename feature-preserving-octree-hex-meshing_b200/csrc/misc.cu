@@ -65,30 +65,8 @@ __global__ void gather_points_kernel(const double *__restrict__ V, const int32_t
 __global__ void iota_kernel(int32_t *p, int64_t n) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = (int32_t)t;
 }
-// similar-triangle face samples (extern/vcg/sampling.h:496-540 lattice; per-face count from the cumulative density so
-// that faces are independent — the reference never enables face sampling, metro_hausdorff.cpp:47-48)
-__global__ void face_sample_count_kernel(const double *__restrict__ tri, int64_t nF, double density, const double *__restrict__ cum_area,
-                                         int64_t *__restrict__ cnt, int32_t *__restrict__ per_edge)
-{
-	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x) {
-		const double hi = cum_area[f + 1] * density, lo = cum_area[f] * density;
-		const long long want = (long long)floor(hi) - (long long)floor(lo);
-		int m = 0; long long got = 0;
-		if (want > 0) {
-			m = (int)((sqrt(1.0 + 8.0 * (double)want) + 5.0) / 2.0);
-			got = m >= 4 ? (long long)(m - 2) * (m - 3) / 2 : 0;
-		}
-		cnt[f] = got; per_edge[f] = m;
-	}
-}
-__global__ void tri_area_kernel(const double *__restrict__ tri, int64_t nF, double *__restrict__ area) {
-	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x) {
-		const double *t = tri + 9 * f;
-		const V3 a = sub(ld3(t + 3), ld3(t)), b = sub(ld3(t + 6), ld3(t));
-		const V3 c = {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-		area[f] = 0.5 * sqrt(sqnorm(c));
-	}
-}
+// similar-triangle face samples: the lattice of Sampling::SimilarTriangles (extern/vcg/sampling.h:496-511) for the per-face edge
+// counts the host recurrence produced
 __global__ void face_samples_kernel(const double *__restrict__ tri, int64_t nF, const int64_t *__restrict__ off, const int32_t *__restrict__ per_edge,
                                     double *__restrict__ P)
 {
@@ -297,30 +275,48 @@ Stats directed(fpohm_ctx *ctx, fpohm_mesh *A, fpohm_mesh *B, int64_t extra, doub
 	DevBuf<int64_t> foff;
 	DevBuf<int32_t> per_edge;
 	if (extra > 0) {
-		DevBuf<double> area(A->nF + 1, s), cum(A->nF + 1, s);
-		area.zero();
-		tri_area_kernel<<<grid_for(ctx, A->nF, blk), blk, 0, s>>>(A->tri.p, A->nF, area.p);
-		FPOHM_LAUNCH_CHECK(ctx);
-		size_t t2 = 0;
-		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, area.p, cum.p, A->nF + 1, s));
-		DevBuf<uint8_t> tmp2((int64_t)t2, s);
-		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, t2, area.p, cum.p, A->nF + 1, s));
-		double total_area = 0;
-		FPOHM_CUDA(cudaMemcpyAsync(&total_area, cum.p + A->nF, 8, cudaMemcpyDeviceToHost, s));
-		FPOHM_CUDA(cudaStreamSynchronize(s));
-		const double density = total_area > 0 ? (double)extra / total_area : 0.0;
-		DevBuf<int64_t> fc(A->nF + 1, s);
-		fc.zero();
+		// VCG's similar-triangle rule is a SEQUENTIAL recurrence over the faces (extern/vcg/sampling.h:513-540): a running
+		// decimal `n_samples_decimal += 0.5 * DoubleArea(f) * density`, n = (int) of it, m = samples per edge from n, and
+		// what the lattice really produced ((m-2)(m-3)/2) is taken off again.  Identical sample sets need the identical
+		// recurrence in the identical fp64 order, so the counts are made on the host from the mesh's own arrays (2 M faces:
+		// ~10 ms); positions are then generated on the device.  DoubleArea = Norm((v1-v0)^(v2-v0)), sums left to right
+		// (vcg/space/triangle3.h:241, deprecated_point3.h:282-290,321-324); area_S1 = sum / 2 (sampling.h:212-222);
+		// density = (n_samples_target - n_vertex_samples) / area_S1 (sampling.h:573-586).
+		const double *hV = A->hV.data();
+		const int32_t *hF = A->hF.data();
+		std::vector<double> da((size_t)A->nF);
+		double area2 = 0.0;
+		for (int64_t f = 0; f < A->nF; ++f) {
+			const double *v0 = hV + 3 * (int64_t)hF[3 * f], *v1 = hV + 3 * (int64_t)hF[3 * f + 1], *v2 = hV + 3 * (int64_t)hF[3 * f + 2];
+			const double ax = v1[0] - v0[0], ay = v1[1] - v0[1], az = v1[2] - v0[2];
+			const double bx = v2[0] - v0[0], by = v2[1] - v0[1], bz = v2[2] - v0[2];
+			const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+			da[(size_t)f] = std::sqrt(cx * cx + cy * cy + cz * cz);
+			area2 += da[(size_t)f];
+		}
+		const double area_S1 = area2 / 2.0;
+		const double density = (double)(unsigned long)extra / area_S1;
+		std::vector<int64_t> hoff((size_t)A->nF + 1);
+		std::vector<int32_t> hper((size_t)A->nF);
+		double dec = 0.0;
+		int64_t tot = 0;
+		for (int64_t f = 0; f < A->nF; ++f) {
+			dec += 0.5 * da[(size_t)f] * density;
+			const int n = (int)dec;
+			int m = 0; int64_t got = 0;
+			if (n) {
+				m = (int)((std::sqrt(1.0 + 8.0 * (double)n) + 5.0) / 2.0);
+				got = (int64_t)(m - 2) * (m - 3) / 2;      // i = 1..m-2, j = 1..m-2-i
+			}
+			hoff[(size_t)f] = tot; hper[(size_t)f] = m >= 4 ? m : 0;
+			tot += got;
+			dec -= (double)got;
+		}
+		hoff[(size_t)A->nF] = tot;
+		nf_samples = tot;
 		foff.alloc(A->nF + 1, s); per_edge.alloc(A->nF, s);
-		face_sample_count_kernel<<<grid_for(ctx, A->nF, blk), blk, 0, s>>>(A->tri.p, A->nF, density, cum.p, fc.p, per_edge.p);
-		FPOHM_LAUNCH_CHECK(ctx);
-		size_t t3 = 0;
-		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t3, fc.p, foff.p, A->nF + 1, s));
-		DevBuf<uint8_t> tmp3((int64_t)t3, s);
-		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp3.p, t3, fc.p, foff.p, A->nF + 1, s));
-		ctx->launches += 2;
-		FPOHM_CUDA(cudaMemcpyAsync(&nf_samples, foff.p + A->nF, 8, cudaMemcpyDeviceToHost, s));
-		FPOHM_CUDA(cudaStreamSynchronize(s));
+		foff.upload(hoff.data(), A->nF + 1); per_edge.upload(hper.data(), A->nF);
+		FPOHM_CUDA(cudaStreamSynchronize(s));      // the staging vectors are locals
 	}
 	const int64_t n = nv + nf_samples;
 	DevBuf<double> P(3 * n, s), sq(n, s);

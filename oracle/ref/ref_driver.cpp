@@ -565,6 +565,41 @@ int ref_hausdorff_ratio(const double *VA, int64_t nVA, const int32_t *FA, int64_
 	return ok;
 }
 
+// metro with FACE sampling switched on: the statements of compute() (metro_hausdorff.cpp:30-170) around the real vcg::Sampling
+// class, with flags VERTEX | FACE | SIMILAR (the reference clears FACE_SAMPLING at :47-48; this is the mode BASELINE config C5's
+// 50 M samples need) and SetSamplesTarget(n_target) per direction.  out = {diag, max_ab, max_ba, mean_ab, mean_ba}; ns = samples.
+void ref_hausdorff_face_sampled(const double *VA, int64_t nVA, const int32_t *FA, int64_t nFA,
+	const double *VB, int64_t nVB, const int32_t *FB, int64_t nFB, uint64_t n_target_ab, uint64_t n_target_ba, double out[5], uint64_t ns[2])
+{
+	CMesh S1, S2;
+	auto fill = [](CMesh &S, const double *V, int64_t nV, const int32_t *F, int64_t nF) {
+		S.vert.resize((size_t)nV);
+		for (int64_t i = 0; i < nV; ++i) { CVertex v; v.P()[0] = V[3 * i]; v.P()[1] = V[3 * i + 1]; v.P()[2] = V[3 * i + 2]; S.vert[(size_t)i] = v; }
+		S.face.resize((size_t)nF);
+		for (int64_t i = 0; i < nF; ++i) {
+			CFace f;
+			f.V(0) = &(S.vert[(size_t)F[3 * i]]); f.V(1) = &(S.vert[(size_t)F[3 * i + 1]]); f.V(2) = &(S.vert[(size_t)F[3 * i + 2]]);
+			S.face[(size_t)i] = f;
+		}
+		S.vn = (int)S.vert.size(); S.fn = (int)S.face.size();
+	};
+	fill(S1, VA, nVA, FA, nFA); fill(S2, VB, nVB, FB, nFB);
+	int flags = SamplingFlags::VERTEX_SAMPLING | SamplingFlags::FACE_SAMPLING | SamplingFlags::SIMILAR_SAMPLING | SamplingFlags::USE_STATIC_GRID;
+	tri::UpdateComponentEP<CMesh>::Set(S1);
+	tri::UpdateComponentEP<CMesh>::Set(S2);
+	tri::UpdateBounding<CMesh>::Box(S1);
+	tri::UpdateBounding<CMesh>::Box(S2);
+	Box3<CMesh::ScalarType> bbox;
+	bbox.Add(S1.bbox); bbox.Add(S2.bbox);
+	bbox.Offset(bbox.Diag() * 0.02);
+	S1.bbox = bbox; S2.bbox = bbox;
+	Sampling<CMesh> fw(S1, S2), bw(S2, S1);
+	fw.SetFlags(flags); fw.SetSamplesTarget((unsigned long)n_target_ab); fw.Hausdorff();
+	bw.SetFlags(flags); bw.SetSamplesTarget((unsigned long)n_target_ba); bw.Hausdorff();
+	out[0] = bbox.Diag(); out[1] = fw.GetDistMax(); out[2] = bw.GetDistMax(); out[3] = fw.GetDistMean(); out[4] = bw.GetDistMean();
+	ns[0] = fw.GetNSamples(); ns[1] = bw.GetNSamples();
+}
+
 // hausdorff_dis(mesh0, mesh1, outlierVs, thr) itself, gf.cpp:3590-3628 (igl::point_mesh_squared_distance both ways, threshold
 // decaying x0.9 until the list is non-empty).  Two-phase: returns the count, fills `out` when it is large enough.  The list
 // comes back in the reference's own push order.

@@ -260,6 +260,15 @@ def hausdorff_ratio(VA, FA, VB, FB, thr):
     return bool(ok), r.value
 
 
+def hausdorff_face_sampled(VA, FA, VB, FB, n_target_ab, n_target_ba):
+    """vcg::Sampling with VERTEX | FACE | SIMILAR sampling (extern/vcg/sampling.h:513-602) and the given total sample targets."""
+    VA, FA, VB, FB = _f64(VA), _i32(FA), _f64(VB), _i32(FB)
+    out = np.zeros(5); ns = np.zeros(2, np.uint64)
+    lib().ref_hausdorff_face_sampled(_p(VA), C.c_int64(len(VA)), _p(FA), C.c_int64(len(FA)), _p(VB), C.c_int64(len(VB)), _p(FB),
+                                     C.c_int64(len(FB)), C.c_uint64(n_target_ab), C.c_uint64(n_target_ba), _p(out), _p(ns))
+    return dict(diag=out[0], max_ab=out[1], max_ba=out[2], mean_ab=out[3], mean_ba=out[4], n_ab=int(ns[0]), n_ba=int(ns[1]))
+
+
 def hausdorff_dis_outliers(VA, FA, VB, FB, thr):
     """hausdorff_dis(mesh0, mesh1, outlierVs, thr), global_functions.cpp:3590-3628 — the compiled function; vertex ids of mesh1
     in the reference's own push order."""
