@@ -1560,30 +1560,44 @@ __global__ void query_bbox_kernel(const double *__restrict__ P, int64_t np, int 
 		for (int c = 0; c < 3; ++c) { atomicMin(box + c, lo[c]); atomicMax(box + 3 + c, hi[c]); }
 	}
 }
-// Is the batch already coherent (consecutive queries close to each other)?  Mean squared distance of 4 096 sampled
-// neighbours against the spacing np points spread evenly over the batch's box would have.  box[6] := 1 if NOT coherent.
-// Packets cut from an already ordered batch (octree leaves, lattice rows of a sorted caller) are aligned with the caller's
-// hierarchy; re-sorting them along a Morton curve makes the packets straddle its jumps (measured: +37 % candidate clusters).
+// Is the batch already coherent — do 32 CONSECUTIVE queries (one packet) sit in a compact clump?  4 096 sampled packets: the
+// squared diagonal of the box of four of their members (first, last and two in between) against the diagonal a clump of 32
+// points would have if the np points were spread evenly over the batch's box.  box[6] := 1 if NOT coherent.  Neighbouring
+// queries being close is not enough: a lattice row (z-fastest ids) or a strip of facets makes packets 30 cells long, and the
+// candidate funnel of the packet kernel grows with the packet's box.  Packets cut from an already ordered batch (octree
+// leaves) are left alone: they are aligned with the caller's hierarchy, while windows of a Morton curve straddle its jumps
+// (measured on octree-ordered leaf centres: +37 % candidate clusters after re-sorting).
 __global__ void query_probe_kernel(const double *__restrict__ P, int64_t np, int *__restrict__ box, int force) {
 	__shared__ double s_sum[32];
-	const int64_t m = 4096, stride = (np - 1) / m;
+	const int64_t m = 4096, npk = np / 32, stride = npk > m ? npk / m : 1;
 	double acc = 0;
-	for (int64_t k = threadIdx.x; k < m && stride > 0; k += blockDim.x) {
-		const double *a = P + 3 * (k * stride), *b = a + 3;
-		const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-		const double d2 = dx * dx + dy * dy + dz * dz;
-		if (isfinite(d2)) acc += d2;
+	int cnt = 0;
+	for (int64_t k = threadIdx.x; k < m && k * stride < npk; k += blockDim.x) {
+		const int64_t base = k * stride * 32;
+		double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+		const int pick[4] = {0, 10, 21, 31};
+		for (int j = 0; j < 4; ++j) {
+			const double *a = P + 3 * (base + pick[j]);
+			for (int c = 0; c < 3; ++c) if (isfinite(a[c])) { lo[c] = fmin(lo[c], a[c]); hi[c] = fmax(hi[c], a[c]); }
+		}
+		double d2 = 0;
+		for (int c = 0; c < 3; ++c) if (hi[c] >= lo[c]) d2 += (hi[c] - lo[c]) * (hi[c] - lo[c]);
+		acc += d2; ++cnt;
 	}
-	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-	if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+	for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+	__shared__ int s_cnt[32];
+	if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = acc; s_cnt[threadIdx.x >> 5] = cnt; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		double t = 0;
-		for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_sum[k];
-		t /= (double)m;
+		double t = 0; int n = 0;
+		for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { t += s_sum[k]; n += s_cnt[k]; }
+		t /= (double)(n > 0 ? n : 1);
 		const double ex = (double)ord2f(box[3]) - (double)ord2f(box[0]), ey = (double)ord2f(box[4]) - (double)ord2f(box[1]), ez = (double)ord2f(box[5]) - (double)ord2f(box[2]);
-		const double D2 = ex * ex + ey * ey + ez * ez;
-		box[6] = force ? 1 : ((D2 > 0 && t > 64.0 * D2 / pow((double)np, 2.0 / 3.0)) ? 1 : 0);
+		const double em = fmax(ex, fmax(ey, ez));
+		// volume of the box, flat directions counted as 1 % of the longest one
+		const double vol = fmax(ex, 0.01 * em) * fmax(ey, 0.01 * em) * fmax(ez, 0.01 * em);
+		const double clump2 = 3.0 * pow(32.0 * vol / (double)np, 2.0 / 3.0);      // squared diagonal of a cube holding 32 evenly spread points
+		box[6] = force ? 1 : ((em > 0 && n > 0 && t > 16.0 * clump2) ? 1 : 0);
 	}
 }
 __global__ void query_keys_dev_kernel(const double *__restrict__ P, int64_t np, const int *__restrict__ box,
@@ -1751,10 +1765,10 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 }
 
 void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
-                          double *S, int32_t *I, double *C, double *N, cudaStream_t s)
+                          double *S, int32_t *I, double *C, double *N, cudaStream_t s, int sort_policy)
 {
 	QueryScratch q;
-	launch_closest_point_ex(ctx, m, with_sign, P_dev, np, S, I, C, N, s, q);
+	launch_closest_point_ex(ctx, m, with_sign, P_dev, np, S, I, C, N, s, q, sort_policy);
 }
 
 } // namespace fpohm
@@ -1797,18 +1811,26 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	// neighbours against the spacing np points would have if spread evenly over their box); a batch that fails is walked
 	// in Morton order and its results are scattered back to the caller's order (a shuffled 4.6 M batch: 3.6 x faster).
 	if (np >= (1 << 16)) {
-		const int64_t m = 4096, stride = (np - 1) / m;
+		// same criterion as query_probe_kernel: sampled packets of 32 consecutive queries against an evenly spread clump of 32
+		const int64_t m = 4096, npk = np / 32, stride = npk > m ? npk / m : 1;
 		double mn[3] = {P[0], P[1], P[2]}, mx[3] = {P[0], P[1], P[2]}, adj = 0;
-		for (int64_t k = 0; k < m; ++k) {
-			const double *a = P + 3 * (k * stride), *b = a + 3;
-			double d2 = 0;
-			for (int c = 0; c < 3; ++c) { d2 += (a[c] - b[c]) * (a[c] - b[c]); mn[c] = std::min(mn[c], a[c]); mx[c] = std::max(mx[c], a[c]); }
-			adj += d2;
+		int64_t cnt = 0;
+		for (int64_t k = 0; k < m && k * stride < npk; ++k) {
+			const int64_t base = k * stride * 32;
+			double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+			for (int j : {0, 10, 21, 31}) {
+				const double *a = P + 3 * (base + j);
+				for (int c = 0; c < 3; ++c) if (std::isfinite(a[c])) { lo[c] = std::min(lo[c], a[c]); hi[c] = std::max(hi[c], a[c]); mn[c] = std::min(mn[c], a[c]); mx[c] = std::max(mx[c], a[c]); }
+			}
+			for (int c = 0; c < 3; ++c) if (hi[c] >= lo[c]) adj += (hi[c] - lo[c]) * (hi[c] - lo[c]);
+			++cnt;
 		}
-		adj /= (double)m;
-		const double D2 = (mx[0] - mn[0]) * (mx[0] - mn[0]) + (mx[1] - mn[1]) * (mx[1] - mn[1]) + (mx[2] - mn[2]) * (mx[2] - mn[2]);
+		adj /= (double)std::max<int64_t>(cnt, 1);
+		const double em = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+		const double vol = std::max(mx[0] - mn[0], 0.01 * em) * std::max(mx[1] - mn[1], 0.01 * em) * std::max(mx[2] - mn[2], 0.01 * em);
+		const double D2 = em > 0 ? 16.0 * 3.0 * std::pow(32.0 * vol / (double)np, 2.0 / 3.0) : 0.0;
 		static const bool never = getenv("FPOHM_CP_NOSORT") != nullptr;
-		if (!never && D2 > 0 && std::isfinite(adj) && adj > 64.0 * D2 / std::pow((double)np, 2.0 / 3.0)) {
+		if (!never && D2 > 0 && std::isfinite(adj) && adj > D2) {
 			FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "%s: %lld queries in one call", who, (long long)np);
 			const double ext = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
 			dP.upload(P, 3 * np);
@@ -1878,7 +1900,7 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 		FPOHM_CUDA(cudaStreamWaitEvent(cs, ctx->ev_pool[(size_t)(2 * k)], 0));
 		if (timeline) cudaEventRecord(tl[(size_t)(4 * k)], cs);
 		launch_closest_point(ctx, mesh, with_sign, dP.p + 3 * o, n, S ? dS.p + o : nullptr, I ? dI.p + o : nullptr,
-		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs);
+		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs, CP_SORT_NEVER);   // the host probe above found the batch coherent
 		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k + 1)], cs));
 		if (timeline) cudaEventRecord(tl[(size_t)(4 * k + 1)], cs);
 		static const bool own_down = getenv("FPOHM_CP_DOWN") ? atoi(getenv("FPOHM_CP_DOWN")) != 0 : true;

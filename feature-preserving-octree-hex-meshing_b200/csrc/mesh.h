@@ -100,6 +100,7 @@ void classify_hexes_dev(fpohm_ctx *ctx, fpohm_mesh *surface, const double *V_dev
                         double *S_dev, uint8_t *flag_dev, cudaStream_t s);
 // closest point (+ pseudonormal sign when with_sign) of np device-resident points; S = signed distance, or the
 // SQUARED distance when !with_sign.  Any output may be null.
+// sort_policy: 0 probe the batch on the device and walk it in Morton order if its packets are not compact, 1 never, 2 always
 void launch_closest_point(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sign, const double *P_dev, int64_t np,
-                          double *S, int32_t *I, double *C, double *N, cudaStream_t s);
+                          double *S, int32_t *I, double *C, double *N, cudaStream_t s, int sort_policy = 0);
 } // namespace fpohm
