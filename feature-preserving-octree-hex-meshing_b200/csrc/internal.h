@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <chrono>
 
 #include "../../include/fpohm.h"
 
@@ -41,30 +42,59 @@ struct Failure { int code; };
 	catch (const std::bad_alloc &) { ::fpohm::set_error("host out of memory"); return FPOHM_ENOMEM; } \
 	catch (...) { ::fpohm::set_error("unexpected exception"); return FPOHM_ECUDA; }
 
-// Plain device buffer (stream-ordered allocation keeps repeated calls cheap).
+// debug probe of the allocator (FPOHM_OCTREE_TIMELINE): host time spent allocating device memory
+extern bool g_alloc_probe;
+extern double g_alloc_ms;
+extern long long g_alloc_calls;
+
+// Device arena owned by a context.  Round 1 took every buffer from the device's default stream-ordered pool with the release
+// threshold raised to "never": a process-wide side effect (memory invisible to the caller's own allocator), and a 1024^3-
+// equivalent octree build spent 5 - 54 ms (once 227 ms) of its 40 - 150 ms inside cudaMallocAsync, whatever the pool had to
+// re-map for the build's ~250 buffers of up to 1.8 GB.  The arena is a handful of big cudaMalloc chunks (doubling up to 4 GB)
+// with a host-side best-fit free list; a block freed by a buffer is handed to the next request at once, which is safe for
+// work ordered on ONE stream — so only buffers of the context's main stream live here, everything allocated on another
+// stream (the caller's stream of the _dev entry points, the compute lanes of the host pipelines) stays with cudaMallocAsync.
+// fpohm_ctx_trim returns unused chunks to the driver; fpohm_ctx_destroy returns everything.
+struct Arena;
+Arena *arena_for_stream(cudaStream_t s);                 // nullptr: not a context's main stream
+void *arena_alloc(Arena *a, size_t bytes);               // throws Failure{FPOHM_ENOMEM}
+void arena_free(Arena *a, void *p);
+Arena *arena_create(int device, cudaStream_t main_stream);
+void arena_destroy(Arena *a);
+size_t arena_trim(Arena *a);                             // bytes returned to the driver
+void arena_stats(Arena *a, size_t *reserved, size_t *in_use);
+
+// Plain device buffer: arena memory on a context's main stream, stream-ordered allocation elsewhere.
 template <class T>
 struct DevBuf {
 	T *p = nullptr;
 	int64_t n = 0;
 	cudaStream_t s = nullptr;
+	Arena *arena = nullptr;
 	DevBuf() = default;
 	DevBuf(int64_t count, cudaStream_t stream) { alloc(count, stream); }
 	DevBuf(const DevBuf &) = delete;
 	DevBuf &operator=(const DevBuf &) = delete;
-	DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+	DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s), arena(o.arena) { o.p = nullptr; o.n = 0; }
 	DevBuf &operator=(DevBuf &&o) noexcept {
-		if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+		if (this != &o) { release(); p = o.p; n = o.n; s = o.s; arena = o.arena; o.p = nullptr; o.n = 0; }
 		return *this;
 	}
 	~DevBuf() { release(); }
 	void alloc(int64_t count, cudaStream_t stream) {
 		release();
 		n = count; s = stream;
-		if (count > 0) FPOHM_CUDA(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)count, stream));
+		if (count > 0) {
+			const auto t0 = g_alloc_probe ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
+			arena = arena_for_stream(stream);
+			if (arena) p = (T *)arena_alloc(arena, sizeof(T) * (size_t)count);
+			else FPOHM_CUDA(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)count, stream));
+			if (g_alloc_probe) { g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++g_alloc_calls; }
+		}
 	}
 	void release() {
-		if (p) cudaFreeAsync(p, s);
-		p = nullptr; n = 0;
+		if (p) { if (arena) arena_free(arena, p); else cudaFreeAsync(p, s); }
+		p = nullptr; n = 0; arena = nullptr;
 	}
 	void zero() { if (n) FPOHM_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * (size_t)n, s)); }
 	void upload(const T *h, int64_t count) {
@@ -92,6 +122,7 @@ struct fpohm_ctx {
 	cudaEvent_t q_ev0[QRING] = {}, q_ev1[QRING] = {};
 	int64_t q_launches = 0;
 	int64_t launches = 0;
+	fpohm::Arena *arena = nullptr;
 };
 
 namespace fpohm {

@@ -21,6 +21,7 @@
 // code>>3 then x8 expansion.  Phase 3 numbers cells/nodes canonically and derives every link table with
 // binary searches instead of the reference's linked-list walks.
 #include "octree.h"
+#include <chrono>
 
 #include <algorithm>
 #include <map>
@@ -713,12 +714,21 @@ void close_and_number(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &P, std::ve
 	for (int l = 0; l < (int)P.size(); ++l) if (nP[l] > 0) Lmax = l;
 	std::vector<DevBuf<uint64_t>> I((size_t)std::max(Lmax + 1, 0));
 	std::vector<int64_t> nI((size_t)std::max(Lmax + 1, 0), 0);
+	static const bool timeline = getenv("FPOHM_OCTREE_TIMELINE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
 	for (int l = Lmax; l >= 0; --l) {
 		DevBuf<uint64_t> cand;
 		const int64_t n_cand = level_candidates(o, l, P[l].p, nP[l], l < Lmax ? I[l + 1].p : nullptr, l < Lmax ? nI[l + 1] : 0, cand);
 		nI[l] = close_level(o, l, cand, n_cand, I[l]);
 	}
+	if (timeline) cudaStreamSynchronize(o->ctx->stream);
+	const auto t1 = std::chrono::steady_clock::now();
 	number_levels(o, I, nI);
+	if (timeline) {
+		cudaStreamSynchronize(o->ctx->stream);
+		o->dbg_close_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		o->dbg_number_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+	}
 }
 
 // phase 3 given the closed internal sets I[l] (sorted device arrays)
@@ -1109,10 +1119,22 @@ int fpohm_octree_build(fpohm_ctx *ctx, const fpohm_mesh *mesh, const fpohm_octre
 		o->ctx = ctx; o->prm = *p;
 		setup_geometry(o, p->grid_size);
 		KernelTimer t(ctx, ctx->stream);
+		static const bool timeline = getenv("FPOHM_OCTREE_TIMELINE") != nullptr;     // debug: host wall clock per phase on stderr
+		const auto t0 = std::chrono::steady_clock::now();
 		std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
 		predicate_sets(o, mesh, p->stop_extent, true, P, nP);
+		if (timeline) cudaStreamSynchronize(ctx->stream);
+		const auto t1 = std::chrono::steady_clock::now();
 		close_and_number(o, P, nP);
+		if (timeline) cudaStreamSynchronize(ctx->stream);
+		const auto t2 = std::chrono::steady_clock::now();
 		t.stop();
+		if (timeline) {
+			fprintf(stderr, "[fpohm octree] phase 1 %.2f ms, phases 2+3 %.2f ms (closure %.2f, numbering %.2f), launches so far %lld; cudaMallocAsync %.2f ms in %lld calls\n",
+			        std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+			        o->dbg_close_ms, o->dbg_number_ms, (long long)ctx->launches, g_alloc_ms, g_alloc_calls);
+			g_alloc_ms = 0; g_alloc_calls = 0;
+		}
 	} catch (...) { delete o; throw; }
 	*out = o;
 	FPOHM_API_END

@@ -62,4 +62,5 @@ struct fpohm_octree {
 	fpohm::DevBuf<uint64_t> node_key;
 	fpohm::DevBuf<int32_t> node_pos, node_neigh;
 	fpohm::DevBuf<int32_t> leaf_cell; // hex2Octree_map
+	double dbg_close_ms = 0, dbg_number_ms = 0;   // FPOHM_OCTREE_TIMELINE
 };

@@ -53,6 +53,10 @@ int fpohm_device_count(void);
 int  fpohm_ctx_create(int device, fpohm_ctx **out);
 void fpohm_ctx_destroy(fpohm_ctx *ctx);
 int  fpohm_ctx_sync(fpohm_ctx *ctx);
+/* Device memory of a context lives in its own arena (big cudaMalloc chunks, reused across calls; the device's default
+ * stream-ordered pool is not touched).  _trim returns the chunks nothing lives in to the driver, _memory reports bytes. */
+int  fpohm_ctx_trim(fpohm_ctx *ctx, int64_t *bytes_released);
+int  fpohm_ctx_memory(fpohm_ctx *ctx, int64_t *bytes_reserved, int64_t *bytes_in_use);
 /* milliseconds of the kernels launched by the last host-pointer call on this ctx (CUDA events) */
 int  fpohm_ctx_last_kernel_ms(fpohm_ctx *ctx, double *ms);
 /* mean duration (CUDA events on the launching stream) of the dominant query kernel — the packet walk — over the last
