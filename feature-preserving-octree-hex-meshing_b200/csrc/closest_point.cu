@@ -268,7 +268,9 @@ __device__ __forceinline__ float box_low(const float *__restrict__ mn, const flo
 	return __fmul_rd(__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))), 0.99999905f);
 }
 
-#define PK_TIES 3
+#define PK_TIES 7          /* exact ties kept besides the winner: a vertex of valence 8 (the first version kept 3 and sent every
+                              closest-to-a-vertex query — 18 % of the tie list of far-away lattice points — into the igl-order re-walk) */
+#define TT_STRIDE (PK_TIES + 1)
 struct Packet {
 	V3 p;
 	double best;
@@ -310,10 +312,22 @@ __device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_
 // true iff igl's depth-first order for query p reaches facet fa before facet fb: decided at their lowest common
 // ancestor, where igl looks first at the child that contains p or is nearer (AABB.cpp:392-437).
 __device__ __forceinline__ bool igl_visits_first(const QNode *__restrict__ nodes, const int32_t *__restrict__ prim_parent,
-                                                 const V3 &p, int32_t fa, int32_t fb)
+                                                 const V3 &p, int32_t fa, int32_t fb, const int2 *__restrict__ pd = nullptr)
 {
 	int32_t na = prim_parent[fa], nb = prim_parent[fb];
 	int32_t ca = ~fa, cb = ~fb;                      // child reference through which each side enters the ancestor
+	if (pd) {
+		// the climb reads 8 bytes per node from a table that stays in L2 (16 MB at 2 M facets) instead of a 128-byte node line
+		// from DRAM (ncu launch list, C4 step: the tie-break was 16 % of the step, 6.8 ms for 7.6 M queries)
+		int2 a = __ldg(pd + na), b = __ldg(pd + nb);
+		while (a.y > b.y) { ca = na; na = a.x; a = __ldg(pd + na); }
+		while (b.y > a.y) { cb = nb; nb = b.x; b = __ldg(pd + nb); }
+		while (na != nb) { ca = na; na = a.x; a = __ldg(pd + na); cb = nb; nb = b.x; b = __ldg(pd + nb); }
+		const QNode *n = nodes + na;
+		const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
+		const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
+		return (n->left == ca) == left_first;
+	}
 	int da = nodes[na].depth, db = nodes[nb].depth;
 	while (da > db) { ca = na; na = nodes[na].parent; --da; }
 	while (db > da) { cb = nb; nb = nodes[nb].parent; --db; }
@@ -333,12 +347,12 @@ __device__ __forceinline__ bool igl_visits_first(const QNode *__restrict__ nodes
 // fails (then only the walk in igl's order can tell).
 __device__ __forceinline__ int32_t igl_tie_winner(const QNode *__restrict__ nodes, const int32_t *__restrict__ prim_parent,
                                                   const double *__restrict__ tri, const V3 &p, double dmin, int32_t bf,
-                                                  const int32_t *__restrict__ ties, int stride, int nt)
+                                                  const int32_t *__restrict__ ties, int stride, int nt, const int2 *__restrict__ pd = nullptr)
 {
 	int32_t win = bf;
 	for (int j = 0; j < nt; ++j) {
 		const int32_t f = ties[j * stride];
-		if (igl_visits_first(nodes, prim_parent, p, f, win)) win = f;
+		if (igl_visits_first(nodes, prim_parent, p, f, win, pd)) win = f;
 	}
 	const double *t = tri + 9 * (int64_t)win;
 	const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
@@ -523,7 +537,7 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			if (code == TODO_WALK) {
 				const int slot = bw + __popc(mw & lt);
 				todo[slot] = (int32_t)i;
-				int32_t *tr = todo_ties + 4 * (int64_t)slot;
+				int32_t *tr = todo_ties + TT_STRIDE * (int64_t)slot;
 				tr[0] = nt;
 				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? ties[32 * j] : -1;
 			} else if (code == TODO_SEARCH) {
@@ -775,7 +789,7 @@ cp_wide_kernel(const WNode *__restrict__ wnodes, const double *__restrict__ tri,
 			if (code == TODO_WALK) {
 				const int sl = bw + __popc(mw & lt);
 				todo[sl] = (int32_t)i;
-				int32_t *tr = todo_ties + 4 * (int64_t)sl;
+				int32_t *tr = todo_ties + TT_STRIDE * (int64_t)sl;
 				tr[0] = nt;
 				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? ties[32 * j] : -1;
 			} else if (code == TODO_SEARCH) {
@@ -1192,7 +1206,7 @@ cp_pair_kernel(const WNode *__restrict__ wnodes, const float4 *__restrict__ trif
 			if (code == TODO_WALK) {
 				const int sl = bw + __popc(mw & lt);
 				todo[sl] = (int32_t)i;
-				int32_t *tr = todo_ties + 4 * (int64_t)sl;
+				int32_t *tr = todo_ties + TT_STRIDE * (int64_t)sl;
 				tr[0] = nt;
 				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < nt ? s.tie[warp][j][lane] : -1;
 			} else if (code == TODO_SEARCH) {
@@ -1258,7 +1272,7 @@ __global__ void __launch_bounds__(128)
 cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
               const double *__restrict__ P, const int32_t *__restrict__ todo, const int32_t *__restrict__ todo_ties,
               int32_t *__restrict__ counters, double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C,
-              int32_t *__restrict__ heavy, int walk_budget, SignArgs sa)
+              int32_t *__restrict__ heavy, int walk_budget, SignArgs sa, const int2 *__restrict__ pd, bool count_walks = false)
 {
 	const int n_todo = counters[0];
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_todo; t += gridDim.x * blockDim.x) {
@@ -1266,11 +1280,11 @@ cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__res
 		const V3 p = ld3(P + 3 * i);
 		const double best = S[i];
 		const int32_t bf = I[i];
-		const int nt = todo_ties[4 * (int64_t)t];
+		const int nt = todo_ties[TT_STRIDE * (int64_t)t];
 		int32_t ties[PK_TIES];
-		for (int j = 0; j < PK_TIES; ++j) ties[j] = todo_ties[4 * (int64_t)t + 1 + j];
+		for (int j = 0; j < PK_TIES; ++j) ties[j] = todo_ties[TT_STRIDE * (int64_t)t + 1 + j];
 		int32_t win = -1;
-		if (nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, p, best, bf, ties, 1, nt);
+		if (nt <= PK_TIES) win = igl_tie_winner(nodes, prim_parent, tri, p, best, bf, ties, 1, nt, pd);
 		if (win >= 0) {
 			V3 c;
 			if (win != bf) {
@@ -1282,12 +1296,14 @@ cp_tie_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__res
 			finalize_sign(sa, i, p, win, c, best, S);
 		} else {
 			Hit h;
+			if (count_walks) atomicAdd(counters + 5, 1);
 			if (traverse_limited(nodes, root, tri, p, best + best * PK_EPS_WALK, best, walk_budget, h)) {
 				I[i] = h.f;
 				C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z;
 				S[i] = h.sqr_d;
 				finalize_sign(sa, i, p, h.f, h.c, h.sqr_d, S);
 			} else {
+				if (count_walks) atomicAdd(counters + 6, 1);
 				heavy[atomicAdd(counters + 1, 1)] = (int32_t)i;      // S[i] stays a valid upper bound for K3
 			}
 		}
@@ -1379,7 +1395,7 @@ cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			else if (finished && k.near > 1) {
 				const int slot = bw + __popc(mw & lt);          // the walk list grows from the front, we consume from the back
 				todo[slot] = (int32_t)i;
-				int32_t *tr = todo_ties + 4 * (int64_t)slot;
+				int32_t *tr = todo_ties + TT_STRIDE * (int64_t)slot;
 				tr[0] = k.nt;
 				for (int j = 0; j < PK_TIES; ++j) tr[1 + j] = j < k.nt ? ties[j] : -1;
 			}
@@ -1694,7 +1710,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 			perm = q.perm.p;
 		}
 		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
-		q.todo.alloc(2 * np, s); q.todo_ties.alloc(4 * np, s); q.heavy.alloc(np, s);
+		q.todo.alloc(2 * np, s); q.todo_ties.alloc(TT_STRIDE * np, s); q.heavy.alloc(np, s);
 		q.cnt.alloc(8, s);                                 // walk entries, heavy entries, search entries, next search entry, next packet
 		FPOHM_CUDA(cudaMemsetAsync(q.cnt.p, 0, 8 * sizeof(int32_t), s));
 		SignArgs sa = {m->V.p, m->F.p, m->nF, m->FN.p, m->VN.p, m->EN.p, m->EMAP.p, stats ? nullptr : N, (with_sign && (S || N)) ? 1 : 0};
@@ -1711,10 +1727,17 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, s>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search, sa);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, sa);
+		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, sa, m->node_pd.p, getenv("FPOHM_CP_COUNTERS") != nullptr);
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, sa);
 		FPOHM_LAUNCH_CHECK(ctx);
+		static const bool counters = getenv("FPOHM_CP_COUNTERS") != nullptr;      // debug: work-list sizes on stderr (synchronises)
+		if (counters) {
+			int32_t hc[8] = {};
+			FPOHM_CUDA(cudaMemcpyAsync(hc, q.cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+			fprintf(stderr, "[fpohm cp] %lld queries: tie-break list %d, heavy list %d, search list %d, tie walks %d, walk give-ups %d\n", (long long)np, hc[0], hc[1], hc[2], hc[5], hc[6]);
+		}
 		return;
 	}
 	const int blk = 128;
@@ -1735,7 +1758,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		if (!C) { q.tmpC.alloc(3 * np, s); C = q.tmpC.p; }
 		if (!S) { q.tmpS.alloc(np, s); S = q.tmpS.p; }
 		const int pgrid = (int)((np + 127) / 128);        // one CTA per 128 queries: the block scheduler balances uneven packets
-		q.todo.alloc(2 * np, s); q.todo_ties.alloc(4 * np, s); q.heavy.alloc(np, s);
+		q.todo.alloc(2 * np, s); q.todo_ties.alloc(TT_STRIDE * np, s); q.heavy.alloc(np, s);
 		q.cnt.alloc(4, s);                                 // walk entries, heavy entries, search entries, next search entry
 		FPOHM_CUDA(cudaMemsetAsync(q.cnt.p, 0, 4 * sizeof(int32_t), s));
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
@@ -1750,7 +1773,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_search_kernel<<<ctx->sm_count * 5, blk, 0, sc>>>(m->qfnodes.p, m->qroot, m->tri.p, P_dev, np, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_search, no_sign);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, no_sign);
+		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, no_sign, nullptr);
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, no_sign);
 	} else {

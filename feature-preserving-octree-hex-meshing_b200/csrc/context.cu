@@ -120,6 +120,28 @@ void arena_stats(Arena *a, size_t *reserved, size_t *in_use) {
 	if (in_use) *in_use = a->in_use;
 }
 
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_side_pool[64] = {};
+cudaMemPool_t side_pool() {
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+	return g_side_pool[dev];
+}
+static void side_pool_ensure(int device) {
+	std::lock_guard<std::mutex> l(g_pool_mu);
+	if (device < 0 || device >= 64 || g_side_pool[device]) return;
+	cudaMemPoolProps props = {};
+	props.allocType = cudaMemAllocationTypePinned;
+	props.handleTypes = cudaMemHandleTypeNone;
+	props.location.type = cudaMemLocationTypeDevice;
+	props.location.id = device;
+	cudaMemPool_t pool = nullptr;
+	if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return; }
+	uint64_t thr = UINT64_MAX;
+	cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+	g_side_pool[device] = pool;
+}
+
 static thread_local std::string g_err;
 void set_error(const char *fmt, ...) {
 	char buf[1024];
@@ -168,6 +190,7 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	FPOHM_CUDA(cudaEventCreate(&c->ev1));
 	// (the device's default stream-ordered pool is left as the process configured it: this context's buffers live in its own arena)
 	c->arena = arena_create(device, c->stream);
+	side_pool_ensure(device);
 	*out = c;
 	FPOHM_API_END
 }
@@ -195,6 +218,7 @@ int fpohm_ctx_trim(fpohm_ctx *ctx, int64_t *bytes_released) {
 	DeviceGuard g(ctx->device);
 	FPOHM_CUDA(cudaStreamSynchronize(ctx->stream));
 	const size_t f = arena_trim(ctx->arena);
+	if (cudaMemPool_t pool = side_pool()) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
 	if (bytes_released) *bytes_released = (int64_t)f;
 	FPOHM_API_END
 }

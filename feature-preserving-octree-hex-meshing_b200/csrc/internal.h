@@ -63,6 +63,10 @@ Arena *arena_create(int device, cudaStream_t main_stream);
 void arena_destroy(Arena *a);
 size_t arena_trim(Arena *a);                             // bytes returned to the driver
 void arena_stats(Arena *a, size_t *reserved, size_t *in_use);
+// Buffers on any OTHER stream (scratch of the _dev entry points on the caller's stream, lanes of the host pipelines) are
+// stream-ordered allocations from a PRIVATE pool of the library, one per device, which keeps what is freed (the entry points
+// are called in loops) — not from the device's default pool, whose configuration belongs to the process.
+cudaMemPool_t side_pool();                               // pool of the current device; nullptr before the first context
 
 // Plain device buffer: arena memory on a context's main stream, stream-ordered allocation elsewhere.
 template <class T>
@@ -88,6 +92,7 @@ struct DevBuf {
 			const auto t0 = g_alloc_probe ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
 			arena = arena_for_stream(stream);
 			if (arena) p = (T *)arena_alloc(arena, sizeof(T) * (size_t)count);
+			else if (cudaMemPool_t pool = side_pool()) FPOHM_CUDA(cudaMallocFromPoolAsync((void **)&p, sizeof(T) * (size_t)count, pool, stream));
 			else FPOHM_CUDA(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)count, stream));
 			if (g_alloc_probe) { g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++g_alloc_calls; }
 		}

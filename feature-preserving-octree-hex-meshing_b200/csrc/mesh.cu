@@ -157,6 +157,11 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	}
 	m->prim_parent.alloc((int64_t)pp.size(), s);
 	m->prim_parent.upload(pp.data(), (int64_t)pp.size());
+	std::vector<int2> pd((size_t)std::max<int32_t>(ni, 1));
+	for (int32_t i = 0; i < ni; ++i) pd[(size_t)i] = make_int2(q[(size_t)i].parent, q[(size_t)i].depth);
+	m->node_pd.alloc((int64_t)pd.size(), s);
+	m->node_pd.upload(pd.data(), (int64_t)pd.size());
+	FPOHM_CUDA(cudaStreamSynchronize(s));      // pd is a local
 	// fp32 filter copy, boxes rounded outwards
 	auto f_dn = [](double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; };
 	auto f_up = [](double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; };

@@ -81,6 +81,7 @@ struct fpohm_mesh {
 	int32_t qdepth = 0;            // deepest internal node
 	fpohm::DevBuf<fpohm::QNodeF> qfnodes;
 	fpohm::DevBuf<int32_t> prim_parent; // internal node holding facet f as a child
+	fpohm::DevBuf<int2> node_pd;        // (parent, depth) per internal node: 8 B instead of a 128-byte QNode line for the tie-break's walks to a common ancestor
 	int64_t n_wnodes = 0;
 	fpohm::DevBuf<fpohm::WNode> wnodes; // 8-wide collapse (node 0 = root); empty when nF < 2
 	fpohm::DevBuf<float4> trif;         // 3 float4 per facet: vertices rounded to nearest float (fp32 refine filter)

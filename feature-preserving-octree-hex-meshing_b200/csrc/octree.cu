@@ -888,6 +888,15 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 	FPOHM_CUDA(cudaStreamSynchronize(s));
 }
 
+__global__ void gather_cells_kernel(const int32_t *__restrict__ ids, int64_t n, const uint8_t *__restrict__ level, const uint64_t *__restrict__ code,
+                                    const int32_t *__restrict__ first_child, uint8_t *__restrict__ l, uint64_t *__restrict__ c, int32_t *__restrict__ f)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t id = ids[i];
+		l[i] = level[id]; c[i] = code[id]; f[i] = first_child[id];
+	}
+}
+
 // leaf codes of the level-l cells of an already numbered octree (cells of one level are a contiguous id range)
 __global__ void old_leaf_codes_kernel(const uint64_t *__restrict__ code, const int32_t *__restrict__ first_child, int64_t id0, int64_t n,
                                       uint64_t *__restrict__ out)
@@ -1204,26 +1213,32 @@ int fpohm_octree_refine(fpohm_octree *o, const fpohm_mesh *mesh, const int32_t *
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
 	const int blk = 256;
-	// listed LEAF cells, per level (host: the list is the pipeline's tb_subdivided_cells, small)
-	std::vector<uint8_t> lvl((size_t)o->n_cells);
-	std::vector<uint64_t> code((size_t)o->n_cells);
-	std::vector<int32_t> fc((size_t)o->n_cells);
-	o->cell_level.download(lvl.data(), o->n_cells);
-	o->cell_code.download(code.data(), o->n_cells);
-	o->cell_first_child.download(fc.data(), o->n_cells);
-	FPOHM_CUDA(cudaStreamSynchronize(s));
+	// listed LEAF cells, per level.  The list is the pipeline's tb_subdivided_cells (short); its (level, code, leaf) triples are
+	// gathered on the device — the first version downloaded the whole cell table for this (13 B x n_cells: 740 MB at the C3 size,
+	// once per pass of the outer loop, ghm.cpp:518-521).
+	for (int64_t i = 0; i < n; ++i)
+		FPOHM_REQUIRE(cell_ids[i] >= 0 && cell_ids[i] < o->n_cells, FPOHM_EINVAL, "fpohm_octree_refine: cell id %d out of range", cell_ids[i]);
+	std::vector<uint8_t> lvl((size_t)n);
+	std::vector<uint64_t> code((size_t)n);
+	std::vector<int32_t> fc((size_t)n);
+	if (n > 0) {
+		DevBuf<int32_t> dids(n, s), gfc(n, s);
+		DevBuf<uint8_t> glvl(n, s);
+		DevBuf<uint64_t> gcode(n, s);
+		dids.upload(cell_ids, n);
+		gather_cells_kernel<<<grid_for(ctx, n, blk), blk, 0, s>>>(dids.p, n, o->cell_level.p, o->cell_code.p, o->cell_first_child.p, glvl.p, gcode.p, gfc.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		glvl.download(lvl.data(), n); gcode.download(code.data(), n); gfc.download(fc.data(), n);
+		FPOHM_CUDA(cudaStreamSynchronize(s));
+	}
 	std::vector<std::set<uint64_t>> L((size_t)o->depth + 1);
 	for (int64_t i = 0; i < n; ++i) {
-		const int32_t id = cell_ids[i];
-		FPOHM_REQUIRE(id >= 0 && id < o->n_cells, FPOHM_EINVAL, "fpohm_octree_refine: cell id %d out of range", id);
-		if (fc[(size_t)id] >= 0) continue; // octree.cpp:694: only leaves are queued
-		const int extent = 1 << (o->depth - lvl[(size_t)id]);
+		if (fc[(size_t)i] >= 0) continue; // octree.cpp:694: only leaves are queued
+		const int extent = 1 << (o->depth - lvl[(size_t)i]);
 		if (extent <= stop_extent || extent <= 1) continue;
-		L[lvl[(size_t)id]].insert(code[(size_t)id]);
+		L[lvl[(size_t)i]].insert(code[(size_t)i]);
 	}
 	mesh_ensure_pred(ctx, const_cast<fpohm_mesh *>(mesh), s);
-	const double bx = o->prm.mesh_transform[0] + o->prm.origin[0], by = o->prm.mesh_transform[1] + o->prm.origin[1],
-	             bz = o->prm.mesh_transform[2] + o->prm.origin[2];
 	// P_l = old internal cells of level l  ∪  listed leaves whose predicate is true
 	std::vector<DevBuf<uint64_t>> P; std::vector<int64_t> nP;
 	const int top = std::max(o->n_levels, o->depth + 1);
@@ -1235,20 +1250,9 @@ int fpohm_octree_refine(fpohm_octree *o, const fpohm_mesh *mesh, const int32_t *
 		if (n_old) FPOHM_CUDA(cudaMemcpyAsync(merged.p, o->icode.p + o->lvl_off[l], 8 * (size_t)n_old, cudaMemcpyDeviceToDevice, s));
 		int64_t n_new = 0;
 		if (!cand.empty()) {
-			DevBuf<uint64_t> dc((int64_t)cand.size(), s), sel((int64_t)cand.size(), s);
-			DevBuf<uint8_t> flag((int64_t)cand.size(), s);
-			DevBuf<int64_t> cnt(1, s);
+			DevBuf<uint64_t> dc((int64_t)cand.size(), s), sel;
 			dc.upload(cand.data(), (int64_t)cand.size());
-			predicate_kernel<<<grid_for(ctx, (int64_t)cand.size(), blk), blk, 0, s>>>(dc.p, (int64_t)cand.size(), o->depth - l, bx, by, bz,
-				o->prm.voxel_size, mesh->pred_box.p, mesh->pred_nodes / 2, flag.p, PRED_BUDGET);
-			FPOHM_LAUNCH_CHECK(ctx);
-			size_t tb = 0;
-			FPOHM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, dc.p, flag.p, sel.p, cnt.p, (int64_t)cand.size(), s));
-			DevBuf<uint8_t> tmp((int64_t)tb, s);
-			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, dc.p, flag.p, sel.p, cnt.p, (int64_t)cand.size(), s));
-			ctx->launches += 2;
-			cnt.download(&n_new, 1);
-			FPOHM_CUDA(cudaStreamSynchronize(s));
+			n_new = test_cells(o, mesh, l, dc.p, (int64_t)cand.size(), sel);      // warp-per-cell kernel for short lists, FPOHM_PRED_BUDGET honoured
 			if (n_new) FPOHM_CUDA(cudaMemcpyAsync(merged.p + n_old, sel.p, 8 * (size_t)n_new, cudaMemcpyDeviceToDevice, s));
 			FPOHM_CUDA(cudaStreamSynchronize(s));
 		}

@@ -23,7 +23,13 @@ using namespace fpohm;
 
 namespace {
 
+// Hit lists have a per-call capacity: 32 per column / cell to begin with (a handful is typical).  The kernels keep counting past
+// the capacity and report the largest count; a call that overflowed is repeated with the next capacity that fits (128, 512,
+// 2048) — the reference collects hits in a std::vector (voxelization.h:248-256) and stacked sheets or finned parts do
+// cross a column more than 32 times.  Beyond 2048 hits in one column the call fails with FPOHM_ERANGE.
 constexpr int HIT_CAP = 32;
+constexpr int HIT_CAP_MAX = 2048;
+inline int next_hit_cap(int need) { for (int c : {32, 128, 512, 2048}) if (need <= c) return c; return 0; }
 
 // voxelization.cpp:57-68
 __device__ __forceinline__ int orientation(double x1, double y1, double x2, double y2, double &twice_signed_area) {
@@ -69,6 +75,7 @@ __device__ __forceinline__ int intersect_ray_z(const double *__restrict__ t, dou
 struct ColumnGrid {      // VoxelGrid / DexelGrid columns
 	double ox, oy, spacing;
 	int nx, ny;
+	int cap;             // capacity of a column's hit list in this pass
 };
 
 // gather hits of the vertical ray through (qx,qy); facets are pre-filtered by the reference's xy box [bx0,bx1]x[by0,by1]
@@ -87,7 +94,8 @@ __device__ __forceinline__ int gather_hits(const double *__restrict__ box, int64
 			double z;
 			const int s = intersect_ray_z(tri + 9 * (int64_t)order[nd - P], qx, qy, z);
 			if (s) {
-				if (n < cap) { hz[n] = z; hs[n] = (int8_t)s; ++n; } else overflow = true;
+				if (n < cap) { hz[n] = z; hs[n] = (int8_t)s; } else overflow = true;
+				++n;      // keeps counting: the caller learns how much room the retry needs
 			}
 			continue;
 		}
@@ -149,10 +157,11 @@ __device__ __forceinline__ void append_hit(const ColumnGrid &g, int x, int y, do
                                            int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag, int32_t *__restrict__ hit_ev, double oz, int nz)
 {
 	const int64_t col = (int64_t)y * g.nx + x;
+	const int cap = g.cap;
 	const int slot = atomicAdd(&hit_n[col], 1);
-	if (slot >= HIT_CAP) atomicExch(overflow_flag, 1);
-	else if (hit_ev) hit_ev[col * HIT_CAP + slot] = (first_layer_above(z, oz, g.spacing, nz) << 2) | (s + 1);
-	else { hit_z[col * HIT_CAP + slot] = z; hit_s[col * HIT_CAP + slot] = (int8_t)s; }
+	if (slot >= cap) atomicMax(overflow_flag, slot + 1);      // largest count seen: what the retry must hold
+	else if (hit_ev) hit_ev[col * cap + slot] = (first_layer_above(z, oz, g.spacing, nz) << 2) | (s + 1);
+	else { hit_z[col * cap + slot] = z; hit_s[col * cap + slot] = (int8_t)s; }
 }
 
 // Rectangle of columns per facet.  Facets covering at most RECT_INLINE columns (the common case on fine meshes) are
@@ -254,18 +263,19 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b) {          // bits [
 // A dirty chunk's 32 layer bits are worked out here as well, once, and stored at dmask[chunk * ncol + col] (coalesced over
 // neighbouring columns): the fill then reads 4 bytes per dirty chunk instead of re-walking the column's 128-byte event list
 // (ncu: 0.24 GB of reads and a third of the fill's instructions at 1024^3 before).
+template <int CAP>
 __global__ void __launch_bounds__(256)
 column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
                       uint32_t *__restrict__ sum, uint32_t *__restrict__ dmask)
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
-		const int n = min(hit_n[col], HIT_CAP);
-		const int32_t *ev = hit_ev + col * HIT_CAP;
+		const int n = min(hit_n[col], CAP);
+		const int32_t *ev = hit_ev + col * CAP;
 		if (n == 0) {
 			for (int w = 0; w < 2 * n_words; ++w) sum[(int64_t)w * ncol + col] = 0u;
 			continue;
 		}
-		int32_t e[HIT_CAP];
+		int32_t e[CAP];
 		for (int i = 0; i < n; ++i) {                       // insertion sort by k0 (order among equal k0 is irrelevant)
 			const int32_t v = ev[i];
 			int j = i - 1;
@@ -364,34 +374,36 @@ voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, co
 }
 
 // DexelGrid: sorted hits reduced to entry/exit events, voxelization.h:312-321
+template <int CAP>
 __global__ void dexel_reduce_kernel(int64_t ncol, double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
                                     int64_t *__restrict__ count)
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
-		const int n = min(hit_n[col], HIT_CAP);
-		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
-		for (int i = 0; i < n; ++i) { hz[i] = hit_z[col * HIT_CAP + i]; hs[i] = hit_s[col * HIT_CAP + i]; }
+		const int n = min(hit_n[col], CAP);
+		double hz[CAP]; int8_t hs[CAP];
+		for (int i = 0; i < n; ++i) { hz[i] = hit_z[col * CAP + i]; hs[i] = hit_s[col * CAP + i]; }
 		sort_hits(hz, hs, n);
 		int m = 0;
 		for (int i = 0, s = 0; i < n; ++i) {
 			const int ds = hs[i];
 			s += ds;
-			if ((s == -1 && ds < 0) || (s == 0 && ds > 0)) hit_z[col * HIT_CAP + m++] = hz[i];
+			if ((s == -1 && ds < 0) || (s == 0 && ds > 0)) hit_z[col * CAP + m++] = hz[i];
 		}
 		hit_n[col] = m;
 		count[col] = m;
 	}
 }
-__global__ void dexel_emit_kernel(int64_t ncol, const double *__restrict__ hit_z, const int32_t *__restrict__ hit_n,
+__global__ void dexel_emit_kernel(int64_t ncol, int cap, const double *__restrict__ hit_z, const int32_t *__restrict__ hit_n,
                                   const int64_t *__restrict__ off, double *__restrict__ values)
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
 		const int n = hit_n[col];
-		for (int i = 0; i < n; ++i) values[off[col] + i] = hit_z[col * HIT_CAP + i];
+		for (int i = 0; i < n; ++i) values[off[col] + i] = hit_z[col * cap + i];
 	}
 }
 
 // compute_sign(OctreeGrid), voxelization.cpp:114-158: one thread per cell (ALL cells, leaves and internal)
+template <int CAP>
 __global__ void __launch_bounds__(128)
 cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int64_t n_cells, int depth,
                  double ox, double oy, double oz, double spacing, const double *__restrict__ box, int64_t P,
@@ -407,10 +419,10 @@ cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ c
 		const double bx1 = bx0 + spacing * extent, by1 = by0 + spacing * extent;
 		const double cx = bx0 + 0.5 * spacing * extent, cy = by0 + 0.5 * spacing * extent;
 		const double cz = oz + spacing * z + 0.5 * spacing * extent;
-		double hz[HIT_CAP]; int8_t hs[HIT_CAP];
+		double hz[CAP]; int8_t hs[CAP];
 		bool ov = false;
-		const int n = gather_hits(box, P, order, tri, bx0, bx1, by0, by1, cx, cy, hz, hs, HIT_CAP, ov);
-		if (ov) atomicExch(overflow_flag, 1);
+		int n = gather_hits(box, P, order, tri, bx0, bx1, by0, by1, cx, cy, hz, hs, CAP, ov);
+		if (ov) { atomicMax(overflow_flag, n); n = CAP; }
 		sort_hits(hz, hs, n);
 		int num_before = 0;
 		for (int i = 0, s = 0; i < n; ++i) {
@@ -431,7 +443,7 @@ void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitS
                      double oz = 0, int nz = 0)
 {
 	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
-	if (voxel_events) h.ev.alloc(ncol * HIT_CAP, s); else { h.z.alloc(ncol * HIT_CAP, s); h.s.alloc(ncol * HIT_CAP, s); }
+	if (voxel_events) h.ev.alloc(ncol * g.cap, s); else { h.z.alloc(ncol * g.cap, s); h.s.alloc(ncol * g.cap, s); }
 	h.n.alloc(ncol, s); h.ov.alloc(1, s);
 	h.ov.zero(); h.n.zero();
 	DevBuf<int4> rect(nF, s);
@@ -450,11 +462,15 @@ void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitS
 	FPOHM_LAUNCH_CHECK(ctx);
 }
 
-void check_overflow(HitScratch &h, cudaStream_t s, const char *who) {
+// 0 if every list fitted, else the capacity the pass has to be repeated with (FPOHM_ERANGE beyond HIT_CAP_MAX)
+int overflow_retry_cap(DevBuf<int32_t> &ov_flag, cudaStream_t s, const char *who) {
 	int32_t ov = 0;
-	h.ov.download(&ov, 1);
+	ov_flag.download(&ov, 1);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
-	FPOHM_REQUIRE(ov == 0, FPOHM_ERANGE, "%s: more than %d ray/facet hits in one column", who, HIT_CAP);
+	if (ov == 0) return 0;
+	const int cap = next_hit_cap(ov);
+	FPOHM_REQUIRE(cap > 0, FPOHM_ERANGE, "%s: %d ray/facet hits in one column (the limit is %d)", who, ov, HIT_CAP_MAX);
+	return cap;
 }
 
 void check_dims(const int32_t *dims, int nd, const char *who) {
@@ -492,14 +508,20 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	              "fpohm_voxel_sign_slab_dev: slab [%d,%d) must be non-empty, inside [0,%d) and aligned to %d layers", z_begin, z_end, dims[2], FILL_Z);
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = (cudaStream_t)stream;
+	for (int cap = HIT_CAP;;) {      // optimistic pass; repeated with more room only if a column overflowed (read-back at the end)
 	HitScratch h;
-	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1]};
+	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1], cap};
 	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
 	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s, true, grid_origin[2], dims[2]);
 	const int gz = (dims[2] + FILL_Z - 1) / FILL_Z, n_words = (gz + 31) / 32;
 	const int64_t ncol = (int64_t)dims[0] * dims[1];
 	DevBuf<uint32_t> summary(2 * n_words * ncol, s), dmask((int64_t)gz * ncol, s);      // dmask is only written / read where a chunk is dirty
-	column_summary_kernel<<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p);
+	switch (cap) {
+	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
+	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
+	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
+	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
+	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
 	static const int fill_ch = getenv("FPOHM_FILL_CH") ? atoi(getenv("FPOHM_FILL_CH")) : FILL_CH_DEFAULT;
@@ -513,7 +535,10 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
-	check_overflow(h, s, "fpohm_voxel_sign");
+	const int retry = overflow_retry_cap(h.ov, s, "fpohm_voxel_sign");
+	if (!retry) break;
+	cap = retry;
+	}
 	FPOHM_API_END
 }
 
@@ -553,29 +578,39 @@ int fpohm_dexel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_o
 	check_dims(dims2, 2, "fpohm_dexel_sign");
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
-	HitScratch h;
-	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims2[0], dims2[1]};
 	const int64_t ncol = (int64_t)dims2[0] * dims2[1];
 	KernelTimer t(ctx, s);
-	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
 	DevBuf<int64_t> cnt(ncol + 1, s), off(ncol + 1, s);
-	cnt.zero();
-	dexel_reduce_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p);
-	FPOHM_LAUNCH_CHECK(ctx);
-	size_t tb = 0;
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, ncol + 1, s));
-	DevBuf<uint8_t> tmp((int64_t)tb, s);
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, ncol + 1, s));
-	ctx->launches += 2;
-	int64_t tot = 0;
-	FPOHM_CUDA(cudaMemcpyAsync(&tot, off.p + ncol, 8, cudaMemcpyDeviceToHost, s));
-	check_overflow(h, s, "fpohm_dexel_sign");
-	*total = tot;
-	if (values) {
-		DevBuf<double> dv(tot, s);
-		dexel_emit_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.n.p, off.p, dv.p);
+	for (int cap = HIT_CAP;;) {
+		HitScratch h;
+		const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims2[0], dims2[1], cap};
+		run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
+		cnt.zero();
+		switch (cap) {
+		case 32: dexel_reduce_kernel<32><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
+		case 128: dexel_reduce_kernel<128><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
+		case 512: dexel_reduce_kernel<512><<<grid_for(ctx, ncol, 128, 4), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
+		default: dexel_reduce_kernel<2048><<<grid_for(ctx, ncol, 128, 2), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
+		}
 		FPOHM_LAUNCH_CHECK(ctx);
-		dv.download(values, tot);
+		size_t tb = 0;
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, ncol + 1, s));
+		DevBuf<uint8_t> tmp((int64_t)tb, s);
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, ncol + 1, s));
+		ctx->launches += 2;
+		int64_t tot = 0;
+		FPOHM_CUDA(cudaMemcpyAsync(&tot, off.p + ncol, 8, cudaMemcpyDeviceToHost, s));
+		const int retry = overflow_retry_cap(h.ov, s, "fpohm_dexel_sign");
+		if (retry) { cap = retry; continue; }
+		*total = tot;
+		if (values) {
+			DevBuf<double> dv(tot, s);
+			dexel_emit_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, cap, h.z.p, h.n.p, off.p, dv.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			dv.download(values, tot);
+			FPOHM_CUDA(cudaStreamSynchronize(s));
+		}
+		break;
 	}
 	t.stop();
 	if (offsets) off.download(offsets, ncol + 1);
@@ -593,17 +628,26 @@ int fpohm_octree_cell_sign(const fpohm_octree *o, const fpohm_mesh *mesh, const 
 	mesh_ensure_pred(ctx, m, s);
 	DevBuf<float> d(o->n_cells, s);
 	DevBuf<int32_t> ov(1, s);
-	ov.zero();
 	KernelTimer t(ctx, s);
-	cell_sign_kernel<<<grid_for(ctx, o->n_cells, 128, 16), 128, 0, s>>>(o->cell_level.p, o->cell_code.p, o->n_cells, o->depth,
-		origin[0], origin[1], origin[2], spacing, m->pred_box.p, m->pred_nodes / 2, m->pred_order.p, m->tri.p, d.p, ov.p);
-	FPOHM_LAUNCH_CHECK(ctx);
+	for (int cap = HIT_CAP;;) {
+		ov.zero();
+#define FPOHM_CELL_SIGN(C, CTAS) cell_sign_kernel<C><<<grid_for(ctx, o->n_cells, 128, CTAS), 128, 0, s>>>(o->cell_level.p, o->cell_code.p, o->n_cells, o->depth, \
+			origin[0], origin[1], origin[2], spacing, m->pred_box.p, m->pred_nodes / 2, m->pred_order.p, m->tri.p, d.p, ov.p)
+		switch (cap) {
+		case 32: FPOHM_CELL_SIGN(32, 16); break;
+		case 128: FPOHM_CELL_SIGN(128, 8); break;
+		case 512: FPOHM_CELL_SIGN(512, 4); break;
+		default: FPOHM_CELL_SIGN(2048, 1); break;
+		}
+#undef FPOHM_CELL_SIGN
+		FPOHM_LAUNCH_CHECK(ctx);
+		const int retry = overflow_retry_cap(ov, s, "fpohm_octree_cell_sign");
+		if (!retry) break;
+		cap = retry;
+	}
 	t.stop();
-	int32_t hov = 0;
-	ov.download(&hov, 1);
 	d.download(inside, o->n_cells);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
-	FPOHM_REQUIRE(hov == 0, FPOHM_ERANGE, "fpohm_octree_cell_sign: more than %d ray/facet hits for one cell", HIT_CAP);
 	FPOHM_API_END
 }
 

@@ -174,21 +174,43 @@ def test_edge_cases_octree(fp, ctx, ref):
     o.close(); m.close()
 
 
-def test_ray_hit_capacity_is_reported_not_truncated(fp, ctx):
-    # 40 stacked sheets: more than 32 ray/facet hits in one column must fail loudly (FPOHM_ERANGE), not clip
-    quads = []
+def _stacked_sheets(n_sheets):
     Vs, Fs = [], []
-    for k in range(40):
-        z = 0.01 * k
+    for k in range(n_sheets):
+        z = 0.6 * (k + 0.37) / n_sheets
         b = len(Vs)
         Vs += [[-1, -1, z], [1, -1, z], [1, 1, z], [-1, 1, z]]
-        Fs += [[b, b + 1, b + 2], [b, b + 2, b + 3]]
-    V = np.array(Vs, float); F = np.array(Fs, np.int32)
+        # alternate orientation: entry / exit sheets, so the parity rule has something to count
+        Fs += [[b, b + 1, b + 2], [b, b + 2, b + 3]] if k % 2 == 1 else [[b, b + 2, b + 1], [b, b + 3, b + 2]]
+    return np.array(Vs, float), np.array(Fs, np.int32)
+
+
+@pytest.mark.parametrize("n_sheets", [40, 150, 600])
+def test_ray_hit_lists_grow_with_the_input(fp, ctx, ref, n_sheets):
+    """More than 32 ray/facet hits in one column: the reference collects them in a std::vector (voxelization.h:248-256), round 1
+    refused with FPOHM_ERANGE.  The pass is now repeated with a larger list (128 / 512 / 2048) and must equal the reference for
+    all three grid flavours — stacked alternating sheets, 40 .. 600 hits per column."""
+    V, F = _stacked_sheets(n_sheets)
     m = fp.TriMesh(ctx, V, F)
-    g = fp.VoxelGrid([-0.5, -0.5, -0.1], [1, 1, 0.6], 0.05, 0)
+    org, ext, sp = np.array([-0.5, -0.5, -0.1]), np.array([1.0, 1.0, 0.8]), 0.05
+    g = fp.VoxelGrid(org, ext, sp, 0)
+    vox = fp.compute_sign_voxels(ctx, m, g)
+    rv, _ = ref.voxel_sign(V, F, org, ext, sp, 0)
+    assert np.array_equal(vox.reshape(-1), rv.reshape(-1))
+    off, val = fp.compute_sign_dexels(ctx, m, g)
+    roff, rval, _ = ref.dexel_sign(V, F, org, ext, sp, 0)
+    assert np.array_equal(off, roff) and np.array_equal(val, rval)
+    assert len(val) > 0 and vox.any()
+    m.close()
+
+
+def test_ray_hit_lists_have_a_documented_limit(fp, ctx):
+    V, F = _stacked_sheets(2100)
+    m = fp.TriMesh(ctx, V, F)
+    g = fp.VoxelGrid([-0.5, -0.5, -0.1], [1, 1, 0.8], 0.25, 0)
     with pytest.raises(fp.FpohmError) as e:
         fp.compute_sign_voxels(ctx, m, g)
-    assert e.value.code == -5
+    assert e.value.code == -5      # FPOHM_ERANGE: more than 2048 hits in one column
     m.close()
 
 
