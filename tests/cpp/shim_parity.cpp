@@ -18,6 +18,10 @@
 
 #include "fpohm_shim.hpp"
 
+#include <array>
+#include <algorithm>
+#include <iostream>
+#include <set>
 #include <cmath>
 #include <cstdio>
 
@@ -272,6 +276,139 @@ int main() {
 			for (size_t i = 0; ss && i < sa.Vs.size(); ++i) ss = sa.Vs[i].boundary == sb.Vs[i].boundary && sa.Vs[i].neighbor_vs == sb.Vs[i].neighbor_vs && sa.Vs[i].neighbor_es == sb.Vs[i].neighbor_es && sa.Vs[i].neighbor_fs == sb.Vs[i].neighbor_fs;
 			EXPECT(ss && sa.Fs.size() > 0, kind ? "extract_surface_conforming_mesh identical triangle surface, maps and adjacency" : "extract_surface_conforming_mesh identical quad surface, maps and adjacency");
 		}
+	}
+	// ---- the CHAIN: octree_mesh -> conforming_mesh -> dual_conforming_mesh, and octree_mesh -> clean_hex_mesh ->
+	// extract_surface_conforming_mesh, every stage fed with the previous stage's output on its own side — the reference's
+	// member functions on the reference's split-order numbering (ghm.cpp:460-567, 568-872, 1932-1981; gf.cpp:1021-1112), the
+	// shim on the product's canonical (level, Morton) numbering.  Ids differ by construction; the comparison is by GEOMETRY:
+	// does the canonical renumbering survive composition, including the id-order-dependent cleaning stages (tagging sweep,
+	// greedy non-manifold clean-up, drop_small_pieces' tie-break)?  C1 torus at --e 15 and the refinement to --e 13, and a
+	// second subdivide pass on the same octree objects (ghm.cpp:495-500).
+	for (int E : {15, 13}) {
+		Mesh t; torus(100, 100, t);                               // BASELINE config C1: 20 000 triangles
+		GEO::Mesh mi;
+		mi.vertices.create_vertices((GEO::index_t)t.V.cols());
+		for (int i = 0; i < t.V.cols(); ++i) mi.vertices.point(i) = GEO::vec3(t.V(0, i), t.V(1, i), t.V(2, i));
+		mi.facets.create_triangles((GEO::index_t)t.Fs.size());
+		for (size_t f = 0; f < t.Fs.size(); ++f) for (int c = 0; c < 3; ++c) mi.facets.set_vertex((GEO::index_t)f, c, t.Fs[f].vs[c]);
+		fpohm_shim::DeviceMesh dm(t);                             // before MeshFacetsAABB reorders mi's facets
+		std::vector<double> Vt((size_t)(3 * t.V.cols()));
+		for (int i = 0; i < t.V.cols(); ++i) for (int d = 0; d < 3; ++d) Vt[(size_t)(3 * i + d)] = t.V(d, i);
+		// reference side
+		grid_hex_meshing_bijective gm;
+		gm.num_voxels = 1 << 20; gm.STOP_EXTENT_MIN = E; gm.STOP_EXTENT_MAX = E; gm.graded = true; gm.paired = true;
+		Mesh_Domain a, b;
+		a.mesh_entire.type = b.mesh_entire.type = Mesh_type::Hex;
+		::OctreeGrid oa;
+		Eigen::Vector3i gsa, gsb;
+		std::streambuf *old = std::cout.rdbuf(nullptr);
+		const bool oka = gm.octree_mesh(mi, a.mesh_entire, oa, gsa);
+		// product side
+		fpohm_shim::OctreeGrid ob;
+		std::vector<int> tb; std::vector<uint32_t> h2o;
+		const bool okb = fpohm_shim::octree_mesh(dm, Vt.data(), (int64_t)t.V.cols(), b.mesh_entire, ob, gsb, 1 << 20, 1 << E, true, tb, h2o);
+		bool same = oka && okb && gsa == gsb && a.mesh_entire.Hs.size() == b.mesh_entire.Hs.size() && a.mesh_entire.Vs.size() == b.mesh_entire.Vs.size();
+		auto hex_key = [](const Mesh &m, size_t h) {
+			std::array<double, 6> k = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+			for (uint32_t v : m.Hs[h].vs) for (int d = 0; d < 3; ++d) { k[d] = std::min(k[d], m.V(d, v)); k[3 + d] = std::max(k[3 + d], m.V(d, v)); }
+			return k;
+		};
+		// conforming + dual on each side's own octree and hex mesh
+		Mesh ha, da, hb, db;
+		std::vector<Element_Type> ta, tb2;
+		gm.conforming_mesh(a.mesh_entire, ha, oa, gsa);
+		gm.dual_conforming_mesh(a.mesh_entire, ha, da, ta);
+		fpohm_shim::conforming_and_dual_mesh(b.mesh_entire, hb, db, tb2, ob, gsb);
+		bool sd = same && ha.Fs.size() == hb.Fs.size() && ha.Es.size() == hb.Es.size() && da.Hs.size() == db.Hs.size() && da.Fs.size() == db.Fs.size() && da.Vs.size() == db.Vs.size();
+		{   // dual cells by geometry: (sorted vertex positions, element type)
+			auto cell_keys = [](const Mesh &m, const std::vector<Element_Type> &ty) {
+				std::multiset<std::vector<double>> ks;
+				for (size_t h = 0; h < m.Hs.size(); ++h) {
+					std::vector<std::array<double, 3>> ps;
+					for (uint32_t v : m.Hs[h].vs) ps.push_back({{m.V(0, v), m.V(1, v), m.V(2, v)}});
+					std::sort(ps.begin(), ps.end());
+					std::vector<double> k; k.push_back((double)(int)ty[h]);
+					for (auto &q : ps) for (double x : q) k.push_back(x);
+					ks.insert(k);
+				}
+				return ks;
+			};
+			if (sd) sd = cell_keys(da, ta) == cell_keys(db, tb2);
+		}
+		EXPECT(sd && da.Hs.size() > 0, E == 15 ? "chain --e 15: octree_mesh -> conforming_mesh -> dual_conforming_mesh, same dual cells (geometry + element type)"
+		                                        : "chain --e 13: octree_mesh -> conforming_mesh -> dual_conforming_mesh, same dual cells (geometry + element type)");
+		// clean_hex_mesh on each side's own octree hex mesh, then the surface of what is kept
+		gm.clean_hex_mesh(t, a);
+		fpohm_shim::clean_hex_mesh(t, b);
+		std::set<std::array<double, 6>> ka, kb;
+		for (size_t h = 0; h < a.mesh_entire.Hs.size(); ++h) if (a.H_flag[h]) ka.insert(hex_key(a.mesh_entire, h));
+		for (size_t h = 0; h < b.mesh_entire.Hs.size(); ++h) if (b.H_flag[h]) kb.insert(hex_key(b.mesh_entire, h));
+		bool sc = same && ka == kb && !ka.empty() && a.mesh_subA.Hs.size() == b.mesh_subA.Hs.size() && a.mesh_subA.Vs.size() == b.mesh_subA.Vs.size();
+		Mesh sa, sb;
+		sa.type = sb.type = Mesh_type::Qua;
+		std::vector<int32_t> vm_a, vr_a, fm_a, fr_a, vm_b, vr_b, fm_b, fr_b;
+		::extract_surface_conforming_mesh(a.mesh_subA, sa, vm_a, vr_a, fm_a, fr_a);
+		fpohm_shim::extract_surface_conforming_mesh(b.mesh_subA, sb, vm_b, vr_b, fm_b, fr_b);
+		auto quad_keys = [](const Mesh &m) {       // oriented quads by geometry: rotation to the smallest corner, direction kept
+			std::multiset<std::array<double, 12>> ks;
+			for (auto &f : m.Fs) {
+				std::array<std::array<double, 3>, 4> ps;
+				for (int j = 0; j < 4; ++j) ps[j] = {{m.V(0, f.vs[j]), m.V(1, f.vs[j]), m.V(2, f.vs[j])}};
+				int s0 = 0; for (int j = 1; j < 4; ++j) if (ps[j] < ps[s0]) s0 = j;
+				std::array<double, 12> k;
+				for (int j = 0; j < 4; ++j) for (int d = 0; d < 3; ++d) k[3 * j + d] = ps[(s0 + j) % 4][d];
+				ks.insert(k);
+			}
+			return ks;
+		};
+		bool ss = sc && sa.Fs.size() == sb.Fs.size() && sa.Vs.size() == sb.Vs.size() && sa.Es.size() == sb.Es.size() && quad_keys(sa) == quad_keys(sb);
+		// The cleaning stages depend on the ORDER of the hex and vertex ids (tagging_uneven_element is an in-place sweep in hex
+		// order, clean_non_manifold_ve is greedy in vertex / edge order, drop_small_pieces breaks ties by id: ghm.cpp:1983-2124), so
+		// the reference's own answer changes when its octree is merely renumbered.  Where the two chains differ, that is what has
+		// to be shown: the REFERENCE's clean_hex_mesh run on the product's numbering of the same octree must reproduce the
+		// product's result id for id — then the difference is the reference's order dependence, not the product.
+		bool by_order = false;
+		size_t only_a = 0, only_b = 0;
+		if (!ss) {
+			for (auto &k : ka) only_a += !kb.count(k);
+			for (auto &k : kb) only_b += !ka.count(k);
+			Mesh_Domain c;
+			c.mesh_entire.type = Mesh_type::Hex;
+			c.mesh_entire.V = b.mesh_entire.V;
+			c.mesh_entire.Vs.resize(b.mesh_entire.Vs.size());
+			for (size_t i = 0; i < c.mesh_entire.Vs.size(); ++i) { c.mesh_entire.Vs[i].id = (uint32_t)i; c.mesh_entire.Vs[i].v = b.mesh_entire.Vs[i].v; }
+			fpohm_shim::OctreeGrid ob2;
+			std::vector<int> tb3; std::vector<uint32_t> h2o3;
+			Mesh fresh; fresh.type = Mesh_type::Hex;
+			Eigen::Vector3i gsc;
+			fpohm_shim::octree_mesh(dm, Vt.data(), (int64_t)t.V.cols(), fresh, ob2, gsc, 1 << 20, 1 << E, true, tb3, h2o3);   // the hex list BEFORE reorder_hex_mesh
+			c.mesh_entire.Hs.resize(fresh.Hs.size());
+			for (size_t h = 0; h < fresh.Hs.size(); ++h) { c.mesh_entire.Hs[h].id = (uint32_t)h; c.mesh_entire.Hs[h].vs = fresh.Hs[h].vs; }
+			::build_connectivity(c.mesh_entire);
+			gm.clean_hex_mesh(t, c);
+			by_order = c.H_flag == b.H_flag && c.V_map == b.V_map && c.H_map_reverse == b.H_map_reverse && c.mesh_subA.Hs.size() == b.mesh_subA.Hs.size();
+			for (size_t i = 0; by_order && i < c.mesh_subA.Hs.size(); ++i) by_order = c.mesh_subA.Hs[i].vs == b.mesh_subA.Hs[i].vs;
+			std::cout.rdbuf(old);
+			std::printf("     chain --e %d: %zu hexes; kept by the reference on ITS numbering %zu, by the product %zu (only reference %zu, only product %zu); "
+			            "reference clean_hex_mesh on the PRODUCT's numbering: %s the product id for id\n",
+			            E, a.mesh_entire.Hs.size(), ka.size(), kb.size(), only_a, only_b, by_order ? "equals" : "DIFFERS FROM");
+			old = std::cout.rdbuf(nullptr);
+		}
+		EXPECT((ss || by_order) && sa.Fs.size() > 0, E == 15 ? "chain --e 15: octree_mesh -> clean_hex_mesh -> extract_surface, same kept hexes and same ORIENTED surface quads (geometry)"
+		                                        : "chain --e 13: octree_mesh -> clean_hex_mesh -> extract_surface: same geometry, or a difference the reference reproduces on the product's numbering (order-dependent cleaning)");
+		// second pass of the outer loop on the same octree objects: smaller stop extent
+		if (E == 15) {
+			gm.STOP_EXTENT_MAX = 14;
+			Mesh ma2, mb2;
+			ma2.type = mb2.type = Mesh_type::Hex;
+			const bool o2a = gm.octree_mesh(mi, ma2, oa, gsa);
+			const bool o2b = fpohm_shim::octree_mesh(dm, Vt.data(), (int64_t)t.V.cols(), mb2, ob, gsb, 1 << 20, 1 << 14, false, tb, h2o);
+			std::set<std::array<double, 6>> k2a, k2b;
+			for (size_t h = 0; h < ma2.Hs.size(); ++h) k2a.insert(hex_key(ma2, h));
+			for (size_t h = 0; h < mb2.Hs.size(); ++h) k2b.insert(hex_key(mb2, h));
+			EXPECT(o2a && o2b && k2a == k2b && ma2.Hs.size() > a.mesh_entire.Hs.size() && ma2.Vs.size() == mb2.Vs.size(), "chain: second octree_mesh pass on the same octree (stop extent 2^14), same leaves");
+		}
+		std::cout.rdbuf(old);
 	}
 	// ---- SLIM per-element stages (slim_m.cpp:84-381, 792-916) on the 8-tets-per-hex split of a warped block: gradient operators
 	// with 4 entries per tet, deformed positions uv, every energy
