@@ -16,6 +16,7 @@ __all__ = [
     "octree_grid_setup", "host_igl_tree", "host_igl_normals", "scaled_jacobian", "scaled_jacobian_dev", "points_inside_mesh", "HexConnectivity", "classify_hexes", "conforming_mesh", "conforming_mesh_tables", "conforming_and_dual", "conforming_and_dual_tables", "voxel_lattice", "VoxelGrid", "compute_sign_voxels", "voxel_sign_dev", "voxel_sign_slab_dev",
     "voxel_occupancy", "compute_sign_dexels", "polyline_project", "hausdorff", "hausdorff_outliers",
     "reorder_hexes", "tag_uneven_elements", "reindex_submesh", "clean_non_manifold", "drop_small_pieces", "medial_surface_flags", "clean_hex_mesh", "extract_surface",
+    "MESH_TYPES", "write_mesh", "write_vtk", "read_fgraph", "write_fgraph",
     "SLIM_ENERGIES", "slim_jacobians", "slim_weights_rotations", "slim_energy", "slim_weights_rotations_dev", "slim_energy_dev", "slim_max_step", "slim_rhs_terms",
 ]
 
@@ -729,3 +730,39 @@ def voxel_lattice(ctx: Context, bb_min, bb_max, num_voxels: int):
     Vp = np.zeros((nv, 3)); hexa = np.zeros((nh, 8), np.uint32)
     _chk(lib().fpohm_voxel_lattice(ctx.h, _p(mn), _p(mx), C.c_int32(num_voxels), _p(Vp), _p(hexa)))
     return Vp, hexa, dim
+
+
+# ---- wire formats: h_io::write_hybrid_mesh_MESH / _VTK, read / write_feature_Graph_FGRAPH (io.cpp) ----------------
+MESH_TYPES = {"Tri": 0, "Qua": 1, "HSur": 2, "Tet": 3, "Hyb": 4, "Hex": 5}
+
+
+def write_mesh(path, V, mesh_type: str, elems):
+    V = _f64(V); el = np.ascontiguousarray(elems, np.uint32)
+    _chk(lib().fpohm_io_write_mesh(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int32(MESH_TYPES[mesh_type]), _p(el), C.c_int64(len(el))))
+
+
+def write_vtk(path, V, mesh_type: str, elems, V_boundary=None, elem_off=None):
+    V = _f64(V)
+    vb = np.ascontiguousarray(V_boundary, np.uint8) if V_boundary is not None else np.zeros(len(V), np.uint8)
+    if mesh_type == "Hyb":
+        off = np.ascontiguousarray(elem_off, np.int64); el = np.ascontiguousarray(elems, np.uint32).reshape(-1)
+        _chk(lib().fpohm_io_write_vtk(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int32(4), _p(off), _p(el), C.c_int64(len(off) - 1), C.c_int32(0),
+                                      _p(vb), C.c_int64(len(vb))))
+    else:
+        el = np.ascontiguousarray(elems, np.uint32)
+        _chk(lib().fpohm_io_write_vtk(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int32(MESH_TYPES[mesh_type]), None, _p(el), C.c_int64(len(el)),
+                                      C.c_int32(el.shape[1]), _p(vb), C.c_int64(len(vb))))
+
+
+def read_fgraph(path):
+    ang = C.c_double(); oc = C.c_int32(); ocs = C.c_int32(); nc = C.c_int64(0); npairs = C.c_int64(0)
+    _chk(lib().fpohm_io_read_fgraph(str(path).encode(), C.byref(ang), C.byref(oc), C.byref(ocs), None, C.byref(nc), None, C.byref(npairs)))
+    corners = np.zeros(max(nc.value, 1), np.int32); pairs = np.zeros((max(npairs.value, 1), 2), np.int32)
+    _chk(lib().fpohm_io_read_fgraph(str(path).encode(), C.byref(ang), C.byref(oc), C.byref(ocs), _p(corners), C.byref(nc), _p(pairs), C.byref(npairs)))
+    return dict(angle_threshold=ang.value, orphan_curve=oc.value, orphan_curve_single=ocs.value, corners=corners[:nc.value].copy(), pairs=pairs[:npairs.value].copy())
+
+
+def write_fgraph(path, angle_threshold, orphan_curve, orphan_curve_single, corners, pairs):
+    c = np.ascontiguousarray(corners, np.int32); p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+    _chk(lib().fpohm_io_write_fgraph(str(path).encode(), C.c_double(angle_threshold), C.c_int32(orphan_curve), C.c_int32(orphan_curve_single),
+                                     _p(c), C.c_int64(len(c)), _p(p), C.c_int64(len(p))))

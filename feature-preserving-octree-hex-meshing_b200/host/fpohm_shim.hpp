@@ -834,4 +834,42 @@ bool hausdorff_dis(MeshT &mesh0, MeshT &mesh1, std::vector<int> &outlierVs, doub
 	return true;
 }
 
+// ---- wire formats: h_io::write_hybrid_mesh_MESH / _VTK (io.cpp:295-325, 101-181), read_feature_Graph_FGRAPH (io.cpp:412-434).
+// Same files byte for byte; the rows are formatted by all host threads (fpohm_io_*).
+template <class MeshT>
+void write_hybrid_mesh_MESH(MeshT &hmi, const std::string &path) {
+	const int type = (int)hmi.type;
+	std::vector<uint32_t> el;
+	int64_t n = 0;
+	if (type == 0 || type == 2) { n = (int64_t)hmi.Fs.size(); el.reserve((size_t)(3 * n)); for (auto &f : hmi.Fs) for (int k = 0; k < 3; ++k) el.push_back(f.vs[(size_t)k]); }
+	else if (type == 5) { n = (int64_t)hmi.Hs.size(); el.reserve((size_t)(8 * n)); for (auto &h : hmi.Hs) for (uint32_t v : h.vs) el.push_back(v); }
+	check(fpohm_io_write_mesh(path.c_str(), hmi.V.data(), (int64_t)hmi.V.cols(), type, el.data(), n), "fpohm_io_write_mesh");
+}
+template <class MeshT>
+void write_hybrid_mesh_VTK(MeshT &hmi, const std::string &path) {
+	const int type = (int)hmi.type;
+	std::vector<uint32_t> el;
+	std::vector<int64_t> off;
+	std::vector<uint8_t> vb(hmi.Vs.size());
+	for (size_t i = 0; i < hmi.Vs.size(); ++i) vb[i] = hmi.Vs[i].boundary ? 1 : 0;
+	int64_t n = 0; int arity = 0;
+	if (type == 0 || type == 1) { n = (int64_t)hmi.Fs.size(); arity = n ? (int)hmi.Fs[0].vs.size() : 3; for (auto &f : hmi.Fs) for (int k = 0; k < arity; ++k) el.push_back(f.vs[(size_t)k]); }
+	else if (type == 4) { n = (int64_t)hmi.Fs.size(); off.push_back(0); for (auto &f : hmi.Fs) { for (uint32_t v : f.vs) el.push_back(v); off.push_back((int64_t)el.size()); } }
+	else { n = (int64_t)hmi.Hs.size(); arity = n ? (int)hmi.Hs[0].vs.size() : 8; for (auto &h : hmi.Hs) for (int k = 0; k < arity; ++k) el.push_back(h.vs[(size_t)k]); }
+	check(fpohm_io_write_vtk(path.c_str(), hmi.V.data(), (int64_t)hmi.V.cols(), type, type == 4 ? off.data() : nullptr, el.data(), n, arity, vb.data(), (int64_t)vb.size()),
+	      "fpohm_io_write_vtk");
+}
+template <class FeatureT>
+bool read_feature_Graph_FGRAPH(FeatureT &mf, const std::string &path) {
+	double ang = 0; int32_t oc = 0, ocs = 0; int64_t nc = 0, np = 0;
+	if (fpohm_io_read_fgraph(path.c_str(), &ang, &oc, &ocs, nullptr, &nc, nullptr, &np) != FPOHM_OK) return false;      // io.cpp:414
+	std::vector<int32_t> c((size_t)std::max<int64_t>(nc, 1)), p((size_t)std::max<int64_t>(2 * np, 2));
+	if (fpohm_io_read_fgraph(path.c_str(), &ang, &oc, &ocs, c.data(), &nc, p.data(), &np) != FPOHM_OK) return false;
+	mf.angle_threshold = ang; mf.orphan_curve = oc; mf.orphan_curve_single = ocs;
+	mf.IN_corners.assign(c.begin(), c.begin() + nc);
+	mf.IN_v_pairs.assign((size_t)np, {});
+	for (int64_t i = 0; i < np; ++i) { mf.IN_v_pairs[(size_t)i].push_back(p[(size_t)(2 * i)]); mf.IN_v_pairs[(size_t)i].push_back(p[(size_t)(2 * i + 1)]); }
+	return true;
+}
+
 } // namespace fpohm_shim

@@ -354,6 +354,25 @@ int fpohm_voxel_lattice_dims(const double bb_min[3], const double bb_max[3], int
 int fpohm_voxel_lattice(fpohm_ctx *ctx, const double bb_min[3], const double bb_max[3], int32_t num_voxels,
                         double *Vpos, uint32_t *hex);
 
+/* ---- wire formats, host code: ASCII files byte-identical to the reference's writers, rows formatted by
+ * all host threads.  V is xyz-interleaved (Mesh::V, 3 x n column-major).  mesh_type = the reference's Mesh_type
+ * (global_types.h:457-465: 0 Tri, 1 Qua, 2 HSur, 3 Tet, 4 Hyb, 5 Hex).
+ * _write_mesh:  h_io::write_hybrid_mesh_MESH (io.cpp:295-325): "Vertices", then "Triangles" (Tri / HSur, elems = 3 ids per
+ *               face) or "Hexahedra" (Hex, 8 ids per hex), ids written 1-based; other types get no element block, as there.
+ * _write_vtk:   h_io::write_hybrid_mesh_VTK (io.cpp:101-181): Tri / Qua faces, Hyb polygons (elem_off = CSR offsets,
+ *               n_elems + 1 entries), otherwise cells of `arity` vertices (Tet -> type 10, else 12); POINT_DATA "fixed" =
+ *               V_boundary for n_point_data entries (the reference writes hmi.Vs.size() of them).
+ * _read_fgraph: h_io::read_feature_Graph_FGRAPH (io.cpp:412-434), two-phase (NULL arrays: header and counts only);
+ *               pairs = 2 ids per feature edge.  A missing file is FPOHM_EINVAL (the reference returns false).
+ * _write_fgraph: h_io::write_feature_Graph_FGRAPH (io.cpp:435-446) for already selected corners / feature edges. */
+int fpohm_io_write_mesh(const char *path, const double *V, int64_t nV, int32_t mesh_type, const uint32_t *elems, int64_t n_elems);
+int fpohm_io_write_vtk(const char *path, const double *V, int64_t nV, int32_t mesh_type, const int64_t *elem_off, const uint32_t *elems,
+                       int64_t n_elems, int32_t arity, const uint8_t *V_boundary, int64_t n_point_data);
+int fpohm_io_read_fgraph(const char *path, double *angle_threshold, int32_t *orphan_curve, int32_t *orphan_curve_single,
+                         int32_t *corners, int64_t *n_corners, int32_t *pairs, int64_t *n_pairs);
+int fpohm_io_write_fgraph(const char *path, double angle_threshold, int32_t orphan_curve, int32_t orphan_curve_single,
+                          const int32_t *corners, int64_t n_corners, const int32_t *pairs, int64_t n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,13 +21,12 @@ STUB(_ZNK3tbb8internal32allocate_root_with_context_proxy4freeERNS_4taskE)
 STUB(_ZNK3tbb8internal32allocate_root_with_context_proxy8allocateEm)
 STUB(rtcCommit) STUB(rtcDeleteScene) STUB(rtcGetError) STUB(rtcInit) STUB(rtcIntersect)
 STUB(rtcMapBuffer) STUB(rtcNewScene) STUB(rtcNewTriangleMesh) STUB(rtcSetMask) STUB(rtcUnmapBuffer)
-// grid_hex_meshing.cpp is linked for conforming_mesh only; the SLIM optimiser and the .fgraph reader it references
-// elsewhere (optimization.cpp, io.cpp) are not built
+// grid_hex_meshing.cpp is linked for conforming_mesh only; the SLIM optimiser it references elsewhere (optimization.cpp) is
+// not built (io.cpp is: §8(f)-4)
 STUB(_ZN12optimization10slim_m_optER13Tetralize_Setjib)
 STUB(_ZN12optimization12slim_opt_iglER13Tetralize_Setj)
 STUB(_ZN12optimization9pipeline2Ev)
 STUB(_ZN12optimization18assign_constraintsERN5Eigen6MatrixIdLin1ELin1ELi0ELin1ELin1EEERSt6vectorI13Deform_V_TypeSaIS5_EE)
-STUB(_ZN4h_io25read_feature_Graph_FGRAPHER12Mesh_FeatureNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEE)
 // typeinfo object for tbb::task (data symbol)
 void *stub_ti_tbb_task[2] __asm__("_ZTIN3tbb4taskE") = {0, 0};
 }

@@ -468,3 +468,28 @@ def slim_rhs_terms(W, Ri):
     W = _f64(W).reshape(-1, 9); Ri = _f64(Ri).reshape(-1, 9); f = np.zeros(9 * len(W))
     lib().ref_slim_rhs_terms(_p(W), _p(Ri), C.c_int64(len(W)), _p(f))
     return f
+
+
+# ---- §8(f)-4: the reference's own h_io (io.cpp) -----------------------------------------------------------------------------
+def io_write_mesh(path, V, mesh_type: int, elems):
+    V = _f64(V); el = np.ascontiguousarray(elems, np.uint32)
+    lib().ref_io_write_mesh(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int(mesh_type), _p(el), C.c_int64(len(el)), C.c_int(el.shape[1]))
+
+
+def io_write_vtk(path, V, mesh_type: int, elems, V_boundary, elem_off=None):
+    V = _f64(V); vb = np.ascontiguousarray(V_boundary, np.uint8)
+    if elem_off is not None:
+        off = np.ascontiguousarray(elem_off, np.int64); el = np.ascontiguousarray(elems, np.uint32).reshape(-1)
+        lib().ref_io_write_vtk(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int(mesh_type), _p(off), _p(el), C.c_int64(len(off) - 1), C.c_int(0), _p(vb))
+    else:
+        el = np.ascontiguousarray(elems, np.uint32)
+        lib().ref_io_write_vtk(str(path).encode(), _p(V), C.c_int64(len(V)), C.c_int(mesh_type), None, _p(el), C.c_int64(len(el)), C.c_int(el.shape[1]), _p(vb))
+
+
+def io_read_fgraph(path):
+    ang = C.c_double(); oc = C.c_int(); ocs = C.c_int(); nc = C.c_int64(1 << 20); npairs = C.c_int64(1 << 20)
+    corners = np.zeros(1 << 20, np.int32); pairs = np.zeros((1 << 20, 2), np.int32)
+    ok = lib().ref_io_read_fgraph(str(path).encode(), C.byref(ang), C.byref(oc), C.byref(ocs), _p(corners), C.byref(nc), _p(pairs), C.byref(npairs))
+    if not ok:
+        return None
+    return dict(angle_threshold=ang.value, orphan_curve=oc.value, orphan_curve_single=ocs.value, corners=corners[:nc.value].copy(), pairs=pairs[:npairs.value].copy())

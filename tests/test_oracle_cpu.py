@@ -386,3 +386,56 @@ def test_golden_slim_matches_live_reference(ref):
     W, Ri = ref.slim_weights_rotations(g["J"], "SYMMETRIC_DIRICHLET", float(g["exp_factor"]))
     assert np.array_equal(W, g["SYMMETRIC_DIRICHLET_W"]) and np.array_equal(Ri, g["SYMMETRIC_DIRICHLET_Ri"])
     assert ref.slim_energy(g["J"], g["areas"], "CONFORMAL", float(g["exp_factor"])) == float(g["CONFORMAL_energy"])
+
+
+def test_io_wire_formats_byte_identical_to_reference(tmp_path):
+    """§8(f)-4: .mesh / .vtk writers and the .fgraph reader against the reference's own h_io (io.cpp compiled into oracle/_ref):
+    the files are compared BYTE for byte (doubles go through the same "%g", ids 1-based in .mesh), for every Mesh_type branch the
+    writers have; .fgraph is read back through both and written by the product."""
+    R = pytest.importorskip("oracle.ref_oracle")
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    import fpohm_b200 as fp
+    pm = fp.procedural
+    rng = np.random.default_rng(3)
+    Vt, Ft = pm.torus(40, 24)
+    Vt = Vt * np.array([1.0, 1e-3, 1e5]) + np.array([0.1, -2.5e-7, 123456.789])          # exponents on both sides of %g's switch to e-notation
+    Vt[:4] = [[0.0, -0.0, 1.0], [1e-5, 123456.5, 1234567.0], [0.0001, 100000.0, 999999.5], [-1.5e300, 2.5e-300, 3.0]]
+    Vh, H = pm.warped_hex_block(9, 0.3)
+    vb = (rng.random(len(Vh)) < 0.3).astype(np.uint8)
+    quads = H[:, [0, 1, 2, 3]]
+    tets = H[:, [0, 1, 3, 4]]
+    cases = [("Tri", Vt, Ft.astype(np.uint32)), ("HSur", Vt, Ft.astype(np.uint32)), ("Hex", Vh, H), ("Qua", Vh, quads)]
+    for name, V, el in cases:
+        a, b = tmp_path / f"{name}_ref.mesh", tmp_path / f"{name}_ours.mesh"
+        R.io_write_mesh(a, V, fp.MESH_TYPES[name], el)
+        fp.write_mesh(b, V, name, el)
+        assert a.read_bytes() == b.read_bytes(), name
+    for name, V, el in [("Tri", Vt, Ft.astype(np.uint32)), ("Qua", Vh, quads), ("Tet", Vh, tets), ("Hex", Vh, H)]:
+        v_b = vb if len(V) == len(Vh) else (np.arange(len(V)) % 3 == 0).astype(np.uint8)
+        a, b = tmp_path / f"{name}_ref.vtk", tmp_path / f"{name}_ours.vtk"
+        R.io_write_vtk(a, V, fp.MESH_TYPES[name], el, v_b)
+        fp.write_vtk(b, V, name, el, v_b)
+        assert a.read_bytes() == b.read_bytes(), name
+    # Hyb: polygons of 3..7 vertices in CSR
+    sizes = rng.integers(3, 8, 500)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    poly = rng.integers(0, len(Vh), off[-1]).astype(np.uint32)
+    a, b = tmp_path / "hyb_ref.vtk", tmp_path / "hyb_ours.vtk"
+    R.io_write_vtk(a, Vh, 4, poly, vb, off)
+    fp.write_vtk(b, Vh, "Hyb", poly, vb, off)
+    assert a.read_bytes() == b.read_bytes()
+    # .fgraph: the gear's crease edges, written by the product, read by both
+    gV, gF, crease = pm.gear(teeth=12, n_radial=4, n_axial=6, n_arc=2)
+    corners = np.unique(crease)[::7].astype(np.int32)
+    fg = tmp_path / "gear.fgraph"
+    fp.write_fgraph(fg, 30.5, 1, 0, corners, crease)
+    mine, ref = fp.read_fgraph(fg), R.io_read_fgraph(fg)
+    assert ref is not None
+    for k in ("angle_threshold", "orphan_curve", "orphan_curve_single"):
+        assert mine[k] == ref[k], k
+    assert np.array_equal(mine["corners"], ref["corners"]) and np.array_equal(mine["pairs"], ref["pairs"]) and len(mine["pairs"]) == len(crease)
+    assert np.array_equal(mine["pairs"], crease)
+    with pytest.raises(fp.FpohmError):
+        fp.read_fgraph(tmp_path / "missing.fgraph")
+    assert R.io_read_fgraph(tmp_path / "missing.fgraph") is None
