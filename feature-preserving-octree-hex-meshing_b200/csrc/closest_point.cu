@@ -1680,6 +1680,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		static const int64_t sort_min = getenv("FPOHM_CP_SORT_MIN") ? atoll(getenv("FPOHM_CP_SORT_MIN")) : (1 << 16);
 		static const int k2_search = getenv("FPOHM_K2_SEARCH") ? atoi(getenv("FPOHM_K2_SEARCH")) : K2_SEARCH_BUDGET;
 		static const int k2_walk = getenv("FPOHM_K2_WALK") ? atoi(getenv("FPOHM_K2_WALK")) : K2_WALK_BUDGET;
+		static const int minb = getenv("FPOHM_CP_MINB") ? atoi(getenv("FPOHM_CP_MINB")) : 6;      // debug A/B: CTAs per SM the packet kernel is compiled for
 		static const int b3_budget = getenv("FPOHM_CP_B3") ? atoi(getenv("FPOHM_CP_B3")) : 512;
 		static const int c_budget = getenv("FPOHM_CP_CB") ? atoi(getenv("FPOHM_CP_CB")) : 32;
 		FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "closest point: %lld queries in one launch", (long long)np);
@@ -1719,6 +1720,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		if (mode == 3 && m->nF < (1ll << 27)) {
 			const int pers = (int)std::min<int64_t>(pgrid, (int64_t)ctx->sm_count * 6);
 			if (stats && N) cp_pair_kernel<true, 3><<<pers, blk, 0, s>>>(m->wnodes.p, m->trif.p, m->tri.p, P_dev, np, perm, S, I, C, sa, m->eps_v, m->slack_q, q.todo.p, q.todo_ties.p, q.cnt.p, q.heavy.p, b3_budget, c_budget, N);
+			else if (minb == 5) cp_pair_kernel<false, 5><<<(int)std::min<int64_t>(pgrid, (int64_t)ctx->sm_count * 5), blk, 0, s>>>(m->wnodes.p, m->trif.p, m->tri.p, P_dev, np, perm, S, I, C, sa, m->eps_v, m->slack_q, q.todo.p, q.todo_ties.p, q.cnt.p, q.heavy.p, b3_budget, c_budget, nullptr);
 			else cp_pair_kernel<false, 6><<<pers, blk, 0, s>>>(m->wnodes.p, m->trif.p, m->tri.p, P_dev, np, perm, S, I, C, sa, m->eps_v, m->slack_q, q.todo.p, q.todo_ties.p, q.cnt.p, q.heavy.p, b3_budget, c_budget, nullptr);
 		} else if (stats && N) cp_wide_kernel<true, 4><<<pgrid, blk, 0, s>>>(m->wnodes.p, m->tri.p, P_dev, np, perm, S, I, C, sa, q.todo.p, q.todo_ties.p, q.cnt.p, N);
 		else cp_wide_kernel<false, 5><<<pgrid, blk, 0, s>>>(m->wnodes.p, m->tri.p, P_dev, np, perm, S, I, C, sa, q.todo.p, q.todo_ties.p, q.cnt.p, nullptr);

@@ -115,6 +115,21 @@ struct Builder {
 
 } // namespace
 
+// rank of every facet's barycentre on axis d in igl::sort's order (igl/AABB.cpp:63-88): the host half of the device tree build,
+// needed only for axes on which two barycentre coordinates are EQUAL (their order is libstdc++'s introsort's, tree_device.cu)
+void host_rank_axis(const double *V, const int32_t *F, int64_t nF, int d, int32_t *rank) {
+	std::vector<double> col((size_t)nF);
+	const double third = 1.0 / 3.0;
+	for (int64_t f = 0; f < nF; ++f) {
+		double s = 0.0;
+		s += V[3 * (int64_t)F[3 * f] + d]; s += V[3 * (int64_t)F[3 * f + 1] + d]; s += V[3 * (int64_t)F[3 * f + 2] + d];
+		col[(size_t)f] = s * third;
+	}
+	std::vector<size_t> order;
+	igl_sort_column(col, order);
+	for (size_t i = 0; i < (size_t)nF; ++i) rank[order[i]] = (int32_t)i;
+}
+
 void build_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, HostTree &out) {
 	(void)nV;
 	out.box.clear(); out.prim.clear(); out.lr.clear();

@@ -2,6 +2,7 @@
 #include "mesh.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
@@ -21,13 +22,6 @@ __global__ void gather_triangles_kernel(const double *__restrict__ V, const int3
 			tri[9 * f + 3 * k + 1] = V[3 * v + 1];
 			tri[9 * f + 3 * k + 2] = V[3 * v + 2];
 		}
-	}
-}
-
-__global__ void float_triangles_kernel(const double *__restrict__ tri, int64_t nF, float4 *__restrict__ out) {
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 3 * nF; t += (int64_t)gridDim.x * blockDim.x) {
-		const double *v = tri + 3 * t;
-		out[t] = make_float4((float)v[0], (float)v[1], (float)v[2], 0.f);
 	}
 }
 
@@ -123,135 +117,66 @@ void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 
 void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	if (m->has_tree) return;
-	build_igl_tree(m->hV.data(), m->nV, m->hF.data(), m->nF, m->htree);
-	build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
-	const HostTree &t = m->htree;
-	const size_t nn = t.prim.size();
-	std::vector<int32_t> internal_id(nn, -1);
-	int32_t ni = 0;
-	for (size_t i = 0; i < nn; ++i) if (t.prim[i] < 0) internal_id[i] = ni++;
-	std::vector<QNode> q((size_t)ni);
-	auto child_ref = [&](int32_t c) -> int32_t { return t.prim[c] >= 0 ? ~t.prim[c] : internal_id[c]; };
-	for (size_t i = 0; i < nn; ++i) {
-		if (t.prim[i] >= 0) continue;
-		QNode &n = q[(size_t)internal_id[i]];
-		const int32_t l = t.lr[2 * i], r = t.lr[2 * i + 1];
-		for (int c = 0; c < 3; ++c) {
-			n.lmin[c] = t.box[6 * (size_t)l + c]; n.lmax[c] = t.box[6 * (size_t)l + 3 + c];
-			n.rmin[c] = t.box[6 * (size_t)r + c]; n.rmax[c] = t.box[6 * (size_t)r + 3 + c];
-		}
-		n.left = child_ref(l); n.right = child_ref(r);
-		n.pad[0] = n.pad[1] = 0;
+	// igl::AABB::init: on the device (tree_device.cu; FPOHM_TREE_HOST=1 keeps the host builder for A/B), host for tiny meshes
+	static const bool host_tree = getenv("FPOHM_TREE_HOST") != nullptr;
+	static const bool timeline = getenv("FPOHM_TREE_TIMELINE") != nullptr;      // debug: stage times on stderr
+	auto now = []() { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+	const auto t0 = now();
+	const bool on_host = host_tree || m->nF < 64;
+	if (on_host) {
+		build_igl_tree(m->hV.data(), m->nV, m->hF.data(), m->nF, m->htree);
+		m->htree_valid = true;
+		m->t_box.alloc((int64_t)m->htree.box.size(), s); m->t_box.upload(m->htree.box.data(), (int64_t)m->htree.box.size());
+		m->t_prim.alloc((int64_t)m->htree.prim.size(), s); m->t_prim.upload(m->htree.prim.data(), (int64_t)m->htree.prim.size());
+	} else {
+		build_igl_tree_device(ctx, m, s, m->tree_ties_host);
 	}
-	// parents / depths (pre-order: a parent precedes its children)
-	int32_t maxd = 0;
-	if (ni) { q[0].parent = -1; q[0].depth = 0; }
-	for (int32_t i = 0; i < ni; ++i)
-		for (int32_t c : {q[(size_t)i].left, q[(size_t)i].right})
-			if (c >= 0) { q[(size_t)c].parent = i; q[(size_t)c].depth = q[(size_t)i].depth + 1; maxd = std::max(maxd, q[(size_t)c].depth); }
-	m->qdepth = maxd;
-	std::vector<int32_t> pp((size_t)std::max<int64_t>(m->nF, 1), -1);
-	for (int32_t i = 0; i < ni; ++i) {
-		if (q[(size_t)i].left < 0) pp[(size_t)~q[(size_t)i].left] = i;
-		if (q[(size_t)i].right < 0) pp[(size_t)~q[(size_t)i].right] = i;
+	const auto t1 = now();
+	static const bool host_normals = getenv("FPOHM_NORMALS_HOST") != nullptr;      // A/B: the host builder of round 1
+	if (host_normals) {
+		build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
+		m->hnormals_valid = true; m->nE = (int64_t)m->hE.size() / 2;
+		m->FN.alloc((int64_t)m->hFN.size(), s); m->FN.upload(m->hFN.data(), (int64_t)m->hFN.size());
+		m->VN.alloc((int64_t)m->hVN.size(), s); m->VN.upload(m->hVN.data(), (int64_t)m->hVN.size());
+		m->EN.alloc((int64_t)m->hEN.size(), s); m->EN.upload(m->hEN.data(), (int64_t)m->hEN.size());
+		m->EMAP.alloc((int64_t)m->hEMAP.size(), s); m->EMAP.upload(m->hEMAP.data(), (int64_t)m->hEMAP.size());
+		m->dE.alloc((int64_t)m->hE.size(), s); m->dE.upload(m->hE.data(), (int64_t)m->hE.size());
+	} else {
+		build_normals_device(ctx, m, s);
 	}
-	m->prim_parent.alloc((int64_t)pp.size(), s);
-	m->prim_parent.upload(pp.data(), (int64_t)pp.size());
-	std::vector<int2> pd((size_t)std::max<int32_t>(ni, 1));
-	for (int32_t i = 0; i < ni; ++i) pd[(size_t)i] = make_int2(q[(size_t)i].parent, q[(size_t)i].depth);
-	m->node_pd.alloc((int64_t)pd.size(), s);
-	m->node_pd.upload(pd.data(), (int64_t)pd.size());
-	FPOHM_CUDA(cudaStreamSynchronize(s));      // pd is a local
-	// fp32 filter copy, boxes rounded outwards
-	auto f_dn = [](double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; };
-	auto f_up = [](double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; };
-	std::vector<QNodeF> qf((size_t)std::max<int32_t>(ni, 1));
-	for (int32_t i = 0; i < ni; ++i) {
-		const QNode &n = q[(size_t)i];
-		QNodeF &f = qf[(size_t)i];
-		for (int c = 0; c < 3; ++c) {
-			f.lmin[c] = f_dn(n.lmin[c]); f.lmax[c] = f_up(n.lmax[c]);
-			f.rmin[c] = f_dn(n.rmin[c]); f.rmax[c] = f_up(n.rmax[c]);
-		}
-		f.left = n.left; f.right = n.right; f.pad[0] = f.pad[1] = 0;
-	}
-	m->qfnodes.alloc((int64_t)qf.size(), s);
-	m->qfnodes.upload(qf.data(), (int64_t)qf.size());
-	// 8-wide collapse for the box-parallel packet search: starting from a binary node's two children, the child with the
-	// most facets is opened until there are eight (igl's median splits are balanced by count, so this regroups three
-	// binary levels; a subtree of <= 8 facets becomes one all-facet node, a "cluster").
-	if (ni > 0) {
-		std::vector<int32_t> leaves(nn, 1);
-		for (size_t i = nn; i-- > 0;) if (t.prim[i] < 0) leaves[i] = leaves[(size_t)t.lr[2 * i]] + leaves[(size_t)t.lr[2 * i + 1]];
-		std::vector<WNode> w;
-		w.reserve((size_t)ni / 3 + 8);
-		std::vector<std::pair<int32_t, int32_t>> work;   // (binary node, wide node index)
-		w.emplace_back();
-		work.push_back({0, 0});
-		while (!work.empty()) {
-			const auto [b, wi] = work.back();
-			work.pop_back();
-			int32_t kids[8];
-			int nk = 2;
-			kids[0] = t.lr[2 * (size_t)b]; kids[1] = t.lr[2 * (size_t)b + 1];
-			while (nk < 8) {
-				int best = -1;
-				for (int k = 0; k < nk; ++k)
-					if (t.prim[(size_t)kids[k]] < 0 && (best < 0 || leaves[(size_t)kids[k]] > leaves[(size_t)kids[best]])) best = k;
-				if (best < 0) break;
-				const int32_t o = kids[best];
-				for (int k = nk; k > best + 1; --k) kids[k] = kids[k - 1];      // keep the binary tree's left-to-right order
-				kids[best] = t.lr[2 * (size_t)o]; kids[best + 1] = t.lr[2 * (size_t)o + 1];
-				++nk;
-			}
-			for (int k = 0; k < 8; ++k) {
-				WChild e;
-				if (k < nk) {
-					const size_t c = (size_t)kids[k];
-					for (int a = 0; a < 3; ++a) { e.lo[a] = f_dn(t.box[6 * c + a]); e.hi[a] = f_up(t.box[6 * c + 3 + a]); }
-					if (t.prim[c] >= 0) { e.child = ~t.prim[c]; e.flags = 0; }
-					else {
-						e.child = (int32_t)w.size();
-						e.flags = leaves[c] <= 8 ? 1 : 0;
-						w.emplace_back();
-						work.push_back({kids[k], e.child});
-					}
-				} else {
-					for (int a = 0; a < 3; ++a) { e.lo[a] = INFINITY; e.hi[a] = -INFINITY; }
-					e.child = WCHILD_EMPTY; e.flags = 0;
-				}
-				w[(size_t)wi].c[k] = e;
-			}
-		}
-		m->n_wnodes = (int64_t)w.size();
-		m->wnodes.alloc(m->n_wnodes, s);
-		m->wnodes.upload(w.data(), m->n_wnodes);
-		m->trif.alloc(3 * m->nF, s);
-		float_triangles_kernel<<<grid_for(ctx, 3 * m->nF, 256), 256, 0, s>>>(m->tri.p, m->nF, m->trif.p);
-		FPOHM_LAUNCH_CHECK(ctx);
-		double ev = 0, mc = 0;
-		for (int64_t v = 0; v < m->nV; ++v) {
-			double e2 = 0;
-			for (int a = 0; a < 3; ++a) {
-				const double x = m->hV[(size_t)(3 * v + a)], e = x - (double)(float)x;
-				e2 += e * e; mc = std::max(mc, std::fabs(x));
-			}
-			ev = std::max(ev, e2);
-		}
-		m->eps_v = f_up(std::sqrt(ev) * 1.000001);
-		m->slack_q = f_up(36.0 * 5.9604644775390625e-8 * mc * 1.01);
-		FPOHM_CUDA(cudaStreamSynchronize(s));
-	}
-	m->n_qnodes = ni;
-	m->qroot = nn ? (t.prim[0] >= 0 ? ~t.prim[0] : 0) : 0;
-	m->qnodes.alloc(std::max<int64_t>(ni, 1), s);
-	m->qnodes.upload(q.data(), ni);
-	m->FN.alloc((int64_t)m->hFN.size(), s); m->FN.upload(m->hFN.data(), (int64_t)m->hFN.size());
-	m->VN.alloc((int64_t)m->hVN.size(), s); m->VN.upload(m->hVN.data(), (int64_t)m->hVN.size());
-	m->EN.alloc((int64_t)m->hEN.size(), s); m->EN.upload(m->hEN.data(), (int64_t)m->hEN.size());
-	m->EMAP.alloc((int64_t)m->hEMAP.size(), s); m->EMAP.upload(m->hEMAP.data(), (int64_t)m->hEMAP.size());
-	FPOHM_CUDA(cudaStreamSynchronize(s)); // q is a local: the upload must finish before it dies
+	const auto t2 = now();
+	// QNode / QNodeF / prim_parent / (parent, depth) / 8-wide collapse / float triangles: on the device (tree_flatten.cu)
+	flatten_tree_device(ctx, m, s, m->t_box.p, m->t_prim.p);
+	m->qroot = m->nF == 1 ? ~0 : 0;      // a single facet: the root is the leaf ~0
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	if (timeline) fprintf(stderr, "[fpohm tree] %lld facets: igl tree %.1f ms (%s; host-sorted axes %d%d%d), normals %.1f ms, flattening + wide tree + uploads %.1f ms\n",
+	                      (long long)m->nF, ms(t0, t1), on_host ? "host" : "device", m->tree_ties_host[0], m->tree_ties_host[1], m->tree_ties_host[2],
+	                      ms(t1, t2), ms(t2, now()));
 	m->has_tree = true;
+}
+
+// host copy of the DFS pre-order arrays for fpohm_mesh_tree_export: box and prim come down from the device, the child ids follow
+// from the facet count (left = me + 1, right = me + 2 * ceil(n / 2))
+void mesh_host_tree(fpohm_mesh *m) {
+	if (m->htree_valid) return;
+	const int64_t nF = m->nF, nn = 2 * nF - 1;
+	HostTree &t = m->htree;
+	t.box.assign(6 * (size_t)nn, 0.0); t.prim.assign((size_t)nn, -1); t.lr.assign(2 * (size_t)nn, -1);
+	m->t_box.download(t.box.data(), 6 * nn);
+	m->t_prim.download(t.prim.data(), nn);
+	cudaStreamSynchronize(m->t_box.s);
+	std::vector<std::pair<int32_t, int32_t>> st;
+	st.push_back({0, (int32_t)nF});
+	while (!st.empty()) {
+		const auto [id, cnt] = st.back();
+		st.pop_back();
+		if (cnt <= 1) continue;
+		const int32_t nl = (cnt + 1) / 2;
+		t.lr[2 * (size_t)id] = id + 1; t.lr[2 * (size_t)id + 1] = id + 2 * nl;
+		st.push_back({id + 1, nl}); st.push_back({id + 2 * nl, cnt - nl});
+	}
+	m->htree_valid = true;
 }
 
 } // namespace fpohm
@@ -307,7 +232,7 @@ int fpohm_mesh_num_edges(const fpohm_mesh *mesh, int64_t *n_edges) {
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(mesh && n_edges, FPOHM_EINVAL, "fpohm_mesh_num_edges: null argument");
 	FPOHM_REQUIRE(mesh->has_tree, FPOHM_ESTATE, "fpohm_mesh_num_edges: call fpohm_mesh_build_query_tree first");
-	*n_edges = (int64_t)mesh->hE.size() / 2;
+	*n_edges = mesh->nE;
 	FPOHM_API_END
 }
 
@@ -315,6 +240,7 @@ int fpohm_mesh_normals(const fpohm_mesh *mesh, double *FN, double *VN, double *E
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(mesh, FPOHM_EINVAL, "fpohm_mesh_normals: null argument");
 	FPOHM_REQUIRE(mesh->has_tree, FPOHM_ESTATE, "fpohm_mesh_normals: call fpohm_mesh_build_query_tree first");
+	fpohm::mesh_host_normals(const_cast<fpohm_mesh *>(mesh));
 	if (FN) std::copy(mesh->hFN.begin(), mesh->hFN.end(), FN);
 	if (VN) std::copy(mesh->hVN.begin(), mesh->hVN.end(), VN);
 	if (EN) std::copy(mesh->hEN.begin(), mesh->hEN.end(), EN);
@@ -327,7 +253,7 @@ int fpohm_mesh_tree_nodes(const fpohm_mesh *mesh, int64_t *n_nodes) {
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(mesh && n_nodes, FPOHM_EINVAL, "fpohm_mesh_tree_nodes: null argument");
 	FPOHM_REQUIRE(mesh->has_tree, FPOHM_ESTATE, "fpohm_mesh_tree_nodes: call fpohm_mesh_build_query_tree first");
-	*n_nodes = (int64_t)mesh->htree.prim.size();
+	*n_nodes = 2 * mesh->nF - 1;
 	FPOHM_API_END
 }
 
@@ -335,6 +261,7 @@ int fpohm_mesh_tree_export(const fpohm_mesh *mesh, double *box, int32_t *prim, i
 	FPOHM_API_BEGIN
 	FPOHM_REQUIRE(mesh, FPOHM_EINVAL, "fpohm_mesh_tree_export: null argument");
 	FPOHM_REQUIRE(mesh->has_tree, FPOHM_ESTATE, "fpohm_mesh_tree_export: call fpohm_mesh_build_query_tree first");
+	fpohm::mesh_host_tree(const_cast<fpohm_mesh *>(mesh));
 	const fpohm::HostTree &t = mesh->htree;
 	if (box) std::copy(t.box.begin(), t.box.end(), box);
 	if (prim) std::copy(t.prim.begin(), t.prim.end(), prim);

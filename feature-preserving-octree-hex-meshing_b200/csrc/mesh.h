@@ -49,6 +49,7 @@ struct HostTree {
 };
 
 void build_igl_tree(const double *V, int64_t nV, const int32_t *F, int64_t nF, HostTree &out);
+void host_rank_axis(const double *V, const int32_t *F, int64_t nF, int d, int32_t *rank);
 void build_igl_normals(const double *V, int64_t nV, const int32_t *F, int64_t nF,
                        std::vector<double> &FN, std::vector<double> &VN, std::vector<double> &EN,
                        std::vector<int32_t> &E, std::vector<int32_t> &EMAP);
@@ -74,6 +75,10 @@ struct fpohm_mesh {
 
 	// query structure
 	bool has_tree = false;
+	int tree_ties_host[3] = {0, 0, 0};   // axes whose barycentre ranks came from the host sort (equal coordinates)
+	fpohm::DevBuf<double> t_box;         // igl tree in DFS pre-order (node 0 = root): box 6 per node, prim -1 for internal nodes
+	fpohm::DevBuf<int32_t> t_prim;
+	bool htree_valid = false;            // host copy (fpohm_mesh_tree_export) is made on demand
 	fpohm::HostTree htree;
 	int64_t n_qnodes = 0;
 	fpohm::DevBuf<fpohm::QNode> qnodes;
@@ -87,13 +92,23 @@ struct fpohm_mesh {
 	fpohm::DevBuf<float4> trif;         // 3 float4 per facet: vertices rounded to nearest float (fp32 refine filter)
 	float eps_v = 0.f;                  // >= max |v - float(v)| over the vertices
 	float slack_q = 0.f;                // >= the error of an fp32 barycentric combination of three vertices (36 u max|coordinate|)
-	std::vector<double> hFN, hVN, hEN;
+	std::vector<double> hFN, hVN, hEN;   // host copies for fpohm_mesh_normals, made on demand (mesh_host_normals)
 	std::vector<int32_t> hE, hEMAP;
+	bool hnormals_valid = false;
+	int64_t nE = 0;
+	fpohm::DevBuf<int32_t> dE;           // 2 per unique undirected edge
 	fpohm::DevBuf<double> FN, VN, EN;
 	fpohm::DevBuf<int32_t> EMAP;
 };
 
 namespace fpohm {
+// igl::AABB::init on the device (tree_device.cu): fills `out` exactly as build_igl_tree does.  ties_host[d] reports the axes whose
+// ranks had to come from the host sort.
+void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ties_host[3]);      // fills m->t_box / m->t_prim
+void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const double *box, const int32_t *prim);   // tree_flatten.cu
+void mesh_host_tree(fpohm_mesh *m);
+void build_normals_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);                           // normals_device.cu: FN / VN / EN / E / EMAP
+void mesh_host_normals(fpohm_mesh *m);                                                              // host copies, on demand                                                                 // host copy of the DFS arrays, on demand
 void mesh_ensure_pred(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
 void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);
 // head of clean_hex_mesh on device arrays: bbox centres -> signed distance -> flag = S < 0 (closest_point.cu)

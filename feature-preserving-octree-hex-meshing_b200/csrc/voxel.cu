@@ -160,7 +160,7 @@ __device__ __forceinline__ void append_hit(const ColumnGrid &g, int x, int y, do
 	const int cap = g.cap;
 	const int slot = atomicAdd(&hit_n[col], 1);
 	if (slot >= cap) atomicMax(overflow_flag, slot + 1);      // largest count seen: what the retry must hold
-	else if (hit_ev) hit_ev[col * cap + slot] = (first_layer_above(z, oz, g.spacing, nz) << 2) | (s + 1);
+	else if (hit_ev) hit_ev[(int64_t)slot * ((int64_t)g.nx * g.ny) + col] = (first_layer_above(z, oz, g.spacing, nz) << 2) | (s + 1);   // [slot][column]: the summary reads a slot of neighbouring columns in one line
 	else { hit_z[col * cap + slot] = z; hit_s[col * cap + slot] = (int8_t)s; }
 }
 
@@ -270,14 +270,14 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 {
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
 		const int n = min(hit_n[col], CAP);
-		const int32_t *ev = hit_ev + col * CAP;
+		const int32_t *ev = hit_ev + col;                    // event i of this column at ev[i * ncol]
 		if (n == 0) {
 			for (int w = 0; w < 2 * n_words; ++w) sum[(int64_t)w * ncol + col] = 0u;
 			continue;
 		}
 		int32_t e[CAP];
 		for (int i = 0; i < n; ++i) {                       // insertion sort by k0 (order among equal k0 is irrelevant)
-			const int32_t v = ev[i];
+			const int32_t v = ev[(int64_t)i * ncol];
 			int j = i - 1;
 			while (j >= 0 && (e[j] >> 2) > (v >> 2)) { e[j + 1] = e[j]; --j; }
 			e[j + 1] = v;

@@ -128,10 +128,19 @@ def build_octree_sharded(fp, ctx, mesh, params, comm, device=None, stats: dict |
     """fpohm_octree_build over `comm.world` z slabs (include/fpohm.h protocol).  Every rank returns the complete,
     canonically numbered octree, bit-identical to `fp.Octree.build` on one GPU.  `fp` is the fpohm_b200 module.
     `stats`, if given, receives halo sizes (codes sent per level) and the slab cut."""
+    import time
     device = device if device is not None else torch.device("cuda", ctx.device)
+    ph = {}
+
+    def tick(name, t0):
+        ctx.sync()
+        ph[name] = ph.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+    t0 = time.perf_counter()
     sh = fp.OctreeShard(ctx, mesh, params, comm.rank, comm.world)
     try:
         lmax = sh.refine()
+        t0 = tick("phase1_predicate_own_slab", t0)
         G = comm.allreduce_max(lmax, device)
         if stats is not None:
             stats.update(sh.info()); stats["halo_codes"] = {}; stats["global_max_level"] = G
@@ -140,11 +149,14 @@ def build_octree_sharded(fp, ctx, mesh, params, comm, device=None, stats: dict |
             buf = torch.empty(n, dtype=torch.int64, device=device)
             if n:
                 sh.outgoing_copy(buf.data_ptr())
+            t0 = tick("phase2_closure_own_slab", t0)
             got = comm.allgather_var(buf)
             _sync(got)
+            t0 = tick("phase2_halo_exchange", t0)
             sh.level_close(l, got.data_ptr() if got.numel() else 0, got.numel())
             if stats is not None:
                 stats["halo_codes"][l] = n
+        t0 = tick("phase2_closure_own_slab", t0)
         ptrs, counts, keep = [], [], []
         for l in range(G + 1):
             n = sh.level_result(l)
@@ -156,7 +168,12 @@ def build_octree_sharded(fp, ctx, mesh, params, comm, device=None, stats: dict |
             keep.append(got)
             ptrs.append(got.data_ptr() if got.numel() else 0)
             counts.append(got.numel())
-        return sh.finish(ptrs, counts)
+        t0 = tick("gather_closed_sets", t0)
+        out = sh.finish(ptrs, counts)
+        t0 = tick("phase3_numbering_replicated", t0)
+        if stats is not None:
+            stats["phase_ms"] = {k: round(v, 2) for k, v in ph.items()}
+        return out
     finally:
         sh.close()
 

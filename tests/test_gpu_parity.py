@@ -922,3 +922,41 @@ def test_slim_rhs_terms_bit_exact(fp, ctx, ref):
     ok = np.isfinite(W).all(1) & np.isfinite(Ri).all(1)
     got = fp.slim_rhs_terms(ctx, W[ok], Ri[ok]); want = ref.slim_rhs_terms(W[ok], Ri[ok])
     assert np.array_equal(got, want)
+
+
+def test_device_tree_build_identical_to_host_and_reference(fp, ctx, ref):
+    """a7: igl::AABB::init built ON THE DEVICE (tree_device.cu: radix sorts of the barycentre columns, level-synchronous median
+    splits) — box, primitive and child arrays of every node equal the host builder's and the compiled igl tree's, on meshes whose
+    barycentre coordinates are all distinct (no host involvement at all) and on meshes full of ties (symmetric gear, translated
+    tori, an axis-aligned grid: the tied axes take their ranks from the host's std::sort)."""
+    pm = fp.procedural
+    rng = np.random.default_rng(17)
+    Vt, Ft = pm.torus(60, 40)
+    Vj = Vt + rng.normal(0, 1e-4, Vt.shape)                       # generic position: no two barycentre coordinates equal
+    g = np.arange(13, dtype=np.float64) / 12
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    Vg = np.stack([X.reshape(-1), Y.reshape(-1), 0.1 * np.sin(3 * X.reshape(-1))], -1)      # grid: massive ties on x and y
+    q = np.arange(13 * 13).reshape(13, 13)
+    Fg = np.concatenate([np.stack([q[:-1, :-1], q[1:, :-1], q[1:, 1:]], -1).reshape(-1, 3),
+                         np.stack([q[:-1, :-1], q[1:, 1:], q[:-1, 1:]], -1).reshape(-1, 3)]).astype(np.int32)
+    cases = {"jittered torus": (Vj, Ft), "torus": (Vt, Ft), "gear": pm.gear(teeth=12, n_radial=4, n_axial=6, n_arc=2)[:2],
+             "tori": pm.linked_tori(2, 16, 8), "grid": (Vg, Fg), "gear full": pm.gear()[:2]}
+    for name, (V, F) in cases.items():
+        m = fp.TriMesh(ctx, V, F)
+        m.build_aabb_tree()
+        box, prim, lr = m.tree()
+        hbox, hprim, hlr = fp.host_igl_tree(V, F)
+        assert np.array_equal(prim, hprim) and np.array_equal(lr, hlr), name
+        assert np.array_equal(box, hbox), name
+        # the three normal sets + E / EMAP, built on the device (normals_device.cu; only acos of the corner angles runs on the host)
+        dn = m.normals()
+        hn = fp.host_igl_normals(V, F)
+        for a, b, what in zip(dn, hn, ("FN", "VN", "EN", "E", "EMAP")):
+            assert np.array_equal(a, b, equal_nan=True), (name, what)
+        if len(F) < 50000:
+            rt = ref.RefTree(V, F)
+            rbox, rprim, rlr = rt.flatten()
+            assert np.array_equal(prim, rprim) and np.array_equal(lr, rlr) and np.array_equal(box, rbox), name
+            rFN, rVN, rEN, rE, rEMAP = rt.normals()
+            assert np.array_equal(dn[0], rFN) and np.array_equal(dn[1], rVN, equal_nan=True) and np.array_equal(dn[2], rEN) and np.array_equal(dn[4], rEMAP), name
+        m.close()
