@@ -108,11 +108,14 @@ class Context:
 class TriMesh:
     """Device-resident triangle mesh (the reference's M_i / mf.tri) with lazily built trees."""
 
-    def __init__(self, ctx: Context, V, F):
+    def __init__(self, ctx: Context, V, F, cached: bool = False):
+        """cached=True: keyed on the content of (V, F) in the context (fpohm_mesh_upload_cached) — a surface seen before comes back
+        with its trees built; close() only drops the reference."""
         self.ctx = ctx
         self.V, self.F = _f64(V), _i32(F)
         self.h = C.c_void_p()
-        _chk(lib().fpohm_mesh_upload(ctx.h, _p(self.V), C.c_int64(len(self.V)), _p(self.F), C.c_int64(len(self.F)), C.byref(self.h)))
+        up = lib().fpohm_mesh_upload_cached if cached else lib().fpohm_mesh_upload
+        _chk(up(ctx.h, _p(self.V), C.c_int64(len(self.V)), _p(self.F), C.c_int64(len(self.F)), C.byref(self.h)))
 
     # build_aabb_tree, ghm.cpp:4231-4248
     def build_aabb_tree(self):
@@ -191,7 +194,7 @@ def host_igl_normals(V, F):
 
 # points_inside_mesh, gf.cpp:4024-4048
 def points_inside_mesh(ctx: Context, Ps, V, F):
-    m = TriMesh(ctx, V, F)
+    m = TriMesh(ctx, V, F, cached=True)      # the reference rebuilds its igl::AABB on every call (gf.cpp:4038)
     try:
         return m.signed_distance_pseudonormal(Ps, want=("S",))[0]
     finally:

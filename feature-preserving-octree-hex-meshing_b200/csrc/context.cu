@@ -199,6 +199,7 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	if (!ctx) return;
 	DeviceGuard g(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	fpohm_ctx_mesh_cache_clear(ctx);
 	for (int k = 0; k < fpohm_ctx::QRING; ++k) { cudaEventDestroy(ctx->q_ev0[k]); cudaEventDestroy(ctx->q_ev1[k]); }
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);

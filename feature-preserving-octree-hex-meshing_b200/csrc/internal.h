@@ -128,6 +128,11 @@ struct fpohm_ctx {
 	int64_t q_launches = 0;
 	int64_t launches = 0;
 	fpohm::Arena *arena = nullptr;
+	// content-keyed cache of uploaded surfaces (fpohm_mesh_upload_cached): points_inside_mesh rebuilds its tree on EVERY call in the
+	// reference (gf.cpp:4038) and the outer loop hands the same surface in again and again
+	struct CachedMesh { uint64_t h0, h1; int64_t nV, nF; struct ::fpohm_mesh *mesh; int refs; uint64_t stamp; };
+	std::vector<CachedMesh> mesh_cache;
+	uint64_t cache_clock = 0;
 };
 
 namespace fpohm {

@@ -215,9 +215,63 @@ int fpohm_mesh_upload(fpohm_ctx *ctx, const double *V, int64_t nV, const int32_t
 
 void fpohm_mesh_free(fpohm_mesh *mesh) {
 	if (!mesh) return;
+	if (mesh->cached) {      // a cached surface stays with its context; it goes when the cache evicts it or the context dies
+		for (auto &c : mesh->ctx->mesh_cache) if (c.mesh == mesh && c.refs > 0) --c.refs;
+		return;
+	}
 	DeviceGuard g(mesh->ctx->device);
 	cudaStreamSynchronize(mesh->ctx->stream);
 	delete mesh;
+}
+
+// 128 bits over the bytes of V and F (two multiply-xorshift lanes, 8 bytes at a time): a key, not a secret
+static void content_hash(const double *V, int64_t nV, const int32_t *F, int64_t nF, uint64_t &h0, uint64_t &h1) {
+	uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)nV, b = 0xc2b2ae3d27d4eb4full ^ (uint64_t)nF;
+	auto mix = [&](uint64_t x) {
+		a = (a ^ x) * 0xff51afd7ed558ccdull; a ^= a >> 29;
+		b = (b + x) * 0xc4ceb9fe1a85ec53ull; b ^= b >> 32;
+	};
+	const uint64_t *pv = reinterpret_cast<const uint64_t *>(V);
+	for (int64_t i = 0; i < 3 * nV; ++i) mix(pv[i]);
+	for (int64_t i = 0; i + 1 < 3 * nF; i += 2) mix((uint64_t)(uint32_t)F[i] | ((uint64_t)(uint32_t)F[i + 1] << 32));
+	if ((3 * nF) & 1) mix((uint64_t)(uint32_t)F[3 * nF - 1]);
+	h0 = a; h1 = b;
+}
+
+int fpohm_mesh_upload_cached(fpohm_ctx *ctx, const double *V, int64_t nV, const int32_t *F, int64_t nF, fpohm_mesh **out) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx && V && F && out && nV > 0 && nF > 0, FPOHM_EINVAL, "fpohm_mesh_upload_cached: bad argument");
+	uint64_t h0, h1;
+	content_hash(V, nV, F, nF, h0, h1);
+	for (auto &c : ctx->mesh_cache)
+		if (c.h0 == h0 && c.h1 == h1 && c.nV == nV && c.nF == nF) { ++c.refs; c.stamp = ++ctx->cache_clock; *out = c.mesh; return FPOHM_OK; }
+	fpohm_mesh *m = nullptr;
+	const int rc = fpohm_mesh_upload(ctx, V, nV, F, nF, &m);
+	if (rc != FPOHM_OK) return rc;
+	m->cached = true;
+	// at most 8 surfaces: evict the least recently used one nobody holds
+	if (ctx->mesh_cache.size() >= 8) {
+		int victim = -1;
+		for (int i = 0; i < (int)ctx->mesh_cache.size(); ++i)
+			if (ctx->mesh_cache[(size_t)i].refs == 0 && (victim < 0 || ctx->mesh_cache[(size_t)i].stamp < ctx->mesh_cache[(size_t)victim].stamp)) victim = i;
+		if (victim >= 0) {
+			fpohm_mesh *old = ctx->mesh_cache[(size_t)victim].mesh;
+			old->cached = false;
+			fpohm_mesh_free(old);
+			ctx->mesh_cache.erase(ctx->mesh_cache.begin() + victim);
+		}
+	}
+	ctx->mesh_cache.push_back({h0, h1, nV, nF, m, 1, ++ctx->cache_clock});
+	*out = m;
+	FPOHM_API_END
+}
+
+int fpohm_ctx_mesh_cache_clear(fpohm_ctx *ctx) {
+	FPOHM_API_BEGIN
+	FPOHM_REQUIRE(ctx, FPOHM_EINVAL, "fpohm_ctx_mesh_cache_clear: null ctx");
+	for (auto &c : ctx->mesh_cache) { c.mesh->cached = false; fpohm_mesh_free(c.mesh); }
+	ctx->mesh_cache.clear();
+	FPOHM_API_END
 }
 
 int fpohm_mesh_build_query_tree(fpohm_ctx *ctx, fpohm_mesh *mesh) {

@@ -74,6 +74,7 @@ struct fpohm_mesh {
 	fpohm::DevBuf<int32_t> pred_order; // leaf j of the tree holds facet pred_order[j]
 
 	// query structure
+	bool cached = false;                 // owned by the context's cache: fpohm_mesh_free only drops a reference
 	bool has_tree = false;
 	int tree_ties_host[3] = {0, 0, 0};   // axes whose barycentre ranks came from the host sort (equal coordinates)
 	fpohm::DevBuf<double> t_box;         // igl tree in DFS pre-order (node 0 = root): box 6 per node, prim -1 for internal nodes

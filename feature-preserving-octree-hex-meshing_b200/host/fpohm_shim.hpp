@@ -87,6 +87,16 @@ struct DeviceMesh {
 	DeviceMesh(const double *V, int64_t nV, const int32_t *Fp, int64_t nF) {
 		check(fpohm_mesh_upload(context(), V, nV, Fp, nF, &h), "fpohm_mesh_upload");
 	}
+	// content-keyed: a surface seen before comes back with its trees built (points_inside_mesh is called with the same surface
+	// over and over, and rebuilds its igl::AABB every time in the reference, gf.cpp:4038)
+	struct Cached {};
+	template <class MeshT>
+	DeviceMesh(const MeshT &tmi, Cached) {
+		F.resize(3 * tmi.Fs.size());
+		for (size_t i = 0; i < tmi.Fs.size(); ++i)
+			for (int k = 0; k < 3; ++k) F[3 * i + k] = (int32_t)tmi.Fs[i].vs[k];
+		check(fpohm_mesh_upload_cached(context(), tmi.V.data(), (int64_t)tmi.V.cols(), F.data(), (int64_t)tmi.Fs.size(), &h), "fpohm_mesh_upload_cached");
+	}
 	DeviceMesh(const DeviceMesh &) = delete;
 	DeviceMesh &operator=(const DeviceMesh &) = delete;
 	~DeviceMesh() { fpohm_mesh_free(h); }
@@ -156,7 +166,7 @@ void signed_distance_pseudonormal(const MatP &P, const TreestrT &a_tree, VecS &S
 // points_inside_mesh(MatrixXd &Ps, Mesh &tmi, VectorXd &signed_dis), gf.cpp:4024-4048
 template <class MatP, class MeshT, class VecS>
 void points_inside_mesh(MatP &Ps, MeshT &tmi, VecS &signed_dis) {
-	DeviceMesh dm(tmi);
+	DeviceMesh dm(tmi, DeviceMesh::Cached{});
 	const int64_t np = (int64_t)Ps.rows();
 	std::vector<double> p(3 * np), s(np);
 	for (int64_t i = 0; i < np; ++i) for (int k = 0; k < 3; ++k) p[3 * i + k] = Ps(i, k);

@@ -69,6 +69,13 @@ int  fpohm_ctx_launch_count(fpohm_ctx *ctx, int64_t *n);
 /* triangle mesh (the reference's GEO::Mesh M_i / Mesh mf.tri)                                        */
 int  fpohm_mesh_upload(fpohm_ctx *ctx, const double *V, int64_t nV, const int32_t *F, int64_t nF, fpohm_mesh **out);
 void fpohm_mesh_free(fpohm_mesh *mesh);
+/* Same as fpohm_mesh_upload, but keyed on the CONTENT of (V, F): a surface the context has seen before comes back with its
+ * trees and normals already built (the reference's points_inside_mesh rebuilds an igl::AABB on every call, gf.cpp:4038, and the
+ * outer loop passes the same surface again and again).  Handles are reference counted — release them with fpohm_mesh_free as
+ * usual; the context keeps up to 8 surfaces (least recently used unreferenced one evicted) until fpohm_ctx_mesh_cache_clear /
+ * fpohm_ctx_destroy. */
+int  fpohm_mesh_upload_cached(fpohm_ctx *ctx, const double *V, int64_t nV, const int32_t *F, int64_t nF, fpohm_mesh **out);
+int  fpohm_ctx_mesh_cache_clear(fpohm_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* octree (OctreeGrid, grid_meshing/octree.h:62-270, octree.cpp; octree_mesh, ghm.cpp:460-567)        */

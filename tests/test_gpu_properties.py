@@ -263,3 +263,26 @@ def test_full_size_clean_hex_mesh_properties(fp, ctx, gear):
     vol = sum(np.einsum("ij,ij->i", np.cross(P[Fv[:, k]], P[Fv[:, (k + 1) % 4]]), c).sum() for k in range(4)) / 6
     kept_vol = float(flag.sum()) * float(np.prod(Vl[Hl[0, 6]] - Vl[Hl[0, 0]]))
     assert abs(vol - kept_vol) < 1e-9 * kept_vol          # orient_surface_mesh leaves res <= 0, i.e. a positive enclosed volume
+
+
+def test_mesh_cache_is_keyed_on_content(fp, ctx, ref):
+    """points_inside_mesh rebuilds its tree on every call in the reference; fpohm_mesh_upload_cached returns the SAME
+    surface (trees built) for the same (V, F) content, a different one when a single coordinate changes, and the answers do not depend
+    on which path served them."""
+    import time
+    V, F = fp.procedural.torus(60, 40)
+    a = fp.TriMesh(ctx, V, F, cached=True)
+    b = fp.TriMesh(ctx, V.copy(), F.copy(), cached=True)
+    assert a.h.value == b.h.value
+    V2 = V.copy(); V2[7, 1] += 1e-9
+    c = fp.TriMesh(ctx, V2, F, cached=True)
+    assert c.h.value != a.h.value
+    P = np.random.default_rng(1).uniform(-0.6, 0.6, (5000, 3))
+    S0 = fp.TriMesh(ctx, V, F).signed_distance_pseudonormal(P, want=("S",))[0]
+    t = time.perf_counter(); S1 = fp.points_inside_mesh(ctx, P, V, F); t1 = time.perf_counter() - t
+    t = time.perf_counter(); S2 = fp.points_inside_mesh(ctx, P, V, F); t2 = time.perf_counter() - t
+    assert np.array_equal(S0, S1) and np.array_equal(S1, S2)
+    assert np.array_equal(S1 < 0, ref.points_inside_mesh(V, F, P) < 0)
+    for m in (a, b, c):
+        m.close()
+    assert fp.lib().fpohm_ctx_mesh_cache_clear(ctx.h) == 0
