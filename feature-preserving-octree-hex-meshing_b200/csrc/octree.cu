@@ -356,31 +356,14 @@ child_links_kernel(int64_t id0, int64_t n, int32_t n_roots, const int32_t *__res
 	}
 }
 
-// node keys: Morton code of (corner position >> node_shift); 8 per leaf, payload = 8 * leaf + corner
-__global__ void leaf_corner_keys_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const uint8_t *__restrict__ lvl,
-                                        const uint64_t *__restrict__ code, int depth, int node_shift, uint64_t *__restrict__ keys,
-                                        uint32_t *__restrict__ payload)
-{
-	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_leaves; i += (int64_t)gridDim.x * blockDim.x) {
-		const int32_t id = leaf_cell[i];
-		const int l = lvl[id];
-		const uint64_t c = code[id];
-		const int sh = depth - l - node_shift; // extent in key units = 1 << sh
-		const uint32_t x = compact1by2(c) << sh, y = compact1by2(c >> 1) << sh, z = compact1by2(c >> 2) << sh;
-		const uint32_t e = 1u << sh;
-#pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			const int m = corner_to_morton(k);
-			keys[8 * i + k] = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
-			payload[8 * i + k] = (uint32_t)(8 * i + k);
-		}
-	}
-}
-
 // Family-level node keys.  Most leaves sit in families of 8 sibling leaves, whose 64 corners are only 27 distinct lattice
-// points: such a family emits 27 keys (payload FAMILY | 27 * family + point), every other leaf its 8 corners (payload
-// 8 * slot + corner).  Halves the key/payload sort, which was the largest item of the numbering (15 of 57 ms at 59 M cells).
-#define NODE_FAMILY_BIT 0x80000000u
+// points: such a family emits 27 keys, every other leaf its 8 corners.  Halves the sort, which was the largest item of
+// the numbering (15 of 57 ms at 59 M cells).  The payload of a key is its own index t in the unsorted array (t < 27 *
+// n_fam: point t % 27 of family t / 27; else corner (t - 27 n_fam) & 7 of loose leaf (t - 27 n_fam) >> 3) and travels
+// as the value array of a (key, value) sort.  FPOHM_OCTREE_PACK=1 instead sorts ONE 8-byte word (key << 31 | index) on
+// its upper bits when both fit (node lattices up to 2^11 per axis): a third less traffic on paper, but measured 1.5 ms
+// SLOWER at 59 M cells (cub's keys-only onesweep at this size; profiles/r02_octree.md), so it is not the default.
+#define NODE_PACK_BITS 31
 __global__ void full_family_flags_kernel(const int32_t *__restrict__ icell, int64_t n_internal, const int32_t *__restrict__ first_child,
                                          uint8_t *__restrict__ fam_flag)
 {
@@ -403,7 +386,7 @@ __global__ void loose_leaf_flags_kernel(const int32_t *__restrict__ leaf_cell, i
 }
 __global__ void family_keys_kernel(const int32_t *__restrict__ fam /* internal ranks g */, int64_t n_fam, const int32_t *__restrict__ icell,
                                    const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int depth, int node_shift,
-                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ payload)
+                                   int pack, uint64_t *__restrict__ keys, uint32_t *__restrict__ payload)
 {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 27 * n_fam; t += (int64_t)gridDim.x * blockDim.x) {
 		const int64_t fi = t / 27; const int j = (int)(t % 27);
@@ -413,13 +396,13 @@ __global__ void family_keys_kernel(const int32_t *__restrict__ fam /* internal r
 		const uint32_t x = (compact1by2(c) << (sh + 1)) + ((uint32_t)(j % 3) << sh);
 		const uint32_t y = (compact1by2(c >> 1) << (sh + 1)) + ((uint32_t)((j / 3) % 3) << sh);
 		const uint32_t z = (compact1by2(c >> 2) << (sh + 1)) + ((uint32_t)(j / 9) << sh);
-		keys[t] = morton3(x, y, z);
-		payload[t] = NODE_FAMILY_BIT | (uint32_t)t;
+		if (pack) keys[t] = (morton3(x, y, z) << pack) | (uint64_t)t;
+		else { keys[t] = morton3(x, y, z); payload[t] = (uint32_t)t; }
 	}
 }
 __global__ void loose_leaf_keys_kernel(const int32_t *__restrict__ loose_leaf /* cell ids */, int64_t n_loose, const uint8_t *__restrict__ lvl,
-                                       const uint64_t *__restrict__ code, int depth, int node_shift, uint64_t *__restrict__ keys,
-                                       uint32_t *__restrict__ payload)
+                                       const uint64_t *__restrict__ code, int depth, int node_shift, int pack, int64_t t0,
+                                       uint64_t *__restrict__ keys, uint32_t *__restrict__ payload)
 {
 	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_loose; i += (int64_t)gridDim.x * blockDim.x) {
 		const int32_t id = loose_leaf[i];
@@ -431,23 +414,26 @@ __global__ void loose_leaf_keys_kernel(const int32_t *__restrict__ loose_leaf /*
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
 			const int m = corner_to_morton(k);
-			keys[8 * i + k] = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
-			payload[8 * i + k] = (uint32_t)(8 * i + k);
+			const uint64_t key = morton3(x + ((m & 1) ? e : 0), y + ((m & 2) ? e : 0), z + ((m & 4) ? e : 0));
+			const int64_t t = t0 + 8 * i + k;
+			if (pack) keys[t] = (key << pack) | (uint64_t)t;
+			else { keys[t] = key; payload[t] = (uint32_t)t; }
 		}
 	}
 }
 // After the sort: node id = index of the key's run; leaf corners are written through the payload, no search.
-__global__ void node_scatter2_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, const int32_t *__restrict__ head,
-                                     const int32_t *__restrict__ nid_incl, int64_t n, const int32_t *__restrict__ fam,
+__global__ void node_scatter2_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, int pack,
+                                     const int32_t *__restrict__ head,
+                                     const int32_t *__restrict__ nid_incl, int64_t n, const int32_t *__restrict__ fam, int64_t n_fam_keys,
                                      const int32_t *__restrict__ icell, const int32_t *__restrict__ first_child,
                                      const int32_t *__restrict__ loose_leaf, int node_shift,
                                      uint64_t *__restrict__ node_key, int32_t *__restrict__ node_pos, int32_t *__restrict__ corner)
 {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
 		const int32_t nid = nid_incl[t] - 1;
-		const uint32_t pl = payload[t];
-		if (pl & NODE_FAMILY_BIT) {
-			const uint32_t q = pl & ~NODE_FAMILY_BIT;
+		const uint64_t kt = key[t];
+		const uint32_t q = pack ? (uint32_t)(kt & ((1ull << NODE_PACK_BITS) - 1)) : payload[t];
+		if ((int64_t)q < n_fam_keys) {
 			const int j = (int)(q % 27);
 			const int32_t fc = first_child[icell[fam[q / 27]]];
 			const int a = j % 3, b = (j / 3) % 3, c = j / 9;       // lattice point; child (mx,my,mz) has it as local corner (a-mx, b-my, c-mz)
@@ -459,10 +445,11 @@ __global__ void node_scatter2_kernel(const uint64_t *__restrict__ key, const uin
 						corner[8 * (int64_t)(fc + child) + loc] = nid;
 					}
 		} else {
+			const uint32_t pl = q - (uint32_t)n_fam_keys;
 			corner[8 * (int64_t)loose_leaf[pl >> 3] + (pl & 7)] = nid;
 		}
 		if (head[t]) {
-			const uint64_t k = key[t];
+			const uint64_t k = kt >> pack;
 			node_key[nid] = k;
 			node_pos[3 * (int64_t)nid] = (int32_t)(compact1by2(k) << node_shift);
 			node_pos[3 * (int64_t)nid + 1] = (int32_t)(compact1by2(k >> 1) << node_shift);
@@ -471,29 +458,9 @@ __global__ void node_scatter2_kernel(const uint64_t *__restrict__ key, const uin
 	}
 }
 
-__global__ void key_heads_kernel(const uint64_t *__restrict__ k, int64_t n, int32_t *__restrict__ head) {
+__global__ void key_heads_kernel(const uint64_t *__restrict__ k, int64_t n, int pack, int32_t *__restrict__ head) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-		head[t] = (t == 0 || k[t] != k[t - 1]) ? 1 : 0;
-}
-
-// After the (key, payload) sort: the node id of a corner is the index of its run, so leaf corners are written by a
-// scatter through the payload — no search (the first version did 8 binary searches per cell: 17 of 83 ms at 59 M cells).
-__global__ void node_scatter_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, const int32_t *__restrict__ head,
-                                    const int32_t *__restrict__ nid_incl, int64_t n, const int32_t *__restrict__ leaf_cell, int node_shift,
-                                    uint64_t *__restrict__ node_key, int32_t *__restrict__ node_pos, int32_t *__restrict__ corner)
-{
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-		const int32_t nid = nid_incl[t] - 1;
-		const uint32_t pl = payload[t];
-		corner[8 * (int64_t)leaf_cell[pl >> 3] + (pl & 7)] = nid;
-		if (head[t]) {
-			const uint64_t k = key[t];
-			node_key[nid] = k;
-			node_pos[3 * (int64_t)nid] = (int32_t)(compact1by2(k) << node_shift);
-			node_pos[3 * (int64_t)nid + 1] = (int32_t)(compact1by2(k >> 1) << node_shift);
-			node_pos[3 * (int64_t)nid + 2] = (int32_t)(compact1by2(k >> 2) << node_shift);
-		}
-	}
+		head[t] = (t == 0 || (k[t] >> pack) != (k[t - 1] >> pack)) ? 1 : 0;
 }
 
 // corner k of an internal cell = corner k of its child k, recursively down to a leaf (octree.cpp:549-556)
@@ -508,39 +475,15 @@ __global__ void internal_corners_kernel(const int32_t *__restrict__ first_child,
 	}
 }
 
-// Node::neighNodeId = other end of the SHORTEST leaf edge leaving the node in each direction: one atomicMin per edge end on
-// the packed value (length << 32 | other node) — no search.  12 edges as (lower corner, upper corner, axis), octree.h:85-94.
+// Node::neighNodeId = other end of the SHORTEST leaf edge leaving the node in each direction (octree.h:85-94 names the 12
+// edges as lower corner, upper corner, axis).  Levels are processed coarse to fine with plain 4-byte stores, so the edge
+// of the finest (= shortest) leaf touching a node in a direction is the one that stays; leaves of one level that share an
+// edge store identical values.  (An atomicMin on (length << 32 | node) was 14.2 of 73 ms at 59 M cells.)
 __global__ void __launch_bounds__(256)
-leaf_edges_kernel(const int32_t *__restrict__ leaf_cell, int64_t n_leaves, const uint8_t *__restrict__ lvl, int depth,
-                  const int32_t *__restrict__ corner, unsigned long long *__restrict__ link)
-{
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 12 * n_leaves; t += (int64_t)gridDim.x * blockDim.x) {
-		const int64_t i = t / 12; const int k = (int)(t % 12);
-		const int32_t id = leaf_cell[i];
-		const unsigned long long len = 1ull << (depth - lvl[id]);
-		const int ea[12] = {0, 3, 4, 7, 0, 1, 4, 5, 0, 1, 3, 2};
-		const int eb[12] = {1, 2, 5, 6, 3, 2, 7, 6, 4, 5, 7, 6};
-		const int ax = k >> 2;
-		const uint32_t a = (uint32_t)corner[8 * (int64_t)id + ea[k]], b = (uint32_t)corner[8 * (int64_t)id + eb[k]];
-		atomicMin(&link[6 * (int64_t)a + 2 * ax + 1], (len << 32) | b);
-		atomicMin(&link[6 * (int64_t)b + 2 * ax], (len << 32) | a);
-	}
-}
-__global__ void node_links_kernel(const unsigned long long *__restrict__ link, int64_t n, int32_t *__restrict__ neigh) {
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-		neigh[t] = link[t] == ~0ull ? -1 : (int32_t)(link[t] & 0xffffffffull);
-}
-
-// The same links without atomics: levels are processed coarse to fine with plain 4-byte stores, so the edge of the finest
-// (= shortest) leaf touching a node in a direction is the one that stays; leaves of one level that share an edge store
-// identical values.  (The atomicMin form was 14.2 of 73 ms at 59 M cells: 1.2 G 64-bit atomics.)
-__global__ void __launch_bounds__(256)
-level_edges_kernel(int64_t id0, int64_t n, const int32_t *__restrict__ first_child, const int32_t *__restrict__ corner,
-                   int32_t *__restrict__ node_neigh)
+loose_edges_kernel(const int32_t *__restrict__ loose_leaf, int64_t n, const int32_t *__restrict__ corner, int32_t *__restrict__ node_neigh)
 {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 12 * n; t += (int64_t)gridDim.x * blockDim.x) {
-		const int64_t id = id0 + t / 12; const int k = (int)(t % 12);
-		if (first_child[id] >= 0) continue;
+		const int64_t id = loose_leaf[t / 12]; const int k = (int)(t % 12);
 		const int ea[12] = {0, 3, 4, 7, 0, 1, 4, 5, 0, 1, 3, 2};
 		const int eb[12] = {1, 2, 5, 6, 3, 2, 7, 6, 4, 5, 7, 6};
 		const int ax = k >> 2;
@@ -548,6 +491,40 @@ level_edges_kernel(int64_t id0, int64_t n, const int32_t *__restrict__ first_chi
 		node_neigh[6 * (int64_t)a + 2 * ax + 1] = b;
 		node_neigh[6 * (int64_t)b + 2 * ax] = a;
 	}
+}
+// A family of 8 sibling leaves has 96 leaf edges but only 54 distinct ones between its 27 lattice points: one thread per
+// lattice point writes the (up to 6) links of its own 24-byte row — 108 stores per family instead of 192.
+__global__ void __launch_bounds__(256)
+family_edges_kernel(const int32_t *__restrict__ fam, int64_t n_fam, const int32_t *__restrict__ icell, const int32_t *__restrict__ first_child,
+                    const int32_t *__restrict__ corner, int32_t *__restrict__ node_neigh)
+{
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 27 * n_fam; t += (int64_t)gridDim.x * blockDim.x) {
+		const int j = (int)(t % 27);
+		const int64_t fc = first_child[icell[fam[t / 27]]];
+		const int p[3] = {j % 3, (j / 3) % 3, j / 9};
+		auto node_at = [&](int a, int b, int c) {   // child (mx,my,mz) holds lattice point (a,b,c) as its local corner (a-mx, b-my, c-mz)
+			const int mx = min(a, 1), my = min(b, 1), mz = min(c, 1);
+			return corner[8 * (fc + morton_to_corner(mx | (my << 1) | (mz << 2))) + morton_to_corner((a - mx) | ((b - my) << 1) | ((c - mz) << 2))];
+		};
+		const int64_t me = node_at(p[0], p[1], p[2]);
+#pragma unroll
+		for (int ax = 0; ax < 3; ++ax) {
+			int q[3] = {p[0], p[1], p[2]};
+			if (p[ax] < 2) { q[ax] = p[ax] + 1; node_neigh[6 * me + 2 * ax + 1] = node_at(q[0], q[1], q[2]); }
+			if (p[ax] > 0) { q[ax] = p[ax] - 1; node_neigh[6 * me + 2 * ax] = node_at(q[0], q[1], q[2]); }
+		}
+	}
+}
+// where each level's full families (ascending internal ranks) and loose leaves (ascending cell ids) begin in their lists
+struct LevelBounds { int n; int64_t g[26], id[26]; };
+__global__ void level_ranges_kernel(LevelBounds lb, const int32_t *__restrict__ fam, int64_t n_fam, const int32_t *__restrict__ loose,
+                                    int64_t n_loose, int64_t *__restrict__ out /* [2][26] */)
+{
+	const int l = threadIdx.x;
+	if (l >= lb.n) return;
+	auto lower = [](const int32_t *a, int64_t n, int64_t v) { int64_t lo = 0, hi = n; while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (a[m] < v) lo = m + 1; else hi = m; } return lo; };
+	out[l] = lower(fam, n_fam, lb.g[l]);
+	out[26 + l] = lower(loose, n_loose, lb.id[l]);
 }
 
 __global__ void iota_i32_kernel(int32_t *p, int64_t n) {
@@ -818,11 +795,14 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 		FPOHM_REQUIRE((o->prm.grid_size[d] >> o->node_shift) < (1 << 21), FPOHM_ERANGE,
 		              "octree: %d node positions per axis after shift do not fit 21-bit Morton keys", (o->prm.grid_size[d] >> o->node_shift) + 1);
 	o->cell_corner.alloc(8 * n_cells, s);
+	// the leaves outside full families keep the per-leaf path; their number needs no read-back
+	const int64_t n_loose = o->n_leaves - 8 * n_fam;
+	DevBuf<int32_t> loose(std::max<int64_t>(n_loose, 1), s);
+	int64_t ranges[2][26];
+	FPOHM_REQUIRE(o->n_levels + 2 <= 26, FPOHM_ERANGE, "octree: %d levels", o->n_levels);
 	{
-		// the leaves outside full families keep the per-leaf path; their number needs no read-back
-		const int64_t n_loose = o->n_leaves - 8 * n_fam;
 		DevBuf<uint8_t> loose_flag(std::max<int64_t>(o->n_leaves, 1), s);
-		DevBuf<int32_t> loose(std::max<int64_t>(o->n_leaves, 1), s);
+		DevBuf<int64_t> d_ranges(2 * 26, s);
 		if (n_loose > 0) {
 			DevBuf<int64_t> cnt2(1, s);
 			loose_leaf_flags_kernel<<<grid_for(ctx, o->n_leaves, blk), blk, 0, s>>>(o->leaf_cell.p, o->n_leaves, o->n_roots, fam_flag.p, loose_flag.p);
@@ -833,29 +813,49 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 			FPOHM_CUDA(cub::DeviceSelect::Flagged(tmp1.p, tb1, o->leaf_cell.p, loose_flag.p, loose.p, cnt2.p, o->n_leaves, s));
 			ctx->launches += 2;
 		}
+		{
+			// level l = 0 .. n_levels holds the leaves whose parents have internal ranks [lvl_off[l-1], lvl_off[l]) and whose own
+			// ids are [id0(l), id0(l+1)); entry n_levels + 1 closes the last range
+			LevelBounds lb; lb.n = o->n_levels + 2;
+			for (int l = 0; l <= o->n_levels + 1; ++l) {
+				lb.g[l] = l == 0 ? 0 : o->lvl_off[l - 1];
+				lb.id[l] = l == 0 ? 0 : o->n_roots + 8 * o->lvl_off[l - 1];
+			}
+			level_ranges_kernel<<<1, 32, 0, s>>>(lb, fam.p, n_fam, loose.p, n_loose, d_ranges.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			d_ranges.download(&ranges[0][0], 2 * 26);   // read after the synchronize that follows the scan below
+		}
 		const int64_t nk = 27 * n_fam + 8 * n_loose;
 		FPOHM_REQUIRE(nk < (1ll << 31), FPOHM_ERANGE, "octree: %lld node keys exceed the 31-bit payload", (long long)nk);
+		const int64_t gmax = std::max(o->prm.grid_size[0], std::max(o->prm.grid_size[1], o->prm.grid_size[2]));
+		const int bits = std::min(64, key_bits(gmax >> o->node_shift));
+		static const bool want_pack = getenv("FPOHM_OCTREE_PACK") != nullptr;
+		const int pack = (bits + NODE_PACK_BITS <= 64 && want_pack) ? NODE_PACK_BITS : 0;
 		DevBuf<uint64_t> keys(nk, s), skeys(nk, s);
-		DevBuf<uint32_t> pay(nk, s), spay(nk, s);
+		DevBuf<uint32_t> pay(pack ? 0 : nk, s), spay(pack ? 0 : nk, s);
 		if (n_fam) {
 			family_keys_kernel<<<grid_for(ctx, 27 * n_fam, blk), blk, 0, s>>>(fam.p, n_fam, icell.p, o->cell_level.p, o->cell_code.p,
-				o->depth, o->node_shift, keys.p, pay.p);
+				o->depth, o->node_shift, pack, keys.p, pay.p);
 			FPOHM_LAUNCH_CHECK(ctx);
 		}
 		if (n_loose) {
 			loose_leaf_keys_kernel<<<grid_for(ctx, n_loose, blk), blk, 0, s>>>(loose.p, n_loose, o->cell_level.p, o->cell_code.p, o->depth,
-				o->node_shift, keys.p + 27 * n_fam, pay.p + 27 * n_fam);
+				o->node_shift, pack, 27 * n_fam, keys.p, pay.p);
 			FPOHM_LAUNCH_CHECK(ctx);
 		}
-		const int64_t gmax = std::max(o->prm.grid_size[0], std::max(o->prm.grid_size[1], o->prm.grid_size[2]));
-		const int bits = std::min(64, key_bits(gmax >> o->node_shift));
 		size_t tb = 0;
-		FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skeys.p, pay.p, spay.p, nk, 0, bits, s));
-		DevBuf<uint8_t> tmp((int64_t)tb, s);
-		FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skeys.p, pay.p, spay.p, nk, 0, bits, s));
+		if (pack) {
+			FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, skeys.p, nk, pack, pack + bits, s));
+			DevBuf<uint8_t> tmp((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys.p, skeys.p, nk, pack, pack + bits, s));
+		} else {
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skeys.p, pay.p, spay.p, nk, 0, bits, s));
+			DevBuf<uint8_t> tmp((int64_t)tb, s);
+			FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skeys.p, pay.p, spay.p, nk, 0, bits, s));
+		}
 		keys.release(); pay.release();
 		DevBuf<int32_t> head(nk, s), nid(nk, s);
-		key_heads_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, nk, head.p);
+		key_heads_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, nk, pack, head.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 		size_t tb2 = 0;
 		FPOHM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, head.p, nid.p, nk, s));
@@ -868,8 +868,8 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 		o->n_nodes = last;
 		o->node_key.alloc(o->n_nodes, s);
 		o->node_pos.alloc(3 * o->n_nodes, s);
-		node_scatter2_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, spay.p, head.p, nid.p, nk, fam.p, icell.p, o->cell_first_child.p,
-			loose.p, o->node_shift, o->node_key.p, o->node_pos.p, o->cell_corner.p);
+		node_scatter2_kernel<<<grid_for(ctx, nk, blk), blk, 0, s>>>(skeys.p, spay.p, pack, head.p, nid.p, nk, fam.p, 27 * n_fam, icell.p,
+			o->cell_first_child.p, loose.p, o->node_shift, o->node_key.p, o->node_pos.p, o->cell_corner.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 	}
 	internal_corners_kernel<<<grid_for(ctx, 8 * n_cells, blk), blk, 0, s>>>(o->cell_first_child.p, n_cells, o->cell_corner.p);
@@ -878,11 +878,16 @@ void number_levels(fpohm_octree *o, std::vector<DevBuf<uint64_t>> &I, std::vecto
 		o->node_neigh.alloc(6 * o->n_nodes, s);
 		FPOHM_CUDA(cudaMemsetAsync(o->node_neigh.p, 0xff, 4 * (size_t)(6 * o->n_nodes), s));
 		for (int l = 0; l <= o->n_levels; ++l) {
-			const int64_t id0 = l == 0 ? 0 : o->n_roots + 8 * o->lvl_off[l - 1];
-			const int64_t n = l == 0 ? o->n_roots : 8 * (o->lvl_off[l] - o->lvl_off[l - 1]);
-			if (n == 0) continue;
-			level_edges_kernel<<<grid_for(ctx, 12 * n, blk), blk, 0, s>>>(id0, n, o->cell_first_child.p, o->cell_corner.p, o->node_neigh.p);
-			FPOHM_LAUNCH_CHECK(ctx);
+			const int64_t f0 = ranges[0][l], nf = ranges[0][l + 1] - f0, l0 = ranges[1][l], nl = ranges[1][l + 1] - l0;
+			if (nl > 0) {
+				loose_edges_kernel<<<grid_for(ctx, 12 * nl, blk), blk, 0, s>>>(loose.p + l0, nl, o->cell_corner.p, o->node_neigh.p);
+				FPOHM_LAUNCH_CHECK(ctx);
+			}
+			if (nf > 0) {
+				family_edges_kernel<<<grid_for(ctx, 27 * nf, blk), blk, 0, s>>>(fam.p + f0, nf, icell.p, o->cell_first_child.p, o->cell_corner.p,
+					o->node_neigh.p);
+				FPOHM_LAUNCH_CHECK(ctx);
+			}
 		}
 	}
 	FPOHM_CUDA(cudaStreamSynchronize(s));
