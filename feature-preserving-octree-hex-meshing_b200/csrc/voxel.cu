@@ -165,22 +165,31 @@ __device__ __forceinline__ void append_hit(const ColumnGrid &g, int x, int y, do
 }
 
 // Rectangle of columns per facet.  Facets covering at most RECT_INLINE columns (the common case on fine meshes) are
-// finished right here; larger ones are left to the load-balanced pair kernel through cnt[]/rect[].
+// finished right here; larger ones are left to the load-balanced pair kernel through a compact list.
 // The small rectangles of a warp's 32 facets are pooled: a warp prefix sum over the pair counts, then the lanes take
 // the (facet, column) pairs 32 at a time whatever facet they belong to.  (ncu on the first version, where each lane
 // looped over its own facet's columns: 8.8 of 32 lanes active, 154 M warp instructions, 0.29 of the 0.77 ms at 1024^3.)
+// Big facets: a warp reserves list slots AND pair offsets for its big facets with ONE 64-bit atomicAdd on
+// (count << BIG_PAIR_BITS | pairs), so the list is ordered by pair offset whatever order the warps arrive in and the pair
+// kernel can binary-search it — no scan over all facets, no per-facet rect / count arrays (round 1 wrote 32 B per facet and
+// ran a cub scan of nF + 1 counts: two more launches in front of a pair kernel that has nothing to do on fine meshes).
+// Limits, both checked: nF < 2^28, and < 2^36 big pairs in total (ctl[4..5] holds the exact sum).
 #define RECT_INLINE 16
+#define BIG_PAIR_BITS 36
+#define HIT_CTL_WORDS 8     // ctl[0] largest hit count past the capacity, ctl[2..3] packed big counter, ctl[4..5] exact big pair sum
 __global__ void __launch_bounds__(256)
-facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ rect, int64_t *__restrict__ cnt,
-                  double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n, int32_t *__restrict__ overflow_flag,
+facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4 *__restrict__ big_rect, int32_t *__restrict__ big_f,
+                  int64_t *__restrict__ big_off, int32_t *__restrict__ ctl,
+                  double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
                   int32_t *__restrict__ hit_ev, double oz, int nz)
 {
 	const int lane = threadIdx.x & 31;
+	int32_t *overflow_flag = ctl;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base <= nF; base += stride) {   // warp-uniform trip count
+	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < nF; base += stride) {   // warp-uniform trip count
 		const int64_t f = base + lane;
-		int x0 = 0, y0 = 0, w = 0, n_small = 0;
-		if (f == nF) cnt[f] = 0;
+		int x0 = 0, y0 = 0, w = 0, h = 0, n_small = 0;
+		int64_t n_big = 0;
 		if (f < nF) {
 			const double *t = tri + 9 * f;
 			const double xmin = fmin(t[0], fmin(t[3], t[6])), xmax = fmax(t[0], fmax(t[3], t[6]));
@@ -189,10 +198,28 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
 			y0 = first_center_ge(ymin, g.oy, g.spacing, g.ny);
 			const int x1 = last_center_le(xmax, g.ox, g.spacing, g.nx), y1 = last_center_le(ymax, g.oy, g.spacing, g.ny);
 			w = x1 - x0 + 1;
-			const int h = y1 - y0 + 1;
+			h = y1 - y0 + 1;
 			const int64_t n = (w > 0 && h > 0) ? (int64_t)w * h : 0;
-			if (n <= RECT_INLINE) { n_small = (int)n; rect[f] = make_int4(0, 0, 0, 0); cnt[f] = 0; }
-			else { rect[f] = make_int4(x0, y0, w, h); cnt[f] = n; }
+			if (n <= RECT_INLINE) n_small = (int)n; else n_big = n;
+		}
+		const unsigned big_mask = __ballot_sync(0xffffffffu, n_big > 0);
+		if (big_mask) {                                   // rare on fine meshes; warp-uniform
+			long long incl64 = n_big;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, incl64, o); if (lane >= o) incl64 += v; }
+			const long long total64 = __shfl_sync(0xffffffffu, incl64, 31);
+			unsigned long long old = 0;
+			if (lane == 0) {
+				old = atomicAdd(reinterpret_cast<unsigned long long *>(ctl + 2), ((unsigned long long)__popc(big_mask) << BIG_PAIR_BITS) + (unsigned long long)total64);
+				atomicAdd(reinterpret_cast<unsigned long long *>(ctl + 4), (unsigned long long)total64);
+			}
+			old = __shfl_sync(0xffffffffu, old, 0);
+			if (n_big > 0) {
+				const int64_t pos = (int64_t)(old >> BIG_PAIR_BITS) + __popc(big_mask & ((1u << lane) - 1u));
+				big_rect[pos] = make_int4(x0, y0, w, h);
+				big_f[pos] = (int32_t)f;
+				big_off[pos] = (int64_t)(old & ((1ull << BIG_PAIR_BITS) - 1ull)) + (incl64 - n_big);
+			}
 		}
 		// exclusive prefix sum of the small pair counts over the warp
 		int incl = n_small;
@@ -200,6 +227,7 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
 		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
 		const int excl = incl - n_small;
 		const int total = __shfl_sync(0xffffffffu, incl, 31);
+		const float inv_w = w > 0 ? __frcp_rn((float)w) : 0.0f;
 		for (int p0 = 0; p0 < total; p0 += 32) {
 			const int p = p0 + lane;
 			int src = 0;                                    // largest lane with excl <= p
@@ -210,9 +238,11 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
 			}
 			const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
 			const int sw = __shfl_sync(0xffffffffu, w, src), se = __shfl_sync(0xffffffffu, excl, src);
+			const float siw = __shfl_sync(0xffffffffu, inv_w, src);
 			if (p < total) {
-				const int k = p - se;
-				const int x = sx0 + k % sw, y = sy0 + k / sw;
+				const int k = p - se;                         // 0 <= k < RECT_INLINE, 1 <= sw <= RECT_INLINE: (k + 0.5) / sw is at least
+				const int row = __float2int_rz(((float)k + 0.5f) * siw);   // 0.5 / 16 away from an integer, far beyond the float error
+				const int x = sx0 + (k - row * sw), y = sy0 + row;
 				const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
 				double z;
 				const int sgn = intersect_ray_z(tri + 9 * (base + src), cx, cy, z);
@@ -223,22 +253,25 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
 }
 
 __global__ void __launch_bounds__(256)
-pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, const int4 *__restrict__ rect, const int64_t *__restrict__ off,
+pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, const int4 *__restrict__ big_rect, const int32_t *__restrict__ big_f,
+                 const int64_t *__restrict__ big_off, int32_t *__restrict__ ctl,
                  double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
-                 int32_t *__restrict__ overflow_flag, int32_t *__restrict__ hit_ev, double oz, int nz)
+                 int32_t *__restrict__ hit_ev, double oz, int nz)
 {
-	const int64_t n_pairs = off[nF];                // read on the device: no host round trip between the scan and this launch
+	// counts are read on the device: no host round trip in front of this launch
+	const unsigned long long packed = *reinterpret_cast<const unsigned long long *>(ctl + 2);
+	const int64_t n_big = (int64_t)(packed >> BIG_PAIR_BITS), n_pairs = (int64_t)(packed & ((1ull << BIG_PAIR_BITS) - 1ull));
+	if (*reinterpret_cast<const unsigned long long *>(ctl + 4) >> BIG_PAIR_BITS) return;      // offsets wrapped: the host reports FPOHM_ERANGE
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
-		int64_t lo = 0, hi = nF;                       // largest f with off[f] <= t
-		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
-		const int64_t f = lo;
-		const int4 r = rect[f];
-		const int64_t k = t - off[f];
+		int64_t lo = 0, hi = n_big;                    // largest i with big_off[i] <= t
+		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (big_off[mid] <= t) lo = mid; else hi = mid; }
+		const int4 r = big_rect[lo];
+		const int64_t k = t - big_off[lo];
 		const int x = r.x + (int)(k % r.z), y = r.y + (int)(k / r.z);
 		const double cx = (x + 0.5) * g.spacing + g.ox, cy = (y + 0.5) * g.spacing + g.oy; // voxel_center, voxelization.h:85-91
 		double z;
-		const int s = intersect_ray_z(tri + 9 * f, cx, cy, z);
-		if (s) append_hit(g, x, y, z, s, hit_z, hit_s, hit_n, overflow_flag, hit_ev, oz, nz);
+		const int s = intersect_ray_z(tri + 9 * (int64_t)big_f[lo], cx, cy, z);
+		if (s) append_hit(g, x, y, z, s, hit_z, hit_s, hit_n, ctl, hit_ev, oz, nz);
 	}
 }
 
@@ -282,30 +315,35 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 			while (j >= 0 && (e[j] >> 2) > (v >> 2)) { e[j + 1] = e[j]; --j; }
 			e[j + 1] = v;
 		}
-		int run = 0;
-		for (int i = 0; i < n; ++i) { run += (e[i] & 3) - 1; e[i] = ((e[i] >> 2) << 8) | (run + 128); }   // (k << 8) | (sum after the event + 128)
-		int i = 0, s = 0;
+		// Event driven (round 2; the first version walked all chunks of every column: 1 217 instructions per column, 78 us at
+		// 1024^2 columns).  Events in ascending k; s = sum of the signs so far.  The state ENTERING chunk b is the state after
+		// every event with k <= 32 b, so a stretch with s < 0 between events at k_prev and k sets the inside bits
+		// [ceil(k_prev / 32), ceil(k / 32)); an event strictly inside a chunk (k % 32 != 0) makes that chunk dirty and its
+		// 32 layer bits are accumulated while the events of the chunk go by.
+		const int n_chunks = (nz + FILL_Z - 1) / FILL_Z;
 		for (int w = 0; w < n_words; ++w) {
-			uint32_t inside = 0, dirty = 0;
-			for (int b = 0; b < 32; ++b) {
-				const int zc = w * 32 + b;
-				const int z0 = zc * FILL_Z, z1 = z0 + FILL_Z;
-				if (z0 >= nz) break;
-				while (i < n && (e[i] >> 8) <= z0) { s = (e[i] & 0xff) - 128; ++i; }   // state entering the chunk
-				if (s < 0) inside |= 1u << b;
-				if (i < n && (e[i] >> 8) < z1) {
-					dirty |= 1u << b;
-					uint32_t mask = 0;
-					int t = s, prev = z0, j = i;
-					for (; j < n && (e[j] >> 8) < z1; ++j) {
-						const int k = e[j] >> 8;
-						if (t < 0) mask |= bit_range(prev - z0, k - z0);
-						prev = k; t = (e[j] & 0xff) - 128;
+			const int c0 = 32 * w, c1 = min(c0 + 32, n_chunks);           // chunks of this summary word
+			uint32_t inside = 0, dirty = 0, mask = 0;
+			int s = 0, from = 0 /* ceil(k_prev / 32) */, cur = -1 /* open dirty chunk */, t = 0, prev = 0;
+			for (int i = 0; i <= n; ++i) {
+				const int k = i < n ? (e[i] >> 2) : nz + FILL_Z * 32;       // sentinel: closes the last stretch
+				const int to = min((k + FILL_Z - 1) / FILL_Z, n_chunks);
+				if (s < 0) inside |= bit_range(max(from, c0) - c0, min(to, c1) - c0);
+				from = to;
+				if (i == n) break;
+				const int b = k / FILL_Z, r = k % FILL_Z;
+				if (r != 0 && b >= c0 && b < c1) {
+					if (b != cur) {
+						if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
+						cur = b; dirty |= 1u << (b - c0); mask = 0; t = s; prev = 0;
 					}
-					if (t < 0) mask |= bit_range(prev - z0, z1 - z0);
-					dmask[(int64_t)zc * ncol + col] = mask;
+					if (t < 0) mask |= bit_range(prev, r);
+					prev = r;
+					t = s + (e[i] & 3) - 1;
 				}
+				s += (e[i] & 3) - 1;
 			}
+			if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
 			sum[(int64_t)(2 * w) * ncol + col] = inside;
 			sum[(int64_t)(2 * w + 1) * ncol + col] = dirty;
 		}
@@ -435,7 +473,8 @@ cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ c
 }
 
 struct HitScratch {
-	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> n, ov, ev;
+	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> ctl /* HIT_CTL_WORDS control words, then one count per column */, ev;
+	int32_t *n() const { return ctl.p + HIT_CTL_WORDS; }
 };
 
 // voxel_events: store packed (k0, sign) events for the VoxelGrid fill instead of (z, sign) pairs
@@ -443,30 +482,30 @@ void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitS
                      double oz = 0, int nz = 0)
 {
 	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
+	FPOHM_REQUIRE(nF < (1ll << (64 - BIG_PAIR_BITS)), FPOHM_ERANGE, "ray parity: %lld facets (the limit is 2^28)", (long long)nF);
 	if (voxel_events) h.ev.alloc(ncol * g.cap, s); else { h.z.alloc(ncol * g.cap, s); h.s.alloc(ncol * g.cap, s); }
-	h.n.alloc(ncol, s); h.ov.alloc(1, s);
-	h.ov.zero(); h.n.zero();
-	DevBuf<int4> rect(nF, s);
-	DevBuf<int64_t> cnt(nF + 1, s), off(nF + 1, s);
-	facet_rect_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, cnt.p, h.z.p, h.s.p, h.n.p, h.ov.p,
+	h.ctl.alloc(HIT_CTL_WORDS + ncol, s);
+	h.ctl.zero();                                      // counts and control words in one memset
+	DevBuf<int4> big_rect(nF, s);                     // touched only where a facet covers more than RECT_INLINE columns
+	DevBuf<int32_t> big_f(nF, s);
+	DevBuf<int64_t> big_off(nF, s);
+	facet_rect_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(g, mesh->tri.p, nF, big_rect.p, big_f.p, big_off.p, h.ctl.p, h.z.p, h.s.p, h.n(),
 		voxel_events ? h.ev.p : nullptr, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
-	size_t tb = 0;
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nF + 1, s));
-	DevBuf<uint8_t> tmp((int64_t)tb, s);
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nF + 1, s));
-	ctx->launches += 1;
-	// the pair count stays on the device; on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
-	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, nF, rect.p, off.p, h.z.p, h.s.p, h.n.p, h.ov.p,
+	// on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
+	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, big_rect.p, big_f.p, big_off.p, h.ctl.p, h.z.p, h.s.p, h.n(),
 		voxel_events ? h.ev.p : nullptr, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 }
 
 // 0 if every list fitted, else the capacity the pass has to be repeated with (FPOHM_ERANGE beyond HIT_CAP_MAX)
-int overflow_retry_cap(DevBuf<int32_t> &ov_flag, cudaStream_t s, const char *who) {
-	int32_t ov = 0;
-	ov_flag.download(&ov, 1);
+int overflow_retry_cap(DevBuf<int32_t> &ctl_dev /* HIT_CTL_WORDS control words first */, cudaStream_t s, const char *who) {
+	int32_t ctl[HIT_CTL_WORDS] = {0};
+	ctl_dev.download(ctl, HIT_CTL_WORDS);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
+	unsigned long long big_pairs; memcpy(&big_pairs, ctl + 4, 8);
+	FPOHM_REQUIRE((big_pairs >> BIG_PAIR_BITS) == 0, FPOHM_ERANGE, "%s: %llu (facet, column) pairs (the limit is 2^%d)", who, big_pairs, BIG_PAIR_BITS);
+	const int32_t ov = ctl[0];
 	if (ov == 0) return 0;
 	const int cap = next_hit_cap(ov);
 	FPOHM_REQUIRE(cap > 0, FPOHM_ERANGE, "%s: %d ray/facet hits in one column (the limit is %d)", who, ov, HIT_CAP_MAX);
@@ -517,10 +556,10 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	const int64_t ncol = (int64_t)dims[0] * dims[1];
 	DevBuf<uint32_t> summary(2 * n_words * ncol, s), dmask((int64_t)gz * ncol, s);      // dmask is only written / read where a chunk is dirty
 	switch (cap) {
-	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
-	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
-	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
-	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n.p, summary.p, dmask.p); break;
+	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
+	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
+	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
+	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
@@ -535,7 +574,7 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
-	const int retry = overflow_retry_cap(h.ov, s, "fpohm_voxel_sign");
+	const int retry = overflow_retry_cap(h.ctl, s, "fpohm_voxel_sign");
 	if (!retry) break;
 	cap = retry;
 	}
@@ -587,10 +626,10 @@ int fpohm_dexel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_o
 		run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s);
 		cnt.zero();
 		switch (cap) {
-		case 32: dexel_reduce_kernel<32><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
-		case 128: dexel_reduce_kernel<128><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
-		case 512: dexel_reduce_kernel<512><<<grid_for(ctx, ncol, 128, 4), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
-		default: dexel_reduce_kernel<2048><<<grid_for(ctx, ncol, 128, 2), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n.p, cnt.p); break;
+		case 32: dexel_reduce_kernel<32><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n(), cnt.p); break;
+		case 128: dexel_reduce_kernel<128><<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n(), cnt.p); break;
+		case 512: dexel_reduce_kernel<512><<<grid_for(ctx, ncol, 128, 4), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n(), cnt.p); break;
+		default: dexel_reduce_kernel<2048><<<grid_for(ctx, ncol, 128, 2), 128, 0, s>>>(ncol, h.z.p, h.s.p, h.n(), cnt.p); break;
 		}
 		FPOHM_LAUNCH_CHECK(ctx);
 		size_t tb = 0;
@@ -600,12 +639,12 @@ int fpohm_dexel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_o
 		ctx->launches += 2;
 		int64_t tot = 0;
 		FPOHM_CUDA(cudaMemcpyAsync(&tot, off.p + ncol, 8, cudaMemcpyDeviceToHost, s));
-		const int retry = overflow_retry_cap(h.ov, s, "fpohm_dexel_sign");
+		const int retry = overflow_retry_cap(h.ctl, s, "fpohm_dexel_sign");
 		if (retry) { cap = retry; continue; }
 		*total = tot;
 		if (values) {
 			DevBuf<double> dv(tot, s);
-			dexel_emit_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, cap, h.z.p, h.n.p, off.p, dv.p);
+			dexel_emit_kernel<<<grid_for(ctx, ncol, 128), 128, 0, s>>>(ncol, cap, h.z.p, h.n(), off.p, dv.p);
 			FPOHM_LAUNCH_CHECK(ctx);
 			dv.download(values, tot);
 			FPOHM_CUDA(cudaStreamSynchronize(s));
@@ -627,7 +666,7 @@ int fpohm_octree_cell_sign(const fpohm_octree *o, const fpohm_mesh *mesh, const 
 	fpohm_mesh *m = const_cast<fpohm_mesh *>(mesh);
 	mesh_ensure_pred(ctx, m, s);
 	DevBuf<float> d(o->n_cells, s);
-	DevBuf<int32_t> ov(1, s);
+	DevBuf<int32_t> ov(HIT_CTL_WORDS, s);
 	KernelTimer t(ctx, s);
 	for (int cap = HIT_CAP;;) {
 		ov.zero();
