@@ -301,13 +301,15 @@ def main():
         gC = [torch.empty(world * n, 3, dtype=torch.float64, device=dev) for n in nmax]; gN = [torch.empty(world * n, 3, dtype=torch.float64, device=dev) for n in nmax]
 
     def step_dev():
-        for k in range(2):
+        # the large set first: its results travel (NCCL's own stream, async_op) while the small set is computed
+        works = []
+        for k in (1, 0):
             n = len(my[k])
             mesh.signed_distance_dev(dP[k].data_ptr(), n, dS[k].data_ptr(), dI[k].data_ptr(), dC[k].data_ptr(), dN[k].data_ptr(), stream.cuda_stream)
-        if world > 1:       # the job's result lands in every rank's HBM (rank 0's included): NCCL all-gather of the padded slices
-            for k in range(2):
-                dist.all_gather_into_tensor(gS[k], dS[k]); dist.all_gather_into_tensor(gI[k], dI[k])
-                dist.all_gather_into_tensor(gC[k], dC[k]); dist.all_gather_into_tensor(gN[k], dN[k])
+            if world > 1:   # the job's result lands in every rank's HBM (rank 0's included): NCCL all-gather of the padded slices
+                works += [dist.all_gather_into_tensor(g, d, async_op=True) for g, d in ((gS[k], dS[k]), (gI[k], dI[k]), (gC[k], dC[k]), (gN[k], dN[k]))]
+        for w in works:
+            w.wait()            # stream-side wait: the step's closing event comes after the gathers
 
     for _ in range(args.warmup):
         step_dev()
@@ -482,7 +484,7 @@ def main():
             g_ms = timed(lambda: gm.signed_distance_dev(dgP.data_ptr(), gQ, dgS.data_ptr(), dgI.data_ptr(), dgC.data_ptr(), dgN.data_ptr(), stream.cuda_stream), 10, 3)
             also["c2_gear"] = {"tris": int(len(gF)), "cells": int(gsz["cells"]), "leaves": int(gsz["leaves"]), "octree_build_ms": float(np.median(gb[3:])),
                                "octree_build_ms_max": float(np.max(gb[3:])), "queries": int(gQ), "query_ms": g_ms, "queries_per_s": gQ / (g_ms * 1e-3),
-                               "query_tree_build_s_host": g_tree_s, "round1_queries_per_s": 794.0e6}
+                               "query_tree_build_s": g_tree_s, "round1_queries_per_s": 794.0e6}
             go.close(); gm.close(); del dgP, dgS, dgI, dgC, dgN
         except Exception as e:
             also["c2_gear"] = {"error": str(e)}
@@ -543,11 +545,11 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 24 * Q, "d2h_bytes_per_step": 60 * Q,
                         "note": "host-pointer C-ABI call per query set, pinned rank-local buffers" + ("; each rank moves its own slice" if world > 1 else "")},
                 "e2e_cold": {"seconds": e2e_cold_s, "queries_per_s": (Q / world / e2e_cold_s) if e2e_cold_s else None,
-                             "note": "fresh mesh handle: upload + igl-identical tree and normals built on the host + wide tree + one step (rank 0's slice)"},
+                             "note": "fresh mesh handle: upload + igl-identical tree, normals and wide tree built on the device (host std::sort only for axes with tied barycentres, host acos) + one step (rank 0's slice)"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "also": also}
-        line["also"]["query_tree_build_s_host"] = tree_build_s
+        line["also"]["query_tree_build_s"] = tree_build_s
         if not args.no_cpu_baseline and world == 1:
             try:
                 res = (np.concatenate([hS[0].numpy(), hS[1].numpy()]), np.concatenate([hI[0].numpy(), hI[1].numpy()]),
