@@ -134,6 +134,17 @@ def test_host_igl_tree_identical_to_reference_even_with_ties(fp, G):
     assert np.array_equal(FN, G["sd_FN"]) and np.array_equal(VN, G["sd_VN"]) and np.array_equal(EN, G["sd_EN"]) and np.array_equal(EMAP, G["sd_EMAP"])
 
 
+def test_host_tree_of_a_large_tied_mesh_equals_compiled_igl(fp, ref):
+    """Above 131 072 facets the barycentre columns are sorted by std::sort's own pieces on several threads (sort_like_std,
+    igl_tree_host.cpp).  The full bench gear has 150 k - 200 k tied barycentre coordinates per axis, so any deviation from libstdc++'s
+    order of equal keys shows up as a different tree: node for node against igl::AABB::init compiled from the reference."""
+    V, F = fp.procedural.gear()[:2]
+    assert len(F) >= 4 * 32768
+    box, prim, lr = fp.host_igl_tree(V, F)
+    rbox, rprim, rlr = ref.RefTree(V, F).flatten()
+    assert np.array_equal(prim, rprim) and np.array_equal(lr, rlr) and np.array_equal(box, rbox)
+
+
 def test_host_grid_setups(fp, port, G):
     p = fp.octree_grid_setup(G["sd_V"], 1 << 20)
     assert np.array_equal(p.grid_size, G["oct_gs"]) and np.array_equal(p.origin, G["oct_origin"])
