@@ -1835,6 +1835,7 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 	// The packet search lives on consecutive queries being close to each other.  Probe that on the host (4 096 sampled
 	// neighbours against the spacing np points would have if spread evenly over their box); a batch that fails is walked
 	// in Morton order and its results are scattered back to the caller's order (a shuffled 4.6 M batch: 3.6 x faster).
+	bool incoherent = false;
 	if (np >= (1 << 16)) {
 		// same criterion as query_probe_kernel: sampled packets of 32 consecutive queries against an evenly spread clump of 32
 		const int64_t m = 4096, npk = np / 32, stride = npk > m ? npk / m : 1;
@@ -1858,18 +1859,13 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 		if (!never && D2 > 0 && std::isfinite(adj) && adj > D2) {
 			FPOHM_REQUIRE(np < (1ll << 30), FPOHM_ERANGE, "%s: %lld queries in one call", who, (long long)np);
 			const double ext = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
-			dP.upload(P, 3 * np);
-			if (cp_mode() >= 2 && mesh->n_wnodes > 0) {     // the wide-packet kernels walk a permutation themselves: no gather / scatter passes
-				QueryScratch q;
-				launch_closest_point_ex(ctx, mesh, with_sign, dP.p, np, S ? dS.p : nullptr, I ? dI.p : nullptr, C ? dC.p : nullptr, N ? dN.p : nullptr, s, q, CP_SORT_ALWAYS);
-				if (S) dS.download(S, np);
-				if (I) dI.download(I, np);
-				if (C) dC.download(C, 3 * np);
-				if (N) dN.download(N, 3 * np);
-				t.stop();
-				FPOHM_CUDA(cudaStreamSynchronize(s));
-				return FPOHM_OK;
+			if (cp_mode() >= 2 && mesh->n_wnodes > 0) {
+				// the wide-packet kernels walk a permutation themselves (no gather / scatter passes): the batch goes through the same
+				// upload / compute / download pipeline as a coherent one, in a few large chunks that are each walked in Morton order
+				incoherent = true;
+				goto pipeline;
 			}
+			dP.upload(P, 3 * np);
 			DevBuf<uint32_t> key(np, s), key2(np, s), idx(np, s), perm(np, s);
 			query_keys_kernel<<<grid_for(ctx, np, 256), 256, 0, s>>>(dP.p, np, mn[0], mn[1], mn[2], ext > 0 ? 1024.0 / ext : 0.0, key.p, idx.p);
 			FPOHM_LAUNCH_CHECK(ctx);
@@ -1895,8 +1891,38 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 			return FPOHM_OK;
 		}
 	}
-	static const int64_t chunk = getenv("FPOHM_CP_CHUNK") ? atoll(getenv("FPOHM_CP_CHUNK")) : (1 << 19);
-	static const int n_comp = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 3;
+pipeline:
+	static const int64_t chunk_coherent = getenv("FPOHM_CP_CHUNK") ? atoll(getenv("FPOHM_CP_CHUNK")) : (1 << 19);
+	static const int64_t chunk_sorted_env = getenv("FPOHM_CP_CHUNK_SORT") ? atoll(getenv("FPOHM_CP_CHUNK_SORT")) : 0;
+	static const int n_comp_env = getenv("FPOHM_CP_LANES") ? atoi(getenv("FPOHM_CP_LANES")) : 0;
+	// A chunk of an incoherent batch is ordered on its own, so the fewer points it has the wider its packets are: chunks are large
+	// and of equal size.  If a stretch of 2^20 consecutive queries is a compact part of the batch (lattice rows: 35.4 ms for the
+	// 10 M classification set against 45.2 ms in one piece) chunks of 2^20 overlap best; a batch in random order is best cut at
+	// 2^21 (43.6 against 45.6 ms; 2^20: 46.9, 2^19: 55 ms).  scripts/e2e_c4.py.
+	int64_t chunk = chunk_coherent;
+	if (incoherent) {
+		int64_t target = chunk_sorted_env;
+		if (target <= 0) {
+			target = 1 << 21;
+			if (np > (1 << 20)) {
+				double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL}, all_lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, all_hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+				for (int64_t k = 0; k < 2048; ++k) {
+					const double *a = P + 3 * (k * ((1 << 20) / 2048)), *b = P + 3 * (k * (np / 2048));
+					for (int c = 0; c < 3; ++c) {
+						if (std::isfinite(a[c])) { lo[c] = std::min(lo[c], a[c]); hi[c] = std::max(hi[c], a[c]); }
+						if (std::isfinite(b[c])) { all_lo[c] = std::min(all_lo[c], b[c]); all_hi[c] = std::max(all_hi[c], b[c]); }
+					}
+				}
+				double v = 1, va = 1;
+				for (int c = 0; c < 3; ++c) { v *= std::max(hi[c] - lo[c], 0.0); va *= std::max(all_hi[c] - all_lo[c], 0.0); }
+				if (va > 0 && v <= 0.3 * va) target = 1 << 20;
+			}
+		}
+		const int64_t k = (np + target - 1) / target;
+		chunk = (((np + k - 1) / k) + 31) & ~(int64_t)31;
+	}
+	const int n_comp = n_comp_env > 0 ? n_comp_env : (incoherent ? 4 : 3);
+	const int sort_policy = incoherent ? CP_SORT_ALWAYS : CP_SORT_NEVER;
 	const int64_t n_chunks = (np + chunk - 1) / chunk;
 	while ((int64_t)ctx->ev_pool.size() < 2 * n_chunks) {
 		cudaEvent_t e;
@@ -1925,7 +1951,7 @@ static int host_query(fpohm_ctx *ctx, fpohm_mesh *mesh, bool with_sign, const do
 		FPOHM_CUDA(cudaStreamWaitEvent(cs, ctx->ev_pool[(size_t)(2 * k)], 0));
 		if (timeline) cudaEventRecord(tl[(size_t)(4 * k)], cs);
 		launch_closest_point(ctx, mesh, with_sign, dP.p + 3 * o, n, S ? dS.p + o : nullptr, I ? dI.p + o : nullptr,
-		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs, CP_SORT_NEVER);   // the host probe above found the batch coherent
+		                     C ? dC.p + 3 * o : nullptr, N ? dN.p + 3 * o : nullptr, cs, sort_policy);   // decided by the host probe above
 		FPOHM_CUDA(cudaEventRecord(ctx->ev_pool[(size_t)(2 * k + 1)], cs));
 		if (timeline) cudaEventRecord(tl[(size_t)(4 * k + 1)], cs);
 		static const bool own_down = getenv("FPOHM_CP_DOWN") ? atoi(getenv("FPOHM_CP_DOWN")) != 0 : true;
