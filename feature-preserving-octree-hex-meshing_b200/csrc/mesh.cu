@@ -124,35 +124,46 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
 	const auto t0 = now();
 	const bool on_host = host_tree || m->nF < 64;
+	// independent of the tree: the three normal sets and the SHAPE of the 8-wide collapse (a function of nF alone).  In the device
+	// build they run while the host threads sort the tied barycentre axes (the longest single item of a build).
+	std::vector<WideKid> kids;
+	int32_t n_wide = 0;
+	double ms_normals = 0, ms_shape = 0;
+	auto independent = [&]() {
+		const auto a = now();
+		static const bool host_normals = getenv("FPOHM_NORMALS_HOST") != nullptr;      // A/B: the host builder of round 1
+		if (host_normals) {
+			build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
+			m->hnormals_valid = true; m->nE = (int64_t)m->hE.size() / 2;
+			m->FN.alloc((int64_t)m->hFN.size(), s); m->FN.upload(m->hFN.data(), (int64_t)m->hFN.size());
+			m->VN.alloc((int64_t)m->hVN.size(), s); m->VN.upload(m->hVN.data(), (int64_t)m->hVN.size());
+			m->EN.alloc((int64_t)m->hEN.size(), s); m->EN.upload(m->hEN.data(), (int64_t)m->hEN.size());
+			m->EMAP.alloc((int64_t)m->hEMAP.size(), s); m->EMAP.upload(m->hEMAP.data(), (int64_t)m->hEMAP.size());
+			m->dE.alloc((int64_t)m->hE.size(), s); m->dE.upload(m->hE.data(), (int64_t)m->hE.size());
+		} else {
+			build_normals_device(ctx, m, s);
+		}
+		const auto b2 = now();
+		wide_shape_host(m->nF, kids, n_wide);
+		ms_normals = ms(a, b2); ms_shape = ms(b2, now());
+	};
 	if (on_host) {
 		build_igl_tree(m->hV.data(), m->nV, m->hF.data(), m->nF, m->htree);
 		m->htree_valid = true;
 		m->t_box.alloc((int64_t)m->htree.box.size(), s); m->t_box.upload(m->htree.box.data(), (int64_t)m->htree.box.size());
 		m->t_prim.alloc((int64_t)m->htree.prim.size(), s); m->t_prim.upload(m->htree.prim.data(), (int64_t)m->htree.prim.size());
+		independent();
 	} else {
-		build_igl_tree_device(ctx, m, s, m->tree_ties_host);
-	}
-	const auto t1 = now();
-	static const bool host_normals = getenv("FPOHM_NORMALS_HOST") != nullptr;      // A/B: the host builder of round 1
-	if (host_normals) {
-		build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
-		m->hnormals_valid = true; m->nE = (int64_t)m->hE.size() / 2;
-		m->FN.alloc((int64_t)m->hFN.size(), s); m->FN.upload(m->hFN.data(), (int64_t)m->hFN.size());
-		m->VN.alloc((int64_t)m->hVN.size(), s); m->VN.upload(m->hVN.data(), (int64_t)m->hVN.size());
-		m->EN.alloc((int64_t)m->hEN.size(), s); m->EN.upload(m->hEN.data(), (int64_t)m->hEN.size());
-		m->EMAP.alloc((int64_t)m->hEMAP.size(), s); m->EMAP.upload(m->hEMAP.data(), (int64_t)m->hEMAP.size());
-		m->dE.alloc((int64_t)m->hE.size(), s); m->dE.upload(m->hE.data(), (int64_t)m->hE.size());
-	} else {
-		build_normals_device(ctx, m, s);
+		build_igl_tree_device(ctx, m, s, m->tree_ties_host, independent);
 	}
 	const auto t2 = now();
 	// QNode / QNodeF / prim_parent / (parent, depth) / 8-wide collapse / float triangles: on the device (tree_flatten.cu)
-	flatten_tree_device(ctx, m, s, m->t_box.p, m->t_prim.p);
+	flatten_tree_device(ctx, m, s, m->t_box.p, m->t_prim.p, kids, n_wide);
 	m->qroot = m->nF == 1 ? ~0 : 0;      // a single facet: the root is the leaf ~0
 	FPOHM_CUDA(cudaStreamSynchronize(s));
-	if (timeline) fprintf(stderr, "[fpohm tree] %lld facets: igl tree %.1f ms (%s; host-sorted axes %d%d%d), normals %.1f ms, flattening + wide tree + uploads %.1f ms\n",
-	                      (long long)m->nF, ms(t0, t1), on_host ? "host" : "device", m->tree_ties_host[0], m->tree_ties_host[1], m->tree_ties_host[2],
-	                      ms(t1, t2), ms(t2, now()));
+	if (timeline) fprintf(stderr, "[fpohm tree] %lld facets: igl tree + normals + wide shape %.1f ms (%s; host-sorted axes %d%d%d; normals %.1f ms and wide shape %.1f ms under the host sorts), flattening kernels + uploads %.1f ms\n",
+	                      (long long)m->nF, ms(t0, t2), on_host ? "host" : "device", m->tree_ties_host[0], m->tree_ties_host[1], m->tree_ties_host[2],
+	                      ms_normals, ms_shape, ms(t2, now()));
 	m->has_tree = true;
 }
 

@@ -3,6 +3,9 @@
 #pragma once
 #include "internal.h"
 
+#include <functional>
+#include <vector>
+
 namespace fpohm {
 
 // One internal node of the flattened closest-point tree.  Both child boxes live in the parent so a
@@ -105,8 +108,12 @@ struct fpohm_mesh {
 namespace fpohm {
 // igl::AABB::init on the device (tree_device.cu): fills `out` exactly as build_igl_tree does.  ties_host[d] reports the axes whose
 // ranks had to come from the host sort.
-void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ties_host[3]);      // fills m->t_box / m->t_prim
-void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const double *box, const int32_t *prim);   // tree_flatten.cu
+// `while_sorting` runs on the calling thread after the host sorts of the tied axes have been started and before they are joined
+void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ties_host[3], const std::function<void()> &while_sorting);      // fills m->t_box / m->t_prim
+struct WideKid { int32_t dfs, cnt, wide; };      // binary node behind a wide child, its facet count (0: empty slot), wide node it becomes
+// shape of the 8-wide collapse: a function of the facet count alone (host, data-free) -> 8 entries per wide node
+void wide_shape_host(int64_t nF, std::vector<WideKid> &kids, int32_t &n_wide);
+void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const double *box, const int32_t *prim, const std::vector<WideKid> &kids, int32_t n_wide);   // tree_flatten.cu
 void mesh_host_tree(fpohm_mesh *m);
 void build_normals_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s);                           // normals_device.cu: FN / VN / EN / E / EMAP
 void mesh_host_normals(fpohm_mesh *m);                                                              // host copies, on demand                                                                 // host copy of the DFS arrays, on demand

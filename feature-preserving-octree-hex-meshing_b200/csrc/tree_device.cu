@@ -159,7 +159,7 @@ __global__ void leaf_prim_kernel(const int32_t *__restrict__ leaf_id_of_pos, con
 
 namespace fpohm {
 
-void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ties_host[3]) {
+void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ties_host[3], const std::function<void()> &while_sorting) {
 	const int64_t nF = m->nF;
 	const size_t nn = 2 * (size_t)nF - 1;
 	FPOHM_REQUIRE(nF < (1ll << 31), FPOHM_ERANGE, "tree build: %lld facets", (long long)nF);
@@ -227,6 +227,9 @@ void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ti
 			ties_host[d] = h_ties[d] > 0 ? 1 : 0;
 			if (ties_host[d]) { hr[(size_t)d].resize((size_t)nF); th.emplace_back(host_rank_axis, m->hV.data(), m->hF.data(), nF, d, hr[(size_t)d].data()); }
 		}
+		// the caller's independent work (normals, the wide tree's shape) runs here, under the host sorts; a throw must not leave
+		// joinable threads behind
+		try { if (while_sorting) while_sorting(); } catch (...) { for (auto &t : th) t.join(); throw; }
 		for (auto &t : th) t.join();
 		for (int d = 0; d < 3; ++d) if (ties_host[d]) rank[d].upload(hr[(size_t)d].data(), nF);
 		FPOHM_CUDA(cudaStreamSynchronize(s));      // hr is a local

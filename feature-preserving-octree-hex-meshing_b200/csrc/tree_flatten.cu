@@ -62,7 +62,6 @@ __global__ void flatten_kernel(int64_t nF, const double *__restrict__ box, const
 	}
 }
 
-struct WideKid { int32_t dfs, cnt, wide; };      // binary node behind a wide child, its facet count (0: empty slot), wide node it becomes
 __global__ void wide_fill_kernel(int64_t n_wide, const WideKid *__restrict__ kids, const double *__restrict__ box, const int32_t *__restrict__ prim,
                                  WNode *__restrict__ w)
 {
@@ -107,7 +106,49 @@ __global__ void vertex_rounding_kernel(const double *__restrict__ V, int64_t nV,
 namespace fpohm {
 
 // box / prim: device arrays of the 2 nF - 1 DFS pre-order nodes
-void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const double *box, const int32_t *prim) {
+void wide_shape_host(int64_t nF, std::vector<WideKid> &kids, int32_t &n_wide_out) {
+	kids.clear(); n_wide_out = 0;
+	if (nF < 2) return;
+	const int64_t ni = nF - 1;
+	kids.reserve((size_t)ni / 2 + 64);
+	struct Work { int32_t dfs, cnt, wide; };
+	std::vector<Work> work;
+	int32_t n_wide = 1;
+	kids.resize(8);
+	work.push_back({0, (int32_t)nF, 0});
+	while (!work.empty()) {
+		const Work b = work.back();
+		work.pop_back();
+		int32_t kid[8], kc[8];
+		int nk = 2;
+		const int32_t nl = (b.cnt + 1) / 2;
+		kid[0] = b.dfs + 1; kc[0] = nl; kid[1] = b.dfs + 2 * nl; kc[1] = b.cnt - nl;
+		while (nk < 8) {
+			int best = -1;
+			for (int k = 0; k < nk; ++k) if (kc[k] > 1 && (best < 0 || kc[k] > kc[best])) best = k;
+			if (best < 0) break;
+			const int32_t o = kid[best], oc = kc[best], onl = (oc + 1) / 2;
+			for (int k = nk; k > best + 1; --k) { kid[k] = kid[k - 1]; kc[k] = kc[k - 1]; }      // keep the binary tree's left-to-right order
+			kid[best] = o + 1; kc[best] = onl; kid[best + 1] = o + 2 * onl; kc[best + 1] = oc - onl;
+			++nk;
+		}
+		for (int k = 0; k < 8; ++k) {
+			WideKid e{0, 0, 0};
+			if (k < nk) {
+				e.dfs = kid[k]; e.cnt = kc[k];
+				if (kc[k] > 1) {
+					e.wide = n_wide++;
+					kids.resize(8 * (size_t)n_wide);
+					work.push_back({kid[k], kc[k], e.wide});
+				}
+			}
+			kids[8 * (size_t)b.wide + (size_t)k] = e;
+		}
+	}
+	n_wide_out = n_wide;
+}
+
+void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const double *box, const int32_t *prim, const std::vector<WideKid> &kids, int32_t n_wide) {
 	const int64_t nF = m->nF, nn = 2 * nF - 1, ni = nF - 1;
 	const int blk = 256;
 	m->n_qnodes = ni;
@@ -124,43 +165,6 @@ void flatten_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, const do
 	{ int32_t c = (int32_t)nF, d = 0; while ((c + 1) / 2 > 1) { c = (c + 1) / 2; ++d; } m->qdepth = nF > 1 ? d : 0; }
 	m->n_wnodes = 0;
 	if (ni > 0) {
-		// structure of the 8-wide collapse from counts (host, data-free), then one fill kernel
-		std::vector<WideKid> kids;
-		kids.reserve((size_t)ni / 2 + 64);
-		struct Work { int32_t dfs, cnt, wide; };
-		std::vector<Work> work;
-		int32_t n_wide = 1;
-		kids.resize(8);
-		work.push_back({0, (int32_t)nF, 0});
-		while (!work.empty()) {
-			const Work b = work.back();
-			work.pop_back();
-			int32_t kid[8], kc[8];
-			int nk = 2;
-			const int32_t nl = (b.cnt + 1) / 2;
-			kid[0] = b.dfs + 1; kc[0] = nl; kid[1] = b.dfs + 2 * nl; kc[1] = b.cnt - nl;
-			while (nk < 8) {
-				int best = -1;
-				for (int k = 0; k < nk; ++k) if (kc[k] > 1 && (best < 0 || kc[k] > kc[best])) best = k;
-				if (best < 0) break;
-				const int32_t o = kid[best], oc = kc[best], onl = (oc + 1) / 2;
-				for (int k = nk; k > best + 1; --k) { kid[k] = kid[k - 1]; kc[k] = kc[k - 1]; }      // keep the binary tree's left-to-right order
-				kid[best] = o + 1; kc[best] = onl; kid[best + 1] = o + 2 * onl; kc[best + 1] = oc - onl;
-				++nk;
-			}
-			for (int k = 0; k < 8; ++k) {
-				WideKid e{0, 0, 0};
-				if (k < nk) {
-					e.dfs = kid[k]; e.cnt = kc[k];
-					if (kc[k] > 1) {
-						e.wide = n_wide++;
-						kids.resize(8 * (size_t)n_wide);
-						work.push_back({kid[k], kc[k], e.wide});
-					}
-				}
-				kids[8 * (size_t)b.wide + (size_t)k] = e;
-			}
-		}
 		m->n_wnodes = n_wide;
 		m->wnodes.alloc(n_wide, s);
 		DevBuf<WideKid> dk(8 * (int64_t)n_wide, s);
