@@ -473,7 +473,11 @@ cp_packet_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 			if (STATS) ++leaf_steps;
 		};
 		while (top > 0) {
+			// the per-warp stack is shared memory every lane pushes the same values to: vote intrinsics are not memory barriers, so
+			// the pushes of the previous iteration are ordered against this pop explicitly
+			__syncwarp();
 			const int32_t cur = stk[--top];
+			__syncwarp();                                    // nobody re-uses the slot before every lane has read it
 			const NodeBoxes nb = load_node(fnodes + cur);
 			const float dl = gap2_low(nb.a.x, nb.a.y, nb.a.z, nb.a.w, nb.b.x, nb.b.y, pfx, pfy, pfz);
 			const float dr = gap2_low(nb.b.z, nb.b.w, nb.c.x, nb.c.y, nb.c.z, nb.c.w, pfx, pfy, pfz);

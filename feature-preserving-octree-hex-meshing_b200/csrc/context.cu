@@ -178,6 +178,7 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	              "fpohm_ctx_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
 	DeviceGuard g(device);
 	fpohm_ctx *c = new fpohm_ctx;
+	struct Guard { fpohm_ctx *c; ~Guard() { if (c) fpohm_ctx_destroy(c); } } guard{c};      // a failing call below must not leak the context
 	c->device = device;
 	c->sm_count = prop.multiProcessorCount;
 	FPOHM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -191,6 +192,7 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 	// (the device's default stream-ordered pool is left as the process configured it: this context's buffers live in its own arena)
 	c->arena = arena_create(device, c->stream);
 	side_pool_ensure(device);
+	guard.c = nullptr;
 	*out = c;
 	FPOHM_API_END
 }
@@ -198,18 +200,18 @@ int fpohm_ctx_create(int device, fpohm_ctx **out) {
 void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	if (!ctx) return;
 	DeviceGuard g(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
+	// (also the failure path of fpohm_ctx_create: members may still be null)
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	fpohm_ctx_mesh_cache_clear(ctx);
-	for (int k = 0; k < fpohm_ctx::QRING; ++k) { cudaEventDestroy(ctx->q_ev0[k]); cudaEventDestroy(ctx->q_ev1[k]); }
-	cudaEventDestroy(ctx->ev0);
-	cudaEventDestroy(ctx->ev1);
-	cudaStreamDestroy(ctx->aux[0]);
-	cudaStreamDestroy(ctx->aux[1]);
-	for (int k = 2; k < 5; ++k) cudaStreamDestroy(ctx->aux[k]);
+	for (int k = 0; k < fpohm_ctx::QRING; ++k) { if (ctx->q_ev0[k]) cudaEventDestroy(ctx->q_ev0[k]); if (ctx->q_ev1[k]) cudaEventDestroy(ctx->q_ev1[k]); }
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	for (int k = 0; k < 5; ++k) if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-	cudaEventDestroy(ctx->ev_sync);
-	arena_destroy(ctx->arena);
-	cudaStreamDestroy(ctx->stream);
+	if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+	if (ctx->arena) arena_destroy(ctx->arena);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	cudaGetLastError();
 	delete ctx;
 }
 
