@@ -188,43 +188,95 @@ __device__ __forceinline__ void occ_set_bits(uint32_t *__restrict__ bits, int64_
 		first += take; count -= take;
 	}
 }
+// One warp = 32 facets.  The rows (fixed y, z; a run of x) of the small boxes of a warp are POOLED: a warp prefix sum over the row
+// counts, then the lanes take rows 32 at a time whatever facet they belong to (the first version let every lane walk its own box
+// row by row: lanes with 4 rows waited for lanes with 27, 214 us at 1024^3 / 2 M facets).  Boxes over OCC_INLINE voxels go to a
+// compact list: slots AND row offsets reserved with one packed 64-bit atomicAdd per warp (count << OCC_ROW_BITS | rows), so the
+// list is ordered by row offset and occupancy_rows_kernel binary-searches it — no scan over all facets.
+#define OCC_ROW_BITS 36
 __global__ void __launch_bounds__(256)
-occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, int *__restrict__ box6, int64_t *__restrict__ cnt,
-                       uint32_t *__restrict__ bits)
+occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, int *__restrict__ big_box6, int64_t *__restrict__ big_off,
+                       unsigned long long *__restrict__ ctl /* [0] packed counter, [1] exact row sum */, uint32_t *__restrict__ bits)
 {
-	for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f <= nF; f += (int64_t)gridDim.x * blockDim.x) {
-		if (f == nF) { cnt[f] = 0; continue; }
-		const double *t = tri + 9 * f;
-		int lo[3], hi[3];
-		const int n[3] = {g.nx, g.ny, g.nz};
-		const double o[3] = {g.ox, g.oy, g.oz};
-		int64_t vol = 1;
+	const int lane = threadIdx.x & 31;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < nF; base += stride) {   // warp-uniform trip count
+		const int64_t f = base + lane;
+		int lo[3] = {0, 0, 0}, ext[3] = {0, 0, 0}, n_small = 0;
+		int64_t n_big = 0;
+		if (f < nF) {
+			const double *t = tri + 9 * f;
+			const int n[3] = {g.nx, g.ny, g.nz};
+			const double o[3] = {g.ox, g.oy, g.oz};
+			int64_t vol = 1;
 #pragma unroll
-		for (int c = 0; c < 3; ++c) {
-			const double mn = fmin(t[c], fmin(t[3 + c], t[6 + c])), mx = fmax(t[c], fmax(t[3 + c], t[6 + c]));
-			lo[c] = first_cell_max_ge(mn, o[c], g.sp, n[c]);
-			hi[c] = last_cell_min_le(mx, o[c], g.sp, n[c]);
-			vol *= hi[c] >= lo[c] ? (hi[c] - lo[c] + 1) : 0;
+			for (int c = 0; c < 3; ++c) {
+				const double mn = fmin(t[c], fmin(t[3 + c], t[6 + c])), mx = fmax(t[c], fmax(t[3 + c], t[6 + c]));
+				lo[c] = first_cell_max_ge(mn, o[c], g.sp, n[c]);
+				const int hi = last_cell_min_le(mx, o[c], g.sp, n[c]);
+				ext[c] = hi >= lo[c] ? hi - lo[c] + 1 : 0;
+				vol *= ext[c];
+			}
+			if (vol == 0) { }
+			else if (vol <= OCC_INLINE) n_small = ext[1] * ext[2];
+			else n_big = (int64_t)ext[1] * ext[2];
 		}
-		if (vol <= OCC_INLINE) {
-			for (int z = lo[2]; z <= hi[2] && vol; ++z)
-				for (int y = lo[1]; y <= hi[1]; ++y)
-					occ_set_bits(bits, ((int64_t)z * g.ny + y) * g.nx + lo[0], hi[0] - lo[0] + 1);      // one row of the box
-			cnt[f] = 0;
-		} else {
-			cnt[f] = (int64_t)(hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);                             // rows of a large box, one per thread
-			for (int c = 0; c < 3; ++c) { box6[6 * f + c] = lo[c]; box6[6 * f + 3 + c] = hi[c] - lo[c] + 1; }
+		const unsigned big_mask = __ballot_sync(0xffffffffu, n_big > 0);
+		if (big_mask) {                                   // rare on fine meshes; warp-uniform
+			long long incl64 = n_big;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, incl64, o); if (lane >= o) incl64 += v; }
+			const long long total64 = __shfl_sync(0xffffffffu, incl64, 31);
+			unsigned long long old = 0;
+			if (lane == 0) {
+				old = atomicAdd(ctl, ((unsigned long long)__popc(big_mask) << OCC_ROW_BITS) + (unsigned long long)total64);
+				atomicAdd(ctl + 1, (unsigned long long)total64);
+			}
+			old = __shfl_sync(0xffffffffu, old, 0);
+			if (n_big > 0) {
+				const int64_t pos = (int64_t)(old >> OCC_ROW_BITS) + __popc(big_mask & ((1u << lane) - 1u));
+				for (int c = 0; c < 3; ++c) { big_box6[6 * pos + c] = lo[c]; big_box6[6 * pos + 3 + c] = ext[c]; }
+				big_off[pos] = (int64_t)(old & ((1ull << OCC_ROW_BITS) - 1ull)) + (incl64 - n_big);
+			}
+		}
+		int incl = n_small;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		const int excl = incl - n_small;
+		const int total = __shfl_sync(0xffffffffu, incl, 31);
+		const float inv_h = ext[1] > 0 ? __frcp_rn((float)ext[1]) : 0.0f;
+		for (int p0 = 0; p0 < total; p0 += 32) {
+			const int p = p0 + lane;
+			int src = 0;                                    // largest lane with excl <= p
+#pragma unroll
+			for (int step = 16; step > 0; step >>= 1) {
+				const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
+				if (src + step < 32 && e <= p) src += step;
+			}
+			const int sx = __shfl_sync(0xffffffffu, lo[0], src), sy = __shfl_sync(0xffffffffu, lo[1], src), sz = __shfl_sync(0xffffffffu, lo[2], src);
+			const int sw = __shfl_sync(0xffffffffu, ext[0], src), sh = __shfl_sync(0xffffffffu, ext[1], src), se = __shfl_sync(0xffffffffu, excl, src);
+			const float sih = __shfl_sync(0xffffffffu, inv_h, src);
+			if (p < total) {
+				const int k = p - se;                         // 0 <= k < 64, 1 <= sh <= 64: (k + 0.5) / sh is at least 0.5 / 64 off an integer
+				const int zz = __float2int_rz(((float)k + 0.5f) * sih);
+				const int y = sy + (k - zz * sh), z = sz + zz;
+				occ_set_bits(bits, ((int64_t)z * g.ny + y) * g.nx + sx, sw);      // one row of the box
+			}
 		}
 	}
 }
 __global__ void __launch_bounds__(256)
-occupancy_rows_kernel(OccGrid g, int64_t nF, const int *__restrict__ box6, const int64_t *__restrict__ off, uint32_t *__restrict__ bits) {
-	const int64_t n_rows = off[nF];                     // read on the device: no host round trip after the scan
+occupancy_rows_kernel(OccGrid g, const int *__restrict__ big_box6, const int64_t *__restrict__ big_off, const unsigned long long *__restrict__ ctl,
+                      uint32_t *__restrict__ bits)
+{
+	// counts are read on the device: no host round trip in front of this launch
+	const int64_t n_big = (int64_t)(ctl[0] >> OCC_ROW_BITS), n_rows = (int64_t)(ctl[0] & ((1ull << OCC_ROW_BITS) - 1ull));
+	if (ctl[1] >> OCC_ROW_BITS) return;                // offsets wrapped: the host reports FPOHM_ERANGE
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_rows; t += (int64_t)gridDim.x * blockDim.x) {
-		int64_t lo = 0, hi = nF;
-		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
-		const int *b = box6 + 6 * lo;
-		const int64_t k = t - off[lo];
+		int64_t lo = 0, hi = n_big;
+		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (big_off[mid] <= t) lo = mid; else hi = mid; }
+		const int *b = big_box6 + 6 * lo;
+		const int64_t k = t - big_off[lo];
 		const int y = b[1] + (int)(k % b[4]), z = b[2] + (int)(k / b[4]);
 		occ_set_bits(bits, ((int64_t)z * g.ny + y) * g.nx + b[0], b[3]);
 	}
@@ -486,28 +538,29 @@ int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double g
 	FPOHM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n < (1ll << 31), FPOHM_ERANGE, "fpohm_voxel_occupancy: bad dims");
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = ctx->stream;
-	DevBuf<uint8_t> d(n, s);
-	DevBuf<uint32_t> bits((n + 31) / 32 + 1, s);
-	KernelTimer t(ctx, s);
-	bits.zero();
-	const OccGrid og{dims[0], dims[1], dims[2], grid_origin[0], grid_origin[1], grid_origin[2], spacing};
 	const int64_t nF = mesh->nF;
-	DevBuf<int> box6(6 * nF, s);
-	DevBuf<int64_t> cnt(nF + 1, s), off(nF + 1, s);
-	occupancy_boxes_kernel<<<grid_for(ctx, nF + 1, 256), 256, 0, s>>>(og, mesh->tri.p, nF, box6.p, cnt.p, bits.p);
+	FPOHM_REQUIRE(nF < (1ll << (64 - OCC_ROW_BITS)), FPOHM_ERANGE, "fpohm_voxel_occupancy: %lld facets (the limit is 2^28)", (long long)nF);
+	DevBuf<uint8_t> d(n, s);
+	const int64_t n_words = (((n + 31) / 32 + 1) + 1) & ~(int64_t)1;        // even: the two 64-bit control words behind the bits are aligned
+	DevBuf<uint32_t> bits(n_words + 4, s);
+	unsigned long long *ctl = reinterpret_cast<unsigned long long *>(bits.p + n_words);
+	KernelTimer t(ctx, s);
+	bits.zero();                                       // bits and control words in one memset
+	const OccGrid og{dims[0], dims[1], dims[2], grid_origin[0], grid_origin[1], grid_origin[2], spacing};
+	DevBuf<int> box6(6 * nF, s);                        // touched only where a facet's box holds more than OCC_INLINE voxels
+	DevBuf<int64_t> off(nF, s);
+	occupancy_boxes_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(og, mesh->tri.p, nF, box6.p, off.p, ctl, bits.p);
 	FPOHM_LAUNCH_CHECK(ctx);
-	size_t tb = 0;
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nF + 1, s));
-	DevBuf<uint8_t> tmp((int64_t)tb, s);
-	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nF + 1, s));
-	ctx->launches += 1;
-	occupancy_rows_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(og, nF, box6.p, off.p, bits.p);
+	occupancy_rows_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(og, box6.p, off.p, ctl, bits.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	occupancy_expand_kernel<<<grid_for(ctx, n >> 4, 256, 16), 256, 0, s>>>(bits.p, n, d.p);
 	FPOHM_LAUNCH_CHECK(ctx);
 	t.stop();
+	unsigned long long h_ctl[2] = {0, 0};
+	FPOHM_CUDA(cudaMemcpyAsync(h_ctl, ctl, 16, cudaMemcpyDeviceToHost, s));
 	d.download(out, n);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
+	FPOHM_REQUIRE((h_ctl[1] >> OCC_ROW_BITS) == 0, FPOHM_ERANGE, "fpohm_voxel_occupancy: %llu box rows (the limit is 2^%d)", h_ctl[1], OCC_ROW_BITS);
 	FPOHM_API_END
 }
 
