@@ -176,33 +176,38 @@ __device__ __forceinline__ int last_cell_min_le(double hi, double o, double sp, 
 
 struct OccGrid { int nx, ny, nz; double ox, oy, oz, sp; };
 #define OCC_INLINE 64
-// Facets stamp BITS (one per voxel, 128 MB at 1024^3: mostly L2 traffic), a streaming kernel then writes every output byte
-// exactly once, 16 per thread.  The first version zeroed the byte grid and scattered single byte stores into it: every
-// stamped voxel cost a 32-byte sector read-modify-write on top of the 1 GiB memset (0.79 ms at 1024^3, 23 % of HBM peak).
-__device__ __forceinline__ void occ_set_bits(uint32_t *__restrict__ bits, int64_t first, int count) {   // voxels [first, first + count)
-	while (count > 0) {
-		const int64_t w = first >> 5;
-		const int b = (int)(first & 31), take = min(count, 32 - b);
-		const uint32_t m = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << b;
-		if ((bits[w] & m) != m) atomicOr(bits + w, m);
-		first += take; count -= take;
-	}
+// Facets stamp BITS, a streaming kernel then writes every output byte exactly once.  (The first version zeroed the byte grid and
+// scattered single byte stores into it: every stamped voxel cost a 32-byte sector read-modify-write on top of the 1 GiB memset,
+// 0.79 ms at 1024^3, 23 % of HBM peak.)  The bits are TILED: one 32-bit word = a 4 x 4 x 2 block of voxels (bit = (z&1)*16 +
+// (y&3)*4 + (x&3)), words x-fastest over the tile grid, so a 32-byte sector holds 32 x 4 x 2 voxels and the box of a facet — a few
+// voxels in every direction — lies in 1 - 4 sectors.  With one bit ROW per x-run (round-2 first form) a 3 x 3 x 3 box touched 9
+// different sectors; ncu: 34 M sector loads = 1.1 GB of L2 traffic for 2 M facets, 203 us, L2-bandwidth bound.
+__device__ __forceinline__ uint32_t occ_tile_mask(int x0, int x1, int y0, int y1, int z0, int z1, int tx, int ty, int tz) {
+	// voxels of the closed box [x0,x1] x [y0,y1] x [z0,z1] that lie in tile (tx, ty, tz); the box meets the tile
+	const int xa = max(x0 - 4 * tx, 0), xb = min(x1 - 4 * tx, 3), ya = max(y0 - 4 * ty, 0), yb = min(y1 - 4 * ty, 3);
+	const int za = max(z0 - 2 * tz, 0), zb = min(z1 - 2 * tz, 1);
+	const uint32_t mx = ((1u << (xb - xa + 1)) - 1u) << xa, yb4 = ((1u << (yb - ya + 1)) - 1u) << ya;
+	const uint32_t spread = (yb4 & 1u) | ((yb4 & 2u) << 3) | ((yb4 & 4u) << 6) | ((yb4 & 8u) << 9);      // bit i -> bit 4 i
+	const uint32_t layer = mx * spread;                                                                    // 16 bits, no carries (mx < 16)
+	return (za == 0 ? layer : 0u) | (zb == 1 ? layer << 16 : 0u);
 }
-// One warp = 32 facets.  The rows (fixed y, z; a run of x) of the small boxes of a warp are POOLED: a warp prefix sum over the row
-// counts, then the lanes take rows 32 at a time whatever facet they belong to (the first version let every lane walk its own box
-// row by row: lanes with 4 rows waited for lanes with 27, 214 us at 1024^3 / 2 M facets).  Boxes over OCC_INLINE voxels go to a
-// compact list: slots AND row offsets reserved with one packed 64-bit atomicAdd per warp (count << OCC_ROW_BITS | rows), so the
-// list is ordered by row offset and occupancy_rows_kernel binary-searches it — no scan over all facets.
+// One warp = 32 facets.  The tiles of the small boxes of a warp are POOLED: a warp prefix sum over the tile counts, then the lanes
+// take (facet, tile) pairs OCC_MLP x 32 at a time whatever facet they belong to; all words of a step are LOADED first (independent
+// loads in flight), then compared and OR-ed (an atomic only where a bit is missing).  Boxes over OCC_INLINE voxels go to a compact
+// list: slots AND tile offsets reserved with one packed 64-bit atomicAdd per warp (count << OCC_ROW_BITS | tiles), so the list is
+// ordered by offset and occupancy_tiles_kernel binary-searches it — no scan over all facets.
 #define OCC_ROW_BITS 36
+#define OCC_MLP 4
 __global__ void __launch_bounds__(256)
 occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, int *__restrict__ big_box6, int64_t *__restrict__ big_off,
-                       unsigned long long *__restrict__ ctl /* [0] packed counter, [1] exact row sum */, uint32_t *__restrict__ bits)
+                       unsigned long long *__restrict__ ctl /* [0] packed counter, [1] exact tile sum */, uint32_t *__restrict__ bits)
 {
 	const int lane = threadIdx.x & 31;
+	const int ntx = (g.nx + 3) >> 2, nty = (g.ny + 3) >> 2;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < nF; base += stride) {   // warp-uniform trip count
 		const int64_t f = base + lane;
-		int lo[3] = {0, 0, 0}, ext[3] = {0, 0, 0}, n_small = 0;
+		int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1}, n_small = 0, nwx = 0, nwy = 0;
 		int64_t n_big = 0;
 		if (f < nF) {
 			const double *t = tri + 9 * f;
@@ -213,13 +218,14 @@ occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, in
 			for (int c = 0; c < 3; ++c) {
 				const double mn = fmin(t[c], fmin(t[3 + c], t[6 + c])), mx = fmax(t[c], fmax(t[3 + c], t[6 + c]));
 				lo[c] = first_cell_max_ge(mn, o[c], g.sp, n[c]);
-				const int hi = last_cell_min_le(mx, o[c], g.sp, n[c]);
-				ext[c] = hi >= lo[c] ? hi - lo[c] + 1 : 0;
-				vol *= ext[c];
+				hi[c] = last_cell_min_le(mx, o[c], g.sp, n[c]);
+				vol *= hi[c] >= lo[c] ? hi[c] - lo[c] + 1 : 0;
 			}
-			if (vol == 0) { }
-			else if (vol <= OCC_INLINE) n_small = ext[1] * ext[2];
-			else n_big = (int64_t)ext[1] * ext[2];
+			if (vol > 0) {
+				nwx = (hi[0] >> 2) - (lo[0] >> 2) + 1; nwy = (hi[1] >> 2) - (lo[1] >> 2) + 1;
+				const int64_t tiles = (int64_t)nwx * nwy * ((hi[2] >> 1) - (lo[2] >> 1) + 1);
+				if (vol <= OCC_INLINE) n_small = (int)tiles; else n_big = tiles;
+			}
 		}
 		const unsigned big_mask = __ballot_sync(0xffffffffu, n_big > 0);
 		if (big_mask) {                                   // rare on fine meshes; warp-uniform
@@ -235,7 +241,7 @@ occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, in
 			old = __shfl_sync(0xffffffffu, old, 0);
 			if (n_big > 0) {
 				const int64_t pos = (int64_t)(old >> OCC_ROW_BITS) + __popc(big_mask & ((1u << lane) - 1u));
-				for (int c = 0; c < 3; ++c) { big_box6[6 * pos + c] = lo[c]; big_box6[6 * pos + 3 + c] = ext[c]; }
+				for (int c = 0; c < 3; ++c) { big_box6[6 * pos + c] = lo[c]; big_box6[6 * pos + 3 + c] = hi[c]; }
 				big_off[pos] = (int64_t)(old & ((1ull << OCC_ROW_BITS) - 1ull)) + (incl64 - n_big);
 			}
 		}
@@ -244,59 +250,117 @@ occupancy_boxes_kernel(OccGrid g, const double *__restrict__ tri, int64_t nF, in
 		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
 		const int excl = incl - n_small;
 		const int total = __shfl_sync(0xffffffffu, incl, 31);
-		const float inv_h = ext[1] > 0 ? __frcp_rn((float)ext[1]) : 0.0f;
-		for (int p0 = 0; p0 < total; p0 += 32) {
-			const int p = p0 + lane;
-			int src = 0;                                    // largest lane with excl <= p
+		for (int p0 = 0; p0 < total; p0 += 32 * OCC_MLP) {
+			int64_t w[OCC_MLP];
+			uint32_t m[OCC_MLP], v[OCC_MLP];
 #pragma unroll
-			for (int step = 16; step > 0; step >>= 1) {
-				const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
-				if (src + step < 32 && e <= p) src += step;
+			for (int u = 0; u < OCC_MLP; ++u) {
+				const int p = p0 + 32 * u + lane;
+				int src = 0;                                    // largest lane with excl <= p
+#pragma unroll
+				for (int step = 16; step > 0; step >>= 1) {
+					const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
+					if (src + step < 32 && e <= p) src += step;
+				}
+				const int x0 = __shfl_sync(0xffffffffu, lo[0], src), y0 = __shfl_sync(0xffffffffu, lo[1], src), z0 = __shfl_sync(0xffffffffu, lo[2], src);
+				const int x1 = __shfl_sync(0xffffffffu, hi[0], src), y1 = __shfl_sync(0xffffffffu, hi[1], src), z1 = __shfl_sync(0xffffffffu, hi[2], src);
+				const int swx = __shfl_sync(0xffffffffu, nwx, src), swy = __shfl_sync(0xffffffffu, nwy, src), se = __shfl_sync(0xffffffffu, excl, src);
+				w[u] = 0; m[u] = 0;
+				if (p < total) {
+					// tile number inside the box, x fastest.  A small box (<= 64 voxels) has fewer than 64 tiles and no side over 17: the
+					// quotients (k + 0.5) / d stay at least 0.5 / 64 away from an integer, far beyond the float error of the reciprocal
+					const int k = p - se, sxy = swx * swy;
+					const int kz = __float2int_rz(((float)k + 0.5f) * __frcp_rn((float)sxy)), kr = k - kz * sxy;
+					const int ky = __float2int_rz(((float)kr + 0.5f) * __frcp_rn((float)swx)), kx = kr - ky * swx;
+					const int tx = (x0 >> 2) + kx, ty = (y0 >> 2) + ky, tz = (z0 >> 1) + kz;
+					w[u] = ((int64_t)tz * nty + ty) * ntx + tx;
+					m[u] = occ_tile_mask(x0, x1, y0, y1, z0, z1, tx, ty, tz);
+				}
 			}
-			const int sx = __shfl_sync(0xffffffffu, lo[0], src), sy = __shfl_sync(0xffffffffu, lo[1], src), sz = __shfl_sync(0xffffffffu, lo[2], src);
-			const int sw = __shfl_sync(0xffffffffu, ext[0], src), sh = __shfl_sync(0xffffffffu, ext[1], src), se = __shfl_sync(0xffffffffu, excl, src);
-			const float sih = __shfl_sync(0xffffffffu, inv_h, src);
-			if (p < total) {
-				const int k = p - se;                         // 0 <= k < 64, 1 <= sh <= 64: (k + 0.5) / sh is at least 0.5 / 64 off an integer
-				const int zz = __float2int_rz(((float)k + 0.5f) * sih);
-				const int y = sy + (k - zz * sh), z = sz + zz;
-				occ_set_bits(bits, ((int64_t)z * g.ny + y) * g.nx + sx, sw);      // one row of the box
-			}
+#pragma unroll
+			for (int u = 0; u < OCC_MLP; ++u) v[u] = m[u] ? bits[w[u]] : 0xffffffffu;
+#pragma unroll
+			for (int u = 0; u < OCC_MLP; ++u) if ((v[u] & m[u]) != m[u]) atomicOr(bits + w[u], m[u]);
 		}
 	}
 }
 __global__ void __launch_bounds__(256)
-occupancy_rows_kernel(OccGrid g, const int *__restrict__ big_box6, const int64_t *__restrict__ big_off, const unsigned long long *__restrict__ ctl,
-                      uint32_t *__restrict__ bits)
+occupancy_tiles_kernel(OccGrid g, const int *__restrict__ big_box6, const int64_t *__restrict__ big_off, const unsigned long long *__restrict__ ctl,
+                       uint32_t *__restrict__ bits)
 {
 	// counts are read on the device: no host round trip in front of this launch
-	const int64_t n_big = (int64_t)(ctl[0] >> OCC_ROW_BITS), n_rows = (int64_t)(ctl[0] & ((1ull << OCC_ROW_BITS) - 1ull));
+	const int64_t n_big = (int64_t)(ctl[0] >> OCC_ROW_BITS), n_tiles = (int64_t)(ctl[0] & ((1ull << OCC_ROW_BITS) - 1ull));
 	if (ctl[1] >> OCC_ROW_BITS) return;                // offsets wrapped: the host reports FPOHM_ERANGE
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_rows; t += (int64_t)gridDim.x * blockDim.x) {
+	const int ntx = (g.nx + 3) >> 2, nty = (g.ny + 3) >> 2;
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_tiles; t += (int64_t)gridDim.x * blockDim.x) {
 		int64_t lo = 0, hi = n_big;
 		while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (big_off[mid] <= t) lo = mid; else hi = mid; }
-		const int *b = big_box6 + 6 * lo;
+		const int *b = big_box6 + 6 * lo;                 // lo[3], hi[3]
 		const int64_t k = t - big_off[lo];
-		const int y = b[1] + (int)(k % b[4]), z = b[2] + (int)(k / b[4]);
-		occ_set_bits(bits, ((int64_t)z * g.ny + y) * g.nx + b[0], b[3]);
+		const int nwx = (b[3] >> 2) - (b[0] >> 2) + 1, nwy = (b[4] >> 2) - (b[1] >> 2) + 1;
+		const int kz = (int)(k / ((int64_t)nwx * nwy)), kr = (int)(k - (int64_t)kz * nwx * nwy), ky = kr / nwx, kx = kr - ky * nwx;
+		const int tx = (b[0] >> 2) + kx, ty = (b[1] >> 2) + ky, tz = (b[2] >> 1) + kz;
+		const uint32_t m = occ_tile_mask(b[0], b[3], b[1], b[4], b[2], b[5], tx, ty, tz);
+		uint32_t *wp = bits + ((int64_t)tz * nty + ty) * ntx + tx;
+		if ((*wp & m) != m) atomicOr(wp, m);
 	}
 }
-// bits -> bytes, 16 voxels (one 16-byte streaming store) per thread
+// tiled bits -> bytes.  One thread = one tile word: 4 bytes (4 voxels along x) into each of its 4 x 2 (y, z) rows, so a warp
+// (32 consecutive tiles along x) stores 128 contiguous bytes per row — the store pattern of the voxel fill.
+__device__ __forceinline__ uint32_t occ_nibble_bytes(uint32_t q) { return (q & 1u) | ((q & 2u) << 7) | ((q & 4u) << 14) | ((q & 8u) << 21); }
+// Fast path (nx a multiple of 16): one thread = FOUR tile words (one 16-byte load) -> 16 bytes into each of their 4 x 2 (y, z) rows,
+// a warp stores 512 contiguous bytes per row.  (One word and 4-byte stores per thread was latency bound: 335 us against 211 us.)
 __global__ void __launch_bounds__(256)
-occupancy_expand_kernel(const uint32_t *__restrict__ bits, int64_t n, uint8_t *__restrict__ out) {
-	const int64_t n16 = n >> 4;
-	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n16; t += (int64_t)gridDim.x * blockDim.x) {
-		const uint32_t h = (__ldg(bits + (t >> 1)) >> ((t & 1) * 16)) & 0xffffu;
-		uint4 v;
-		uint32_t q = h & 15u;          v.x = (q & 1u) | ((q & 2u) << 7) | ((q & 4u) << 14) | ((q & 8u) << 21);
-		q = (h >> 4) & 15u;            v.y = (q & 1u) | ((q & 2u) << 7) | ((q & 4u) << 14) | ((q & 8u) << 21);
-		q = (h >> 8) & 15u;            v.z = (q & 1u) | ((q & 2u) << 7) | ((q & 4u) << 14) | ((q & 8u) << 21);
-		q = (h >> 12) & 15u;           v.w = (q & 1u) | ((q & 2u) << 7) | ((q & 4u) << 14) | ((q & 8u) << 21);
-		__stcs(reinterpret_cast<uint4 *>(out) + t, v);
+occupancy_expand4_kernel(OccGrid g, const uint32_t *__restrict__ bits, uint8_t *__restrict__ out) {
+	const unsigned ntx4 = (unsigned)(g.nx >> 4), nty = (unsigned)((g.ny + 3) >> 2), ntz = (unsigned)((g.nz + 1) >> 1);
+	const unsigned n_items = ntx4 * nty * ntz;         // < 2^31 / 128
+	const int64_t layer = (int64_t)g.nx * g.ny;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+		const unsigned row = it / ntx4, i = it - row * ntx4, tz = row / nty, ty = row - tz * nty;
+		const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(bits) + it);
+#pragma unroll
+		for (int dz = 0; dz < 2; ++dz) {
+			const int z = 2 * (int)tz + dz;
+			if (z >= g.nz) break;
+#pragma unroll
+			for (int dy = 0; dy < 4; ++dy) {
+				const int y = 4 * (int)ty + dy;
+				if (y >= g.ny) break;
+				const int sh = 16 * dz + 4 * dy;
+				uint4 v;
+				v.x = occ_nibble_bytes((wv.x >> sh) & 15u); v.y = occ_nibble_bytes((wv.y >> sh) & 15u);
+				v.z = occ_nibble_bytes((wv.z >> sh) & 15u); v.w = occ_nibble_bytes((wv.w >> sh) & 15u);
+				__stcs(reinterpret_cast<uint4 *>(out + (int64_t)z * layer + (int64_t)y * g.nx + 16 * (int64_t)i), v);   // index_from_index3, voxelization.cpp:26-28
+			}
+		}
 	}
-	if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {    // ragged tail
-		const int64_t i = (n16 << 4) + threadIdx.x;
-		out[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+}
+// any dims: one thread = one tile word
+__global__ void __launch_bounds__(256)
+occupancy_expand_kernel(OccGrid g, const uint32_t *__restrict__ bits, uint8_t *__restrict__ out) {
+	const int ntx = (g.nx + 3) >> 2, nty = (g.ny + 3) >> 2, ntz = (g.nz + 1) >> 1;
+	const int n_rows = nty * ntz;                      // rows of tiles
+	const int64_t layer = (int64_t)g.nx * g.ny;
+	const bool aligned = (g.nx & 3) == 0;
+	for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {      // block-uniform: the two divisions are per row, not per tile
+		const int ty = row % nty, tz = row / nty;
+		for (int tx = threadIdx.x; tx < ntx; tx += blockDim.x) {
+			const uint32_t wv = __ldg(bits + (int64_t)row * ntx + tx);
+#pragma unroll
+			for (int dz = 0; dz < 2; ++dz) {
+				const int z = 2 * tz + dz;
+				if (z >= g.nz) break;
+#pragma unroll
+				for (int dy = 0; dy < 4; ++dy) {
+					const int y = 4 * ty + dy;
+					if (y >= g.ny) break;
+					const uint32_t q = (wv >> (16 * dz + 4 * dy)) & 15u;
+					uint8_t *o = out + (int64_t)z * layer + (int64_t)y * g.nx + 4 * tx;
+					if (aligned) __stcs(reinterpret_cast<uint32_t *>(o), occ_nibble_bytes(q));
+					else for (int dx = 0; dx < 4 && 4 * tx + dx < g.nx; ++dx) o[dx] = (q >> dx) & 1u;
+				}
+			}
+		}
 	}
 }
 
@@ -541,7 +605,7 @@ int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double g
 	const int64_t nF = mesh->nF;
 	FPOHM_REQUIRE(nF < (1ll << (64 - OCC_ROW_BITS)), FPOHM_ERANGE, "fpohm_voxel_occupancy: %lld facets (the limit is 2^28)", (long long)nF);
 	DevBuf<uint8_t> d(n, s);
-	const int64_t n_words = (((n + 31) / 32 + 1) + 1) & ~(int64_t)1;        // even: the two 64-bit control words behind the bits are aligned
+	const int64_t n_words = ((int64_t)((dims[0] + 3) / 4) * ((dims[1] + 3) / 4) * ((dims[2] + 1) / 2) + 1) & ~(int64_t)1;   // tiles; even: the 64-bit control words behind them are aligned
 	DevBuf<uint32_t> bits(n_words + 4, s);
 	unsigned long long *ctl = reinterpret_cast<unsigned long long *>(bits.p + n_words);
 	KernelTimer t(ctx, s);
@@ -551,16 +615,21 @@ int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double g
 	DevBuf<int64_t> off(nF, s);
 	occupancy_boxes_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(og, mesh->tri.p, nF, box6.p, off.p, ctl, bits.p);
 	FPOHM_LAUNCH_CHECK(ctx);
-	occupancy_rows_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(og, box6.p, off.p, ctl, bits.p);
+	occupancy_tiles_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(og, box6.p, off.p, ctl, bits.p);
 	FPOHM_LAUNCH_CHECK(ctx);
-	occupancy_expand_kernel<<<grid_for(ctx, n >> 4, 256, 16), 256, 0, s>>>(bits.p, n, d.p);
+	if ((dims[0] & 15) == 0) {
+		const int64_t items = (int64_t)(dims[0] / 16) * ((dims[1] + 3) / 4) * ((dims[2] + 1) / 2);
+		occupancy_expand4_kernel<<<grid_for(ctx, items, 256, 16), 256, 0, s>>>(og, bits.p, d.p);
+	} else {
+		occupancy_expand_kernel<<<(int)std::min<int64_t>((int64_t)((dims[1] + 3) / 4) * ((dims[2] + 1) / 2), (int64_t)ctx->sm_count * 32), 256, 0, s>>>(og, bits.p, d.p);
+	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	t.stop();
 	unsigned long long h_ctl[2] = {0, 0};
 	FPOHM_CUDA(cudaMemcpyAsync(h_ctl, ctl, 16, cudaMemcpyDeviceToHost, s));
 	d.download(out, n);
 	FPOHM_CUDA(cudaStreamSynchronize(s));
-	FPOHM_REQUIRE((h_ctl[1] >> OCC_ROW_BITS) == 0, FPOHM_ERANGE, "fpohm_voxel_occupancy: %llu box rows (the limit is 2^%d)", h_ctl[1], OCC_ROW_BITS);
+	FPOHM_REQUIRE((h_ctl[1] >> OCC_ROW_BITS) == 0, FPOHM_ERANGE, "fpohm_voxel_occupancy: %llu box tiles (the limit is 2^%d)", h_ctl[1], OCC_ROW_BITS);
 	FPOHM_API_END
 }
 

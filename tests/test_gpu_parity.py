@@ -425,6 +425,16 @@ def test_voxel_occupancy_bit_exact_vs_predicate(fp, ctx, ref, port):
         e = L.port_box_overlaps_any(tb2.ctypes.data_as(C.c_void_p), C.c_int64(len(tb2)), C.c_double(g2.origin[0]), C.c_double(g2.origin[1]),
                                     C.c_double(g2.origin[2]), C.c_double(g2.spacing), C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(1))
         assert occ2[z, y, x] == e
+    # x extent a multiple of 16: the 16-byte expansion path (one thread = four 4 x 4 x 2 bit tiles); odd y / z extents clip the last tiles
+    g3 = fp.VoxelGrid(V.min(0) - 0.01, np.array([48, 37, 21]) / 30.0 - 1e-9, 1 / 30.0, 0)
+    assert g3.dims[0] % 16 == 0 and g3.dims[1] % 4 and g3.dims[2] % 2
+    occ3 = fp.voxel_occupancy(ctx, m, g3)
+    for i in np.random.default_rng(1).integers(0, occ3.size, 6000):
+        z, r = divmod(int(i), int(g3.dims[0]) * int(g3.dims[1])); y, x = divmod(r, int(g3.dims[0]))
+        e = L.port_box_overlaps_any(tb.ctypes.data_as(C.c_void_p), C.c_int64(len(tb)), C.c_double(g3.origin[0]), C.c_double(g3.origin[1]),
+                                    C.c_double(g3.origin[2]), C.c_double(g3.spacing), C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(1))
+        assert occ3[z, y, x] == e
+    assert 0 < occ3.sum() < occ3.size
     m.close(); m2.close()
 
 
