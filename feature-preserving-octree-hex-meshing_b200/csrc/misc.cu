@@ -619,7 +619,8 @@ int fpohm_voxel_occupancy(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double g
 	FPOHM_LAUNCH_CHECK(ctx);
 	if ((dims[0] & 15) == 0) {
 		const int64_t items = (int64_t)(dims[0] / 16) * ((dims[1] + 3) / 4) * ((dims[2] + 1) / 2);
-		occupancy_expand4_kernel<<<grid_for(ctx, items, 256, 16), 256, 0, s>>>(og, bits.p, d.p);
+		static const int ex_ctas = getenv("FPOHM_OCC_CTAS") ? atoi(getenv("FPOHM_OCC_CTAS")) : 256;     // CTAs per SM in the grid (1024^3: one item per thread).  16 / 32 / 64 / 128 / 256: 0.367 / 0.352 / 0.347 / 0.343 / 0.334 ms; the bare store pattern goes 6.5 -> 7.1 TB/s from 16 to 64 (scripts/micro/write_patterns.cu, rows16x8)
+		occupancy_expand4_kernel<<<grid_for(ctx, items, 256, ex_ctas), 256, 0, s>>>(og, bits.p, d.p);
 	} else {
 		occupancy_expand_kernel<<<(int)std::min<int64_t>((int64_t)((dims[1] + 3) / 4) * ((dims[2] + 1) / 2), (int64_t)ctx->sm_count * 32), 256, 0, s>>>(og, bits.p, d.p);
 	}

@@ -350,7 +350,7 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 	}
 }
 
-#define FILL_CH_DEFAULT 4      // chunks of 32 layers per thread: amortises the summary loads over 64 stores
+#define FILL_CH_DEFAULT 2      // chunks of 32 layers per thread (swept 1 / 2 / 4 with 32 .. 256 CTAs per SM in the grid: 2 and 256)
 template <int FILL_CH>
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, const uint32_t *__restrict__ sum, uint8_t *__restrict__ out,
@@ -476,33 +476,35 @@ struct HitScratch {
 	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> ctl /* HIT_CTL_WORDS control words, then one count per column */, ev;
 	int32_t *n() const { return ctl.p + HIT_CTL_WORDS; }
 };
+struct HitPtrs {        // the same buffers as raw pointers (the VoxelGrid pass carves them out of one allocation)
+	double *z; int8_t *s; int32_t *ctl /* zeroed: HIT_CTL_WORDS control words, then one count per column */, *ev;
+	int4 *big_rect; int32_t *big_f; int64_t *big_off;      // nF entries each; touched only where a facet covers more than RECT_INLINE columns
+};
 
-// voxel_events: store packed (k0, sign) events for the VoxelGrid fill instead of (z, sign) pairs
-void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s, bool voxel_events = false,
-                     double oz = 0, int nz = 0)
-{
-	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
-	FPOHM_REQUIRE(nF < (1ll << (64 - BIG_PAIR_BITS)), FPOHM_ERANGE, "ray parity: %lld facets (the limit is 2^28)", (long long)nF);
-	if (voxel_events) h.ev.alloc(ncol * g.cap, s); else { h.z.alloc(ncol * g.cap, s); h.s.alloc(ncol * g.cap, s); }
-	h.ctl.alloc(HIT_CTL_WORDS + ncol, s);
-	h.ctl.zero();                                      // counts and control words in one memset
-	DevBuf<int4> big_rect(nF, s);                     // touched only where a facet covers more than RECT_INLINE columns
-	DevBuf<int32_t> big_f(nF, s);
-	DevBuf<int64_t> big_off(nF, s);
-	facet_rect_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(g, mesh->tri.p, nF, big_rect.p, big_f.p, big_off.p, h.ctl.p, h.z.p, h.s.p, h.n(),
-		voxel_events ? h.ev.p : nullptr, oz, nz);
+void launch_column_hits(fpohm_ctx *ctx, const fpohm_mesh *mesh, const ColumnGrid &g, const HitPtrs &h, cudaStream_t s, double oz, int nz) {
+	const int64_t nF = mesh->nF;
+	facet_rect_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(g, mesh->tri.p, nF, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 	// on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
-	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, big_rect.p, big_f.p, big_off.p, h.ctl.p, h.z.p, h.s.p, h.n(),
-		voxel_events ? h.ev.p : nullptr, oz, nz);
+	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 }
 
-// 0 if every list fitted, else the capacity the pass has to be repeated with (FPOHM_ERANGE beyond HIT_CAP_MAX)
-int overflow_retry_cap(DevBuf<int32_t> &ctl_dev /* HIT_CTL_WORDS control words first */, cudaStream_t s, const char *who) {
-	int32_t ctl[HIT_CTL_WORDS] = {0};
-	ctl_dev.download(ctl, HIT_CTL_WORDS);
-	FPOHM_CUDA(cudaStreamSynchronize(s));
+// (z, sign) hit lists of all columns (DexelGrid)
+void run_column_hits(fpohm_ctx *ctx, fpohm_mesh *mesh, const ColumnGrid &g, HitScratch &h, cudaStream_t s) {
+	const int64_t ncol = (int64_t)g.nx * g.ny, nF = mesh->nF;
+	FPOHM_REQUIRE(nF < (1ll << (64 - BIG_PAIR_BITS)), FPOHM_ERANGE, "ray parity: %lld facets (the limit is 2^28)", (long long)nF);
+	h.z.alloc(ncol * g.cap, s); h.s.alloc(ncol * g.cap, s);
+	h.ctl.alloc(HIT_CTL_WORDS + ncol, s);
+	h.ctl.zero();                                      // counts and control words in one memset
+	DevBuf<int4> big_rect(nF, s);
+	DevBuf<int32_t> big_f(nF, s);
+	DevBuf<int64_t> big_off(nF, s);
+	launch_column_hits(ctx, mesh, g, HitPtrs{h.z.p, h.s.p, h.ctl.p, nullptr, big_rect.p, big_f.p, big_off.p}, s, 0, 0);
+}
+
+// control words of a pass -> 0 if every list fitted, else the capacity the pass has to be repeated with (FPOHM_ERANGE beyond HIT_CAP_MAX)
+int retry_cap_from(const int32_t *ctl, const char *who) {
 	unsigned long long big_pairs; memcpy(&big_pairs, ctl + 4, 8);
 	FPOHM_REQUIRE((big_pairs >> BIG_PAIR_BITS) == 0, FPOHM_ERANGE, "%s: %llu (facet, column) pairs (the limit is 2^%d)", who, big_pairs, BIG_PAIR_BITS);
 	const int32_t ov = ctl[0];
@@ -510,6 +512,14 @@ int overflow_retry_cap(DevBuf<int32_t> &ctl_dev /* HIT_CTL_WORDS control words f
 	const int cap = next_hit_cap(ov);
 	FPOHM_REQUIRE(cap > 0, FPOHM_ERANGE, "%s: %d ray/facet hits in one column (the limit is %d)", who, ov, HIT_CAP_MAX);
 	return cap;
+}
+
+// 0 if every list fitted, else the capacity the pass has to be repeated with (FPOHM_ERANGE beyond HIT_CAP_MAX)
+int overflow_retry_cap(DevBuf<int32_t> &ctl_dev /* HIT_CTL_WORDS control words first */, cudaStream_t s, const char *who) {
+	int32_t ctl[HIT_CTL_WORDS] = {0};
+	ctl_dev.download(ctl, HIT_CTL_WORDS);
+	FPOHM_CUDA(cudaStreamSynchronize(s));
+	return retry_cap_from(ctl, who);
 }
 
 void check_dims(const int32_t *dims, int nd, const char *who) {
@@ -547,34 +557,58 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	              "fpohm_voxel_sign_slab_dev: slab [%d,%d) must be non-empty, inside [0,%d) and aligned to %d layers", z_begin, z_end, dims[2], FILL_Z);
 	DeviceGuard g(ctx->device);
 	cudaStream_t s = (cudaStream_t)stream;
-	for (int cap = HIT_CAP;;) {      // optimistic pass; repeated with more room only if a column overflowed (read-back at the end)
-	HitScratch h;
+	const int64_t nF = mesh->nF;
+	FPOHM_REQUIRE(nF < (1ll << (64 - BIG_PAIR_BITS)), FPOHM_ERANGE, "fpohm_voxel_sign: %lld facets (the limit is 2^28)", (long long)nF);
+	if (!ctx->pinned_words) {
+		FPOHM_CUDA(cudaHostAlloc((void **)&ctx->pinned_words, 16 * sizeof(int32_t), cudaHostAllocDefault));
+		FPOHM_CUDA(cudaEventCreateWithFlags(&ctx->early_ev0, cudaEventDisableTiming));
+		FPOHM_CUDA(cudaEventCreateWithFlags(&ctx->early_ev1, cudaEventDisableTiming));
+	}
+	for (int cap = HIT_CAP;;) {      // optimistic pass; repeated with more room only if a column overflowed
 	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1], cap};
-	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
-	run_column_hits(ctx, const_cast<fpohm_mesh *>(mesh), cg, h, s, true, grid_origin[2], dims[2]);
 	const int gz = (dims[2] + FILL_Z - 1) / FILL_Z, n_words = (gz + 31) / 32;
 	const int64_t ncol = (int64_t)dims[0] * dims[1];
-	DevBuf<uint32_t> summary(2 * n_words * ncol, s), dmask((int64_t)gz * ncol, s);      // dmask is only written / read where a chunk is dirty
+	// ONE allocation for the pass (seven stream-ordered allocations cost ~20 us of host time in front of the first kernel)
+	auto up = [](int64_t b) { return (b + 255) & ~(int64_t)255; };
+	const int64_t b_ev = up(4 * ncol * cap), b_ctl = up(4 * (HIT_CTL_WORDS + ncol)), b_rect = up(16 * nF), b_f = up(4 * nF), b_off = up(8 * nF);
+	const int64_t b_sum = up(4 * 2 * (int64_t)n_words * ncol), b_dm = up(4 * (int64_t)gz * ncol);      // dmask is only written / read where a chunk is dirty
+	DevBuf<uint8_t> slab(b_ev + b_ctl + b_rect + b_f + b_off + b_sum + b_dm, s);
+	uint8_t *q = slab.p;
+	HitPtrs h{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	h.ev = (int32_t *)q; q += b_ev; h.ctl = (int32_t *)q; q += b_ctl; h.big_rect = (int4 *)q; q += b_rect; h.big_f = (int32_t *)q; q += b_f; h.big_off = (int64_t *)q; q += b_off;
+	uint32_t *summary = (uint32_t *)q; q += b_sum;
+	uint32_t *dmask = (uint32_t *)q;
+	FPOHM_CUDA(cudaMemsetAsync(h.ctl, 0, 4 * (size_t)(HIT_CTL_WORDS + ncol), s));      // counts and control words in one memset
+	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
+	launch_column_hits(ctx, mesh, cg, h, s, grid_origin[2], dims[2]);
+	// the control words are final once the hits are in: they travel to pinned memory on a copy stream while summary and fill run,
+	// so the call returns (stream-ordered result, like every _dev entry point) without waiting for the fill
+	FPOHM_CUDA(cudaEventRecord(ctx->early_ev0, s));
+	FPOHM_CUDA(cudaStreamWaitEvent(ctx->aux[1], ctx->early_ev0, 0));
+	FPOHM_CUDA(cudaMemcpyAsync(ctx->pinned_words, h.ctl, HIT_CTL_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->aux[1]));
+	FPOHM_CUDA(cudaEventRecord(ctx->early_ev1, ctx->aux[1]));
+	int32_t *h_n = h.ctl + HIT_CTL_WORDS;
 	switch (cap) {
-	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
-	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
-	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
-	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev.p, h.n(), summary.p, dmask.p); break;
+	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
+	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
+	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
+	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
 	static const int fill_ch = getenv("FPOHM_FILL_CH") ? atoi(getenv("FPOHM_FILL_CH")) : FILL_CH_DEFAULT;
-	static const int fill_ctas = getenv("FPOHM_FILL_CTAS") ? atoi(getenv("FPOHM_FILL_CTAS")) : 32;
+	static const int fill_ctas = getenv("FPOHM_FILL_CTAS") ? atoi(getenv("FPOHM_FILL_CTAS")) : 256;
 	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + fill_ch - 1) / fill_ch);
 	const int fgrid = grid_for(ctx, nthreads, 256, fill_ctas);
 	switch (fill_ch) {
-	case 1: voxel_fill_kernel<1><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
-	case 2: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
-	case 8: voxel_fill_kernel<8><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
-	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask.p, summary.p, out_dev, zc0, zc1); break;
+	case 1: voxel_fill_kernel<1><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 2: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 8: voxel_fill_kernel<8><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
-	const int retry = overflow_retry_cap(h.ctl, s, "fpohm_voxel_sign");
+	FPOHM_CUDA(cudaEventSynchronize(ctx->early_ev1));
+	const int retry = retry_cap_from(ctx->pinned_words, "fpohm_voxel_sign");
 	if (!retry) break;
 	cap = retry;
 	}
