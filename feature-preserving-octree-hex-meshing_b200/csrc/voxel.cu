@@ -124,8 +124,16 @@ __device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
 // column's fixed-capacity list with one atomicAdd.  Work is proportional to the number of (facet, column) pairs the
 // reference tests, instead of one tree descent per column (first version: 6.9 of 7.1 ms at 1024^2 columns, 2 M facets).
 // first layer index k in [0, nz] with  hit_z < (k + 0.5) * spacing + oz   (exactly the comparison of voxelization.h:259-261)
+// The three index searches below decide with the reference's own floating-point expression.  t = (value - origin) / spacing - 0.5
+// is the same quantity in real numbers; unless t lies within INDEX_MARGIN of an integer (or is huge) the rounding of either
+// expression (a few ulps of its operands, i.e. < 1e-6 cells for |t| < 1e9) cannot change the outcome, and the answer follows from
+// floor(t) alone.  Only the near-integer cases run the exact comparison loops (ncu: the loops were 21 % of facet_rect_kernel).
+#define INDEX_MARGIN 1e-3
+__device__ __forceinline__ bool index_safe(double t, double ft) { return t - ft > INDEX_MARGIN && t - ft < 1.0 - INDEX_MARGIN && fabs(t) < 1e9; }
 __device__ __forceinline__ int first_layer_above(double z, double oz, double spacing, int nz) {
-	int k = (int)floor((z - oz) * __drcp_rn(spacing) - 0.5);   // guess only: the two loops below decide with the exact expression
+	const double t = (z - oz) * __drcp_rn(spacing) - 0.5, ft = floor(t);
+	if (index_safe(t, ft)) return max(0, min(nz, (int)ft + 1));        // smallest k with t < k
+	int k = (int)fmax(-1.0, fmin(ft, 2147483000.0));                   // guess only: the two loops below decide with the exact expression
 	if (k < 0) k = 0;
 	if (k > nz) k = nz;
 	while (k > 0 && z < ((k - 1) + 0.5) * spacing + oz) --k;
@@ -135,7 +143,9 @@ __device__ __forceinline__ int first_layer_above(double z, double oz, double spa
 
 __device__ __forceinline__ int first_center_ge(double lo, double o, double sp, int n) {
 	// smallest index i in [0, n] with (i + 0.5) * sp + o >= lo
-	int i = (int)floor((lo - o) * __drcp_rn(sp) - 0.5);          // guess only
+	const double t = (lo - o) * __drcp_rn(sp) - 0.5, ft = floor(t);
+	if (index_safe(t, ft)) return max(0, min(n, (int)ft + 1));         // smallest i with i >= t
+	int i = (int)fmax(-1.0, fmin(ft, 2147483000.0));                   // guess only
 	if (i < 0) i = 0;
 	if (i > n) i = n;
 	while (i > 0 && ((i - 1) + 0.5) * sp + o >= lo) --i;
@@ -144,7 +154,9 @@ __device__ __forceinline__ int first_center_ge(double lo, double o, double sp, i
 }
 __device__ __forceinline__ int last_center_le(double hi, double o, double sp, int n) {
 	// largest index i in [-1, n-1] with (i + 0.5) * sp + o <= hi
-	int i = (int)floor((hi - o) * __drcp_rn(sp) - 0.5);          // guess only
+	const double t = (hi - o) * __drcp_rn(sp) - 0.5, ft = floor(t);
+	if (index_safe(t, ft)) return max(-1, min(n - 1, (int)ft));        // largest i with i <= t
+	int i = (int)fmax(-2.0, fmin(ft, 2147483000.0));                   // guess only
 	if (i < -1) i = -1;
 	if (i > n - 1) i = n - 1;
 	while (i < n - 1 && ((i + 1) + 0.5) * sp + o <= hi) ++i;
@@ -296,6 +308,44 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b) {          // bits [
 // A dirty chunk's 32 layer bits are worked out here as well, once, and stored at dmask[chunk * ncol + col] (coalesced over
 // neighbouring columns): the fill then reads 4 bytes per dirty chunk instead of re-walking the column's 128-byte event list
 // (ncu: 0.24 GB of reads and a third of the fill's instructions at 1024^3 before).
+// Event driven (round 2; the first version walked all chunks of every column: 1 217 instructions per column, 78 us at 1024^2
+// columns).  Events in ascending k; s = sum of the signs so far.  The state ENTERING chunk b is the state after every event with
+// k <= 32 b, so a stretch with s < 0 between events at k_prev and k sets the inside bits [ceil(k_prev / 32), ceil(k / 32)); an
+// event strictly inside a chunk (k % 32 != 0) makes that chunk dirty and its 32 layer bits are accumulated while the events of
+// the chunk go by.  `get(i)` = i-th event in ascending k.
+template <class Get>
+__device__ __forceinline__ void summarize_column(Get get, int n, int64_t col, int64_t ncol, int nz, int n_words, uint32_t *__restrict__ sum,
+                                                 uint32_t *__restrict__ dmask)
+{
+	const int n_chunks = (nz + FILL_Z - 1) / FILL_Z;
+	for (int w = 0; w < n_words; ++w) {
+		const int c0 = 32 * w, c1 = min(c0 + 32, n_chunks);           // chunks of this summary word
+		uint32_t inside = 0, dirty = 0, mask = 0;
+		int s = 0, from = 0 /* ceil(k_prev / 32) */, cur = -1 /* open dirty chunk */, t = 0, prev = 0;
+		for (int i = 0; i <= n; ++i) {
+			const int32_t ei = i < n ? get(i) : 0;
+			const int k = i < n ? (ei >> 2) : nz + FILL_Z * 32;          // sentinel: closes the last stretch
+			const int to = min((k + FILL_Z - 1) / FILL_Z, n_chunks);
+			if (s < 0) inside |= bit_range(max(from, c0) - c0, min(to, c1) - c0);
+			from = to;
+			if (i == n) break;
+			const int b = k / FILL_Z, r = k % FILL_Z;
+			if (r != 0 && b >= c0 && b < c1) {
+				if (b != cur) {
+					if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
+					cur = b; dirty |= 1u << (b - c0); mask = 0; t = s; prev = 0;
+				}
+				if (t < 0) mask |= bit_range(prev, r);
+				prev = r;
+				t = s + (ei & 3) - 1;
+			}
+			s += (ei & 3) - 1;
+		}
+		if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
+		sum[(int64_t)(2 * w) * ncol + col] = inside;
+		sum[(int64_t)(2 * w + 1) * ncol + col] = dirty;
+	}
+}
 template <int CAP>
 __global__ void __launch_bounds__(256)
 column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
@@ -308,6 +358,7 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 			for (int w = 0; w < 2 * n_words; ++w) sum[(int64_t)w * ncol + col] = 0u;
 			continue;
 		}
+		// (sorting networks in registers for n <= 4 / n <= 8 were measured: no gain, the kernel is bound by its divergent event loop)
 		int32_t e[CAP];
 		for (int i = 0; i < n; ++i) {                       // insertion sort by k0 (order among equal k0 is irrelevant)
 			const int32_t v = ev[(int64_t)i * ncol];
@@ -315,38 +366,7 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 			while (j >= 0 && (e[j] >> 2) > (v >> 2)) { e[j + 1] = e[j]; --j; }
 			e[j + 1] = v;
 		}
-		// Event driven (round 2; the first version walked all chunks of every column: 1 217 instructions per column, 78 us at
-		// 1024^2 columns).  Events in ascending k; s = sum of the signs so far.  The state ENTERING chunk b is the state after
-		// every event with k <= 32 b, so a stretch with s < 0 between events at k_prev and k sets the inside bits
-		// [ceil(k_prev / 32), ceil(k / 32)); an event strictly inside a chunk (k % 32 != 0) makes that chunk dirty and its
-		// 32 layer bits are accumulated while the events of the chunk go by.
-		const int n_chunks = (nz + FILL_Z - 1) / FILL_Z;
-		for (int w = 0; w < n_words; ++w) {
-			const int c0 = 32 * w, c1 = min(c0 + 32, n_chunks);           // chunks of this summary word
-			uint32_t inside = 0, dirty = 0, mask = 0;
-			int s = 0, from = 0 /* ceil(k_prev / 32) */, cur = -1 /* open dirty chunk */, t = 0, prev = 0;
-			for (int i = 0; i <= n; ++i) {
-				const int k = i < n ? (e[i] >> 2) : nz + FILL_Z * 32;       // sentinel: closes the last stretch
-				const int to = min((k + FILL_Z - 1) / FILL_Z, n_chunks);
-				if (s < 0) inside |= bit_range(max(from, c0) - c0, min(to, c1) - c0);
-				from = to;
-				if (i == n) break;
-				const int b = k / FILL_Z, r = k % FILL_Z;
-				if (r != 0 && b >= c0 && b < c1) {
-					if (b != cur) {
-						if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
-						cur = b; dirty |= 1u << (b - c0); mask = 0; t = s; prev = 0;
-					}
-					if (t < 0) mask |= bit_range(prev, r);
-					prev = r;
-					t = s + (e[i] & 3) - 1;
-				}
-				s += (e[i] & 3) - 1;
-			}
-			if (cur >= 0) { if (t < 0) mask |= bit_range(prev, FILL_Z); dmask[(int64_t)cur * ncol + col] = mask; }
-			sum[(int64_t)(2 * w) * ncol + col] = inside;
-			sum[(int64_t)(2 * w + 1) * ncol + col] = dirty;
-		}
+		summarize_column([&](int i) { return e[i]; }, n, col, ncol, nz, n_words, sum, dmask);
 	}
 }
 
@@ -598,13 +618,15 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
 	static const int fill_ch = getenv("FPOHM_FILL_CH") ? atoi(getenv("FPOHM_FILL_CH")) : FILL_CH_DEFAULT;
 	static const int fill_ctas = getenv("FPOHM_FILL_CTAS") ? atoi(getenv("FPOHM_FILL_CTAS")) : 256;
+	// (a 16-columns-per-thread variant with 16-byte stores was measured as well: the bare pattern is faster, 6.7 vs 5.9 TB/s, the fill
+	// is not — 182 us either way at 1024^3, profiles/r02_ncu_summary.md)
 	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + fill_ch - 1) / fill_ch);
 	const int fgrid = grid_for(ctx, nthreads, 256, fill_ctas);
 	switch (fill_ch) {
 	case 1: voxel_fill_kernel<1><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
-	case 2: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 4: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
 	case 8: voxel_fill_kernel<8><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
-	default: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	default: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	FPOHM_CUDA(cudaEventSynchronize(ctx->early_ev1));
