@@ -155,9 +155,15 @@ __global__ void lattice_hexes_kernel(int d0, int d1, int d2, uint32_t *__restric
 // (geo/basic/geometry.h:612-622).  Per axis the overlap condition is monotone in the cell index, so every facet owns an
 // index BOX [x0,x1] x [y0,y1] x [z0,z1] whose limits are found with the reference's own expressions; the grid is zeroed
 // once and each facet stamps its box.  Work ~ number of (facet, cell) overlaps instead of one tree descent per voxel.
+// As in voxel.cu: t = (value - origin) / spacing is the same quantity in real numbers; unless t lies within 1e-3 of an integer (or is
+// huge) the rounding of the reference's expression cannot change the outcome and floor(t) decides; only the near-integer cases run
+// the exact comparison loops.
+__device__ __forceinline__ bool occ_index_safe(double t, double ft) { return t - ft > 1e-3 && t - ft < 1.0 - 1e-3 && fabs(t) < 1e9; }
 __device__ __forceinline__ int first_cell_max_ge(double lo, double o, double sp, int n) {
 	// smallest i in [0, n] with (o + sp*i) + sp*1 >= lo      (cell.max < tri.min fails)
-	int i = (int)floor((lo - o) * __drcp_rn(sp) - 1.0);
+	const double t = (lo - o) * __drcp_rn(sp), ft = floor(t);
+	if (occ_index_safe(t, ft)) return max(0, min(n, (int)ft));          // smallest i with i + 1 >= t
+	int i = (int)fmax(-2.0, fmin(ft - 1.0, 2147483000.0));              // guess only
 	if (i < 0) i = 0;
 	if (i > n) i = n;
 	while (i > 0 && (o + sp * (i - 1)) + sp * 1 >= lo) --i;
@@ -166,7 +172,9 @@ __device__ __forceinline__ int first_cell_max_ge(double lo, double o, double sp,
 }
 __device__ __forceinline__ int last_cell_min_le(double hi, double o, double sp, int n) {
 	// largest i in [-1, n-1] with o + sp*i <= hi             (cell.min > tri.max fails)
-	int i = (int)floor((hi - o) * __drcp_rn(sp));
+	const double t = (hi - o) * __drcp_rn(sp), ft = floor(t);
+	if (occ_index_safe(t, ft)) return max(-1, min(n - 1, (int)ft));     // largest i with i <= t
+	int i = (int)fmax(-2.0, fmin(ft, 2147483000.0));                    // guess only
 	if (i < -1) i = -1;
 	if (i > n - 1) i = n - 1;
 	while (i < n - 1 && o + sp * (i + 1) <= hi) ++i;
