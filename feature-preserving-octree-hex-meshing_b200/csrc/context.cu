@@ -210,8 +210,6 @@ void fpohm_ctx_destroy(fpohm_ctx *ctx) {
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
 	if (ctx->pinned_words) cudaFreeHost(ctx->pinned_words);
-	if (ctx->early_ev0) cudaEventDestroy(ctx->early_ev0);
-	if (ctx->early_ev1) cudaEventDestroy(ctx->early_ev1);
 	if (ctx->arena) arena_destroy(ctx->arena);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	cudaGetLastError();

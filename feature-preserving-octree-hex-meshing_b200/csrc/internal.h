@@ -121,8 +121,8 @@ struct fpohm_ctx {
 	cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // upload / download / extra compute lanes of the host-pointer entry points
 	std::vector<cudaEvent_t> ev_pool;                     // per-chunk ordering events of those pipelines (grown on demand)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
-	int32_t *pinned_words = nullptr;              // 16 pinned host words: early read-back of control words (voxel.cu), created on first use
-	cudaEvent_t early_ev0 = nullptr, early_ev1 = nullptr;
+	int32_t *pinned_words = nullptr;              // 16 pinned host words a kernel posts control words to (voxel.cu), created on first use
+	int32_t post_seq = 0;                         // sequence number of the last post
 	double last_ms = 0;
 	// CUDA-event ring around the dominant query kernel (packet walk) of the last resident/host query launches
 	static constexpr int QRING = 32;

@@ -105,6 +105,13 @@ __device__ __forceinline__ int gather_hits(const double *__restrict__ box, int64
 	return n;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel that opens with pdl_release() lets the NEXT kernel of the stream be scheduled as
+// soon as every CTA of this one has started; the next kernel's CTAs then sit in pdl_wait() until this grid has completed and its
+// writes are visible.  Launch latency and CTA ramp-up of the VoxelGrid pass's four kernels hide behind each other's tails.
+// Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // std::sort of pair<double,int>: ascending z, then ascending sign
 __device__ __forceinline__ void sort_hits(double *hz, int8_t *hs, int n) {
 	for (int i = 1; i < n; ++i) {
@@ -195,6 +202,7 @@ facet_rect_kernel(ColumnGrid g, const double *__restrict__ tri, int64_t nF, int4
                   double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
                   int32_t *__restrict__ hit_ev, double oz, int nz)
 {
+	pdl_release();
 	const int lane = threadIdx.x & 31;
 	int32_t *overflow_flag = ctl;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -270,6 +278,8 @@ pair_hits_kernel(ColumnGrid g, const double *__restrict__ tri, const int4 *__res
                  double *__restrict__ hit_z, int8_t *__restrict__ hit_s, int32_t *__restrict__ hit_n,
                  int32_t *__restrict__ hit_ev, double oz, int nz)
 {
+	pdl_release();
+	pdl_wait();
 	// counts are read on the device: no host round trip in front of this launch
 	const unsigned long long packed = *reinterpret_cast<const unsigned long long *>(ctl + 2);
 	const int64_t n_big = (int64_t)(packed >> BIG_PAIR_BITS), n_pairs = (int64_t)(packed & ((1ull << BIG_PAIR_BITS) - 1ull));
@@ -349,8 +359,17 @@ __device__ __forceinline__ void summarize_column(Get get, int n, int64_t col, in
 template <int CAP>
 __global__ void __launch_bounds__(256)
 column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restrict__ hit_ev, const int32_t *__restrict__ hit_n,
-                      uint32_t *__restrict__ sum, uint32_t *__restrict__ dmask)
+                      uint32_t *__restrict__ sum, uint32_t *__restrict__ dmask, const int32_t *__restrict__ ctl, volatile int32_t *host_post, int32_t seq)
 {
+	pdl_release();
+	pdl_wait();
+	// The control words of the hit stage are final now: post them to the host (pinned, mapped) so that the caller learns whether
+	// a list overflowed while summary and fill are still running — no event, no copy, nothing between the kernels of the pass.
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (int j = 0; j < HIT_CTL_WORDS; ++j) host_post[j] = ctl[j];
+		__threadfence_system();
+		host_post[HIT_CTL_WORDS] = seq;
+	}
 	for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < ncol; col += (int64_t)gridDim.x * blockDim.x) {
 		const int n = min(hit_n[col], CAP);
 		const int32_t *ev = hit_ev + col;                    // event i of this column at ev[i * ncol]
@@ -376,6 +395,7 @@ __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, const uint32_t *__restrict__ sum, uint8_t *__restrict__ out,
                   int zc_begin, int zc_end)
 {
+	pdl_wait();
 	// layers [zc_begin * 32, min(zc_end * 32, nz)) are written, the first of them at `out` (z-slab sharding)
 	const int gx = (nx + 3) / 4, gzc = zc_end, gz = (zc_end - zc_begin + FILL_CH - 1) / FILL_CH;
 	const int64_t nthreads = (int64_t)gx * ny * gz;
@@ -492,6 +512,20 @@ cell_sign_kernel(const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ c
 	}
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_release / pdl_wait)
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+	static const bool off = getenv("FPOHM_NO_PDL") != nullptr;      // A/B switch
+	if (off) { kernel<<<grid, block, 0, s>>>(args...); return; }
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	FPOHM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 struct HitScratch {
 	DevBuf<double> z; DevBuf<int8_t> s; DevBuf<int32_t> ctl /* HIT_CTL_WORDS control words, then one count per column */, ev;
 	int32_t *n() const { return ctl.p + HIT_CTL_WORDS; }
@@ -506,7 +540,7 @@ void launch_column_hits(fpohm_ctx *ctx, const fpohm_mesh *mesh, const ColumnGrid
 	facet_rect_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(g, mesh->tri.p, nF, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 	// on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
-	pair_hits_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(g, mesh->tri.p, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
+	launch_pdl(pair_hits_kernel, ctx->sm_count * 8, 256, s, g, mesh->tri.p, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 }
 
@@ -580,9 +614,8 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	const int64_t nF = mesh->nF;
 	FPOHM_REQUIRE(nF < (1ll << (64 - BIG_PAIR_BITS)), FPOHM_ERANGE, "fpohm_voxel_sign: %lld facets (the limit is 2^28)", (long long)nF);
 	if (!ctx->pinned_words) {
-		FPOHM_CUDA(cudaHostAlloc((void **)&ctx->pinned_words, 16 * sizeof(int32_t), cudaHostAllocDefault));
-		FPOHM_CUDA(cudaEventCreateWithFlags(&ctx->early_ev0, cudaEventDisableTiming));
-		FPOHM_CUDA(cudaEventCreateWithFlags(&ctx->early_ev1, cudaEventDisableTiming));
+		FPOHM_CUDA(cudaHostAlloc((void **)&ctx->pinned_words, 16 * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+		memset(ctx->pinned_words, 0, 16 * sizeof(int32_t));
 	}
 	for (int cap = HIT_CAP;;) {      // optimistic pass; repeated with more room only if a column overflowed
 	const ColumnGrid cg{grid_origin[0], grid_origin[1], spacing, dims[0], dims[1], cap};
@@ -601,18 +634,14 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	FPOHM_CUDA(cudaMemsetAsync(h.ctl, 0, 4 * (size_t)(HIT_CTL_WORDS + ncol), s));      // counts and control words in one memset
 	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
 	launch_column_hits(ctx, mesh, cg, h, s, grid_origin[2], dims[2]);
-	// the control words are final once the hits are in: they travel to pinned memory on a copy stream while summary and fill run,
-	// so the call returns (stream-ordered result, like every _dev entry point) without waiting for the fill
-	FPOHM_CUDA(cudaEventRecord(ctx->early_ev0, s));
-	FPOHM_CUDA(cudaStreamWaitEvent(ctx->aux[1], ctx->early_ev0, 0));
-	FPOHM_CUDA(cudaMemcpyAsync(ctx->pinned_words, h.ctl, HIT_CTL_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->aux[1]));
-	FPOHM_CUDA(cudaEventRecord(ctx->early_ev1, ctx->aux[1]));
 	int32_t *h_n = h.ctl + HIT_CTL_WORDS;
+	const int32_t seq = ++ctx->post_seq;
+	volatile int32_t *post = ctx->pinned_words;
 	switch (cap) {
-	case 32: column_summary_kernel<32><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
-	case 128: column_summary_kernel<128><<<grid_for(ctx, ncol, 256, 8), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
-	case 512: column_summary_kernel<512><<<grid_for(ctx, ncol, 256, 4), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
-	default: column_summary_kernel<2048><<<grid_for(ctx, ncol, 256, 2), 256, 0, s>>>(ncol, dims[2], n_words, h.ev, h_n, summary, dmask); break;
+	case 32: launch_pdl(column_summary_kernel<32>, grid_for(ctx, ncol, 256, 8), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
+	case 128: launch_pdl(column_summary_kernel<128>, grid_for(ctx, ncol, 256, 8), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
+	case 512: launch_pdl(column_summary_kernel<512>, grid_for(ctx, ncol, 256, 4), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
+	default: launch_pdl(column_summary_kernel<2048>, grid_for(ctx, ncol, 256, 2), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
 	const int zc0 = z_begin / FILL_Z, zc1 = (z_end + FILL_Z - 1) / FILL_Z;
@@ -623,14 +652,19 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	const int64_t nthreads = (int64_t)((dims[0] + 3) / 4) * dims[1] * ((zc1 - zc0 + fill_ch - 1) / fill_ch);
 	const int fgrid = grid_for(ctx, nthreads, 256, fill_ctas);
 	switch (fill_ch) {
-	case 1: voxel_fill_kernel<1><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
-	case 4: voxel_fill_kernel<4><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
-	case 8: voxel_fill_kernel<8><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
-	default: voxel_fill_kernel<2><<<fgrid, 256, 0, s>>>(dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 1: launch_pdl(voxel_fill_kernel<1>, fgrid, 256, s, dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 4: launch_pdl(voxel_fill_kernel<4>, fgrid, 256, s, dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	case 8: launch_pdl(voxel_fill_kernel<8>, fgrid, 256, s, dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
+	default: launch_pdl(voxel_fill_kernel<2>, fgrid, 256, s, dims[0], dims[1], z_end, dmask, summary, out_dev, zc0, zc1); break;
 	}
 	FPOHM_LAUNCH_CHECK(ctx);
-	FPOHM_CUDA(cudaEventSynchronize(ctx->early_ev1));
-	const int retry = retry_cap_from(ctx->pinned_words, "fpohm_voxel_sign");
+	// wait for the post of THIS pass (the call returns stream-ordered, like every _dev entry point, without waiting for the fill)
+	for (int64_t spin = 1; post[HIT_CTL_WORDS] != seq; ++spin) {
+		if ((spin & 4095) == 0) { const cudaError_t q = cudaStreamQuery(s); if (q != cudaSuccess && q != cudaErrorNotReady) FPOHM_CUDA(q); if (q == cudaSuccess && post[HIT_CTL_WORDS] != seq) FPOHM_REQUIRE(false, FPOHM_ESTATE, "fpohm_voxel_sign: the pass finished without posting its control words"); }
+	}
+	int32_t h_ctl[HIT_CTL_WORDS];
+	for (int j = 0; j < HIT_CTL_WORDS; ++j) h_ctl[j] = post[j];
+	const int retry = retry_cap_from(h_ctl, "fpohm_voxel_sign");
 	if (!retry) break;
 	cap = retry;
 	}
