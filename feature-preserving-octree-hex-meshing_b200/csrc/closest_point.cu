@@ -994,6 +994,7 @@ cp_pair_kernel(const WNode *__restrict__ wnodes, const float4 *__restrict__ trif
 			// spills, instruction-cache misses); the loops are arranged so that one site serves every trigger.
 			for (;;) {
 				// ---- phase A: box-parallel expansion of the upper tree against the packet box and the largest threshold ----
+				__syncwarp();                                      // lane 0's pushes in phase B1 are ordered against the reads below (racecheck)
 				while (top > 0 && ncand <= PK_CAND - 32) {
 					const int j = lane >> 3, c = lane & 7;
 					const int take = top < 4 ? top : 4;
