@@ -389,7 +389,7 @@ column_summary_kernel(int64_t ncol, int nz, int n_words, const int32_t *__restri
 	}
 }
 
-#define FILL_CH_DEFAULT 2      // chunks of 32 layers per thread (swept 1 / 2 / 4 with 32 .. 256 CTAs per SM in the grid: 2 and 256)
+#define FILL_CH_DEFAULT 1      // chunks of 32 layers per thread (1 / 2 / 4 with the grid uncapped: 0.357 / 0.364 / 0.383 ms per pass)
 template <int FILL_CH>
 __global__ void __launch_bounds__(256)
 voxel_fill_kernel(int nx, int ny, int nz, const uint32_t *__restrict__ dmask, const uint32_t *__restrict__ sum, uint8_t *__restrict__ out,
@@ -537,7 +537,8 @@ struct HitPtrs {        // the same buffers as raw pointers (the VoxelGrid pass 
 
 void launch_column_hits(fpohm_ctx *ctx, const fpohm_mesh *mesh, const ColumnGrid &g, const HitPtrs &h, cudaStream_t s, double oz, int nz) {
 	const int64_t nF = mesh->nF;
-	facet_rect_kernel<<<grid_for(ctx, nF, 256), 256, 0, s>>>(g, mesh->tri.p, nF, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
+	static const int rect_ctas = getenv("FPOHM_RECT_CTAS") ? atoi(getenv("FPOHM_RECT_CTAS")) : 8;      // CTAs per SM in the grid (debug sweep)
+	facet_rect_kernel<<<grid_for(ctx, nF, 256, rect_ctas), 256, 0, s>>>(g, mesh->tri.p, nF, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
 	FPOHM_LAUNCH_CHECK(ctx);
 	// on fine meshes (no facet over RECT_INLINE columns) the launch finds nothing to do
 	launch_pdl(pair_hits_kernel, ctx->sm_count * 8, 256, s, g, mesh->tri.p, h.big_rect, h.big_f, h.big_off, h.ctl, h.z, h.s, h.ctl + HIT_CTL_WORDS, h.ev, oz, nz);
@@ -635,11 +636,12 @@ int fpohm_voxel_sign_slab_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const doub
 	// hits and per-column summaries are global (every slab needs the parity of everything below it); only the fill is sliced
 	launch_column_hits(ctx, mesh, cg, h, s, grid_origin[2], dims[2]);
 	int32_t *h_n = h.ctl + HIT_CTL_WORDS;
+	static const int sum_ctas = getenv("FPOHM_SUM_CTAS") ? atoi(getenv("FPOHM_SUM_CTAS")) : 32;         // CTAs per SM in the grid: 4 / 8 / 16 / 32 / 64 -> 0.383 / 0.375 / 0.368 / 0.363 / 0.366 ms per pass
 	const int32_t seq = ++ctx->post_seq;
 	volatile int32_t *post = ctx->pinned_words;
 	switch (cap) {
-	case 32: launch_pdl(column_summary_kernel<32>, grid_for(ctx, ncol, 256, 8), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
-	case 128: launch_pdl(column_summary_kernel<128>, grid_for(ctx, ncol, 256, 8), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
+	case 32: launch_pdl(column_summary_kernel<32>, grid_for(ctx, ncol, 256, sum_ctas), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
+	case 128: launch_pdl(column_summary_kernel<128>, grid_for(ctx, ncol, 256, sum_ctas), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
 	case 512: launch_pdl(column_summary_kernel<512>, grid_for(ctx, ncol, 256, 4), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
 	default: launch_pdl(column_summary_kernel<2048>, grid_for(ctx, ncol, 256, 2), 256, s, ncol, dims[2], n_words, h.ev, h_n, summary, dmask, h.ctl, post, seq); break;
 	}

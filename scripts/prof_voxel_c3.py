@@ -18,3 +18,9 @@ for _ in range(n):
     e0.record(); fp.voxel_sign_dev(ctx, m, g, d.data_ptr(), 0); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print("voxel_sign 1024^3 ms:", [round(t, 3) for t in ts], "dims", g.dims.tolist(), "filled", int(d.sum().item()))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    fp.voxel_sign_dev(ctx, m, g, d.data_ptr(), 0)
+b.record(); torch.cuda.synchronize()
+print("10 calls back to back (the bench's way): %.4f ms per call" % (a.elapsed_time(b) / 10))
