@@ -1922,6 +1922,9 @@ pipeline:
 				for (int c = 0; c < 3; ++c) { v *= std::max(hi[c] - lo[c], 0.0); va *= std::max(all_hi[c] - all_lo[c], 0.0); }
 				if (va > 0 && v <= 0.3 * va) target = 1 << 20;
 			}
+			// a batch of only a few such chunks would barely overlap its transfers with its compute: at least four chunks, none under 2^19
+			// (the 1.78 M projection set: 6.98 ms in one piece, 5.5 ms in four)
+			if (np < 4 * target) target = std::max<int64_t>(1 << 19, (np + 3) / 4);
 		}
 		const int64_t k = (np + target - 1) / target;
 		chunk = (((np + k - 1) / k) + 31) & ~(int64_t)31;
