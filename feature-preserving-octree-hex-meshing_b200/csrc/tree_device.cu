@@ -18,8 +18,10 @@
 #include "mesh.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <math_constants.h>
 #include <algorithm>
+#include <map>
 #include <thread>
 
 using namespace fpohm;
@@ -151,6 +153,32 @@ __global__ void seg_keys_kernel(const Seg *__restrict__ segs, int nseg, const in
 		key[p] = ((unsigned long long)(unsigned)j << 32) | (unsigned)r;
 	}
 }
+// next level's segments, on the device (the shape is a function of nF alone; round 2's first version enumerated every level on the
+// host and uploaded it: ~50 MB of pageable copies and ~15 ms of host loops per 2 M facets, serial in front of everything else)
+__global__ void seg_fanout_kernel(const Seg *__restrict__ segs, int nseg, int32_t *__restrict__ fan) {
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nseg; j += gridDim.x * blockDim.x) fan[j] = segs[j].count > 1 ? 2 : 1;
+}
+__global__ void seg_split_kernel(const Seg *__restrict__ segs, int nseg, const int32_t *__restrict__ off, Seg *__restrict__ out,
+                                 int32_t *__restrict__ leaf_id_of_pos)
+{
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nseg; j += gridDim.x * blockDim.x) {
+		const Seg g = segs[j];
+		const int32_t o = off[j];
+		if (g.count > 1) {
+			const int32_t nl = (g.count + 1) / 2;       // igl sizes the sides (n + 1) / 2 and n / 2 (AABB.cpp:168)
+			out[o] = Seg{g.begin, nl, g.id + 1};
+			out[o + 1] = Seg{g.begin + nl, g.count - nl, g.id + 2 * nl};
+		} else {
+			// a leaf stays in place as a segment of one element (it keeps its position in the order); id < 0: already written
+			out[o] = Seg{g.begin, 1, g.id >= 0 ? -1 - g.id : g.id};
+			if (g.id >= 0) leaf_id_of_pos[g.begin] = g.id;
+		}
+	}
+}
+__global__ void seg_leaves_kernel(const Seg *__restrict__ segs, int nseg, int32_t *__restrict__ leaf_id_of_pos) {
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nseg; j += gridDim.x * blockDim.x)
+		if (segs[j].count == 1 && segs[j].id >= 0) leaf_id_of_pos[segs[j].begin] = segs[j].id;
+}
 __global__ void leaf_prim_kernel(const int32_t *__restrict__ leaf_id_of_pos, const int32_t *__restrict__ elem, int64_t nF, int32_t *__restrict__ prim) {
 	for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nF; p += (int64_t)gridDim.x * blockDim.x) prim[leaf_id_of_pos[p]] = elem[p];
 }
@@ -184,38 +212,23 @@ void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ti
 	ctx->launches += 3;
 	int32_t h_ties[3] = {0, 0, 0};
 	n_ties.download(h_ties, 3);
-	// ---- the tree's shape, level by level (host: depends on nF only) — overlaps the device sorts above ----
-	struct Level { std::vector<Seg> segs; };
-	std::vector<Level> levels;
-	std::vector<int32_t> leaf_id_of_pos((size_t)nF);
+	// ---- segments per level: counts only (the multiset of segment sizes of a level has two or three distinct values) ----
+	std::vector<int64_t> nseg_of;                 // segments of level L, finished leaves included
+	std::vector<char> splits_of;                  // does level L still hold a segment of more than one element
 	{
-		Level cur;
-		cur.segs.push_back({0, (int32_t)nF, 0});
+		std::map<int32_t, int64_t> cur;           // size -> how many
+		cur[(int32_t)nF] = 1;
 		for (;;) {
-			bool any = false;
-			Level next;
-			next.segs.reserve(2 * cur.segs.size());
-			for (const Seg &g : cur.segs) {
-				if (g.count > 1) {
-					const int32_t nl = (g.count + 1) / 2;
-					next.segs.push_back({g.begin, nl, g.id + 1});
-					next.segs.push_back({g.begin + nl, g.count - nl, g.id + 2 * nl});
-					any = true;
-				} else if (g.id >= 0) {
-					leaf_id_of_pos[(size_t)g.begin] = g.id;
-				}
+			int64_t n = 0; bool any = false;
+			std::map<int32_t, int64_t> next;
+			for (const auto &kv : cur) {
+				n += kv.second;
+				if (kv.first > 1) { any = true; next[(kv.first + 1) / 2] += kv.second; next[kv.first / 2] += kv.second; }
+				else next[1] += kv.second;
 			}
-			levels.push_back(std::move(cur));
+			nseg_of.push_back(n); splits_of.push_back(any ? 1 : 0);
 			if (!any) break;
-			// leaves finished at this level stay in place as segments of one element (they keep their position in the order)
-			Level merged;
-			merged.segs.reserve(next.segs.size() + 16);
-			size_t a = 0;
-			for (const Seg &g : levels.back().segs) {
-				if (g.count > 1) { merged.segs.push_back(next.segs[a]); merged.segs.push_back(next.segs[a + 1]); a += 2; }
-				else merged.segs.push_back({g.begin, 1, g.id >= 0 ? -1 - g.id : g.id});      // id < 0: already written, not a node of this level
-			}
-			cur = std::move(merged);
+			cur.swap(next);
 		}
 	}
 	FPOHM_CUDA(cudaStreamSynchronize(s));
@@ -242,42 +255,56 @@ void build_igl_tree_device(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s, int ti
 	DevBuf<double> &node_box = m->t_box;
 	FPOHM_CUDA(cudaMemcpyAsync(elem.p, idx.p, 4 * (size_t)nF, cudaMemcpyDeviceToDevice, s));      // 0, 1, 2, ...
 	FPOHM_CUDA(cudaMemsetAsync(prim.p, 0xff, 4 * nn, s));
-	size_t max_segs = 0;
-	for (auto &L : levels) max_segs = std::max(max_segs, L.segs.size());
-	DevBuf<Seg> dsegs((int64_t)max_segs, s);
-	DevBuf<unsigned long long> sbox(6 * (int64_t)max_segs, s), lkey(nF, s), lkey2(nF, s);
-	DevBuf<int8_t> axis((int64_t)max_segs, s);
-	size_t tb2 = 0;
+	int64_t max_segs = 0;
+	for (int64_t n : nseg_of) max_segs = std::max(max_segs, n);
+	FPOHM_REQUIRE(max_segs < (1ll << 31), FPOHM_ERANGE, "tree build: %lld segments", (long long)max_segs);
+	DevBuf<Seg> segs_a(max_segs, s), segs_b(max_segs, s);
+	DevBuf<int32_t> fan(max_segs, s), fan_off(max_segs, s);
+	DevBuf<unsigned long long> sbox(6 * max_segs, s), lkey(nF, s), lkey2(nF, s);
+	DevBuf<int8_t> axis(max_segs, s);
+	size_t tb2 = 0, tb3 = 0;
 	FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, lkey.p, lkey2.p, elem.p, elem2.p, (int)nF, 0, 64, s));
-	DevBuf<uint8_t> tmp2((int64_t)tb2, s);
+	FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb3, fan.p, fan_off.p, (int)max_segs, s));
+	DevBuf<uint8_t> tmp2((int64_t)std::max(tb2, tb3), s);
+	const Seg root_seg{0, (int32_t)nF, 0};
+	FPOHM_CUDA(cudaMemcpyAsync(segs_a.p, &root_seg, sizeof(Seg), cudaMemcpyHostToDevice, s));
+	FPOHM_CUDA(cudaStreamSynchronize(s));              // root_seg is a local
 	int32_t *e_in = elem.p, *e_out = elem2.p;
-	for (size_t L = 0; L < levels.size(); ++L) {
+	Seg *sg_in = segs_a.p, *sg_out = segs_b.p;
+	for (size_t L = 0; L < nseg_of.size(); ++L) {
 		// segments of this level: nodes (id >= 0) and earlier leaves (id < 0, skipped by the node kernels through count == 1 and id)
-		std::vector<Seg> &sg = levels[L].segs;
-		const int nseg = (int)sg.size();
-		FPOHM_CUDA(cudaMemcpyAsync(dsegs.p, sg.data(), sizeof(Seg) * (size_t)nseg, cudaMemcpyHostToDevice, s));
+		const int nseg = (int)nseg_of[L];
 		seg_box_init_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(nseg, sbox.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		seg_box_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(dsegs.p, nseg, e_in, tbox.p, nF, sbox.p);
+		seg_box_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(sg_in, nseg, e_in, tbox.p, nF, sbox.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		seg_axis_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(dsegs.p, nseg, sbox.p, node_box.p, axis.p);
+		seg_axis_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(sg_in, nseg, sbox.p, node_box.p, axis.p);
 		FPOHM_LAUNCH_CHECK(ctx);
-		bool splits = false;
-		for (const Seg &g : sg) if (g.count > 1) { splits = true; break; }
-		if (!splits) break;
-		seg_keys_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(dsegs.p, nseg, axis.p, e_in, nF, rank[0].p, rank[1].p, rank[2].p, lkey.p);
+		if (!splits_of[L]) {
+			seg_leaves_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(sg_in, nseg, d_leaf.p);
+			FPOHM_LAUNCH_CHECK(ctx);
+			break;
+		}
+		seg_keys_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(sg_in, nseg, axis.p, e_in, nF, rank[0].p, rank[1].p, rank[2].p, lkey.p);
 		FPOHM_LAUNCH_CHECK(ctx);
 		int sbits = 1;
 		while ((1ll << sbits) < nseg) ++sbits;
-		FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, lkey.p, lkey2.p, e_in, e_out, (int)nF, 0, 32 + sbits, s));
-		ctx->launches += 1;
+		size_t tbs = tb2;
+		FPOHM_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tbs, lkey.p, lkey2.p, e_in, e_out, (int)nF, 0, 32 + sbits, s));
 		std::swap(e_in, e_out);
-		FPOHM_CUDA(cudaStreamSynchronize(s));      // sg (host) is re-used by the async copy above only until here
+		// next level's segments
+		seg_fanout_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(sg_in, nseg, fan.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		size_t tbx = tb3;
+		FPOHM_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, tbx, fan.p, fan_off.p, nseg, s));
+		seg_split_kernel<<<grid_for(ctx, nseg, blk), blk, 0, s>>>(sg_in, nseg, fan_off.p, sg_out, d_leaf.p);
+		FPOHM_LAUNCH_CHECK(ctx);
+		ctx->launches += 2;
+		std::swap(sg_in, sg_out);
 	}
-	d_leaf.upload(leaf_id_of_pos.data(), nF);
 	leaf_prim_kernel<<<grid_for(ctx, nF, blk), blk, 0, s>>>(d_leaf.p, e_in, nF, prim.p);
 	FPOHM_LAUNCH_CHECK(ctx);
-	FPOHM_CUDA(cudaStreamSynchronize(s));      // leaf_id_of_pos is a local
+	FPOHM_CUDA(cudaStreamSynchronize(s));
 }
 
 } // namespace fpohm
