@@ -1421,10 +1421,11 @@ cp_search_kernel(const QNodeF *__restrict__ fnodes, int32_t root, const double *
 }
 
 // ---- K3 ---------------------------------------------------------------------------------------------------------
+// One WARP per query, 32 tree nodes per step: the form for LONG lists (at least one query per resident warp).
 __global__ void __launch_bounds__(128)
-cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
+cp_heavy_warp_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
                 const double *__restrict__ P, const int32_t *__restrict__ heavy, const int32_t *__restrict__ heavy_count,
-                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa)
+                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa, int min_count)
 {
 	__shared__ int32_t s_node[4][HV_STACK];
 	__shared__ unsigned long long s_key[4][HV_STACK];
@@ -1432,6 +1433,7 @@ cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__r
 	int32_t *stk = s_node[warp];
 	unsigned long long *stkk = s_key[warp];
 	const int n_heavy = *heavy_count;
+	if (n_heavy < min_count) return;                   // short lists: cp_heavy_kernel (one CTA per query)
 	const unsigned lt = (1u << lane) - 1;
 	for (int hq = blockIdx.x * 4 + warp; hq < n_heavy; hq += gridDim.x * 4) {
 		const int64_t i = heavy[hq];
@@ -1513,6 +1515,119 @@ cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__r
 			finalize_sign(sa, i, p, h.f, h.c, h.sqr_d, S);
 		}
 		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(128)
+cp_heavy_kernel(const QNode *__restrict__ nodes, int32_t root, const double *__restrict__ tri, const int32_t *__restrict__ prim_parent,
+                const double *__restrict__ P, const int32_t *__restrict__ heavy, const int32_t *__restrict__ heavy_count,
+                double *__restrict__ S, int32_t *__restrict__ I, double *__restrict__ C, SignArgs sa, int max_count)
+{
+	// One CTA (4 warps) per query, 128 tree nodes per step: the form for SHORT lists (fewer queries than resident warps).  (One WARP per query until late in round 2: a launch could not be shorter
+	// than its longest query, ~0.36 ms — 14 launches per host-pointer C4 step, two per rank and step under strong scaling.)  The
+	// winner is the minimum over (distance, igl rank) of every leaf within the shrinking bound, so the visiting order is free.
+	constexpr int CAP = 4 * HV_STACK;
+	__shared__ int32_t stk[CAP];
+	__shared__ unsigned long long stkk[CAP];
+	__shared__ double r_d[4];
+	__shared__ unsigned long long r_k[4];
+	__shared__ int32_t r_f[4];
+	__shared__ int s_cnt[4][2];
+	__shared__ int s_deep;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n_heavy = *heavy_count;
+	if (n_heavy >= max_count) return;                  // long lists: cp_heavy_warp_kernel
+	const unsigned lt = (1u << lane) - 1;
+	for (int hq = blockIdx.x; hq < n_heavy; hq += gridDim.x) {
+		const int64_t i = heavy[hq];
+		const V3 p = ld3(P + 3 * i);
+		double best = S[i];                               // exact distance of some facet (or +inf): a valid upper bound
+		unsigned long long bkey = ~0ull;
+		int32_t bfac = -1;
+		int top = 1;
+		if (tid == 0) { stk[0] = root; stkk[0] = 0ull; s_deep = 0; }
+		__syncthreads();
+		while (top > 0) {
+			int take = top < 128 ? top : 128;
+			if (top > CAP - 320) take = 1;                  // nearly full: pure depth-first, growth bounded by the tree depth
+			int32_t cl = 0, cr = 0;
+			unsigned long long kl = 0, kr = 0;
+			bool wl = false, wr = false;
+			const double lim = best + best * PK_EPS_TIE;
+			if (tid < take) {
+				const QNode *n = nodes + stk[top - 1 - tid];
+				const unsigned long long key = stkk[top - 1 - tid];
+				const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
+				const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
+				const int depth = n->depth;
+				if (depth > 61) s_deep = 1;                  // a rank does not fit 62 bits (benign race: every writer stores 1)
+				const unsigned long long bit = depth > 61 ? 0ull : 1ull << (61 - depth);
+				kl = left_first ? key : key | bit; kr = left_first ? key | bit : key;
+				wl = dl <= lim; wr = dr <= lim;
+				cl = n->left; cr = n->right;
+			}
+			// leaves: exact distance; candidate ordered by (distance, igl rank)
+			double d = CUDART_INF; unsigned long long dk = ~0ull; int32_t df = -1;
+			if (wl && cl < 0) { const double *t = tri + 9 * (int64_t)~cl; d = sqnorm(sub(p, closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6)))); dk = kl; df = ~cl; }
+			if (wr && cr < 0) {
+				const double *t = tri + 9 * (int64_t)~cr;
+				const double d2 = sqnorm(sub(p, closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6))));
+				if (d2 < d || (d2 == d && kr < dk)) { d = d2; dk = kr; df = ~cr; }
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const double od = __shfl_xor_sync(0xffffffffu, d, o);
+				const unsigned long long ok = __shfl_xor_sync(0xffffffffu, dk, o);
+				const int32_t of = __shfl_xor_sync(0xffffffffu, df, o);
+				if (od < d || (od == d && ok < dk)) { d = od; dk = ok; df = of; }
+			}
+			const bool pl = wl && cl >= 0, pr = wr && cr >= 0;
+			const unsigned mpl = __ballot_sync(0xffffffffu, pl), mpr = __ballot_sync(0xffffffffu, pr);
+			__syncthreads();                                 // every pop of this step has been read: the slots may be overwritten
+			if (lane == 0) { r_d[warp] = d; r_k[warp] = dk; r_f[warp] = df; s_cnt[warp][0] = __popc(mpl); s_cnt[warp][1] = __popc(mpr); }
+			__syncthreads();
+			top -= take;
+#pragma unroll
+			for (int w = 0; w < 4; ++w) {
+				const double od = r_d[w]; const unsigned long long ok = r_k[w]; const int32_t of = r_f[w];
+				if (of >= 0 && (od < best || (od == best && ok < bkey))) { best = od; bkey = ok; bfac = of; }
+			}
+			int base_l = top, total_l = 0, before_r = 0, total_r = 0;
+#pragma unroll
+			for (int w = 0; w < 4; ++w) {
+				if (w < warp) { base_l += s_cnt[w][0]; before_r += s_cnt[w][1]; }
+				total_l += s_cnt[w][0]; total_r += s_cnt[w][1];
+			}
+			if (pl) { const int q = base_l + __popc(mpl & lt); stk[q] = cl; stkk[q] = kl; }
+			if (pr) { const int q = top + total_l + before_r + __popc(mpr & lt); stk[q] = cr; stkk[q] = kr; }
+			top += total_l + total_r;
+			__syncthreads();
+		}
+		if (tid == 0) {
+			// igl reaches the first-ranked exact-minimum leaf if every box on its path is at most `best` away
+			bool ok = !s_deep && bfac >= 0;
+			if (ok) {
+				int32_t child = ~bfac, nd = prim_parent[bfac];
+				while (nd >= 0 && ok) {
+					const QNode *n = nodes + nd;
+					const double bd = n->left == child ? box_ext_sqdist(n->lmin, n->lmax, p) : box_ext_sqdist(n->rmin, n->rmax, p);
+					ok = bd <= best;
+					child = nd; nd = n->parent;
+				}
+			}
+			Hit h;
+			if (ok) {
+				const double *t = tri + 9 * (int64_t)bfac;
+				h.f = bfac; h.sqr_d = best; h.c = closest_on_triangle(p, ld3(t), ld3(t + 3), ld3(t + 6));
+			} else {
+				traverse_limited(nodes, root, tri, p, best + best * PK_EPS_WALK, best, 0x7fffffff, h);
+			}
+			if (I) I[i] = h.f;
+			if (C) { C[3 * i] = h.c.x; C[3 * i + 1] = h.c.y; C[3 * i + 2] = h.c.z; }
+			if (S) S[i] = h.sqr_d;
+			finalize_sign(sa, i, p, h.f, h.c, h.sqr_d, S);
+		}
+		__syncthreads();
 	}
 }
 
@@ -1736,7 +1851,11 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_tie_kernel<<<pgrid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, sa, m->node_pd.p, getenv("FPOHM_CP_COUNTERS") != nullptr);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, sa);
+		// the list length is only known on the device: both forms are launched, one of them returns at once
+		const int heavy_switch = ctx->sm_count * 6 * 4;    // = warps of the grid
+		cp_heavy_warp_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, sa, heavy_switch);
+		FPOHM_LAUNCH_CHECK(ctx);
+		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, sa, heavy_switch);
 		FPOHM_LAUNCH_CHECK(ctx);
 		static const bool counters = getenv("FPOHM_CP_COUNTERS") != nullptr;      // debug: work-list sizes on stderr (synchronises)
 		if (counters) {
@@ -1782,7 +1901,7 @@ static void launch_closest_point_ex(fpohm_ctx *ctx, fpohm_mesh *m, bool with_sig
 		FPOHM_LAUNCH_CHECK(ctx);
 		cp_tie_kernel<<<pgrid, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.todo.p, q.todo_ties.p, q.cnt.p, S, I, C, q.heavy.p, k2_walk, no_sign, nullptr);
 		FPOHM_LAUNCH_CHECK(ctx);
-		cp_heavy_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, no_sign);
+		cp_heavy_warp_kernel<<<ctx->sm_count * 6, blk, 0, sc>>>(m->qnodes.p, m->qroot, m->tri.p, m->prim_parent.p, P_dev, q.heavy.p, q.cnt.p + 1, S, I, C, no_sign, 0);
 	} else {
 		if (stats) closest_point_kernel<true><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
 		else closest_point_kernel<false><<<grid, blk, 0, s>>>(m->qnodes.p, m->qroot, m->tri.p, P_dev, np, S, I, C, N);
