@@ -159,6 +159,8 @@ int fpohm_voxel_grid_setup(const double origin[3], const double extent[3], doubl
 /* out: dims[0]*dims[1]*dims[2] bytes, x fastest (voxelization.cpp:26-28); 1 = inside */
 int fpohm_voxel_sign(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
                      const int32_t dims[3], uint8_t *out);
+/* device output on the caller's stream.  Returns once the hit stage has reported that every hit list fitted (the pass is repeated with
+ * more room otherwise); the fill may still be running: out_dev is complete in stream order, like the output of any kernel on `stream`. */
 int fpohm_voxel_sign_dev(fpohm_ctx *ctx, const fpohm_mesh *mesh, const double grid_origin[3], double spacing,
                          const int32_t dims[3], uint8_t *out_dev, void *stream);
 /* z-slab of the same grid (multi-GPU sharding): writes layers [z_begin, z_end) only, the first at out_dev.
