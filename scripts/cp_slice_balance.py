@@ -24,7 +24,7 @@ def time_slice(P):
     b.record(st); torch.cuda.synchronize()
     return a.elapsed_time(b) / 3
 
-for M in (1, 2, 4, 8):
+for M in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1, 2, 4, 8)):
     per_rank = np.zeros(N)
     for P in sets:
         n = len(P); B = -(-n // (N * M))
