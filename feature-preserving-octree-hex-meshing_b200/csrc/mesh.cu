@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
@@ -131,6 +132,9 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 	double ms_normals = 0, ms_shape = 0;
 	auto independent = [&]() {
 		const auto a = now();
+		// the shape enumeration is pure host work on its own thread, beside the normals (device kernels + host acos threads)
+		std::thread shape_thread([&]() { const auto b0 = now(); wide_shape_host(m->nF, kids, n_wide); ms_shape = ms(b0, now()); });
+		struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_shape{shape_thread};
 		static const bool host_normals = getenv("FPOHM_NORMALS_HOST") != nullptr;      // A/B: the host builder of round 1
 		if (host_normals) {
 			build_igl_normals(m->hV.data(), m->nV, m->hF.data(), m->nF, m->hFN, m->hVN, m->hEN, m->hE, m->hEMAP);
@@ -143,9 +147,8 @@ void mesh_ensure_tree(fpohm_ctx *ctx, fpohm_mesh *m, cudaStream_t s) {
 		} else {
 			build_normals_device(ctx, m, s);
 		}
-		const auto b2 = now();
-		wide_shape_host(m->nF, kids, n_wide);
-		ms_normals = ms(a, b2); ms_shape = ms(b2, now());
+		ms_normals = ms(a, now());
+		shape_thread.join();
 	};
 	if (on_host) {
 		build_igl_tree(m->hV.data(), m->nV, m->hF.data(), m->nF, m->htree);
