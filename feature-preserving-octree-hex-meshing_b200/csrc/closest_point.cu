@@ -294,15 +294,6 @@ __device__ __forceinline__ void lane_update(Packet &k, int32_t *__restrict__ tie
 		if (d == k.best) { if (k.nt < PK_TIES) ties[k.nt * STRIDE] = prim; ++k.nt; }
 	}
 }
-// exact evaluation of one leaf: warp-uniform triangle (K1) / per-lane triangle (K2)
-__device__ __forceinline__ void packet_leaf(const double *__restrict__ tri, int32_t prim, bool want, Packet &k, int32_t *__restrict__ ties) {
-	const double *t = tri + 9 * (int64_t)prim;
-	const V3 a = ld3(t), b = ld3(t + 3), c = ld3(t + 6);
-	if (want) {
-		const V3 q = closest_on_triangle(k.p, a, b, c);
-		lane_update<false, 32>(k, ties, prim, q, sqnorm(sub(k.p, q)));      // K1 recomputes the closest point of the winner at the end
-	}
-}
 __device__ __forceinline__ void lane_leaf(const double *__restrict__ tri, int32_t prim, Packet &k, int32_t *__restrict__ ties) {
 	const double *t = tri + 9 * (int64_t)prim;
 	const V3 q = closest_on_triangle(k.p, ld3(t), ld3(t + 3), ld3(t + 6));
@@ -315,14 +306,14 @@ __device__ __forceinline__ bool igl_visits_first(const QNode *__restrict__ nodes
                                                  const V3 &p, int32_t fa, int32_t fb, const int2 *__restrict__ pd = nullptr)
 {
 	int32_t na = prim_parent[fa], nb = prim_parent[fb];
-	int32_t ca = ~fa, cb = ~fb;                      // child reference through which each side enters the ancestor
+	int32_t ca = ~fa;                                // child reference through which a's side enters the ancestor (b's is the other one)
 	if (pd) {
 		// the climb reads 8 bytes per node from a table that stays in L2 (16 MB at 2 M facets) instead of a 128-byte node line
 		// from DRAM (ncu launch list, C4 step: the tie-break was 16 % of the step, 6.8 ms for 7.6 M queries)
 		int2 a = __ldg(pd + na), b = __ldg(pd + nb);
 		while (a.y > b.y) { ca = na; na = a.x; a = __ldg(pd + na); }
-		while (b.y > a.y) { cb = nb; nb = b.x; b = __ldg(pd + nb); }
-		while (na != nb) { ca = na; na = a.x; a = __ldg(pd + na); cb = nb; nb = b.x; b = __ldg(pd + nb); }
+		while (b.y > a.y) { nb = b.x; b = __ldg(pd + nb); }
+		while (na != nb) { ca = na; na = a.x; a = __ldg(pd + na); nb = b.x; b = __ldg(pd + nb); }
 		const QNode *n = nodes + na;
 		const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
 		const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
@@ -330,8 +321,8 @@ __device__ __forceinline__ bool igl_visits_first(const QNode *__restrict__ nodes
 	}
 	int da = nodes[na].depth, db = nodes[nb].depth;
 	while (da > db) { ca = na; na = nodes[na].parent; --da; }
-	while (db > da) { cb = nb; nb = nodes[nb].parent; --db; }
-	while (na != nb) { ca = na; na = nodes[na].parent; cb = nb; nb = nodes[nb].parent; }
+	while (db > da) { nb = nodes[nb].parent; --db; }
+	while (na != nb) { ca = na; na = nodes[na].parent; nb = nodes[nb].parent; }
 	const QNode *n = nodes + na;
 	const double dl = box_ext_sqdist(n->lmin, n->lmax, p), dr = box_ext_sqdist(n->rmin, n->rmax, p);
 	const bool left_first = box_contains(n->lmin, n->lmax, p) || dl < dr;
@@ -1093,7 +1084,6 @@ cp_pair_kernel(const WNode *__restrict__ wnodes, const float4 *__restrict__ trif
 							const bool has = lane < cnt;
 							const int32_t ent = s.q2[warp][has ? n2 - cnt + lane : 0];
 							n2 -= cnt;
-							bool o = false;
 							if (has && !((dead >> (int)((uint32_t)ent >> 27)) & 1u)) {
 								const int owner = (int)((uint32_t)ent >> 27);
 								const int32_t prim = ent & 0x07ffffff;

@@ -240,53 +240,7 @@ __global__ void child_cells_kernel(LevelTable t, int64_t n_internal, uint8_t *__
 	}
 }
 
-__device__ __forceinline__ int32_t cell_id_of(const LevelTable &t, int level, int x, int y, int z) {
-	// id of the EXISTING cell (level, x, y, z), or -1 when its parent is not internal
-	if (level == 0) return x + t.roots[0] * (y + t.roots[1] * z);
-	const int64_t r = internal_rank(t, level - 1, morton3(x >> 1, y >> 1, z >> 1));
-	if (r < 0) return -1;
-	return (int32_t)(t.n_roots + 8 * r + morton_to_corner((x & 1) | ((y & 1) << 1) | ((z & 1) << 2)));
-}
-
-__global__ void __launch_bounds__(256)
-cell_links_kernel(LevelTable t, const uint8_t *__restrict__ lvl, const uint64_t *__restrict__ code, int64_t n_cells,
-                  int32_t *__restrict__ first_child, int32_t *__restrict__ neigh, uint8_t *__restrict__ leaf_flag)
-{
-	for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n_cells; id += (int64_t)gridDim.x * blockDim.x) {
-		const int l = lvl[id];
-		const uint64_t c = code[id];
-		const int64_t r = internal_rank(t, l, c);
-		first_child[id] = r < 0 ? -1 : (int32_t)(t.n_roots + 8 * r);
-		leaf_flag[id] = r < 0;
-		const int x = (int)compact1by2(c), y = (int)compact1by2(c >> 1), z = (int)compact1by2(c >> 2);
-		const int bound[3] = {t.roots[0] << l, t.roots[1] << l, t.roots[2] << l};
-#pragma unroll
-		for (int ax = 0; ax < 3; ++ax) {
-#pragma unroll
-			for (int dir = 0; dir < 2; ++dir) {
-				int q[3] = {x, y, z};
-				q[ax] += dir ? 1 : -1;
-				int32_t res = -1;
-				const int own = ax == 0 ? x : (ax == 1 ? y : z);
-				if (l > 0 && ((own & 1) == (dir ? 0 : 1))) {
-					// the neighbour is a sibling (same parent): same block of 8 ids, no search
-					const int m = (q[0] & 1) | ((q[1] & 1) << 1) | ((q[2] & 1) << 2);
-					res = (int32_t)(id - ((id - t.n_roots) & 7) + morton_to_corner(m));
-				} else if (q[ax] >= 0 && q[ax] < bound[ax]) {
-					// same-size neighbour if it exists, else the (larger) leaf that contains it:
-					// updateSubcellLinks, octree.cpp:255-281
-					for (int ll = l; ll >= 0 && res < 0; --ll) {
-						const int sh = l - ll;
-						res = cell_id_of(t, ll, q[0] >> sh, q[1] >> sh, q[2] >> sh);
-					}
-				}
-				neigh[6 * id + 2 * ax + dir] = res;
-			}
-		}
-	}
-}
-
-// Top-down form of the same tables (replaces cell_links_kernel in the build: 12.2 of 73 ms at 59 M cells were its ~8
+// Top-down form of the link tables (replaced a per-cell search kernel in the build: 12.2 of 73 ms at 59 M cells were its ~8
 // binary searches per cell).  (a) per INTERNAL cell g: its own cell id (one search of the parent) gives firstChild;
 // (b) per level, coarse to fine: a child's neighbour is a sibling, or hangs off the parent's neighbour q in that
 // direction: the mirrored child of q if q is internal (then q has the parent's size), else q itself — the larger (or
