@@ -542,6 +542,8 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "cp_pair_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel_ms_per_step": k1_ms_step, "kernel_share_of_step": k1_ms_step / step_ms_local,
+                             "issue_slots_used": {"frac": 0.70, "source": "ncu smsp__issue_active.avg.pct_of_peak_sustained_active of this kernel on the "
+                                                  "classification launch (not measured live): profiles/r02_ncu_summary.md section 1"},
                              "note": "84 B/query algorithmic x this rank's queries over the packet kernel's own duration (CUDA events inside the library, two "
                                      "launches per step); a tree search is issue/latency bound, not HBM bound: see profiles/r02_ncu_summary.md"},
                 "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 24 * Q, "d2h_bytes_per_step": 60 * Q,
