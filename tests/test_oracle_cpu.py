@@ -145,6 +145,25 @@ def test_host_tree_of_a_large_tied_mesh_equals_compiled_igl(fp, ref):
     assert np.array_equal(prim, rprim) and np.array_equal(lr, rlr) and np.array_equal(box, rbox)
 
 
+@pytest.mark.parametrize("pattern", ["sorted", "reversed", "organ_pipe", "three_values", "sawtooth"])
+def test_host_tree_sort_patterns_equal_compiled_igl(fp, ref, pattern):
+    """The multi-threaded restatement of std::sort (sort_like_std) on inputs that stress introsort's partitioning: 140 000 disjoint
+    triangles whose barycentre x follows a pattern (already sorted, reversed, organ pipe, three distinct values, sawtooth), y and z
+    random with many ties.  The tree must equal igl::AABB::init compiled from the reference node for node."""
+    n = 140000
+    rng = np.random.default_rng(11)
+    i = np.arange(n, dtype=np.float64)
+    x = {"sorted": i, "reversed": n - i, "organ_pipe": np.minimum(i, n - i), "three_values": np.floor(i * 3 / n),
+         "sawtooth": np.mod(i, 1000.0)}[pattern]
+    c = np.stack([x * 1e-3, np.floor(rng.uniform(0, 50, n)) * 0.1, np.floor(rng.uniform(0, 7, n))], 1)
+    off = np.array([[0.0, 0.0, 0.0], [0.03, 0.0, 0.0], [0.0, 0.03, 0.0]]) - np.array([0.01, 0.01, 0.0])
+    V = (c[:, None, :] + off[None, :, :]).reshape(-1, 3)
+    F = np.arange(3 * n, dtype=np.int32).reshape(-1, 3)
+    box, prim, lr = fp.host_igl_tree(V, F)
+    rbox, rprim, rlr = ref.RefTree(V, F).flatten()
+    assert np.array_equal(prim, rprim) and np.array_equal(lr, rlr) and np.array_equal(box, rbox)
+
+
 def test_host_grid_setups(fp, port, G):
     p = fp.octree_grid_setup(G["sd_V"], 1 << 20)
     assert np.array_equal(p.grid_size, G["oct_gs"]) and np.array_equal(p.origin, G["oct_origin"])
